@@ -86,3 +86,31 @@ def test_prng_known_vectors():
     assert O._debug_hash4(1, 2, 3, 4) == 11_323_120_931_611_735_037
     assert O._debug_hash4(0, 0, 0, 0) == 0
     assert O._debug_hash4(0xDEADBEEF, 0xCAFE, 0xBABE, 1) == 5_244_362_157_944_750_963
+
+
+def test_pyref_haps_annotated():
+    """Oracle == the reference's own pure-Python reconstruct_haplotype_from_sparse
+    (python/genvarloader/_dataset/_genotypes.py:125-248) on 150 richer cases incl. annotations,
+    negative starts, contig overshoot, shifts, keep masks (fixtures: tests/golden/make_pyref_golden.py)."""
+    cases = _golden.load_golden("pyref_haps")
+    assert len(cases) == 150
+    for ci, (inputs, (g_out, g_av, g_ap)) in enumerate(cases):
+        n = int(inputs[0][-1])
+        out, av, ap = np.zeros(n, np.uint8), np.zeros(n, np.int32), np.zeros(n, np.int32)
+        O.reconstruct_haplotypes_from_sparse(out, *inputs, av, ap)
+        _golden.eq("pyref_haps.out", ci, out, g_out)
+        _golden.eq("pyref_haps.annot_v", ci, av, g_av)
+        _golden.eq("pyref_haps.annot_pos", ci, ap, g_ap)
+
+
+def test_pyref_tracks():
+    """Oracle == the reference's pure-Python shift_and_realign_track_sparse
+    (python/genvarloader/_dataset/_tracks.py:706-824), all five fills, bit-exact."""
+    cases = _golden.load_golden("pyref_tracks")
+    assert len(cases) == 150
+    for ci, (inputs, g_out) in enumerate(cases):
+        out = np.zeros(int(inputs[0][-1]), np.float32)
+        args = list(inputs)
+        args[13] = int(args[13])
+        O.shift_and_realign_tracks_sparse(out, *args)
+        _golden.eq("pyref_tracks", ci, out, g_out)

@@ -1,0 +1,106 @@
+"""ctypes binding of the C ABI declared in include/gvl_b200.h.
+
+There is no CPU fallback: importing this module without the built CUDA library raises.
+Build it with ``python -m genvarloader_b200._build`` (or ``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "_lib" / "libgvl_b200.so"
+
+GVL_OK = 0
+MODE_U8, MODE_ONEHOT, MODE_ANNOTATED, MODE_ONEHOT_CF = 0, 1, 2, 3
+
+c_i64, c_i32, c_u8, c_u64, c_vp = C.c_int64, C.c_int32, C.c_uint8, C.c_uint64, C.c_void_p
+
+
+class GvlError(RuntimeError):
+    """A gvl_* entry returned a non-zero status (the reference would panic / raise,
+    src/ffi/mod.rs:45-55)."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"[gvl_b200 status {code}] {msg}")
+        self.code = code
+
+
+class SparseTables(C.Structure):
+    """gvl_sparse_tables (include/gvl_b200.h)."""
+
+    _fields_ = [
+        ("ref", c_vp), ("ref_offsets", c_vp), ("n_contigs", c_i64),
+        ("v_starts", c_vp), ("ilens", c_vp), ("alt_alleles", c_vp), ("alt_offsets", c_vp), ("n_variants", c_i64),
+        ("geno_v_idxs", c_vp), ("geno_starts", c_vp), ("geno_stops", c_vp), ("n_geno", c_i64),
+    ]
+
+
+class Intervals(C.Structure):
+    """gvl_intervals (include/gvl_b200.h)."""
+
+    _fields_ = [("itv_starts", c_vp), ("itv_ends", c_vp), ("itv_values", c_vp), ("itv_offsets", c_vp),
+                ("n_slots", c_i64)]
+
+
+def _load() -> C.CDLL:
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA extension is not built. Run `python -m genvarloader_b200._build` "
+            "(needs nvcc). genvarloader_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(str(LIB_PATH))
+    lib.gvl_last_error.restype = C.c_char_p
+    lib.gvl_launch_count.restype = c_i64
+    lib.gvl_launch_count.argtypes = [C.c_int]
+    return lib
+
+
+lib = _load()
+
+
+def check(code: int) -> None:
+    if code != GVL_OK:
+        raise GvlError(code, (lib.gvl_last_error() or b"").decode())
+
+
+def launch_count(reset: bool = False) -> int:
+    return int(lib.gvl_launch_count(1 if reset else 0))
+
+
+def ptr(x) -> C.c_void_p:
+    """Pointer of a torch tensor / numpy array / None."""
+    if x is None:
+        return c_vp(0)
+    if hasattr(x, "data_ptr"):
+        return c_vp(x.data_ptr())
+    return c_vp(x.ctypes.data)
+
+
+class Ctx:
+    """Owner of a gvl_ctx (device workspace, host-layer upload cache)."""
+
+    def __init__(self, device: int = 0):
+        self._h = c_vp(0)
+        check(lib.gvl_ctx_create(C.c_int(int(device)), C.byref(self._h)))
+        self.device = int(device)
+
+    @property
+    def handle(self) -> C.c_void_p:
+        if not self._h:
+            raise GvlError(4, "context was destroyed")
+        return self._h
+
+    def close(self) -> None:
+        if self._h:
+            lib.gvl_ctx_destroy(self._h)
+            self._h = c_vp(0)
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, stream: int = 0) -> None:
+        check(lib.gvl_ctx_check(self.handle, c_vp(stream)))

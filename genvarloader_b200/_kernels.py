@@ -1,0 +1,190 @@
+"""Host-buffer kernels with the names and argument order of the reference's PyO3 module
+``genvarloader.genvarloader`` (src/ffi/mod.rs) -- numpy arrays in, numpy arrays out, the work
+done by the CUDA library through the gvl_* host layer of include/gvl_b200.h.
+
+A maintainer swaps ``from ..genvarloader import reconstruct_haplotypes_fused`` for
+``from genvarloader_b200._kernels import reconstruct_haplotypes_fused``.
+`parallel` is accepted for signature compatibility and ignored (the GPU is always parallel).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import MODE_ANNOTATED, MODE_ONEHOT, MODE_ONEHOT_CF, MODE_U8, c_i64, c_u8, c_u64, c_vp, check, lib
+
+_MODES = {"u8": MODE_U8, "bytes": MODE_U8, "onehot": MODE_ONEHOT, "onehot_cf": MODE_ONEHOT_CF,
+          "annotated": MODE_ANNOTATED}
+
+_ctx: dict[int, _ffi.Ctx] = {}
+
+
+def default_ctx(device: int = 0) -> _ffi.Ctx:
+    if device not in _ctx:
+        _ctx[device] = _ffi.Ctx(device)
+    return _ctx[device]
+
+
+def _c(a, dt):
+    return None if a is None else np.ascontiguousarray(a, dt)
+
+
+def _p(a):
+    return c_vp(0) if a is None else c_vp(a.ctypes.data)
+
+
+def _starts_stops(geno_offsets) -> np.ndarray:
+    """(2, n) starts/stops; 1-D offsets normalised like _dataset/_genotypes.py:13-22."""
+    go = np.asarray(geno_offsets)
+    if go.ndim == 1:
+        go = np.stack([go[:-1], go[1:]])
+    return np.ascontiguousarray(go, np.int64)
+
+
+def pin_static(*arrays, ctx: _ffi.Ctx | None = None) -> None:
+    """Upload sample-scale arrays once; later calls that pass the SAME array objects reuse the
+    device copies (the zero-copy memmap crossing of _dataset/_utils.py:13-35, GPU edition)."""
+    ctx = ctx or default_ctx()
+    for a in arrays:
+        if a is None:
+            continue
+        assert a.flags.c_contiguous
+        check(lib.gvl_pin_static(ctx.handle, _p(a), c_i64(a.nbytes)))
+
+
+def unpin_static(*arrays, ctx: _ffi.Ctx | None = None) -> None:
+    ctx = ctx or default_ctx()
+    for a in arrays:
+        if a is not None:
+            check(lib.gvl_unpin_static(ctx.handle, _p(a)))
+
+
+class PinnedBuffer:
+    """Page-locked host array (gvl_host_alloc) -- outputs copied into it travel at full PCIe rate."""
+
+    def __init__(self, nbytes: int):
+        self._p = c_vp(0)
+        check(lib.gvl_host_alloc(c_i64(int(nbytes)), C.byref(self._p)))
+        self.nbytes = int(nbytes)
+        self.array = np.ctypeslib.as_array(C.cast(self._p, C.POINTER(C.c_uint8)), shape=(max(self.nbytes, 1),))[: self.nbytes]
+
+    def close(self):
+        if self._p:
+            lib.gvl_host_free(self._p)
+            self._p = c_vp(0)
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _begin(ctx, regions, shifts, geno_offset_idx, geno_offsets, geno_v_idxs, v_starts, ilens, alt_alleles,
+           alt_offsets, ref_, ref_offsets, output_length, keep, keep_offsets, to_rc):
+    rg, sh = _c(regions, np.int32), _c(shifts, np.int32)
+    goi = _c(geno_offset_idx, np.int64)
+    batch, ploidy = goi.shape
+    go = geno_offsets if (isinstance(geno_offsets, np.ndarray) and geno_offsets.ndim == 2 and
+                          geno_offsets.dtype == np.int64 and geno_offsets.flags.c_contiguous) else _starts_stops(geno_offsets)
+    gv, vs, il = _c(geno_v_idxs, np.int32), _c(v_starts, np.int32), _c(ilens, np.int32)
+    aa, ao = _c(alt_alleles, np.uint8), _c(alt_offsets, np.int64)
+    rf, ro = _c(ref_, np.uint8), _c(ref_offsets, np.int64)
+    kp, ko, rc = _c(keep, np.bool_), _c(keep_offsets, np.int64), _c(to_rc, np.bool_)
+    out_offsets = np.empty(batch * ploidy + 1, np.int64)
+    total = c_i64(0)
+    keepalive = (rg, sh, goi, go, gv, vs, il, aa, ao, rf, ro, kp, ko, rc)
+    check(lib.gvl_reconstruct_haplotypes_fused_begin(
+        ctx.handle, _p(rg), _p(sh), _p(goi), c_i64(batch), c_i64(ploidy), _p(go), c_i64(go.shape[1]), _p(gv),
+        c_i64(gv.size), _p(vs), _p(il), c_i64(vs.size), _p(aa), _p(ao), _p(rf), _p(ro), c_i64(ro.size - 1),
+        c_i64(int(output_length)), _p(kp), _p(ko), _p(rc), _p(out_offsets), C.byref(total)))
+    del keepalive
+    return out_offsets, int(total.value)
+
+
+def reconstruct_haplotypes_fused(regions, shifts, geno_offset_idx, geno_offsets, geno_v_idxs, v_starts, ilens,
+                                 alt_alleles, alt_offsets, ref_, ref_offsets, pad_char, output_length, keep=None,
+                                 keep_offsets=None, to_rc=None, parallel=True, *, mode="u8", out=None, ctx=None):
+    """src/ffi/mod.rs:724-860.  Returns ``(out_data, out_offsets)``.
+
+    ``mode="u8"`` is the reference's return value; ``"onehot"`` / ``"onehot_cf"`` return the fused
+    one-hot encoding instead ((total, 4) uint8, resp. (n_rows, 4, L) for a fixed length).
+    ``out`` may be a preallocated (e.g. pinned) uint8 buffer of the right size."""
+    ctx = ctx or default_ctx()
+    m = _MODES[mode]
+    if m == MODE_ANNOTATED:
+        raise ValueError("use reconstruct_annotated_haplotypes_fused")
+    out_offsets, total = _begin(ctx, regions, shifts, geno_offset_idx, geno_offsets, geno_v_idxs, v_starts, ilens,
+                                alt_alleles, alt_offsets, ref_, ref_offsets, output_length, keep, keep_offsets, to_rc)
+    nbytes = total * (4 if m in (MODE_ONEHOT, MODE_ONEHOT_CF) else 1)
+    if out is None:
+        out = np.empty(nbytes, np.uint8)
+    assert out.dtype == np.uint8 and out.size >= nbytes and out.flags.c_contiguous
+    check(lib.gvl_reconstruct_haplotypes_fused_finish(ctx.handle, C.c_int(m), c_u8(int(pad_char)), _p(out), c_vp(0), c_vp(0)))
+    data = out[:nbytes]
+    if m == MODE_ONEHOT:
+        data = data.reshape(total, 4)
+    elif m == MODE_ONEHOT_CF:
+        n_rows = out_offsets.size - 1
+        data = data.reshape(n_rows, 4, int(output_length)) if n_rows else data.reshape(0, 4, 0)
+    return data, out_offsets
+
+
+def reconstruct_annotated_haplotypes_fused(regions, shifts, geno_offset_idx, geno_offsets, geno_v_idxs, v_starts,
+                                           ilens, alt_alleles, alt_offsets, ref_, ref_offsets, pad_char,
+                                           output_length, keep=None, keep_offsets=None, to_rc=None, parallel=True,
+                                           *, ctx=None):
+    """src/ffi/mod.rs:2239-2397.  Returns ``(out_data, annot_v, annot_pos, out_offsets)``."""
+    ctx = ctx or default_ctx()
+    out_offsets, total = _begin(ctx, regions, shifts, geno_offset_idx, geno_offsets, geno_v_idxs, v_starts, ilens,
+                                alt_alleles, alt_offsets, ref_, ref_offsets, output_length, keep, keep_offsets, to_rc)
+    out = np.empty(total, np.uint8)
+    av, ap = np.empty(total, np.int32), np.empty(total, np.int32)
+    check(lib.gvl_reconstruct_haplotypes_fused_finish(ctx.handle, C.c_int(MODE_ANNOTATED), c_u8(int(pad_char)),
+                                                      _p(out), _p(av), _p(ap)))
+    return out, av, ap, out_offsets
+
+
+def reconstruct_haplotypes_from_sparse(out, out_offsets, regions, shifts, geno_offset_idx, geno_offsets, geno_v_idxs,
+                                       v_starts, ilens, alt_alleles, alt_offsets, ref_, ref_offsets, pad_char,
+                                       keep=None, keep_offsets=None, annot_v_idxs=None, annot_ref_pos=None,
+                                       parallel=True, *, ctx=None):
+    """src/ffi/mod.rs:634-655.  Caller-sized rows; writes ``out`` (and the annotation buffers) in place."""
+    ctx = ctx or default_ctx()
+    assert out.dtype == np.uint8 and out.flags.c_contiguous
+    oo = _c(out_offsets, np.int64)
+    rg, sh = _c(regions, np.int32), _c(shifts, np.int32)
+    goi = _c(geno_offset_idx, np.int64)
+    batch, ploidy = goi.shape
+    go = _starts_stops(geno_offsets)
+    gv, vs, il = _c(geno_v_idxs, np.int32), _c(v_starts, np.int32), _c(ilens, np.int32)
+    aa, ao = _c(alt_alleles, np.uint8), _c(alt_offsets, np.int64)
+    rf, ro = _c(ref_, np.uint8), _c(ref_offsets, np.int64)
+    kp, ko = _c(keep, np.bool_), _c(keep_offsets, np.int64)
+    for a in (annot_v_idxs, annot_ref_pos):
+        assert a is None or (a.dtype == np.int32 and a.flags.c_contiguous)
+    check(lib.gvl_reconstruct_haplotypes_from_sparse(
+        ctx.handle, _p(out), _p(oo), _p(rg), _p(sh), _p(goi), c_i64(batch), c_i64(ploidy), _p(go), c_i64(go.shape[1]),
+        _p(gv), c_i64(gv.size), _p(vs), _p(il), c_i64(vs.size), _p(aa), _p(ao), _p(rf), _p(ro), c_i64(ro.size - 1),
+        c_u8(int(pad_char)), _p(kp), _p(ko), _p(annot_v_idxs), _p(annot_ref_pos)))
+
+
+def get_diffs_sparse(geno_offset_idx, geno_v_idxs, geno_offsets, ilens, keep=None, keep_offsets=None, q_starts=None,
+                     q_ends=None, v_starts=None, parallel=True, *, ctx=None):
+    """src/ffi/mod.rs:145-157.  Returns int32 ``(n_queries, ploidy)``."""
+    ctx = ctx or default_ctx()
+    goi = _c(geno_offset_idx, np.int64)
+    n_q, ploidy = goi.shape
+    go = _starts_stops(geno_offsets)
+    gv, il = _c(geno_v_idxs, np.int32), _c(ilens, np.int32)
+    kp, ko = _c(keep, np.bool_), _c(keep_offsets, np.int64)
+    qs, qe, vs = _c(q_starts, np.int32), _c(q_ends, np.int32), _c(v_starts, np.int32)
+    if not (qs is not None and qe is not None and vs is not None):
+        qs = qe = vs = None  # src/genotypes/mod.rs:35: the clipped branch needs all three
+    diffs = np.zeros((n_q, ploidy), np.int32)
+    check(lib.gvl_get_diffs_sparse(ctx.handle, _p(goi), c_i64(n_q), c_i64(ploidy), _p(gv), c_i64(gv.size), _p(go),
+                                   c_i64(go.shape[1]), _p(il), c_i64(il.size), _p(kp), _p(ko), _p(qs), _p(qe), _p(vs),
+                                   _p(diffs)))
+    return diffs

@@ -1,0 +1,81 @@
+// gvl_common.cuh -- shared declarations of the B200 haplotype path (device structs, ctx).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/gvl_b200.h"
+#include "gvl_plan.cuh"
+
+namespace gvl {
+
+// Per-(query, hap) row header written by the plan kernels and read by the execute kernels.
+struct __align__(16) RowPlan {
+    int64_t out_off;     // first element of this row in the flat output
+    int64_t ref_base;    // ref_offsets[contig]                       (haps)   | slot base of intervals (tracks)
+    int64_t rec_off;     // first record of this row in the record arrays
+    int32_t length;      // output positions in this row
+    int32_t contig_len;  // contig length (haps) | source window length (tracks)
+    int32_t lead_pad;    // leading pad positions, clamped to length (haps)
+    int32_t ref0;        // reference/track position feeding the first span
+    int32_t n_rec;       // records of this row
+    int32_t rc;          // reverse(-complement) this row
+    int32_t diff;        // get_diffs_sparse value of the row
+    int32_t q_start;     // regions[q,1]
+};
+
+// Record arrays (SoA).  Haplotypes use a, n, src, resume, vidx, vpos; tracks reuse
+// a, n, resume, vpos (= v_rel_pos), vidx (= v_len handed to the fill) and src (= ilen).
+struct RecArrays {
+    int32_t *a;
+    int32_t *n;
+    int64_t *src;
+    int32_t *resume;
+    int32_t *vidx;
+    int32_t *vpos;
+};
+
+// Device status words (ctx->dev_words).
+enum { W_CURSOR = 0, W_STATUS = 1, W_TOTAL = 2, W_TILES = 3, W_COUNT = 8 };
+
+constexpr int TILE = 4096;       // output positions per execute CTA
+constexpr int EXEC_THREADS = 256;
+constexpr int REC_CAP = 256;     // records staged in shared memory per pass
+constexpr int64_t ALT_PAD = INT64_MIN;  // RecArrays.src sentinel: "ALT piece" is padding (leading pad)
+
+}  // namespace gvl
+
+struct gvl_static_entry {
+    void *dev;
+    int64_t bytes;
+};
+
+struct gvl_ctx {
+    int device;
+    cudaStream_t own_stream;  // used by the host layer
+    // workspace
+    gvl::RowPlan *rows;
+    int64_t rows_cap;
+    gvl::RecArrays rec;
+    int64_t rec_cap;
+    int64_t *dev_words;   // W_COUNT words
+    int64_t *host_words;  // pinned mirror
+    int64_t *tile_off;    // i64[rows_cap+1] (ragged plans)
+    int32_t *row_len;     // i32[rows_cap]
+    // current haplotype plan
+    bool plan_valid;
+    int64_t n_work;
+    int64_t fixed_len;  // >=0 fixed, -1 ragged
+    int64_t total;      // -1 = unknown (ragged before sync)
+    int64_t *plan_out_offsets;  // device pointer supplied at plan time
+    // host layer
+    std::map<const void *, gvl_static_entry> statics;
+    std::vector<std::pair<void *, int64_t>> scratch;  // per-call device scratch (name-less pool)
+    void *pinned;
+    int64_t pinned_bytes;
+    gvl_sparse_tables host_tab;  // device pointers resolved by the last host-layer plan
+    int64_t *host_out_offsets_dev;
+};

@@ -1,0 +1,765 @@
+// gvl_hap.cu -- haplotype reconstruction on sm_100a: plan + execute kernels and their
+// device-pointer C entries (include/gvl_b200.h: gvl_dev_hap_plan / _total / _exec,
+// gvl_dev_get_diffs_sparse).
+//
+// Reference path replaced: src/ffi/mod.rs:724-860 (reconstruct_haplotypes_fused) and
+// :2239-2397 (annotated) = get_diffs_sparse -> prefix sum -> alloc ->
+// reconstruct_haplotypes_from_sparse -> rc_flat_rows_inplace, plus the one-hot transform the
+// reference leaves to seqpro (docs/source/index.md:108-119).
+//
+// Data flow (all in HBM, nothing on the host):
+//   plan    one warp per (query, hap) row walks the row's sparse variant list in chunks of 32
+//           (coalesced index loads, gathered table loads) and drives the reference's state
+//           machine (gvl_plan.cuh) in lock-step; emits <= n_variants records
+//           (alt_out_start, alt_len, alt_src, ref_resume, variant_idx, variant_pos) + a row header.
+//   scan    (ragged plans only) single-CTA exclusive scan of row lengths -> out_offsets, tile map.
+//   execute one CTA per 4096-position output tile; records of the tile are staged in shared
+//           memory; every thread produces 4 consecutive output positions per step: 4 reference
+//           bytes with two aligned 32-bit loads + funnel shift, ALT/pad bytes patched in,
+//           reverse-complement and the encoding fused, one 16-byte store (one-hot) per step.
+//           Every output byte is written exactly once; no intermediate haplotype in HBM.
+#include "gvl_internal.cuh"
+
+namespace gvl {
+
+// =====================================================================================
+// plan
+// =====================================================================================
+struct HapPlanParams {
+    gvl_sparse_tables tab;
+    const int32_t *regions;
+    const int32_t *shifts;
+    const int64_t *goi;
+    const uint8_t *keep;
+    const int64_t *keep_off;
+    const uint8_t *to_rc;
+    int64_t n_work, ploidy, output_length, rec_cap;
+    RowPlan *rows;
+    RecArrays rec;
+    int64_t *words;
+    int64_t *out_offsets;
+    int32_t *diffs;
+    int32_t *row_len;
+};
+
+constexpr int PLAN_WARPS = 4;
+
+__global__ void __launch_bounds__(PLAN_WARPS * 32) hap_plan_kernel(HapPlanParams P) {
+    const int lane = lane_id();
+    const int64_t k = (int64_t)blockIdx.x * PLAN_WARPS + (threadIdx.x >> 5);
+    if (k >= P.n_work) return;
+    const int64_t query = k / P.ploidy;
+    const int64_t o_idx = P.goi[k];
+    const int64_t o_s = P.tab.geno_starts[o_idx];
+    const int64_t nvar = imax64(P.tab.geno_stops[o_idx] - o_s, 0);
+    const int64_t c_idx = P.regions[query * 3 + 0];
+    const int64_t c_s = P.tab.ref_offsets[c_idx];
+    const int64_t contig_len = P.tab.ref_offsets[c_idx + 1] - c_s;
+    const int64_t q_start = P.regions[query * 3 + 1];
+    const int64_t q_end = P.regions[query * 3 + 2];
+    const int64_t shift = P.shifts[k];
+    const int64_t keep_base = (P.keep && P.keep_off) ? P.keep_off[k] : 0;
+    const bool has_keep = (P.keep && P.keep_off);
+    const int32_t *__restrict__ gv = P.tab.geno_v_idxs + o_s;
+
+    // ---- get_diffs_sparse (src/genotypes/mod.rs:48-86), needed first for ragged sizing ----
+    DiffState ds;
+    diff_init(ds, q_start, q_end);
+    bool diff_live = nvar > 0;  // :46-47
+    const bool ragged = P.output_length < 0;      // row lengths vary: offsets come from the scan kernel
+    const bool sized = P.output_length == -1;     // ... and are sized here from the diffs
+    if (sized) {
+        for (int64_t base = 0; base < nvar && diff_live; base += 32) {
+            int64_t i = base + lane;
+            int32_t pos = 0, il = 0;
+            bool kp = false;
+            if (i < nvar) {
+                int32_t vi = gv[i];
+                pos = P.tab.v_starts[vi];
+                il = P.tab.ilens[vi];
+                kp = has_keep ? (P.keep[keep_base + i] != 0) : true;
+            }
+            unsigned mask = __ballot_sync(0xffffffffu, kp);
+            while (mask) {
+                int t = __ffs(mask) - 1;
+                mask &= mask - 1;
+                int32_t p = __shfl_sync(0xffffffffu, pos, t), l = __shfl_sync(0xffffffffu, il, t);
+                if (!diff_step(ds, p, l)) {
+                    diff_live = false;
+                    break;
+                }
+            }
+        }
+        diff_live = false;
+    }
+    int64_t length;
+    if (sized) {
+        length = imax64((q_end - q_start) + (int64_t)(int32_t)ds.acc, 0);  // src/ffi/mod.rs:801-807
+    } else if (ragged) {
+        length = imax64(P.out_offsets[k + 1] - P.out_offsets[k], 0);  // caller-supplied row bounds
+    } else {
+        length = P.output_length;
+    }
+
+    // ---- workspace for this row's records: nvar + 1 slots ----
+    int64_t rec_off = 0;
+    if (lane == 0) rec_off = (int64_t)atomicAdd((unsigned long long *)&P.words[W_CURSOR], (unsigned long long)(nvar + 1));
+    rec_off = __shfl_sync(0xffffffffu, rec_off, 0);
+    const bool overflow = rec_off + nvar + 1 > P.rec_cap;
+    if (overflow && lane == 0) atomicMax((unsigned long long *)&P.words[W_STATUS], (unsigned long long)(rec_off + nvar + 1));
+
+    // ---- reconstruct_haplotype_core state machine (src/reconstruct/mod.rs:39-256) ----
+    HapState hs;
+    hap_init(hs, q_start, shift, length);
+    int64_t n_emit = 0, ref0 = 0, prev_resume = 0;
+    bool done = false;
+    for (int64_t base = 0; base < nvar && (!done || diff_live); base += 32) {
+        int64_t i = base + lane;
+        int32_t pos = 0, il = 0, alen = 0, vi = 0;
+        int64_t aoff = 0;
+        bool kp = false;
+        if (i < nvar) {
+            vi = gv[i];
+            pos = P.tab.v_starts[vi];
+            il = P.tab.ilens[vi];
+            aoff = P.tab.alt_offsets[vi];
+            alen = (int32_t)(P.tab.alt_offsets[vi + 1] - aoff);
+            kp = has_keep ? (P.keep[keep_base + i] != 0) : true;
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, kp);
+        while (mask && (!done || diff_live)) {
+            int t = __ffs(mask) - 1;
+            mask &= mask - 1;
+            int32_t p = __shfl_sync(0xffffffffu, pos, t);
+            int32_t l = __shfl_sync(0xffffffffu, il, t);
+            int32_t al = __shfl_sync(0xffffffffu, alen, t);
+            if (diff_live && !diff_step(ds, p, l)) diff_live = false;
+            if (done) continue;
+            HapRec r;
+            int act = hap_step(hs, p, l, al, r);
+            if (act == STEP_BREAK) {
+                done = true;
+            } else if (act == STEP_EMIT) {
+                if (n_emit == 0) ref0 = r.span_src;
+                if (n_emit > 0 && r.span_src != prev_resume) {
+                    // unsorted input moved ref_idx between emissions: zero-length "jump" record.
+                    // span start (output coordinate) of this record = r.a - (v_pos - span_src)
+                    int64_t span_out = r.a - ((int64_t)p - r.span_src);
+                    if (lane == t && !overflow) {
+                        int64_t w = rec_off + n_emit;
+                        P.rec.a[w] = (int32_t)span_out;
+                        P.rec.n[w] = 0;
+                        P.rec.src[w] = 0;
+                        P.rec.resume[w] = (int32_t)r.span_src;
+                        P.rec.vidx[w] = -1;
+                        P.rec.vpos[w] = -1;
+                    }
+                    n_emit++;
+                }
+                if (lane == t && !overflow) {
+                    int64_t w = rec_off + n_emit;
+                    P.rec.a[w] = (int32_t)r.a;
+                    P.rec.n[w] = (int32_t)r.n;
+                    P.rec.src[w] = aoff + r.trim;
+                    P.rec.resume[w] = (int32_t)r.resume;
+                    P.rec.vidx[w] = vi;
+                    P.rec.vpos[w] = p;
+                }
+                n_emit++;
+                prev_resume = r.resume;
+                if (hs.out_idx >= hs.length) done = true;  // :195-197
+            }
+        }
+    }
+    hap_finish(hs, contig_len);
+    if (n_emit == 0) {
+        ref0 = hs.ref_idx;
+    } else if (hs.ref_idx != prev_resume) {  // unsorted input: trailing jump
+        if (lane == 0 && !overflow) {
+            int64_t w = rec_off + n_emit;
+            P.rec.a[w] = (int32_t)imin64(hs.out_idx, length);
+            P.rec.n[w] = 0;
+            P.rec.src[w] = 0;
+            P.rec.resume[w] = (int32_t)hs.ref_idx;
+            P.rec.vidx[w] = -1;
+            P.rec.vpos[w] = -1;
+        }
+        n_emit++;
+    }
+
+    if (lane == 0) {
+        RowPlan rp;
+        rp.out_off = ragged ? 0 : k * length;
+        rp.ref_base = c_s;
+        rp.rec_off = rec_off;
+        rp.length = (int32_t)length;
+        rp.contig_len = (int32_t)contig_len;
+        rp.lead_pad = (int32_t)imin64(hs.lead_pad, length);
+        rp.ref0 = (int32_t)ref0;
+        rp.n_rec = overflow ? 0 : (int32_t)n_emit;
+        rp.rc = (P.to_rc && P.to_rc[k]) ? 1 : 0;
+        rp.diff = nvar > 0 ? (int32_t)ds.acc : 0;
+        rp.q_start = (int32_t)q_start;
+        P.rows[k] = rp;
+        if (P.diffs) P.diffs[k] = rp.diff;
+        if (ragged) {
+            P.row_len[k] = (int32_t)length;
+        } else {
+            P.out_offsets[k] = k * length;
+            if (k == P.n_work - 1) P.out_offsets[P.n_work] = P.n_work * length;
+        }
+    }
+}
+
+// ragged plans: exclusive scan of row lengths -> out_offsets, RowPlan.out_off, tile map, totals.
+__global__ void __launch_bounds__(1024) row_scan_kernel(int64_t n_work, const int32_t *__restrict__ row_len,
+                                                        RowPlan *rows, int64_t *out_offsets, int64_t *tile_off,
+                                                        int64_t *words) {
+    __shared__ int64_t s_len[32], s_tile[32];
+    __shared__ int64_t carry_len, carry_tile;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        carry_len = 0;
+        carry_tile = 0;
+    }
+    __syncthreads();
+    for (int64_t base = 0; base < n_work; base += 1024) {
+        int64_t k = base + tid;
+        int64_t len = (k < n_work) ? (int64_t)row_len[k] : 0;
+        int64_t til = (len + TILE - 1) / TILE;
+        int64_t xl = len, xt = til;
+        for (int o = 1; o < 32; o <<= 1) {
+            int64_t yl = __shfl_up_sync(0xffffffffu, xl, o), yt = __shfl_up_sync(0xffffffffu, xt, o);
+            if (lane >= o) {
+                xl += yl;
+                xt += yt;
+            }
+        }
+        if (lane == 31) {
+            s_len[warp] = xl;
+            s_tile[warp] = xt;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            int64_t wl = s_len[lane], wt = s_tile[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                int64_t yl = __shfl_up_sync(0xffffffffu, wl, o), yt = __shfl_up_sync(0xffffffffu, wt, o);
+                if (lane >= o) {
+                    wl += yl;
+                    wt += yt;
+                }
+            }
+            s_len[lane] = wl;
+            s_tile[lane] = wt;
+        }
+        __syncthreads();
+        int64_t pre_l = carry_len + (warp ? s_len[warp - 1] : 0) + xl - len;
+        int64_t pre_t = carry_tile + (warp ? s_tile[warp - 1] : 0) + xt - til;
+        if (k < n_work) {
+            if (out_offsets) out_offsets[k] = pre_l;
+            rows[k].out_off = pre_l;
+            tile_off[k] = pre_t;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            carry_len += s_len[31];
+            carry_tile += s_tile[31];
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        if (out_offsets) out_offsets[n_work] = carry_len;
+        tile_off[n_work] = carry_tile;
+        words[W_TOTAL] = carry_len;
+        words[W_TILES] = carry_tile;
+    }
+}
+
+// =====================================================================================
+// execute
+// =====================================================================================
+struct HapExecParams {
+    const RowPlan *rows;
+    RecArrays rec;
+    const uint8_t *ref;
+    const uint8_t *alt;
+    int64_t n_work;
+    int64_t tiles_per_row;    // >0: fixed-length plan
+    const int64_t *tile_off;  // ragged plan: first tile of each row
+    uint8_t *out;
+    int32_t *annot_v;
+    int32_t *annot_pos;
+    uint32_t pad_char;
+};
+
+struct TileRecs {
+    int32_t a[REC_CAP + 1];       // ALT start (output/hap coordinate); a[m+1] sentinel
+    int32_t e[REC_CAP];           // ALT end = start of the following reference span
+    int32_t resume[REC_CAP];      // reference position at e[]
+    int64_t src[REC_CAP];         // ALT source (offset into alt_alleles), ALT_PAD for the leading pad
+    int32_t vidx[REC_CAP];
+    int32_t vpos[REC_CAP];
+};
+
+// complement 4 packed bases: A<->T (xor 0x15), C<->G (xor 0x04), everything else unchanged
+// (src/reverse.rs:45-53).
+__device__ __forceinline__ uint32_t comp4(uint32_t v) {
+    uint32_t at = __vcmpeq4(v, 0x41414141u) | __vcmpeq4(v, 0x54545454u);
+    uint32_t cg = __vcmpeq4(v, 0x43434343u) | __vcmpeq4(v, 0x47474747u);
+    return v ^ (at & 0x15151515u) ^ (cg & 0x04040404u);
+}
+
+// one-hot of a single base: byte c of the word is (b == "ACGT"[c]).
+__device__ __forceinline__ uint32_t onehot1(uint32_t b) {
+    return (b == 'A' ? 1u : 0u) | (b == 'C' ? 0x100u : 0u) | (b == 'G' ? 0x10000u : 0u) | (b == 'T' ? 0x1000000u : 0u);
+}
+
+// one-hot of 4 packed bases -> 4 words (word i = base i).
+__device__ __forceinline__ uint4 onehot4(uint32_t v) {
+    uint32_t mA = __vcmpeq4(v, 0x41414141u) & 0x01010101u;
+    uint32_t mC = __vcmpeq4(v, 0x43434343u) & 0x01010101u;
+    uint32_t mG = __vcmpeq4(v, 0x47474747u) & 0x01010101u;
+    uint32_t mT = __vcmpeq4(v, 0x54545454u) & 0x01010101u;
+    // 4x4 byte transpose: word i = [mA.b_i, mC.b_i, mG.b_i, mT.b_i]
+    uint32_t ac_lo = __byte_perm(mA, mC, 0x5140);  // A0 C0 A1 C1
+    uint32_t ac_hi = __byte_perm(mA, mC, 0x7362);  // A2 C2 A3 C3
+    uint32_t gt_lo = __byte_perm(mG, mT, 0x5140);
+    uint32_t gt_hi = __byte_perm(mG, mT, 0x7362);
+    uint4 r;
+    r.x = __byte_perm(ac_lo, gt_lo, 0x5410);
+    r.y = __byte_perm(ac_lo, gt_lo, 0x7632);
+    r.z = __byte_perm(ac_hi, gt_hi, 0x5410);
+    r.w = __byte_perm(ac_hi, gt_hi, 0x7632);
+    return r;
+}
+
+struct PosInfo {
+    uint32_t byte;
+    int32_t av, ap;
+};
+
+// Generic (slow-path) resolution of one haplotype position against the staged records.
+template <bool ANNOT>
+__device__ __forceinline__ PosInfo resolve_pos(const TileRecs &S, int m, int32_t p, const RowPlan &rp,
+                                               const HapExecParams &P) {
+    // entry i = last with a[i] <= p (entry 0 always qualifies)
+    int lo = 0, hi = m;  // answer in [0, m-1]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (S.a[mid] <= p) lo = mid; else hi = mid;
+    }
+    const int i = lo;
+    PosInfo r;
+    if (p < S.e[i]) {
+        int64_t src = S.src[i];
+        if (src == ALT_PAD) {
+            r.byte = P.pad_char;
+            r.av = -1;
+            r.ap = -1;  // leading pad (src/reconstruct/mod.rs:75-80)
+        } else {
+            r.byte = P.alt[src + (p - S.a[i])];
+            r.av = S.vidx[i];
+            r.ap = S.vpos[i];
+        }
+    } else {
+        int64_t rpos = (int64_t)S.resume[i] + (p - S.e[i]);
+        if (rpos < rp.contig_len) {
+            r.byte = P.ref[rp.ref_base + rpos];
+            r.av = -1;
+            r.ap = (int32_t)rpos;
+        } else {
+            r.byte = P.pad_char;
+            r.av = -1;
+            r.ap = INT32_MAX;  // trailing pad (:248-253)
+        }
+    }
+    return r;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(EXEC_THREADS) hap_exec_kernel(HapExecParams P) {
+    __shared__ TileRecs S;
+    __shared__ int64_t s_lo, s_hi;
+    constexpr bool ANNOT = (MODE == GVL_MODE_ANNOTATED);
+
+    // ---- tile -> (row, tile-in-row) ----
+    int64_t row, tile;
+    if (P.tiles_per_row > 0) {
+        row = blockIdx.x / P.tiles_per_row;
+        tile = blockIdx.x % P.tiles_per_row;
+        if (row >= P.n_work) return;
+    } else {
+        int64_t b = blockIdx.x;
+        if (b >= P.tile_off[P.n_work]) return;
+        int64_t lo = 0, hi = P.n_work;  // last row with tile_off[row] <= b
+        while (hi - lo > 1) {
+            int64_t mid = (lo + hi) >> 1;
+            if (P.tile_off[mid] <= b) lo = mid; else hi = mid;
+        }
+        row = lo;
+        tile = b - P.tile_off[row];
+    }
+    const RowPlan rp = P.rows[row];
+    const int32_t L = rp.length;
+    const int32_t t0 = (int32_t)(tile * TILE);
+    if (t0 >= L) return;
+    const int32_t t1 = min(t0 + TILE, L);
+    const bool rc = rp.rc != 0;
+    // haplotype-coordinate range covered by this output tile
+    const int32_t h0 = rc ? L - t1 : t0;
+    const int32_t h1 = rc ? L - t0 : t1;
+
+    const int32_t *__restrict__ ra = P.rec.a + rp.rec_off;
+    // r_lo = last record with a <= h0 (or -1); r_hi = first record with a >= h1
+    if (threadIdx.x < 32) {
+        int64_t r_lo = warp_upper_le(ra, 0, rp.n_rec, h0);
+        int64_t r_hi = warp_upper_le(ra, imax64(r_lo, 0), rp.n_rec, h1 - 1) + 1;
+        if (threadIdx.x == 0) {
+            s_lo = r_lo;
+            s_hi = r_hi;
+        }
+    }
+    __syncthreads();
+    const int64_t r_hi = s_hi;
+    int64_t r = s_lo;
+    int32_t cur = h0;
+
+    while (cur < h1) {
+        // ---- stage entry 0 (carry) + up to REC_CAP-1 following records ----
+        const int m_new = (int)imin64(REC_CAP - 1, r_hi - (r + 1));
+        const int m = m_new + 1;
+        const int32_t seg_end = (r + 1 + m_new < r_hi) ? ra[r + 1 + m_new] : h1;
+        __syncthreads();  // previous pass finished reading S
+        for (int i = threadIdx.x; i < m; i += EXEC_THREADS) {
+            int64_t idx = r + i;
+            if (idx < 0) {  // virtual record: leading pad, then reference from ref0
+                S.a[0] = 0;
+                S.e[0] = rp.lead_pad;
+                S.resume[0] = rp.ref0;
+                S.src[0] = ALT_PAD;
+                S.vidx[0] = -1;
+                S.vpos[0] = -1;
+            } else {
+                int64_t g = rp.rec_off + idx;
+                int32_t a = P.rec.a[g], n = P.rec.n[g];
+                S.a[i] = a;
+                S.e[i] = a + n;
+                S.resume[i] = P.rec.resume[g];
+                S.src[i] = P.rec.src[g];
+                if (ANNOT) {
+                    S.vidx[i] = P.rec.vidx[g];
+                    S.vpos[i] = P.rec.vpos[g];
+                }
+            }
+        }
+        if (threadIdx.x == 0) S.a[m] = INT32_MAX;
+        __syncthreads();
+
+        // ---- output range of this pass, chunked by 4 on the GLOBAL flat index ----
+        const int32_t jo_lo = rc ? L - seg_end : cur;
+        const int32_t jo_hi = rc ? L - cur : seg_end;
+        const int64_t g0 = (rp.out_off + jo_lo) & ~(int64_t)3;
+        const int32_t n_chunks = (int32_t)((rp.out_off + jo_hi - g0 + 3) >> 2);
+        for (int32_t c = threadIdx.x; c < n_chunks; c += EXEC_THREADS) {
+            const int64_t g = g0 + 4 * (int64_t)c;
+            const int32_t j = (int32_t)(g - rp.out_off);  // row-relative output position of the chunk
+            const bool full = (j >= jo_lo) && (j + 4 <= jo_hi);
+            uint32_t v = 0;  // 4 output bases, byte i = output position j+i
+            int32_t av[4], ap[4];
+            bool fast = false;
+            if (full) {
+                const int32_t p0 = rc ? (L - 4 - j) : j;  // lowest haplotype position of the chunk
+                int lo = 0, hi = m;
+                while (hi - lo > 1) {
+                    int mid = (lo + hi) >> 1;
+                    if (S.a[mid] <= p0) lo = mid; else hi = mid;
+                }
+                const int i = lo;
+                const int64_t rpos = (int64_t)S.resume[i] + (p0 - S.e[i]);
+                if (p0 >= S.e[i] && p0 + 3 < S.a[i + 1] && rpos + 3 < rp.contig_len) {
+                    fast = true;
+                    const int64_t abs_ = rp.ref_base + rpos;
+                    const uint32_t *w = reinterpret_cast<const uint32_t *>(P.ref + (abs_ & ~(int64_t)3));
+                    const unsigned sh = (unsigned)(abs_ & 3) * 8u;
+                    uint32_t w0 = __ldg(w);
+                    uint32_t w1 = sh ? __ldg(w + 1) : 0u;
+                    v = __funnelshift_r(w0, w1, sh);
+                    if (rc) v = comp4(__byte_perm(v, 0, 0x0123));
+                    if (ANNOT) {
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            av[q] = -1;
+                            ap[q] = (int32_t)rpos + (rc ? 3 - q : q);
+                        }
+                    }
+                }
+            }
+            if (fast) {
+                if (MODE == GVL_MODE_U8) {
+                    *reinterpret_cast<uint32_t *>(P.out + g) = v;
+                } else if (MODE == GVL_MODE_ONEHOT) {
+                    *reinterpret_cast<uint4 *>(P.out + 4 * g) = onehot4(v);
+                } else if (MODE == GVL_MODE_ONEHOT_CF) {
+                    uint32_t mA = __vcmpeq4(v, 0x41414141u) & 0x01010101u;
+                    uint32_t mC = __vcmpeq4(v, 0x43434343u) & 0x01010101u;
+                    uint32_t mG = __vcmpeq4(v, 0x47474747u) & 0x01010101u;
+                    uint32_t mT = __vcmpeq4(v, 0x54545454u) & 0x01010101u;
+                    uint8_t *o = P.out + 4 * rp.out_off + j;  // (4, L) block of this row
+                    *reinterpret_cast<uint32_t *>(o) = mA;
+                    *reinterpret_cast<uint32_t *>(o + L) = mC;
+                    *reinterpret_cast<uint32_t *>(o + 2 * (int64_t)L) = mG;
+                    *reinterpret_cast<uint32_t *>(o + 3 * (int64_t)L) = mT;
+                } else {
+                    *reinterpret_cast<uint32_t *>(P.out + g) = v;
+                    *reinterpret_cast<int4 *>(P.annot_v + g) = make_int4(av[0], av[1], av[2], av[3]);
+                    *reinterpret_cast<int4 *>(P.annot_pos + g) = make_int4(ap[0], ap[1], ap[2], ap[3]);
+                }
+            } else {
+                // slow path: positions of the chunk that belong to this pass, one at a time
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int32_t jj = j + q;
+                    if (jj < jo_lo || jj >= jo_hi) continue;
+                    const int32_t p = rc ? (L - 1 - jj) : jj;
+                    PosInfo pi = resolve_pos<ANNOT>(S, m, p, rp, P);
+                    uint32_t b = pi.byte;
+                    if (rc) b = comp4(b) & 0xffu;
+                    const int64_t gg = g + q;
+                    if (MODE == GVL_MODE_U8) {
+                        P.out[gg] = (uint8_t)b;
+                    } else if (MODE == GVL_MODE_ONEHOT) {
+                        *reinterpret_cast<uint32_t *>(P.out + 4 * gg) = onehot1(b);
+                    } else if (MODE == GVL_MODE_ONEHOT_CF) {
+                        uint8_t *o = P.out + 4 * rp.out_off + jj;
+                        o[0] = (b == 'A');
+                        o[L] = (b == 'C');
+                        o[2 * (int64_t)L] = (b == 'G');
+                        o[3 * (int64_t)L] = (b == 'T');
+                    } else {
+                        P.out[gg] = (uint8_t)b;
+                        P.annot_v[gg] = pi.av;
+                        P.annot_pos[gg] = pi.ap;
+                    }
+                }
+            }
+        }
+        cur = seg_end;
+        r += m_new;
+    }
+}
+
+// standalone get_diffs_sparse (all four branches of src/genotypes/mod.rs:46-104)
+struct DiffParams {
+    gvl_sparse_tables tab;
+    const int64_t *goi;
+    const uint8_t *keep;
+    const int64_t *keep_off;
+    const int32_t *q_starts;
+    const int32_t *q_ends;
+    int use_v_starts;
+    int64_t n_work, ploidy;
+    int32_t *diffs;
+};
+
+__global__ void __launch_bounds__(PLAN_WARPS * 32) diffs_kernel(DiffParams P) {
+    const int lane = lane_id();
+    const int64_t k = (int64_t)blockIdx.x * PLAN_WARPS + (threadIdx.x >> 5);
+    if (k >= P.n_work) return;
+    const int64_t query = k / P.ploidy;
+    const int64_t o_idx = P.goi[k];
+    const int64_t o_s = P.tab.geno_starts[o_idx];
+    const int64_t nvar = imax64(P.tab.geno_stops[o_idx] - o_s, 0);
+    const bool has_query = P.q_starts && P.q_ends && P.use_v_starts;
+    const bool has_keep = P.keep && P.keep_off;
+    const int64_t keep_base = has_keep ? P.keep_off[k] : 0;
+    const int32_t *__restrict__ gv = P.tab.geno_v_idxs + o_s;
+    int64_t acc = 0;
+    if (has_query) {
+        DiffState ds;
+        diff_init(ds, P.q_starts[query], P.q_ends[query]);
+        bool live = true;
+        for (int64_t base = 0; base < nvar && live; base += 32) {
+            int64_t i = base + lane;
+            int32_t pos = 0, il = 0;
+            bool kp = false;
+            if (i < nvar) {
+                int32_t vi = gv[i];
+                pos = P.tab.v_starts[vi];
+                il = P.tab.ilens[vi];
+                kp = has_keep ? (P.keep[keep_base + i] != 0) : true;
+            }
+            unsigned mask = __ballot_sync(0xffffffffu, kp);
+            while (mask) {
+                int t = __ffs(mask) - 1;
+                mask &= mask - 1;
+                int32_t p = __shfl_sync(0xffffffffu, pos, t), l = __shfl_sync(0xffffffffu, il, t);
+                if (!diff_step(ds, p, l)) {
+                    live = false;
+                    break;
+                }
+            }
+        }
+        acc = ds.acc;
+    } else {
+        int64_t part = 0;
+        for (int64_t i = lane; i < nvar; i += 32) {
+            bool kp = has_keep ? (P.keep[keep_base + i] != 0) : true;
+            if (kp) part += P.tab.ilens[gv[i]];
+        }
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        acc = part;
+    }
+    if (lane == 0) P.diffs[k] = (int32_t)acc;
+}
+
+}  // namespace gvl
+
+using namespace gvl;
+
+extern "C" {
+
+int gvl_dev_hap_plan(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_t *regions, const int32_t *shifts,
+                     const int64_t *geno_offset_idx, int64_t batch, int64_t ploidy, const uint8_t *keep,
+                     const int64_t *keep_offsets, const uint8_t *to_rc, int64_t output_length, int64_t max_records,
+                     int64_t *out_offsets, int32_t *diffs, gvl_stream stream) {
+    if (!ctx || !tab || !regions || !shifts || !geno_offset_idx || !out_offsets)
+        return fail(GVL_ERR_ARG, "gvl_dev_hap_plan: NULL argument");
+    if (batch < 0 || ploidy < 1) return fail(GVL_ERR_ARG, "gvl_dev_hap_plan: batch=%lld ploidy=%lld", (long long)batch, (long long)ploidy);
+    if (output_length > INT32_MAX) return fail(GVL_ERR_ARG, "gvl_dev_hap_plan: output_length too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    GVL_CUDA(cudaSetDevice(ctx->device));
+    const int64_t n_work = batch * ploidy;
+    ctx->plan_valid = false;
+    int rc;
+    if ((rc = ensure_rows(ctx, n_work))) return rc;
+    if ((rc = ensure_records(ctx, max_records + n_work))) return rc;
+    GVL_CUDA(cudaMemsetAsync(ctx->dev_words, 0, sizeof(int64_t) * 4, st));
+    ctx->n_work = n_work;
+    ctx->fixed_len = output_length >= 0 ? output_length : -1;
+    ctx->plan_out_offsets = out_offsets;
+    if (n_work == 0) {
+        GVL_CUDA(cudaMemsetAsync(out_offsets, 0, sizeof(int64_t), st));
+        ctx->total = 0;
+        ctx->plan_valid = true;
+        return GVL_OK;
+    }
+    HapPlanParams P;
+    P.tab = *tab;
+    P.regions = regions;
+    P.shifts = shifts;
+    P.goi = geno_offset_idx;
+    P.keep = keep;
+    P.keep_off = keep_offsets;
+    P.to_rc = to_rc;
+    P.n_work = n_work;
+    P.ploidy = ploidy;
+    P.output_length = output_length >= 0 ? output_length : (output_length == -2 ? -2 : -1);
+    P.rec_cap = ctx->rec_cap;
+    P.rows = ctx->rows;
+    P.rec = ctx->rec;
+    P.words = ctx->dev_words;
+    P.out_offsets = out_offsets;
+    P.diffs = diffs;
+    P.row_len = ctx->row_len;
+    const unsigned grid = (unsigned)((n_work + PLAN_WARPS - 1) / PLAN_WARPS);
+    hap_plan_kernel<<<grid, PLAN_WARPS * 32, 0, st>>>(P);
+    GVL_LAUNCH_CHECK();
+    if (output_length >= 0) {
+        ctx->total = n_work * output_length;
+    } else {
+        row_scan_kernel<<<1, 1024, 0, st>>>(n_work, ctx->row_len, ctx->rows, output_length == -2 ? nullptr : out_offsets,
+                                            ctx->tile_off, ctx->dev_words);
+        GVL_LAUNCH_CHECK();
+        ctx->total = -1;
+    }
+    ctx->plan_valid = true;
+    return GVL_OK;
+}
+
+int gvl_dev_hap_total(gvl_ctx *ctx, gvl_stream stream, int64_t *total) {
+    if (!ctx || !total) return fail(GVL_ERR_ARG, "gvl_dev_hap_total: NULL argument");
+    if (!ctx->plan_valid) return fail(GVL_ERR_STATE, "gvl_dev_hap_total: no plan");
+    if (ctx->total < 0) {
+        int rc = gvl_ctx_check(ctx, stream);  // syncs, mirrors the status words
+        if (rc) return rc;
+        ctx->total = ctx->host_words[W_TOTAL];
+    }
+    *total = ctx->total;
+    return GVL_OK;
+}
+
+int gvl_dev_hap_exec(gvl_ctx *ctx, const gvl_sparse_tables *tab, int mode, uint8_t pad_char, uint8_t *out,
+                     int32_t *annot_v, int32_t *annot_pos, gvl_stream stream) {
+    if (!ctx || !tab) return fail(GVL_ERR_ARG, "gvl_dev_hap_exec: NULL argument");
+    if (!ctx->plan_valid) return fail(GVL_ERR_STATE, "gvl_dev_hap_exec: no plan");
+    cudaStream_t st = (cudaStream_t)stream;
+    GVL_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->n_work == 0 || ctx->total == 0) return GVL_OK;
+    if (!out) return fail(GVL_ERR_ARG, "gvl_dev_hap_exec: out is NULL");
+    if (((uintptr_t)out & 15) || ((uintptr_t)annot_v & 15) || ((uintptr_t)annot_pos & 15))
+        return fail(GVL_ERR_ARG, "gvl_dev_hap_exec: output buffers must be 16-byte aligned");
+    if (mode == GVL_MODE_ANNOTATED && (!annot_v || !annot_pos))
+        return fail(GVL_ERR_ARG, "gvl_dev_hap_exec: annotated mode needs annot_v and annot_pos");
+    HapExecParams P;
+    P.rows = ctx->rows;
+    P.rec = ctx->rec;
+    P.ref = tab->ref;
+    P.alt = tab->alt_alleles;
+    P.n_work = ctx->n_work;
+    P.out = out;
+    P.annot_v = annot_v;
+    P.annot_pos = annot_pos;
+    P.pad_char = pad_char;
+    int64_t grid;
+    if (ctx->fixed_len >= 0) {
+        P.tiles_per_row = (ctx->fixed_len + TILE - 1) / TILE;
+        P.tile_off = nullptr;
+        grid = P.tiles_per_row * ctx->n_work;
+    } else {
+        if (ctx->total < 0) return fail(GVL_ERR_STATE, "gvl_dev_hap_exec: ragged plan needs gvl_dev_hap_total first");
+        if (mode == GVL_MODE_ONEHOT_CF) return fail(GVL_ERR_ARG, "gvl_dev_hap_exec: channels-first one-hot needs a fixed length");
+        P.tiles_per_row = 0;
+        P.tile_off = ctx->tile_off;
+        grid = ctx->host_words[W_TILES];
+    }
+    if (grid == 0) return GVL_OK;
+    if (grid > INT32_MAX) return fail(GVL_ERR_ARG, "gvl_dev_hap_exec: too many tiles");
+    if (mode == GVL_MODE_ONEHOT_CF && (ctx->fixed_len & 3))
+        return fail(GVL_ERR_ARG, "gvl_dev_hap_exec: channels-first one-hot needs output_length %% 4 == 0");
+    switch (mode) {
+        case GVL_MODE_U8: hap_exec_kernel<GVL_MODE_U8><<<(unsigned)grid, EXEC_THREADS, 0, st>>>(P); break;
+        case GVL_MODE_ONEHOT: hap_exec_kernel<GVL_MODE_ONEHOT><<<(unsigned)grid, EXEC_THREADS, 0, st>>>(P); break;
+        case GVL_MODE_ONEHOT_CF: hap_exec_kernel<GVL_MODE_ONEHOT_CF><<<(unsigned)grid, EXEC_THREADS, 0, st>>>(P); break;
+        case GVL_MODE_ANNOTATED: hap_exec_kernel<GVL_MODE_ANNOTATED><<<(unsigned)grid, EXEC_THREADS, 0, st>>>(P); break;
+        default: return fail(GVL_ERR_ARG, "gvl_dev_hap_exec: unknown mode %d", mode);
+    }
+    GVL_LAUNCH_CHECK();
+    return GVL_OK;
+}
+
+int gvl_dev_get_diffs_sparse(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int64_t *geno_offset_idx,
+                             int64_t n_queries, int64_t ploidy, const uint8_t *keep, const int64_t *keep_offsets,
+                             const int32_t *q_starts, const int32_t *q_ends, int use_v_starts, int32_t *diffs,
+                             gvl_stream stream) {
+    if (!ctx || !tab || !geno_offset_idx || !diffs) return fail(GVL_ERR_ARG, "gvl_dev_get_diffs_sparse: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    GVL_CUDA(cudaSetDevice(ctx->device));
+    const int64_t n_work = n_queries * ploidy;
+    if (n_work == 0) return GVL_OK;
+    DiffParams P;
+    P.tab = *tab;
+    P.goi = geno_offset_idx;
+    P.keep = keep;
+    P.keep_off = keep_offsets;
+    P.q_starts = q_starts;
+    P.q_ends = q_ends;
+    P.use_v_starts = use_v_starts;
+    P.n_work = n_work;
+    P.ploidy = ploidy;
+    P.diffs = diffs;
+    diffs_kernel<<<(unsigned)((n_work + PLAN_WARPS - 1) / PLAN_WARPS), PLAN_WARPS * 32, 0, st>>>(P);
+    GVL_LAUNCH_CHECK();
+    return GVL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,330 @@
+// gvl_host.cu -- HOST-buffer entries of the C ABI: same argument lists as the reference's
+// #[pyfunction]s (src/ffi/mod.rs), host pointers in, host pointers out.
+//
+// Static arrays (reference, variant table, genotype CSR, interval SoA) are uploaded once and
+// cached by host address; O(batch) arrays travel through one pinned staging buffer and one
+// H2D copy per call; outputs come back with one D2H copy per array.
+#include <cstring>
+
+#include "gvl_internal.cuh"
+
+namespace gvl {
+
+static inline int64_t round16(int64_t x) { return (x + 15) & ~(int64_t)15; }
+
+// scratch slot i: a growable device buffer private to the host layer
+static int scratch(gvl_ctx *ctx, size_t slot, int64_t bytes, void **dev);
+
+// upload a static array into its own allocation and register it by host address
+static int pin_static(gvl_ctx *ctx, const void *host, int64_t bytes, const void **dev) {
+    void *d = nullptr;
+    const int64_t cap = round16(bytes) + 16;  // slack: 32-bit loads may touch up to the next 16 B
+    GVL_CUDA(cudaMalloc(&d, (size_t)cap));
+    GVL_CUDA(cudaMemsetAsync((char *)d + (bytes / 16) * 16, 0, (size_t)(cap - (bytes / 16) * 16), ctx->own_stream));
+    if (bytes) GVL_CUDA(cudaMemcpyAsync(d, host, (size_t)bytes, cudaMemcpyHostToDevice, ctx->own_stream));
+    GVL_CUDA(cudaStreamSynchronize(ctx->own_stream));
+    ctx->statics[host] = gvl_static_entry{d, bytes};
+    if (dev) *dev = d;
+    return GVL_OK;
+}
+
+// device view of a sample-scale host array: the pinned copy when the caller registered it with
+// gvl_pin_static (same address and size), otherwise a per-call upload into scratch slot `slot`.
+static int static_dev(gvl_ctx *ctx, const void *host, int64_t bytes, size_t slot, const void **dev) {
+    if (!host) {
+        *dev = nullptr;
+        return GVL_OK;
+    }
+    auto it = ctx->statics.find(host);
+    if (it != ctx->statics.end() && it->second.bytes == bytes) {
+        *dev = it->second.dev;
+        return GVL_OK;
+    }
+    void *d;
+    int rc;
+    if ((rc = scratch(ctx, slot, bytes + 32, &d))) return rc;
+    GVL_CUDA(cudaMemsetAsync((char *)d + (bytes / 16) * 16, 0, 32, ctx->own_stream));
+    if (bytes) GVL_CUDA(cudaMemcpyAsync(d, host, (size_t)bytes, cudaMemcpyHostToDevice, ctx->own_stream));
+    *dev = d;
+    return GVL_OK;
+}
+
+static int scratch(gvl_ctx *ctx, size_t slot, int64_t bytes, void **dev) {
+    if (ctx->scratch.size() <= slot) ctx->scratch.resize(slot + 1, {nullptr, 0});
+    auto &s = ctx->scratch[slot];
+    if (s.second < bytes || !s.first) {
+        if (s.first) GVL_CUDA(cudaFree(s.first));
+        s.first = nullptr;
+        int64_t cap = round16(bytes + bytes / 4) + 256;
+        GVL_CUDA(cudaMalloc(&s.first, (size_t)cap));
+        s.second = cap;
+    }
+    *dev = s.first;
+    return GVL_OK;
+}
+
+static int pinned(gvl_ctx *ctx, int64_t bytes, void **p) {
+    if (ctx->pinned_bytes < bytes) {
+        if (ctx->pinned) GVL_CUDA(cudaFreeHost(ctx->pinned));
+        ctx->pinned = nullptr;
+        int64_t cap = round16(bytes * 2) + 4096;
+        GVL_CUDA(cudaHostAlloc(&ctx->pinned, (size_t)cap, cudaHostAllocDefault));
+        ctx->pinned_bytes = cap;
+    }
+    *p = ctx->pinned;
+    return GVL_OK;
+}
+
+// Pack several small host arrays into the pinned buffer, upload with ONE copy, hand back device pointers.
+struct Packer {
+    struct Item {
+        const void *host;
+        int64_t bytes;
+        int64_t off;
+    };
+    std::vector<Item> items;
+    int64_t total = 0;
+    size_t add(const void *host, int64_t bytes) {
+        Item it{host, host ? bytes : 0, total};
+        if (host) total += round16(bytes) + 16;
+        items.push_back(it);
+        return items.size() - 1;
+    }
+    char *dev_base = nullptr;
+    int upload(gvl_ctx *ctx, size_t slot) {
+        void *pin, *dev;
+        int rc;
+        if ((rc = pinned(ctx, total + 16, &pin))) return rc;
+        if ((rc = scratch(ctx, slot, total + 16, &dev))) return rc;
+        for (auto &it : items)
+            if (it.host && it.bytes) memcpy((char *)pin + it.off, it.host, (size_t)it.bytes);
+        if (total) GVL_CUDA(cudaMemcpyAsync(dev, pin, (size_t)total, cudaMemcpyHostToDevice, ctx->own_stream));
+        dev_base = (char *)dev;
+        return GVL_OK;
+    }
+    template <typename T>
+    const T *ptr(size_t i) const {
+        return items[i].host ? reinterpret_cast<const T *>(dev_base + items[i].off) : nullptr;
+    }
+};
+
+static int64_t sum_variants(const int64_t *geno_offsets, int64_t n_geno, const int64_t *goi, int64_t n_work) {
+    int64_t s = 0;
+    for (int64_t k = 0; k < n_work; k++) {
+        int64_t o = goi[k];
+        int64_t d = geno_offsets[n_geno + o] - geno_offsets[o];
+        if (d > 0) s += d;
+    }
+    return s;
+}
+
+}  // namespace gvl
+
+using namespace gvl;
+
+extern "C" {
+
+int gvl_host_alloc(int64_t bytes, void **out) {
+    if (!out) return fail(GVL_ERR_ARG, "gvl_host_alloc: out is NULL");
+    GVL_CUDA(cudaHostAlloc(out, (size_t)(bytes > 0 ? bytes : 1), cudaHostAllocDefault));
+    return GVL_OK;
+}
+
+int gvl_host_free(void *p) {
+    if (p) GVL_CUDA(cudaFreeHost(p));
+    return GVL_OK;
+}
+
+int gvl_pin_static(gvl_ctx *ctx, const void *host_ptr, int64_t bytes) {
+    if (!ctx || !host_ptr) return fail(GVL_ERR_ARG, "gvl_pin_static: NULL argument");
+    GVL_CUDA(cudaSetDevice(ctx->device));
+    auto it = ctx->statics.find(host_ptr);
+    if (it != ctx->statics.end()) {  // refresh
+        GVL_CUDA(cudaDeviceSynchronize());
+        cudaFree(it->second.dev);
+        ctx->statics.erase(it);
+    }
+    return pin_static(ctx, host_ptr, bytes, nullptr);
+}
+
+int gvl_unpin_static(gvl_ctx *ctx, const void *host_ptr) {
+    if (!ctx) return fail(GVL_ERR_ARG, "gvl_unpin_static: ctx is NULL");
+    auto it = ctx->statics.find(host_ptr);
+    if (it == ctx->statics.end()) return GVL_OK;
+    GVL_CUDA(cudaSetDevice(ctx->device));
+    GVL_CUDA(cudaDeviceSynchronize());
+    cudaFree(it->second.dev);
+    ctx->statics.erase(it);
+    return GVL_OK;
+}
+
+static int resolve_tables(gvl_ctx *ctx, const int64_t *geno_offsets, int64_t n_geno, const int32_t *geno_v_idxs,
+                          int64_t n_geno_v, const int32_t *v_starts, const int32_t *ilens, int64_t n_variants,
+                          const uint8_t *alt_alleles, const int64_t *alt_offsets, const uint8_t *ref_,
+                          const int64_t *ref_offsets, int64_t n_contigs, gvl_sparse_tables *t) {
+    int rc;
+    const void *d;
+    memset(t, 0, sizeof(*t));
+    if ((rc = static_dev(ctx, geno_offsets, sizeof(int64_t) * 2 * n_geno, 8, &d))) return rc;
+    t->geno_starts = (const int64_t *)d;
+    t->geno_stops = t->geno_starts ? t->geno_starts + n_geno : nullptr;
+    t->n_geno = n_geno;
+    if ((rc = static_dev(ctx, geno_v_idxs, sizeof(int32_t) * n_geno_v, 9, &d))) return rc;
+    t->geno_v_idxs = (const int32_t *)d;
+    if ((rc = static_dev(ctx, v_starts, sizeof(int32_t) * n_variants, 10, &d))) return rc;
+    t->v_starts = (const int32_t *)d;
+    if ((rc = static_dev(ctx, ilens, sizeof(int32_t) * n_variants, 11, &d))) return rc;
+    t->ilens = (const int32_t *)d;
+    t->n_variants = n_variants;
+    if (alt_offsets) {
+        if ((rc = static_dev(ctx, alt_offsets, sizeof(int64_t) * (n_variants + 1), 12, &d))) return rc;
+        t->alt_offsets = (const int64_t *)d;
+        if ((rc = static_dev(ctx, alt_alleles, alt_offsets[n_variants], 13, &d))) return rc;
+        t->alt_alleles = (const uint8_t *)d;
+    }
+    if (ref_offsets) {
+        if ((rc = static_dev(ctx, ref_offsets, sizeof(int64_t) * (n_contigs + 1), 14, &d))) return rc;
+        t->ref_offsets = (const int64_t *)d;
+        if ((rc = static_dev(ctx, ref_, ref_offsets[n_contigs], 15, &d))) return rc;
+        t->ref = (const uint8_t *)d;
+        t->n_contigs = n_contigs;
+    }
+    return GVL_OK;
+}
+
+static int hap_begin(
+    gvl_ctx *ctx, const int32_t *regions, const int32_t *shifts, const int64_t *geno_offset_idx, int64_t batch,
+    int64_t ploidy, const int64_t *geno_offsets, int64_t n_geno, const int32_t *geno_v_idxs, int64_t n_geno_v,
+    const int32_t *v_starts, const int32_t *ilens, int64_t n_variants, const uint8_t *alt_alleles,
+    const int64_t *alt_offsets, const uint8_t *ref_, const int64_t *ref_offsets, int64_t n_contigs,
+    int64_t output_length, const uint8_t *keep, const int64_t *keep_offsets, const uint8_t *to_rc,
+    int64_t *out_offsets, int64_t *total) {
+    if (!ctx || !regions || !shifts || !geno_offset_idx || !geno_offsets || !geno_v_idxs || !v_starts || !ilens ||
+        !alt_offsets || !ref_offsets || !out_offsets || !total)
+        return fail(GVL_ERR_ARG, "gvl_reconstruct_haplotypes_fused_begin: NULL argument");
+    GVL_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    const int64_t n_work = batch * ploidy;
+    if ((rc = resolve_tables(ctx, geno_offsets, n_geno, geno_v_idxs, n_geno_v, v_starts, ilens, n_variants, alt_alleles,
+                             alt_offsets, ref_, ref_offsets, n_contigs, &ctx->host_tab)))
+        return rc;
+    Packer pk;
+    size_t i_reg = pk.add(regions, sizeof(int32_t) * 3 * batch);
+    size_t i_sh = pk.add(shifts, sizeof(int32_t) * n_work);
+    size_t i_goi = pk.add(geno_offset_idx, sizeof(int64_t) * n_work);
+    size_t i_ko = pk.add(keep_offsets, sizeof(int64_t) * (n_work + 1));
+    size_t i_kp = pk.add(keep, keep_offsets ? keep_offsets[n_work] : 0);
+    size_t i_rc = pk.add(to_rc, n_work);
+    if ((rc = pk.upload(ctx, 0))) return rc;
+    void *oo_dev;
+    if ((rc = scratch(ctx, 1, sizeof(int64_t) * (n_work + 1), &oo_dev))) return rc;
+    ctx->host_out_offsets_dev = (int64_t *)oo_dev;
+    if (output_length == -2)  // caller-sized rows: offsets are an input
+        GVL_CUDA(cudaMemcpyAsync(oo_dev, out_offsets, sizeof(int64_t) * (n_work + 1), cudaMemcpyHostToDevice, ctx->own_stream));
+    const int64_t max_rec = sum_variants(geno_offsets, n_geno, geno_offset_idx, n_work);
+    if ((rc = gvl_dev_hap_plan(ctx, &ctx->host_tab, pk.ptr<int32_t>(i_reg), pk.ptr<int32_t>(i_sh), pk.ptr<int64_t>(i_goi),
+                               batch, ploidy, keep && keep_offsets ? pk.ptr<uint8_t>(i_kp) : nullptr,
+                               keep && keep_offsets ? pk.ptr<int64_t>(i_ko) : nullptr, pk.ptr<uint8_t>(i_rc),
+                               output_length, max_rec, ctx->host_out_offsets_dev, nullptr, ctx->own_stream)))
+        return rc;
+    if (output_length != -2)
+        GVL_CUDA(cudaMemcpyAsync(out_offsets, oo_dev, sizeof(int64_t) * (n_work + 1), cudaMemcpyDeviceToHost, ctx->own_stream));
+    if ((rc = gvl_ctx_check(ctx, ctx->own_stream))) return rc;  // syncs; reports workspace overflow
+    if (ctx->total < 0) ctx->total = ctx->host_words[W_TOTAL];
+    *total = ctx->total;
+    return GVL_OK;
+}
+
+int gvl_reconstruct_haplotypes_fused_begin(
+    gvl_ctx *ctx, const int32_t *regions, const int32_t *shifts, const int64_t *geno_offset_idx, int64_t batch,
+    int64_t ploidy, const int64_t *geno_offsets, int64_t n_geno, const int32_t *geno_v_idxs, int64_t n_geno_v,
+    const int32_t *v_starts, const int32_t *ilens, int64_t n_variants, const uint8_t *alt_alleles,
+    const int64_t *alt_offsets, const uint8_t *ref_, const int64_t *ref_offsets, int64_t n_contigs,
+    int64_t output_length, const uint8_t *keep, const int64_t *keep_offsets, const uint8_t *to_rc,
+    int64_t *out_offsets, int64_t *total) {
+    if (output_length < -1) return fail(GVL_ERR_ARG, "output_length must be >= -1");
+    return hap_begin(ctx, regions, shifts, geno_offset_idx, batch, ploidy, geno_offsets, n_geno, geno_v_idxs, n_geno_v,
+                     v_starts, ilens, n_variants, alt_alleles, alt_offsets, ref_, ref_offsets, n_contigs, output_length,
+                     keep, keep_offsets, to_rc, out_offsets, total);
+}
+
+int gvl_reconstruct_haplotypes_from_sparse(
+    gvl_ctx *ctx, uint8_t *out, const int64_t *out_offsets, const int32_t *regions, const int32_t *shifts,
+    const int64_t *geno_offset_idx, int64_t batch, int64_t ploidy, const int64_t *geno_offsets, int64_t n_geno,
+    const int32_t *geno_v_idxs, int64_t n_geno_v, const int32_t *v_starts, const int32_t *ilens, int64_t n_variants,
+    const uint8_t *alt_alleles, const int64_t *alt_offsets, const uint8_t *ref_, const int64_t *ref_offsets,
+    int64_t n_contigs, uint8_t pad_char, const uint8_t *keep, const int64_t *keep_offsets, int32_t *annot_v_idxs,
+    int32_t *annot_ref_pos) {
+    int64_t total = 0;
+    int rc = hap_begin(ctx, regions, shifts, geno_offset_idx, batch, ploidy, geno_offsets, n_geno, geno_v_idxs, n_geno_v,
+                       v_starts, ilens, n_variants, alt_alleles, alt_offsets, ref_, ref_offsets, n_contigs, -2, keep,
+                       keep_offsets, nullptr, const_cast<int64_t *>(out_offsets), &total);
+    if (rc) return rc;
+    const bool annot = annot_v_idxs && annot_ref_pos;
+    return gvl_reconstruct_haplotypes_fused_finish(ctx, annot ? GVL_MODE_ANNOTATED : GVL_MODE_U8, pad_char, out,
+                                                   annot_v_idxs, annot_ref_pos);
+}
+
+int gvl_reconstruct_haplotypes_fused_finish(gvl_ctx *ctx, int mode, uint8_t pad_char, uint8_t *out, int32_t *annot_v,
+                                            int32_t *annot_pos) {
+    if (!ctx) return fail(GVL_ERR_ARG, "gvl_reconstruct_haplotypes_fused_finish: ctx is NULL");
+    if (!ctx->plan_valid) return fail(GVL_ERR_STATE, "gvl_reconstruct_haplotypes_fused_finish: begin was not called");
+    GVL_CUDA(cudaSetDevice(ctx->device));
+    const int64_t total = ctx->total;
+    if (total == 0) return GVL_OK;
+    if (!out) return fail(GVL_ERR_ARG, "gvl_reconstruct_haplotypes_fused_finish: out is NULL");
+    const bool oh = (mode == GVL_MODE_ONEHOT || mode == GVL_MODE_ONEHOT_CF);
+    const int64_t out_bytes = oh ? total * 4 : total;
+    int rc;
+    void *d_out, *d_av = nullptr, *d_ap = nullptr;
+    if ((rc = scratch(ctx, 2, out_bytes, &d_out))) return rc;
+    if (mode == GVL_MODE_ANNOTATED) {
+        if (!annot_v || !annot_pos) return fail(GVL_ERR_ARG, "annotated mode needs annot_v and annot_pos");
+        if ((rc = scratch(ctx, 3, total * 4, &d_av))) return rc;
+        if ((rc = scratch(ctx, 4, total * 4, &d_ap))) return rc;
+    }
+    if ((rc = gvl_dev_hap_exec(ctx, &ctx->host_tab, mode, pad_char, (uint8_t *)d_out, (int32_t *)d_av, (int32_t *)d_ap,
+                               ctx->own_stream)))
+        return rc;
+    GVL_CUDA(cudaMemcpyAsync(out, d_out, (size_t)out_bytes, cudaMemcpyDeviceToHost, ctx->own_stream));
+    if (mode == GVL_MODE_ANNOTATED) {
+        GVL_CUDA(cudaMemcpyAsync(annot_v, d_av, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->own_stream));
+        GVL_CUDA(cudaMemcpyAsync(annot_pos, d_ap, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->own_stream));
+    }
+    GVL_CUDA(cudaStreamSynchronize(ctx->own_stream));
+    return GVL_OK;
+}
+
+int gvl_get_diffs_sparse(gvl_ctx *ctx, const int64_t *geno_offset_idx, int64_t n_queries, int64_t ploidy,
+                         const int32_t *geno_v_idxs, int64_t n_geno_v, const int64_t *geno_offsets, int64_t n_geno,
+                         const int32_t *ilens, int64_t n_variants, const uint8_t *keep, const int64_t *keep_offsets,
+                         const int32_t *q_starts, const int32_t *q_ends, const int32_t *v_starts, int32_t *diffs) {
+    if (!ctx || !geno_offset_idx || !geno_v_idxs || !geno_offsets || !ilens || !diffs)
+        return fail(GVL_ERR_ARG, "gvl_get_diffs_sparse: NULL argument");
+    GVL_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    const int64_t n_work = n_queries * ploidy;
+    gvl_sparse_tables t;
+    if ((rc = resolve_tables(ctx, geno_offsets, n_geno, geno_v_idxs, n_geno_v, v_starts ? v_starts : ilens, ilens,
+                             n_variants, nullptr, nullptr, nullptr, nullptr, 0, &t)))
+        return rc;
+    Packer pk;
+    size_t i_goi = pk.add(geno_offset_idx, sizeof(int64_t) * n_work);
+    size_t i_ko = pk.add(keep_offsets, sizeof(int64_t) * (n_work + 1));
+    size_t i_kp = pk.add(keep, keep_offsets ? keep_offsets[n_work] : 0);
+    size_t i_qs = pk.add(q_starts, sizeof(int32_t) * n_queries);
+    size_t i_qe = pk.add(q_ends, sizeof(int32_t) * n_queries);
+    if ((rc = pk.upload(ctx, 0))) return rc;
+    void *d_diffs;
+    if ((rc = scratch(ctx, 1, sizeof(int32_t) * (n_work + 1), &d_diffs))) return rc;
+    if ((rc = gvl_dev_get_diffs_sparse(ctx, &t, pk.ptr<int64_t>(i_goi), n_queries, ploidy,
+                                       keep && keep_offsets ? pk.ptr<uint8_t>(i_kp) : nullptr,
+                                       keep && keep_offsets ? pk.ptr<int64_t>(i_ko) : nullptr, pk.ptr<int32_t>(i_qs),
+                                       pk.ptr<int32_t>(i_qe), v_starts != nullptr, (int32_t *)d_diffs, ctx->own_stream)))
+        return rc;
+    if (n_work) GVL_CUDA(cudaMemcpyAsync(diffs, d_diffs, sizeof(int32_t) * n_work, cudaMemcpyDeviceToHost, ctx->own_stream));
+    GVL_CUDA(cudaStreamSynchronize(ctx->own_stream));
+    return GVL_OK;
+}
+
+}  // extern "C"

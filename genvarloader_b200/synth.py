@@ -1,0 +1,184 @@
+"""Synthetic in-memory datasets shaped like SURVEY.md section 8(d) -- used by bench.py and the tests.
+
+Everything is generated with ``numpy.random.default_rng(seed)``; layouts are the reference's
+on-disk / in-memory layouts:
+  * reference: uint8 ASCII contigs concatenated + int64 offsets (``Reference``,
+    python/genvarloader/_dataset/_reference.py:53-120), pad char ``N``
+  * variant table: ``v_starts`` i32 sorted per contig, ``ilens`` i32, atomised left-aligned ALT
+    alleles incl. the anchor base (SNP 1 B, INS 1+ilen B, DEL 1 B) as ragged u8 + i64 offsets
+  * sparse genotypes: CSR over (region, sample, ploid) slots holding variant indices sorted by
+    position (``genotypes/variant_idxs.npy`` + ``offsets.npy``, docs/source/format.md:8-49)
+  * regions: int32 (R, 4) = contig_idx, start, end, strand
+  * tracks: interval SoA (starts, ends, values) + CSR offsets per (region, sample) slot
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+ACGT = np.frombuffer(b"ACGT", np.uint8)
+
+
+@dataclass
+class SynthData:
+    reference: np.ndarray          # u8
+    ref_offsets: np.ndarray        # i64 (C+1)
+    v_starts: np.ndarray           # i32 (V)
+    ilens: np.ndarray              # i32 (V)
+    alt_alleles: np.ndarray        # u8
+    alt_offsets: np.ndarray        # i64 (V+1)
+    geno_v_idxs: np.ndarray        # i32 (G)
+    geno_offsets: np.ndarray       # i64 (2, R*S*P)
+    regions: np.ndarray            # i32 (R, 4)
+    n_samples: int
+    ploidy: int
+    max_jitter: int = 0
+    tracks: dict = field(default_factory=dict)  # name -> (itv_starts, itv_ends, itv_values, itv_offsets)
+
+    @property
+    def n_regions(self) -> int:
+        return int(self.regions.shape[0])
+
+
+def make_reference(rng, contig_lens, n_frac=0.01) -> tuple[np.ndarray, np.ndarray]:
+    """Uniform ACGT with ~n_frac of the bases inside short runs of N."""
+    ref_offsets = np.concatenate([[0], np.cumsum(contig_lens)]).astype(np.int64)
+    total = int(ref_offsets[-1])
+    ref = ACGT[rng.integers(0, 4, total, dtype=np.uint8)]
+    if n_frac > 0 and total > 1000:
+        run = 50
+        n_runs = max(1, int(total * n_frac / run))
+        for s in rng.integers(0, total - run, n_runs):
+            ref[s:s + run] = ord("N")
+    return ref, ref_offsets
+
+
+def make_variants(rng, contig_len: int, n_variants: int, snp_frac=0.8, max_indel=20):
+    """Sorted unique positions; SNP/INS/DEL mix (snp_frac, rest split evenly)."""
+    n_variants = min(n_variants, contig_len - 2)
+    pos = np.sort(rng.choice(contig_len - 1, n_variants, replace=False)).astype(np.int32)
+    u = rng.random(n_variants)
+    ins = u >= snp_frac + (1 - snp_frac) / 2
+    dele = (u >= snp_frac) & ~ins
+    mag = rng.integers(1, max_indel + 1, n_variants)
+    ilens = np.where(ins, mag, np.where(dele, -mag, 0)).astype(np.int32)
+    alt_lens = np.where(ilens > 0, ilens + 1, 1).astype(np.int64)
+    alt_offsets = np.concatenate([[0], np.cumsum(alt_lens)]).astype(np.int64)
+    alt = ACGT[rng.integers(0, 4, int(alt_offsets[-1]), dtype=np.uint8)]
+    return pos, ilens, alt, alt_offsets
+
+
+def make_genotypes(rng, regions, v_starts, n_samples, ploidy, max_jitter=0, af_a=0.5, af_b=5.0, dense_af=None):
+    """CSR of variant indices per (region, sample, ploid): every variant overlapping the jitter-
+    expanded region is carried by each haplotype with probability AF ~ Beta(af_a, af_b)
+    (or the constant ``dense_af``)."""
+    V = len(v_starts)
+    af = np.full(V, dense_af) if dense_af is not None else rng.beta(af_a, af_b, V)
+    R = regions.shape[0]
+    lo = np.searchsorted(v_starts, regions[:, 1] - max_jitter - 64, "left")
+    hi = np.searchsorted(v_starts, regions[:, 2] + max_jitter + 64, "left")
+    chunks, lengths = [], np.zeros(R * n_samples * ploidy, np.int64)
+    slot = 0
+    for r in range(R):
+        idx = np.arange(lo[r], hi[r], dtype=np.int32)
+        n = idx.size
+        if n == 0:
+            slot += n_samples * ploidy
+            continue
+        carry = rng.random((n_samples * ploidy, n)) < af[idx][None, :]
+        cnt = carry.sum(1)
+        lengths[slot:slot + n_samples * ploidy] = cnt
+        chunks.append(np.broadcast_to(idx, carry.shape)[carry])
+        slot += n_samples * ploidy
+    off = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64)
+    geno_v_idxs = np.concatenate(chunks).astype(np.int32) if chunks else np.empty(0, np.int32)
+    return geno_v_idxs, np.ascontiguousarray(np.stack([off[:-1], off[1:]]))
+
+
+def make_track(rng, regions, n_slots_per_region, max_jitter=0, mean_run=50, headroom=64):
+    """Interval SoA per slot: contiguous runs (mean length ``mean_run``) covering the expanded
+    region, ~25% of runs zero-valued and omitted (holes)."""
+    starts, ends, values, counts = [], [], [], []
+    for r in range(regions.shape[0]):
+        s0 = int(regions[r, 1]) - max_jitter
+        e0 = int(regions[r, 2]) + max_jitter + headroom
+        for _ in range(n_slots_per_region):
+            n_runs = max(1, (e0 - s0) // mean_run)
+            cuts = np.sort(rng.choice(np.arange(s0 + 1, e0), min(n_runs, e0 - s0 - 1), replace=False))
+            b = np.concatenate([[s0], cuts, [e0]])
+            keep = rng.random(b.size - 1) > 0.25
+            starts.append(b[:-1][keep])
+            ends.append(b[1:][keep])
+            values.append(rng.gamma(2.0, 2.0, int(keep.sum())).astype(np.float32))
+            counts.append(int(keep.sum()))
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    return (np.concatenate(starts).astype(np.int32), np.concatenate(ends).astype(np.int32),
+            np.concatenate(values).astype(np.float32), off)
+
+
+def make_dataset(seed: int, contig_len: int, n_samples: int, n_regions: int, region_len: int,
+                 variants_per_kb: float = 1.0, ploidy: int = 2, max_jitter: int = 0, snp_frac: float = 0.8,
+                 neg_strand_frac: float = 0.0, straddle_ends: bool = True, n_tracks: int = 0,
+                 sample_tracks: bool = True, dense_af: float | None = None, max_indel: int = 20) -> SynthData:
+    # `variants_per_kb` is the density PER HAPLOTYPE (what the kernels see); the table is denser by
+    # 1/E[AF] so that Bernoulli(AF ~ Beta(0.5, 5)) carriers hit that density.
+    rng = np.random.default_rng(seed)
+    ref, ref_offsets = make_reference(rng, [contig_len])
+    mean_af = dense_af if dense_af is not None else 0.5 / 5.5
+    n_var = int(contig_len * variants_per_kb / 1000 / mean_af)
+    v_starts, ilens, alt, alt_off = make_variants(rng, contig_len, max(n_var, 1), snp_frac, max_indel)
+    lo, hi = max_jitter, max(contig_len - region_len - max_jitter, max_jitter + 1)
+    starts = np.sort(rng.integers(lo, hi, n_regions)).astype(np.int64)
+    if straddle_ends and n_regions >= 4 and max_jitter == 0:
+        starts[0] = -min(37, region_len // 4)                  # leading pad
+        starts[-1] = contig_len - region_len + min(53, region_len // 4)  # trailing pad
+    strand = np.where(rng.random(n_regions) < neg_strand_frac, -1, 1)
+    regions = np.stack([np.zeros(n_regions, np.int64), starts, starts + region_len, strand], 1).astype(np.int32)
+    gv, go = make_genotypes(rng, regions, v_starts, n_samples, ploidy, max_jitter, dense_af=dense_af)
+    d = SynthData(ref, ref_offsets, v_starts, ilens, alt, alt_off, gv, go, regions, n_samples, ploidy, max_jitter)
+    for t in range(n_tracks):
+        d.tracks[f"track{t}"] = make_track(rng, regions, n_samples if sample_tracks else 1, max_jitter)
+    return d
+
+
+# ---- the configurations of BASELINE.json / SURVEY.md section 8(d) -----------------------------
+def cfg1(seed=1, n_regions=1000) -> SynthData:
+    """1 Mb contig, 8 diploid samples, ~1 variant/kb, 1,000 regions x 16,384 bp."""
+    return make_dataset(seed, 1_000_000, 8, n_regions, 16_384, 1.0)
+
+
+def cfg2(seed=2, contig_len=50_000_000, n_samples=32, n_regions=64) -> SynthData:
+    """chr22-scale contig, 131,072-bp windows.  ``n_samples`` defaults below 2,504 to bound host RAM
+    of the synthetic generator; the kernel cost per row does not depend on the cohort size."""
+    return make_dataset(seed, contig_len, n_samples, n_regions, 131_072, 1.0)
+
+
+def cfg3(seed=3, contig_len=20_000_000, n_samples=4, n_regions=16, variants_per_kb=1.0) -> SynthData:
+    """Borzoi-style 524,288-bp windows, >=10% indels, jitter, 50% negative strand, 2 tracks."""
+    return make_dataset(seed, contig_len, n_samples, n_regions, 524_288 + 2 * 128, variants_per_kb, max_jitter=128,
+                        snp_frac=0.8, neg_strand_frac=0.5, straddle_ends=False, n_tracks=2)
+
+
+def cfg4(seed=4, contig_len=5_000_000, n_samples=8, n_regions=256) -> SynthData:
+    """DNA-LM 6,144-bp haplotypes, thousands of rows per call, annotated."""
+    return make_dataset(seed, contig_len, n_samples, n_regions, 6_144, 1.0)
+
+
+def batch_args(d: SynthData, r_idx, s_idx, rng=None, jitter: int = 0):
+    """O(batch) arguments of the fused FFI entries for (region, sample) pairs, built the way the
+    reference's Python host does: regions + jitter (_dataset/_query.py:161-175), geno_offset_idx =
+    ravel of (region, sample, ploid) (_dataset/_haps.py:757-768), per-row to_rc (_haps.py:838-843)."""
+    r_idx = np.asarray(r_idx, np.int64)
+    s_idx = np.asarray(s_idx, np.int64)
+    regions = d.regions[r_idx].copy()
+    if jitter:
+        rng = rng or np.random.default_rng(0)
+        lengths = regions[:, 2] - regions[:, 1]
+        regions[:, 1] += rng.integers(-jitter, jitter + 1, size=len(regions), dtype=np.int32)
+        regions[:, 2] = regions[:, 1] + lengths
+    ploid = np.arange(d.ploidy, dtype=np.int64)
+    goi = (r_idx[:, None] * d.n_samples + s_idx[:, None]) * d.ploidy + ploid[None, :]
+    to_rc = np.repeat(d.regions[r_idx, 3] == -1, d.ploidy)
+    ds_idx = r_idx * d.n_samples + s_idx
+    return np.ascontiguousarray(regions[:, :3]), np.ascontiguousarray(goi), np.ascontiguousarray(to_rc), ds_idx

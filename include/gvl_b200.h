@@ -1,0 +1,239 @@
+/*
+ * gvl_b200.h -- C ABI of the B200-native haplotype-reconstruction path.
+ *
+ * Drop-in boundary for GenVarLoader's PyO3 extension module `genvarloader.genvarloader`
+ * (reference: src/lib.rs:17-89, src/ffi/mod.rs).  Plain pointers and sizes only; no torch,
+ * numpy or C++ types cross this boundary.  Every entry returns a status code
+ * (0 = GVL_OK) and leaves a message retrievable with gvl_last_error() on failure -- the
+ * reference panics/raises instead (src/ffi/mod.rs:45-55), the binding maps codes to
+ * exceptions.
+ *
+ * Two layers:
+ *   gvl_*      HOST-buffer entries with the argument lists of the reference's #[pyfunction]s
+ *              (what a cgo/ctypes/PyO3 stub binds 1:1).  Sample-scale static arrays
+ *              (reference, variant table, genotype CSR, interval SoA) are uploaded once and
+ *              cached by host address (gvl_pin_static); O(batch)
+ *              arrays are copied per call; results are copied back to host buffers.
+ *   gvl_dev_*  DEVICE-pointer entries used by the Python `Dataset` host: inputs/outputs are
+ *              device buffers owned by the caller (torch tensors), work is enqueued on the
+ *              caller's stream, no host synchronisation except where stated.
+ *
+ * All arrays are C-contiguous with the reference's exact dtypes: i32 regions/shifts/positions,
+ * i64 offsets/indices, u8 bytes/bools, f32 tracks, f64 params.
+ */
+#ifndef GVL_B200_H
+#define GVL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+#define GVL_OK 0
+#define GVL_ERR_CUDA 1      /* a CUDA runtime call failed                                   */
+#define GVL_ERR_ARG 2       /* contract violation detectable on the host                   */
+#define GVL_ERR_CAPACITY 3  /* device workspace overflow reported by a kernel              */
+#define GVL_ERR_STATE 4     /* call sequence error (e.g. exec without plan)                */
+
+/* Output encodings of the fused epilogue (a6 + a14 in SURVEY.md section 8). */
+#define GVL_MODE_U8 0        /* ASCII haplotype bytes, what reconstruct_haplotypes_fused returns       */
+#define GVL_MODE_ONEHOT 1    /* uint8 (L,4) one-hot, alphabet ACGT  (seqpro.DNA.ohe of the bytes)      */
+#define GVL_MODE_ANNOTATED 2 /* bytes + int32 variant index + int32 reference coordinate per base      */
+#define GVL_MODE_ONEHOT_CF 3 /* uint8 (4,L) channels-first one-hot ("alphabet length" layout)          */
+
+/* Insertion-fill strategies, python/genvarloader/_dataset/_insertion_fill.py:9-13. */
+#define GVL_FILL_REPEAT_5P 0
+#define GVL_FILL_REPEAT_5P_NORM 1
+#define GVL_FILL_CONSTANT 2
+#define GVL_FILL_FLANK_SAMPLE 3
+#define GVL_FILL_INTERPOLATE 4
+
+typedef struct gvl_ctx gvl_ctx;
+typedef void *gvl_stream; /* cudaStream_t / CUstream; NULL = legacy default stream */
+
+/* ---- context ---------------------------------------------------------------------- */
+int gvl_ctx_create(int device, gvl_ctx **out);
+void gvl_ctx_destroy(gvl_ctx *ctx);
+const char *gvl_last_error(void);
+/* Number of kernels this library has launched since the counter was last reset. */
+int64_t gvl_launch_count(int reset);
+/* Blocks until the stream is idle, then reports any device-side status flag
+ * (GVL_ERR_CAPACITY) raised by kernels of this context. */
+int gvl_ctx_check(gvl_ctx *ctx, gvl_stream stream);
+
+/* SVAR1-style static tables: reference + global variant table + sparse genotype CSR.
+ * Replaces the cached `_HapsFfiStatic` (python/genvarloader/_dataset/_haps.py:233-247,330-348)
+ * and the memmapped `genotypes.data/offsets` passed to every FFI call (_haps.py:844-866).
+ * Device pointers for gvl_dev_*; `ref` must be readable up to the next multiple of 16 bytes. */
+typedef struct {
+    const uint8_t *ref;          /* u8[ref_offsets[n_contigs]]                 */
+    const int64_t *ref_offsets;  /* i64[n_contigs+1]                           */
+    int64_t n_contigs;
+    const int32_t *v_starts;     /* i32[n_variants]                            */
+    const int32_t *ilens;        /* i32[n_variants]                            */
+    const uint8_t *alt_alleles;  /* u8[alt_offsets[n_variants]]                */
+    const int64_t *alt_offsets;  /* i64[n_variants+1]                          */
+    int64_t n_variants;
+    const int32_t *geno_v_idxs;  /* i32[G]                                     */
+    const int64_t *geno_starts;  /* i64[n_geno]  row 0 of the (2,n) offsets    */
+    const int64_t *geno_stops;   /* i64[n_geno]  row 1                         */
+    int64_t n_geno;
+} gvl_sparse_tables;
+
+/* Per-track interval SoA (python/genvarloader/_dataset/_tracks.py:327-339). */
+typedef struct {
+    const int32_t *itv_starts;
+    const int32_t *itv_ends;
+    const float *itv_values;
+    const int64_t *itv_offsets; /* i64[n_slots+1] */
+    int64_t n_slots;
+} gvl_intervals;
+
+/* ---- device layer: haplotypes ------------------------------------------------------ */
+/*
+ * Phase A ("plan").  One launch: per (query, hap) row runs get_diffs_sparse
+ * (src/genotypes/mod.rs:15-125) and the variant state machine of reconstruct_haplotype_core
+ * (src/reconstruct/mod.rs:39-256), emitting a compact segment table into the context's
+ * workspace, then sizes rows exactly as src/ffi/mod.rs:794-811.
+ *   regions (b,3) i32, shifts (b,p) i32, geno_offset_idx (b,p) i64, keep/keep_offsets/to_rc optional (NULL)
+ *   output_length  >=0 fixed; -1 ragged, sized from the diffs; -2 rows sized by the caller:
+ *                  out_offsets is then an INPUT (gap-free, non-decreasing), as in the un-fused
+ *                  reconstruct_haplotypes_from_sparse (src/ffi/mod.rs:634-655)
+ *   max_records    upper bound on the summed per-row variant counts (workspace capacity)
+ *   out_offsets    device i64[b*p+1], written (read when output_length == -2)
+ *   diffs          optional device i32[b*p], written (get_diffs_sparse result)
+ * No host sync.
+ */
+int gvl_dev_hap_plan(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_t *regions, const int32_t *shifts,
+                     const int64_t *geno_offset_idx, int64_t batch, int64_t ploidy, const uint8_t *keep,
+                     const int64_t *keep_offsets, const uint8_t *to_rc, int64_t output_length, int64_t max_records,
+                     int64_t *out_offsets, int32_t *diffs, gvl_stream stream);
+
+/* Total number of output positions of the current plan (= out_offsets[-1]).  Fixed-length plans
+ * answer from the host; ragged plans synchronise the stream once (the reference sizes its
+ * allocation at the same point, src/ffi/mod.rs:814). */
+int gvl_dev_hap_total(gvl_ctx *ctx, gvl_stream stream, int64_t *total);
+
+/*
+ * Phase B ("execute").  One launch over output tiles: copies reference spans, scatters ALT
+ * bytes, pads, reverse-complements masked rows (src/reverse.rs:45-69) and encodes, writing each
+ * output byte exactly once.  Buffers are device pointers, 16-byte aligned:
+ *   GVL_MODE_U8         out u8[total]
+ *   GVL_MODE_ONEHOT     out u8[total*4]           (row-major (L,4) per row)
+ *   GVL_MODE_ONEHOT_CF  out u8[total*4]           ((4,L) per row; fixed-length plans only)
+ *   GVL_MODE_ANNOTATED  out u8[total], annot_v i32[total], annot_pos i32[total]
+ */
+int gvl_dev_hap_exec(gvl_ctx *ctx, const gvl_sparse_tables *tab, int mode, uint8_t pad_char, uint8_t *out,
+                     int32_t *annot_v, int32_t *annot_pos, gvl_stream stream);
+
+/* Standalone get_diffs_sparse on device (src/ffi/mod.rs:145-157).  q_starts/q_ends/v_starts may
+ * be NULL together (unclipped sum).  diffs: device i32[n_queries*ploidy]. */
+int gvl_dev_get_diffs_sparse(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int64_t *geno_offset_idx,
+                             int64_t n_queries, int64_t ploidy, const uint8_t *keep, const int64_t *keep_offsets,
+                             const int32_t *q_starts, const int32_t *q_ends, int use_v_starts, int32_t *diffs,
+                             gvl_stream stream);
+
+/* ---- device layer: tracks ---------------------------------------------------------- */
+/*
+ * intervals_and_realign_track_fused (src/ffi/mod.rs:2553-2672) for ALL tracks of a batch in one
+ * plan launch + one execute launch: paints stored intervals (src/intervals.rs:19-126) and
+ * realigns them to haplotype coordinates (src/tracks/mod.rs:224-406) without the dense scratch.
+ *   n_tracks             tracks realigned in this call
+ *   itv[t]               HOST array of n_tracks descriptors holding DEVICE pointers
+ *   offset_idxs          device i64[n_tracks*b]: interval slot per (track, query) (dataset idx for
+ *                        SAMPLE tracks, region idx for ANNOT tracks, _reconstruct.py:233-236)
+ *   track_lengths        device i32[b]: source window length per query (_reconstruct.py:191)
+ *   out_offsets          device i64[b*p+1] per-track row offsets (same for every track)
+ *   strategy_ids/params  HOST arrays, one per track (python/genvarloader/_dataset/_insertion_fill.py:89)
+ *   out                  device f32[n_tracks * out_offsets[-1]], track-major (_reconstruct.py:238)
+ */
+int gvl_dev_realign_tracks(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_t *regions,
+                           const int32_t *shifts, const int64_t *geno_offset_idx, int64_t batch, int64_t ploidy,
+                           const uint8_t *keep, const int64_t *keep_offsets, const uint8_t *to_rc,
+                           int64_t n_tracks, const gvl_intervals *itv, const int64_t *offset_idxs,
+                           const int32_t *track_lengths, const int64_t *out_offsets, int64_t total_per_track,
+                           int64_t max_out_len, const int32_t *strategy_ids, const double *params,
+                           uint64_t base_seed, int64_t max_records, float *out, gvl_stream stream);
+
+/* intervals_to_tracks on device (src/ffi/mod.rs:190-201): out f32[out_offsets[n]] fully written. */
+int gvl_dev_intervals_to_tracks(gvl_ctx *ctx, const gvl_intervals *itv, const int64_t *offset_idxs,
+                                const int32_t *starts, int64_t n_queries, const int64_t *out_offsets,
+                                int64_t total, int64_t max_len, float *out, gvl_stream stream);
+
+/* ---- host layer: reference-shaped entries (host pointers in, host pointers out) ------ */
+/* Upload (or refresh) a static array and cache it by host address; later gvl_* calls that see
+ * the same (ptr, bytes) use the device copy.  The caller must not mutate or free the host array
+ * while it is pinned.  Arrays that were NOT pinned are uploaded for the duration of the call
+ * (correct, but pays the copy every time).  Replaces the zero-copy memmap crossing that
+ * `_ffi_array` guards (python/genvarloader/_dataset/_utils.py:13-35). */
+int gvl_pin_static(gvl_ctx *ctx, const void *host_ptr, int64_t bytes);
+int gvl_unpin_static(gvl_ctx *ctx, const void *host_ptr);
+/* Page-locked host memory for per-call inputs/outputs (full PCIe rate on the D2H copies). */
+int gvl_host_alloc(int64_t bytes, void **out);
+int gvl_host_free(void *p);
+
+/* reconstruct_haplotypes_fused, src/ffi/mod.rs:724-860 (mode U8) -- also serves
+ * reconstruct_annotated_haplotypes_fused, src/ffi/mod.rs:2239-2397 (mode ANNOTATED) and the
+ * fused one-hot encodings.  Two calls, like every C API that returns a variable-size buffer:
+ *   gvl_reconstruct_haplotypes_fused_begin  runs plan, fills out_offsets (host i64[b*p+1]),
+ *                                           returns the element count in *total
+ *   gvl_reconstruct_haplotypes_fused_finish executes into caller-owned host buffers
+ *                                           (out: total bytes, or total*4 for one-hot)
+ */
+int gvl_reconstruct_haplotypes_fused_begin(
+    gvl_ctx *ctx, const int32_t *regions, const int32_t *shifts, const int64_t *geno_offset_idx, int64_t batch,
+    int64_t ploidy, const int64_t *geno_offsets /* (2,n_geno) */, int64_t n_geno, const int32_t *geno_v_idxs,
+    int64_t n_geno_v, const int32_t *v_starts, const int32_t *ilens, int64_t n_variants, const uint8_t *alt_alleles,
+    const int64_t *alt_offsets, const uint8_t *ref_, const int64_t *ref_offsets, int64_t n_contigs,
+    int64_t output_length, const uint8_t *keep, const int64_t *keep_offsets, const uint8_t *to_rc,
+    int64_t *out_offsets, int64_t *total);
+int gvl_reconstruct_haplotypes_fused_finish(gvl_ctx *ctx, int mode, uint8_t pad_char, uint8_t *out, int32_t *annot_v,
+                                            int32_t *annot_pos);
+
+/* reconstruct_haplotypes_from_sparse, src/ffi/mod.rs:634-655: caller-sized rows, writes `out`
+ * (and the optional annotation buffers) in place.  out: host u8[out_offsets[b*p]]. */
+int gvl_reconstruct_haplotypes_from_sparse(
+    gvl_ctx *ctx, uint8_t *out, const int64_t *out_offsets, const int32_t *regions, const int32_t *shifts,
+    const int64_t *geno_offset_idx, int64_t batch, int64_t ploidy, const int64_t *geno_offsets, int64_t n_geno,
+    const int32_t *geno_v_idxs, int64_t n_geno_v, const int32_t *v_starts, const int32_t *ilens, int64_t n_variants,
+    const uint8_t *alt_alleles, const int64_t *alt_offsets, const uint8_t *ref_, const int64_t *ref_offsets,
+    int64_t n_contigs, uint8_t pad_char, const uint8_t *keep, const int64_t *keep_offsets, int32_t *annot_v_idxs,
+    int32_t *annot_ref_pos);
+
+/* get_diffs_sparse, src/ffi/mod.rs:145-157.  diffs: host i32[n_queries*ploidy]. */
+int gvl_get_diffs_sparse(gvl_ctx *ctx, const int64_t *geno_offset_idx, int64_t n_queries, int64_t ploidy,
+                         const int32_t *geno_v_idxs, int64_t n_geno_v, const int64_t *geno_offsets, int64_t n_geno,
+                         const int32_t *ilens, int64_t n_variants, const uint8_t *keep, const int64_t *keep_offsets,
+                         const int32_t *q_starts, const int32_t *q_ends, const int32_t *v_starts, int32_t *diffs);
+
+/* intervals_and_realign_track_fused, src/ffi/mod.rs:2553-2672 (one track per call, like the
+ * reference's Python loop at _reconstruct.py:228-290).  out: host f32[out_offsets[b*p]]. */
+int gvl_intervals_and_realign_track_fused(
+    gvl_ctx *ctx, float *out, const int64_t *out_offsets, const int32_t *regions, const int32_t *shifts,
+    const int64_t *geno_offset_idx, int64_t batch, int64_t ploidy, const int32_t *geno_v_idxs, int64_t n_geno_v,
+    const int64_t *geno_offsets, int64_t n_geno, const int32_t *v_starts, const int32_t *ilens, int64_t n_variants,
+    const int64_t *offset_idxs, const int32_t *itv_starts, const int32_t *itv_ends, const float *itv_values,
+    int64_t n_itv, const int64_t *itv_offsets, int64_t n_slots, const int64_t *track_offsets, const double *params,
+    int64_t strategy_id, uint64_t base_seed, const uint8_t *keep, const int64_t *keep_offsets, const uint8_t *to_rc);
+
+/* intervals_to_tracks, src/ffi/mod.rs:190-201.  out: host f32[out_offsets[n_queries]]. */
+int gvl_intervals_to_tracks(gvl_ctx *ctx, const int64_t *offset_idxs, const int32_t *starts, int64_t n_queries,
+                            const int32_t *itv_starts, const int32_t *itv_ends, const float *itv_values,
+                            int64_t n_itv, const int64_t *itv_offsets, int64_t n_slots, float *out,
+                            const int64_t *out_offsets);
+
+/* _debug_xorshift64 / _debug_hash4, src/ffi/mod.rs:2824-2834 (evaluated on the device). */
+int gvl_debug_hash4(gvl_ctx *ctx, uint64_t a, uint64_t b, uint64_t c, uint64_t d, uint64_t *out);
+int gvl_debug_xorshift64(gvl_ctx *ctx, uint64_t x, uint64_t *out);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* GVL_B200_H */

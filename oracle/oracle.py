@@ -18,7 +18,21 @@ import numpy as np
 
 _HERE = Path(__file__).resolve().parent
 _SRC = _HERE / "gvl_oracle.c"
-_LIB = _HERE / "libgvl_oracle.so"
+
+
+def _cpu_tag() -> str:
+    """-march=native objects are only valid on the CPU model they were built on: key the .so by
+    the CPU feature flags so the build container and the GPU box each get their own."""
+    import hashlib
+
+    try:
+        flags = next(l for l in open("/proc/cpuinfo") if l.startswith("flags"))
+    except Exception:
+        flags = "generic"
+    return hashlib.md5(flags.encode()).hexdigest()[:8]
+
+
+_LIB = _HERE / f"libgvl_oracle_{_cpu_tag()}.so"
 
 # -ffp-contract=off: the f64 Lagrange arithmetic of Interpolate must not be fused into FMAs.
 _CFLAGS = ["-O3", "-march=native", "-ffp-contract=off", "-fPIC", "-shared", "-pthread"]

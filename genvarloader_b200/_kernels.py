@@ -188,3 +188,75 @@ def get_diffs_sparse(geno_offset_idx, geno_v_idxs, geno_offsets, ilens, keep=Non
                                    c_i64(go.shape[1]), _p(il), c_i64(il.size), _p(kp), _p(ko), _p(qs), _p(qe), _p(vs),
                                    _p(diffs)))
     return diffs
+
+
+# ---------------------------------------------------------------------------------- tracks
+def intervals_to_tracks(offset_idxs, starts, itv_starts, itv_ends, itv_values, itv_offsets, out, out_offsets,
+                        parallel=True, *, ctx=None):
+    """src/ffi/mod.rs:190-201.  Paints intervals into ``out`` (f32, fully overwritten) in place."""
+    ctx = ctx or default_ctx()
+    assert out.dtype == np.float32 and out.flags.c_contiguous
+    oi, st = _c(offset_idxs, np.int64), _c(starts, np.int32)
+    s, e, v = _c(itv_starts, np.int32), _c(itv_ends, np.int32), _c(itv_values, np.float32)
+    io, oo = _c(itv_offsets, np.int64), _c(out_offsets, np.int64)
+    check(lib.gvl_intervals_to_tracks(ctx.handle, _p(oi), _p(st), c_i64(st.size), _p(s), _p(e), _p(v), c_i64(s.size),
+                                      _p(io), c_i64(io.size - 1), _p(out), _p(oo)))
+
+
+def shift_and_realign_tracks_sparse(out, out_offsets, regions, shifts, geno_offset_idx, geno_v_idxs, geno_offsets,
+                                    v_starts, ilens, tracks, track_offsets, params, keep=None, keep_offsets=None,
+                                    strategy_id=0, base_seed=0, parallel=True, *, ctx=None):
+    """src/ffi/mod.rs:2439-2458.  Dense f32 source windows; writes ``out`` in place."""
+    ctx = ctx or default_ctx()
+    assert out.dtype == np.float32 and out.flags.c_contiguous
+    oo, rg, sh = _c(out_offsets, np.int64), _c(regions, np.int32), _c(shifts, np.int32)
+    goi = _c(geno_offset_idx, np.int64)
+    batch, ploidy = goi.shape
+    go = _starts_stops(geno_offsets)
+    gv, vs, il = _c(geno_v_idxs, np.int32), _c(v_starts, np.int32), _c(ilens, np.int32)
+    tr, to, pa = _c(tracks, np.float32), _c(track_offsets, np.int64), _c(params, np.float64)
+    kp, ko = _c(keep, np.bool_), _c(keep_offsets, np.int64)
+    check(lib.gvl_shift_and_realign_tracks_sparse(
+        ctx.handle, _p(out), _p(oo), _p(rg), _p(sh), _p(goi), c_i64(batch), c_i64(ploidy), _p(gv), c_i64(gv.size), _p(go),
+        c_i64(go.shape[1]), _p(vs), _p(il), c_i64(vs.size), _p(tr), _p(to), _p(pa), _p(kp), _p(ko),
+        c_i64(int(strategy_id)), c_u64(int(base_seed))))
+
+
+def intervals_and_realign_track_fused(out, out_offsets, regions, shifts, geno_offset_idx, geno_v_idxs, geno_offsets,
+                                      v_starts, ilens, offset_idxs, itv_starts, itv_ends, itv_values, itv_offsets,
+                                      track_offsets, params, strategy_id, base_seed, keep=None, keep_offsets=None,
+                                      to_rc=None, parallel=True, *, ctx=None):
+    """src/ffi/mod.rs:2553-2672.  Paint + realign (+ reverse for negative strands) of ONE track into
+    the caller's ``out`` slice, exactly the call the reference makes per track (_reconstruct.py:257-290)."""
+    ctx = ctx or default_ctx()
+    assert out.dtype == np.float32 and out.flags.c_contiguous
+    oo, rg, sh = _c(out_offsets, np.int64), _c(regions, np.int32), _c(shifts, np.int32)
+    goi = _c(geno_offset_idx, np.int64)
+    batch, ploidy = goi.shape
+    go = geno_offsets if (isinstance(geno_offsets, np.ndarray) and geno_offsets.ndim == 2 and
+                          geno_offsets.dtype == np.int64 and geno_offsets.flags.c_contiguous) else _starts_stops(geno_offsets)
+    gv, vs, il = _c(geno_v_idxs, np.int32), _c(v_starts, np.int32), _c(ilens, np.int32)
+    oi = _c(offset_idxs, np.int64)
+    s, e, v = _c(itv_starts, np.int32), _c(itv_ends, np.int32), _c(itv_values, np.float32)
+    io, to, pa = _c(itv_offsets, np.int64), _c(track_offsets, np.int64), _c(params, np.float64)
+    kp, ko, rc = _c(keep, np.bool_), _c(keep_offsets, np.int64), _c(to_rc, np.bool_)
+    check(lib.gvl_intervals_and_realign_track_fused(
+        ctx.handle, _p(out), _p(oo), _p(rg), _p(sh), _p(goi), c_i64(batch), c_i64(ploidy), _p(gv), c_i64(gv.size), _p(go),
+        c_i64(go.shape[1]), _p(vs), _p(il), c_i64(vs.size), _p(oi), _p(s), _p(e), _p(v), c_i64(s.size), _p(io),
+        c_i64(io.size - 1), _p(to), _p(pa), c_i64(int(strategy_id)), c_u64(int(base_seed)), _p(kp), _p(ko), _p(rc)))
+
+
+def _debug_xorshift64(x: int, *, ctx=None) -> int:
+    """src/ffi/mod.rs:2824 -- evaluated by a device kernel."""
+    ctx = ctx or default_ctx()
+    out = c_u64(0)
+    check(lib.gvl_debug_xorshift64(ctx.handle, c_u64(int(x)), C.byref(out)))
+    return int(out.value)
+
+
+def _debug_hash4(a: int, b: int, c: int, d: int, *, ctx=None) -> int:
+    """src/ffi/mod.rs:2830 -- evaluated by a device kernel."""
+    ctx = ctx or default_ctx()
+    out = c_u64(0)
+    check(lib.gvl_debug_hash4(ctx.handle, c_u64(int(a)), c_u64(int(b)), c_u64(int(c)), c_u64(int(d)), C.byref(out)))
+    return int(out.value)

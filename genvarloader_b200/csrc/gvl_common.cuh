@@ -48,23 +48,31 @@ constexpr int64_t ALT_PAD = INT64_MIN;  // RecArrays.src sentinel: "ALT piece" i
 
 }  // namespace gvl
 
+#define GVL_TRK_DESC_BYTES 4096
+
 struct gvl_static_entry {
     void *dev;
     int64_t bytes;
 };
 
-struct gvl_ctx {
-    int device;
-    cudaStream_t own_stream;  // used by the host layer
-    // workspace
+// Plan workspace: row headers + record arrays + tile map.  One for haplotypes, one for tracks, so a
+// track plan never invalidates a haplotype plan that has not been executed yet.
+struct gvl_workspace {
     gvl::RowPlan *rows;
     int64_t rows_cap;
     gvl::RecArrays rec;
     int64_t rec_cap;
-    int64_t *dev_words;   // W_COUNT words
+    int64_t *tile_off;  // i64[rows_cap+1] (ragged plans)
+    int32_t *row_len;   // i32[rows_cap]
+};
+
+struct gvl_ctx {
+    int device;
+    cudaStream_t own_stream;  // used by the host layer
+    gvl_workspace hap, trk;
+    void *trk_desc;       // device buffer for per-track descriptors (GVL_TRK_DESC_BYTES)
+    int64_t *dev_words;   // 2 * W_COUNT words (haps, tracks)
     int64_t *host_words;  // pinned mirror
-    int64_t *tile_off;    // i64[rows_cap+1] (ragged plans)
-    int32_t *row_len;     // i32[rows_cap]
     // current haplotype plan
     bool plan_valid;
     int64_t n_work;

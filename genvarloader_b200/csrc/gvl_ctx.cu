@@ -22,38 +22,52 @@ int fail(int code, const char *fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 template <typename T>
-static int grow(T *&p, int64_t &cap_elems_unused, int64_t need, int64_t old_cap) {
-    (void)cap_elems_unused;
-    if (need <= old_cap && p) return GVL_OK;
+static int regrow(T *&p, int64_t need) {
     if (p) GVL_CUDA(cudaFree(p));
     p = nullptr;
     GVL_CUDA(cudaMalloc(&p, sizeof(T) * (size_t)need));
     return GVL_OK;
 }
 
-int ensure_rows(gvl_ctx *ctx, int64_t n_work) {
-    if (n_work <= ctx->rows_cap) return GVL_OK;
-    int64_t cap = n_work + n_work / 2 + 64, dummy = 0;
+int ensure_rows(gvl_ctx *ctx, gvl_workspace &ws, int64_t n_work) {
+    (void)ctx;
+    if (n_work <= ws.rows_cap) return GVL_OK;
+    GVL_CUDA(cudaDeviceSynchronize());  // nothing may still be reading the old buffers
+    int64_t cap = n_work + n_work / 2 + 64;
     int rc;
-    if ((rc = grow(ctx->rows, dummy, cap, 0))) return rc;
-    if ((rc = grow(ctx->tile_off, dummy, cap + 1, 0))) return rc;
-    if ((rc = grow(ctx->row_len, dummy, cap, 0))) return rc;
-    ctx->rows_cap = cap;
+    if ((rc = regrow(ws.rows, cap))) return rc;
+    if ((rc = regrow(ws.tile_off, cap + 1))) return rc;
+    if ((rc = regrow(ws.row_len, cap))) return rc;
+    ws.rows_cap = cap;
     return GVL_OK;
 }
 
-int ensure_records(gvl_ctx *ctx, int64_t n_rec) {
-    if (n_rec <= ctx->rec_cap) return GVL_OK;
-    int64_t cap = n_rec + n_rec / 2 + 1024, dummy = 0;
+int ensure_records(gvl_ctx *ctx, gvl_workspace &ws, int64_t n_rec) {
+    (void)ctx;
+    if (n_rec <= ws.rec_cap) return GVL_OK;
+    GVL_CUDA(cudaDeviceSynchronize());
+    int64_t cap = n_rec + n_rec / 2 + 1024;
     int rc;
-    if ((rc = grow(ctx->rec.a, dummy, cap, 0))) return rc;
-    if ((rc = grow(ctx->rec.n, dummy, cap, 0))) return rc;
-    if ((rc = grow(ctx->rec.src, dummy, cap, 0))) return rc;
-    if ((rc = grow(ctx->rec.resume, dummy, cap, 0))) return rc;
-    if ((rc = grow(ctx->rec.vidx, dummy, cap, 0))) return rc;
-    if ((rc = grow(ctx->rec.vpos, dummy, cap, 0))) return rc;
-    ctx->rec_cap = cap;
+    if ((rc = regrow(ws.rec.a, cap))) return rc;
+    if ((rc = regrow(ws.rec.n, cap))) return rc;
+    if ((rc = regrow(ws.rec.src, cap))) return rc;
+    if ((rc = regrow(ws.rec.resume, cap))) return rc;
+    if ((rc = regrow(ws.rec.vidx, cap))) return rc;
+    if ((rc = regrow(ws.rec.vpos, cap))) return rc;
+    ws.rec_cap = cap;
     return GVL_OK;
+}
+
+static void free_workspace(gvl_workspace &ws) {
+    cudaFree(ws.rows);
+    cudaFree(ws.tile_off);
+    cudaFree(ws.row_len);
+    cudaFree(ws.rec.a);
+    cudaFree(ws.rec.n);
+    cudaFree(ws.rec.src);
+    cudaFree(ws.rec.resume);
+    cudaFree(ws.rec.vidx);
+    cudaFree(ws.rec.vpos);
 }
 
 }  // namespace gvl
@@ -77,14 +91,11 @@ int gvl_ctx_create(int device, gvl_ctx **out) {
     gvl_ctx *ctx = new gvl_ctx();
     ctx->device = device;
     ctx->own_stream = nullptr;
-    ctx->rows = nullptr;
-    ctx->rows_cap = 0;
-    ctx->rec = RecArrays{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    ctx->rec_cap = 0;
+    memset(&ctx->hap, 0, sizeof(ctx->hap));
+    memset(&ctx->trk, 0, sizeof(ctx->trk));
     ctx->dev_words = nullptr;
     ctx->host_words = nullptr;
-    ctx->tile_off = nullptr;
-    ctx->row_len = nullptr;
+    ctx->trk_desc = nullptr;
     ctx->plan_valid = false;
     ctx->n_work = 0;
     ctx->fixed_len = -1;
@@ -95,9 +106,10 @@ int gvl_ctx_create(int device, gvl_ctx **out) {
     ctx->host_out_offsets_dev = nullptr;
     memset(&ctx->host_tab, 0, sizeof(ctx->host_tab));
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaMalloc(&ctx->dev_words, sizeof(int64_t) * W_COUNT);
-    if (e == cudaSuccess) e = cudaMemset(ctx->dev_words, 0, sizeof(int64_t) * W_COUNT);
-    if (e == cudaSuccess) e = cudaHostAlloc(&ctx->host_words, sizeof(int64_t) * W_COUNT, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->dev_words, sizeof(int64_t) * 2 * W_COUNT);
+    if (e == cudaSuccess) e = cudaMemset(ctx->dev_words, 0, sizeof(int64_t) * 2 * W_COUNT);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->trk_desc, GVL_TRK_DESC_BYTES);
+    if (e == cudaSuccess) e = cudaHostAlloc(&ctx->host_words, sizeof(int64_t) * 2 * W_COUNT, cudaHostAllocDefault);
     if (e != cudaSuccess) {
         gvl_ctx_destroy(ctx);
         return fail(GVL_ERR_CUDA, "gvl_ctx_create: %s", cudaGetErrorString(e));
@@ -110,16 +122,10 @@ void gvl_ctx_destroy(gvl_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    cudaFree(ctx->rows);
-    cudaFree(ctx->tile_off);
-    cudaFree(ctx->row_len);
-    cudaFree(ctx->rec.a);
-    cudaFree(ctx->rec.n);
-    cudaFree(ctx->rec.src);
-    cudaFree(ctx->rec.resume);
-    cudaFree(ctx->rec.vidx);
-    cudaFree(ctx->rec.vpos);
+    free_workspace(ctx->hap);
+    free_workspace(ctx->trk);
     cudaFree(ctx->dev_words);
+    cudaFree(ctx->trk_desc);
     if (ctx->host_words) cudaFreeHost(ctx->host_words);
     for (auto &kv : ctx->statics) cudaFree(kv.second.dev);
     for (auto &s : ctx->scratch) cudaFree(s.first);
@@ -132,11 +138,12 @@ int gvl_ctx_check(gvl_ctx *ctx, gvl_stream stream) {
     if (!ctx) return fail(GVL_ERR_ARG, "gvl_ctx_check: ctx is NULL");
     cudaStream_t st = (cudaStream_t)stream;
     GVL_CUDA(cudaSetDevice(ctx->device));
-    GVL_CUDA(cudaMemcpyAsync(ctx->host_words, ctx->dev_words, sizeof(int64_t) * W_COUNT, cudaMemcpyDeviceToHost, st));
+    GVL_CUDA(cudaMemcpyAsync(ctx->host_words, ctx->dev_words, sizeof(int64_t) * 2 * W_COUNT, cudaMemcpyDeviceToHost, st));
     GVL_CUDA(cudaStreamSynchronize(st));
-    if (ctx->host_words[W_STATUS] != 0) {
-        int64_t s = ctx->host_words[W_STATUS];
+    if (ctx->host_words[W_STATUS] != 0 || ctx->host_words[W_COUNT + W_STATUS] != 0) {
+        int64_t s = ctx->host_words[W_STATUS] | ctx->host_words[W_COUNT + W_STATUS];
         cudaMemsetAsync(ctx->dev_words + W_STATUS, 0, sizeof(int64_t), st);
+        cudaMemsetAsync(ctx->dev_words + W_COUNT + W_STATUS, 0, sizeof(int64_t), st);
         return fail(GVL_ERR_CAPACITY, "device workspace overflow (status=%lld): raise max_records", (long long)s);
     }
     return GVL_OK;

@@ -631,8 +631,8 @@ int gvl_dev_hap_plan(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_t *
     const int64_t n_work = batch * ploidy;
     ctx->plan_valid = false;
     int rc;
-    if ((rc = ensure_rows(ctx, n_work))) return rc;
-    if ((rc = ensure_records(ctx, max_records + n_work))) return rc;
+    if ((rc = ensure_rows(ctx, ctx->hap, n_work))) return rc;
+    if ((rc = ensure_records(ctx, ctx->hap, max_records + n_work))) return rc;
     GVL_CUDA(cudaMemsetAsync(ctx->dev_words, 0, sizeof(int64_t) * 4, st));
     ctx->n_work = n_work;
     ctx->fixed_len = output_length >= 0 ? output_length : -1;
@@ -654,21 +654,21 @@ int gvl_dev_hap_plan(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_t *
     P.n_work = n_work;
     P.ploidy = ploidy;
     P.output_length = output_length >= 0 ? output_length : (output_length == -2 ? -2 : -1);
-    P.rec_cap = ctx->rec_cap;
-    P.rows = ctx->rows;
-    P.rec = ctx->rec;
+    P.rec_cap = ctx->hap.rec_cap;
+    P.rows = ctx->hap.rows;
+    P.rec = ctx->hap.rec;
     P.words = ctx->dev_words;
     P.out_offsets = out_offsets;
     P.diffs = diffs;
-    P.row_len = ctx->row_len;
+    P.row_len = ctx->hap.row_len;
     const unsigned grid = (unsigned)((n_work + PLAN_WARPS - 1) / PLAN_WARPS);
     hap_plan_kernel<<<grid, PLAN_WARPS * 32, 0, st>>>(P);
     GVL_LAUNCH_CHECK();
     if (output_length >= 0) {
         ctx->total = n_work * output_length;
     } else {
-        row_scan_kernel<<<1, 1024, 0, st>>>(n_work, ctx->row_len, ctx->rows, output_length == -2 ? nullptr : out_offsets,
-                                            ctx->tile_off, ctx->dev_words);
+        row_scan_kernel<<<1, 1024, 0, st>>>(n_work, ctx->hap.row_len, ctx->hap.rows,
+                                            output_length == -2 ? nullptr : out_offsets, ctx->hap.tile_off, ctx->dev_words);
         GVL_LAUNCH_CHECK();
         ctx->total = -1;
     }
@@ -701,8 +701,8 @@ int gvl_dev_hap_exec(gvl_ctx *ctx, const gvl_sparse_tables *tab, int mode, uint8
     if (mode == GVL_MODE_ANNOTATED && (!annot_v || !annot_pos))
         return fail(GVL_ERR_ARG, "gvl_dev_hap_exec: annotated mode needs annot_v and annot_pos");
     HapExecParams P;
-    P.rows = ctx->rows;
-    P.rec = ctx->rec;
+    P.rows = ctx->hap.rows;
+    P.rec = ctx->hap.rec;
     P.ref = tab->ref;
     P.alt = tab->alt_alleles;
     P.n_work = ctx->n_work;
@@ -719,7 +719,7 @@ int gvl_dev_hap_exec(gvl_ctx *ctx, const gvl_sparse_tables *tab, int mode, uint8
         if (ctx->total < 0) return fail(GVL_ERR_STATE, "gvl_dev_hap_exec: ragged plan needs gvl_dev_hap_total first");
         if (mode == GVL_MODE_ONEHOT_CF) return fail(GVL_ERR_ARG, "gvl_dev_hap_exec: channels-first one-hot needs a fixed length");
         P.tiles_per_row = 0;
-        P.tile_off = ctx->tile_off;
+        P.tile_off = ctx->hap.tile_off;
         grid = ctx->host_words[W_TILES];
     }
     if (grid == 0) return GVL_OK;

@@ -328,3 +328,147 @@ int gvl_get_diffs_sparse(gvl_ctx *ctx, const int64_t *geno_offset_idx, int64_t n
 }
 
 }  // extern "C"
+
+// ---- tracks ----------------------------------------------------------------------------------
+extern "C" {
+
+static int resolve_intervals(gvl_ctx *ctx, const int32_t *itv_starts, const int32_t *itv_ends, const float *itv_values,
+                             int64_t n_itv, const int64_t *itv_offsets, int64_t n_slots, gvl_intervals *iv) {
+    int rc;
+    const void *d;
+    if ((rc = static_dev(ctx, itv_starts, sizeof(int32_t) * n_itv, 16, &d))) return rc;
+    iv->itv_starts = (const int32_t *)d;
+    if ((rc = static_dev(ctx, itv_ends, sizeof(int32_t) * n_itv, 17, &d))) return rc;
+    iv->itv_ends = (const int32_t *)d;
+    if ((rc = static_dev(ctx, itv_values, sizeof(float) * n_itv, 18, &d))) return rc;
+    iv->itv_values = (const float *)d;
+    if ((rc = static_dev(ctx, itv_offsets, sizeof(int64_t) * (n_slots + 1), 19, &d))) return rc;
+    iv->itv_offsets = (const int64_t *)d;
+    iv->n_slots = n_slots;
+    return GVL_OK;
+}
+
+int gvl_intervals_and_realign_track_fused(
+    gvl_ctx *ctx, float *out, const int64_t *out_offsets, const int32_t *regions, const int32_t *shifts,
+    const int64_t *geno_offset_idx, int64_t batch, int64_t ploidy, const int32_t *geno_v_idxs, int64_t n_geno_v,
+    const int64_t *geno_offsets, int64_t n_geno, const int32_t *v_starts, const int32_t *ilens, int64_t n_variants,
+    const int64_t *offset_idxs, const int32_t *itv_starts, const int32_t *itv_ends, const float *itv_values,
+    int64_t n_itv, const int64_t *itv_offsets, int64_t n_slots, const int64_t *track_offsets, const double *params,
+    int64_t strategy_id, uint64_t base_seed, const uint8_t *keep, const int64_t *keep_offsets, const uint8_t *to_rc) {
+    if (!ctx || !out_offsets || !regions || !shifts || !geno_offset_idx || !geno_v_idxs || !geno_offsets || !v_starts ||
+        !ilens || !offset_idxs || !itv_offsets || !track_offsets || !params)
+        return fail(GVL_ERR_ARG, "gvl_intervals_and_realign_track_fused: NULL argument");
+    GVL_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    const int64_t n_work = batch * ploidy;
+    const int64_t total = out_offsets[n_work];
+    if (n_work == 0 || total == 0) return GVL_OK;
+    if (!out) return fail(GVL_ERR_ARG, "gvl_intervals_and_realign_track_fused: out is NULL");
+    gvl_sparse_tables t;
+    if ((rc = resolve_tables(ctx, geno_offsets, n_geno, geno_v_idxs, n_geno_v, v_starts, ilens, n_variants, nullptr,
+                             nullptr, nullptr, nullptr, 0, &t)))
+        return rc;
+    gvl_intervals iv;
+    if ((rc = resolve_intervals(ctx, itv_starts, itv_ends, itv_values, n_itv, itv_offsets, n_slots, &iv))) return rc;
+    std::vector<int32_t> tl((size_t)batch);
+    for (int64_t q = 0; q < batch; q++) tl[q] = (int32_t)(track_offsets[q + 1] - track_offsets[q]);
+    Packer pk;
+    size_t i_reg = pk.add(regions, sizeof(int32_t) * 3 * batch);
+    size_t i_sh = pk.add(shifts, sizeof(int32_t) * n_work);
+    size_t i_goi = pk.add(geno_offset_idx, sizeof(int64_t) * n_work);
+    size_t i_ko = pk.add(keep_offsets, sizeof(int64_t) * (n_work + 1));
+    size_t i_kp = pk.add(keep, keep_offsets ? keep_offsets[n_work] : 0);
+    size_t i_rc = pk.add(to_rc, n_work);
+    size_t i_oi = pk.add(offset_idxs, sizeof(int64_t) * batch);
+    size_t i_tl = pk.add(tl.data(), sizeof(int32_t) * batch);
+    size_t i_oo = pk.add(out_offsets, sizeof(int64_t) * (n_work + 1));
+    if ((rc = pk.upload(ctx, 0))) return rc;
+    void *d_out;
+    if ((rc = scratch(ctx, 2, total * 4, &d_out))) return rc;
+    const int32_t strat = (int32_t)strategy_id;
+    const int64_t max_rec = sum_variants(geno_offsets, n_geno, geno_offset_idx, n_work);
+    if ((rc = gvl_dev_realign_tracks(ctx, &t, pk.ptr<int32_t>(i_reg), pk.ptr<int32_t>(i_sh), pk.ptr<int64_t>(i_goi), batch,
+                                     ploidy, keep && keep_offsets ? pk.ptr<uint8_t>(i_kp) : nullptr,
+                                     keep && keep_offsets ? pk.ptr<int64_t>(i_ko) : nullptr, pk.ptr<uint8_t>(i_rc), 1, &iv,
+                                     pk.ptr<int64_t>(i_oi), pk.ptr<int32_t>(i_tl), pk.ptr<int64_t>(i_oo), total, &strat,
+                                     params, base_seed, nullptr, max_rec, (float *)d_out, ctx->own_stream)))
+        return rc;
+    GVL_CUDA(cudaMemcpyAsync(out, d_out, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->own_stream));
+    return gvl_ctx_check(ctx, ctx->own_stream);
+}
+
+int gvl_shift_and_realign_tracks_sparse(
+    gvl_ctx *ctx, float *out, const int64_t *out_offsets, const int32_t *regions, const int32_t *shifts,
+    const int64_t *geno_offset_idx, int64_t batch, int64_t ploidy, const int32_t *geno_v_idxs, int64_t n_geno_v,
+    const int64_t *geno_offsets, int64_t n_geno, const int32_t *v_starts, const int32_t *ilens, int64_t n_variants,
+    const float *tracks, const int64_t *track_offsets, const double *params, const uint8_t *keep,
+    const int64_t *keep_offsets, int64_t strategy_id, uint64_t base_seed) {
+    if (!ctx || !out_offsets || !regions || !shifts || !geno_offset_idx || !geno_v_idxs || !geno_offsets || !v_starts ||
+        !ilens || !track_offsets || !params)
+        return fail(GVL_ERR_ARG, "gvl_shift_and_realign_tracks_sparse: NULL argument");
+    GVL_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    const int64_t n_work = batch * ploidy;
+    const int64_t total = out_offsets[n_work];
+    if (n_work == 0 || total == 0) return GVL_OK;
+    if (!out || !tracks) return fail(GVL_ERR_ARG, "gvl_shift_and_realign_tracks_sparse: NULL buffer");
+    gvl_sparse_tables t;
+    if ((rc = resolve_tables(ctx, geno_offsets, n_geno, geno_v_idxs, n_geno_v, v_starts, ilens, n_variants, nullptr,
+                             nullptr, nullptr, nullptr, 0, &t)))
+        return rc;
+    const void *d_tracks;
+    if ((rc = static_dev(ctx, tracks, sizeof(float) * track_offsets[batch], 16, &d_tracks))) return rc;
+    std::vector<int32_t> tl((size_t)batch);
+    for (int64_t q = 0; q < batch; q++) tl[q] = (int32_t)(track_offsets[q + 1] - track_offsets[q]);
+    Packer pk;
+    size_t i_reg = pk.add(regions, sizeof(int32_t) * 3 * batch);
+    size_t i_sh = pk.add(shifts, sizeof(int32_t) * n_work);
+    size_t i_goi = pk.add(geno_offset_idx, sizeof(int64_t) * n_work);
+    size_t i_ko = pk.add(keep_offsets, sizeof(int64_t) * (n_work + 1));
+    size_t i_kp = pk.add(keep, keep_offsets ? keep_offsets[n_work] : 0);
+    size_t i_to = pk.add(track_offsets, sizeof(int64_t) * (batch + 1));
+    size_t i_tl = pk.add(tl.data(), sizeof(int32_t) * batch);
+    size_t i_oo = pk.add(out_offsets, sizeof(int64_t) * (n_work + 1));
+    if ((rc = pk.upload(ctx, 0))) return rc;
+    void *d_out;
+    if ((rc = scratch(ctx, 2, total * 4, &d_out))) return rc;
+    const int64_t max_rec = sum_variants(geno_offsets, n_geno, geno_offset_idx, n_work);
+    if ((rc = gvl_dev_shift_and_realign_tracks(
+             ctx, &t, pk.ptr<int32_t>(i_reg), pk.ptr<int32_t>(i_sh), pk.ptr<int64_t>(i_goi), batch, ploidy,
+             keep && keep_offsets ? pk.ptr<uint8_t>(i_kp) : nullptr, keep && keep_offsets ? pk.ptr<int64_t>(i_ko) : nullptr,
+             nullptr, (const float *)d_tracks, pk.ptr<int64_t>(i_to), pk.ptr<int32_t>(i_tl), pk.ptr<int64_t>(i_oo), total,
+             (int32_t)strategy_id, params[0], base_seed, nullptr, max_rec, (float *)d_out, ctx->own_stream)))
+        return rc;
+    GVL_CUDA(cudaMemcpyAsync(out, d_out, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->own_stream));
+    return gvl_ctx_check(ctx, ctx->own_stream);
+}
+
+int gvl_intervals_to_tracks(gvl_ctx *ctx, const int64_t *offset_idxs, const int32_t *starts, int64_t n_queries,
+                            const int32_t *itv_starts, const int32_t *itv_ends, const float *itv_values,
+                            int64_t n_itv, const int64_t *itv_offsets, int64_t n_slots, float *out,
+                            const int64_t *out_offsets) {
+    if (!ctx || !offset_idxs || !starts || !itv_offsets || !out_offsets)
+        return fail(GVL_ERR_ARG, "gvl_intervals_to_tracks: NULL argument");
+    GVL_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    const int64_t total = out_offsets[n_queries];
+    if (n_queries == 0 || total == 0) return GVL_OK;
+    if (!out) return fail(GVL_ERR_ARG, "gvl_intervals_to_tracks: out is NULL");
+    gvl_intervals iv;
+    if ((rc = resolve_intervals(ctx, itv_starts, itv_ends, itv_values, n_itv, itv_offsets, n_slots, &iv))) return rc;
+    Packer pk;
+    size_t i_oi = pk.add(offset_idxs, sizeof(int64_t) * n_queries);
+    size_t i_st = pk.add(starts, sizeof(int32_t) * n_queries);
+    size_t i_oo = pk.add(out_offsets, sizeof(int64_t) * (n_queries + 1));
+    if ((rc = pk.upload(ctx, 0))) return rc;
+    void *d_out;
+    if ((rc = scratch(ctx, 2, total * 4, &d_out))) return rc;
+    if ((rc = gvl_dev_intervals_to_tracks(ctx, &iv, pk.ptr<int64_t>(i_oi), pk.ptr<int32_t>(i_st), n_queries,
+                                          pk.ptr<int64_t>(i_oo), total, (float *)d_out, ctx->own_stream)))
+        return rc;
+    GVL_CUDA(cudaMemcpyAsync(out, d_out, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->own_stream));
+    GVL_CUDA(cudaStreamSynchronize(ctx->own_stream));
+    return GVL_OK;
+}
+
+}  // extern "C"

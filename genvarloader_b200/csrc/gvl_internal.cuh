@@ -6,8 +6,8 @@ namespace gvl {
 
 int fail(int code, const char *fmt, ...);
 void count_launch(int n = 1);
-int ensure_rows(gvl_ctx *ctx, int64_t n_work);
-int ensure_records(gvl_ctx *ctx, int64_t n_rec);
+int ensure_rows(gvl_ctx *ctx, gvl_workspace &ws, int64_t n_work);
+int ensure_records(gvl_ctx *ctx, gvl_workspace &ws, int64_t n_rec);
 
 #define GVL_CUDA(expr)                                                                                  \
     do {                                                                                                \

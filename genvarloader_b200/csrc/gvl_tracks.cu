@@ -1,0 +1,673 @@
+// gvl_tracks.cu -- indel-aware track realignment on sm_100a (include/gvl_b200.h:
+// gvl_dev_realign_tracks, gvl_dev_intervals_to_tracks).
+//
+// Reference path replaced: intervals_and_realign_track_fused (src/ffi/mod.rs:2553-2672) =
+// intervals_to_tracks (src/intervals.rs:19-126) into a dense scratch -> shift_and_realign_tracks_sparse
+// (src/tracks/mod.rs:224-406, 495-667) -> reverse_flat_rows_inplace (src/reverse.rs:25-38), called
+// once per track from a Python loop (_dataset/_reconstruct.py:228-290).
+//
+// Here: ONE plan launch per batch (the variant state machine does not depend on the track) and ONE
+// execute launch for all tracks.  Each execute CTA owns a tile of one (track, row): it paints the
+// stored intervals that cover the tile's source window into shared memory (no dense scratch in
+// HBM), then every thread produces 4 consecutive output values per step (source span copies,
+// deletion/insertion fills, trailing zeros, reversal for negative strands) and writes them with one
+// 16-byte store.
+#include "gvl_internal.cuh"
+
+namespace gvl {
+
+constexpr int TRK_TILE = 2048;             // output values per execute CTA
+constexpr int TRK_WIN = TRK_TILE + 512;    // source-window values staged in shared memory
+constexpr int TRK_MARGIN = 16;             // window starts a little before the first needed value
+constexpr int TRK_THREADS = 256;
+constexpr int TRK_REC_CAP = 128;
+
+// =====================================================================================
+// plan: shift_and_realign_track_core state machine (src/tracks/mod.rs:224-406), one warp per row
+// =====================================================================================
+struct TrkPlanParams {
+    gvl_sparse_tables tab;
+    const int32_t *regions;
+    const int32_t *shifts;
+    const int64_t *goi;
+    const uint8_t *keep;
+    const int64_t *keep_off;
+    const uint8_t *to_rc;
+    const int32_t *track_lengths;  // [batch]
+    const int64_t *out_offsets;    // [n_work+1]
+    int64_t n_work, ploidy, rec_cap;
+    RowPlan *rows;
+    RecArrays rec;
+    int64_t *words;
+    int32_t *row_len;
+};
+
+constexpr int TPLAN_WARPS = 4;
+
+__global__ void __launch_bounds__(TPLAN_WARPS * 32) trk_plan_kernel(TrkPlanParams P) {
+    const int lane = lane_id();
+    const int64_t k = (int64_t)blockIdx.x * TPLAN_WARPS + (threadIdx.x >> 5);
+    if (k >= P.n_work) return;
+    const int64_t query = k / P.ploidy;
+    const int64_t o_idx = P.goi[k];
+    const int64_t o_s = P.tab.geno_starts[o_idx];
+    const int64_t nvar = imax64(P.tab.geno_stops[o_idx] - o_s, 0);
+    const int64_t q_start = P.regions[query * 3 + 1];
+    const int64_t shift = P.shifts[k];
+    const bool has_keep = (P.keep && P.keep_off);
+    const int64_t keep_base = has_keep ? P.keep_off[k] : 0;
+    const int32_t *__restrict__ gv = P.tab.geno_v_idxs + o_s;
+    const int64_t length = imax64(P.out_offsets[k + 1] - P.out_offsets[k], 0);
+    const int64_t track_n = P.track_lengths[query];
+
+    int64_t rec_off = 0;
+    if (lane == 0) rec_off = (int64_t)atomicAdd((unsigned long long *)&P.words[W_CURSOR], (unsigned long long)(nvar + 1));
+    rec_off = __shfl_sync(0xffffffffu, rec_off, 0);
+    const bool overflow = rec_off + nvar + 1 > P.rec_cap;
+    if (overflow && lane == 0) atomicMax((unsigned long long *)&P.words[W_STATUS], (unsigned long long)(rec_off + nvar + 1));
+
+    TrkState ts;
+    trk_init(ts, shift, length);
+    int64_t n_emit = 0, track0 = 0, prev_resume = 0;
+    bool done = false;
+    for (int64_t base = 0; base < nvar && !done; base += 32) {
+        int64_t i = base + lane;
+        int32_t pos = 0, il = 0;
+        bool kp = false;
+        if (i < nvar) {
+            int32_t vi = gv[i];
+            pos = P.tab.v_starts[vi];
+            il = P.tab.ilens[vi];
+            kp = has_keep ? (P.keep[keep_base + i] != 0) : true;
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, kp);
+        while (mask && !done) {
+            int t = __ffs(mask) - 1;
+            mask &= mask - 1;
+            int64_t p = __shfl_sync(0xffffffffu, pos, t);
+            int64_t l = __shfl_sync(0xffffffffu, il, t);
+            TrkRec r;
+            int act = trk_step(ts, p - q_start, l, r);  // v_rel_pos = v_start - query_start (:264)
+            if (act == STEP_BREAK) {
+                done = true;
+            } else if (act == STEP_EMIT) {
+                if (n_emit == 0) track0 = r.span_src;
+                if (n_emit > 0 && r.span_src != prev_resume) {  // unsorted input: jump record
+                    if (lane == t && !overflow) {
+                        int64_t w = rec_off + n_emit;
+                        P.rec.a[w] = (int32_t)(r.a - (r.v_rel_pos - r.span_src));
+                        P.rec.n[w] = 0;
+                        P.rec.src[w] = 0;
+                        P.rec.resume[w] = (int32_t)r.span_src;
+                        P.rec.vidx[w] = 1;
+                        P.rec.vpos[w] = 0;
+                    }
+                    n_emit++;
+                }
+                if (lane == t && !overflow) {
+                    int64_t w = rec_off + n_emit;
+                    P.rec.a[w] = (int32_t)r.a;
+                    P.rec.n[w] = (int32_t)r.n;
+                    P.rec.src[w] = r.v_diff;
+                    P.rec.resume[w] = (int32_t)r.resume;
+                    P.rec.vidx[w] = (int32_t)r.v_len;
+                    P.rec.vpos[w] = (int32_t)r.v_rel_pos;
+                }
+                n_emit++;
+                prev_resume = r.resume;
+                if (ts.out_idx >= ts.length) done = true;  // :359-361
+            }
+        }
+    }
+    if (nvar == 0) {
+        track0 = 0;  // :240-246: an EMPTY variant list copies track[:length], whatever the shift
+    } else {
+        trk_finish(ts, track_n);
+        if (n_emit == 0) {
+            track0 = ts.track_idx;
+        } else if (ts.track_idx != prev_resume) {
+            if (lane == 0 && !overflow) {
+                int64_t w = rec_off + n_emit;
+                P.rec.a[w] = (int32_t)imin64(ts.out_idx, length);
+                P.rec.n[w] = 0;
+                P.rec.src[w] = 0;
+                P.rec.resume[w] = (int32_t)ts.track_idx;
+                P.rec.vidx[w] = 1;
+                P.rec.vpos[w] = 0;
+            }
+            n_emit++;
+        }
+    }
+    if (lane == 0) {
+        RowPlan rp;
+        rp.out_off = P.out_offsets[k];
+        rp.ref_base = 0;
+        rp.rec_off = rec_off;
+        rp.length = (int32_t)length;
+        rp.contig_len = (int32_t)track_n;
+        rp.lead_pad = 0;
+        rp.ref0 = (int32_t)track0;
+        rp.n_rec = overflow ? 0 : (int32_t)n_emit;
+        rp.rc = (P.to_rc && P.to_rc[k]) ? 1 : 0;
+        rp.diff = 0;
+        rp.q_start = (int32_t)q_start;
+        P.rows[k] = rp;
+        P.row_len[k] = (int32_t)length;
+    }
+}
+
+// identity plan for intervals_to_tracks: one row per query, no records, source window = row
+__global__ void paint_plan_kernel(int64_t n, const int32_t *__restrict__ starts, const int64_t *__restrict__ out_offsets,
+                                  RowPlan *rows, int32_t *row_len) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    int64_t length = imax64(out_offsets[q + 1] - out_offsets[q], 0);
+    RowPlan rp;
+    rp.out_off = out_offsets[q];
+    rp.ref_base = 0;
+    rp.rec_off = 0;
+    rp.length = (int32_t)length;
+    rp.contig_len = (int32_t)length;
+    rp.lead_pad = 0;
+    rp.ref0 = 0;
+    rp.n_rec = 0;
+    rp.rc = 0;
+    rp.diff = 0;
+    rp.q_start = starts[q];
+    rows[q] = rp;
+    row_len[q] = (int32_t)length;
+}
+
+// tile map for TRK_TILE-sized tiles (same scan as the haplotype path, different tile size)
+__global__ void __launch_bounds__(1024) trk_tile_scan_kernel(int64_t n_work, const int32_t *__restrict__ row_len,
+                                                             int64_t *tile_off) {
+    __shared__ int64_t s_tile[32];
+    __shared__ int64_t carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n_work; base += 1024) {
+        int64_t k = base + tid;
+        int64_t til = (k < n_work) ? ((int64_t)row_len[k] + TRK_TILE - 1) / TRK_TILE : 0;
+        int64_t x = til;
+        for (int o = 1; o < 32; o <<= 1) {
+            int64_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_tile[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int64_t w = s_tile[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                int64_t y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            s_tile[lane] = w;
+        }
+        __syncthreads();
+        if (k < n_work) tile_off[k] = carry + (warp ? s_tile[warp - 1] : 0) + x - til;
+        __syncthreads();
+        if (tid == 0) carry += s_tile[31];
+        __syncthreads();
+    }
+    if (tid == 0) tile_off[n_work] = carry;
+}
+
+// =====================================================================================
+// execute
+// =====================================================================================
+constexpr int MAX_TRACKS = 64;
+
+struct TrkDesc {
+    const int32_t *itv_starts;
+    const int32_t *itv_ends;
+    const float *itv_values;
+    const int64_t *itv_offsets;
+    const float *dense;            // non-NULL: dense f32 source windows instead of intervals
+    const int64_t *dense_offsets;  //           i64[n_queries+1] offsets of each query's window
+    int32_t strategy;
+    double param;
+};
+
+struct TrkExecParams {
+    const RowPlan *rows;
+    RecArrays rec;
+    const int64_t *tile_off;   // [n_work+1]
+    int64_t n_work, ploidy;
+    int64_t grid_per_track;    // CTAs per track (upper bound on tiles)
+    int64_t total_per_track;   // output values per track
+    const int64_t *offset_idxs;  // [n_tracks * n_queries]
+    int64_t n_queries;
+    const int64_t *query_seed;   // optional [n_queries]
+    uint64_t base_seed;
+    float *out;
+    const TrkDesc *tracks;       // device array [n_tracks]
+};
+
+struct TrkTileRecs {
+    int32_t a[TRK_REC_CAP + 1];
+    int32_t e[TRK_REC_CAP];
+    int32_t resume[TRK_REC_CAP];
+    int32_t vlen[TRK_REC_CAP];
+    int32_t vrel[TRK_REC_CAP];
+    int32_t vdiff[TRK_REC_CAP];
+};
+
+// value of the painted source track at relative position tp (0 <= tp < track_n), straight from the
+// interval SoA: last interval with start <= q_start + tp, if it also ends after it (intervals are
+// sorted and non-overlapping, src/intervals.rs contract).
+__device__ __forceinline__ float track_at_global(const TrkDesc &T, int64_t lo, int64_t hi, int64_t q_start, int64_t tp) {
+    if (T.dense) return T.dense[lo + tp];  // dense source: `lo` is the window's offset
+    const int64_t g = q_start + tp;
+    int64_t a = lo, b = hi;  // find last i in [lo,hi) with starts[i] <= g
+    while (a < b) {
+        int64_t mid = (a + b) >> 1;
+        if ((int64_t)T.itv_starts[mid] <= g) a = mid + 1; else b = mid;
+    }
+    const int64_t i = a - 1;
+    if (i < lo) return 0.0f;
+    return ((int64_t)T.itv_ends[i] > g) ? T.itv_values[i] : 0.0f;
+}
+
+struct TrkSrc {
+    const float *win;   // shared-memory window
+    int64_t w0, w1;     // window covers source positions [w0, w1)
+    int64_t track_n;
+    const TrkDesc *T;
+    int64_t itv_lo, itv_hi, q_start;
+    __device__ __forceinline__ float at(int64_t tp) const {  // 0 <= tp < track_n expected
+        if (tp >= w0 && tp < w1) return win[tp - w0];
+        if (tp < 0 || tp >= track_n) return 0.0f;  // out of contract in the reference (index panic)
+        return track_at_global(*T, itv_lo, itv_hi, q_start, tp);
+    }
+};
+
+// apply_insertion_fill, src/tracks/mod.rs:87-190, for ONE written value (index i within the write).
+__device__ float insertion_fill_value(const TrkSrc &S, int strategy, double param, int64_t v_len, int64_t v_rel_pos,
+                                      int64_t i, int64_t out_pos, uint64_t base_seed, uint64_t query, uint64_t hap) {
+    if (strategy == GVL_FILL_REPEAT_5P) {
+        return S.at(v_rel_pos);
+    } else if (strategy == GVL_FILL_REPEAT_5P_NORM) {
+        return __fdiv_rn(S.at(v_rel_pos), (float)v_len);  // :115
+    } else if (strategy == GVL_FILL_CONSTANT) {
+        return (float)param;  // :121
+    } else if (strategy == GVL_FILL_FLANK_SAMPLE) {  // :125-137
+        int64_t width = (int64_t)param;
+        int64_t pool_lo = imax64(v_rel_pos - width, 0);
+        int64_t pool_hi = imin64(v_rel_pos + width, S.track_n - 1);
+        uint64_t pool_size = (uint64_t)(pool_hi - pool_lo + 1);
+        uint64_t seed = hash4(base_seed, query, hap, (uint64_t)out_pos);
+        int64_t offset = (int64_t)(seed % pool_size);
+        return S.at(pool_lo + offset);
+    } else {  // GVL_FILL_INTERPOLATE :138-188
+        int64_t order = (int64_t)param;
+        int64_t k = (order + 1 + 1) / 2;
+        int n_anchors = (int)(2 * k);
+        double xs[8], ys[8];
+        for (int j = 0; j < (int)k; j++) {
+            int64_t ri = imax64(v_rel_pos - j, 0);
+            xs[j] = -(double)j;
+            ys[j] = (double)S.at(ri);
+        }
+        for (int j = 0; j < (int)k; j++) {
+            int64_t ri = imin64(v_rel_pos + 1 + j, S.track_n - 1);
+            xs[k + j] = (double)v_len + (double)j;
+            ys[k + j] = (double)S.at(ri);
+        }
+        double x = (double)i;
+        double acc = 0.0;
+        for (int a = 0; a < n_anchors; a++) {
+            double term = ys[a];
+            for (int b = 0; b < n_anchors; b++) {
+                if (b == a) continue;
+                term = __dmul_rn(term, __ddiv_rn(__dsub_rn(x, xs[b]), __dsub_rn(xs[a], xs[b])));
+            }
+            acc = __dadd_rn(acc, term);
+        }
+        return (float)acc;
+    }
+}
+
+__global__ void __launch_bounds__(TRK_THREADS) trk_exec_kernel(TrkExecParams P) {
+    __shared__ TrkTileRecs S;
+    __shared__ float s_win[TRK_WIN];
+    __shared__ int64_t s_lo, s_hi, s_itv_first;
+
+    const int64_t track = blockIdx.x / P.grid_per_track;
+    const int64_t b = blockIdx.x % P.grid_per_track;
+    if (b >= P.tile_off[P.n_work]) return;
+    int64_t row;
+    {
+        int64_t lo = 0, hi = P.n_work;
+        while (hi - lo > 1) {
+            int64_t mid = (lo + hi) >> 1;
+            if (P.tile_off[mid] <= b) lo = mid; else hi = mid;
+        }
+        row = lo;
+    }
+    const int64_t tile = b - P.tile_off[row];
+    const RowPlan rp = P.rows[row];
+    const int32_t L = rp.length;
+    const int32_t t0 = (int32_t)(tile * TRK_TILE);
+    if (t0 >= L) return;
+    const int32_t t1 = min(t0 + TRK_TILE, L);
+    const bool rc = rp.rc != 0;
+    const int32_t h0 = rc ? L - t1 : t0;
+    const int32_t h1 = rc ? L - t0 : t1;
+    const int64_t query = row / P.ploidy;
+    const uint64_t hap = (uint64_t)(row % P.ploidy);
+    const uint64_t qseed = P.query_seed ? (uint64_t)P.query_seed[query] : (uint64_t)query;
+    const TrkDesc T = P.tracks[track];
+    int64_t itv_lo, itv_hi;
+    if (T.dense) {
+        itv_lo = T.dense_offsets[query];
+        itv_hi = T.dense_offsets[query + 1];
+    } else {
+        const int64_t slot = P.offset_idxs[track * P.n_queries + query];
+        itv_lo = T.itv_offsets[slot];
+        itv_hi = T.itv_offsets[slot + 1];
+    }
+    const int64_t track_n = rp.contig_len;
+    const int64_t q_start = rp.q_start;
+    float *__restrict__ out = P.out;
+    const int64_t row_base = track * P.total_per_track + rp.out_off;  // flat index of the row's first value
+
+    const int32_t *__restrict__ ra = P.rec.a + rp.rec_off;
+    if (threadIdx.x < 32) {
+        int64_t r_lo = warp_upper_le(ra, 0, rp.n_rec, h0);
+        int64_t r_hi = warp_upper_le(ra, imax64(r_lo, 0), rp.n_rec, h1 - 1) + 1;
+        if (threadIdx.x == 0) {
+            s_lo = r_lo;
+            s_hi = r_hi;
+        }
+    }
+    __syncthreads();
+    const int64_t r_hi = s_hi;
+    int64_t r = s_lo;
+    int32_t cur = h0;
+
+    while (cur < h1) {
+        const int m_new = (int)imin64(TRK_REC_CAP - 1, r_hi - (r + 1));
+        const int m = m_new + 1;
+        const int32_t seg_end = (r + 1 + m_new < r_hi) ? ra[r + 1 + m_new] : h1;
+        __syncthreads();
+        for (int i = threadIdx.x; i < m; i += TRK_THREADS) {
+            int64_t idx = r + i;
+            if (idx < 0) {
+                S.a[0] = 0;
+                S.e[0] = 0;
+                S.resume[0] = rp.ref0;
+                S.vlen[0] = 1;
+                S.vrel[0] = 0;
+                S.vdiff[0] = 0;
+            } else {
+                int64_t g = rp.rec_off + idx;
+                int32_t a = P.rec.a[g], n = P.rec.n[g];
+                S.a[i] = a;
+                S.e[i] = a + n;
+                S.resume[i] = P.rec.resume[g];
+                S.vlen[i] = P.rec.vidx[g];
+                S.vrel[i] = P.rec.vpos[g];
+                S.vdiff[i] = (int32_t)P.rec.src[g];
+            }
+        }
+        if (threadIdx.x == 0) S.a[m] = INT32_MAX;
+        __syncthreads();
+
+        // ---- source window: starts at the source position of `cur` (minus a margin) ----
+        // source position feeding `cur`: inside the carry record's own values the reads go to
+        // track[v_rel_pos] and then continue at its resume point; otherwise we are in its span.
+        const int64_t src_cur = (cur < S.e[0]) ? imin64((int64_t)S.vrel[0], (int64_t)S.resume[0])
+                                               : (int64_t)S.resume[0] + (cur - S.e[0]);
+        const int64_t w0 = imax64(src_cur - TRK_MARGIN, 0);
+        const int64_t w1 = imin64(w0 + TRK_WIN, track_n);
+        if (T.dense) {
+            for (int64_t i = threadIdx.x; i < w1 - w0; i += TRK_THREADS) s_win[i] = T.dense[itv_lo + w0 + i];
+        } else {
+            for (int i = threadIdx.x; i < TRK_WIN; i += TRK_THREADS) s_win[i] = 0.0f;
+        }
+        if (!T.dense && threadIdx.x < 32) {
+            // first interval whose end is > q_start + w0  (ends are sorted: intervals do not overlap)
+            int64_t first = warp_upper_le(T.itv_ends, itv_lo, itv_hi, (int32_t)imin64(q_start + w0, INT32_MAX)) + 1;
+            if (threadIdx.x == 0) s_itv_first = first;
+        }
+        __syncthreads();
+        if (!T.dense && w1 > w0) {
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+            for (int64_t it = s_itv_first + warp; it < itv_hi; it += TRK_THREADS / 32) {
+                const int64_t s = (int64_t)T.itv_starts[it] - q_start;
+                if (s >= w1) break;  // sorted starts (also covers src/intervals.rs:72-76: start >= length)
+                const int64_t e = (int64_t)T.itv_ends[it] - q_start;
+                const float v = T.itv_values[it];
+                const int64_t ps = imax64(s, w0), pe = imin64(e, w1);
+                for (int64_t x = ps + lane; x < pe; x += 32) s_win[x - w0] = v;
+            }
+        }
+        __syncthreads();
+        TrkSrc src{s_win, w0, w1, track_n, &T, itv_lo, itv_hi, q_start};
+
+        const int32_t jo_lo = rc ? L - seg_end : cur;
+        const int32_t jo_hi = rc ? L - cur : seg_end;
+        const int64_t g0 = (row_base + jo_lo) & ~(int64_t)3;
+        const int32_t n_chunks = (int32_t)((row_base + jo_hi - g0 + 3) >> 2);
+        for (int32_t c = threadIdx.x; c < n_chunks; c += TRK_THREADS) {
+            const int64_t g = g0 + 4 * (int64_t)c;
+            const int32_t j = (int32_t)(g - row_base);
+            float vals[4];
+            bool valid[4];
+            int i = 0;
+            bool have_i = false;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int32_t jj = j + q;
+                valid[q] = (jj >= jo_lo) && (jj < jo_hi);
+                vals[q] = 0.0f;
+                if (!valid[q]) continue;
+                const int32_t p = rc ? (L - 1 - jj) : jj;
+                if (!have_i || p < S.a[i] || p >= S.a[i + 1]) {
+                    int lo = 0, hi = m;
+                    while (hi - lo > 1) {
+                        int mid = (lo + hi) >> 1;
+                        if (S.a[mid] <= p) lo = mid; else hi = mid;
+                    }
+                    i = lo;
+                    have_i = true;
+                }
+                if (p < S.e[i]) {
+                    // values written by the variant itself (:329-354)
+                    const int64_t vrel = S.vrel[i];
+                    if (S.vdiff[i] > 0 && T.strategy != GVL_FILL_REPEAT_5P) {
+                        vals[q] = insertion_fill_value(src, T.strategy, T.param, S.vlen[i], vrel, p - S.a[i], p,
+                                                       P.base_seed, qseed, hap);
+                    } else {
+                        vals[q] = src.at(vrel);
+                    }
+                } else {
+                    const int64_t tp = (int64_t)S.resume[i] + (p - S.e[i]);
+                    vals[q] = (tp < track_n) ? src.at(tp) : 0.0f;  // :381-404 trailing zeros
+                }
+            }
+            if (valid[0] && valid[1] && valid[2] && valid[3]) {
+                *reinterpret_cast<float4 *>(out + g) = make_float4(vals[0], vals[1], vals[2], vals[3]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (valid[q]) out[g + q] = vals[q];
+            }
+        }
+        cur = seg_end;
+        r += m_new;
+    }
+}
+
+__global__ void prng_kernel(uint64_t a, uint64_t b, uint64_t c, uint64_t d, int which, uint64_t *out) {
+    *out = which ? hash4(a, b, c, d) : xorshift64(a);
+}
+
+}  // namespace gvl
+
+using namespace gvl;
+
+static int launch_trk_exec(gvl_ctx *ctx, int64_t n_work, int64_t ploidy, int64_t n_queries, int64_t n_tracks,
+                           const TrkDesc *host_desc, const int64_t *offset_idxs, int64_t total_per_track,
+                           const int64_t *query_seed, uint64_t base_seed, float *out, cudaStream_t st) {
+    if (n_tracks > MAX_TRACKS) return fail(GVL_ERR_ARG, "at most %d tracks per call", MAX_TRACKS);
+    static_assert(sizeof(TrkDesc) * MAX_TRACKS <= GVL_TRK_DESC_BYTES, "descriptor buffer too small");
+    TrkDesc *d_desc = reinterpret_cast<TrkDesc *>(ctx->trk_desc);
+    GVL_CUDA(cudaMemcpyAsync(d_desc, host_desc, sizeof(TrkDesc) * (size_t)n_tracks, cudaMemcpyHostToDevice, st));
+    trk_tile_scan_kernel<<<1, 1024, 0, st>>>(n_work, ctx->trk.row_len, ctx->trk.tile_off);
+    GVL_LAUNCH_CHECK();
+    TrkExecParams P;
+    P.rows = ctx->trk.rows;
+    P.rec = ctx->trk.rec;
+    P.tile_off = ctx->trk.tile_off;
+    P.n_work = n_work;
+    P.ploidy = ploidy;
+    P.grid_per_track = total_per_track / TRK_TILE + n_work;
+    P.total_per_track = total_per_track;
+    P.offset_idxs = offset_idxs;
+    P.n_queries = n_queries;
+    P.query_seed = query_seed;
+    P.base_seed = base_seed;
+    P.out = out;
+    P.tracks = d_desc;
+    const int64_t grid = P.grid_per_track * n_tracks;
+    if (grid > INT32_MAX) return fail(GVL_ERR_ARG, "too many track tiles");
+    trk_exec_kernel<<<(unsigned)grid, TRK_THREADS, 0, st>>>(P);
+    GVL_LAUNCH_CHECK();
+    return GVL_OK;
+}
+
+extern "C" {
+
+static int realign_impl(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_t *regions,
+                        const int32_t *shifts, const int64_t *geno_offset_idx, int64_t batch, int64_t ploidy,
+                        const uint8_t *keep, const int64_t *keep_offsets, const uint8_t *to_rc,
+                        int64_t n_tracks, const gvl_intervals *itv, const int64_t *offset_idxs,
+                        const float *dense, const int64_t *dense_offsets,
+                        const int32_t *track_lengths, const int64_t *out_offsets, int64_t total_per_track,
+                        const int32_t *strategy_ids, const double *params, uint64_t base_seed,
+                        const int64_t *query_seed, int64_t max_records, float *out, gvl_stream stream) {
+    if (!ctx || !tab || !regions || !shifts || !geno_offset_idx || !(itv || dense) || !(offset_idxs || dense) ||
+        !track_lengths || !out_offsets || !strategy_ids || !params)
+        return fail(GVL_ERR_ARG, "gvl_dev_realign_tracks: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    GVL_CUDA(cudaSetDevice(ctx->device));
+    const int64_t n_work = batch * ploidy;
+    if (n_work == 0 || n_tracks == 0 || total_per_track == 0) return GVL_OK;
+    if (!out || ((uintptr_t)out & 15)) return fail(GVL_ERR_ARG, "gvl_dev_realign_tracks: out must be 16-byte aligned");
+    int rc;
+    if ((rc = ensure_rows(ctx, ctx->trk, n_work))) return rc;
+    if ((rc = ensure_records(ctx, ctx->trk, max_records + n_work))) return rc;
+    int64_t *words = ctx->dev_words + W_COUNT;
+    GVL_CUDA(cudaMemsetAsync(words, 0, sizeof(int64_t) * 4, st));
+    TrkPlanParams PP;
+    PP.tab = *tab;
+    PP.regions = regions;
+    PP.shifts = shifts;
+    PP.goi = geno_offset_idx;
+    PP.keep = keep;
+    PP.keep_off = keep_offsets;
+    PP.to_rc = to_rc;
+    PP.track_lengths = track_lengths;
+    PP.out_offsets = out_offsets;
+    PP.n_work = n_work;
+    PP.ploidy = ploidy;
+    PP.rec_cap = ctx->trk.rec_cap;
+    PP.rows = ctx->trk.rows;
+    PP.rec = ctx->trk.rec;
+    PP.words = words;
+    PP.row_len = ctx->trk.row_len;
+    trk_plan_kernel<<<(unsigned)((n_work + TPLAN_WARPS - 1) / TPLAN_WARPS), TPLAN_WARPS * 32, 0, st>>>(PP);
+    GVL_LAUNCH_CHECK();
+    TrkDesc desc[MAX_TRACKS];
+    if (n_tracks > MAX_TRACKS) return fail(GVL_ERR_ARG, "at most %d tracks per call", MAX_TRACKS);
+    for (int64_t t = 0; t < n_tracks; t++) {
+        desc[t].itv_starts = itv ? itv[t].itv_starts : nullptr;
+        desc[t].itv_ends = itv ? itv[t].itv_ends : nullptr;
+        desc[t].itv_values = itv ? itv[t].itv_values : nullptr;
+        desc[t].itv_offsets = itv ? itv[t].itv_offsets : nullptr;
+        desc[t].dense = dense;
+        desc[t].dense_offsets = dense_offsets;
+        desc[t].strategy = strategy_ids[t];
+        desc[t].param = params[t];
+        if (strategy_ids[t] < 0 || strategy_ids[t] > GVL_FILL_INTERPOLATE)
+            return fail(GVL_ERR_ARG, "unknown insertion-fill strategy %d", strategy_ids[t]);
+        if (strategy_ids[t] == GVL_FILL_INTERPOLATE && !(params[t] >= 1 && params[t] <= 3))
+            return fail(GVL_ERR_ARG, "Interpolate order must be 1, 2 or 3");
+    }
+    return launch_trk_exec(ctx, n_work, ploidy, batch, n_tracks, desc, offset_idxs, total_per_track, query_seed,
+                           base_seed, out, st);
+}
+
+int gvl_dev_realign_tracks(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_t *regions,
+                           const int32_t *shifts, const int64_t *geno_offset_idx, int64_t batch, int64_t ploidy,
+                           const uint8_t *keep, const int64_t *keep_offsets, const uint8_t *to_rc,
+                           int64_t n_tracks, const gvl_intervals *itv, const int64_t *offset_idxs,
+                           const int32_t *track_lengths, const int64_t *out_offsets, int64_t total_per_track,
+                           const int32_t *strategy_ids, const double *params, uint64_t base_seed,
+                           const int64_t *query_seed, int64_t max_records, float *out, gvl_stream stream) {
+    if (!itv || !offset_idxs) return fail(GVL_ERR_ARG, "gvl_dev_realign_tracks: NULL argument");
+    return realign_impl(ctx, tab, regions, shifts, geno_offset_idx, batch, ploidy, keep, keep_offsets, to_rc, n_tracks,
+                        itv, offset_idxs, nullptr, nullptr, track_lengths, out_offsets, total_per_track, strategy_ids,
+                        params, base_seed, query_seed, max_records, out, stream);
+}
+
+int gvl_dev_shift_and_realign_tracks(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_t *regions,
+                                     const int32_t *shifts, const int64_t *geno_offset_idx, int64_t batch,
+                                     int64_t ploidy, const uint8_t *keep, const int64_t *keep_offsets,
+                                     const uint8_t *to_rc, const float *tracks, const int64_t *track_offsets,
+                                     const int32_t *track_lengths, const int64_t *out_offsets, int64_t total,
+                                     int32_t strategy_id, double param, uint64_t base_seed,
+                                     const int64_t *query_seed, int64_t max_records, float *out, gvl_stream stream) {
+    if (!tracks || !track_offsets) return fail(GVL_ERR_ARG, "gvl_dev_shift_and_realign_tracks: NULL argument");
+    return realign_impl(ctx, tab, regions, shifts, geno_offset_idx, batch, ploidy, keep, keep_offsets, to_rc, 1, nullptr,
+                        nullptr, tracks, track_offsets, track_lengths, out_offsets, total, &strategy_id, &param,
+                        base_seed, query_seed, max_records, out, stream);
+}
+
+int gvl_dev_intervals_to_tracks(gvl_ctx *ctx, const gvl_intervals *itv, const int64_t *offset_idxs,
+                                const int32_t *starts, int64_t n_queries, const int64_t *out_offsets,
+                                int64_t total, float *out, gvl_stream stream) {
+    if (!ctx || !itv || !offset_idxs || !starts || !out_offsets)
+        return fail(GVL_ERR_ARG, "gvl_dev_intervals_to_tracks: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    GVL_CUDA(cudaSetDevice(ctx->device));
+    if (n_queries == 0 || total == 0) return GVL_OK;
+    if (!out || ((uintptr_t)out & 15)) return fail(GVL_ERR_ARG, "gvl_dev_intervals_to_tracks: out must be 16-byte aligned");
+    int rc;
+    if ((rc = ensure_rows(ctx, ctx->trk, n_queries))) return rc;
+    if ((rc = ensure_records(ctx, ctx->trk, 1))) return rc;
+    paint_plan_kernel<<<(unsigned)((n_queries + 255) / 256), 256, 0, st>>>(n_queries, starts, out_offsets, ctx->trk.rows,
+                                                                            ctx->trk.row_len);
+    GVL_LAUNCH_CHECK();
+    TrkDesc desc;
+    desc.itv_starts = itv->itv_starts;
+    desc.itv_ends = itv->itv_ends;
+    desc.itv_values = itv->itv_values;
+    desc.itv_offsets = itv->itv_offsets;
+    desc.dense = nullptr;
+    desc.dense_offsets = nullptr;
+    desc.strategy = GVL_FILL_REPEAT_5P;
+    desc.param = 0.0;
+    return launch_trk_exec(ctx, n_queries, 1, n_queries, 1, &desc, offset_idxs, total, nullptr, 0, out, st);
+}
+
+static int run_prng(gvl_ctx *ctx, uint64_t a, uint64_t b, uint64_t c, uint64_t d, int which, uint64_t *out) {
+    if (!ctx || !out) return fail(GVL_ERR_ARG, "gvl_debug prng: NULL argument");
+    GVL_CUDA(cudaSetDevice(ctx->device));
+    uint64_t *dv = (uint64_t *)(ctx->dev_words + 2 * W_COUNT - 1);
+    prng_kernel<<<1, 1, 0, ctx->own_stream>>>(a, b, c, d, which, dv);
+    GVL_LAUNCH_CHECK();
+    GVL_CUDA(cudaMemcpyAsync(out, dv, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->own_stream));
+    GVL_CUDA(cudaStreamSynchronize(ctx->own_stream));
+    return GVL_OK;
+}
+
+int gvl_debug_hash4(gvl_ctx *ctx, uint64_t a, uint64_t b, uint64_t c, uint64_t d, uint64_t *out) {
+    return run_prng(ctx, a, b, c, d, 1, out);
+}
+
+int gvl_debug_xorshift64(gvl_ctx *ctx, uint64_t x, uint64_t *out) { return run_prng(ctx, x, 0, 0, 0, 0, out); }
+
+}  // extern "C"

@@ -142,27 +142,42 @@ int gvl_dev_get_diffs_sparse(gvl_ctx *ctx, const gvl_sparse_tables *tab, const i
  * intervals_and_realign_track_fused (src/ffi/mod.rs:2553-2672) for ALL tracks of a batch in one
  * plan launch + one execute launch: paints stored intervals (src/intervals.rs:19-126) and
  * realigns them to haplotype coordinates (src/tracks/mod.rs:224-406) without the dense scratch.
- *   n_tracks             tracks realigned in this call
+ *   n_tracks             tracks realigned in this call (<= 64)
  *   itv[t]               HOST array of n_tracks descriptors holding DEVICE pointers
  *   offset_idxs          device i64[n_tracks*b]: interval slot per (track, query) (dataset idx for
  *                        SAMPLE tracks, region idx for ANNOT tracks, _reconstruct.py:233-236)
  *   track_lengths        device i32[b]: source window length per query (_reconstruct.py:191)
- *   out_offsets          device i64[b*p+1] per-track row offsets (same for every track)
+ *   out_offsets          device i64[b*p+1] per-track row offsets (same for every track), input
+ *   total_per_track      out_offsets[b*p] (host value)
  *   strategy_ids/params  HOST arrays, one per track (python/genvarloader/_dataset/_insertion_fill.py:89)
- *   out                  device f32[n_tracks * out_offsets[-1]], track-major (_reconstruct.py:238)
+ *   query_seed           optional device i64[b]: global batch row used as the FlankSample seed
+ *                        component when one logical batch is split over several calls / GPUs
+ *                        (src/tracks/mod.rs:696-702); NULL = local row index
+ *   out                  device f32[n_tracks * total_per_track], track-major (_reconstruct.py:238)
  */
 int gvl_dev_realign_tracks(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_t *regions,
                            const int32_t *shifts, const int64_t *geno_offset_idx, int64_t batch, int64_t ploidy,
                            const uint8_t *keep, const int64_t *keep_offsets, const uint8_t *to_rc,
                            int64_t n_tracks, const gvl_intervals *itv, const int64_t *offset_idxs,
                            const int32_t *track_lengths, const int64_t *out_offsets, int64_t total_per_track,
-                           int64_t max_out_len, const int32_t *strategy_ids, const double *params,
-                           uint64_t base_seed, int64_t max_records, float *out, gvl_stream stream);
+                           const int32_t *strategy_ids, const double *params, uint64_t base_seed,
+                           const int64_t *query_seed, int64_t max_records, float *out, gvl_stream stream);
 
-/* intervals_to_tracks on device (src/ffi/mod.rs:190-201): out f32[out_offsets[n]] fully written. */
+/* shift_and_realign_tracks_sparse on device (src/ffi/mod.rs:2439-2458): ONE track whose source is
+ * a dense f32 window per query (`tracks` ragged by `track_offsets` i64[b+1]) instead of intervals.
+ * track_lengths[q] = track_offsets[q+1]-track_offsets[q] as device i32[b]. */
+int gvl_dev_shift_and_realign_tracks(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_t *regions,
+                                     const int32_t *shifts, const int64_t *geno_offset_idx, int64_t batch,
+                                     int64_t ploidy, const uint8_t *keep, const int64_t *keep_offsets,
+                                     const uint8_t *to_rc, const float *tracks, const int64_t *track_offsets,
+                                     const int32_t *track_lengths, const int64_t *out_offsets, int64_t total,
+                                     int32_t strategy_id, double param, uint64_t base_seed,
+                                     const int64_t *query_seed, int64_t max_records, float *out, gvl_stream stream);
+
+/* intervals_to_tracks on device (src/ffi/mod.rs:190-201): out f32[total = out_offsets[n]] fully written. */
 int gvl_dev_intervals_to_tracks(gvl_ctx *ctx, const gvl_intervals *itv, const int64_t *offset_idxs,
                                 const int32_t *starts, int64_t n_queries, const int64_t *out_offsets,
-                                int64_t total, int64_t max_len, float *out, gvl_stream stream);
+                                int64_t total, float *out, gvl_stream stream);
 
 /* ---- host layer: reference-shaped entries (host pointers in, host pointers out) ------ */
 /* Upload (or refresh) a static array and cache it by host address; later gvl_* calls that see
@@ -219,6 +234,14 @@ int gvl_intervals_and_realign_track_fused(
     const int64_t *offset_idxs, const int32_t *itv_starts, const int32_t *itv_ends, const float *itv_values,
     int64_t n_itv, const int64_t *itv_offsets, int64_t n_slots, const int64_t *track_offsets, const double *params,
     int64_t strategy_id, uint64_t base_seed, const uint8_t *keep, const int64_t *keep_offsets, const uint8_t *to_rc);
+
+/* shift_and_realign_tracks_sparse, src/ffi/mod.rs:2439-2458 (dense source, writes `out` in place). */
+int gvl_shift_and_realign_tracks_sparse(
+    gvl_ctx *ctx, float *out, const int64_t *out_offsets, const int32_t *regions, const int32_t *shifts,
+    const int64_t *geno_offset_idx, int64_t batch, int64_t ploidy, const int32_t *geno_v_idxs, int64_t n_geno_v,
+    const int64_t *geno_offsets, int64_t n_geno, const int32_t *v_starts, const int32_t *ilens, int64_t n_variants,
+    const float *tracks, const int64_t *track_offsets, const double *params, const uint8_t *keep,
+    const int64_t *keep_offsets, int64_t strategy_id, uint64_t base_seed);
 
 /* intervals_to_tracks, src/ffi/mod.rs:190-201.  out: host f32[out_offsets[n_queries]]. */
 int gvl_intervals_to_tracks(gvl_ctx *ctx, const int64_t *offset_idxs, const int32_t *starts, int64_t n_queries,

@@ -1,0 +1,165 @@
+"""Device-resident engine: static tables in HBM as torch tensors + thin calls into the gvl_dev_*
+layer of include/gvl_b200.h on torch's current CUDA stream.
+
+torch is plumbing here (device memory, streams); all compute is in the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _ffi
+from ._ffi import (MODE_ANNOTATED, MODE_ONEHOT, MODE_ONEHOT_CF, MODE_U8, Intervals, SparseTables, c_i32, c_i64, c_u8,
+                   c_u64, c_vp, check, lib, ptr)
+
+MODES = {"haplotypes": MODE_U8, "u8": MODE_U8, "onehot": MODE_ONEHOT, "onehot_cf": MODE_ONEHOT_CF,
+         "annotated": MODE_ANNOTATED}
+
+
+def _stream() -> c_vp:
+    return c_vp(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev(a, dtype, device, pad: int = 0) -> torch.Tensor:
+    """Upload a host array (numpy / memmap) as a device tensor, optionally with `pad` spare elements
+    (the reference buffer must be readable up to the next multiple of 16 bytes)."""
+    a = np.ascontiguousarray(a, dtype)
+    t = torch.empty(a.size + pad, dtype=torch.from_numpy(np.empty(0, dtype)).dtype, device=device)
+    if pad:
+        t[a.size:].zero_()
+    if a.size:
+        t[: a.size].copy_(torch.from_numpy(a.reshape(-1)), non_blocking=False)
+    return t
+
+
+class Engine:
+    """Static tables of one dataset replica on one GPU (SVAR1-style: reference + variant table +
+    sparse genotype CSR [+ interval tracks]) -- the device-side counterpart of `_HapsFfiStatic`
+    (python/genvarloader/_dataset/_haps.py:233-247) plus the memmapped genotype/interval arrays."""
+
+    def __init__(self, device, reference, ref_offsets, v_starts, ilens, alt_alleles, alt_offsets, geno_v_idxs,
+                 geno_offsets, pad_char: int = ord("N")):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("genvarloader_b200 needs a CUDA device; there is no CPU path")
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", idx)
+        self.ctx = _ffi.Ctx(idx)
+        self.pad_char = int(pad_char)
+        go = np.asarray(geno_offsets)
+        if go.ndim == 1:
+            go = np.stack([go[:-1], go[1:]])
+        self.geno_offsets_host = np.ascontiguousarray(go, np.int64)  # O(batch) capacity sums stay on the host
+        with torch.cuda.device(self.device):
+            self.ref = _dev(reference, np.uint8, self.device, pad=32)
+            self.ref_offsets = _dev(ref_offsets, np.int64, self.device)
+            self.v_starts = _dev(v_starts, np.int32, self.device)
+            self.ilens = _dev(ilens, np.int32, self.device)
+            self.alt_alleles = _dev(alt_alleles, np.uint8, self.device, pad=16)
+            self.alt_offsets = _dev(alt_offsets, np.int64, self.device)
+            self.geno_v_idxs = _dev(geno_v_idxs, np.int32, self.device, pad=4)
+            self.geno_starts = _dev(self.geno_offsets_host[0], np.int64, self.device)
+            self.geno_stops = _dev(self.geno_offsets_host[1], np.int64, self.device)
+        self.n_contigs = int(np.asarray(ref_offsets).size - 1)
+        self.tab = SparseTables(
+            ptr(self.ref), ptr(self.ref_offsets), self.n_contigs, ptr(self.v_starts), ptr(self.ilens),
+            ptr(self.alt_alleles), ptr(self.alt_offsets), int(self.v_starts.numel()), ptr(self.geno_v_idxs),
+            ptr(self.geno_starts), ptr(self.geno_stops), int(self.geno_starts.numel()))
+        self.tracks: dict[str, tuple] = {}
+        self._n_work = 0
+        self._fixed = -1
+
+    def fork(self) -> "Engine":
+        """A second planning context (own workspace) over the SAME device tables -- one per pipeline
+        slot, so several batches can be in flight on different streams."""
+        e = object.__new__(Engine)
+        e.__dict__.update(self.__dict__)
+        e.ctx = _ffi.Ctx(self.device.index)
+        e._n_work, e._fixed = 0, -1
+        return e
+
+    # ------------------------------------------------------------------ tracks
+    def add_track(self, name: str, itv_starts, itv_ends, itv_values, itv_offsets) -> None:
+        with torch.cuda.device(self.device):
+            t = (_dev(itv_starts, np.int32, self.device, pad=4), _dev(itv_ends, np.int32, self.device, pad=4),
+                 _dev(itv_values, np.float32, self.device, pad=4), _dev(itv_offsets, np.int64, self.device))
+        self.tracks[name] = t + (Intervals(ptr(t[0]), ptr(t[1]), ptr(t[2]), ptr(t[3]), int(t[3].numel() - 1)),)
+
+    # ------------------------------------------------------------------ capacity
+    def max_records(self, geno_offset_idx_host: np.ndarray) -> int:
+        """Upper bound on the summed per-row variant counts (host O(batch) gather)."""
+        g = np.asarray(geno_offset_idx_host).reshape(-1)
+        d = self.geno_offsets_host[1, g] - self.geno_offsets_host[0, g]
+        return int(np.maximum(d, 0).sum())
+
+    # ------------------------------------------------------------------ haplotypes
+    def plan(self, regions: torch.Tensor, shifts: torch.Tensor, geno_offset_idx: torch.Tensor, output_length: int,
+             max_records: int, keep=None, keep_offsets=None, to_rc=None, out_offsets=None, diffs=None):
+        """gvl_dev_hap_plan.  All tensors live on this engine's device; nothing synchronises."""
+        batch, ploidy = geno_offset_idx.shape
+        n_work = batch * ploidy
+        if out_offsets is None:
+            out_offsets = torch.empty(n_work + 1, dtype=torch.int64, device=self.device)
+        check(lib.gvl_dev_hap_plan(self.ctx.handle, C.byref(self.tab), ptr(regions), ptr(shifts), ptr(geno_offset_idx),
+                                   c_i64(batch), c_i64(ploidy), ptr(keep), ptr(keep_offsets), ptr(to_rc),
+                                   c_i64(int(output_length)), c_i64(int(max_records)), ptr(out_offsets), ptr(diffs),
+                                   _stream()))
+        self._n_work, self._fixed = n_work, int(output_length)
+        return out_offsets
+
+    def total(self) -> int:
+        t = c_i64(0)
+        check(lib.gvl_dev_hap_total(self.ctx.handle, _stream(), C.byref(t)))
+        return int(t.value)
+
+    def execute(self, mode: str = "haplotypes", out=None, annot_v=None, annot_pos=None):
+        """gvl_dev_hap_exec into (pre)allocated tensors.  Returns the flat buffers."""
+        m = MODES[mode]
+        total = self.total()
+        mult = 4 if m in (MODE_ONEHOT, MODE_ONEHOT_CF) else 1
+        if out is None:
+            out = torch.empty(total * mult, dtype=torch.uint8, device=self.device)
+        if m == MODE_ANNOTATED:
+            if annot_v is None:
+                annot_v = torch.empty(total, dtype=torch.int32, device=self.device)
+            if annot_pos is None:
+                annot_pos = torch.empty(total, dtype=torch.int32, device=self.device)
+        check(lib.gvl_dev_hap_exec(self.ctx.handle, C.byref(self.tab), C.c_int(m), c_u8(self.pad_char), ptr(out),
+                                   ptr(annot_v), ptr(annot_pos), _stream()))
+        if m == MODE_ANNOTATED:
+            return out, annot_v, annot_pos
+        return out
+
+    def get_diffs(self, geno_offset_idx, q_starts=None, q_ends=None, keep=None, keep_offsets=None, clipped=True):
+        n_q, ploidy = geno_offset_idx.shape
+        diffs = torch.empty((n_q, ploidy), dtype=torch.int32, device=self.device)
+        check(lib.gvl_dev_get_diffs_sparse(self.ctx.handle, C.byref(self.tab), ptr(geno_offset_idx), c_i64(n_q),
+                                           c_i64(ploidy), ptr(keep), ptr(keep_offsets), ptr(q_starts), ptr(q_ends),
+                                           C.c_int(1 if clipped else 0), ptr(diffs), _stream()))
+        return diffs
+
+    # ------------------------------------------------------------------ tracks
+    def realign_tracks(self, names, regions, shifts, geno_offset_idx, offset_idxs, track_lengths, out_offsets,
+                       total_per_track: int, strategy_ids, params, base_seed: int, max_records: int, keep=None,
+                       keep_offsets=None, to_rc=None, query_seed=None, out=None):
+        """gvl_dev_realign_tracks: all `names` in one plan + one execute launch.
+        offset_idxs: int64 (n_tracks, batch) device; out: float32 (n_tracks * total_per_track,) track-major."""
+        batch, ploidy = geno_offset_idx.shape
+        n_tracks = len(names)
+        itv = (Intervals * n_tracks)(*[self.tracks[n][4] for n in names])
+        sid = (c_i32 * n_tracks)(*[int(s) for s in strategy_ids])
+        par = (C.c_double * n_tracks)(*[float(p) for p in params])
+        if out is None:
+            out = torch.empty(n_tracks * total_per_track, dtype=torch.float32, device=self.device)
+        check(lib.gvl_dev_realign_tracks(
+            self.ctx.handle, C.byref(self.tab), ptr(regions), ptr(shifts), ptr(geno_offset_idx), c_i64(batch),
+            c_i64(ploidy), ptr(keep), ptr(keep_offsets), ptr(to_rc), c_i64(n_tracks), itv, ptr(offset_idxs),
+            ptr(track_lengths), ptr(out_offsets), c_i64(int(total_per_track)), sid, par, c_u64(int(base_seed)),
+            ptr(query_seed), c_i64(int(max_records)), ptr(out), _stream()))
+        return out
+
+    def check(self) -> None:
+        """Synchronise and surface device-side status flags (workspace overflow)."""
+        self.ctx.check(torch.cuda.current_stream().cuda_stream)

@@ -286,6 +286,7 @@ struct HapExecParams {
     int64_t n_work;
     int64_t tiles_per_row;    // >0: fixed-length plan
     const int64_t *tile_off;  // ragged plan: first tile of each row
+    int32_t tile_len;         // haplotype positions per CTA (multiple of EXEC_UNIT)
     uint8_t *out;
     int32_t *annot_v;
     int32_t *annot_pos;
@@ -293,7 +294,7 @@ struct HapExecParams {
 };
 
 struct TileRecs {
-    int32_t a[REC_CAP + 1];       // ALT start (output/hap coordinate); a[m+1] sentinel
+    int32_t a[REC_CAP + 1];       // ALT start (haplotype coordinate); a[m] sentinel
     int32_t e[REC_CAP];           // ALT end = start of the following reference span
     int32_t resume[REC_CAP];      // reference position at e[]
     int64_t src[REC_CAP];         // ALT source (offset into alt_alleles), ALT_PAD for the leading pad
@@ -301,8 +302,15 @@ struct TileRecs {
     int32_t vpos[REC_CAP];
 };
 
-// complement 4 packed bases: A<->T (xor 0x15), C<->G (xor 0x04), everything else unchanged
+// complement one base: A<->T (xor 0x15), C<->G (xor 0x04), everything else unchanged
 // (src/reverse.rs:45-53).
+__device__ __forceinline__ uint32_t comp1(uint32_t b) {
+    uint32_t at = (b == 'A' || b == 'T') ? 0x15u : 0u;
+    uint32_t cg = (b == 'C' || b == 'G') ? 0x04u : 0u;
+    return b ^ at ^ cg;
+}
+
+// complement 4 packed bases (SWAR form of comp1)
 __device__ __forceinline__ uint32_t comp4(uint32_t v) {
     uint32_t at = __vcmpeq4(v, 0x41414141u) | __vcmpeq4(v, 0x54545454u);
     uint32_t cg = __vcmpeq4(v, 0x43434343u) | __vcmpeq4(v, 0x47474747u);
@@ -314,36 +322,15 @@ __device__ __forceinline__ uint32_t onehot1(uint32_t b) {
     return (b == 'A' ? 1u : 0u) | (b == 'C' ? 0x100u : 0u) | (b == 'G' ? 0x10000u : 0u) | (b == 'T' ? 0x1000000u : 0u);
 }
 
-// one-hot of 4 packed bases -> 4 words (word i = base i).
-__device__ __forceinline__ uint4 onehot4(uint32_t v) {
-    uint32_t mA = __vcmpeq4(v, 0x41414141u) & 0x01010101u;
-    uint32_t mC = __vcmpeq4(v, 0x43434343u) & 0x01010101u;
-    uint32_t mG = __vcmpeq4(v, 0x47474747u) & 0x01010101u;
-    uint32_t mT = __vcmpeq4(v, 0x54545454u) & 0x01010101u;
-    // 4x4 byte transpose: word i = [mA.b_i, mC.b_i, mG.b_i, mT.b_i]
-    uint32_t ac_lo = __byte_perm(mA, mC, 0x5140);  // A0 C0 A1 C1
-    uint32_t ac_hi = __byte_perm(mA, mC, 0x7362);  // A2 C2 A3 C3
-    uint32_t gt_lo = __byte_perm(mG, mT, 0x5140);
-    uint32_t gt_hi = __byte_perm(mG, mT, 0x7362);
-    uint4 r;
-    r.x = __byte_perm(ac_lo, gt_lo, 0x5410);
-    r.y = __byte_perm(ac_lo, gt_lo, 0x7632);
-    r.z = __byte_perm(ac_hi, gt_hi, 0x5410);
-    r.w = __byte_perm(ac_hi, gt_hi, 0x7632);
-    return r;
-}
-
 struct PosInfo {
     uint32_t byte;
     int32_t av, ap;
 };
 
 // Generic (slow-path) resolution of one haplotype position against the staged records.
-template <bool ANNOT>
 __device__ __forceinline__ PosInfo resolve_pos(const TileRecs &S, int m, int32_t p, const RowPlan &rp,
                                                const HapExecParams &P) {
-    // entry i = last with a[i] <= p (entry 0 always qualifies)
-    int lo = 0, hi = m;  // answer in [0, m-1]
+    int lo = 0, hi = m;  // entry i = last with a[i] <= p (entry 0 always qualifies)
     while (hi - lo > 1) {
         int mid = (lo + hi) >> 1;
         if (S.a[mid] <= p) lo = mid; else hi = mid;
@@ -376,11 +363,16 @@ __device__ __forceinline__ PosInfo resolve_pos(const TileRecs &S, int m, int32_t
     return r;
 }
 
+constexpr int COUNT_MAX = 2048;  // rows with more records locate their tile range by 32-ary search
+
 template <int MODE>
 __global__ void __launch_bounds__(EXEC_THREADS) hap_exec_kernel(HapExecParams P) {
-    __shared__ TileRecs S;
-    __shared__ int64_t s_lo, s_hi;
     constexpr bool ANNOT = (MODE == GVL_MODE_ANNOTATED);
+    constexpr bool OH = (MODE == GVL_MODE_ONEHOT || MODE == GVL_MODE_ONEHOT_CF);
+    __shared__ TileRecs S;
+    __shared__ uint32_t s_lut[OH ? 512 : 1];  // [0,256): one-hot(b); [256,512): one-hot(complement(b))
+    __shared__ int s_cnt[2];
+    __shared__ int64_t s_lo, s_hi;
 
     // ---- tile -> (row, tile-in-row) ----
     int64_t row, tile;
@@ -401,20 +393,49 @@ __global__ void __launch_bounds__(EXEC_THREADS) hap_exec_kernel(HapExecParams P)
     }
     const RowPlan rp = P.rows[row];
     const int32_t L = rp.length;
-    const int32_t t0 = (int32_t)(tile * TILE);
-    if (t0 >= L) return;
-    const int32_t t1 = min(t0 + TILE, L);
+    // tiles are cut in HAPLOTYPE coordinates; a reversed row writes them back to front
+    const int64_t h0_64 = tile * (int64_t)P.tile_len;
+    if (h0_64 >= L) return;
+    const int32_t h0 = (int32_t)h0_64;
+    const int32_t h1 = (int32_t)imin64(h0_64 + P.tile_len, L);
     const bool rc = rp.rc != 0;
-    // haplotype-coordinate range covered by this output tile
-    const int32_t h0 = rc ? L - t1 : t0;
-    const int32_t h1 = rc ? L - t0 : t1;
+    const int tid = threadIdx.x;
 
+    if (OH) {
+        for (int i = tid; i < 512; i += EXEC_THREADS) {
+            uint32_t b = i & 255;
+            s_lut[i] = onehot1(i >= 256 ? comp1(b) : b);
+        }
+    }
+    if (tid < 2) s_cnt[tid] = 0;
+    __syncthreads();
+
+    // ---- records of this tile: r_lo = last with a <= h0 (or -1), r_hi = first with a >= h1 ----
     const int32_t *__restrict__ ra = P.rec.a + rp.rec_off;
-    // r_lo = last record with a <= h0 (or -1); r_hi = first record with a >= h1
-    if (threadIdx.x < 32) {
+    if (rp.n_rec <= COUNT_MAX) {
+        int c0 = 0, c1 = 0;  // sorted array: counts are indices
+        for (int i = tid; i < rp.n_rec; i += EXEC_THREADS) {
+            int32_t a = ra[i];
+            c0 += (a <= h0);
+            c1 += (a < h1);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+            c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+        }
+        if ((tid & 31) == 0 && (c0 | c1)) {
+            atomicAdd(&s_cnt[0], c0);
+            atomicAdd(&s_cnt[1], c1);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            s_lo = (int64_t)s_cnt[0] - 1;
+            s_hi = s_cnt[1];
+        }
+    } else if (tid < 32) {
         int64_t r_lo = warp_upper_le(ra, 0, rp.n_rec, h0);
         int64_t r_hi = warp_upper_le(ra, imax64(r_lo, 0), rp.n_rec, h1 - 1) + 1;
-        if (threadIdx.x == 0) {
+        if (tid == 0) {
             s_lo = r_lo;
             s_hi = r_hi;
         }
@@ -430,7 +451,7 @@ __global__ void __launch_bounds__(EXEC_THREADS) hap_exec_kernel(HapExecParams P)
         const int m = m_new + 1;
         const int32_t seg_end = (r + 1 + m_new < r_hi) ? ra[r + 1 + m_new] : h1;
         __syncthreads();  // previous pass finished reading S
-        for (int i = threadIdx.x; i < m; i += EXEC_THREADS) {
+        for (int i = tid; i < m; i += EXEC_THREADS) {
             int64_t idx = r + i;
             if (idx < 0) {  // virtual record: leading pad, then reference from ref0
                 S.a[0] = 0;
@@ -452,93 +473,118 @@ __global__ void __launch_bounds__(EXEC_THREADS) hap_exec_kernel(HapExecParams P)
                 }
             }
         }
-        if (threadIdx.x == 0) S.a[m] = INT32_MAX;
+        if (tid == 0) S.a[m] = INT32_MAX;
         __syncthreads();
 
         // ---- output range of this pass, chunked by 4 on the GLOBAL flat index ----
         const int32_t jo_lo = rc ? L - seg_end : cur;
         const int32_t jo_hi = rc ? L - cur : seg_end;
         const int64_t g0 = (rp.out_off + jo_lo) & ~(int64_t)3;
-        const int32_t n_chunks = (int32_t)((rp.out_off + jo_hi - g0 + 3) >> 2);
-        for (int32_t c = threadIdx.x; c < n_chunks; c += EXEC_THREADS) {
-            const int64_t g = g0 + 4 * (int64_t)c;
-            const int32_t j = (int32_t)(g - rp.out_off);  // row-relative output position of the chunk
-            const bool full = (j >= jo_lo) && (j + 4 <= jo_hi);
-            uint32_t v = 0;  // 4 output bases, byte i = output position j+i
-            int32_t av[4], ap[4];
-            bool fast = false;
-            if (full) {
-                const int32_t p0 = rc ? (L - 4 - j) : j;  // lowest haplotype position of the chunk
-                int lo = 0, hi = m;
-                while (hi - lo > 1) {
-                    int mid = (lo + hi) >> 1;
-                    if (S.a[mid] <= p0) lo = mid; else hi = mid;
-                }
-                const int i = lo;
-                const int64_t rpos = (int64_t)S.resume[i] + (p0 - S.e[i]);
-                if (p0 >= S.e[i] && p0 + 3 < S.a[i + 1] && rpos + 3 < rp.contig_len) {
-                    fast = true;
-                    const int64_t abs_ = rp.ref_base + rpos;
-                    const uint32_t *w = reinterpret_cast<const uint32_t *>(P.ref + (abs_ & ~(int64_t)3));
-                    const unsigned sh = (unsigned)(abs_ & 3) * 8u;
-                    uint32_t w0 = __ldg(w);
-                    uint32_t w1 = sh ? __ldg(w + 1) : 0u;
-                    v = __funnelshift_r(w0, w1, sh);
-                    if (rc) v = comp4(__byte_perm(v, 0, 0x0123));
-                    if (ANNOT) {
+        const int32_t j0 = (int32_t)(g0 - rp.out_off);  // row-relative position of chunk 0 (may be < jo_lo)
+        const int32_t n_chunks = (jo_hi - j0 + 3) >> 2;
+        int ic = rc ? (m - 1) : 0;  // record cursor: chunks are visited in monotone haplotype order
+        const uint8_t *__restrict__ refrow = P.ref + rp.ref_base;
+
+        for (int32_t cb = 0; cb < n_chunks; cb += 4 * EXEC_THREADS) {
+            uint32_t w0[4], w1[4];
+            int32_t rp32[4];
+            int st[4];  // 0 nothing, 1 fast (reference-only chunk), 2 slow
+            // ---- phase 1: classify the 4 chunks of this thread and issue their loads ----
 #pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            av[q] = -1;
-                            ap[q] = (int32_t)rpos + (rc ? 3 - q : q);
+            for (int k = 0; k < 4; k++) {
+                const int32_t c = cb + k * EXEC_THREADS + tid;
+                st[k] = 0;
+                w0[k] = w1[k] = 0;
+                rp32[k] = 0;
+                if (c < n_chunks) {
+                    const int32_t j = j0 + 4 * c;
+                    st[k] = 2;
+                    if (j >= jo_lo && j + 4 <= jo_hi) {
+                        const int32_t p0 = rc ? (L - 4 - j) : j;  // lowest haplotype position of the chunk
+                        if (!rc) {
+                            while (S.a[ic + 1] <= p0) ic++;
+                        } else {
+                            while (S.a[ic] > p0) ic--;
+                        }
+                        const int32_t e_i = S.e[ic];
+                        const int64_t rpos = (int64_t)S.resume[ic] + (p0 - e_i);
+                        if (p0 >= e_i && p0 + 3 < S.a[ic + 1] && rpos + 3 < rp.contig_len) {
+                            st[k] = 1;
+                            rp32[k] = (int32_t)rpos;
+                            const uint8_t *ptr = refrow + rpos;
+                            const uint32_t *w = reinterpret_cast<const uint32_t *>(
+                                reinterpret_cast<uintptr_t>(ptr) & ~(uintptr_t)3);
+                            w0[k] = __ldg(w);
+                            w1[k] = __ldg(w + 1);  // (readable: buffers carry >= 16 B of slack)
                         }
                     }
                 }
             }
-            if (fast) {
-                if (MODE == GVL_MODE_U8) {
-                    *reinterpret_cast<uint32_t *>(P.out + g) = v;
-                } else if (MODE == GVL_MODE_ONEHOT) {
-                    *reinterpret_cast<uint4 *>(P.out + 4 * g) = onehot4(v);
-                } else if (MODE == GVL_MODE_ONEHOT_CF) {
-                    uint32_t mA = __vcmpeq4(v, 0x41414141u) & 0x01010101u;
-                    uint32_t mC = __vcmpeq4(v, 0x43434343u) & 0x01010101u;
-                    uint32_t mG = __vcmpeq4(v, 0x47474747u) & 0x01010101u;
-                    uint32_t mT = __vcmpeq4(v, 0x54545454u) & 0x01010101u;
-                    uint8_t *o = P.out + 4 * rp.out_off + j;  // (4, L) block of this row
-                    *reinterpret_cast<uint32_t *>(o) = mA;
-                    *reinterpret_cast<uint32_t *>(o + L) = mC;
-                    *reinterpret_cast<uint32_t *>(o + 2 * (int64_t)L) = mG;
-                    *reinterpret_cast<uint32_t *>(o + 3 * (int64_t)L) = mT;
-                } else {
-                    *reinterpret_cast<uint32_t *>(P.out + g) = v;
-                    *reinterpret_cast<int4 *>(P.annot_v + g) = make_int4(av[0], av[1], av[2], av[3]);
-                    *reinterpret_cast<int4 *>(P.annot_pos + g) = make_int4(ap[0], ap[1], ap[2], ap[3]);
-                }
-            } else {
-                // slow path: positions of the chunk that belong to this pass, one at a time
+            // ---- phase 2: assemble, encode, store ----
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int32_t jj = j + q;
-                    if (jj < jo_lo || jj >= jo_hi) continue;
-                    const int32_t p = rc ? (L - 1 - jj) : jj;
-                    PosInfo pi = resolve_pos<ANNOT>(S, m, p, rp, P);
-                    uint32_t b = pi.byte;
-                    if (rc) b = comp4(b) & 0xffu;
-                    const int64_t gg = g + q;
-                    if (MODE == GVL_MODE_U8) {
-                        P.out[gg] = (uint8_t)b;
-                    } else if (MODE == GVL_MODE_ONEHOT) {
-                        *reinterpret_cast<uint32_t *>(P.out + 4 * gg) = onehot1(b);
-                    } else if (MODE == GVL_MODE_ONEHOT_CF) {
-                        uint8_t *o = P.out + 4 * rp.out_off + jj;
-                        o[0] = (b == 'A');
-                        o[L] = (b == 'C');
-                        o[2 * (int64_t)L] = (b == 'G');
-                        o[3 * (int64_t)L] = (b == 'T');
+            for (int k = 0; k < 4; k++) {
+                if (st[k] == 0) continue;
+                const int32_t c = cb + k * EXEC_THREADS + tid;
+                const int32_t j = j0 + 4 * c;
+                const int64_t g = g0 + 4 * (int64_t)c;
+                if (st[k] == 1) {
+                    const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(refrow + rp32[k]) & 3) * 8u;
+                    uint32_t v = __funnelshift_r(w0[k], w1[k], sh);  // byte i = haplotype position p0+i
+                    if (rc) v = __byte_perm(v, 0, 0x0123);            // byte i = output position j+i
+                    if (OH) {
+                        const uint32_t *lut = s_lut + (rc ? 256 : 0);
+                        uint4 o;
+                        o.x = lut[v & 0xffu];
+                        o.y = lut[(v >> 8) & 0xffu];
+                        o.z = lut[(v >> 16) & 0xffu];
+                        o.w = lut[v >> 24];
+                        if (MODE == GVL_MODE_ONEHOT) {
+                            *reinterpret_cast<uint4 *>(P.out + 4 * g) = o;
+                        } else {
+                            uint8_t *op = P.out + 4 * rp.out_off + j;  // (4, L) block of this row
+                            const uint32_t xy0 = __byte_perm(o.x, o.y, 0x5140), xy1 = __byte_perm(o.x, o.y, 0x7362);
+                            const uint32_t zw0 = __byte_perm(o.z, o.w, 0x5140), zw1 = __byte_perm(o.z, o.w, 0x7362);
+                            *reinterpret_cast<uint32_t *>(op) = __byte_perm(xy0, zw0, 0x5410);
+                            *reinterpret_cast<uint32_t *>(op + L) = __byte_perm(xy0, zw0, 0x7632);
+                            *reinterpret_cast<uint32_t *>(op + 2 * (int64_t)L) = __byte_perm(xy1, zw1, 0x5410);
+                            *reinterpret_cast<uint32_t *>(op + 3 * (int64_t)L) = __byte_perm(xy1, zw1, 0x7632);
+                        }
                     } else {
-                        P.out[gg] = (uint8_t)b;
-                        P.annot_v[gg] = pi.av;
-                        P.annot_pos[gg] = pi.ap;
+                        if (rc) v = comp4(v);
+                        *reinterpret_cast<uint32_t *>(P.out + g) = v;
+                        if (ANNOT) {
+                            const int32_t r0 = rp32[k];
+                            *reinterpret_cast<int4 *>(P.annot_v + g) = make_int4(-1, -1, -1, -1);
+                            *reinterpret_cast<int4 *>(P.annot_pos + g) =
+                                rc ? make_int4(r0 + 3, r0 + 2, r0 + 1, r0) : make_int4(r0, r0 + 1, r0 + 2, r0 + 3);
+                        }
+                    }
+                } else {
+                    // slow path: positions of the chunk that belong to this pass, one at a time
+#pragma unroll 1
+                    for (int q = 0; q < 4; q++) {
+                        const int32_t jj = j + q;
+                        if (jj < jo_lo || jj >= jo_hi) continue;
+                        const int32_t p = rc ? (L - 1 - jj) : jj;
+                        PosInfo pi = resolve_pos(S, m, p, rp, P);
+                        uint32_t b = pi.byte;
+                        if (rc) b = comp1(b);
+                        const int64_t gg = g + q;
+                        if (MODE == GVL_MODE_ONEHOT) {
+                            *reinterpret_cast<uint32_t *>(P.out + 4 * gg) = onehot1(b);
+                        } else if (MODE == GVL_MODE_ONEHOT_CF) {
+                            uint8_t *op = P.out + 4 * rp.out_off + jj;
+                            op[0] = (b == 'A');
+                            op[L] = (b == 'C');
+                            op[2 * (int64_t)L] = (b == 'G');
+                            op[3 * (int64_t)L] = (b == 'T');
+                        } else {
+                            P.out[gg] = (uint8_t)b;
+                            if (ANNOT) {
+                                P.annot_v[gg] = pi.av;
+                                P.annot_pos[gg] = pi.ap;
+                            }
+                        }
                     }
                 }
             }
@@ -615,6 +661,23 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) diffs_kernel(DiffParams P) {
 }  // namespace gvl
 
 using namespace gvl;
+
+// resident CTAs of the execute kernel on this device (one wave)
+static int64_t exec_capacity(gvl_ctx *ctx, int mode) {
+    static int64_t cache[8][4] = {};
+    if (ctx->device < 8 && cache[ctx->device][mode & 3]) return cache[ctx->device][mode & 3];
+    int sms = 148, per_sm = 8;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    switch (mode) {
+        case GVL_MODE_U8: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hap_exec_kernel<GVL_MODE_U8>, EXEC_THREADS, 0); break;
+        case GVL_MODE_ONEHOT: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hap_exec_kernel<GVL_MODE_ONEHOT>, EXEC_THREADS, 0); break;
+        case GVL_MODE_ONEHOT_CF: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hap_exec_kernel<GVL_MODE_ONEHOT_CF>, EXEC_THREADS, 0); break;
+        default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hap_exec_kernel<GVL_MODE_ANNOTATED>, EXEC_THREADS, 0); break;
+    }
+    int64_t cap = (int64_t)sms * (per_sm > 0 ? per_sm : 1);
+    if (ctx->device < 8) cache[ctx->device][mode & 3] = cap;
+    return cap;
+}
 
 extern "C" {
 
@@ -712,10 +775,17 @@ int gvl_dev_hap_exec(gvl_ctx *ctx, const gvl_sparse_tables *tab, int mode, uint8
     P.pad_char = pad_char;
     int64_t grid;
     if (ctx->fixed_len >= 0) {
-        P.tiles_per_row = (ctx->fixed_len + TILE - 1) / TILE;
+        // pick the tile length so that the whole batch is ONE wave of CTAs when it can be
+        const int64_t units_per_row = (ctx->fixed_len + EXEC_UNIT - 1) / EXEC_UNIT;
+        const int64_t tiles_target = imax64(1, exec_capacity(ctx, mode) / ctx->n_work);
+        int64_t units_per_tile = (units_per_row + tiles_target - 1) / tiles_target;
+        units_per_tile = imax64(4, imin64(units_per_tile, 64));
+        P.tile_len = (int32_t)(units_per_tile * EXEC_UNIT);
+        P.tiles_per_row = (ctx->fixed_len + P.tile_len - 1) / P.tile_len;
         P.tile_off = nullptr;
         grid = P.tiles_per_row * ctx->n_work;
     } else {
+        P.tile_len = TILE;
         if (ctx->total < 0) return fail(GVL_ERR_STATE, "gvl_dev_hap_exec: ragged plan needs gvl_dev_hap_total first");
         if (mode == GVL_MODE_ONEHOT_CF) return fail(GVL_ERR_ARG, "gvl_dev_hap_exec: channels-first one-hot needs a fixed length");
         P.tiles_per_row = 0;

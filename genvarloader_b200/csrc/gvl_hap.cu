@@ -18,6 +18,8 @@
 //           bytes with two aligned 32-bit loads + funnel shift, ALT/pad bytes patched in,
 //           reverse-complement and the encoding fused, one 16-byte store (one-hot) per step.
 //           Every output byte is written exactly once; no intermediate haplotype in HBM.
+#include <cstdlib>
+
 #include "gvl_internal.cuh"
 
 namespace gvl {
@@ -44,10 +46,11 @@ struct HapPlanParams {
 
 constexpr int PLAN_WARPS = 4;
 
-__global__ void __launch_bounds__(PLAN_WARPS * 32) hap_plan_kernel(HapPlanParams P) {
+// Serial (lock-step) plan of one row by ONE warp: the reference's loop, one variant per step.
+// Exact for any input order; used for rows whose variant list is not position-sorted and by the
+// GVL_PLAN=serial debugging switch.  The scan-based kernel below handles everything else.
+__device__ void plan_row_serial(const HapPlanParams &P, const int64_t k, const int64_t rec_off_in = -1) {
     const int lane = lane_id();
-    const int64_t k = (int64_t)blockIdx.x * PLAN_WARPS + (threadIdx.x >> 5);
-    if (k >= P.n_work) return;
     const int64_t query = k / P.ploidy;
     const int64_t o_idx = P.goi[k];
     const int64_t o_s = P.tab.geno_starts[o_idx];
@@ -102,9 +105,11 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) hap_plan_kernel(HapPlanParams
     }
 
     // ---- workspace for this row's records: nvar + 1 slots ----
-    int64_t rec_off = 0;
-    if (lane == 0) rec_off = (int64_t)atomicAdd((unsigned long long *)&P.words[W_CURSOR], (unsigned long long)(nvar + 1));
-    rec_off = __shfl_sync(0xffffffffu, rec_off, 0);
+    int64_t rec_off = rec_off_in;
+    if (rec_off_in < 0) {
+        if (lane == 0) rec_off = (int64_t)atomicAdd((unsigned long long *)&P.words[W_CURSOR], (unsigned long long)(nvar + 1));
+        rec_off = __shfl_sync(0xffffffffu, rec_off, 0);
+    }
     const bool overflow = rec_off + nvar + 1 > P.rec_cap;
     if (overflow && lane == 0) atomicMax((unsigned long long *)&P.words[W_STATUS], (unsigned long long)(rec_off + nvar + 1));
 
@@ -210,6 +215,14 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) hap_plan_kernel(HapPlanParams
         }
     }
 }
+
+__global__ void __launch_bounds__(PLAN_WARPS * 32) hap_plan_serial_kernel(HapPlanParams P) {
+    const int64_t k = (int64_t)blockIdx.x * PLAN_WARPS + (threadIdx.x >> 5);
+    if (k >= P.n_work) return;
+    plan_row_serial(P, k);
+}
+
+#include "gvl_plan_par.cuh"
 
 // ragged plans: exclusive scan of row lengths -> out_offsets, RowPlan.out_off, tile map, totals.
 __global__ void __launch_bounds__(1024) row_scan_kernel(int64_t n_work, const int32_t *__restrict__ row_len,
@@ -477,56 +490,78 @@ __global__ void __launch_bounds__(EXEC_THREADS) hap_exec_kernel(HapExecParams P)
         __syncthreads();
 
         // ---- output range of this pass, chunked by 4 on the GLOBAL flat index ----
+        // chunk c covers row positions j0+4c .. j0+4c+3; a GROUP is 32 chunks (one per lane, 128
+        // positions, one 512-byte one-hot store per warp), a BLOCK is 4 groups.  Warp w owns blocks
+        // w, w+4, ...  All loads of a block are issued before its first store.
         const int32_t jo_lo = rc ? L - seg_end : cur;
         const int32_t jo_hi = rc ? L - cur : seg_end;
         const int64_t g0 = (rp.out_off + jo_lo) & ~(int64_t)3;
         const int32_t j0 = (int32_t)(g0 - rp.out_off);  // row-relative position of chunk 0 (may be < jo_lo)
         const int32_t n_chunks = (jo_hi - j0 + 3) >> 2;
-        int ic = rc ? (m - 1) : 0;  // record cursor: chunks are visited in monotone haplotype order
+        const int32_t n_blocks = (n_chunks + 127) >> 7;
+        const int lane = tid & 31, warp = tid >> 5;
+        int ic = rc ? (m - 1) : 0;  // warp-uniform record cursor (groups are visited in monotone order)
         const uint8_t *__restrict__ refrow = P.ref + rp.ref_base;
+        uint8_t *__restrict__ out_row = P.out + (OH ? 4 : 1) * rp.out_off;  // element j of the row lives at out_row[(4*)j]
 
-        for (int32_t cb = 0; cb < n_chunks; cb += 4 * EXEC_THREADS) {
+        for (int32_t blk = warp; blk < n_blocks; blk += EXEC_THREADS / 32) {
             uint32_t w0[4], w1[4];
             int32_t rp32[4];
             int st[4];  // 0 nothing, 1 fast (reference-only chunk), 2 slow
-            // ---- phase 1: classify the 4 chunks of this thread and issue their loads ----
+            // ---- phase 1: classify the chunks of this block and issue their loads ----
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const int32_t c = cb + k * EXEC_THREADS + tid;
+                const int32_t cg = (blk * 4 + k) * 32;  // first chunk of the group (warp-uniform)
+                const int32_t jg = j0 + 4 * cg;         // first row position of the group
                 st[k] = 0;
                 w0[k] = w1[k] = 0;
                 rp32[k] = 0;
-                if (c < n_chunks) {
-                    const int32_t j = j0 + 4 * c;
-                    st[k] = 2;
-                    if (j >= jo_lo && j + 4 <= jo_hi) {
-                        const int32_t p0 = rc ? (L - 4 - j) : j;  // lowest haplotype position of the chunk
-                        if (!rc) {
-                            while (S.a[ic + 1] <= p0) ic++;
-                        } else {
-                            while (S.a[ic] > p0) ic--;
-                        }
-                        const int32_t e_i = S.e[ic];
-                        const int64_t rpos = (int64_t)S.resume[ic] + (p0 - e_i);
-                        if (p0 >= e_i && p0 + 3 < S.a[ic + 1] && rpos + 3 < rp.contig_len) {
-                            st[k] = 1;
-                            rp32[k] = (int32_t)rpos;
-                            const uint8_t *ptr = refrow + rpos;
-                            const uint32_t *w = reinterpret_cast<const uint32_t *>(
-                                reinterpret_cast<uintptr_t>(ptr) & ~(uintptr_t)3);
-                            w0[k] = __ldg(w);
-                            w1[k] = __ldg(w + 1);  // (readable: buffers carry >= 16 B of slack)
+                if (cg >= n_chunks) continue;
+                const int32_t j = jg + 4 * lane;
+                bool fast = false;
+                int32_t rpos_l = 0;
+                if (jg >= jo_lo && jg + 128 <= jo_hi) {
+                    // whole group inside the pass: test it against the records once, warp-uniformly
+                    const int32_t p_lo = rc ? (L - 128 - jg) : jg;  // lowest haplotype position of the group
+                    if (!rc) {
+                        while (S.a[ic + 1] <= p_lo) ic++;
+                    } else {
+                        while (S.a[ic] > p_lo) ic--;
+                    }
+                    const int32_t e_i = S.e[ic];
+                    const int64_t rpos_lo = (int64_t)S.resume[ic] + (p_lo - e_i);
+                    if (p_lo >= e_i && p_lo + 127 < S.a[ic + 1] && rpos_lo + 127 < rp.contig_len) {
+                        fast = true;
+                        rpos_l = (int32_t)rpos_lo + (rc ? 124 - 4 * lane : 4 * lane);
+                    } else {
+                        // mixed group: each lane checks its own 4 positions (cursor starts at the group's record)
+                        const int32_t p0 = rc ? (L - 4 - j) : j;
+                        int il = ic;
+                        while (S.a[il + 1] <= p0) il++;
+                        const int32_t e_l = S.e[il];
+                        const int64_t rpos = (int64_t)S.resume[il] + (p0 - e_l);
+                        if (p0 >= e_l && p0 + 3 < S.a[il + 1] && rpos + 3 < rp.contig_len) {
+                            fast = true;
+                            rpos_l = (int32_t)rpos;
                         }
                     }
+                }
+                if (fast) {
+                    st[k] = 1;
+                    rp32[k] = rpos_l;
+                    const uint32_t *w = reinterpret_cast<const uint32_t *>(
+                        reinterpret_cast<uintptr_t>(refrow + rpos_l) & ~(uintptr_t)3);
+                    w0[k] = __ldg(w);
+                    w1[k] = __ldg(w + 1);  // (readable: buffers carry >= 16 B of slack)
+                } else if (cg + lane < n_chunks) {
+                    st[k] = 2;
                 }
             }
             // ---- phase 2: assemble, encode, store ----
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 if (st[k] == 0) continue;
-                const int32_t c = cb + k * EXEC_THREADS + tid;
-                const int32_t j = j0 + 4 * c;
-                const int64_t g = g0 + 4 * (int64_t)c;
+                const int32_t j = j0 + 4 * ((blk * 4 + k) * 32 + lane);
                 if (st[k] == 1) {
                     const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(refrow + rp32[k]) & 3) * 8u;
                     uint32_t v = __funnelshift_r(w0[k], w1[k], sh);  // byte i = haplotype position p0+i
@@ -539,9 +574,9 @@ __global__ void __launch_bounds__(EXEC_THREADS) hap_exec_kernel(HapExecParams P)
                         o.z = lut[(v >> 16) & 0xffu];
                         o.w = lut[v >> 24];
                         if (MODE == GVL_MODE_ONEHOT) {
-                            *reinterpret_cast<uint4 *>(P.out + 4 * g) = o;
+                            *reinterpret_cast<uint4 *>(out_row + 4 * (int64_t)j) = o;
                         } else {
-                            uint8_t *op = P.out + 4 * rp.out_off + j;  // (4, L) block of this row
+                            uint8_t *op = out_row + j;  // (4, L) block of this row
                             const uint32_t xy0 = __byte_perm(o.x, o.y, 0x5140), xy1 = __byte_perm(o.x, o.y, 0x7362);
                             const uint32_t zw0 = __byte_perm(o.z, o.w, 0x5140), zw1 = __byte_perm(o.z, o.w, 0x7362);
                             *reinterpret_cast<uint32_t *>(op) = __byte_perm(xy0, zw0, 0x5410);
@@ -551,9 +586,10 @@ __global__ void __launch_bounds__(EXEC_THREADS) hap_exec_kernel(HapExecParams P)
                         }
                     } else {
                         if (rc) v = comp4(v);
-                        *reinterpret_cast<uint32_t *>(P.out + g) = v;
+                        *reinterpret_cast<uint32_t *>(out_row + j) = v;
                         if (ANNOT) {
                             const int32_t r0 = rp32[k];
+                            const int64_t g = rp.out_off + j;
                             *reinterpret_cast<int4 *>(P.annot_v + g) = make_int4(-1, -1, -1, -1);
                             *reinterpret_cast<int4 *>(P.annot_pos + g) =
                                 rc ? make_int4(r0 + 3, r0 + 2, r0 + 1, r0) : make_int4(r0, r0 + 1, r0 + 2, r0 + 3);
@@ -569,20 +605,19 @@ __global__ void __launch_bounds__(EXEC_THREADS) hap_exec_kernel(HapExecParams P)
                         PosInfo pi = resolve_pos(S, m, p, rp, P);
                         uint32_t b = pi.byte;
                         if (rc) b = comp1(b);
-                        const int64_t gg = g + q;
                         if (MODE == GVL_MODE_ONEHOT) {
-                            *reinterpret_cast<uint32_t *>(P.out + 4 * gg) = onehot1(b);
+                            *reinterpret_cast<uint32_t *>(out_row + 4 * (int64_t)jj) = onehot1(b);
                         } else if (MODE == GVL_MODE_ONEHOT_CF) {
-                            uint8_t *op = P.out + 4 * rp.out_off + jj;
+                            uint8_t *op = out_row + jj;
                             op[0] = (b == 'A');
                             op[L] = (b == 'C');
                             op[2 * (int64_t)L] = (b == 'G');
                             op[3 * (int64_t)L] = (b == 'T');
                         } else {
-                            P.out[gg] = (uint8_t)b;
+                            out_row[jj] = (uint8_t)b;
                             if (ANNOT) {
-                                P.annot_v[gg] = pi.av;
-                                P.annot_pos[gg] = pi.ap;
+                                P.annot_v[rp.out_off + jj] = pi.av;
+                                P.annot_pos[rp.out_off + jj] = pi.ap;
                             }
                         }
                     }
@@ -724,8 +759,18 @@ int gvl_dev_hap_plan(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_t *
     P.out_offsets = out_offsets;
     P.diffs = diffs;
     P.row_len = ctx->hap.row_len;
-    const unsigned grid = (unsigned)((n_work + PLAN_WARPS - 1) / PLAN_WARPS);
-    hap_plan_kernel<<<grid, PLAN_WARPS * 32, 0, st>>>(P);
+    static const bool force_serial = [] {
+        const char *e = getenv("GVL_PLAN");
+        return e && e[0] == 's';
+    }();
+    if (force_serial) {
+        const unsigned grid = (unsigned)((n_work + PLAN_WARPS - 1) / PLAN_WARPS);
+        hap_plan_serial_kernel<<<grid, PLAN_WARPS * 32, 0, st>>>(P);
+    } else if (max_records <= 40 * n_work) {  // short lists: one warp per row, 4 rows per CTA
+        hap_plan_par_kernel<32><<<(unsigned)((n_work + 3) / 4), 128, 0, st>>>(P);
+    } else {  // one 256-thread CTA per row
+        hap_plan_par_kernel<256><<<(unsigned)n_work, 256, 0, st>>>(P);
+    }
     GVL_LAUNCH_CHECK();
     if (output_length >= 0) {
         ctx->total = n_work * output_length;

@@ -1,0 +1,411 @@
+// gvl_plan_par.cuh -- scan-based parallel haplotype plan (included by gvl_hap.cu).
+//
+// The reference walks a haplotype's variants one by one (src/reconstruct/mod.rs:85-198).  For a
+// position-sorted list the walk decomposes into data-parallel steps over a chunk of NT variants
+// (one per thread), with the state (ref_idx R, out_idx O, shifted) carried between chunks:
+//
+//  A  variants left of the window: only a deletion spanning the window start acts (:99-102); the
+//     LAST such deletion in list order sets R.                                   -> block max
+//  B  while the shift is not consumed (:115-146) neither R nor `shifted` change until the first
+//     variant j* with shifted + (pos - R) + alt_len >= shift; everything before it is skipped
+//     without side effects.                                                       -> block min
+//  C  afterwards a variant is applied iff pos >= R_current, where R_current is the end of the last
+//     APPLIED variant (:108-110, first ALT wins).  A variant whose pos is >= every earlier end
+//     (and >= R) is certainly applied ("head").  Variants between heads overlap something and are
+//     resolved by a short serial walk started at each head (clusters are tiny in practice; the
+//     walk is exact for any size).                                                -> max-scan + walk
+//  D  reference gap before each applied variant = pos - end(previous applied)      -> max-scan
+//     output position of its ALT bytes = O + sum(gaps + ALT lengths before) + gap  -> sum-scan
+//     the loop `break`s (:154-158) at the first applied variant whose ALT would start at or
+//     beyond `length`; positions are monotone, so validity is a prefix.          -> sum-scan (rank)
+//
+// Unsorted lists (out of contract for the reference's writers, but legal inputs of the kernel) are
+// detected and replanned by plan_row_serial, which is exact for any order.
+// get_diffs_sparse (src/genotypes/mod.rs:48-86) has the same shape: a variant counts iff it starts
+// left of the window or at/after the running maximum end of counted variants.
+#pragma once
+// (included from inside `namespace gvl` in gvl_hap.cu)
+
+template <int NT>
+__device__ __forceinline__ void grp_sync() {
+    if (NT == 32) __syncwarp(); else __syncthreads();
+}
+
+// inclusive scan over the NT threads of a group (a warp, or the whole CTA) -- OP in {max, add}
+template <int NT, bool IS_MAX>
+__device__ __forceinline__ int64_t grp_scan_incl(int64_t x, int64_t *s_warp /* >= NT/32 + 1 slots */) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int64_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x = IS_MAX ? imax64(x, y) : x + y;
+    }
+    if (NT == 32) return x;
+    const int warp = threadIdx.x >> 5;
+    __syncthreads();  // s_warp may still be read by the previous scan
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    int64_t pre = IS_MAX ? INT64_MIN : 0;
+    for (int w = 0; w < warp; w++) pre = IS_MAX ? imax64(pre, s_warp[w]) : pre + s_warp[w];
+    return IS_MAX ? imax64(x, pre) : x + pre;
+}
+
+// reduction to ALL threads of the group
+template <int NT, bool IS_MAX>
+__device__ __forceinline__ int64_t grp_reduce(int64_t x, int64_t *s_warp) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        int64_t y = __shfl_xor_sync(0xffffffffu, x, o);
+        x = IS_MAX ? imax64(x, y) : imin64(x, y);
+    }
+    if (NT == 32) return x;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = x;
+    __syncthreads();
+    int64_t r = s_warp[0];
+    for (int w = 1; w < NT / 32; w++) r = IS_MAX ? imax64(r, s_warp[w]) : imin64(r, s_warp[w]);
+    return r;
+}
+
+template <int NT>
+struct PlanSmem {
+    int32_t pos[NT];
+    int32_t end[NT];
+    uint8_t elig[NT];
+    uint8_t head[NT];
+    uint8_t applied[NT];
+    int64_t warp[NT / 32 + 1];
+    int flag;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(NT == 32 ? 128 : NT) hap_plan_par_kernel(HapPlanParams P) {
+    constexpr int ROWS_PER_CTA = (NT == 32) ? 4 : 1;
+    __shared__ PlanSmem<NT> s_all[ROWS_PER_CTA];
+    PlanSmem<NT> &S = s_all[(NT == 32) ? (threadIdx.x >> 5) : 0];
+    const int t = (NT == 32) ? (threadIdx.x & 31) : threadIdx.x;  // index within the row's group
+    const int64_t k = (NT == 32) ? ((int64_t)blockIdx.x * 4 + (threadIdx.x >> 5)) : (int64_t)blockIdx.x;
+    if (k >= P.n_work) return;  // (NT == 32: whole warps exit; NT == 256: whole CTA)
+
+    const int64_t query = k / P.ploidy;
+    const int64_t o_idx = P.goi[k];
+    const int64_t o_s = P.tab.geno_starts[o_idx];
+    const int64_t nvar = imax64(P.tab.geno_stops[o_idx] - o_s, 0);
+    const int64_t c_idx = P.regions[query * 3 + 0];
+    const int64_t c_s = P.tab.ref_offsets[c_idx];
+    const int64_t contig_len = P.tab.ref_offsets[c_idx + 1] - c_s;
+    const int64_t q_start = P.regions[query * 3 + 1];
+    const int64_t q_end = P.regions[query * 3 + 2];
+    const int64_t shift = P.shifts[k];
+    const bool has_keep = (P.keep && P.keep_off);
+    const int64_t keep_base = has_keep ? P.keep_off[k] : 0;
+    const int32_t *__restrict__ gv = P.tab.geno_v_idxs + o_s;
+    const bool ragged = P.output_length < 0;
+    const bool sized = P.output_length == -1;
+    const bool want_diff = sized || (P.diffs != nullptr);
+
+    int64_t rec_off = 0;
+    if (t == 0) rec_off = (int64_t)atomicAdd((unsigned long long *)&P.words[W_CURSOR], (unsigned long long)(nvar + 1));
+    if (NT == 32) {
+        rec_off = __shfl_sync(0xffffffffu, rec_off, 0);
+    } else {
+        if (t == 0) S.warp[NT / 32] = rec_off;
+        __syncthreads();
+        rec_off = S.warp[NT / 32];
+    }
+    const bool overflow = rec_off + nvar + 1 > P.rec_cap;
+    if (overflow && t == 0) atomicMax((unsigned long long *)&P.words[W_STATUS], (unsigned long long)(rec_off + nvar + 1));
+
+    // ---------------------------------------------------------------- pass 1: diffs (only if needed)
+    bool unsorted = false;
+    int64_t diff_acc = 0;
+    if (want_diff && nvar > 0) {
+        int64_t d_ref = q_start;  // running max end of counted variants (src/genotypes/mod.rs:57,78)
+        int64_t last_pos = INT64_MIN;
+        for (int64_t base = 0; base < nvar; base += NT) {
+            const int64_t i = base + t;
+            int64_t pos = INT64_MAX, il = 0;
+            bool kept = false;
+            if (i < nvar) {
+                const int32_t vi = gv[i];
+                pos = P.tab.v_starts[vi];
+                il = P.tab.ilens[vi];
+                kept = has_keep ? (P.keep[keep_base + i] != 0) : true;
+            }
+            const int64_t end = (i < nvar) ? pos - imin64(il, 0) + 1 : INT64_MIN;
+            // sortedness (of the whole list, kept or not)
+            grp_sync<NT>();
+            S.pos[t] = (int32_t)imin64(pos, INT32_MAX);
+            grp_sync<NT>();
+            const int64_t prev = (t > 0) ? (int64_t)S.pos[t - 1] : last_pos;
+            bool bad = (i < nvar) && (pos < prev);
+            // variants that take part at all: :69-74 (the `break` is a suffix cut for sorted input)
+            const bool in = kept && (end > q_start) && (pos < q_end);
+            const int64_t mx_incl = grp_scan_incl<NT, true>(in ? end : INT64_MIN, S.warp);
+            int64_t mx_excl = __shfl_up_sync(0xffffffffu, mx_incl, 1);
+            if (NT != 32) {
+                grp_sync<NT>();
+                if ((t & 31) == 31) S.warp[t >> 5] = mx_incl;
+                grp_sync<NT>();
+                if ((t & 31) == 0) mx_excl = (t > 0) ? S.warp[(t >> 5) - 1] : INT64_MIN;
+            } else if (t == 0) {
+                mx_excl = INT64_MIN;
+            }
+            mx_excl = imax64(mx_excl, d_ref);
+            const bool left = in && pos < q_start;          // always counted
+            const bool head = in && !left && pos >= mx_excl;  // certainly counted, resets the running max
+            S.end[t] = (int32_t)imax64(imin64(end, INT32_MAX), INT32_MIN);
+            S.elig[t] = in ? (left ? 2 : 1) : 0;
+            S.head[t] = head;
+            S.applied[t] = (left || head);
+            grp_sync<NT>();
+            // cluster walks: from every head, and from the chunk start (virtual head with cur = d_ref)
+            if (head || t == 0) {
+                int64_t cur = head ? end : d_ref;
+                int u = head ? t + 1 : 0;
+                for (; u < NT && !S.head[u]; u++) {
+                    const int e = S.elig[u];
+                    if (e == 0) continue;
+                    if (e == 2) {
+                        cur = imax64(cur, S.end[u]);
+                    } else if ((int64_t)S.pos[u] >= cur) {
+                        S.applied[u] = 1;
+                        cur = imax64(cur, S.end[u]);
+                    }
+                }
+            }
+            grp_sync<NT>();
+            const bool counted = S.applied[t] != 0;
+            int64_t adj = 0;
+            if (counted) {
+                adj = il;
+                if (il < 0) adj += imax64(q_start - pos - 1, 0);  // :79-81
+                adj += imax64(end - q_end, 0);                     // :82
+            }
+            const int64_t tot = grp_scan_incl<NT, false>(adj, S.warp);
+            // totals + carried state, broadcast from the last thread
+            int64_t chunk_sum, chunk_max;
+            {
+                int64_t cm = grp_reduce<NT, true>(counted ? end : INT64_MIN, S.warp);
+                chunk_max = cm;
+                if (NT == 32) {
+                    chunk_sum = __shfl_sync(0xffffffffu, tot, 31);
+                } else {
+                    grp_sync<NT>();
+                    if (t == NT - 1) S.warp[NT / 32] = tot;
+                    grp_sync<NT>();
+                    chunk_sum = S.warp[NT / 32];
+                }
+            }
+            diff_acc += chunk_sum;
+            d_ref = imax64(d_ref, chunk_max);
+            {
+                int64_t lp = grp_reduce<NT, true>((i < nvar) ? pos : INT64_MIN, S.warp);
+                last_pos = imax64(last_pos, lp);
+            }
+            if (NT == 32) bad = __any_sync(0xffffffffu, bad); else bad = __syncthreads_or(bad);
+            if (bad) {
+                unsorted = true;
+                break;
+            }
+        }
+    }
+
+    int64_t length;
+    if (sized) {
+        length = imax64((q_end - q_start) + (int64_t)(int32_t)diff_acc, 0);  // src/ffi/mod.rs:801-807
+    } else if (ragged) {
+        length = imax64(P.out_offsets[k + 1] - P.out_offsets[k], 0);
+    } else {
+        length = P.output_length;
+    }
+
+    // ---------------------------------------------------------------- pass 2: haplotype records
+    HapState hs;
+    hap_init(hs, q_start, shift, length);  // leading pad, :68-83
+    int64_t R = hs.ref_idx, O = hs.out_idx, shifted = hs.shifted;
+    int64_t n_emit = 0, ref0 = 0;
+    bool done = false;
+    int64_t last_pos = INT64_MIN;
+    for (int64_t base = 0; base < nvar && !done && !unsorted; base += NT) {
+        const int64_t i = base + t;
+        int64_t pos = INT64_MAX, il = 0, alen = 0, aoff = 0;
+        int32_t vi = 0;
+        bool kept = false;
+        if (i < nvar) {
+            vi = gv[i];
+            pos = P.tab.v_starts[vi];
+            il = P.tab.ilens[vi];
+            aoff = P.tab.alt_offsets[vi];
+            alen = P.tab.alt_offsets[vi + 1] - aoff;
+            kept = has_keep ? (P.keep[keep_base + i] != 0) : true;
+        }
+        const int64_t end = (i < nvar) ? pos - imin64(il, 0) + 1 : INT64_MIN;
+        grp_sync<NT>();
+        S.pos[t] = (int32_t)imin64(pos, INT32_MAX);
+        S.end[t] = (int32_t)imax64(imin64(end, INT32_MAX), INT32_MIN);
+        grp_sync<NT>();
+        {
+            const int64_t prev = (t > 0) ? (int64_t)S.pos[t - 1] : last_pos;
+            bool bad = (i < nvar) && (pos < prev);
+            if (NT == 32) bad = __any_sync(0xffffffffu, bad); else bad = __syncthreads_or(bad);
+            if (bad) {
+                unsorted = true;
+                break;
+            }
+            last_pos = imax64(last_pos, grp_reduce<NT, true>((i < nvar) ? pos : INT64_MIN, S.warp));
+        }
+        // -- A: deletions spanning the window start (:99-102): the last one sets R
+        const bool span = kept && pos < q_start && il < 0 && end >= q_start;
+        const int64_t last_span = grp_reduce<NT, true>(span ? (int64_t)t : -1, S.warp);
+        if (last_span >= 0) R = S.end[last_span];
+        bool elig = kept && pos >= q_start;  // everything else is skipped without side effects
+        // -- B: shift phase (:115-146)
+        int64_t start = 0, trim_at = -1, trim = 0;
+        if (shifted < shift) {
+            const bool cand = elig && pos >= R && (shifted + (pos - R) + alen >= shift);
+            const int64_t js = grp_reduce<NT, false>(cand ? (int64_t)t : INT64_MAX, S.warp);
+            if (js == INT64_MAX) continue;  // the whole chunk is skipped; R and shifted unchanged
+            // operands of j*: broadcast through shared memory
+            grp_sync<NT>();
+            if (t == js) {
+                S.warp[0] = pos;
+                S.warp[1] = alen;
+                S.warp[2] = end;
+            }
+            grp_sync<NT>();
+            const int64_t jpos = S.warp[0], jalen = S.warp[1], jend = S.warp[2];
+            grp_sync<NT>();
+            const int64_t d = jpos - R;
+            if (shifted + d >= shift) {  // :123-128
+                R += shift - shifted;
+                start = js;
+            } else {
+                const int64_t tr = shift - shifted - d;  // :132
+                if (tr == jalen) {                        // :135-140
+                    R = jend;
+                    start = js + 1;
+                } else {
+                    R = jpos;  // :143
+                    start = js;
+                    trim_at = js;
+                    trim = tr;
+                }
+            }
+            shifted = shift;
+        }
+        elig = elig && t >= start;
+        // -- C: applied set
+        const int64_t mx_incl = grp_scan_incl<NT, true>(elig ? end : INT64_MIN, S.warp);
+        int64_t mx_excl = __shfl_up_sync(0xffffffffu, mx_incl, 1);
+        if (NT != 32) {
+            grp_sync<NT>();
+            if ((t & 31) == 31) S.warp[t >> 5] = mx_incl;
+            grp_sync<NT>();
+            if ((t & 31) == 0) mx_excl = (t > 0) ? S.warp[(t >> 5) - 1] : INT64_MIN;
+        } else if (t == 0) {
+            mx_excl = INT64_MIN;
+        }
+        mx_excl = imax64(mx_excl, R);
+        const bool head = elig && pos >= mx_excl;
+        grp_sync<NT>();
+        S.elig[t] = elig;
+        S.head[t] = head;
+        S.applied[t] = head;
+        grp_sync<NT>();
+        if (head || t == 0) {
+            int64_t cur = head ? end : R;
+            int u = head ? t + 1 : 0;
+            for (; u < NT && !S.head[u]; u++) {
+                if (S.elig[u] && (int64_t)S.pos[u] >= cur) {  // :108-110
+                    S.applied[u] = 1;
+                    cur = S.end[u];
+                }
+            }
+        }
+        grp_sync<NT>();
+        const bool applied = S.applied[t] != 0;
+        // -- D: gaps, output positions, validity
+        const int64_t pe_incl = grp_scan_incl<NT, true>(applied ? end : INT64_MIN, S.warp);
+        int64_t pe_excl = __shfl_up_sync(0xffffffffu, pe_incl, 1);
+        if (NT != 32) {
+            grp_sync<NT>();
+            if ((t & 31) == 31) S.warp[t >> 5] = pe_incl;
+            grp_sync<NT>();
+            if ((t & 31) == 0) pe_excl = (t > 0) ? S.warp[(t >> 5) - 1] : INT64_MIN;
+        } else if (t == 0) {
+            pe_excl = INT64_MIN;
+        }
+        const int64_t prev_end = imax64(pe_excl, R);
+        const int64_t my_trim = (t == trim_at) ? trim : 0;
+        const int64_t ref_len = applied ? pos - prev_end : 0;
+        const int64_t alen_eff = applied ? alen - my_trim : 0;
+        const int64_t c_incl = grp_scan_incl<NT, false>(ref_len + alen_eff, S.warp);
+        const int64_t a = O + (c_incl - (ref_len + alen_eff)) + ref_len;  // ALT start in the output
+        const bool valid = applied && a < length;                         // :154-158
+        const bool broke = applied && !valid;
+        const int64_t n = valid ? imin64(alen_eff, length - a) : 0;     // :178
+        const int64_t rank_incl = grp_scan_incl<NT, false>(valid ? 1 : 0, S.warp);
+        if (valid && !overflow) {
+            const int64_t w = rec_off + n_emit + rank_incl - 1;
+            P.rec.a[w] = (int32_t)a;
+            P.rec.n[w] = (int32_t)n;
+            P.rec.src[w] = aoff + my_trim;
+            P.rec.resume[w] = (int32_t)end;
+            P.rec.vidx[w] = vi;
+            P.rec.vpos[w] = (int32_t)pos;
+        }
+        // carried state: last valid record of the chunk
+        const int64_t last_valid = grp_reduce<NT, true>(valid ? (int64_t)t : -1, S.warp);
+        const bool any_broke = (NT == 32) ? __any_sync(0xffffffffu, broke) : (__syncthreads_or(broke) != 0);
+        if (last_valid >= 0) {
+            grp_sync<NT>();
+            if (t == last_valid) {
+                S.warp[0] = a + n;
+                S.warp[1] = end;
+                S.warp[2] = rank_incl;
+            }
+            grp_sync<NT>();
+            if (n_emit == 0) ref0 = R;  // the first applied variant's gap starts at R (after the shift)
+            O = S.warp[0];
+            R = S.warp[1];
+            n_emit += S.warp[2];
+            grp_sync<NT>();
+        }
+        if (any_broke || O >= length) done = true;  // :154-158, :195-197
+    }
+
+    if (unsorted) {
+        // exact replan in list order by one warp (rare; out of the writers' contract)
+        if (NT == 32 || threadIdx.x < 32) plan_row_serial(P, k, rec_off);
+        return;
+    }
+
+    if (shifted < shift) {  // :200-205
+        R = imin64(R + (shift - shifted), contig_len);
+    }
+    if (n_emit == 0) ref0 = R;
+    if (t == 0) {
+        RowPlan rp;
+        rp.out_off = ragged ? 0 : k * length;
+        rp.ref_base = c_s;
+        rp.rec_off = rec_off;
+        rp.length = (int32_t)length;
+        rp.contig_len = (int32_t)contig_len;
+        rp.lead_pad = (int32_t)imin64(hs.lead_pad, length);
+        rp.ref0 = (int32_t)ref0;
+        rp.n_rec = overflow ? 0 : (int32_t)n_emit;
+        rp.rc = (P.to_rc && P.to_rc[k]) ? 1 : 0;
+        rp.diff = (int32_t)diff_acc;
+        rp.q_start = (int32_t)q_start;
+        P.rows[k] = rp;
+        if (P.diffs) P.diffs[k] = rp.diff;
+        if (ragged) {
+            P.row_len[k] = (int32_t)length;
+        } else {
+            P.out_offsets[k] = k * length;
+            if (k == P.n_work - 1) P.out_offsets[P.n_work] = P.n_work * length;
+        }
+    }
+}
+

@@ -180,3 +180,46 @@ def test_config1_full_size_properties(K, O):
     O.rc_flat_rows_inplace(rc_out, oo, rc_all)
     _golden.eq("cfg1.rc_roundtrip", 0, rc_out, out)
     K.unpin_static(d.geno_offsets, d.geno_v_idxs, d.v_starts, d.ilens, d.alt_alleles, d.alt_offsets, d.reference, d.ref_offsets)
+
+
+def test_unsorted_variant_lists_fall_back_to_exact_serial_plan(K, O):
+    """Position-unsorted genotype lists are outside the reference writers' contract but legal kernel
+    inputs: the scan-based plan must detect them and reproduce the sequential semantics exactly."""
+    from genvarloader_b200 import synth
+
+    d = synth.make_dataset(21, 80_000, 3, 10, 2500, 12.0, max_indel=15, snp_frac=0.5)
+    rng = np.random.default_rng(9)
+    gv = d.geno_v_idxs.copy()
+    for s, e in zip(d.geno_offsets[0], d.geno_offsets[1]):
+        if e - s > 2 and rng.random() < 0.5:
+            gv[s:e] = rng.permutation(gv[s:e])
+    args, to_rc = _rand_case(rng, d, 14, -1, synth, shifts=False)
+    args = list(args)
+    args[4] = gv
+    for out_len, sh in ((-1, False), (2000, True)):
+        args[12] = out_len
+        args[1] = rng.integers(0, 50, args[1].shape).astype(np.int32) if sh else np.zeros_like(args[1])
+        e = O.reconstruct_annotated_haplotypes_fused(*args, None, None, to_rc)
+        g = K.reconstruct_annotated_haplotypes_fused(*args, None, None, to_rc)
+        for j, nm in enumerate(["out", "annot_v", "annot_pos", "offsets"]):
+            _golden.eq(f"unsorted.{nm}", out_len, g[j], e[j])
+
+
+@pytest.mark.parametrize("vkb,L", [(0.5, 40_000), (40.0, 30_000), (150.0, 9_000)])
+def test_long_rows_many_chunks_with_shifts(K, O, vkb, L):
+    """Rows with far more variants than one plan chunk (256), shifts that skip many variants,
+    overlapping variants (dense_af) and windows running over the contig end."""
+    from genvarloader_b200 import synth
+
+    d = synth.make_dataset(int(L + vkb), 150_000, 2, 12, L, vkb, max_indel=12, snp_frac=0.4, dense_af=0.5,
+                           neg_strand_frac=0.3)
+    rng = np.random.default_rng(int(vkb))
+    for out_len in (-1, L - 1000, L + 64):
+        args, to_rc = _rand_case(rng, d, 8, out_len, synth)
+        args = list(args)
+        if out_len > 0:
+            args[1] = rng.integers(0, 900, args[1].shape).astype(np.int32)
+        e = O.reconstruct_annotated_haplotypes_fused(*args, None, None, to_rc)
+        g = K.reconstruct_annotated_haplotypes_fused(*args, None, None, to_rc)
+        for j, nm in enumerate(["out", "annot_v", "annot_pos", "offsets"]):
+            _golden.eq(f"long.{nm}", out_len, g[j], e[j])

@@ -335,45 +335,14 @@ __device__ __forceinline__ uint32_t onehot1(uint32_t b) {
     return (b == 'A' ? 1u : 0u) | (b == 'C' ? 0x100u : 0u) | (b == 'G' ? 0x10000u : 0u) | (b == 'T' ? 0x1000000u : 0u);
 }
 
-struct PosInfo {
-    uint32_t byte;
-    int32_t av, ap;
-};
-
-// Generic (slow-path) resolution of one haplotype position against the staged records.
-__device__ __forceinline__ PosInfo resolve_pos(const TileRecs &S, int m, int32_t p, const RowPlan &rp,
-                                               const HapExecParams &P) {
-    int lo = 0, hi = m;  // entry i = last with a[i] <= p (entry 0 always qualifies)
+// last staged entry i in [0, m) with a[i] <= p (entry 0 always qualifies)
+__device__ __forceinline__ int find_rec(const TileRecs &S, int m, int32_t p) {
+    int lo = 0, hi = m;
     while (hi - lo > 1) {
         int mid = (lo + hi) >> 1;
         if (S.a[mid] <= p) lo = mid; else hi = mid;
     }
-    const int i = lo;
-    PosInfo r;
-    if (p < S.e[i]) {
-        int64_t src = S.src[i];
-        if (src == ALT_PAD) {
-            r.byte = P.pad_char;
-            r.av = -1;
-            r.ap = -1;  // leading pad (src/reconstruct/mod.rs:75-80)
-        } else {
-            r.byte = P.alt[src + (p - S.a[i])];
-            r.av = S.vidx[i];
-            r.ap = S.vpos[i];
-        }
-    } else {
-        int64_t rpos = (int64_t)S.resume[i] + (p - S.e[i]);
-        if (rpos < rp.contig_len) {
-            r.byte = P.ref[rp.ref_base + rpos];
-            r.av = -1;
-            r.ap = (int32_t)rpos;
-        } else {
-            r.byte = P.pad_char;
-            r.av = -1;
-            r.ap = INT32_MAX;  // trailing pad (:248-253)
-        }
-    }
-    return r;
+    return lo;
 }
 
 constexpr int COUNT_MAX = 2048;  // rows with more records locate their tile range by 32-ary search
@@ -383,15 +352,16 @@ __global__ void __launch_bounds__(EXEC_THREADS) hap_exec_kernel(HapExecParams P)
     constexpr bool ANNOT = (MODE == GVL_MODE_ANNOTATED);
     constexpr bool OH = (MODE == GVL_MODE_ONEHOT || MODE == GVL_MODE_ONEHOT_CF);
     __shared__ TileRecs S;
-    __shared__ uint32_t s_lut[OH ? 512 : 1];  // [0,256): one-hot(b); [256,512): one-hot(complement(b))
+    __shared__ __align__(16) uint32_t s_lut[OH ? 512 : 4];  // [0,256): one-hot(b); [256,512): one-hot(complement(b))
     __shared__ int s_cnt[2];
     __shared__ int64_t s_lo, s_hi;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     // ---- tile -> (row, tile-in-row) ----
     int64_t row, tile;
     if (P.tiles_per_row > 0) {
-        row = blockIdx.x / P.tiles_per_row;
-        tile = blockIdx.x % P.tiles_per_row;
+        tile = blockIdx.x;
+        row = (int64_t)blockIdx.y + (int64_t)blockIdx.z * 65535;
         if (row >= P.n_work) return;
     } else {
         int64_t b = blockIdx.x;
@@ -412,16 +382,15 @@ __global__ void __launch_bounds__(EXEC_THREADS) hap_exec_kernel(HapExecParams P)
     const int32_t h0 = (int32_t)h0_64;
     const int32_t h1 = (int32_t)imin64(h0_64 + P.tile_len, L);
     const bool rc = rp.rc != 0;
-    const int tid = threadIdx.x;
 
-    if (OH) {
-        for (int i = tid; i < 512; i += EXEC_THREADS) {
-            uint32_t b = i & 255;
-            s_lut[i] = onehot1(i >= 256 ? comp1(b) : b);
-        }
-    }
+    if (OH) reinterpret_cast<uint4 *>(s_lut)[tid] = make_uint4(0u, 0u, 0u, 0u);  // 128 threads x 16 B = the whole table
     if (tid < 2) s_cnt[tid] = 0;
     __syncthreads();
+    if (OH && tid < 8) {  // the only non-zero entries: ACGT (and their complements in the second half)
+        const int i = tid & 3;
+        const uint32_t letter = (0x54474341u >> (8 * i)) & 0xffu;  // 'A','C','G','T'
+        s_lut[(tid < 4 ? 0 : 256) + letter] = 1u << (8 * (tid < 4 ? i : 3 - i));
+    }
 
     // ---- records of this tile: r_lo = last with a <= h0 (or -1), r_hi = first with a >= h1 ----
     const int32_t *__restrict__ ra = P.rec.a + rp.rec_off;
@@ -436,7 +405,7 @@ __global__ void __launch_bounds__(EXEC_THREADS) hap_exec_kernel(HapExecParams P)
             c0 += __shfl_xor_sync(0xffffffffu, c0, o);
             c1 += __shfl_xor_sync(0xffffffffu, c1, o);
         }
-        if ((tid & 31) == 0 && (c0 | c1)) {
+        if (lane == 0 && (c0 | c1)) {
             atomicAdd(&s_cnt[0], c0);
             atomicAdd(&s_cnt[1], c1);
         }
@@ -457,6 +426,41 @@ __global__ void __launch_bounds__(EXEC_THREADS) hap_exec_kernel(HapExecParams P)
     const int64_t r_hi = s_hi;
     int64_t r = s_lo;
     int32_t cur = h0;
+    const uint8_t *__restrict__ refrow = P.ref + rp.ref_base;
+    uint8_t *__restrict__ out_row = P.out + (OH ? 4 : 1) * rp.out_off;  // position j of the row lives at out_row[(4*)j]
+    const uint32_t *lut = s_lut + (rc ? 256 : 0);
+
+    // one 4-position chunk made only of reference bytes: v holds the bytes in OUTPUT order (not yet
+    // complemented), r0 = reference position of the chunk's lowest haplotype position
+    auto emit_ref4 = [&](int32_t j, uint32_t v, int32_t r0) {
+        if (OH) {
+            uint4 o;
+            o.x = lut[v & 0xffu];
+            o.y = lut[(v >> 8) & 0xffu];
+            o.z = lut[(v >> 16) & 0xffu];
+            o.w = lut[v >> 24];
+            if (MODE == GVL_MODE_ONEHOT) {
+                *reinterpret_cast<uint4 *>(out_row + 4 * (int64_t)j) = o;
+            } else {
+                uint8_t *op = out_row + j;  // (4, L) block of this row
+                const uint32_t xy0 = __byte_perm(o.x, o.y, 0x5140), xy1 = __byte_perm(o.x, o.y, 0x7362);
+                const uint32_t zw0 = __byte_perm(o.z, o.w, 0x5140), zw1 = __byte_perm(o.z, o.w, 0x7362);
+                *reinterpret_cast<uint32_t *>(op) = __byte_perm(xy0, zw0, 0x5410);
+                *reinterpret_cast<uint32_t *>(op + L) = __byte_perm(xy0, zw0, 0x7632);
+                *reinterpret_cast<uint32_t *>(op + 2 * (int64_t)L) = __byte_perm(xy1, zw1, 0x5410);
+                *reinterpret_cast<uint32_t *>(op + 3 * (int64_t)L) = __byte_perm(xy1, zw1, 0x7632);
+            }
+        } else {
+            if (rc) v = comp4(v);
+            *reinterpret_cast<uint32_t *>(out_row + j) = v;
+            if (ANNOT) {
+                const int64_t g = rp.out_off + j;
+                *reinterpret_cast<int4 *>(P.annot_v + g) = make_int4(-1, -1, -1, -1);
+                *reinterpret_cast<int4 *>(P.annot_pos + g) =
+                    rc ? make_int4(r0 + 3, r0 + 2, r0 + 1, r0) : make_int4(r0, r0 + 1, r0 + 2, r0 + 3);
+            }
+        }
+    };
 
     while (cur < h1) {
         // ---- stage entry 0 (carry) + up to REC_CAP-1 following records ----
@@ -490,135 +494,123 @@ __global__ void __launch_bounds__(EXEC_THREADS) hap_exec_kernel(HapExecParams P)
         __syncthreads();
 
         // ---- output range of this pass, chunked by 4 on the GLOBAL flat index ----
-        // chunk c covers row positions j0+4c .. j0+4c+3; a GROUP is 32 chunks (one per lane, 128
+        // chunk c covers row positions j0+4c .. j0+4c+3; a GROUP is 32 chunks (one per lane: 128
         // positions, one 512-byte one-hot store per warp), a BLOCK is 4 groups.  Warp w owns blocks
-        // w, w+4, ...  All loads of a block are issued before its first store.
+        // w, w+4, ...
         const int32_t jo_lo = rc ? L - seg_end : cur;
         const int32_t jo_hi = rc ? L - cur : seg_end;
         const int64_t g0 = (rp.out_off + jo_lo) & ~(int64_t)3;
         const int32_t j0 = (int32_t)(g0 - rp.out_off);  // row-relative position of chunk 0 (may be < jo_lo)
         const int32_t n_chunks = (jo_hi - j0 + 3) >> 2;
         const int32_t n_blocks = (n_chunks + 127) >> 7;
-        const int lane = tid & 31, warp = tid >> 5;
-        int ic = rc ? (m - 1) : 0;  // warp-uniform record cursor (groups are visited in monotone order)
-        const uint8_t *__restrict__ refrow = P.ref + rp.ref_base;
-        uint8_t *__restrict__ out_row = P.out + (OH ? 4 : 1) * rp.out_off;  // element j of the row lives at out_row[(4*)j]
+        int ic = rc ? (m - 1) : 0;  // warp-uniform record cursor (blocks are visited in monotone order)
 
         for (int32_t blk = warp; blk < n_blocks; blk += EXEC_THREADS / 32) {
-            uint32_t w0[4], w1[4];
-            int32_t rp32[4];
-            int st[4];  // 0 nothing, 1 fast (reference-only chunk), 2 slow
-            // ---- phase 1: classify the chunks of this block and issue their loads ----
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int32_t cg = (blk * 4 + k) * 32;  // first chunk of the group (warp-uniform)
-                const int32_t jg = j0 + 4 * cg;         // first row position of the group
-                st[k] = 0;
-                w0[k] = w1[k] = 0;
-                rp32[k] = 0;
-                if (cg >= n_chunks) continue;
-                const int32_t j = jg + 4 * lane;
-                bool fast = false;
-                int32_t rpos_l = 0;
-                if (jg >= jo_lo && jg + 128 <= jo_hi) {
-                    // whole group inside the pass: test it against the records once, warp-uniformly
-                    const int32_t p_lo = rc ? (L - 128 - jg) : jg;  // lowest haplotype position of the group
-                    if (!rc) {
-                        while (S.a[ic + 1] <= p_lo) ic++;
-                    } else {
-                        while (S.a[ic] > p_lo) ic--;
-                    }
-                    const int32_t e_i = S.e[ic];
-                    const int64_t rpos_lo = (int64_t)S.resume[ic] + (p_lo - e_i);
-                    if (p_lo >= e_i && p_lo + 127 < S.a[ic + 1] && rpos_lo + 127 < rp.contig_len) {
-                        fast = true;
-                        rpos_l = (int32_t)rpos_lo + (rc ? 124 - 4 * lane : 4 * lane);
-                    } else {
-                        // mixed group: each lane checks its own 4 positions (cursor starts at the group's record)
-                        const int32_t p0 = rc ? (L - 4 - j) : j;
-                        int il = ic;
-                        while (S.a[il + 1] <= p0) il++;
-                        const int32_t e_l = S.e[il];
-                        const int64_t rpos = (int64_t)S.resume[il] + (p0 - e_l);
-                        if (p0 >= e_l && p0 + 3 < S.a[il + 1] && rpos + 3 < rp.contig_len) {
-                            fast = true;
-                            rpos_l = (int32_t)rpos;
-                        }
-                    }
+            const int32_t jb = j0 + 512 * blk;  // first row position of the block
+            if (jb >= jo_lo && jb + 512 <= jo_hi) {
+                // ---- whole block inside the pass: one warp-uniform test against the records ----
+                const int32_t p_lo = rc ? (L - 512 - jb) : jb;  // lowest haplotype position of the block
+                if (!rc) {
+                    while (S.a[ic + 1] <= p_lo) ic++;
+                } else {
+                    while (S.a[ic] > p_lo) ic--;
                 }
-                if (fast) {
-                    st[k] = 1;
-                    rp32[k] = rpos_l;
-                    const uint32_t *w = reinterpret_cast<const uint32_t *>(
-                        reinterpret_cast<uintptr_t>(refrow + rpos_l) & ~(uintptr_t)3);
-                    w0[k] = __ldg(w);
-                    w1[k] = __ldg(w + 1);  // (readable: buffers carry >= 16 B of slack)
-                } else if (cg + lane < n_chunks) {
-                    st[k] = 2;
+                const int32_t e_i = S.e[ic];
+                const int64_t rpos_lo = (int64_t)S.resume[ic] + (p_lo - e_i);
+                if (p_lo >= e_i && p_lo + 511 < S.a[ic + 1] && rpos_lo + 511 < rp.contig_len) {
+                    // 512 reference bytes in a row: all 8 loads first, then 4 encodes + stores
+                    const int32_t r_lane = (int32_t)rpos_lo + (rc ? 508 - 4 * lane : 4 * lane);
+                    const uintptr_t addr = reinterpret_cast<uintptr_t>(refrow + r_lane);
+                    const uint32_t *w = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
+                    const unsigned sh = (unsigned)(addr & 3) * 8u;
+                    uint32_t w0[4], w1[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int off = rc ? -32 * k : 32 * k;  // group k of the OUTPUT lies 128 bytes further (back)
+                        w0[k] = __ldg(w + off);
+                        w1[k] = __ldg(w + off + 1);  // (readable: buffers carry >= 16 B of slack)
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        uint32_t v = __funnelshift_r(w0[k], w1[k], sh);  // byte i = haplotype position p0+i
+                        if (rc) v = __byte_perm(v, 0, 0x0123);            // byte i = output position j+i
+                        emit_ref4(jb + 128 * k + 4 * lane, v, r_lane + (rc ? -128 * k : 128 * k));
+                    }
+                    continue;
                 }
             }
-            // ---- phase 2: assemble, encode, store ----
-#pragma unroll
+            // ---- block with variants / pads / pass edges: group by group ----
+#pragma unroll 1
             for (int k = 0; k < 4; k++) {
-                if (st[k] == 0) continue;
-                const int32_t j = j0 + 4 * ((blk * 4 + k) * 32 + lane);
-                if (st[k] == 1) {
-                    const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(refrow + rp32[k]) & 3) * 8u;
-                    uint32_t v = __funnelshift_r(w0[k], w1[k], sh);  // byte i = haplotype position p0+i
-                    if (rc) v = __byte_perm(v, 0, 0x0123);            // byte i = output position j+i
-                    if (OH) {
-                        const uint32_t *lut = s_lut + (rc ? 256 : 0);
-                        uint4 o;
-                        o.x = lut[v & 0xffu];
-                        o.y = lut[(v >> 8) & 0xffu];
-                        o.z = lut[(v >> 16) & 0xffu];
-                        o.w = lut[v >> 24];
-                        if (MODE == GVL_MODE_ONEHOT) {
-                            *reinterpret_cast<uint4 *>(out_row + 4 * (int64_t)j) = o;
+                const int32_t cg = blk * 128 + 32 * k;  // first chunk of the group
+                if (cg >= n_chunks) break;
+                const int32_t jg = j0 + 4 * cg;
+                const int32_t j = jg + 4 * lane;
+                if (jg >= jo_lo && jg + 128 <= jo_hi) {
+                    const int32_t p_lo = rc ? (L - 128 - jg) : jg;
+                    const int ig = find_rec(S, m, p_lo);
+                    const int32_t e_i = S.e[ig];
+                    const int64_t rpos_lo = (int64_t)S.resume[ig] + (p_lo - e_i);
+                    if (p_lo >= e_i && p_lo + 127 < S.a[ig + 1] && rpos_lo + 127 < rp.contig_len) {
+                        const int32_t r_lane = (int32_t)rpos_lo + (rc ? 124 - 4 * lane : 4 * lane);
+                        const uintptr_t addr = reinterpret_cast<uintptr_t>(refrow + r_lane);
+                        const uint32_t *w = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
+                        uint32_t v = __funnelshift_r(__ldg(w), __ldg(w + 1), (unsigned)(addr & 3) * 8u);
+                        if (rc) v = __byte_perm(v, 0, 0x0123);
+                        emit_ref4(j, v, r_lane);
+                        continue;
+                    }
+                }
+                // ---- generic chunk: resolve each position against the records ----
+                if (cg + lane >= n_chunks) continue;
+                const int32_t pa = rc ? (L - 4 - j) : j;  // haplotype position of byte t=0 (ascending in t)
+                int il = -1;
+#pragma unroll 1
+                for (int t = 0; t < 4; t++) {
+                    const int q = rc ? 3 - t : t;
+                    const int32_t jj = j + q;
+                    if (jj < jo_lo || jj >= jo_hi) continue;
+                    const int32_t p = pa + t;
+                    if (il < 0) il = find_rec(S, m, p);
+                    while (S.a[il + 1] <= p) il++;
+                    uint32_t b;
+                    int32_t av = -1, ap;
+                    if (p < S.e[il]) {
+                        const int64_t src = S.src[il];
+                        if (src == ALT_PAD) {
+                            b = P.pad_char;
+                            ap = -1;  // leading pad (src/reconstruct/mod.rs:75-80)
                         } else {
-                            uint8_t *op = out_row + j;  // (4, L) block of this row
-                            const uint32_t xy0 = __byte_perm(o.x, o.y, 0x5140), xy1 = __byte_perm(o.x, o.y, 0x7362);
-                            const uint32_t zw0 = __byte_perm(o.z, o.w, 0x5140), zw1 = __byte_perm(o.z, o.w, 0x7362);
-                            *reinterpret_cast<uint32_t *>(op) = __byte_perm(xy0, zw0, 0x5410);
-                            *reinterpret_cast<uint32_t *>(op + L) = __byte_perm(xy0, zw0, 0x7632);
-                            *reinterpret_cast<uint32_t *>(op + 2 * (int64_t)L) = __byte_perm(xy1, zw1, 0x5410);
-                            *reinterpret_cast<uint32_t *>(op + 3 * (int64_t)L) = __byte_perm(xy1, zw1, 0x7632);
+                            b = P.alt[src + (p - S.a[il])];
+                            if (ANNOT) {
+                                av = S.vidx[il];
+                                ap = S.vpos[il];
+                            }
                         }
                     } else {
-                        if (rc) v = comp4(v);
-                        *reinterpret_cast<uint32_t *>(out_row + j) = v;
-                        if (ANNOT) {
-                            const int32_t r0 = rp32[k];
-                            const int64_t g = rp.out_off + j;
-                            *reinterpret_cast<int4 *>(P.annot_v + g) = make_int4(-1, -1, -1, -1);
-                            *reinterpret_cast<int4 *>(P.annot_pos + g) =
-                                rc ? make_int4(r0 + 3, r0 + 2, r0 + 1, r0) : make_int4(r0, r0 + 1, r0 + 2, r0 + 3);
+                        const int64_t rpos = (int64_t)S.resume[il] + (p - S.e[il]);
+                        if (rpos < rp.contig_len) {
+                            b = refrow[rpos];
+                            ap = (int32_t)rpos;
+                        } else {
+                            b = P.pad_char;
+                            ap = INT32_MAX;  // trailing pad (:248-253)
                         }
                     }
-                } else {
-                    // slow path: positions of the chunk that belong to this pass, one at a time
-#pragma unroll 1
-                    for (int q = 0; q < 4; q++) {
-                        const int32_t jj = j + q;
-                        if (jj < jo_lo || jj >= jo_hi) continue;
-                        const int32_t p = rc ? (L - 1 - jj) : jj;
-                        PosInfo pi = resolve_pos(S, m, p, rp, P);
-                        uint32_t b = pi.byte;
-                        if (rc) b = comp1(b);
-                        if (MODE == GVL_MODE_ONEHOT) {
-                            *reinterpret_cast<uint32_t *>(out_row + 4 * (int64_t)jj) = onehot1(b);
-                        } else if (MODE == GVL_MODE_ONEHOT_CF) {
-                            uint8_t *op = out_row + jj;
-                            op[0] = (b == 'A');
-                            op[L] = (b == 'C');
-                            op[2 * (int64_t)L] = (b == 'G');
-                            op[3 * (int64_t)L] = (b == 'T');
-                        } else {
-                            out_row[jj] = (uint8_t)b;
-                            if (ANNOT) {
-                                P.annot_v[rp.out_off + jj] = pi.av;
-                                P.annot_pos[rp.out_off + jj] = pi.ap;
-                            }
+                    if (rc) b = comp1(b);
+                    if (MODE == GVL_MODE_ONEHOT) {
+                        *reinterpret_cast<uint32_t *>(out_row + 4 * (int64_t)jj) = onehot1(b);
+                    } else if (MODE == GVL_MODE_ONEHOT_CF) {
+                        uint8_t *op = out_row + jj;
+                        op[0] = (b == 'A');
+                        op[L] = (b == 'C');
+                        op[2 * (int64_t)L] = (b == 'G');
+                        op[3 * (int64_t)L] = (b == 'T');
+                    } else {
+                        out_row[jj] = (uint8_t)b;
+                        if (ANNOT) {
+                            P.annot_v[rp.out_off + jj] = av;
+                            P.annot_pos[rp.out_off + jj] = ap;
                         }
                     }
                 }
@@ -839,13 +831,18 @@ int gvl_dev_hap_exec(gvl_ctx *ctx, const gvl_sparse_tables *tab, int mode, uint8
     }
     if (grid == 0) return GVL_OK;
     if (grid > INT32_MAX) return fail(GVL_ERR_ARG, "gvl_dev_hap_exec: too many tiles");
+    dim3 grid3((unsigned)grid, 1, 1);
+    if (ctx->fixed_len >= 0) {  // (tile, row) grid: no division in the kernel
+        const int64_t gy = imin64(ctx->n_work, 65535);
+        grid3 = dim3((unsigned)P.tiles_per_row, (unsigned)gy, (unsigned)((ctx->n_work + 65534) / 65535));
+    }
     if (mode == GVL_MODE_ONEHOT_CF && (ctx->fixed_len & 3))
         return fail(GVL_ERR_ARG, "gvl_dev_hap_exec: channels-first one-hot needs output_length %% 4 == 0");
     switch (mode) {
-        case GVL_MODE_U8: hap_exec_kernel<GVL_MODE_U8><<<(unsigned)grid, EXEC_THREADS, 0, st>>>(P); break;
-        case GVL_MODE_ONEHOT: hap_exec_kernel<GVL_MODE_ONEHOT><<<(unsigned)grid, EXEC_THREADS, 0, st>>>(P); break;
-        case GVL_MODE_ONEHOT_CF: hap_exec_kernel<GVL_MODE_ONEHOT_CF><<<(unsigned)grid, EXEC_THREADS, 0, st>>>(P); break;
-        case GVL_MODE_ANNOTATED: hap_exec_kernel<GVL_MODE_ANNOTATED><<<(unsigned)grid, EXEC_THREADS, 0, st>>>(P); break;
+        case GVL_MODE_U8: hap_exec_kernel<GVL_MODE_U8><<<grid3, EXEC_THREADS, 0, st>>>(P); break;
+        case GVL_MODE_ONEHOT: hap_exec_kernel<GVL_MODE_ONEHOT><<<grid3, EXEC_THREADS, 0, st>>>(P); break;
+        case GVL_MODE_ONEHOT_CF: hap_exec_kernel<GVL_MODE_ONEHOT_CF><<<grid3, EXEC_THREADS, 0, st>>>(P); break;
+        case GVL_MODE_ANNOTATED: hap_exec_kernel<GVL_MODE_ANNOTATED><<<grid3, EXEC_THREADS, 0, st>>>(P); break;
         default: return fail(GVL_ERR_ARG, "gvl_dev_hap_exec: unknown mode %d", mode);
     }
     GVL_LAUNCH_CHECK();

@@ -564,53 +564,80 @@ __global__ void __launch_bounds__(EXEC_THREADS) hap_exec_kernel(HapExecParams P)
                 // ---- generic chunk: resolve each position against the records ----
                 if (cg + lane >= n_chunks) continue;
                 const int32_t pa = rc ? (L - 4 - j) : j;  // haplotype position of byte t=0 (ascending in t)
+                const bool full = (j >= jo_lo) && (j + 4 <= jo_hi);
+                uint32_t v = 0;          // byte t = haplotype position pa+t (raw, not complemented)
+                int32_t av[4], ap[4];    // annotations in haplotype order
                 int il = -1;
-#pragma unroll 1
+#pragma unroll
                 for (int t = 0; t < 4; t++) {
-                    const int q = rc ? 3 - t : t;
-                    const int32_t jj = j + q;
-                    if (jj < jo_lo || jj >= jo_hi) continue;
+                    av[t] = -1;
+                    ap[t] = -1;
+                    const int32_t jj = rc ? (j + 3 - t) : (j + t);
+                    if (!full && (jj < jo_lo || jj >= jo_hi)) continue;
                     const int32_t p = pa + t;
                     if (il < 0) il = find_rec(S, m, p);
                     while (S.a[il + 1] <= p) il++;
                     uint32_t b;
-                    int32_t av = -1, ap;
                     if (p < S.e[il]) {
                         const int64_t src = S.src[il];
                         if (src == ALT_PAD) {
-                            b = P.pad_char;
-                            ap = -1;  // leading pad (src/reconstruct/mod.rs:75-80)
+                            b = P.pad_char;  // leading pad (src/reconstruct/mod.rs:75-80): annotations (-1, -1)
                         } else {
                             b = P.alt[src + (p - S.a[il])];
                             if (ANNOT) {
-                                av = S.vidx[il];
-                                ap = S.vpos[il];
+                                av[t] = S.vidx[il];
+                                ap[t] = S.vpos[il];
                             }
                         }
                     } else {
                         const int64_t rpos = (int64_t)S.resume[il] + (p - S.e[il]);
                         if (rpos < rp.contig_len) {
                             b = refrow[rpos];
-                            ap = (int32_t)rpos;
+                            ap[t] = (int32_t)rpos;
                         } else {
                             b = P.pad_char;
-                            ap = INT32_MAX;  // trailing pad (:248-253)
+                            ap[t] = INT32_MAX;  // trailing pad (:248-253)
                         }
                     }
-                    if (rc) b = comp1(b);
-                    if (MODE == GVL_MODE_ONEHOT) {
-                        *reinterpret_cast<uint32_t *>(out_row + 4 * (int64_t)jj) = onehot1(b);
-                    } else if (MODE == GVL_MODE_ONEHOT_CF) {
-                        uint8_t *op = out_row + jj;
-                        op[0] = (b == 'A');
-                        op[L] = (b == 'C');
-                        op[2 * (int64_t)L] = (b == 'G');
-                        op[3 * (int64_t)L] = (b == 'T');
+                    v |= b << (8 * t);
+                }
+                if (rc) v = __byte_perm(v, 0, 0x0123);  // byte i = output position j+i
+                if (full) {
+                    if (OH) {
+                        emit_ref4(j, v, 0);
                     } else {
-                        out_row[jj] = (uint8_t)b;
+                        if (rc) v = comp4(v);
+                        *reinterpret_cast<uint32_t *>(out_row + j) = v;
                         if (ANNOT) {
-                            P.annot_v[rp.out_off + jj] = av;
-                            P.annot_pos[rp.out_off + jj] = ap;
+                            const int64_t g = rp.out_off + j;
+                            *reinterpret_cast<int4 *>(P.annot_v + g) =
+                                rc ? make_int4(av[3], av[2], av[1], av[0]) : make_int4(av[0], av[1], av[2], av[3]);
+                            *reinterpret_cast<int4 *>(P.annot_pos + g) =
+                                rc ? make_int4(ap[3], ap[2], ap[1], ap[0]) : make_int4(ap[0], ap[1], ap[2], ap[3]);
+                        }
+                    }
+                } else {
+                    // chunk cut by a pass / row boundary: position-wise stores
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int32_t jj = j + q;
+                        if (jj < jo_lo || jj >= jo_hi) continue;
+                        uint32_t b = (v >> (8 * q)) & 0xffu;
+                        if (rc) b = comp1(b);
+                        if (MODE == GVL_MODE_ONEHOT) {
+                            *reinterpret_cast<uint32_t *>(out_row + 4 * (int64_t)jj) = onehot1(b);
+                        } else if (MODE == GVL_MODE_ONEHOT_CF) {
+                            uint8_t *op = out_row + jj;
+                            op[0] = (b == 'A');
+                            op[L] = (b == 'C');
+                            op[2 * (int64_t)L] = (b == 'G');
+                            op[3 * (int64_t)L] = (b == 'T');
+                        } else {
+                            out_row[jj] = (uint8_t)b;
+                            if (ANNOT) {
+                                P.annot_v[rp.out_off + jj] = av[rc ? 3 - q : q];
+                                P.annot_pos[rp.out_off + jj] = ap[rc ? 3 - q : q];
+                            }
                         }
                     }
                 }

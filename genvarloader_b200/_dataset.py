@@ -1,0 +1,556 @@
+"""GPU-resident `Dataset`: the reference's `gvl.Dataset` surface for the haplotype / track hot path.
+
+Mirrors (names, argument meaning, error behaviour, return shapes):
+  * `Dataset` state + `with_settings / with_len / with_seqs / with_tracks / with_insertion_fill /
+    with_output_format / subset_to / __getitem__`      python/genvarloader/_dataset/_impl.py:78-2121
+  * index parsing (`DatasetIndexer.parse_idx`)          python/genvarloader/_dataset/_indexing.py:208-264
+  * read-time prep: jitter, strand mask, shifts, seeds   _dataset/_query.py:153-204, _haps.py:678-768,
+                                                         _reconstruct.py:168-226
+  * output shaping (to_fixed / pad / ragged, squeeze)    _dataset/_query.py:94-127
+
+Host work per call is O(batch) numpy (index maths, RNG draws in the reference's order); everything
+sample-scale lives on the GPU inside `Engine`.  Results are torch CUDA tensors.
+Not supported (outside the hot-path scope, raise): splicing, `variants` / `variant-windows`, AF filters.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field, replace
+from typing import Literal
+
+import numpy as np
+import torch
+
+from ._engine import Engine
+from ._insertion_fill import InsertionFill, Repeat5p, lower
+from ._types import AnnotatedHaps, Ragged, RaggedAnnotatedHaps
+
+SeqKind = Literal["reference", "haplotypes", "annotated"]
+N_CHAR = ord("N")
+
+
+def _idx_to_array(idx, n: int) -> np.ndarray:
+    if isinstance(idx, slice):
+        return np.arange(n, dtype=np.int64)[idx]
+    a = np.asarray(idx)
+    if a.dtype == np.bool_:
+        if a.shape != (n,):
+            raise IndexError(f"boolean index of shape {a.shape} does not match axis of size {n}")
+        return np.flatnonzero(a).astype(np.int64)
+    a = a.astype(np.int64)
+    if ((a < -n) | (a >= n)).any():
+        raise IndexError(f"index out of bounds for axis of size {n}")
+    return np.where(a < 0, a + n, a)
+
+
+@dataclass(frozen=True)
+class Dataset:
+    """Effective shape `(n_regions, n_samples, [tracks], [ploidy], output_length)`; indexable on the
+    first two axes like a 2-D array (reference docstring, _impl.py:80-115)."""
+
+    engine: Engine
+    full_regions: np.ndarray            # int32 (R, 4): contig_idx, start, end, strand
+    sample_names: tuple
+    ploidy: int
+    max_jitter: int = 0
+    track_kinds: dict = field(default_factory=dict)   # name -> "sample" | "annot"
+    # ---- settings (reference defaults: _impl.py:119-162) ----
+    output_length: object = "ragged"                  # "ragged" | "variable" | int
+    sequence_type: object = "haplotypes"              # "reference" | "haplotypes" | "annotated" | None
+    active_tracks: tuple = ()
+    insertion_fill: dict = field(default_factory=dict)
+    jitter: int = 0
+    deterministic: bool = True
+    rc_neg: bool = True
+    var_filter: object = None                         # None | "exonic"
+    realign_tracks: bool = True
+    output_format: str = "ragged"                     # "ragged" | "flat"  (with_output_format)
+    encoding: str = "bytes"                           # "bytes" | "onehot" | "onehot_cf"  (this build's fused one-hot)
+    rng: np.random.Generator = field(default_factory=np.random.default_rng)
+    region_subset: object = None
+    sample_subset: object = None
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def from_arrays(cls, device, reference, ref_offsets, v_starts, ilens, alt_alleles, alt_offsets, geno_v_idxs,
+                    geno_offsets, regions, n_samples: int, ploidy: int, max_jitter: int = 0, tracks: dict | None = None,
+                    track_kinds: dict | None = None, sample_names=None, rng=None) -> "Dataset":
+        """In-memory dataset (the GPU counterpart of `get_dummy_dataset`, python/genvarloader/_dummy.py).
+        `tracks`: name -> (itv_starts, itv_ends, itv_values, itv_offsets); SAMPLE tracks have one interval slot
+        per (region, sample), ANNOT tracks one per region (_reconstruct.py:233-236)."""
+        eng = Engine(device, reference, ref_offsets, v_starts, ilens, alt_alleles, alt_offsets, geno_v_idxs, geno_offsets)
+        kinds = {}
+        for name, t in (tracks or {}).items():
+            eng.add_track(name, *t)
+            kinds[name] = (track_kinds or {}).get(name, "sample")
+        regions = np.ascontiguousarray(regions, np.int32)
+        if regions.shape[1] == 3:
+            regions = np.concatenate([regions, np.ones((len(regions), 1), np.int32)], 1)
+        names = tuple(sample_names) if sample_names is not None else tuple(f"s{i}" for i in range(n_samples))
+        return cls(engine=eng, full_regions=regions, sample_names=names, ploidy=int(ploidy), max_jitter=int(max_jitter),
+                   track_kinds=kinds, active_tracks=tuple(kinds), rng=np.random.default_rng(rng))
+
+    @classmethod
+    def from_synth(cls, device, d, rng=None) -> "Dataset":
+        """From a `genvarloader_b200.synth.SynthData`."""
+        return cls.from_arrays(device, d.reference, d.ref_offsets, d.v_starts, d.ilens, d.alt_alleles, d.alt_offsets,
+                               d.geno_v_idxs, d.geno_offsets, d.regions, d.n_samples, d.ploidy, d.max_jitter, d.tracks,
+                               rng=rng)
+
+    @classmethod
+    def open(cls, path, *a, **k):
+        raise NotImplementedError(
+            "Reading the on-disk GVL dataset layout is the next scope row (SURVEY.md 8f-1); build an in-memory "
+            "dataset with Dataset.from_arrays(...) for now.")
+
+    # ------------------------------------------------------------------ properties (reference: _impl.py:954-1110)
+    @property
+    def n_regions(self) -> int:
+        return len(self._r_idx)
+
+    @property
+    def n_samples(self) -> int:
+        return len(self._s_idx)
+
+    @property
+    def samples(self) -> list:
+        return [self.sample_names[i] for i in self._s_idx]
+
+    @property
+    def shape(self) -> tuple:
+        return (self.n_regions, self.n_samples)
+
+    @property
+    def full_shape(self) -> tuple:
+        return (len(self.full_regions), len(self.sample_names))
+
+    @property
+    def available_tracks(self) -> list:
+        return list(self.track_kinds)
+
+    @property
+    def is_subset(self) -> bool:
+        return self.region_subset is not None or self.sample_subset is not None
+
+    @property
+    def regions(self) -> np.ndarray:
+        return self.full_regions[self._r_idx]
+
+    def __len__(self) -> int:
+        return self.n_regions * self.n_samples
+
+    @property
+    def _r_idx(self) -> np.ndarray:
+        return np.arange(len(self.full_regions)) if self.region_subset is None else self.region_subset
+
+    @property
+    def _s_idx(self) -> np.ndarray:
+        return np.arange(len(self.sample_names)) if self.sample_subset is None else self.sample_subset
+
+    # ------------------------------------------------------------------ with_* (immutable evolution)
+    def _check_valid_state(self) -> None:
+        """Same checks and messages as the reference's `_check_valid_state` (_impl.py:501-568) for this scope."""
+        if self.jitter < 0:
+            raise ValueError(f"Jitter ({self.jitter}) must be a non-negative integer.")
+        if self.jitter > self.max_jitter:
+            raise ValueError(f"Jitter ({self.jitter}) must be less than or equal to the maximum jitter of the dataset ({self.max_jitter}).")
+        if isinstance(self.output_length, (int, np.integer)) and not isinstance(self.output_length, bool):
+            if self.output_length < 1:
+                raise ValueError(f"Output length ({self.output_length}) must be a positive integer.")
+            min_r_len = int((self.full_regions[:, 2] - self.full_regions[:, 1]).min())
+            max_output_length = min_r_len + 2 * self.max_jitter
+            eff_length = int(self.output_length) + 2 * self.jitter
+            if eff_length > max_output_length:
+                raise ValueError(
+                    f"Effective length (out_len={self.output_length}) + 2 * ({self.jitter=}) = {eff_length} must be less"
+                    f" than or equal to the maximum output length of the dataset ({max_output_length})."
+                    f" The maximum output length is the minimum region length ({min_r_len}) + 2 * (max_jitter={self.max_jitter}).")
+        elif self.output_length not in ("ragged", "variable"):
+            raise ValueError(f"Output length must be 'ragged', 'variable' or a positive integer, got {self.output_length!r}")
+        if self.encoding != "bytes" and self.sequence_type not in ("haplotypes", "reference"):
+            raise ValueError("one-hot encoding applies to 'haplotypes' / 'reference' sequences only")
+        if self.encoding == "onehot_cf" and not isinstance(self.output_length, (int, np.integer)):
+            raise ValueError("channels-first one-hot needs a fixed output length")
+
+    def _evolve(self, **kw) -> "Dataset":
+        ds = replace(self, **kw)
+        ds._check_valid_state()
+        return ds
+
+    def with_settings(self, jitter=None, rng=None, deterministic=None, rc_neg=None, var_filter=None, realign_tracks=None,
+                      min_af=None, max_af=None, splice_info=None, **unsupported) -> "Dataset":
+        """Reference: `Dataset.with_settings`, _impl.py:228-499 (hot-path settings only)."""
+        if min_af not in (None, False) or max_af not in (None, False):
+            raise NotImplementedError("Filtering by AF is not supported for haplotype output yet.")  # _haps.py:695-698
+        if splice_info not in (None, False):
+            raise NotImplementedError("Splicing is outside the scope of the B200 hot path (SURVEY.md 8f-3).")
+        if unsupported:
+            raise NotImplementedError(f"settings outside the hot-path scope: {sorted(unsupported)}")
+        kw = {}
+        if jitter is not None:
+            kw["jitter"] = int(jitter)
+        if rng is not None:
+            kw["rng"] = np.random.default_rng(rng)
+        if deterministic is not None:
+            kw["deterministic"] = bool(deterministic)
+        if rc_neg is not None:
+            kw["rc_neg"] = bool(rc_neg)
+        if var_filter is not None:
+            if var_filter not in (False, "exonic"):
+                raise ValueError(f"var_filter must be False or 'exonic', got {var_filter!r}")
+            kw["var_filter"] = None if var_filter is False else "exonic"
+        if realign_tracks is not None:
+            kw["realign_tracks"] = bool(realign_tracks)
+        return self._evolve(**kw)
+
+    def with_len(self, output_length) -> "Dataset":
+        """Reference: `Dataset.with_len`, _impl.py:570-647."""
+        if isinstance(output_length, (int, np.integer)) and not isinstance(output_length, bool):
+            if output_length < 1:
+                raise ValueError(f"Output length ({output_length}) must be a positive integer.")
+            output_length = int(output_length)
+        return self._evolve(output_length=output_length)
+
+    def with_seqs(self, kind) -> "Dataset":
+        """Reference: `Dataset.with_seqs`, _impl.py:649-783."""
+        if kind in ("variants", "variant-windows"):
+            raise NotImplementedError(f"with_seqs({kind!r}) is outside the scope of the B200 hot path.")
+        if kind not in (None, "reference", "haplotypes", "annotated"):
+            raise ValueError(f"Unknown sequence type {kind!r}")
+        enc = self.encoding if kind in ("haplotypes", "reference") else "bytes"
+        return self._evolve(sequence_type=kind, encoding=enc)
+
+    def with_encoding(self, encoding: str) -> "Dataset":
+        """Fused one-hot output (this build's extension; the reference leaves one-hot to `seqpro.DNA.ohe`,
+        docs/source/index.md:108-119).  "onehot": uint8 (..., L, 4); "onehot_cf": uint8 (..., 4, L); alphabet ACGT."""
+        if encoding not in ("bytes", "onehot", "onehot_cf"):
+            raise ValueError(f"Unknown encoding {encoding!r}")
+        return self._evolve(encoding=encoding)
+
+    def with_tracks(self, tracks=None, kind=None) -> "Dataset":
+        """Reference: `Dataset.with_tracks`, _impl.py:785-839.  `False`/`[]` disables tracks."""
+        if kind not in (None, "tracks"):
+            raise NotImplementedError("only kind='tracks' (base-pair resolution) is in the hot-path scope")
+        if tracks is None:
+            names = tuple(self.track_kinds)
+        elif tracks is False:
+            names = ()
+        else:
+            names = (tracks,) if isinstance(tracks, str) else tuple(tracks)
+        missing = [t for t in names if t not in self.track_kinds]
+        if missing:
+            raise ValueError(f"Track(s) {missing} not found. Available tracks: {self.available_tracks}")
+        return self._evolve(active_tracks=names)
+
+    def with_insertion_fill(self, strategy) -> "Dataset":
+        """Reference: `Dataset.with_insertion_fill`, _impl.py:841-878 (one strategy for all tracks or a dict)."""
+        if isinstance(strategy, InsertionFill):
+            fills = {name: strategy for name in self.track_kinds}
+        else:
+            fills = dict(self.insertion_fill)
+            for name, s in dict(strategy).items():
+                if name not in self.track_kinds:
+                    raise ValueError(f"Track {name!r} not found. Available tracks: {self.available_tracks}")
+                if not isinstance(s, InsertionFill):
+                    raise TypeError("strategies must be InsertionFill instances")
+                fills[name] = s
+        return self._evolve(insertion_fill=fills)
+
+    def with_output_format(self, fmt: str) -> "Dataset":
+        """Reference: `Dataset.with_output_format`, _impl.py:880-952.  "flat" returns `Ragged` triples untouched."""
+        if fmt not in ("ragged", "flat"):
+            raise ValueError(f"Unknown output format {fmt!r}")
+        return self._evolve(output_format=fmt)
+
+    def subset_to(self, regions=None, samples=None) -> "Dataset":
+        """Reference: `Dataset.subset_to`, _impl.py:1153-1221 (integer / slice / boolean / sample-name selectors)."""
+        kw = {}
+        if regions is not None:
+            kw["region_subset"] = self._r_idx[_idx_to_array(regions, self.n_regions)]
+        if samples is not None:
+            if isinstance(samples, str) or (np.ndim(samples) > 0 and len(samples) and isinstance(samples[0], str)):
+                names = [samples] if isinstance(samples, str) else list(samples)
+                lut = {n: i for i, n in enumerate(self.sample_names)}
+                try:
+                    kw["sample_subset"] = np.array([lut[n] for n in names], np.int64)
+                except KeyError as e:
+                    raise KeyError(f"Sample {e.args[0]!r} not found") from None
+            else:
+                kw["sample_subset"] = self._s_idx[_idx_to_array(samples, self.n_samples)]
+        return self._evolve(**kw)
+
+    def to_full_dataset(self) -> "Dataset":
+        return self._evolve(region_subset=None, sample_subset=None)
+
+    # ------------------------------------------------------------------ indexing
+    def _parse_idx(self, idx):
+        """`DatasetIndexer.parse_idx`, _indexing.py:208-264: flat dataset indices (row-major over the FULL
+        (regions, samples) grid), squeeze flag, optional outer reshape -- "basic" (ints / slices), "adv" (two
+        arrays, paired) and "combo" (one array, one basic -> outer product) indexing."""
+        if not isinstance(idx, tuple):
+            r, s = idx, slice(None)
+        elif len(idx) == 1:
+            r, s = idx[0], slice(None)
+        elif len(idx) == 2:
+            r, s = idx
+        else:
+            raise IndexError("a Dataset is indexed by (regions, samples)")
+        is_basic = lambda x: isinstance(x, (int, np.integer, slice))
+        is_int = lambda x: isinstance(x, (int, np.integer))
+        n_s = len(self.sample_names)
+        r_raw = self._r_idx[_idx_to_array(r, self.n_regions)]
+        s_raw = self._s_idx[_idx_to_array(s, self.n_samples)]
+        squeeze, out_reshape = False, None
+        if is_basic(r) and is_basic(s):
+            squeeze = is_int(r) and is_int(s)
+            ri, si = np.atleast_1d(r_raw), np.atleast_1d(s_raw)
+            flat = (ri[:, None] * n_s + si[None, :]).squeeze()
+            if isinstance(r, slice) and isinstance(s, slice):
+                out_reshape = (len(ri), len(si))
+            if flat.ndim > 1:
+                out_reshape = flat.shape
+        elif not is_basic(r) and not is_basic(s):
+            ri, si = np.broadcast_arrays(r_raw, s_raw)
+            flat = ri * n_s + si
+            if flat.ndim > 1:
+                out_reshape = flat.shape
+        else:
+            flat = r_raw.ravel()[:, None] * n_s + s_raw.ravel()[None, :]
+            if r_raw.ndim > 1 or s_raw.ndim > 1:
+                out_reshape = (*r_raw.shape, *s_raw.shape)
+            else:
+                out_reshape = flat.shape
+        return np.asarray(flat, np.int64).ravel(), squeeze, out_reshape
+
+    # ------------------------------------------------------------------ the hot path
+    def __getitem__(self, idx):
+        """Reference: `Dataset.__getitem__` _impl.py:2074-2121 -> `_query.getitem` _query.py:66-204."""
+        if self.sequence_type is None and not self.active_tracks:
+            raise ValueError("Dataset has neither sequences nor tracks active.")
+        ds_idx, squeeze, out_reshape = self._parse_idx(idx)
+        S = len(self.sample_names)
+        r_idx, s_idx = ds_idx // S, ds_idx % S
+
+        # ---- _getitem_unspliced, _query.py:161-175 ----
+        regions = self.full_regions[r_idx].copy()
+        lengths = regions[:, 2] - regions[:, 1]
+        jitter_off = self.rng.integers(-self.jitter, self.jitter + 1, size=len(regions), dtype=np.int32)
+        regions[:, 1] += jitter_off
+        regions[:, 2] = regions[:, 1] + lengths
+
+        out = self._reconstruct(ds_idx, r_idx, s_idx, regions)
+        out = tuple(self._shape_output(o, out_reshape, squeeze) for o in out)
+        return out[0] if len(out) == 1 else out
+
+    # ---- reconstructors: Haps / HapsTracks / Tracks (_haps.py:578-870, _reconstruct.py:132-307, _tracks.py:370-420)
+    def _reconstruct(self, ds_idx, r_idx, s_idx, regions):
+        eng, dev, p = self.engine, self.engine.device, self.ploidy
+        b = len(ds_idx)
+        fixed = isinstance(self.output_length, (int, np.integer))
+        want_seqs = self.sequence_type is not None
+        want_tracks = len(self.active_tracks) > 0
+        is_ref = self.sequence_type == "reference"
+        realign = want_tracks and want_seqs and not is_ref and self.realign_tracks
+        to_rc_q = (self.full_regions[r_idx, 3] == -1) if self.rc_neg else None
+        lengths = (regions[:, 2] - regions[:, 1]).astype(np.int64)
+
+        # geno_offset_idx = ravel (region, sample, ploid), _haps.py:757-768.  "reference" rows use the engine's
+        # empty CSR slot: the zero-variant case of the same kernels (get_reference, src/reference/mod.rs:56-120).
+        rows_p = 1 if is_ref else p
+        if is_ref:
+            goi = np.full((b, 1), eng.empty_slot, np.int64)
+        else:
+            goi = ds_idx[:, None] * p + np.arange(p, dtype=np.int64)[None, :]
+        to_rc = None if to_rc_q is None else np.repeat(to_rc_q, rows_p)  # _haps.py:838-843
+
+        pk = _Packer(dev)  # one pinned staging buffer, one H2D copy for all O(batch) arrays
+        i_reg = pk.add(regions[:, :3], np.int32)
+        i_goi = pk.add(goi, np.int64)
+        i_rc = pk.add(to_rc, np.uint8) if to_rc is not None else None
+        i_sh = pk.add(np.zeros((b, rows_p), np.int32), np.int32)
+        i_tr = i_trc = None
+        if want_tracks:
+            oi = np.stack([ds_idx if self.track_kinds[n] == "sample" else r_idx for n in self.active_tracks])
+            i_tr = pk.add(oi, np.int64)
+            if to_rc_q is not None:
+                i_trc = pk.add(to_rc_q, np.uint8)
+        pk.upload()
+        t_reg, t_goi, t_shifts = pk.get(i_reg), pk.get(i_goi), pk.get(i_sh)
+        t_rc = pk.get(i_rc) if i_rc is not None else None
+
+        max_rec = 0 if is_ref else eng.max_records(goi)
+        keep = keep_off = None
+        if self.var_filter == "exonic" and not is_ref:
+            keep, keep_off = self._exonic_keep(goi, regions)
+
+        results = []
+        oo = total = diffs = None
+        if want_seqs:
+            out_len = int(self.output_length) if fixed else -1
+            if fixed and not self.deterministic and not is_ref:
+                # random shifts need the diffs first (_haps.py:720-730): one extra device pass + sync; the
+                # draw itself stays on the host generator so seeded runs follow the reference's RNG order
+                dd = eng.get_diffs(t_goi, t_reg[:, 1].contiguous(), t_reg[:, 2].contiguous(), keep, keep_off).cpu().numpy()
+                max_shift = dd.clip(min=0) + (lengths - out_len).clip(min=0)[:, None]
+                t_shifts = torch.from_numpy(self.rng.integers(0, max_shift + 1, dtype=np.int32)).to(dev)
+            if realign:
+                diffs = torch.empty((b, rows_p), dtype=torch.int32, device=dev)
+            oo = eng.plan(t_reg, t_shifts, t_goi, out_len, max_rec, keep, keep_off, t_rc, diffs=diffs)
+            total = eng.total()
+            shape = (b, None) if is_ref else (b, p, None)  # Ref has no ploidy axis (_dataset/_ref.py)
+            if self.sequence_type == "annotated":
+                h, av, ap = eng.execute("annotated")
+                results.append(RaggedAnnotatedHaps(Ragged(h, oo, shape), Ragged(av, oo, shape), Ragged(ap, oo, shape)))
+            elif self.encoding == "bytes":
+                results.append(Ragged(eng.execute("haplotypes"), oo, shape))
+            elif self.encoding == "onehot":
+                results.append(Ragged(eng.execute("onehot").view(total, 4), oo, shape))
+            else:
+                cf = eng.execute("onehot_cf")
+                results.append(cf.view(b, 4, out_len) if is_ref else cf.view(b, p, 4, out_len))
+        if want_tracks:
+            names = list(self.active_tracks)
+            t = len(names)
+            if realign:
+                # HapsTracks.__call__, _reconstruct.py:182-300
+                lengths_d = torch.from_numpy(lengths).to(dev)
+                track_lengths = (lengths_d - diffs.clamp(max=0).min(1).values.to(torch.int64)).to(torch.int32)
+                ids, params = lower([self.insertion_fill.get(n, Repeat5p()) for n in names])
+                if self.deterministic:
+                    base_seed = int(np.bitwise_xor.reduce(ds_idx.astype(np.uint64)))  # :215-218
+                else:
+                    base_seed = int(self.rng.integers(0, np.iinfo(np.uint64).max, dtype=np.uint64))  # :219-222
+                out = eng.realign_tracks(names, t_reg, t_shifts, t_goi, pk.get(i_tr), track_lengths, oo, total, ids, params,
+                                         base_seed, max_rec, keep, keep_off, t_rc)
+                # the flat buffer is track-major (_reconstruct.py:238); reorder to the (b, t, p, ~l) layout the
+                # reference's offsets describe (:292-300) so data and offsets agree for t > 1
+                lens_bp = (oo[1:] - oo[:-1]).view(b, p)
+                if t > 1:
+                    out = _track_major_to_btp(out, oo, t, b, p, total)
+                lens = lens_bp.view(b, 1, p).expand(b, t, p).reshape(-1)
+                offsets = torch.zeros(b * t * p + 1, dtype=torch.int64, device=dev)
+                torch.cumsum(lens, 0, out=offsets[1:])
+                results.append(Ragged(out, offsets, (b, t, p, None)))
+            else:
+                # Tracks alone / un-realigned: paint the stored intervals (Tracks._call_float32, _tracks.py:370-420)
+                out_len_q = np.full(b, int(self.output_length), np.int64) if fixed else lengths
+                offs = np.concatenate([[0], np.cumsum(out_len_q)]).astype(np.int64)
+                d_off = torch.from_numpy(offs).to(dev)
+                starts = t_reg[:, 1].contiguous()
+                per = int(offs[-1])
+                flat = torch.empty(t * per, dtype=torch.float32, device=dev)
+                tr_idx = pk.get(i_tr)
+                for ti, n in enumerate(names):
+                    eng.intervals_to_tracks(n, tr_idx[ti].contiguous(), starts, d_off, per, flat[ti * per:(ti + 1) * per])
+                flat = flat.view(t, per)
+                if i_trc is not None:
+                    flat = _reverse_rows(flat, d_off, pk.get(i_trc).bool())
+                lens_q = d_off[1:] - d_off[:-1]
+                out = _track_major_to_btp(flat.reshape(-1), d_off, t, b, 1, per) if t > 1 else flat.reshape(-1)
+                lens = lens_q.view(b, 1).expand(b, t).reshape(-1)
+                offsets = torch.zeros(b * t + 1, dtype=torch.int64, device=dev)
+                torch.cumsum(lens, 0, out=offsets[1:])
+                results.append(Ragged(out, offsets, (b, t, None)))
+        return tuple(results)
+
+    def _exonic_keep(self, goi, regions):
+        """choose_exonic_variants (src/genotypes/mod.rs:132-176): variants fully inside the query.  O(selected
+        variants) host numpy over the host copy of the CSR offsets + device gather of positions."""
+        eng = self.engine
+        go = eng.geno_offsets_host
+        starts, stops = go[0, goi.ravel()], go[1, goi.ravel()]
+        sizes = np.maximum(stops - starts, 0)
+        keep_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        n = int(keep_off[-1])
+        dev = eng.device
+        if n == 0:
+            return torch.zeros(1, dtype=torch.uint8, device=dev), torch.from_numpy(keep_off).to(dev)
+        row = np.repeat(np.arange(goi.size), sizes)
+        src = np.repeat(starts, sizes) + (np.arange(n) - np.repeat(keep_off[:-1], sizes))
+        vi = eng.geno_v_idxs[torch.from_numpy(src).to(dev)].to(torch.int64)
+        pos = eng.v_starts[vi].to(torch.int64)
+        end = pos - eng.ilens[vi].to(torch.int64).clamp(max=0) + 1
+        q = torch.from_numpy(row // goi.shape[1]).to(dev)
+        rs = torch.from_numpy(regions[:, 1].astype(np.int64)).to(dev)[q]
+        re = torch.from_numpy(regions[:, 2].astype(np.int64)).to(dev)[q]
+        keep = ((pos >= rs) & (end <= re)).to(torch.uint8)
+        return keep, torch.from_numpy(keep_off).to(dev)
+
+    # ---- output shaping, _query.py:94-127 ----
+    def _shape_output(self, o, out_reshape, squeeze):
+        if isinstance(o, torch.Tensor) or self.output_format == "flat" or self.output_length == "ragged":
+            res = o  # channels-first one-hot is already dense; "flat"/"ragged" hand the flat triple back
+        elif self.output_length == "variable":
+            if isinstance(o, RaggedAnnotatedHaps):
+                res = o.to_padded()
+            elif o.data.dtype == torch.float32:
+                res = o.to_padded(0.0)                               # tracks pad with 0 (_query.py:545-548)
+            else:
+                res = o.to_padded(0 if o.data.dim() > 1 else N_CHAR)  # bytes pad with N; one-hot with zeros
+        else:
+            res = o.to_fixed(int(self.output_length))
+        if out_reshape is not None:
+            if isinstance(res, torch.Tensor):
+                res = res.reshape(*out_reshape, *res.shape[1:])
+            elif isinstance(res, AnnotatedHaps):
+                res = res.reshape((*out_reshape, *res.haps.shape[1:]))
+            else:
+                res = res.reshape((*out_reshape, *(d for d in res.shape[1:] if d is not None)))
+        if squeeze:
+            res = res.squeeze(0)  # (1 [p] l) -> ([p] l), _query.py:120-122
+        return res
+
+
+def _reverse_rows(x: torch.Tensor, offsets: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """Reverse the masked rows of a (t, flat) ragged buffer (un-realigned tracks on negative strands)."""
+    lens = offsets[1:] - offsets[:-1]
+    n = int(offsets[-1])
+    row = torch.repeat_interleave(torch.arange(lens.numel(), device=x.device), lens)
+    start = offsets[:-1][row]
+    col = torch.arange(n, device=x.device) - start
+    src = torch.where(mask[row], start + lens[row] - 1 - col, start + col)
+    return x[:, src]
+
+
+def _track_major_to_btp(flat: torch.Tensor, row_offsets: torch.Tensor, t: int, b: int, p: int, per: int) -> torch.Tensor:
+    """(t, rows...) track-major flat buffer -> (b, t, p, ~l) order.  rows = b*p, row_offsets (rows+1,)."""
+    dev = flat.device
+    lens = (row_offsets[1:] - row_offsets[:-1]).view(b, p)
+    # destination order: for q in b, for ti in t, for h in p
+    src_row = torch.arange(b * p, device=dev).view(b, 1, p).expand(b, t, p).reshape(-1)
+    src_trk = torch.arange(t, device=dev).view(1, t, 1).expand(b, t, p).reshape(-1)
+    l = lens.view(b, 1, p).expand(b, t, p).reshape(-1)
+    seg = torch.repeat_interleave(torch.arange(l.numel(), device=dev), l)
+    dst_off = torch.zeros(l.numel() + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(l, 0, out=dst_off[1:])
+    within = torch.arange(int(dst_off[-1]), device=dev) - dst_off[:-1][seg]
+    src = src_trk[seg] * per + row_offsets[:-1][src_row[seg]] + within
+    return flat[src]
+
+
+class _Packer:
+    """All O(batch) host arrays of one call in ONE pinned buffer and ONE async H2D copy."""
+
+    def __init__(self, device):
+        self.device = device
+        self.items = []
+        self.total = 0
+        self.dev = None
+
+    def add(self, arr, dtype) -> int:
+        a = np.ascontiguousarray(arr, dtype)
+        self.items.append((a, self.total))
+        self.total += (a.nbytes + 15) & ~15
+        return len(self.items) - 1
+
+    def upload(self) -> None:
+        host = torch.empty(max(self.total, 16), dtype=torch.uint8, pin_memory=True)
+        hv = host.numpy()
+        for a, off in self.items:
+            hv[off: off + a.nbytes] = a.reshape(-1).view(np.uint8)
+        self.dev = host.to(self.device, non_blocking=True)
+        self._host = host  # keep the pinned buffer alive until the copy has been consumed
+
+    def get(self, i: int) -> torch.Tensor:
+        a, off = self.items[i]
+        tdt = torch.from_numpy(np.empty(0, a.dtype)).dtype
+        return self.dev[off: off + a.nbytes].view(tdt).view(a.shape)

@@ -51,6 +51,9 @@ class Engine:
         go = np.asarray(geno_offsets)
         if go.ndim == 1:
             go = np.stack([go[:-1], go[1:]])
+        # one extra, EMPTY slot at the end: rows that must carry no variants ("reference" sequences) point at it
+        go = np.concatenate([np.ascontiguousarray(go, np.int64), np.zeros((2, 1), np.int64)], 1)
+        self.empty_slot = go.shape[1] - 1
         self.geno_offsets_host = np.ascontiguousarray(go, np.int64)  # O(batch) capacity sums stay on the host
         with torch.cuda.device(self.device):
             self.ref = _dev(reference, np.uint8, self.device, pad=32)
@@ -158,6 +161,15 @@ class Engine:
             c_i64(ploidy), ptr(keep), ptr(keep_offsets), ptr(to_rc), c_i64(n_tracks), itv, ptr(offset_idxs),
             ptr(track_lengths), ptr(out_offsets), c_i64(int(total_per_track)), sid, par, c_u64(int(base_seed)),
             ptr(query_seed), c_i64(int(max_records)), ptr(out), _stream()))
+        return out
+
+    def intervals_to_tracks(self, name, offset_idxs, starts, out_offsets, total: int, out=None):
+        """gvl_dev_intervals_to_tracks: paint one track's stored intervals into dense windows."""
+        n_q = int(starts.numel())
+        if out is None:
+            out = torch.empty(total, dtype=torch.float32, device=self.device)
+        check(lib.gvl_dev_intervals_to_tracks(self.ctx.handle, C.byref(self.tracks[name][4]), ptr(offset_idxs), ptr(starts),
+                                              c_i64(n_q), ptr(out_offsets), c_i64(int(total)), ptr(out), _stream()))
         return out
 
     def check(self) -> None:

@@ -1,0 +1,115 @@
+"""Return containers of the GPU `Dataset` -- torch-tensor counterparts of the reference's
+`_Flat` (python/genvarloader/_flat.py:26-214), `AnnotatedHaps` (python/genvarloader/_types.py:26) and
+`RaggedAnnotatedHaps` (python/genvarloader/_ragged.py)."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Any
+
+import numpy as np
+import torch
+
+INT32_MAX = int(np.iinfo(np.int32).max)
+
+
+@dataclass(frozen=True)
+class Ragged:
+    """Flat `(data, offsets, shape)` ragged array on the device (exactly one ragged axis, last).
+
+    `data` is the flat buffer the kernels wrote, `offsets` int64 `(n_rows + 1,)`, `shape` the outer
+    fixed dims followed by `None`.  For one-hot data the trailing alphabet axis of 4 is kept on `data`
+    (`data.shape == (total, 4)`)."""
+
+    data: torch.Tensor
+    offsets: torch.Tensor
+    shape: tuple
+
+    @property
+    def n_rows(self) -> int:
+        return int(np.prod([d for d in self.shape if d is not None], dtype=np.int64))
+
+    @property
+    def lengths(self) -> torch.Tensor:
+        outer = tuple(d for d in self.shape if d is not None)
+        return (self.offsets[1:] - self.offsets[:-1]).reshape(outer)
+
+    def reshape(self, shape) -> "Ragged":
+        if isinstance(shape, int):
+            shape = (shape,)
+        return Ragged(self.data, self.offsets, tuple(shape) + (None,))
+
+    def squeeze(self, axis: int | None = None) -> "Ragged":
+        outer = [d for d in self.shape if d is not None]
+        if axis is None:
+            outer = [d for d in outer if d != 1]
+        else:
+            if outer[axis] != 1:
+                raise ValueError(f"cannot squeeze axis {axis} with size {outer[axis]}")
+            del outer[axis]
+        return Ragged(self.data, self.offsets, (*outer, None))
+
+    def to_fixed(self, length: int) -> torch.Tensor:
+        """Every row has exactly `length` elements: pure reshape (reference `_Flat.to_fixed`, _flat.py:54-57)."""
+        outer = tuple(d for d in self.shape if d is not None)
+        return self.data.reshape(*outer, length, *self.data.shape[1:])
+
+    def to_padded(self, pad_value: Any) -> torch.Tensor:
+        """Right-pad every row to the longest one (reference `to_padded`, _ragged.py:281-314 ->
+        src/ragged/mod.rs:7-23).  Runs on the device with torch indexing (not a hot path)."""
+        outer = tuple(d for d in self.shape if d is not None)
+        lens = self.offsets[1:] - self.offsets[:-1]
+        n_rows = lens.numel()
+        max_len = int(lens.max().item()) if n_rows else 0
+        out = torch.full((n_rows, max_len, *self.data.shape[1:]), pad_value, dtype=self.data.dtype, device=self.data.device)
+        if self.data.shape[0]:
+            row = torch.repeat_interleave(torch.arange(n_rows, device=self.data.device), lens)
+            col = torch.arange(self.data.shape[0], device=self.data.device) - self.offsets[:-1][row]
+            out[row, col] = self.data
+        return out.reshape(*outer, max_len, *self.data.shape[1:])
+
+    def to_numpy(self):
+        return self.data.cpu().numpy(), self.offsets.cpu().numpy(), self.shape
+
+
+@dataclass(frozen=True)
+class AnnotatedHaps:
+    """Dense annotated haplotypes (reference `AnnotatedHaps`, python/genvarloader/_types.py:26-60)."""
+
+    haps: torch.Tensor        # uint8  (..., L)
+    var_idxs: torch.Tensor    # int32  (..., L)   -1 = reference / pad
+    ref_coords: torch.Tensor  # int32  (..., L)   -1 = leading pad, INT32_MAX = trailing pad
+
+    @property
+    def shape(self):
+        return tuple(self.haps.shape)
+
+    def reshape(self, shape):
+        return AnnotatedHaps(self.haps.reshape(shape), self.var_idxs.reshape(shape), self.ref_coords.reshape(shape))
+
+    def squeeze(self, axis=None):
+        f = (lambda t: t.squeeze()) if axis is None else (lambda t: t.squeeze(axis))
+        return AnnotatedHaps(f(self.haps), f(self.var_idxs), f(self.ref_coords))
+
+
+@dataclass(frozen=True)
+class RaggedAnnotatedHaps:
+    haps: Ragged
+    var_idxs: Ragged
+    ref_coords: Ragged
+
+    @property
+    def shape(self):
+        return self.haps.shape
+
+    def reshape(self, shape):
+        return RaggedAnnotatedHaps(self.haps.reshape(shape), self.var_idxs.reshape(shape), self.ref_coords.reshape(shape))
+
+    def squeeze(self, axis=None):
+        return RaggedAnnotatedHaps(self.haps.squeeze(axis), self.var_idxs.squeeze(axis), self.ref_coords.squeeze(axis))
+
+    def to_fixed(self, length: int) -> AnnotatedHaps:
+        return AnnotatedHaps(self.haps.to_fixed(length), self.var_idxs.to_fixed(length), self.ref_coords.to_fixed(length))
+
+    def to_padded(self) -> AnnotatedHaps:
+        # pad values: python/genvarloader/_flat.py:207-214
+        return AnnotatedHaps(self.haps.to_padded(ord("N")), self.var_idxs.to_padded(-1), self.ref_coords.to_padded(INT32_MAX))

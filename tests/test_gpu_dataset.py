@@ -1,0 +1,182 @@
+"""GPU Dataset vs the oracle driven by a numpy restatement of the reference's read-time prep
+(jitter / strand / shifts / seeds, python/genvarloader/_dataset/_query.py:153-204, _haps.py:678-768,
+_reconstruct.py:168-300).  Bit-exact; RNG draws follow the reference's order so seeded runs match."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+N = ord("N")
+
+
+@pytest.fixture(scope="module")
+def env(cuda_device):
+    from genvarloader_b200 import synth
+    from genvarloader_b200._dataset import Dataset
+    from oracle import oracle as O
+
+    d = synth.make_dataset(77, 400_000, 5, 14, 3000 + 2 * 16, 5.0, max_jitter=16, neg_strand_frac=0.5,
+                           straddle_ends=False, n_tracks=2, max_indel=18, snp_frac=0.5)
+    ds = Dataset.from_synth(cuda_device, d, rng=123)
+    return d, ds, O, synth
+
+
+def _prep(d, ds_idx, jitter, rng):
+    S = d.n_samples
+    r_idx, s_idx = ds_idx // S, ds_idx % S
+    regions = d.regions[r_idx].copy()
+    lengths = regions[:, 2] - regions[:, 1]
+    regions[:, 1] += rng.integers(-jitter, jitter + 1, size=len(regions), dtype=np.int32)
+    regions[:, 2] = regions[:, 1] + lengths
+    goi = ds_idx[:, None] * d.ploidy + np.arange(d.ploidy)[None, :]
+    to_rc = np.repeat(d.regions[r_idx, 3] == -1, d.ploidy)
+    return r_idx, np.ascontiguousarray(regions[:, :3]), goi, to_rc
+
+
+def _hap_args(d, regions, shifts, goi, out_len):
+    return (regions, shifts, goi, d.geno_offsets, d.geno_v_idxs, d.v_starts, d.ilens, d.alt_alleles, d.alt_offsets,
+            d.reference, d.ref_offsets, N, out_len)
+
+
+def test_fixed_length_haplotypes_shapes_and_values(env):
+    d, ds, O, _ = env
+    L = 2048
+    dsl = ds.with_len(L).with_tracks(False)
+    out = dsl[:4, :3]
+    assert tuple(out.shape) == (4, 3, 2, L) and out.dtype.__str__() == "torch.uint8"
+    ds_idx = (np.arange(4)[:, None] * d.n_samples + np.arange(3)[None, :]).ravel()
+    _, regions, goi, to_rc = _prep(d, ds_idx, 0, np.random.default_rng(0))
+    exp, _ = O.reconstruct_haplotypes_fused(*_hap_args(d, regions, np.zeros(goi.shape, np.int32), goi, L), None, None, to_rc)
+    assert (out.cpu().numpy().ravel() == exp).all()
+    one = dsl[2, 1]
+    assert tuple(one.shape) == (2, L)
+    assert (one.cpu().numpy() == out[2, 1].cpu().numpy()).all()
+    col = dsl[[0, 3, 3], [2, 0, 1]]
+    assert tuple(col.shape) == (3, 2, L)
+    assert (col[1].cpu().numpy() == out[3, 0].cpu().numpy()).all()
+
+
+def test_ragged_variable_annotated_and_onehot(env):
+    d, ds, O, _ = env
+    base = ds.with_tracks(False)
+    ds_idx = np.array([1 * d.n_samples + 2, 6 * d.n_samples + 0, 9 * d.n_samples + 4])
+    _, regions, goi, to_rc = _prep(d, ds_idx, 0, np.random.default_rng(0))
+    a = _hap_args(d, regions, np.zeros(goi.shape, np.int32), goi, -1)
+    e_out, e_av, e_ap, e_oo = O.reconstruct_annotated_haplotypes_fused(*a, None, None, to_rc)
+    idx = ([1, 6, 9], [2, 0, 4])
+    rag = base[idx]
+    assert rag.shape == (3, 2, None)
+    assert (rag.offsets.cpu().numpy() == e_oo).all() and (rag.data.cpu().numpy() == e_out).all()
+    ann = base.with_seqs("annotated")[idx]
+    assert (ann.haps.data.cpu().numpy() == e_out).all()
+    assert (ann.var_idxs.data.cpu().numpy() == e_av).all() and (ann.ref_coords.data.cpu().numpy() == e_ap).all()
+    var = base.with_len("variable")[idx]
+    lens = np.diff(e_oo)
+    assert tuple(var.shape) == (3, 2, lens.max())
+    v = var.cpu().numpy().reshape(6, -1)
+    for k in range(6):
+        assert (v[k, :lens[k]] == e_out[e_oo[k]:e_oo[k + 1]]).all() and (v[k, lens[k]:] == N).all()
+    annv = base.with_seqs("annotated").with_len("variable")[idx]
+    assert (annv.ref_coords.cpu().numpy().reshape(6, -1)[0, lens[0]:] == np.iinfo(np.int32).max).all()
+    oh = base.with_encoding("onehot")[idx]
+    assert (oh.data.cpu().numpy() == O.onehot(e_out)).all()
+    L = 1024
+    cf = base.with_len(L).with_encoding("onehot_cf")[idx]
+    e_fix, _ = O.reconstruct_haplotypes_fused(*_hap_args(d, regions, np.zeros(goi.shape, np.int32), goi, L), None, None, to_rc)
+    assert (cf.cpu().numpy() == O.onehot(e_fix).reshape(3, 2, L, 4).transpose(0, 1, 3, 2)).all()
+
+
+def test_jitter_and_random_shifts_follow_reference_rng_order(env):
+    d, ds, O, _ = env
+    L, J = 2500, 16
+    dsj = ds.with_tracks(False).with_len(L).with_settings(jitter=J, deterministic=False, rng=2024)
+    out = dsj[3:9, 1:3]
+    ds_idx = (np.arange(3, 9)[:, None] * d.n_samples + np.arange(1, 3)[None, :]).ravel()
+    rng = np.random.default_rng(2024)
+    _, regions, goi, to_rc = _prep(d, ds_idx, J, rng)  # jitter draw first (_query.py:167-171)
+    diffs = O.get_diffs_sparse(goi, d.geno_v_idxs, d.geno_offsets, d.ilens, None, None, regions[:, 1], regions[:, 2], d.v_starts)
+    lengths = regions[:, 2] - regions[:, 1]
+    max_shift = diffs.clip(min=0) + (lengths - L).clip(min=0)[:, None]
+    shifts = rng.integers(0, max_shift + 1, dtype=np.int32)  # then the shifts (_haps.py:728-730)
+    assert shifts.max() > 0
+    exp, _ = O.reconstruct_haplotypes_fused(*_hap_args(d, regions, shifts, goi, L), None, None, to_rc)
+    assert (out.cpu().numpy().ravel() == exp).all()
+
+
+@pytest.mark.parametrize("fixed", [True, False])
+def test_haplotypes_plus_realigned_tracks(env, fixed):
+    from genvarloader_b200 import FlankSample, Interpolate
+
+    d, ds, O, _ = env
+    L = 2400
+    dst = ds.with_insertion_fill({"track0": Interpolate(2), "track1": FlankSample(3)})
+    if fixed:
+        dst = dst.with_len(L)
+    idx = ([2, 5, 5, 11], [0, 3, 4, 1])
+    haps, tracks = dst[idx]
+    ds_idx = np.array([2 * d.n_samples + 0, 5 * d.n_samples + 3, 5 * d.n_samples + 4, 11 * d.n_samples + 1])
+    r_idx, regions, goi, to_rc = _prep(d, ds_idx, 0, np.random.default_rng(0))
+    sh = np.zeros(goi.shape, np.int32)
+    diffs = O.get_diffs_sparse(goi, d.geno_v_idxs, d.geno_offsets, d.ilens, None, None, regions[:, 1], regions[:, 2], d.v_starts)
+    lengths = (regions[:, 2] - regions[:, 1]).astype(np.int64)
+    out_len = np.full(goi.shape, L, np.int64) if fixed else lengths[:, None] + diffs
+    oo = np.concatenate([[0], np.cumsum(out_len.ravel())]).astype(np.int64)
+    to = np.concatenate([[0], np.cumsum(lengths - diffs.clip(max=0).min(1))]).astype(np.int64)
+    seed = int(np.bitwise_xor.reduce(ds_idx.astype(np.uint64)))
+    exp_t = []
+    for name, (sid, par) in zip(("track0", "track1"), ((4, 2.0), (3, 3.0))):
+        s, e, v, io = d.tracks[name]
+        buf = np.zeros(int(oo[-1]), np.float32)
+        O.intervals_and_realign_track_fused(buf, oo, regions, sh, goi, d.geno_v_idxs, d.geno_offsets, d.v_starts, d.ilens,
+                                            ds_idx, s, e, v, io, to, np.array([par]), sid, seed, None, None, to_rc)
+        exp_t.append(buf)
+    b, p = goi.shape
+    if fixed:
+        assert tuple(tracks.shape) == (b, 2, p, L)
+        got = tracks.cpu().numpy()
+        for ti in range(2):
+            assert (got[:, ti].reshape(-1).view(np.uint32) == exp_t[ti].view(np.uint32)).all()
+        e_h, _ = O.reconstruct_haplotypes_fused(*_hap_args(d, regions, sh, goi, L), None, None, to_rc)
+        assert (haps.cpu().numpy().ravel() == e_h).all()
+    else:
+        assert tracks.shape == (b, 2, p, None)
+        data, offs = tracks.data.cpu().numpy(), tracks.offsets.cpu().numpy()
+        k = 0
+        for q in range(b):
+            for ti in range(2):
+                for h in range(p):
+                    row = q * p + h
+                    seg = data[offs[k]:offs[k + 1]]
+                    assert (seg.view(np.uint32) == exp_t[ti][oo[row]:oo[row + 1]].view(np.uint32)).all()
+                    k += 1
+
+
+def test_reference_sequences_and_unrealigned_tracks(env):
+    d, ds, O, _ = env
+    L = 1500
+    dsr = ds.with_seqs("reference").with_len(L).with_tracks(["track1"])
+    seq, trk = dsr[:5, 2]
+    assert tuple(seq.shape) == (5, L) and tuple(trk.shape) == (5, 1, L)
+    ds_idx = np.arange(5) * d.n_samples + 2
+    r_idx, regions, goi, to_rc = _prep(d, ds_idx, 0, np.random.default_rng(0))
+    oo = np.arange(6, dtype=np.int64) * L
+    reg_fixed = regions.copy()
+    reg_fixed[:, 2] = reg_fixed[:, 1] + L
+    e_ref = O.get_reference(reg_fixed, oo, d.reference, d.ref_offsets, N, False, d.regions[r_idx, 3] == -1)
+    assert (seq.cpu().numpy().ravel() == e_ref).all()
+    s, e, v, io = d.tracks["track1"]
+    e_trk = np.zeros(5 * L, np.float32)
+    O.intervals_to_tracks(ds_idx, regions[:, 1], s, e, v, io, e_trk, oo)
+    O.reverse_flat_rows_inplace(e_trk, oo, d.regions[r_idx, 3] == -1)
+    assert (trk.cpu().numpy().ravel().view(np.uint32) == e_trk.view(np.uint32)).all()
+
+
+def test_exonic_filter_and_subset(env):
+    d, ds, O, _ = env
+    sub = ds.with_tracks(False).with_settings(var_filter="exonic").subset_to(regions=[8, 3], samples=[4, 1, 0])
+    out = sub[:, :]
+    assert out.shape == (2, 3, 2, None)
+    ds_idx = (np.array([8, 3])[:, None] * d.n_samples + np.array([4, 1, 0])[None, :]).ravel()
+    _, regions, goi, to_rc = _prep(d, ds_idx, 0, np.random.default_rng(0))
+    keep, ko = O.choose_exonic_variants(regions[:, 1], regions[:, 2], goi, d.geno_v_idxs, d.geno_offsets, d.v_starts, d.ilens)
+    exp, eoo = O.reconstruct_haplotypes_fused(*_hap_args(d, regions, np.zeros(goi.shape, np.int32), goi, -1), keep, ko, to_rc)
+    assert (out.offsets.cpu().numpy() == eoo).all() and (out.data.cpu().numpy() == exp).all()

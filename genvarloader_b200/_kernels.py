@@ -260,3 +260,35 @@ def _debug_hash4(a: int, b: int, c: int, d: int, *, ctx=None) -> int:
     out = c_u64(0)
     check(lib.gvl_debug_hash4(ctx.handle, c_u64(int(a)), c_u64(int(b)), c_u64(int(c)), c_u64(int(d)), C.byref(out)))
     return int(out.value)
+
+
+# ---------------------------------------------------------------------------------- svar2 source
+def reconstruct_haplotypes_from_svar2(regions, shifts, vk_pos, vk_key, vk_off, dense_pos, dense_key, dense_range,
+                                      dense_present, dense_present_off, key_ilen, key_alt, key_alt_off, ref_,
+                                      ref_offsets, pad_char, output_length, parallel=True, *, to_rc=None, mode="u8",
+                                      ctx=None):
+    """src/ffi/mod.rs:874-893 with the codec keys + LUT replaced by the DECODED key table
+    (key_ilen, key_alt, key_alt_off; see gvl_svar2_channels in include/gvl_b200.h).  Returns (out, out_offsets)."""
+    ctx = ctx or default_ctx()
+    m = _MODES[mode]
+    rg, sh = _c(regions, np.int32), _c(shifts, np.int32)
+    batch, ploidy = sh.shape
+    vp, vk, vo = _c(vk_pos, np.int32), _c(vk_key, np.int32), _c(vk_off, np.int64)
+    dp, dk, dr = _c(dense_pos, np.int32), _c(dense_key, np.int32), _c(dense_range, np.int32)
+    db, do = _c(dense_present, np.uint8), _c(dense_present_off, np.int64)
+    ki, ka, ko = _c(key_ilen, np.int32), _c(key_alt, np.uint8), _c(key_alt_off, np.int64)
+    rf, ro, rc = _c(ref_, np.uint8), _c(ref_offsets, np.int64), _c(to_rc, np.bool_)
+    out_offsets = np.empty(batch * ploidy + 1, np.int64)
+    total = c_i64(0)
+    check(lib.gvl_reconstruct_haplotypes_from_svar2_begin(
+        ctx.handle, _p(rg), _p(sh), c_i64(batch), c_i64(ploidy), _p(vp), _p(vk), _p(vo), _p(dp), _p(dk), c_i64(dp.size),
+        _p(dr), _p(db), _p(do), _p(ki), _p(ka), _p(ko), c_i64(ki.size), _p(rf), _p(ro), c_i64(ro.size - 1),
+        c_i64(int(output_length)), _p(rc), _p(out_offsets), C.byref(total)))
+    n = int(total.value)
+    if m == MODE_ANNOTATED:
+        out, av, ap = np.empty(n, np.uint8), np.empty(n, np.int32), np.empty(n, np.int32)
+        check(lib.gvl_reconstruct_haplotypes_fused_finish(ctx.handle, C.c_int(m), c_u8(int(pad_char)), _p(out), _p(av), _p(ap)))
+        return out, av, ap, out_offsets
+    out = np.empty(n * (4 if m in (MODE_ONEHOT, MODE_ONEHOT_CF) else 1), np.uint8)
+    check(lib.gvl_reconstruct_haplotypes_fused_finish(ctx.handle, C.c_int(m), c_u8(int(pad_char)), _p(out), c_vp(0), c_vp(0)))
+    return (out.reshape(n, 4) if m == MODE_ONEHOT else out), out_offsets

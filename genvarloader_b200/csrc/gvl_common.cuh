@@ -38,6 +38,16 @@ struct RecArrays {
     int32_t *vpos;
 };
 
+// Optional per-call MERGED variant lists: the svar2 two-channel source (var_key + dense/presence,
+// src/svar2/mod.rs:45-66) after the device merge.  Row k's list is key/pos[off[k] .. off[k]+len[k]); keys
+// index the decoded-key table that is passed as gvl_sparse_tables.ilens / alt_offsets / alt_alleles.
+struct MergedLists {
+    const int32_t *pos;
+    const int32_t *key;
+    const int64_t *off;
+    const int32_t *len;
+};
+
 // Device status words (ctx->dev_words).
 enum { W_CURSOR = 0, W_STATUS = 1, W_TOTAL = 2, W_TILES = 3, W_COUNT = 8 };
 
@@ -65,6 +75,11 @@ struct gvl_workspace {
     int64_t rec_cap;
     int64_t *tile_off;  // i64[rows_cap+1] (ragged plans)
     int32_t *row_len;   // i32[rows_cap]
+    // svar2 merge output
+    int32_t *m_pos, *m_key;
+    int64_t m_cap;
+    int64_t *m_off;     // i64[rows_cap]
+    int32_t *m_len;     // i32[rows_cap]
 };
 
 struct gvl_ctx {

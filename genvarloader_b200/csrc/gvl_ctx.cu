@@ -38,6 +38,8 @@ int ensure_rows(gvl_ctx *ctx, gvl_workspace &ws, int64_t n_work) {
     if ((rc = regrow(ws.rows, cap))) return rc;
     if ((rc = regrow(ws.tile_off, cap + 1))) return rc;
     if ((rc = regrow(ws.row_len, cap))) return rc;
+    if ((rc = regrow(ws.m_off, cap))) return rc;
+    if ((rc = regrow(ws.m_len, cap))) return rc;
     ws.rows_cap = cap;
     return GVL_OK;
 }
@@ -58,7 +60,23 @@ int ensure_records(gvl_ctx *ctx, gvl_workspace &ws, int64_t n_rec) {
     return GVL_OK;
 }
 
+int ensure_merged(gvl_ctx *ctx, gvl_workspace &ws, int64_t n) {
+    (void)ctx;
+    if (n <= ws.m_cap) return GVL_OK;
+    GVL_CUDA(cudaDeviceSynchronize());
+    int64_t cap = n + n / 2 + 1024;
+    int rc;
+    if ((rc = regrow(ws.m_pos, cap))) return rc;
+    if ((rc = regrow(ws.m_key, cap))) return rc;
+    ws.m_cap = cap;
+    return GVL_OK;
+}
+
 static void free_workspace(gvl_workspace &ws) {
+    cudaFree(ws.m_pos);
+    cudaFree(ws.m_key);
+    cudaFree(ws.m_off);
+    cudaFree(ws.m_len);
     cudaFree(ws.rows);
     cudaFree(ws.tile_off);
     cudaFree(ws.row_len);

@@ -29,6 +29,7 @@ namespace gvl {
 // =====================================================================================
 struct HapPlanParams {
     gvl_sparse_tables tab;
+    MergedLists merged;  // all-NULL for the SVAR1 CSR source
     const int32_t *regions;
     const int32_t *shifts;
     const int64_t *goi;
@@ -52,9 +53,8 @@ constexpr int PLAN_WARPS = 4;
 __device__ void plan_row_serial(const HapPlanParams &P, const int64_t k, const int64_t rec_off_in = -1) {
     const int lane = lane_id();
     const int64_t query = k / P.ploidy;
-    const int64_t o_idx = P.goi[k];
-    const int64_t o_s = P.tab.geno_starts[o_idx];
-    const int64_t nvar = imax64(P.tab.geno_stops[o_idx] - o_s, 0);
+    const RowVars rv = row_vars(P.tab, P.merged, P.goi, k);
+    const int64_t nvar = rv.nvar;
     const int64_t c_idx = P.regions[query * 3 + 0];
     const int64_t c_s = P.tab.ref_offsets[c_idx];
     const int64_t contig_len = P.tab.ref_offsets[c_idx + 1] - c_s;
@@ -63,7 +63,7 @@ __device__ void plan_row_serial(const HapPlanParams &P, const int64_t k, const i
     const int64_t shift = P.shifts[k];
     const int64_t keep_base = (P.keep && P.keep_off) ? P.keep_off[k] : 0;
     const bool has_keep = (P.keep && P.keep_off);
-    const int32_t *__restrict__ gv = P.tab.geno_v_idxs + o_s;
+    const int32_t *__restrict__ gv = rv.gv;
 
     // ---- get_diffs_sparse (src/genotypes/mod.rs:48-86), needed first for ragged sizing ----
     DiffState ds;
@@ -78,7 +78,7 @@ __device__ void plan_row_serial(const HapPlanParams &P, const int64_t k, const i
             bool kp = false;
             if (i < nvar) {
                 int32_t vi = gv[i];
-                pos = P.tab.v_starts[vi];
+                pos = (int32_t)var_pos(P.tab, rv, i, vi);
                 il = P.tab.ilens[vi];
                 kp = has_keep ? (P.keep[keep_base + i] != 0) : true;
             }
@@ -125,11 +125,13 @@ __device__ void plan_row_serial(const HapPlanParams &P, const int64_t k, const i
         bool kp = false;
         if (i < nvar) {
             vi = gv[i];
-            pos = P.tab.v_starts[vi];
+            pos = (int32_t)var_pos(P.tab, rv, i, vi);
             il = P.tab.ilens[vi];
-            aoff = P.tab.alt_offsets[vi];
-            alen = (int32_t)(P.tab.alt_offsets[vi + 1] - aoff);
+            int64_t alen64;
+            var_alt(P.tab, rv, vi, pos, c_s, aoff, alen64);
+            alen = (int32_t)alen64;
             kp = has_keep ? (P.keep[keep_base + i] != 0) : true;
+            if (rv.mpos) vi = (int32_t)i;  // svar2 annotates with the LOCAL index (src/reconstruct/mod.rs:734)
         }
         unsigned mask = __ballot_sync(0xffffffffu, kp);
         while (mask && (!done || diff_live)) {
@@ -583,7 +585,8 @@ __global__ void __launch_bounds__(EXEC_THREADS) hap_exec_kernel(HapExecParams P)
                         if (src == ALT_PAD) {
                             b = P.pad_char;  // leading pad (src/reconstruct/mod.rs:75-80): annotations (-1, -1)
                         } else {
-                            b = P.alt[src + (p - S.a[il])];
+                            // (src < 0: pure-deletion anchor of the svar2 source, taken from the reference)
+                            b = src >= 0 ? P.alt[src + (p - S.a[il])] : P.ref[~src + (p - S.a[il])];
                             if (ANNOT) {
                                 av[t] = S.vidx[il];
                                 ap[t] = S.vpos[il];
@@ -666,13 +669,13 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) diffs_kernel(DiffParams P) {
     const int64_t k = (int64_t)blockIdx.x * PLAN_WARPS + (threadIdx.x >> 5);
     if (k >= P.n_work) return;
     const int64_t query = k / P.ploidy;
-    const int64_t o_idx = P.goi[k];
-    const int64_t o_s = P.tab.geno_starts[o_idx];
-    const int64_t nvar = imax64(P.tab.geno_stops[o_idx] - o_s, 0);
+    const MergedLists no_merge{nullptr, nullptr, nullptr, nullptr};
+    const RowVars rv = row_vars(P.tab, no_merge, P.goi, k);
+    const int64_t nvar = rv.nvar;
     const bool has_query = P.q_starts && P.q_ends && P.use_v_starts;
     const bool has_keep = P.keep && P.keep_off;
     const int64_t keep_base = has_keep ? P.keep_off[k] : 0;
-    const int32_t *__restrict__ gv = P.tab.geno_v_idxs + o_s;
+    const int32_t *__restrict__ gv = rv.gv;
     int64_t acc = 0;
     if (has_query) {
         DiffState ds;
@@ -735,11 +738,18 @@ static int64_t exec_capacity(gvl_ctx *ctx, int mode) {
 
 extern "C" {
 
-int gvl_dev_hap_plan(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_t *regions, const int32_t *shifts,
-                     const int64_t *geno_offset_idx, int64_t batch, int64_t ploidy, const uint8_t *keep,
-                     const int64_t *keep_offsets, const uint8_t *to_rc, int64_t output_length, int64_t max_records,
-                     int64_t *out_offsets, int32_t *diffs, gvl_stream stream) {
-    if (!ctx || !tab || !regions || !shifts || !geno_offset_idx || !out_offsets)
+}  // extern "C"
+
+// Merge of the svar2 two-channel source (gvl_svar2.cu); fills ctx->hap.m_* for n_work rows.
+int gvl_svar2_merge_launch(gvl_ctx *ctx, const gvl_svar2_channels *ch, int64_t batch, int64_t ploidy, int64_t max_merged,
+                           cudaStream_t st);
+
+static int hap_plan_impl(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_svar2_channels *svar2,
+                         const int32_t *regions, const int32_t *shifts, const int64_t *geno_offset_idx, int64_t batch,
+                         int64_t ploidy, const uint8_t *keep, const int64_t *keep_offsets, const uint8_t *to_rc,
+                         int64_t output_length, int64_t max_records, int64_t *out_offsets, int32_t *diffs,
+                         gvl_stream stream) {
+    if (!ctx || !tab || !regions || !shifts || !(geno_offset_idx || svar2) || !out_offsets)
         return fail(GVL_ERR_ARG, "gvl_dev_hap_plan: NULL argument");
     if (batch < 0 || ploidy < 1) return fail(GVL_ERR_ARG, "gvl_dev_hap_plan: batch=%lld ploidy=%lld", (long long)batch, (long long)ploidy);
     if (output_length > INT32_MAX) return fail(GVL_ERR_ARG, "gvl_dev_hap_plan: output_length too large");
@@ -750,7 +760,7 @@ int gvl_dev_hap_plan(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_t *
     int rc;
     if ((rc = ensure_rows(ctx, ctx->hap, n_work))) return rc;
     if ((rc = ensure_records(ctx, ctx->hap, max_records + n_work))) return rc;
-    GVL_CUDA(cudaMemsetAsync(ctx->dev_words, 0, sizeof(int64_t) * 4, st));
+    GVL_CUDA(cudaMemsetAsync(ctx->dev_words, 0, sizeof(int64_t) * W_COUNT, st));
     ctx->n_work = n_work;
     ctx->fixed_len = output_length >= 0 ? output_length : -1;
     ctx->plan_out_offsets = out_offsets;
@@ -762,6 +772,12 @@ int gvl_dev_hap_plan(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_t *
     }
     HapPlanParams P;
     P.tab = *tab;
+    P.merged = MergedLists{nullptr, nullptr, nullptr, nullptr};
+    if (svar2) {
+        if ((rc = ensure_merged(ctx, ctx->hap, max_records))) return rc;
+        if ((rc = gvl_svar2_merge_launch(ctx, svar2, batch, ploidy, max_records, st))) return rc;
+        P.merged = MergedLists{ctx->hap.m_pos, ctx->hap.m_key, ctx->hap.m_off, ctx->hap.m_len};
+    }
     P.regions = regions;
     P.shifts = shifts;
     P.goi = geno_offset_idx;
@@ -801,6 +817,27 @@ int gvl_dev_hap_plan(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_t *
     }
     ctx->plan_valid = true;
     return GVL_OK;
+}
+
+extern "C" {
+
+int gvl_dev_hap_plan(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_t *regions, const int32_t *shifts,
+                     const int64_t *geno_offset_idx, int64_t batch, int64_t ploidy, const uint8_t *keep,
+                     const int64_t *keep_offsets, const uint8_t *to_rc, int64_t output_length, int64_t max_records,
+                     int64_t *out_offsets, int32_t *diffs, gvl_stream stream) {
+    if (!geno_offset_idx) return fail(GVL_ERR_ARG, "gvl_dev_hap_plan: NULL argument");
+    return hap_plan_impl(ctx, tab, nullptr, regions, shifts, geno_offset_idx, batch, ploidy, keep, keep_offsets, to_rc,
+                         output_length, max_records, out_offsets, diffs, stream);
+}
+
+int gvl_dev_hap_plan_svar2(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_svar2_channels *ch,
+                           const int32_t *regions, const int32_t *shifts, int64_t batch, int64_t ploidy,
+                           const uint8_t *to_rc, int64_t output_length, int64_t max_merged, int64_t *out_offsets,
+                           int32_t *diffs, gvl_stream stream) {
+    if (!ch || !ch->vk_off || !ch->dense_range || !ch->dense_present_off)
+        return fail(GVL_ERR_ARG, "gvl_dev_hap_plan_svar2: NULL channel");
+    return hap_plan_impl(ctx, tab, ch, regions, shifts, nullptr, batch, ploidy, nullptr, nullptr, to_rc, output_length,
+                         max_merged, out_offsets, diffs, stream);
 }
 
 int gvl_dev_hap_total(gvl_ctx *ctx, gvl_stream stream, int64_t *total) {

@@ -248,6 +248,75 @@ int gvl_reconstruct_haplotypes_fused_begin(
                      keep, keep_offsets, to_rc, out_offsets, total);
 }
 
+int gvl_reconstruct_haplotypes_from_svar2_begin(
+    gvl_ctx *ctx, const int32_t *regions, const int32_t *shifts, int64_t batch, int64_t ploidy, const int32_t *vk_pos,
+    const int32_t *vk_key, const int64_t *vk_off, const int32_t *dense_pos, const int32_t *dense_key, int64_t n_dense,
+    const int32_t *dense_range, const uint8_t *dense_present, const int64_t *dense_present_off, const int32_t *key_ilen,
+    const uint8_t *key_alt, const int64_t *key_alt_off, int64_t n_keys, const uint8_t *ref_, const int64_t *ref_offsets,
+    int64_t n_contigs, int64_t output_length, const uint8_t *to_rc, int64_t *out_offsets, int64_t *total) {
+    if (!ctx || !regions || !shifts || !vk_off || !dense_range || !dense_present_off || !key_ilen || !key_alt_off ||
+        !ref_offsets || !out_offsets || !total)
+        return fail(GVL_ERR_ARG, "gvl_reconstruct_haplotypes_from_svar2_begin: NULL argument");
+    if (output_length < -1) return fail(GVL_ERR_ARG, "output_length must be >= -1");
+    GVL_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    const int64_t n_work = batch * ploidy;
+    const void *d;
+    gvl_sparse_tables &t = ctx->host_tab;
+    memset(&t, 0, sizeof(t));
+    if ((rc = static_dev(ctx, key_ilen, sizeof(int32_t) * n_keys, 11, &d))) return rc;
+    t.ilens = (const int32_t *)d;
+    t.v_starts = t.ilens;  // unused by the merged-list source
+    t.n_variants = n_keys;
+    if ((rc = static_dev(ctx, key_alt_off, sizeof(int64_t) * (n_keys + 1), 12, &d))) return rc;
+    t.alt_offsets = (const int64_t *)d;
+    if ((rc = static_dev(ctx, key_alt, key_alt_off[n_keys], 13, &d))) return rc;
+    t.alt_alleles = (const uint8_t *)d;
+    if ((rc = static_dev(ctx, ref_offsets, sizeof(int64_t) * (n_contigs + 1), 14, &d))) return rc;
+    t.ref_offsets = (const int64_t *)d;
+    if ((rc = static_dev(ctx, ref_, ref_offsets[n_contigs], 15, &d))) return rc;
+    t.ref = (const uint8_t *)d;
+    t.n_contigs = n_contigs;
+    gvl_svar2_channels ch;
+    if ((rc = static_dev(ctx, dense_pos, sizeof(int32_t) * n_dense, 16, &d))) return rc;
+    ch.dense_pos = (const int32_t *)d;
+    if ((rc = static_dev(ctx, dense_key, sizeof(int32_t) * n_dense, 17, &d))) return rc;
+    ch.dense_key = (const int32_t *)d;
+    const int64_t n_vk = vk_off[n_work];
+    const int64_t n_bits = dense_present_off[n_work];
+    int64_t max_merged = n_vk;
+    for (int64_t q = 0; q < batch; q++) max_merged += ploidy * (int64_t)(dense_range[2 * q + 1] - dense_range[2 * q] > 0 ? dense_range[2 * q + 1] - dense_range[2 * q] : 0);
+    Packer pk;
+    size_t i_reg = pk.add(regions, sizeof(int32_t) * 3 * batch);
+    size_t i_sh = pk.add(shifts, sizeof(int32_t) * n_work);
+    size_t i_rc = pk.add(to_rc, n_work);
+    size_t i_vp = pk.add(vk_pos ? (const void *)vk_pos : (const void *)vk_off, sizeof(int32_t) * n_vk);
+    size_t i_vkk = pk.add(vk_key ? (const void *)vk_key : (const void *)vk_off, sizeof(int32_t) * n_vk);
+    size_t i_vo = pk.add(vk_off, sizeof(int64_t) * (n_work + 1));
+    size_t i_dr = pk.add(dense_range, sizeof(int32_t) * 2 * batch);
+    size_t i_dp = pk.add(dense_present ? (const void *)dense_present : (const void *)vk_off, (n_bits + 7) / 8);
+    size_t i_do = pk.add(dense_present_off, sizeof(int64_t) * (n_work + 1));
+    if ((rc = pk.upload(ctx, 0))) return rc;
+    ch.vk_pos = pk.ptr<int32_t>(i_vp);
+    ch.vk_key = pk.ptr<int32_t>(i_vkk);
+    ch.vk_off = pk.ptr<int64_t>(i_vo);
+    ch.dense_range = pk.ptr<int32_t>(i_dr);
+    ch.dense_present = pk.ptr<uint8_t>(i_dp);
+    ch.dense_present_off = pk.ptr<int64_t>(i_do);
+    void *oo_dev;
+    if ((rc = scratch(ctx, 1, sizeof(int64_t) * (n_work + 1), &oo_dev))) return rc;
+    ctx->host_out_offsets_dev = (int64_t *)oo_dev;
+    if ((rc = gvl_dev_hap_plan_svar2(ctx, &t, &ch, pk.ptr<int32_t>(i_reg), pk.ptr<int32_t>(i_sh), batch, ploidy,
+                                     pk.ptr<uint8_t>(i_rc), output_length, max_merged, ctx->host_out_offsets_dev, nullptr,
+                                     ctx->own_stream)))
+        return rc;
+    GVL_CUDA(cudaMemcpyAsync(out_offsets, oo_dev, sizeof(int64_t) * (n_work + 1), cudaMemcpyDeviceToHost, ctx->own_stream));
+    if ((rc = gvl_ctx_check(ctx, ctx->own_stream))) return rc;
+    if (ctx->total < 0) ctx->total = ctx->host_words[W_TOTAL];
+    *total = ctx->total;
+    return GVL_OK;
+}
+
 int gvl_reconstruct_haplotypes_from_sparse(
     gvl_ctx *ctx, uint8_t *out, const int64_t *out_offsets, const int32_t *regions, const int32_t *shifts,
     const int64_t *geno_offset_idx, int64_t batch, int64_t ploidy, const int64_t *geno_offsets, int64_t n_geno,

@@ -8,6 +8,7 @@ int fail(int code, const char *fmt, ...);
 void count_launch(int n = 1);
 int ensure_rows(gvl_ctx *ctx, gvl_workspace &ws, int64_t n_work);
 int ensure_records(gvl_ctx *ctx, gvl_workspace &ws, int64_t n_rec);
+int ensure_merged(gvl_ctx *ctx, gvl_workspace &ws, int64_t n);
 
 #define GVL_CUDA(expr)                                                                                  \
     do {                                                                                                \
@@ -23,6 +24,48 @@ int ensure_records(gvl_ctx *ctx, gvl_workspace &ws, int64_t n_rec);
             return gvl::fail(GVL_ERR_CUDA, "%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
         gvl::count_launch();                                                                            \
     } while (0)
+
+// ---- where a row's variant list comes from -------------------------------------------
+struct RowVars {
+    const int32_t *gv;    // SVAR1: variant indices of the row; merged lists: keys of the row
+    const int32_t *mpos;  // merged lists: positions of the row (NULL for SVAR1)
+    int64_t nvar;
+};
+
+__device__ __forceinline__ RowVars row_vars(const gvl_sparse_tables &tab, const MergedLists &M, const int64_t *goi,
+                                            int64_t k) {
+    RowVars r;
+    if (M.key) {
+        const int64_t o = M.off[k];
+        r.gv = M.key + o;
+        r.mpos = M.pos + o;
+        r.nvar = M.len[k];
+    } else {
+        const int64_t o_idx = goi[k];
+        const int64_t o_s = tab.geno_starts[o_idx];
+        r.gv = tab.geno_v_idxs + o_s;
+        r.mpos = nullptr;
+        r.nvar = imax64(tab.geno_stops[o_idx] - o_s, 0);
+    }
+    return r;
+}
+
+// variant i of a row: table index vi, position
+__device__ __forceinline__ int64_t var_pos(const gvl_sparse_tables &tab, const RowVars &r, int64_t i, int32_t vi) {
+    return r.mpos ? (int64_t)r.mpos[i] : (int64_t)tab.v_starts[vi];
+}
+
+// ALT bytes of variant (i, vi): offset into alt_alleles (>= 0) or, for a pure deletion of the svar2 source
+// (empty ALT, src/reconstruct/mod.rs:720-733), the anchor base ref[pos] encoded as ~(absolute ref offset)
+__device__ __forceinline__ void var_alt(const gvl_sparse_tables &tab, const RowVars &r, int32_t vi, int64_t pos,
+                                        int64_t c_s, int64_t &aoff, int64_t &alen) {
+    aoff = tab.alt_offsets[vi];
+    alen = tab.alt_offsets[vi + 1] - aoff;
+    if (r.mpos && alen == 0) {
+        aoff = ~(c_s + pos);
+        alen = 1;
+    }
+}
 
 // ---- small device helpers ----------------------------------------------------------
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }

@@ -88,9 +88,8 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) hap_plan_par_kernel(HapPl
     if (k >= P.n_work) return;  // (NT == 32: whole warps exit; NT == 256: whole CTA)
 
     const int64_t query = k / P.ploidy;
-    const int64_t o_idx = P.goi[k];
-    const int64_t o_s = P.tab.geno_starts[o_idx];
-    const int64_t nvar = imax64(P.tab.geno_stops[o_idx] - o_s, 0);
+    const RowVars rv = row_vars(P.tab, P.merged, P.goi, k);
+    const int64_t nvar = rv.nvar;
     const int64_t c_idx = P.regions[query * 3 + 0];
     const int64_t c_s = P.tab.ref_offsets[c_idx];
     const int64_t contig_len = P.tab.ref_offsets[c_idx + 1] - c_s;
@@ -99,7 +98,7 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) hap_plan_par_kernel(HapPl
     const int64_t shift = P.shifts[k];
     const bool has_keep = (P.keep && P.keep_off);
     const int64_t keep_base = has_keep ? P.keep_off[k] : 0;
-    const int32_t *__restrict__ gv = P.tab.geno_v_idxs + o_s;
+    const int32_t *__restrict__ gv = rv.gv;
     const bool ragged = P.output_length < 0;
     const bool sized = P.output_length == -1;
     const bool want_diff = sized || (P.diffs != nullptr);
@@ -128,7 +127,7 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) hap_plan_par_kernel(HapPl
             bool kept = false;
             if (i < nvar) {
                 const int32_t vi = gv[i];
-                pos = P.tab.v_starts[vi];
+                pos = var_pos(P.tab, rv, i, vi);
                 il = P.tab.ilens[vi];
                 kept = has_keep ? (P.keep[keep_base + i] != 0) : true;
             }
@@ -234,11 +233,11 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) hap_plan_par_kernel(HapPl
         bool kept = false;
         if (i < nvar) {
             vi = gv[i];
-            pos = P.tab.v_starts[vi];
+            pos = var_pos(P.tab, rv, i, vi);
             il = P.tab.ilens[vi];
-            aoff = P.tab.alt_offsets[vi];
-            alen = P.tab.alt_offsets[vi + 1] - aoff;
+            var_alt(P.tab, rv, vi, pos, c_s, aoff, alen);
             kept = has_keep ? (P.keep[keep_base + i] != 0) : true;
+            if (rv.mpos) vi = (int32_t)i;  // svar2 annotates with the LOCAL index (src/reconstruct/mod.rs:734)
         }
         const int64_t end = (i < nvar) ? pos - imin64(il, 0) + 1 : INT64_MIN;
         grp_sync<NT>();

@@ -1,0 +1,125 @@
+// gvl_svar2.cu -- device merge of the svar2 two-channel variant source.
+//
+// Reference: merge_hap (src/svar2/mod.rs:45-66) concatenates a haplotype's own `var_key` entries with
+// the presence-bit-selected entries of the query's shared `dense` window and stable-sorts by position
+// (var_key first on ties), per row, into a fresh Vec.  Both channels are position-sorted, so on the GPU
+// this is a rank computation instead of a sort: a var_key entry moves back by the number of PRESENT dense
+// entries strictly before it, a present dense entry by the number of var_key entries at or before it.
+#include "gvl_internal.cuh"
+
+namespace gvl {
+
+struct MergeParams {
+    gvl_svar2_channels ch;
+    int64_t n_work, ploidy, cap;
+    int32_t *m_pos, *m_key;
+    int64_t *m_off;
+    int32_t *m_len;
+    int64_t *words;
+};
+
+__device__ __forceinline__ int present_bit(const uint8_t *__restrict__ bits, int64_t bit) {  // src/svar2/mod.rs:35-38
+    return (bits[bit >> 3] >> (bit & 7)) & 1;
+}
+
+// number of set bits in [bit0, bit0 + n)
+__device__ __forceinline__ int64_t count_bits(const uint8_t *__restrict__ bits, int64_t bit0, int64_t n) {
+    int64_t c = 0, b = bit0, e = bit0 + n;
+    while (b < e && (b & 7)) c += present_bit(bits, b++);
+    while (e - b >= 8) {
+        c += __popc((unsigned)bits[b >> 3]);
+        b += 8;
+    }
+    while (b < e) c += present_bit(bits, b++);
+    return c;
+}
+
+constexpr int MERGE_WARPS = 4;
+
+__global__ void __launch_bounds__(MERGE_WARPS * 32) svar2_merge_kernel(MergeParams P) {
+    const int lane = lane_id();
+    const int64_t k = (int64_t)blockIdx.x * MERGE_WARPS + (threadIdx.x >> 5);
+    if (k >= P.n_work) return;
+    const int64_t query = k / P.ploidy;
+    const int64_t vk_lo = P.ch.vk_off[k], vk_hi = P.ch.vk_off[k + 1];
+    const int64_t n_vk = imax64(vk_hi - vk_lo, 0);
+    const int64_t ds = P.ch.dense_range[query * 2], de = P.ch.dense_range[query * 2 + 1];
+    const int64_t nd = imax64(de - ds, 0);
+    const int64_t base_bit = P.ch.dense_present_off[k];
+    const int32_t *__restrict__ vpos = P.ch.vk_pos + vk_lo;
+    const int32_t *__restrict__ vkey = P.ch.vk_key + vk_lo;
+    const int32_t *__restrict__ dpos = P.ch.dense_pos + ds;
+    const int32_t *__restrict__ dkey = P.ch.dense_key + ds;
+
+    int64_t off = 0;
+    if (lane == 0) off = (int64_t)atomicAdd((unsigned long long *)&P.words[4], (unsigned long long)(n_vk + nd));
+    off = __shfl_sync(0xffffffffu, off, 0);
+    const bool overflow = off + n_vk + nd > P.cap;
+    if (overflow) {
+        if (lane == 0) {
+            atomicMax((unsigned long long *)&P.words[W_STATUS], (unsigned long long)(off + n_vk + nd));
+            P.m_off[k] = 0;
+            P.m_len[k] = 0;
+        }
+        return;
+    }
+    // dense entries that are present: rank among present + var_key entries at or before them
+    int64_t n_present = 0;
+    for (int64_t base = 0; base < nd; base += 32) {
+        const int64_t j = base + lane;
+        const bool pr = (j < nd) && present_bit(P.ch.dense_present, base_bit + j);
+        const unsigned mask = __ballot_sync(0xffffffffu, pr);
+        if (pr) {
+            const int32_t p = dpos[j];
+            int64_t lo = 0, hi = n_vk;  // number of var_key entries with pos <= p
+            while (lo < hi) {
+                int64_t mid = (lo + hi) >> 1;
+                if (vpos[mid] <= p) lo = mid + 1; else hi = mid;
+            }
+            const int64_t w = off + n_present + __popc(mask & ((1u << lane) - 1u)) + lo;
+            P.m_pos[w] = p;
+            P.m_key[w] = dkey[j];
+        }
+        n_present += __popc(mask);
+    }
+    // var_key entries: move back by the present dense entries strictly before them
+    for (int64_t i = lane; i < n_vk; i += 32) {
+        const int32_t p = vpos[i];
+        int64_t lo = 0, hi = nd;  // number of dense entries with pos < p
+        while (lo < hi) {
+            int64_t mid = (lo + hi) >> 1;
+            if (dpos[mid] < p) lo = mid + 1; else hi = mid;
+        }
+        const int64_t w = off + i + count_bits(P.ch.dense_present, base_bit, lo);
+        P.m_pos[w] = p;
+        P.m_key[w] = vkey[i];
+    }
+    if (lane == 0) {
+        P.m_off[k] = off;
+        P.m_len[k] = (int32_t)(n_vk + n_present);
+    }
+}
+
+}  // namespace gvl
+
+using namespace gvl;
+
+int gvl_svar2_merge_launch(gvl_ctx *ctx, const gvl_svar2_channels *ch, int64_t batch, int64_t ploidy, int64_t max_merged,
+                           cudaStream_t st) {
+    const int64_t n_work = batch * ploidy;
+    if (n_work == 0) return GVL_OK;
+    MergeParams P;
+    P.ch = *ch;
+    P.n_work = n_work;
+    P.ploidy = ploidy;
+    P.cap = ctx->hap.m_cap;
+    P.m_pos = ctx->hap.m_pos;
+    P.m_key = ctx->hap.m_key;
+    P.m_off = ctx->hap.m_off;
+    P.m_len = ctx->hap.m_len;
+    P.words = ctx->dev_words;
+    (void)max_merged;
+    svar2_merge_kernel<<<(unsigned)((n_work + MERGE_WARPS - 1) / MERGE_WARPS), MERGE_WARPS * 32, 0, st>>>(P);
+    GVL_LAUNCH_CHECK();
+    return GVL_OK;
+}

@@ -27,6 +27,7 @@ constexpr int TRK_REC_CAP = 128;
 // =====================================================================================
 struct TrkPlanParams {
     gvl_sparse_tables tab;
+    MergedLists merged;
     const int32_t *regions;
     const int32_t *shifts;
     const int64_t *goi;
@@ -49,14 +50,13 @@ __global__ void __launch_bounds__(TPLAN_WARPS * 32) trk_plan_kernel(TrkPlanParam
     const int64_t k = (int64_t)blockIdx.x * TPLAN_WARPS + (threadIdx.x >> 5);
     if (k >= P.n_work) return;
     const int64_t query = k / P.ploidy;
-    const int64_t o_idx = P.goi[k];
-    const int64_t o_s = P.tab.geno_starts[o_idx];
-    const int64_t nvar = imax64(P.tab.geno_stops[o_idx] - o_s, 0);
+    const RowVars rv = row_vars(P.tab, P.merged, P.goi, k);
+    const int64_t nvar = rv.nvar;
     const int64_t q_start = P.regions[query * 3 + 1];
     const int64_t shift = P.shifts[k];
     const bool has_keep = (P.keep && P.keep_off);
     const int64_t keep_base = has_keep ? P.keep_off[k] : 0;
-    const int32_t *__restrict__ gv = P.tab.geno_v_idxs + o_s;
+    const int32_t *__restrict__ gv = rv.gv;
     const int64_t length = imax64(P.out_offsets[k + 1] - P.out_offsets[k], 0);
     const int64_t track_n = P.track_lengths[query];
 
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(TPLAN_WARPS * 32) trk_plan_kernel(TrkPlanParam
         bool kp = false;
         if (i < nvar) {
             int32_t vi = gv[i];
-            pos = P.tab.v_starts[vi];
+            pos = (int32_t)var_pos(P.tab, rv, i, vi);
             il = P.tab.ilens[vi];
             kp = has_keep ? (P.keep[keep_base + i] != 0) : true;
         }
@@ -563,6 +563,7 @@ static int realign_impl(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_
     GVL_CUDA(cudaMemsetAsync(words, 0, sizeof(int64_t) * 4, st));
     TrkPlanParams PP;
     PP.tab = *tab;
+    PP.merged = MergedLists{nullptr, nullptr, nullptr, nullptr};
     PP.regions = regions;
     PP.shifts = shifts;
     PP.goi = geno_offset_idx;

@@ -182,3 +182,60 @@ def batch_args(d: SynthData, r_idx, s_idx, rng=None, jitter: int = 0):
     to_rc = np.repeat(d.regions[r_idx, 3] == -1, d.ploidy)
     ds_idx = r_idx * d.n_samples + s_idx
     return np.ascontiguousarray(regions[:, :3]), np.ascontiguousarray(goi), np.ascontiguousarray(to_rc), ds_idx
+
+
+def to_svar2_channels(d: SynthData, regions, ds_idx, dense_frac: float = 0.5, seed: int = 0, pure_del: bool = True):
+    """Re-express a batch of an SVAR1-style dataset in the svar2 two-channel flat layout
+    (reference `FlatChannels`, src/svar2/mod.rs:150-160) at the decoded level:
+
+      * a random `dense_frac` of the variant table is declared "dense" (shared): per query the dense window is
+        every dense variant overlapping the (64-bp expanded) region; each haplotype gets LSB-first presence bits
+      * everything else a haplotype carries goes to its private var_key list
+      * keys index a decoded key table (ilen, ALT bytes); deletions become PURE deletions (empty ALT, the
+        anchor comes from the reference) when `pure_del` and their stored ALT equals the reference base
+
+    Returns a dict with the arrays of `gvl_svar2_channels` + the key table."""
+    rng = np.random.default_rng(seed)
+    V = d.v_starts.size
+    is_dense = rng.random(V) < dense_frac
+    b, p = len(ds_idx), d.ploidy
+    key_ilen = d.ilens.copy()
+    alt_off = d.alt_offsets.copy()
+    key_alt = d.alt_alleles
+    if pure_del:
+        # drop the anchor byte of deletions whose ALT is exactly the reference base at that position
+        contig0 = d.reference[d.ref_offsets[0]:d.ref_offsets[1]]
+        lens = np.diff(d.alt_offsets)
+        is_del = (d.ilens < 0) & (lens == 1) & (d.alt_alleles[d.alt_offsets[:-1]] == contig0[d.v_starts])
+        new_lens = np.where(is_del, 0, lens)
+        alt_off = np.concatenate([[0], np.cumsum(new_lens)]).astype(np.int64)
+        keep_bytes = np.repeat(~is_del, lens)
+        key_alt = d.alt_alleles[keep_bytes]
+    vk_pos, vk_key, vk_off = [], [], [0]
+    dense_pos, dense_key, dense_range = [], [], []
+    bits, bit_off = [], [0]
+    dense_idx = np.flatnonzero(is_dense)
+    for q in range(b):
+        lo = np.searchsorted(d.v_starts[dense_idx], regions[q, 1] - 64, "left")
+        hi = np.searchsorted(d.v_starts[dense_idx], regions[q, 2] + 64, "left")
+        win = dense_idx[lo:hi]
+        dense_range.append((len(dense_pos), len(dense_pos) + len(win)))
+        dense_pos.extend(d.v_starts[win].tolist())
+        dense_key.extend(win.tolist())
+        for h in range(p):
+            slot = int(ds_idx[q]) * p + h
+            vi = d.geno_v_idxs[d.geno_offsets[0, slot]:d.geno_offsets[1, slot]]
+            mine_dense = vi[is_dense[vi]]
+            mine_vk = vi[~is_dense[vi]]
+            vk_pos.extend(d.v_starts[mine_vk].tolist())
+            vk_key.extend(mine_vk.tolist())
+            vk_off.append(len(vk_pos))
+            bits.append(np.isin(win, mine_dense))
+            bit_off.append(bit_off[-1] + len(win))
+    allbits = np.concatenate(bits) if bits else np.zeros(0, bool)
+    dense_present = np.packbits(allbits, bitorder="little")
+    return dict(vk_pos=np.array(vk_pos, np.int32), vk_key=np.array(vk_key, np.int32), vk_off=np.array(vk_off, np.int64),
+                dense_pos=np.array(dense_pos, np.int32), dense_key=np.array(dense_key, np.int32),
+                dense_range=np.array(dense_range, np.int32).reshape(b, 2), dense_present=dense_present,
+                dense_present_off=np.array(bit_off, np.int64), key_ilen=key_ilen.astype(np.int32),
+                key_alt=np.ascontiguousarray(key_alt), key_alt_off=alt_off)

@@ -113,6 +113,32 @@ int gvl_dev_hap_plan(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_t *
                      const int64_t *keep_offsets, const uint8_t *to_rc, int64_t output_length, int64_t max_records,
                      int64_t *out_offsets, int32_t *diffs, gvl_stream stream);
 
+/* svar2 two-channel variant source, flat per-call layout of the reference's `FlatChannels`
+ * (src/svar2/mod.rs:150-160; consumed by reconstruct_haplotypes_from_svar2, src/reconstruct/mod.rs:620-826).
+ * Device pointers.  Keys are indices into a DECODED key table that stands for svar2_codec::decode_key +
+ * decode_alt (src/svar2/mod.rs:17-28; third-party codec, parity unpinned): the table is passed as
+ * gvl_sparse_tables.{ilens, alt_offsets, alt_alleles, n_variants}; an empty ALT means a pure deletion whose
+ * anchor base is taken from ref[pos] (src/reconstruct/mod.rs:720-733).  Both channels are position-sorted. */
+typedef struct {
+    const int32_t *vk_pos;            /* per-hap var_key channel: positions                           */
+    const int32_t *vk_key;            /*                          keys                                */
+    const int64_t *vk_off;            /* i64[b*p+1] CSR offsets by flat row k = query*ploidy + hap    */
+    const int32_t *dense_pos;         /* shared dense channel: positions                              */
+    const int32_t *dense_key;         /*                       keys                                   */
+    const int32_t *dense_range;       /* i32[b,2] window [ds, de) of each query                       */
+    const uint8_t *dense_present;     /* presence bits over the window, LSB first                     */
+    const int64_t *dense_present_off; /* i64[b*p+1] BIT offsets by flat row                           */
+} gvl_svar2_channels;
+
+/* gvl_dev_hap_plan for the svar2 source: merges each row's two channels on the device (stable by position,
+ * var_key first on ties, src/svar2/mod.rs:45-66), then plans exactly like the SVAR1 source.  Variant indices
+ * written by the annotated mode are LOCAL to the row (src/reconstruct/mod.rs:734).
+ *   max_merged = sum over rows of (var_key entries + dense window size)  (workspace capacity) */
+int gvl_dev_hap_plan_svar2(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_svar2_channels *ch,
+                           const int32_t *regions, const int32_t *shifts, int64_t batch, int64_t ploidy,
+                           const uint8_t *to_rc, int64_t output_length, int64_t max_merged, int64_t *out_offsets,
+                           int32_t *diffs, gvl_stream stream);
+
 /* Total number of output positions of the current plan (= out_offsets[-1]).  Fixed-length plans
  * answer from the host; ragged plans synchronise the stream once (the reference sizes its
  * allocation at the same point, src/ffi/mod.rs:814). */
@@ -208,6 +234,16 @@ int gvl_reconstruct_haplotypes_fused_begin(
     int64_t *out_offsets, int64_t *total);
 int gvl_reconstruct_haplotypes_fused_finish(gvl_ctx *ctx, int mode, uint8_t pad_char, uint8_t *out, int32_t *annot_v,
                                             int32_t *annot_pos);
+
+/* reconstruct_haplotypes_from_svar2, src/ffi/mod.rs:874-893 (sizes rows like the fused SVAR1 entry; finish with
+ * gvl_reconstruct_haplotypes_fused_finish).  The reference passes codec keys + the long-allele LUT; this entry
+ * takes the DECODED key table (key_ilen, key_alt, key_alt_off) -- see gvl_svar2_channels.  Host pointers. */
+int gvl_reconstruct_haplotypes_from_svar2_begin(
+    gvl_ctx *ctx, const int32_t *regions, const int32_t *shifts, int64_t batch, int64_t ploidy, const int32_t *vk_pos,
+    const int32_t *vk_key, const int64_t *vk_off, const int32_t *dense_pos, const int32_t *dense_key, int64_t n_dense,
+    const int32_t *dense_range, const uint8_t *dense_present, const int64_t *dense_present_off, const int32_t *key_ilen,
+    const uint8_t *key_alt, const int64_t *key_alt_off, int64_t n_keys, const uint8_t *ref_, const int64_t *ref_offsets,
+    int64_t n_contigs, int64_t output_length, const uint8_t *to_rc, int64_t *out_offsets, int64_t *total);
 
 /* reconstruct_haplotypes_from_sparse, src/ffi/mod.rs:634-655: caller-sized rows, writes `out`
  * (and the optional annotation buffers) in place.  out: host u8[out_offsets[b*p]]. */

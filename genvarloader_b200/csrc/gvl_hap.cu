@@ -355,7 +355,6 @@ __global__ void __launch_bounds__(EXEC_THREADS) hap_exec_kernel(HapExecParams P)
     constexpr bool OH = (MODE == GVL_MODE_ONEHOT || MODE == GVL_MODE_ONEHOT_CF);
     __shared__ TileRecs S;
     __shared__ __align__(16) uint32_t s_lut[OH ? 512 : 4];  // [0,256): one-hot(b); [256,512): one-hot(complement(b))
-    __shared__ int s_cnt[2];
     __shared__ int64_t s_lo, s_hi;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -386,8 +385,7 @@ __global__ void __launch_bounds__(EXEC_THREADS) hap_exec_kernel(HapExecParams P)
     const bool rc = rp.rc != 0;
 
     if (OH) reinterpret_cast<uint4 *>(s_lut)[tid] = make_uint4(0u, 0u, 0u, 0u);  // 128 threads x 16 B = the whole table
-    if (tid < 2) s_cnt[tid] = 0;
-    __syncthreads();
+    if (OH) __syncthreads();
     if (OH && tid < 8) {  // the only non-zero entries: ACGT (and their complements in the second half)
         const int i = tid & 3;
         const uint32_t letter = (0x54474341u >> (8 * i)) & 0xffu;  // 'A','C','G','T'
@@ -395,33 +393,26 @@ __global__ void __launch_bounds__(EXEC_THREADS) hap_exec_kernel(HapExecParams P)
     }
 
     // ---- records of this tile: r_lo = last with a <= h0 (or -1), r_hi = first with a >= h1 ----
+    // (warp 0 only: the other warps have nothing to do until the records are staged)
     const int32_t *__restrict__ ra = P.rec.a + rp.rec_off;
-    if (rp.n_rec <= COUNT_MAX) {
-        int c0 = 0, c1 = 0;  // sorted array: counts are indices
-        for (int i = tid; i < rp.n_rec; i += EXEC_THREADS) {
-            int32_t a = ra[i];
-            c0 += (a <= h0);
-            c1 += (a < h1);
+    if (warp == 0) {
+        int64_t r_lo, r_hi0;
+        if (rp.n_rec <= COUNT_MAX) {
+            int c0 = 0, c1 = 0;  // sorted array: counts are indices
+            for (int i = lane; i < rp.n_rec; i += 32) {
+                const int32_t a = ra[i];
+                c0 += (a <= h0);
+                c1 += (a < h1);
+            }
+            r_lo = (int64_t)__reduce_add_sync(0xffffffffu, c0) - 1;
+            r_hi0 = __reduce_add_sync(0xffffffffu, c1);
+        } else {
+            r_lo = warp_upper_le(ra, 0, rp.n_rec, h0);
+            r_hi0 = warp_upper_le(ra, imax64(r_lo, 0), rp.n_rec, h1 - 1) + 1;
         }
-        for (int o = 16; o > 0; o >>= 1) {
-            c0 += __shfl_xor_sync(0xffffffffu, c0, o);
-            c1 += __shfl_xor_sync(0xffffffffu, c1, o);
-        }
-        if (lane == 0 && (c0 | c1)) {
-            atomicAdd(&s_cnt[0], c0);
-            atomicAdd(&s_cnt[1], c1);
-        }
-        __syncthreads();
-        if (tid == 0) {
-            s_lo = (int64_t)s_cnt[0] - 1;
-            s_hi = s_cnt[1];
-        }
-    } else if (tid < 32) {
-        int64_t r_lo = warp_upper_le(ra, 0, rp.n_rec, h0);
-        int64_t r_hi = warp_upper_le(ra, imax64(r_lo, 0), rp.n_rec, h1 - 1) + 1;
-        if (tid == 0) {
+        if (lane == 0) {
             s_lo = r_lo;
-            s_hi = r_hi;
+            s_hi = r_hi0;
         }
     }
     __syncthreads();
@@ -470,7 +461,7 @@ __global__ void __launch_bounds__(EXEC_THREADS) hap_exec_kernel(HapExecParams P)
         const int m = m_new + 1;
         const int32_t seg_end = (r + 1 + m_new < r_hi) ? ra[r + 1 + m_new] : h1;
         __syncthreads();  // previous pass finished reading S
-        for (int i = tid; i < m; i += EXEC_THREADS) {
+        for (int i = tid; i < m; i += EXEC_THREADS) {  // (m is a handful of records: effectively warp 0)
             int64_t idx = r + i;
             if (idx < 0) {  // virtual record: leading pad, then reference from ref0
                 S.a[0] = 0;
@@ -542,6 +533,7 @@ __global__ void __launch_bounds__(EXEC_THREADS) hap_exec_kernel(HapExecParams P)
                 }
             }
             // ---- block with variants / pads / pass edges: group by group ----
+            int ig = (jb >= jo_lo && jb + 512 <= jo_hi) ? ic : -1;  // cursor for the block's lowest position, if known
 #pragma unroll 1
             for (int k = 0; k < 4; k++) {
                 const int32_t cg = blk * 128 + 32 * k;  // first chunk of the group
@@ -550,7 +542,9 @@ __global__ void __launch_bounds__(EXEC_THREADS) hap_exec_kernel(HapExecParams P)
                 const int32_t j = jg + 4 * lane;
                 if (jg >= jo_lo && jg + 128 <= jo_hi) {
                     const int32_t p_lo = rc ? (L - 128 - jg) : jg;
-                    const int ig = find_rec(S, m, p_lo);
+                    if (ig < 0) ig = find_rec(S, m, p_lo);
+                    while (S.a[ig + 1] <= p_lo) ig++;  // forward rows: groups ascend
+                    while (S.a[ig] > p_lo) ig--;       // reversed rows: groups descend
                     const int32_t e_i = S.e[ig];
                     const int64_t rpos_lo = (int64_t)S.resume[ig] + (p_lo - e_i);
                     if (p_lo >= e_i && p_lo + 127 < S.a[ig + 1] && rpos_lo + 127 < rp.contig_len) {

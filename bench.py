@@ -60,15 +60,19 @@ def build_workload(name: str, seed: int):
     return w, d
 
 
-def make_batches(d, w, n_batches: int, seed: int):
-    """Distinct (region, sample) batches, built like the reference's host prep (see synth.batch_args)."""
+def make_batches(d, w, n_batches: int, seed: int, rank: int = 0, world: int = 1):
+    """Distinct (region, sample) batches, built like the reference's host prep (see synth.batch_args).
+    With `world` ranks every GLOBAL batch holds world x pairs (region, sample) pairs drawn from one shared
+    seed; rank r works on its contiguous block of it (genvarloader_b200._dist.shard_bounds) -- weak scaling."""
     from genvarloader_b200 import synth
+    from genvarloader_b200._dist import shard_bounds
 
     rng = np.random.default_rng(seed)
     out = []
     for _ in range(n_batches):
-        r_idx = rng.integers(0, d.n_regions, w["pairs"])
-        s_idx = rng.integers(0, d.n_samples, w["pairs"])
+        lo, hi = shard_bounds(w["pairs"] * world, rank, world)
+        r_idx = rng.integers(0, d.n_regions, w["pairs"] * world)[lo:hi]
+        s_idx = rng.integers(0, d.n_samples, w["pairs"] * world)[lo:hi]
         regions, goi, to_rc, _ = synth.batch_args(d, r_idx, s_idx)
         shifts = np.zeros(goi.shape, np.int32)
         nvar = int((d.geno_offsets[1, goi.ravel()] - d.geno_offsets[0, goi.ravel()]).sum())
@@ -224,7 +228,7 @@ def run_b200(args):
     L, rows = w["window"], w["pairs"] * 2
     n_slots = args.slots
     n_batches = max(args.ring, n_slots)
-    batches = make_batches(d, w, n_batches, args.seed + 1 + rank)  # ranks work on different (region, sample) shards
+    batches = make_batches(d, w, n_batches, args.seed + 1, rank, world)  # this rank's shard of every global batch
     eng0 = Engine(dev, d.reference, d.ref_offsets, d.v_starts, d.ilens, d.alt_alleles, d.alt_offsets, d.geno_v_idxs,
                   d.geno_offsets)
     step_bytes_out = rows * L * 4
@@ -454,7 +458,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--seed", type=int, default=2)
-    ap.add_argument("--slots", type=int, default=4, help="batches in flight (streams)")
+    ap.add_argument("--slots", type=int, default=8, help="batches in flight (streams)")
     ap.add_argument("--ring", type=int, default=8, help="distinct batches / output buffers cycled through")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

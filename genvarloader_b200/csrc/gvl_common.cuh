@@ -52,6 +52,7 @@ struct MergedLists {
 enum { W_CURSOR = 0, W_STATUS = 1, W_TOTAL = 2, W_TILES = 3, W_COUNT = 8 };
 
 constexpr int EXEC_THREADS = 128;
+constexpr int EXEC_MIN_CTAS = 12;        // resident CTAs per SM the execute kernels are compiled for (<= 40 registers)
 constexpr int EXEC_UNIT = EXEC_THREADS * 4;  // positions covered by one CTA-wide step (4 per thread)
 constexpr int TILE = 4096;       // haplotype positions per execute CTA for ragged plans (fixed plans pick theirs)
 constexpr int REC_CAP = 256;     // records staged in shared memory per pass

@@ -350,7 +350,7 @@ __device__ __forceinline__ int find_rec(const TileRecs &S, int m, int32_t p) {
 constexpr int COUNT_MAX = 2048;  // rows with more records locate their tile range by 32-ary search
 
 template <int MODE>
-__global__ void __launch_bounds__(EXEC_THREADS) hap_exec_kernel(HapExecParams P) {
+__global__ void __launch_bounds__(EXEC_THREADS, EXEC_MIN_CTAS) hap_exec_kernel(HapExecParams P) {
     constexpr bool ANNOT = (MODE == GVL_MODE_ANNOTATED);
     constexpr bool OH = (MODE == GVL_MODE_ONEHOT || MODE == GVL_MODE_ONEHOT_CF);
     __shared__ TileRecs S;
@@ -874,6 +874,7 @@ int gvl_dev_hap_exec(gvl_ctx *ctx, const gvl_sparse_tables *tab, int mode, uint8
         const int64_t units_per_row = (ctx->fixed_len + EXEC_UNIT - 1) / EXEC_UNIT;
         const int64_t tiles_target = imax64(1, exec_capacity(ctx, mode) / ctx->n_work);
         int64_t units_per_tile = (units_per_row + tiles_target - 1) / tiles_target;
+        units_per_tile = (units_per_tile + 3) & ~(int64_t)3;  // whole 512-position blocks for each of the 4 warps
         units_per_tile = imax64(4, imin64(units_per_tile, 64));
         P.tile_len = (int32_t)(units_per_tile * EXEC_UNIT);
         P.tiles_per_row = (ctx->fixed_len + P.tile_len - 1) / P.tile_len;

@@ -381,7 +381,7 @@ def run_b200(args):
         del flush
         ab = alg_bytes(w, s["nvar"])
         achieved = ab / (exec_ms * 1e-3) / 1e9
-        step_achieved = ab * args.steps / (ms * 1e-3) / 1e9
+        step_achieved = ab * args.steps / (ms * 1e-3) / 1e9  # per GPU (every rank runs `steps` steps of its shard)
         traffic = None
         tp = ROOT / "profiles" / "ncu_exec_traffic.json"
         if tp.exists():
@@ -429,14 +429,14 @@ def run_b200(args):
                        "l2": f"ring of {len(slots)} distinct batches/outputs = {len(slots) * step_bytes_out >> 20} MiB written per cycle "
                              "(> 126 MB L2); roofline launches are preceded by a 512 MiB L2 flush",
                        "parallelism": f"dp{world} (replicated tables, (region,sample) shards, no collective)"},
-            "output_GBps": value * 4 / 1e9, "algorithmic_GBps": step_achieved,
+            "output_GBps": value * 4 / 1e9, "algorithmic_GBps": step_achieved * world,
             "roofline": {"bound": "hbm", "kernel": "hap_exec_kernel<ONEHOT>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "alg_bytes_per_launch": ab, "launch_ms": exec_ms, "plan_kernel_ms": plan_ms,
                          "launch_ms_isolated_after_l2_flush": exec_ms_isolated,
                          "how": "execute launches of the whole ring replayed back to back as one CUDA graph on one stream; event time / launches",
                          "frac_of_nominal_8TBps": achieved / 8000.0,
-                         "whole_step_frac": step_achieved / world / peak},
+                         "whole_step_frac": step_achieved / peak},
             "cpu_baseline": {"value": cpu_v, "unit": "bp/s", "cores": threads, "kind": "port",
                              "sample": f"{cpu_n} batches ({cpu_s:.1f} s) of the same workload; C restatement of the reference's "
                                        "reconstruct_haplotypes_fused + separate one-hot pass (oracle/gvl_oracle.c)",

@@ -55,7 +55,9 @@ constexpr int EXEC_THREADS = 128;
 constexpr int EXEC_MIN_CTAS = 12;        // resident CTAs per SM the execute kernels are compiled for (<= 40 registers)
 constexpr int EXEC_UNIT = EXEC_THREADS * 4;  // positions covered by one CTA-wide step (4 per thread)
 constexpr int TILE = 4096;       // haplotype positions per execute CTA for ragged plans (fixed plans pick theirs)
-constexpr int REC_CAP = 256;     // records staged in shared memory per pass
+constexpr int REC_CAP = 128;     // records staged in shared memory per pass
+constexpr int EXEC_MAX_UNITS = 16;  // <= 8192 haplotype positions per CTA: its reference window fits shared memory
+constexpr int WIN_CAP = EXEC_MAX_UNITS * EXEC_THREADS * 4 + 1024;  // bytes of reference staged per pass (TMA bulk copy)
 constexpr int64_t ALT_PAD = INT64_MIN;  // RecArrays.src sentinel: "ALT piece" is padding (leading pad)
 
 }  // namespace gvl

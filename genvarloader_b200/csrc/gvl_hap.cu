@@ -355,7 +355,10 @@ __global__ void __launch_bounds__(EXEC_THREADS, EXEC_MIN_CTAS) hap_exec_kernel(H
     constexpr bool OH = (MODE == GVL_MODE_ONEHOT || MODE == GVL_MODE_ONEHOT_CF);
     __shared__ TileRecs S;
     __shared__ __align__(16) uint32_t s_lut[OH ? 512 : 4];  // [0,256): one-hot(b); [256,512): one-hot(complement(b))
-    __shared__ int64_t s_lo, s_hi;
+    __shared__ __align__(16) uint8_t s_win[WIN_CAP + 16];   // reference bytes of the pass, staged by one TMA bulk copy
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ int64_t s_lo, s_hi, s_wabs;
+    __shared__ int32_t s_wbytes;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     // ---- tile -> (row, tile-in-row) ----
@@ -385,7 +388,8 @@ __global__ void __launch_bounds__(EXEC_THREADS, EXEC_MIN_CTAS) hap_exec_kernel(H
     const bool rc = rp.rc != 0;
 
     if (OH) reinterpret_cast<uint4 *>(s_lut)[tid] = make_uint4(0u, 0u, 0u, 0u);  // 128 threads x 16 B = the whole table
-    if (OH) __syncthreads();
+    if (tid == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
     if (OH && tid < 8) {  // the only non-zero entries: ACGT (and their complements in the second half)
         const int i = tid & 3;
         const uint32_t letter = (0x54474341u >> (8 * i)) & 0xffu;  // 'A','C','G','T'
@@ -421,17 +425,19 @@ __global__ void __launch_bounds__(EXEC_THREADS, EXEC_MIN_CTAS) hap_exec_kernel(H
     int32_t cur = h0;
     const uint8_t *__restrict__ refrow = P.ref + rp.ref_base;
     uint8_t *__restrict__ out_row = P.out + (OH ? 4 : 1) * rp.out_off;  // position j of the row lives at out_row[(4*)j]
-    const uint32_t *lut = s_lut + (rc ? 256 : 0);
+    const uint32_t lut_a = smem_u32(s_lut);   // byte address of the table in shared memory
+    const uint32_t lut_rc = rc ? 1024u : 0u;  // second half = one-hot of the complement
+    uint32_t win_phase = 0;
 
     // one 4-position chunk made only of reference bytes: v holds the bytes in OUTPUT order (not yet
     // complemented), r0 = reference position of the chunk's lowest haplotype position
     auto emit_ref4 = [&](int32_t j, uint32_t v, int32_t r0) {
         if (OH) {
-            uint4 o;
-            o.x = lut[v & 0xffu];
-            o.y = lut[(v >> 8) & 0xffu];
-            o.z = lut[(v >> 16) & 0xffu];
-            o.w = lut[v >> 24];
+            uint4 o;  // table offset of base i = (byte_i * 4) | half: one shift + one 3-input logic op each
+            o.x = lds_u32(lut_a + (((v << 2) & 0x3fcu) | lut_rc));
+            o.y = lds_u32(lut_a + (((v >> 6) & 0x3fcu) | lut_rc));
+            o.z = lds_u32(lut_a + (((v >> 14) & 0x3fcu) | lut_rc));
+            o.w = lds_u32(lut_a + (((v >> 22) & 0x3fcu) | lut_rc));
             if (MODE == GVL_MODE_ONEHOT) {
                 *reinterpret_cast<uint4 *>(out_row + 4 * (int64_t)j) = o;
             } else {
@@ -486,6 +492,50 @@ __global__ void __launch_bounds__(EXEC_THREADS, EXEC_MIN_CTAS) hap_exec_kernel(H
         if (tid == 0) S.a[m] = INT32_MAX;
         __syncthreads();
 
+        // ---- stage the pass's reference window with ONE TMA bulk copy (cp.async.bulk -> mbarrier) ----
+        // window = [first reference position read, last + 1) of the spans of this pass, clipped to the contig
+        // and to WIN_CAP; anything outside (huge deletions, unsorted jumps) is read from global memory instead
+        if (warp == 0) {
+            int64_t lo = INT64_MAX, hi = INT64_MIN;
+            for (int i = lane; i < m; i += 32) {
+                const int32_t s0 = max(S.e[i], cur), s1 = min(S.a[i + 1], seg_end);  // span of entry i inside the pass
+                if (s1 > s0) {
+                    const int64_t r0 = (int64_t)S.resume[i] + (s0 - S.e[i]);
+                    lo = imin64(lo, r0);
+                    hi = imax64(hi, r0 + (s1 - s0));
+                }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                lo = imin64(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+                hi = imax64(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            }
+            if (lane == 0) {
+                hi = imin64(hi, rp.contig_len);
+                lo = imax64(lo, 0);
+                int64_t abs0 = 0;
+                int32_t bytes = 0;
+                if (hi > lo) {
+                    abs0 = (rp.ref_base + lo) & ~(int64_t)15;
+                    const int64_t abs1 = (rp.ref_base + hi + 4 + 15) & ~(int64_t)15;  // +4: the 32-bit pair read overruns
+                    bytes = (int32_t)imin64(abs1 - abs0, WIN_CAP);
+                }
+                s_wabs = abs0;
+                s_wbytes = bytes;
+                if (bytes > 0) {
+                    mbar_expect_tx(&s_bar, (uint32_t)bytes);
+                    bulk_g2s(s_win, P.ref + abs0, (uint32_t)bytes, &s_bar);
+                }
+            }
+        }
+        __syncthreads();
+        const int64_t w_abs0 = s_wabs;
+        const int64_t w_abs1 = w_abs0 + s_wbytes;
+        if (s_wbytes > 0) {
+            mbar_wait(&s_bar, win_phase);
+            win_phase ^= 1;
+        }
+        const uint32_t win_a = smem_u32(s_win);
+
         // ---- output range of this pass, chunked by 4 on the GLOBAL flat index ----
         // chunk c covers row positions j0+4c .. j0+4c+3; a GROUP is 32 chunks (one per lane: 128
         // positions, one 512-byte one-hot store per warp), a BLOCK is 4 groups.  Warp w owns blocks
@@ -513,15 +563,28 @@ __global__ void __launch_bounds__(EXEC_THREADS, EXEC_MIN_CTAS) hap_exec_kernel(H
                 if (p_lo >= e_i && p_lo + 511 < S.a[ic + 1] && rpos_lo + 511 < rp.contig_len) {
                     // 512 reference bytes in a row: all 8 loads first, then 4 encodes + stores
                     const int32_t r_lane = (int32_t)rpos_lo + (rc ? 508 - 4 * lane : 4 * lane);
+                    const int64_t abs_lo = rp.ref_base + rpos_lo;  // absolute offset of the block's first reference byte
                     const uintptr_t addr = reinterpret_cast<uintptr_t>(refrow + r_lane);
-                    const uint32_t *w = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
                     const unsigned sh = (unsigned)(addr & 3) * 8u;
                     uint32_t w0[4], w1[4];
+                    if (abs_lo >= w_abs0 && abs_lo + 512 + 4 <= w_abs1) {
+                        // staged: two aligned 32-bit shared-memory loads per chunk (P.ref is 16-byte aligned, so the
+                        // low address bits of the staged copy equal those of the global address)
+                        const uint32_t sa = win_a + (uint32_t)((rp.ref_base + r_lane - w_abs0) & ~(int64_t)3);
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const int off = rc ? -32 * k : 32 * k;  // group k of the OUTPUT lies 128 bytes further (back)
-                        w0[k] = __ldg(w + off);
-                        w1[k] = __ldg(w + off + 1);  // (readable: buffers carry >= 16 B of slack)
+                        for (int k = 0; k < 4; k++) {
+                            const int off = rc ? -128 * k : 128 * k;
+                            w0[k] = lds_u32(sa + off);
+                            w1[k] = lds_u32(sa + off + 4);
+                        }
+                    } else {
+                        const uint32_t *w = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const int off = rc ? -32 * k : 32 * k;  // group k of the OUTPUT lies 128 bytes further (back)
+                            w0[k] = __ldg(w + off);
+                            w1[k] = __ldg(w + off + 1);  // (readable: buffers carry >= 16 B of slack)
+                        }
                     }
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
@@ -549,9 +612,19 @@ __global__ void __launch_bounds__(EXEC_THREADS, EXEC_MIN_CTAS) hap_exec_kernel(H
                     const int64_t rpos_lo = (int64_t)S.resume[ig] + (p_lo - e_i);
                     if (p_lo >= e_i && p_lo + 127 < S.a[ig + 1] && rpos_lo + 127 < rp.contig_len) {
                         const int32_t r_lane = (int32_t)rpos_lo + (rc ? 124 - 4 * lane : 4 * lane);
+                        const int64_t abs_lo = rp.ref_base + rpos_lo;
                         const uintptr_t addr = reinterpret_cast<uintptr_t>(refrow + r_lane);
-                        const uint32_t *w = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
-                        uint32_t v = __funnelshift_r(__ldg(w), __ldg(w + 1), (unsigned)(addr & 3) * 8u);
+                        uint32_t x0, x1;
+                        if (abs_lo >= w_abs0 && abs_lo + 128 + 4 <= w_abs1) {
+                            const uint32_t sa = win_a + (uint32_t)((rp.ref_base + r_lane - w_abs0) & ~(int64_t)3);
+                            x0 = lds_u32(sa);
+                            x1 = lds_u32(sa + 4);
+                        } else {
+                            const uint32_t *w = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
+                            x0 = __ldg(w);
+                            x1 = __ldg(w + 1);
+                        }
+                        uint32_t v = __funnelshift_r(x0, x1, (unsigned)(addr & 3) * 8u);
                         if (rc) v = __byte_perm(v, 0, 0x0123);
                         emit_ref4(j, v, r_lane);
                         continue;
@@ -856,6 +929,7 @@ int gvl_dev_hap_exec(gvl_ctx *ctx, const gvl_sparse_tables *tab, int mode, uint8
     if (!out) return fail(GVL_ERR_ARG, "gvl_dev_hap_exec: out is NULL");
     if (((uintptr_t)out & 15) || ((uintptr_t)annot_v & 15) || ((uintptr_t)annot_pos & 15))
         return fail(GVL_ERR_ARG, "gvl_dev_hap_exec: output buffers must be 16-byte aligned");
+    if ((uintptr_t)tab->ref & 15) return fail(GVL_ERR_ARG, "gvl_dev_hap_exec: the reference buffer must be 16-byte aligned");
     if (mode == GVL_MODE_ANNOTATED && (!annot_v || !annot_pos))
         return fail(GVL_ERR_ARG, "gvl_dev_hap_exec: annotated mode needs annot_v and annot_pos");
     HapExecParams P;
@@ -875,7 +949,7 @@ int gvl_dev_hap_exec(gvl_ctx *ctx, const gvl_sparse_tables *tab, int mode, uint8
         const int64_t tiles_target = imax64(1, exec_capacity(ctx, mode) / ctx->n_work);
         int64_t units_per_tile = (units_per_row + tiles_target - 1) / tiles_target;
         units_per_tile = (units_per_tile + 3) & ~(int64_t)3;  // whole 512-position blocks for each of the 4 warps
-        units_per_tile = imax64(4, imin64(units_per_tile, 64));
+        units_per_tile = imax64(4, imin64(units_per_tile, EXEC_MAX_UNITS));
         P.tile_len = (int32_t)(units_per_tile * EXEC_UNIT);
         P.tiles_per_row = (ctx->fixed_len + P.tile_len - 1) / P.tile_len;
         P.tile_off = nullptr;

@@ -13,7 +13,7 @@ from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
-LIB = PKG / "_lib" / "libgvl_b200.so"
+LIB = PKG / "_lib" / os.environ.get("GVL_LIB_NAME", "libgvl_b200.so")
 SOURCES = ["gvl_ctx.cu", "gvl_hap.cu", "gvl_svar2.cu", "gvl_tracks.cu", "gvl_host.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -44,7 +44,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         return LIB
     LIB.parent.mkdir(exist_ok=True)
     srcs = [str(CSRC / s) for s in SOURCES if (CSRC / s).exists()]
-    cmd = [nvcc(), *NVCC_FLAGS, "-shared", "-o", str(LIB), *srcs]
+    cmd = [nvcc(), *NVCC_FLAGS, *os.environ.get("GVL_EXTRA_NVCC_FLAGS", "").split(), "-shared", "-o", str(LIB), *srcs]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))

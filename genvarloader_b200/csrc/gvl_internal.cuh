@@ -101,6 +101,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
 }
 
+// Ampere-style asynchronous 16-byte copy global -> shared (SASS: LDGSTS), per-thread completion groups
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));

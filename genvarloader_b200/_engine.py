@@ -40,7 +40,7 @@ class Engine:
     (python/genvarloader/_dataset/_haps.py:233-247) plus the memmapped genotype/interval arrays."""
 
     def __init__(self, device, reference, ref_offsets, v_starts, ilens, alt_alleles, alt_offsets, geno_v_idxs,
-                 geno_offsets, pad_char: int = ord("N")):
+                 geno_offsets, pad_char: int = ord("N"), pack_reference: bool = True):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("genvarloader_b200 needs a CUDA device; there is no CPU path")
@@ -66,10 +66,20 @@ class Engine:
             self.geno_starts = _dev(self.geno_offsets_host[0], np.int64, self.device)
             self.geno_stops = _dev(self.geno_offsets_host[1], np.int64, self.device)
         self.n_contigs = int(np.asarray(ref_offsets).size - 1)
+        # 4-bit-per-base copy of the reference for the one-hot execute kernel (gvl_dev_pack_reference)
+        self.ref_packed = None
+        if pack_reference:
+            n_bases = int(np.asarray(reference).size)
+            lib.gvl_packed_reference_words.restype = c_i64
+            n_words = int(lib.gvl_packed_reference_words(c_i64(n_bases)))
+            with torch.cuda.device(self.device):
+                self.ref_packed = torch.empty(n_words, dtype=torch.int32, device=self.device)
+                check(lib.gvl_dev_pack_reference(self.ctx.handle, ptr(self.ref), c_i64(n_bases), ptr(self.ref_packed),
+                                                 _stream()))
         self.tab = SparseTables(
             ptr(self.ref), ptr(self.ref_offsets), self.n_contigs, ptr(self.v_starts), ptr(self.ilens),
             ptr(self.alt_alleles), ptr(self.alt_offsets), int(self.v_starts.numel()), ptr(self.geno_v_idxs),
-            ptr(self.geno_starts), ptr(self.geno_stops), int(self.geno_starts.numel()))
+            ptr(self.geno_starts), ptr(self.geno_stops), int(self.geno_starts.numel()), ptr(self.ref_packed))
         self.tracks: dict[str, tuple] = {}
         self._n_work = 0
         self._fixed = -1

@@ -35,6 +35,7 @@ class SparseTables(C.Structure):
         ("ref", c_vp), ("ref_offsets", c_vp), ("n_contigs", c_i64),
         ("v_starts", c_vp), ("ilens", c_vp), ("alt_alleles", c_vp), ("alt_offsets", c_vp), ("n_variants", c_i64),
         ("geno_v_idxs", c_vp), ("geno_starts", c_vp), ("geno_stops", c_vp), ("n_geno", c_i64),
+        ("ref_packed", c_vp),
     ]
 
 
@@ -55,6 +56,8 @@ def _load() -> C.CDLL:
     lib.gvl_last_error.restype = C.c_char_p
     lib.gvl_launch_count.restype = c_i64
     lib.gvl_launch_count.argtypes = [C.c_int]
+    lib.gvl_packed_reference_words.restype = c_i64
+    lib.gvl_packed_reference_words.argtypes = [c_i64]
     return lib
 
 

@@ -58,6 +58,7 @@ constexpr int TILE = 4096;       // haplotype positions per execute CTA for ragg
 constexpr int REC_CAP = 128;     // records staged in shared memory per pass
 constexpr int EXEC_MAX_UNITS = 16;  // <= 8192 haplotype positions per CTA: its reference window fits shared memory
 constexpr int WIN_CAP = EXEC_MAX_UNITS * EXEC_THREADS * 4 + 1024;  // bytes of reference staged per pass (TMA bulk copy)
+constexpr int DIR_Q = 1024;      // haplotype positions per directory entry (execute tiles are multiples of it)
 constexpr int64_t ALT_PAD = INT64_MIN;  // RecArrays.src sentinel: "ALT piece" is padding (leading pad)
 
 }  // namespace gvl
@@ -83,6 +84,9 @@ struct gvl_workspace {
     int64_t m_cap;
     int64_t *m_off;     // i64[rows_cap]
     int32_t *m_len;     // i32[rows_cap]
+    // fixed-length plans: per-row checkpoint directory, dir[row * stride + q] = records with a < q * DIR_Q
+    int32_t *dir;
+    int64_t dir_cap;
 };
 
 struct gvl_ctx {
@@ -96,10 +100,13 @@ struct gvl_ctx {
     bool plan_valid;
     int64_t n_work;
     int64_t fixed_len;  // >=0 fixed, -1 ragged
+    int64_t dir_stride; // directory entries per row of the current plan (0 = no directory)
     int64_t total;      // -1 = unknown (ragged before sync)
     int64_t *plan_out_offsets;  // device pointer supplied at plan time
+    int last_exec_kernel;       // 0 byte-oriented, 1 packed one-hot (gvl_debug_last_exec_kernel)
     // host layer
     std::map<const void *, gvl_static_entry> statics;
+    std::map<const void *, void *> packed_refs;  // device ASCII reference (pinned static) -> its packed copy
     std::vector<std::pair<void *, int64_t>> scratch;  // per-call device scratch (name-less pool)
     void *pinned;
     int64_t pinned_bytes;

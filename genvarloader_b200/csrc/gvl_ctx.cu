@@ -72,7 +72,19 @@ int ensure_merged(gvl_ctx *ctx, gvl_workspace &ws, int64_t n) {
     return GVL_OK;
 }
 
+int ensure_dir(gvl_ctx *ctx, gvl_workspace &ws, int64_t n) {
+    (void)ctx;
+    if (n <= ws.dir_cap) return GVL_OK;
+    GVL_CUDA(cudaDeviceSynchronize());
+    int64_t cap = n + n / 2 + 1024;
+    int rc;
+    if ((rc = regrow(ws.dir, cap))) return rc;
+    ws.dir_cap = cap;
+    return GVL_OK;
+}
+
 static void free_workspace(gvl_workspace &ws) {
+    cudaFree(ws.dir);
     cudaFree(ws.m_pos);
     cudaFree(ws.m_key);
     cudaFree(ws.m_off);
@@ -146,6 +158,7 @@ void gvl_ctx_destroy(gvl_ctx *ctx) {
     cudaFree(ctx->trk_desc);
     if (ctx->host_words) cudaFreeHost(ctx->host_words);
     for (auto &kv : ctx->statics) cudaFree(kv.second.dev);
+    for (auto &kv : ctx->packed_refs) cudaFree(kv.second);
     for (auto &s : ctx->scratch) cudaFree(s.first);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);

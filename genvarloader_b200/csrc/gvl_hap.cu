@@ -53,9 +53,34 @@ struct HapPlanParams {
     int64_t *out_offsets;
     int32_t *diffs;
     int32_t *row_len;
+    int32_t *dir;        // fixed-length plans: checkpoint directory (NULL otherwise)
+    int64_t dir_stride;  // entries per row = ceil(length / DIR_Q) + 1
 };
 
 constexpr int PLAN_WARPS = 4;
+
+// Checkpoint directory of a row, written by the NT threads that planned it once its records are in
+// global memory: dir[q] = number of records whose ALT starts before haplotype position q * DIR_Q.
+// The execute kernels read their tile's record range from it instead of searching the record list.
+template <int NT>
+__device__ __forceinline__ void write_dir(const HapPlanParams &P, int64_t k, int64_t rec_off, int64_t n_rec, int t) {
+    if (!P.dir) return;
+    if (NT == 32) __syncwarp(); else __syncthreads();  // the row's records are visible to the whole group
+    int32_t *__restrict__ d = P.dir + k * P.dir_stride;
+    const int64_t nq = P.dir_stride - 1;
+    if (n_rec == 0) {
+        for (int64_t q = t; q <= nq; q += NT) d[q] = 0;
+        return;
+    }
+    const int32_t *a = P.rec.a + rec_off;
+    for (int64_t i = t; i < n_rec; i += NT) {
+        const int64_t q_lo = i == 0 ? 0 : (int64_t)a[i - 1] / DIR_Q + 1;
+        const int64_t q_hi = imin64((int64_t)a[i] / DIR_Q, nq);
+        for (int64_t q = q_lo; q <= q_hi; q++) d[q] = (int32_t)i;
+        if (i == n_rec - 1)
+            for (int64_t q = q_hi + 1; q <= nq; q++) d[q] = (int32_t)n_rec;
+    }
+}
 
 // Serial (lock-step) plan of one row by ONE warp: the reference's loop, one variant per step.
 // Exact for any input order; used for rows whose variant list is not position-sorted and by the
@@ -226,6 +251,7 @@ __device__ void plan_row_serial(const HapPlanParams &P, const int64_t k, const i
             if (k == P.n_work - 1) P.out_offsets[P.n_work] = P.n_work * length;
         }
     }
+    write_dir<32>(P, k, rec_off, overflow ? 0 : n_emit, lane);
 }
 
 __global__ void __launch_bounds__(PLAN_WARPS * 32) hap_plan_serial_kernel(HapPlanParams P) {
@@ -307,11 +333,15 @@ struct HapExecParams {
     const RowPlan *rows;
     RecArrays rec;
     const uint8_t *ref;
+    const uint32_t *ref_packed;  // optional 4-bit codes (gvl_hap_oh.cuh)
     const uint8_t *alt;
     int64_t n_work;
     int64_t tiles_per_row;    // >0: fixed-length plan
     const int64_t *tile_off;  // ragged plan: first tile of each row
     int32_t tile_len;         // haplotype positions per CTA (multiple of EXEC_UNIT)
+    const int32_t *dir;       // fixed-length plans: checkpoint directory (write_dir), else NULL
+    int64_t dir_stride;
+    int64_t fixed_len;
     uint8_t *out;
     int32_t *annot_v;
     int32_t *annot_pos;
@@ -812,6 +842,10 @@ __global__ void __launch_bounds__(EXEC_THREADS, EXEC_MIN_CTAS) hap_exec_kernel(H
     }
 }
 
+}  // namespace gvl
+#include "gvl_hap_oh.cuh"
+namespace gvl {
+
 // standalone get_diffs_sparse (all four branches of src/genotypes/mod.rs:46-104)
 struct DiffParams {
     gvl_sparse_tables tab;
@@ -897,9 +931,16 @@ static int64_t exec_capacity(gvl_ctx *ctx, int mode) {
     return cap;
 }
 
-extern "C" {
-
-}  // extern "C"
+static int64_t exec_capacity_oh(gvl_ctx *ctx) {
+    static int64_t cache[8] = {};
+    if (ctx->device < 8 && cache[ctx->device]) return cache[ctx->device];
+    int sms = 148, per_sm = OH_MIN_CTAS;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hap_exec_oh_kernel, EXEC_THREADS, 0);
+    const int64_t cap = (int64_t)sms * (per_sm > 0 ? per_sm : 1);
+    if (ctx->device < 8) cache[ctx->device] = cap;
+    return cap;
+}
 
 // Merge of the svar2 two-channel source (gvl_svar2.cu); fills ctx->hap.m_* for n_work rows.
 int gvl_svar2_merge_launch(gvl_ctx *ctx, const gvl_svar2_channels *ch, int64_t batch, int64_t ploidy, int64_t max_merged,
@@ -955,6 +996,15 @@ static int hap_plan_impl(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_s
     P.out_offsets = out_offsets;
     P.diffs = diffs;
     P.row_len = ctx->hap.row_len;
+    P.dir = nullptr;
+    P.dir_stride = 0;
+    ctx->dir_stride = 0;
+    if (output_length >= 0) {
+        const int64_t stride = (output_length + DIR_Q - 1) / DIR_Q + 1;
+        if ((rc = ensure_dir(ctx, ctx->hap, n_work * stride))) return rc;
+        P.dir = ctx->hap.dir;
+        P.dir_stride = ctx->dir_stride = stride;
+    }
     static const bool force_serial = [] {
         const char *e = getenv("GVL_PLAN");
         return e && e[0] == 's';
@@ -1030,14 +1080,41 @@ int gvl_dev_hap_exec(gvl_ctx *ctx, const gvl_sparse_tables *tab, int mode, uint8
     P.rows = ctx->hap.rows;
     P.rec = ctx->hap.rec;
     P.ref = tab->ref;
+    P.ref_packed = tab->ref_packed;
+    P.dir = ctx->dir_stride > 0 ? ctx->hap.dir : nullptr;
+    P.dir_stride = ctx->dir_stride;
+    P.fixed_len = ctx->fixed_len;
     P.alt = tab->alt_alleles;
     P.n_work = ctx->n_work;
     P.out = out;
     P.annot_v = annot_v;
     P.annot_pos = annot_pos;
     P.pad_char = pad_char;
+    // one-hot over the packed reference (gvl_hap_oh.cuh) when the caller supplied it; GVL_EXEC=bytes forces the
+    // byte-oriented kernel (A/B measurements, parity tests of both)
+    static const bool force_bytes = [] {
+        const char *e = getenv("GVL_EXEC");
+        return e && e[0] == 'b';
+    }();
+    const bool packed = mode == GVL_MODE_ONEHOT && tab->ref_packed && !force_bytes && !((uintptr_t)out & 31) &&
+                        !((uintptr_t)tab->ref_packed & 15);
     int64_t grid;
-    if (ctx->fixed_len >= 0) {
+    if (ctx->fixed_len >= 0 && packed) {
+        // one wave of CTAs when it can be; whole 256-position groups for each of the 4 warps
+        static const int64_t tile_env = [] {
+            const char *e = getenv("GVL_OH_TILE");
+            return e ? (int64_t)atoll(e) : (int64_t)0;
+        }();
+        const int64_t q = 4 * OH_GROUP;
+        const int64_t tiles_target = imax64(1, exec_capacity_oh(ctx) / ctx->n_work);
+        int64_t tl = (ctx->fixed_len + tiles_target - 1) / tiles_target;
+        if (tile_env > 0) tl = tile_env;
+        tl = imax64(q, imin64((tl + q - 1) / q * q, OH_MAX_TILE));
+        P.tile_len = (int32_t)tl;
+        P.tiles_per_row = (ctx->fixed_len + P.tile_len - 1) / P.tile_len;
+        P.tile_off = nullptr;
+        grid = P.tiles_per_row * ctx->n_work;
+    } else if (ctx->fixed_len >= 0) {
         // pick the tile length so that the whole batch is ONE wave of CTAs when it can be
         const int64_t units_per_row = (ctx->fixed_len + EXEC_UNIT - 1) / EXEC_UNIT;
         const int64_t tiles_target = imax64(1, exec_capacity(ctx, mode) / ctx->n_work);
@@ -1067,11 +1144,41 @@ int gvl_dev_hap_exec(gvl_ctx *ctx, const gvl_sparse_tables *tab, int mode, uint8
         return fail(GVL_ERR_ARG, "gvl_dev_hap_exec: channels-first one-hot needs output_length %% 4 == 0");
     switch (mode) {
         case GVL_MODE_U8: hap_exec_kernel<GVL_MODE_U8><<<grid3, EXEC_THREADS, 0, st>>>(P); break;
-        case GVL_MODE_ONEHOT: hap_exec_kernel<GVL_MODE_ONEHOT><<<grid3, EXEC_THREADS, 0, st>>>(P); break;
+        case GVL_MODE_ONEHOT:
+            if (packed) hap_exec_oh_kernel<<<grid3, EXEC_THREADS, 0, st>>>(P);
+            else hap_exec_kernel<GVL_MODE_ONEHOT><<<grid3, EXEC_THREADS, 0, st>>>(P);
+            break;
         case GVL_MODE_ONEHOT_CF: hap_exec_kernel<GVL_MODE_ONEHOT_CF><<<grid3, EXEC_THREADS, 0, st>>>(P); break;
         case GVL_MODE_ANNOTATED: hap_exec_kernel<GVL_MODE_ANNOTATED><<<grid3, EXEC_THREADS, 0, st>>>(P); break;
         default: return fail(GVL_ERR_ARG, "gvl_dev_hap_exec: unknown mode %d", mode);
     }
+    GVL_LAUNCH_CHECK();
+    ctx->last_exec_kernel = packed ? 1 : 0;
+    return GVL_OK;
+}
+
+int gvl_debug_last_exec_kernel(gvl_ctx *ctx) { return ctx ? ctx->last_exec_kernel : -1; }
+
+#if GVL_TRACE
+// trace builds only (profiles/trace_exec.py): device buffer u64[n_ctas * 6] the next execute launches log into
+__attribute__((visibility("default"))) int gvl_debug_set_trace(void *dev_buf) {
+    unsigned long long *p = (unsigned long long *)dev_buf;
+    GVL_CUDA(cudaMemcpyToSymbol(g_trace, &p, sizeof(p)));
+    return GVL_OK;
+}
+#endif
+
+int64_t gvl_packed_reference_words(int64_t n_bases) { return (imax64(n_bases, 0) + 7) / 8 + 4; }  // + zeroed slack
+
+int gvl_dev_pack_reference(gvl_ctx *ctx, const uint8_t *ref, int64_t n_bases, uint32_t *ref_packed, gvl_stream stream) {
+    if (!ctx || !ref_packed || (!ref && n_bases > 0) || n_bases < 0)
+        return fail(GVL_ERR_ARG, "gvl_dev_pack_reference: bad argument");
+    if (((uintptr_t)ref & 15) || ((uintptr_t)ref_packed & 15))
+        return fail(GVL_ERR_ARG, "gvl_dev_pack_reference: buffers must be 16-byte aligned");
+    GVL_CUDA(cudaSetDevice(ctx->device));
+    const int64_t n_words = gvl_packed_reference_words(n_bases);
+    const unsigned grid = (unsigned)imax64(1, imin64((n_words + 255) / 256, 148 * 16));
+    pack_ref_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ref, n_bases, ref_packed, n_words);
     GVL_LAUNCH_CHECK();
     return GVL_OK;
 }

@@ -1,0 +1,410 @@
+// gvl_hap_oh.cuh -- execute kernel for the (L,4) one-hot output over the PACKED reference.
+//
+// The packed reference holds one 4-bit code per base (A=1, C=2, G=4, T=8, anything else 0; base r of the
+// concatenated reference is nibble r&7 of word r>>3, low nibble first).  It is built once per dataset from the
+// ASCII reference (pack_ref_kernel, gvl_dev_pack_reference) and makes the fused epilogue of
+// reconstruct_haplotypes_fused + seqpro.DNA.ohe (src/ffi/mod.rs:724-860, docs/source/index.md:108-119) cheap:
+//   * one lane owns 8 consecutive output positions: two aligned 32-bit loads + one funnel shift fetch their 8 codes
+//     whatever the indel shift of the row is;
+//   * reverse-complement of the 8 positions (src/reverse.rs:45-69) is ONE bit reversal (brev): reversing the nibble
+//     order reverses the positions, reversing the bits inside a nibble swaps A<->T and C<->G;
+//   * a 256-entry shared-memory table maps a byte (2 codes) to its 8 one-hot bytes: 4 lookups per lane;
+//   * the lane's 32 output bytes leave with one 256-bit store (STG.256): a warp writes 1 KiB per instruction.
+// Groups of 256 positions that are plain reference (the common case) take exactly that path; groups that contain
+// a variant, a pad or a tile edge classify every lane on its own, and only the lanes that straddle a record edge
+// rebuild their 8 codes piecewise (ALT bytes come from the ASCII allele buffer) before the common epilogue.
+//
+// Included by gvl_hap.cu (shares HapExecParams / find_rec with the byte-oriented kernel, which keeps serving the
+// u8, annotated and channels-first modes and callers without a packed reference).
+#pragma once
+
+namespace gvl {
+
+constexpr int OH_GROUP = 256;                                  // positions per warp step (8 per lane)
+constexpr int OH_MAX_TILE = EXEC_MAX_UNITS * EXEC_UNIT;        // 8192
+constexpr int OH_MAX_GROUPS = OH_MAX_TILE / OH_GROUP + 2;      // groups a pass can touch (+ misaligned edges)
+constexpr int OH_MIN_CTAS = 8;
+constexpr int OH_UNROLL = 4;                                   // groups per warp whose loads are issued together
+
+struct OhRecs {
+    int32_t a[REC_CAP + 1];   // ALT start (haplotype coordinate); a[m] sentinel
+    int32_t e[REC_CAP];       // ALT end = start of the following reference span
+    int32_t resume[REC_CAP];  // reference position at e[]
+    int64_t src[REC_CAP];     // ALT source (offset into alt_alleles), ALT_PAD for the leading pad
+};
+
+// 4-bit one-hot code of an ASCII base
+__host__ __device__ __forceinline__ uint32_t nib_code(uint32_t b) {
+    return (b == 'A' ? 1u : 0u) | (b == 'C' ? 2u : 0u) | (b == 'G' ? 4u : 0u) | (b == 'T' ? 8u : 0u);
+}
+
+__global__ void __launch_bounds__(256) pack_ref_kernel(const uint8_t *__restrict__ ref, int64_t n_bases,
+                                                       uint32_t *__restrict__ out, int64_t n_words) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
+        const int64_t b0 = w * 8;
+        uint32_t v = 0;
+        if (b0 + 8 <= n_bases) {
+            const uint2 x = *reinterpret_cast<const uint2 *>(ref + b0);  // (ref is 16-byte aligned)
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                v |= nib_code((x.x >> (8 * t)) & 0xffu) << (4 * t);
+                v |= nib_code((x.y >> (8 * t)) & 0xffu) << (4 * (t + 4));
+            }
+        } else {
+            for (int t = 0; t < 8; t++)
+                if (b0 + t < n_bases) v |= nib_code(ref[b0 + t]) << (4 * t);
+        }
+        out[w] = v;
+    }
+}
+
+__device__ __forceinline__ uint2 lds_u64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+
+__device__ __forceinline__ void stg_256(void *p, const uint2 &o0, const uint2 &o1, const uint2 &o2, const uint2 &o3) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(o0.x), "r"(o0.y), "r"(o1.x),
+                 "r"(o1.y), "r"(o2.x), "r"(o2.y), "r"(o3.x), "r"(o3.y)
+                 : "memory");
+}
+
+// 8 codes starting at absolute base index n of the packed reference (nibble t = base n + t)
+__device__ __forceinline__ uint32_t load_codes(const uint32_t *__restrict__ nib, int64_t n) {
+    const uint32_t *w = nib + (n >> 3);
+    return __funnelshift_r(__ldg(w), __ldg(w + 1), (uint32_t)n << 2);
+}
+
+// Codes of the haplotype positions [ps, pe) of a unit that starts at p_lo (nibble t = position p_lo + t), built
+// piece by piece from the staged records; `il` = last staged record with a <= ps.  Semantics of the generic
+// path of hap_exec_kernel (ALT bytes, leading pad, pure-deletion anchors, trailing pad past the contig end).
+__device__ __noinline__ uint32_t oh_slow_unit(const OhRecs &S, const uint8_t *__restrict__ alt,
+                                              const uint8_t *__restrict__ ref, const uint32_t *__restrict__ nib,
+                                              int64_t ref_base, int32_t contig_len, uint32_t padnib, int il,
+                                              int32_t p_lo, int32_t ps, int32_t pe) {
+    uint32_t v = 0;
+    int32_t p = ps;
+    while (p < pe) {
+        while (S.a[il + 1] <= p) il++;
+        const int32_t e_i = S.e[il];
+        if (p < e_i) {
+            const int64_t src = S.src[il];
+            const int32_t a_i = S.a[il];
+            const int32_t q = min(e_i, pe);
+            for (; p < q; p++) {
+                uint32_t c;
+                if (src == ALT_PAD) {
+                    c = padnib & 15u;  // leading pad (src/reconstruct/mod.rs:75-80)
+                } else {
+                    // (src < 0: pure-deletion anchor of the svar2 source, taken from the reference)
+                    c = nib_code(src >= 0 ? alt[src + (p - a_i)] : ref[~src + (p - a_i)]);
+                }
+                v |= c << (4 * (p - p_lo));
+            }
+        } else {
+            const int32_t q = min(S.a[il + 1], pe);
+            const int32_t cnt = q - p;  // 1..8 positions of reference
+            const int64_t rpos = (int64_t)S.resume[il] + (p - e_i);
+            const int32_t valid = (int32_t)imax64(0, imin64((int64_t)contig_len - rpos, cnt));
+            uint32_t x = padnib;  // trailing pad past the contig end (:248-253)
+            if (valid > 0) {
+                const uint32_t keep = valid >= 8 ? 0xffffffffu : ((1u << (4 * valid)) - 1u);
+                x = (load_codes(nib, ref_base + rpos) & keep) | (padnib & ~keep);
+            }
+            const uint32_t cm = cnt >= 8 ? 0xffffffffu : ((1u << (4 * cnt)) - 1u);
+            v |= (x & cm) << (4 * (p - p_lo));
+            p = q;
+        }
+    }
+    return v;
+}
+
+#ifndef GVL_TRACE
+#define GVL_TRACE 0  // 1: every CTA of hap_exec_oh_kernel logs 4 timestamps (profiles/trace_exec.py); never the shipped build
+#endif
+#if GVL_TRACE
+__device__ unsigned long long *g_trace = nullptr;  // [n_ctas][6]: smid, t0..t3 (globaltimer ns), clock64 at t0
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define GVL_TR(slot)                                                                                       \
+    do {                                                                                                   \
+        if (g_trace && threadIdx.x == 0) g_trace[tr_cta * 6 + (slot)] = gtime();                            \
+    } while (0)
+#else
+#define GVL_TR(slot) do { } while (0)
+#endif
+
+__global__ void __launch_bounds__(EXEC_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(HapExecParams P) {
+#if GVL_TRACE
+    const unsigned long long tr_cta = blockIdx.x + (unsigned long long)gridDim.x * (blockIdx.y + (unsigned long long)gridDim.y * blockIdx.z);
+    if (g_trace && threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        g_trace[tr_cta * 6 + 0] = smid;
+        g_trace[tr_cta * 6 + 5] = clock64();
+    }
+    GVL_TR(1);
+#endif
+    __shared__ OhRecs S;
+    __shared__ __align__(16) uint2 s_lut[256];         // byte (2 codes) -> 8 one-hot bytes
+    __shared__ __align__(8) uint2 s_grp[OH_MAX_GROUPS];  // per group: {reference delta, idx | cnt << 8 | plain << 31}
+    __shared__ int64_t s_lo, s_hi;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // ---- tile -> (row, tile-in-row) ----
+    int64_t row, tile;
+    if (P.tiles_per_row > 0) {
+        tile = blockIdx.x;
+        row = (int64_t)blockIdx.y + (int64_t)blockIdx.z * 65535;
+        if (row >= P.n_work) return;
+    } else {
+        int64_t b = blockIdx.x;
+        if (b >= P.tile_off[P.n_work]) return;
+        int64_t lo = 0, hi = P.n_work;  // last row with tile_off[row] <= b
+        while (hi - lo > 1) {
+            int64_t mid = (lo + hi) >> 1;
+            if (P.tile_off[mid] <= b) lo = mid; else hi = mid;
+        }
+        row = lo;
+        tile = b - P.tile_off[row];
+    }
+    // ---- records of this tile: r = last with a < h0 (or -1, the virtual leading-pad record), r_hi = first with
+    //      a >= h1.  Fixed-length plans read both from the plan's checkpoint directory -- the two loads do not
+    //      depend on the row header, so the prologue is ONE round trip; ragged plans count (sorted array). ----
+    int32_t d_lo = 0, d_hi = 0;
+    if (P.dir) {
+        const int64_t h0d = tile * (int64_t)P.tile_len;
+        const int64_t h1d = imin64(h0d + P.tile_len, P.fixed_len);
+        const int32_t *__restrict__ d = P.dir + row * P.dir_stride;
+        d_lo = __ldg(d + h0d / DIR_Q);
+        d_hi = __ldg(d + (h1d + DIR_Q - 1) / DIR_Q);  // (h1 is a multiple of DIR_Q or the row end = last entry)
+    }
+    const RowPlan rp = P.rows[row];
+    const int32_t L = rp.length;
+    const int64_t h0_64 = tile * (int64_t)P.tile_len;  // tiles are cut in HAPLOTYPE coordinates
+    if (h0_64 >= L) return;
+    const int32_t h0 = (int32_t)h0_64;
+    const int32_t h1 = (int32_t)imin64(h0_64 + P.tile_len, L);
+    const bool rc = rp.rc != 0;
+
+    // ---- warm L2 with the packed reference window of this tile while the records travel: the window starts near
+    //      ref0 + (h0 - lead_pad) (exact up to the indels before h0); +-1 Ki bases of slack, 128-byte lines ----
+    if (warp == 1) {
+        const int64_t est = (int64_t)rp.ref0 + (h0 - rp.lead_pad);
+        const int64_t b_lo = imax64(est - 1024, 0), b_hi = imin64(est + (h1 - h0) + 1024, rp.contig_len);
+        const char *base = reinterpret_cast<const char *>(P.ref_packed);
+        for (int64_t line = ((rp.ref_base + b_lo) >> 8) + lane; line <= ((rp.ref_base + b_hi) >> 8); line += 32)
+            if (b_hi > b_lo) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (line << 7)));
+    }
+
+    // spread(n): byte c = bit c of the 4-bit code n   (n * 0x204081 puts bit c at bit 8c, no carries)
+    for (int i = tid; i < 256; i += EXEC_THREADS)
+        s_lut[i] = make_uint2(((i & 15) * 0x204081u) & 0x01010101u, ((i >> 4) * 0x204081u) & 0x01010101u);
+
+    const int32_t *__restrict__ ra = P.rec.a + rp.rec_off;
+    if (!P.dir && warp == 0) {
+        int64_t r_lo, r_hi0;
+        if (rp.n_rec <= 2048) {
+            int c0 = 0, c1 = 0;
+            for (int i0 = 0; i0 < rp.n_rec; i0 += 256) {  // 8 independent loads per lane and trip
+                int32_t a[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int i = i0 + 32 * u + lane;
+                    a[u] = i < rp.n_rec ? ra[i] : INT32_MAX;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    c0 += (a[u] < h0);
+                    c1 += (a[u] < h1);
+                }
+            }
+            r_lo = (int64_t)__reduce_add_sync(0xffffffffu, c0) - 1;
+            r_hi0 = __reduce_add_sync(0xffffffffu, c1);
+        } else {
+            r_lo = h0 > 0 ? warp_upper_le(ra, 0, rp.n_rec, h0 - 1) : -1;
+            r_hi0 = warp_upper_le(ra, imax64(r_lo, 0), rp.n_rec, h1 - 1) + 1;
+        }
+        if (lane == 0) {
+            s_lo = r_lo;
+            s_hi = r_hi0;
+        }
+    }
+    if (P.dir && tid == 0) {
+        s_lo = (int64_t)d_lo - 1;
+        s_hi = rp.n_rec ? d_hi : 0;
+    }
+    __syncthreads();
+    GVL_TR(2);
+    const int64_t r_hi = s_hi;
+    int64_t r = s_lo;
+    int32_t cur = h0;
+    uint8_t *__restrict__ out_row = P.out + 4 * rp.out_off;  // position j of the row lives at out_row[4*j]
+    const uint32_t lut_a = smem_u32(s_lut);
+    const uint32_t padnib = nib_code(P.pad_char) * 0x11111111u;
+    const int32_t lane_off = 8 * (rc ? 31 - lane : lane);  // haplotype offset of the lane's unit inside its group
+    // (reference base index + 2 * table address): (x >> 1) & ~3 is then the byte address of the word that holds
+    // base x, and the low 3 bits still count nibbles (the table is 16-byte aligned)
+    const int64_t nb2 = rp.ref_base + lane_off + 2 * (int64_t)reinterpret_cast<uintptr_t>(P.ref_packed);
+
+    // common epilogue of a full unit: 8 codes (output order) -> 32 one-hot bytes, one 256-bit store
+    auto emit8 = [&](uint8_t *dst, uint32_t v) {
+        const uint2 o0 = lds_u64(lut_a + ((v << 3) & 0x7f8u));
+        const uint2 o1 = lds_u64(lut_a + ((v >> 5) & 0x7f8u));
+        const uint2 o2 = lds_u64(lut_a + ((v >> 13) & 0x7f8u));
+        const uint2 o3 = lds_u64(lut_a + ((v >> 21) & 0x7f8u));
+        stg_256(dst, o0, o1, o2, o3);
+    };
+
+    while (cur < h1) {
+        // ---- stage entry 0 (carry) + up to REC_CAP-1 following records ----
+        const int m_new = (int)imin64(REC_CAP - 1, r_hi - (r + 1));
+        const int m = m_new + 1;
+        const int32_t seg_end = (r + 1 + m_new < r_hi) ? ra[r + 1 + m_new] : h1;
+        __syncthreads();  // previous pass finished reading S
+        for (int i = tid; i < m; i += EXEC_THREADS) {
+            const int64_t idx = r + i;
+            if (idx < 0) {  // virtual record: leading pad, then reference from ref0
+                S.a[0] = 0;
+                S.e[0] = rp.lead_pad;
+                S.resume[0] = rp.ref0;
+                S.src[0] = ALT_PAD;
+            } else {
+                const int64_t g = rp.rec_off + idx;
+                const int32_t a = P.rec.a[g];
+                S.a[i] = a;
+                S.e[i] = a + P.rec.n[g];
+                S.resume[i] = P.rec.resume[g];
+                S.src[i] = P.rec.src[g];
+            }
+        }
+        if (tid == 0) S.a[m] = INT32_MAX;
+        __syncthreads();
+
+        // ---- output range of the pass in units of 8 positions aligned on the GLOBAL flat index (32-byte
+        //      aligned stores); a group is 32 units (one per lane), warp w owns groups w, w+4, ... ----
+        const int32_t jo_lo = rc ? L - seg_end : cur;
+        const int32_t jo_hi = rc ? L - cur : seg_end;
+        const int64_t g0 = (rp.out_off + jo_lo) & ~(int64_t)7;
+        const int32_t j0 = (int32_t)(g0 - rp.out_off);  // row-relative position of unit 0 (may be < jo_lo)
+        const int32_t n_groups = (jo_hi - j0 + OH_GROUP - 1) / OH_GROUP;
+
+        // ---- group table: one thread per group ----
+        if (tid < n_groups) {
+            const int32_t jg = j0 + OH_GROUP * tid;
+            const bool full = jg >= jo_lo && jg + OH_GROUP <= jo_hi;
+            const int32_t pg = rc ? (L - OH_GROUP - jg) : jg;  // lowest haplotype position of the group
+            int idx = 0;
+            {
+                const int32_t ps = max(pg, cur);
+                int hi = m;
+                while (hi - idx > 1) {
+                    const int mid = (idx + hi) >> 1;
+                    if (S.a[mid] <= ps) idx = mid; else hi = mid;
+                }
+            }
+            const int32_t phi = min(pg + OH_GROUP, seg_end);
+            int cnt = 0;
+            while (S.a[idx + 1 + cnt] < phi) cnt++;
+            const int32_t e_i = S.e[idx];
+            const int32_t dl = S.resume[idx] - e_i;
+            const bool plain = full && cnt == 0 && pg >= e_i && (int64_t)pg + dl + OH_GROUP <= rp.contig_len;
+            s_grp[tid] = make_uint2((uint32_t)dl, (uint32_t)idx | ((uint32_t)cnt << 8) | (plain ? 0x80000000u : 0u));
+        }
+        __syncthreads();
+
+        GVL_TR(3);
+        uint8_t *const out_lane = out_row + 4 * ((int64_t)j0 + 8 * lane);
+        const int32_t pg0 = rc ? (L - OH_GROUP - j0) : j0;  // lowest haplotype position of group 0
+        const int32_t pg_step = rc ? -OH_GROUP : OH_GROUP;
+
+        for (int gb = warp; gb < n_groups; gb += OH_UNROLL * (EXEC_THREADS / 32)) {
+            // ---- phase 1: ALL loads of the warp's groups first (2 per group and lane), so that no load queues up
+            //      behind the store stream.  Plain groups share one delta; in a group with variants / pads / edges
+            //      every lane classifies its own unit and loads if its 8 positions are one reference run. ----
+            uint32_t w0[OH_UNROLL], w1[OH_UNROLL], sh[OH_UNROLL];
+            unsigned ldmask = 0, mixmask = 0;  // ldmask is per LANE, mixmask per warp
+#pragma unroll
+            for (int u = 0; u < OH_UNROLL; u++) {
+                const int g = gb + u * (EXEC_THREADS / 32);
+                if (g < n_groups) {
+                    const uint2 meta = s_grp[g];
+                    int32_t dl = (int32_t)meta.x;
+                    bool ok = true;
+                    if (!(meta.y & 0x80000000u)) {
+                        mixmask |= 1u << u;
+                        const int idx = meta.y & 0xff, cnt = (meta.y >> 8) & 0xff;
+                        const int32_t j = j0 + OH_GROUP * g + 8 * lane;  // first output position of the lane's unit
+                        const int32_t p_lo = pg0 + pg_step * g + lane_off;
+                        const int32_t ps = max(p_lo, cur);
+                        int il = idx;
+                        for (int q = 1; q <= cnt; q++) il += (S.a[idx + q] <= ps);
+                        const int32_t e_i = S.e[il];
+                        dl = S.resume[il] - e_i;
+                        ok = j >= jo_lo && j + 8 <= jo_hi && p_lo >= e_i && p_lo + 8 <= S.a[il + 1] &&
+                             (int64_t)p_lo + dl + 8 <= rp.contig_len;
+                    }
+                    if (ok) {
+                        ldmask |= 1u << u;
+                        const int64_t x = nb2 + (int32_t)(pg0 + pg_step * g + dl);
+                        const uint32_t *w = reinterpret_cast<const uint32_t *>((uintptr_t)(x >> 1) & ~(uintptr_t)3);
+                        w0[u] = __ldg(w);
+                        w1[u] = __ldg(w + 1);
+                        sh[u] = (uint32_t)x << 2;
+                    }
+                }
+            }
+            // ---- phase 2: encode + store every unit that is one reference run ----
+#pragma unroll
+            for (int u = 0; u < OH_UNROLL; u++) {
+                if (ldmask & (1u << u)) {
+                    const int g = gb + u * (EXEC_THREADS / 32);
+                    uint32_t v = __funnelshift_r(w0[u], w1[u], sh[u]);  // nibble t = haplotype position p_lo + t
+                    if (rc) v = __brev(v);                               // nibble t = output position j + t, complemented
+                    emit8(out_lane + (int64_t)g * (4 * OH_GROUP), v);
+                }
+            }
+            // ---- phase 3: the remaining units of the mixed groups are rebuilt piece by piece ----
+            while (mixmask) {
+                const int u = __ffs(mixmask) - 1;
+                mixmask &= mixmask - 1;
+                if (ldmask & (1u << u)) continue;
+                const int g = gb + u * (EXEC_THREADS / 32);
+                const int32_t j = j0 + OH_GROUP * g + 8 * lane;
+                if (!(j + 8 > jo_lo && j < jo_hi)) continue;  // unit outside the pass
+                const uint2 meta = s_grp[g];
+                const int idx = meta.y & 0xff, cnt = (meta.y >> 8) & 0xff;
+                const int32_t p_lo = pg0 + pg_step * g + lane_off;
+                const int32_t ps = max(p_lo, cur), pe = min(p_lo + 8, seg_end);
+                int il = idx;
+                for (int q = 1; q <= cnt; q++) il += (S.a[idx + q] <= ps);
+                uint32_t v = oh_slow_unit(S, P.alt, P.ref, P.ref_packed, rp.ref_base, rp.contig_len, padnib, il, p_lo, ps, pe);
+                if (rc) v = __brev(v);
+                uint8_t *dst = out_lane + (int64_t)g * (4 * OH_GROUP);
+                if (j >= jo_lo && j + 8 <= jo_hi) {
+                    emit8(dst, v);
+                } else {  // unit cut by a pass / tile / row boundary: position-wise stores
+#pragma unroll 1
+                    for (int q = 0; q < 8; q++) {
+                        const int32_t jj = j + q;
+                        if (jj >= jo_lo && jj < jo_hi)
+                            *reinterpret_cast<uint32_t *>(dst + 4 * q) = (((v >> (4 * q)) & 15u) * 0x204081u) & 0x01010101u;
+                    }
+                }
+            }
+        }
+        cur = seg_end;
+        r += m_new;
+    }
+#if GVL_TRACE
+    __syncthreads();
+    GVL_TR(4);
+#endif
+}
+
+}  // namespace gvl

@@ -49,6 +49,36 @@ static int static_dev(gvl_ctx *ctx, const void *host, int64_t bytes, size_t slot
     return GVL_OK;
 }
 
+// packed (4-bit) copy of a PINNED reference, built on first use and kept until the reference is unpinned;
+// references uploaded per call keep the byte-oriented kernel (packing would cost more than it saves)
+static int packed_ref(gvl_ctx *ctx, const void *host_ref, const uint8_t *dev_ref, int64_t n_bases,
+                      const uint32_t **out) {
+    *out = nullptr;
+    auto st = ctx->statics.find(host_ref);
+    if (st == ctx->statics.end() || st->second.dev != (void *)dev_ref) return GVL_OK;
+    auto it = ctx->packed_refs.find(dev_ref);
+    if (it == ctx->packed_refs.end()) {
+        void *d = nullptr;
+        GVL_CUDA(cudaMalloc(&d, sizeof(uint32_t) * (size_t)gvl_packed_reference_words(n_bases)));
+        int rc = gvl_dev_pack_reference(ctx, dev_ref, n_bases, (uint32_t *)d, ctx->own_stream);
+        if (rc) {
+            cudaFree(d);
+            return rc;
+        }
+        it = ctx->packed_refs.emplace(dev_ref, d).first;
+    }
+    *out = (const uint32_t *)it->second;
+    return GVL_OK;
+}
+
+static void drop_packed(gvl_ctx *ctx, const void *dev_ref) {
+    auto it = ctx->packed_refs.find(dev_ref);
+    if (it != ctx->packed_refs.end()) {
+        cudaFree(it->second);
+        ctx->packed_refs.erase(it);
+    }
+}
+
 static int scratch(gvl_ctx *ctx, size_t slot, int64_t bytes, void **dev) {
     if (ctx->scratch.size() <= slot) ctx->scratch.resize(slot + 1, {nullptr, 0});
     auto &s = ctx->scratch[slot];
@@ -141,6 +171,7 @@ int gvl_pin_static(gvl_ctx *ctx, const void *host_ptr, int64_t bytes) {
     auto it = ctx->statics.find(host_ptr);
     if (it != ctx->statics.end()) {  // refresh
         GVL_CUDA(cudaDeviceSynchronize());
+        drop_packed(ctx, it->second.dev);
         cudaFree(it->second.dev);
         ctx->statics.erase(it);
     }
@@ -153,6 +184,7 @@ int gvl_unpin_static(gvl_ctx *ctx, const void *host_ptr) {
     if (it == ctx->statics.end()) return GVL_OK;
     GVL_CUDA(cudaSetDevice(ctx->device));
     GVL_CUDA(cudaDeviceSynchronize());
+    drop_packed(ctx, it->second.dev);
     cudaFree(it->second.dev);
     ctx->statics.erase(it);
     return GVL_OK;
@@ -188,6 +220,7 @@ static int resolve_tables(gvl_ctx *ctx, const int64_t *geno_offsets, int64_t n_g
         if ((rc = static_dev(ctx, ref_, ref_offsets[n_contigs], 15, &d))) return rc;
         t->ref = (const uint8_t *)d;
         t->n_contigs = n_contigs;
+        if ((rc = packed_ref(ctx, ref_, t->ref, ref_offsets[n_contigs], &t->ref_packed))) return rc;
     }
     return GVL_OK;
 }
@@ -276,6 +309,7 @@ int gvl_reconstruct_haplotypes_from_svar2_begin(
     t.ref_offsets = (const int64_t *)d;
     if ((rc = static_dev(ctx, ref_, ref_offsets[n_contigs], 15, &d))) return rc;
     t.ref = (const uint8_t *)d;
+    if ((rc = packed_ref(ctx, ref_, t.ref, ref_offsets[n_contigs], &t.ref_packed))) return rc;
     t.n_contigs = n_contigs;
     gvl_svar2_channels ch;
     if ((rc = static_dev(ctx, dense_pos, sizeof(int32_t) * n_dense, 16, &d))) return rc;

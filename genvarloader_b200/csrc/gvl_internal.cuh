@@ -9,6 +9,7 @@ void count_launch(int n = 1);
 int ensure_rows(gvl_ctx *ctx, gvl_workspace &ws, int64_t n_work);
 int ensure_records(gvl_ctx *ctx, gvl_workspace &ws, int64_t n_rec);
 int ensure_merged(gvl_ctx *ctx, gvl_workspace &ws, int64_t n);
+int ensure_dir(gvl_ctx *ctx, gvl_workspace &ws, int64_t n);
 
 #define GVL_CUDA(expr)                                                                                  \
     do {                                                                                                \

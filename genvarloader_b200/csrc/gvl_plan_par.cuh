@@ -406,5 +406,6 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) hap_plan_par_kernel(HapPl
             if (k == P.n_work - 1) P.out_offsets[P.n_work] = P.n_work * length;
         }
     }
+    write_dir<NT>(P, k, rec_off, overflow ? 0 : n_emit, t);
 }
 

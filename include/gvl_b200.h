@@ -82,7 +82,17 @@ typedef struct {
     const int64_t *geno_starts;  /* i64[n_geno]  row 0 of the (2,n) offsets    */
     const int64_t *geno_stops;   /* i64[n_geno]  row 1                         */
     int64_t n_geno;
+    /* Optional (NULL = absent): the reference re-encoded by gvl_dev_pack_reference, one 4-bit one-hot code per
+     * base.  When present, GVL_MODE_ONEHOT executes over it (8 positions per lane, 256-bit stores); results are
+     * identical with and without it. */
+    const uint32_t *ref_packed;  /* u32[gvl_packed_reference_words(ref_offsets[n_contigs])], 16-byte aligned */
 } gvl_sparse_tables;
+
+/* Packed form of the reference for the one-hot execute path: base r of the concatenated reference is nibble r&7
+ * (low nibble first) of word r>>3, code A=1 C=2 G=4 T=8, any other byte 0.  Built once per dataset replica on the
+ * device (a static-table transform like the upload itself; the reference keeps ASCII only, _reference.py:53-120). */
+int64_t gvl_packed_reference_words(int64_t n_bases);
+int gvl_dev_pack_reference(gvl_ctx *ctx, const uint8_t *ref, int64_t n_bases, uint32_t *ref_packed, gvl_stream stream);
 
 /* Per-track interval SoA (python/genvarloader/_dataset/_tracks.py:327-339). */
 typedef struct {
@@ -288,6 +298,9 @@ int gvl_intervals_to_tracks(gvl_ctx *ctx, const int64_t *offset_idxs, const int3
 /* _debug_xorshift64 / _debug_hash4, src/ffi/mod.rs:2824-2834 (evaluated on the device). */
 int gvl_debug_hash4(gvl_ctx *ctx, uint64_t a, uint64_t b, uint64_t c, uint64_t d, uint64_t *out);
 int gvl_debug_xorshift64(gvl_ctx *ctx, uint64_t x, uint64_t *out);
+/* Which execute kernel the last gvl_dev_hap_exec of this context launched: 0 byte-oriented, 1 packed one-hot
+ * (tests assert that the intended kernel ran). */
+int gvl_debug_last_exec_kernel(gvl_ctx *ctx);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -67,19 +67,22 @@ class Engine:
             self.geno_stops = _dev(self.geno_offsets_host[1], np.int64, self.device)
         self.n_contigs = int(np.asarray(ref_offsets).size - 1)
         # 4-bit-per-base copy of the reference for the one-hot execute kernel (gvl_dev_pack_reference)
-        self.ref_packed = None
+        self.ref_packed = self.alt_packed = None
         if pack_reference:
-            n_bases = int(np.asarray(reference).size)
-            lib.gvl_packed_reference_words.restype = c_i64
-            n_words = int(lib.gvl_packed_reference_words(c_i64(n_bases)))
-            with torch.cuda.device(self.device):
-                self.ref_packed = torch.empty(n_words, dtype=torch.int32, device=self.device)
-                check(lib.gvl_dev_pack_reference(self.ctx.handle, ptr(self.ref), c_i64(n_bases), ptr(self.ref_packed),
-                                                 _stream()))
+            def pack(t: torch.Tensor, n_bases: int) -> torch.Tensor:
+                n_words = int(lib.gvl_packed_reference_words(c_i64(n_bases)))
+                with torch.cuda.device(self.device):
+                    out = torch.empty(n_words, dtype=torch.int32, device=self.device)
+                    check(lib.gvl_dev_pack_reference(self.ctx.handle, ptr(t), c_i64(n_bases), ptr(out), _stream()))
+                return out
+
+            self.ref_packed = pack(self.ref, int(np.asarray(reference).size))
+            self.alt_packed = pack(self.alt_alleles, int(np.asarray(alt_alleles).size))
         self.tab = SparseTables(
             ptr(self.ref), ptr(self.ref_offsets), self.n_contigs, ptr(self.v_starts), ptr(self.ilens),
             ptr(self.alt_alleles), ptr(self.alt_offsets), int(self.v_starts.numel()), ptr(self.geno_v_idxs),
-            ptr(self.geno_starts), ptr(self.geno_stops), int(self.geno_starts.numel()), ptr(self.ref_packed))
+            ptr(self.geno_starts), ptr(self.geno_stops), int(self.geno_starts.numel()), ptr(self.ref_packed),
+            ptr(self.alt_packed))
         self.tracks: dict[str, tuple] = {}
         self._n_work = 0
         self._fixed = -1

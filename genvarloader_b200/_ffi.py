@@ -35,7 +35,7 @@ class SparseTables(C.Structure):
         ("ref", c_vp), ("ref_offsets", c_vp), ("n_contigs", c_i64),
         ("v_starts", c_vp), ("ilens", c_vp), ("alt_alleles", c_vp), ("alt_offsets", c_vp), ("n_variants", c_i64),
         ("geno_v_idxs", c_vp), ("geno_starts", c_vp), ("geno_stops", c_vp), ("n_geno", c_i64),
-        ("ref_packed", c_vp),
+        ("ref_packed", c_vp), ("alt_packed", c_vp),
     ]
 
 

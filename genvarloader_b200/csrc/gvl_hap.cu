@@ -334,6 +334,7 @@ struct HapExecParams {
     RecArrays rec;
     const uint8_t *ref;
     const uint32_t *ref_packed;  // optional 4-bit codes (gvl_hap_oh.cuh)
+    const uint32_t *alt_packed;  // optional 4-bit codes of alt_alleles
     const uint8_t *alt;
     int64_t n_work;
     int64_t tiles_per_row;    // >0: fixed-length plan
@@ -1081,6 +1082,7 @@ int gvl_dev_hap_exec(gvl_ctx *ctx, const gvl_sparse_tables *tab, int mode, uint8
     P.rec = ctx->hap.rec;
     P.ref = tab->ref;
     P.ref_packed = tab->ref_packed;
+    P.alt_packed = ((uintptr_t)tab->alt_packed & 15) ? nullptr : tab->alt_packed;
     P.dir = ctx->dir_stride > 0 ? ctx->hap.dir : nullptr;
     P.dir_stride = ctx->dir_stride;
     P.fixed_len = ctx->fixed_len;

@@ -27,7 +27,7 @@ constexpr int OH_MIN_CTAS = 8;
 constexpr int OH_UNROLL = 4;                                   // groups per warp whose loads are issued together
 
 struct OhRecs {
-    int32_t a[REC_CAP + 1];   // ALT start (haplotype coordinate); a[m] sentinel
+    int32_t a[REC_CAP + 2];   // ALT start (haplotype coordinate); a[m], a[m+1] sentinels
     int32_t e[REC_CAP];       // ALT end = start of the following reference span
     int32_t resume[REC_CAP];  // reference position at e[]
     int64_t src[REC_CAP];     // ALT source (offset into alt_alleles), ALT_PAD for the leading pad
@@ -65,7 +65,13 @@ __device__ __forceinline__ uint2 lds_u64(uint32_t addr) {
     return v;
 }
 
+#ifndef GVL_EXP
+#define GVL_EXP 0  // timing experiments only (results are WRONG): 1 no stores, 2 every group plain, 4 no table lookups
+#endif
 __device__ __forceinline__ void stg_256(void *p, const uint2 &o0, const uint2 &o1, const uint2 &o2, const uint2 &o3) {
+#if GVL_EXP & 1
+    if (o0.x != 0x12345678u) return;
+#endif
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(o0.x), "r"(o0.y), "r"(o1.x),
                  "r"(o1.y), "r"(o2.x), "r"(o2.y), "r"(o3.x), "r"(o3.y)
                  : "memory");
@@ -121,6 +127,56 @@ __device__ __noinline__ uint32_t oh_slow_unit(const OhRecs &S, const uint8_t *__
     return v;
 }
 
+
+// ---- one unit (8 haplotype positions from p_lo) of a group that is not plain reference ----
+enum { U_SKIP = 0, U_FAST = 1, U_PATCH = 2, U_SLOW = 3 };
+
+// Shape of a PATCH unit: [0, x1) reference with delta dlA | [x1, x2) ALT codes starting at base index `alt` of the
+// packed allele buffer (ALT_PAD: pad codes; < 0: ~index into the packed reference, the svar2 pure-deletion
+// anchor) | [x2, 8) reference with delta dlB.  x1 == 8: reference only (a unit that merely runs past the contig end).
+struct UnitShape {
+    int il, x1, x2;
+    int32_t dlA, dlB;
+    int64_t alt;
+};
+
+__device__ __forceinline__ uint32_t nib_mask(int k) { return k >= 8 ? 0xffffffffu : ((1u << (4 * k)) - 1u); }
+
+__device__ __forceinline__ int oh_classify(const OhRecs &S, int idx, int cnt, int32_t p_lo, int32_t ps, bool inside,
+                                           bool anyin, int64_t ref_base, int32_t contig_len, bool alt_packed,
+                                           UnitShape &U) {
+    if (!anyin) return U_SKIP;
+    int il = idx;
+    for (int q = 1; q <= cnt; q++) il += (S.a[idx + q] <= ps);
+    U.il = il;
+    if (!inside) return U_SLOW;
+    const int32_t end = p_lo + 8, e_i = S.e[il], a1 = S.a[il + 1];
+    U.dlA = S.resume[il] - e_i;
+    if (p_lo >= e_i) {
+        if (a1 >= end) {  // one reference run
+            U.x1 = U.x2 = 8;
+            return ((int64_t)p_lo + U.dlA + 8 <= contig_len) ? U_FAST : U_PATCH;
+        }
+        if (S.a[il + 2] < end) return U_SLOW;  // two records start inside the unit
+        const int32_t e1 = S.e[il + 1];
+        U.x1 = a1 - p_lo;
+        U.x2 = min(e1, end) - p_lo;
+        U.dlB = S.resume[il + 1] - e1;
+        U.alt = S.src[il + 1];
+        if (ref_base + p_lo + U.dlB < 0) return U_SLOW;  // (the 8-code window would start before the buffer)
+    } else {  // the unit starts inside the ALT of record il
+        if (a1 < end) return U_SLOW;
+        U.x1 = 0;
+        U.x2 = min(e_i, end) - p_lo;
+        U.dlB = U.dlA;
+        const int64_t src = S.src[il], off = p_lo - S.a[il];
+        U.alt = src == ALT_PAD ? ALT_PAD : (src >= 0 ? src + off : ~(~src + off));
+        if (ref_base + p_lo + U.dlA < 0) return U_SLOW;
+    }
+    if (!alt_packed && U.alt >= 0) return U_SLOW;  // ASCII alleles only: the piecewise path reads them
+    return U_PATCH;
+}
+
 #ifndef GVL_TRACE
 #define GVL_TRACE 0  // 1: every CTA of hap_exec_oh_kernel logs 4 timestamps (profiles/trace_exec.py); never the shipped build
 #endif
@@ -153,6 +209,7 @@ __global__ void __launch_bounds__(EXEC_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(
     __shared__ OhRecs S;
     __shared__ __align__(16) uint2 s_lut[256];         // byte (2 codes) -> 8 one-hot bytes
     __shared__ __align__(8) uint2 s_grp[OH_MAX_GROUPS];  // per group: {reference delta, idx | cnt << 8 | plain << 31}
+    __shared__ uint32_t s_patch[EXEC_THREADS / 32][OH_UNROLL][7][32];  // per lane and mixed group: 6 staged code words + descriptor
     __shared__ int64_t s_lo, s_hi;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -254,6 +311,10 @@ __global__ void __launch_bounds__(EXEC_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(
 
     // common epilogue of a full unit: 8 codes (output order) -> 32 one-hot bytes, one 256-bit store
     auto emit8 = [&](uint8_t *dst, uint32_t v) {
+#if GVL_EXP & 4
+        stg_256(dst, make_uint2(v, v >> 1), make_uint2(v >> 2, v >> 3), make_uint2(v >> 4, v >> 5), make_uint2(v >> 6, v >> 7));
+        return;
+#endif
         const uint2 o0 = lds_u64(lut_a + ((v << 3) & 0x7f8u));
         const uint2 o1 = lds_u64(lut_a + ((v >> 5) & 0x7f8u));
         const uint2 o2 = lds_u64(lut_a + ((v >> 13) & 0x7f8u));
@@ -283,7 +344,7 @@ __global__ void __launch_bounds__(EXEC_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(
                 S.src[i] = P.rec.src[g];
             }
         }
-        if (tid == 0) S.a[m] = INT32_MAX;
+        if (tid == 0) S.a[m] = S.a[m + 1] = INT32_MAX;
         __syncthreads();
 
         // ---- output range of the pass in units of 8 positions aligned on the GLOBAL flat index (32-byte
@@ -324,66 +385,124 @@ __global__ void __launch_bounds__(EXEC_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(
         const int32_t pg_step = rc ? -OH_GROUP : OH_GROUP;
 
         for (int gb = warp; gb < n_groups; gb += OH_UNROLL * (EXEC_THREADS / 32)) {
-            // ---- phase 1: ALL loads of the warp's groups first (2 per group and lane), so that no load queues up
-            //      behind the store stream.  Plain groups share one delta; in a group with variants / pads / edges
-            //      every lane classifies its own unit and loads if its 8 positions are one reference run. ----
+            // ---- phase 0 (rolled): groups with variants / pads / edges.  Every lane classifies its own unit
+            //      (oh_classify) and starts ASYNCHRONOUS 4-byte copies of the code words it will need -- first
+            //      reference window, second reference window, ALT codes -- into its private scratch slots; the
+            //      blend happens in phase 3, after the plain groups have been streamed. ----
+            unsigned mixmask = 0;  // warp-uniform
+#pragma unroll 1
+            for (int u = 0; u < OH_UNROLL; u++) {
+                const int g = gb + u * (EXEC_THREADS / 32);
+                if (g >= n_groups) break;
+                const uint2 meta = s_grp[g];
+                if ((GVL_EXP & 2) || (meta.y & 0x80000000u)) continue;
+                mixmask |= 1u << u;
+                const int32_t j = j0 + OH_GROUP * g + 8 * lane;  // first output position of the lane's unit
+                const int32_t p_lo = pg0 + pg_step * g + lane_off;
+                UnitShape U;
+                const int kind = oh_classify(S, meta.y & 0xff, (meta.y >> 8) & 0xff, p_lo, max(p_lo, cur),
+                                             j >= jo_lo && j + 8 <= jo_hi, j + 8 > jo_lo && j < jo_hi, rp.ref_base,
+                                             rp.contig_len, P.alt_packed != nullptr, U);
+                uint32_t desc = (uint32_t)kind;
+                if (kind == U_FAST || kind == U_PATCH) {
+                    const uint32_t slot = smem_u32(&s_patch[warp][u][0][lane]);
+                    const int64_t nA = rp.ref_base + p_lo + U.dlA;
+                    const int vA = (int)imax64(0, imin64((int64_t)rp.contig_len - ((int64_t)p_lo + U.dlA), 8));
+                    desc |= (uint32_t)U.x1 << 2 | (uint32_t)U.x2 << 6 | (uint32_t)vA << 10 | ((uint32_t)nA & 7u) << 18;
+                    if (vA > 0 && (U.x1 > 0 || U.x2 < 8)) {
+                        const uint32_t *w = P.ref_packed + (nA >> 3);
+                        cp_async4(slot, w);
+                        cp_async4(slot + 128, w + 1);
+                    }
+                    if (U.x1 < 8) {
+                        if (U.x1 > 0 && U.x2 < 8) {  // a record starts inside the unit: reference resumes with its own delta
+                            const int64_t nB = rp.ref_base + p_lo + U.dlB;
+                            const int vB = (int)imax64(0, imin64((int64_t)rp.contig_len - ((int64_t)p_lo + U.dlB), 8));
+                            desc |= (uint32_t)vB << 14 | ((uint32_t)nB & 7u) << 21;
+                            if (vB > 0) {
+                                const uint32_t *w = P.ref_packed + (nB >> 3);
+                                cp_async4(slot + 256, w);
+                                cp_async4(slot + 384, w + 1);
+                            }
+                        }
+                        if (U.alt == ALT_PAD) {
+                            desc |= 1u << 27;
+                        } else {  // ALT codes, or the svar2 pure-deletion anchor from the packed reference
+                            const int64_t nC = U.alt >= 0 ? U.alt : ~U.alt;
+                            const uint32_t *w = (U.alt >= 0 ? P.alt_packed : P.ref_packed) + (nC >> 3);
+                            desc |= ((uint32_t)nC & 7u) << 24;
+                            cp_async4(slot + 512, w);
+                            cp_async4(slot + 640, w + 1);
+                        }
+                    }
+                }
+                s_patch[warp][u][6][lane] = desc;
+            }
+            cp_async_commit();
+
+            // ---- phase 1: the two loads of every plain group (up to 2 * OH_UNROLL in flight per lane) ----
             uint32_t w0[OH_UNROLL], w1[OH_UNROLL], sh[OH_UNROLL];
-            unsigned ldmask = 0, mixmask = 0;  // ldmask is per LANE, mixmask per warp
+            unsigned plainmask = 0;
 #pragma unroll
             for (int u = 0; u < OH_UNROLL; u++) {
                 const int g = gb + u * (EXEC_THREADS / 32);
-                if (g < n_groups) {
-                    const uint2 meta = s_grp[g];
-                    int32_t dl = (int32_t)meta.x;
-                    bool ok = true;
-                    if (!(meta.y & 0x80000000u)) {
-                        mixmask |= 1u << u;
-                        const int idx = meta.y & 0xff, cnt = (meta.y >> 8) & 0xff;
-                        const int32_t j = j0 + OH_GROUP * g + 8 * lane;  // first output position of the lane's unit
-                        const int32_t p_lo = pg0 + pg_step * g + lane_off;
-                        const int32_t ps = max(p_lo, cur);
-                        int il = idx;
-                        for (int q = 1; q <= cnt; q++) il += (S.a[idx + q] <= ps);
-                        const int32_t e_i = S.e[il];
-                        dl = S.resume[il] - e_i;
-                        ok = j >= jo_lo && j + 8 <= jo_hi && p_lo >= e_i && p_lo + 8 <= S.a[il + 1] &&
-                             (int64_t)p_lo + dl + 8 <= rp.contig_len;
-                    }
-                    if (ok) {
-                        ldmask |= 1u << u;
-                        const int64_t x = nb2 + (int32_t)(pg0 + pg_step * g + dl);
-                        const uint32_t *w = reinterpret_cast<const uint32_t *>((uintptr_t)(x >> 1) & ~(uintptr_t)3);
-                        w0[u] = __ldg(w);
-                        w1[u] = __ldg(w + 1);
-                        sh[u] = (uint32_t)x << 2;
-                    }
+                if (g < n_groups && !(mixmask & (1u << u))) {
+                    plainmask |= 1u << u;
+                    const int64_t x = nb2 + (int32_t)(pg0 + pg_step * g + (int32_t)s_grp[g].x);
+                    const uint32_t *w = reinterpret_cast<const uint32_t *>((uintptr_t)(x >> 1) & ~(uintptr_t)3);
+                    w0[u] = __ldg(w);
+                    w1[u] = __ldg(w + 1);
+                    sh[u] = (uint32_t)x << 2;
                 }
             }
-            // ---- phase 2: encode + store every unit that is one reference run ----
+            // ---- phase 2: encode + store the plain groups ----
 #pragma unroll
             for (int u = 0; u < OH_UNROLL; u++) {
-                if (ldmask & (1u << u)) {
+                if (plainmask & (1u << u)) {
                     const int g = gb + u * (EXEC_THREADS / 32);
                     uint32_t v = __funnelshift_r(w0[u], w1[u], sh[u]);  // nibble t = haplotype position p_lo + t
                     if (rc) v = __brev(v);                               // nibble t = output position j + t, complemented
                     emit8(out_lane + (int64_t)g * (4 * OH_GROUP), v);
                 }
             }
-            // ---- phase 3: the remaining units of the mixed groups are rebuilt piece by piece ----
-            while (mixmask) {
-                const int u = __ffs(mixmask) - 1;
-                mixmask &= mixmask - 1;
-                if (ldmask & (1u << u)) continue;
+            // ---- phase 3 (rolled): blend the units of the mixed groups from the staged code words ----
+            if (mixmask) cp_async_wait<0>();
+#pragma unroll 1
+            for (int u = 0; u < OH_UNROLL; u++) {
+                if (!(mixmask & (1u << u))) continue;
+                const uint32_t desc = s_patch[warp][u][6][lane];
+                const int kind = desc & 3u;
+                if (kind == U_SKIP) continue;
                 const int g = gb + u * (EXEC_THREADS / 32);
                 const int32_t j = j0 + OH_GROUP * g + 8 * lane;
-                if (!(j + 8 > jo_lo && j < jo_hi)) continue;  // unit outside the pass
-                const uint2 meta = s_grp[g];
-                const int idx = meta.y & 0xff, cnt = (meta.y >> 8) & 0xff;
-                const int32_t p_lo = pg0 + pg_step * g + lane_off;
-                const int32_t ps = max(p_lo, cur), pe = min(p_lo + 8, seg_end);
-                int il = idx;
-                for (int q = 1; q <= cnt; q++) il += (S.a[idx + q] <= ps);
-                uint32_t v = oh_slow_unit(S, P.alt, P.ref, P.ref_packed, rp.ref_base, rp.contig_len, padnib, il, p_lo, ps, pe);
+                uint32_t v;
+                if (kind != U_SLOW) {
+                    const uint32_t *sp = &s_patch[warp][u][0][lane];
+                    const int x1 = (desc >> 2) & 15, x2 = (desc >> 6) & 15;
+                    const uint32_t mA = nib_mask((desc >> 10) & 15);
+                    const uint32_t A = (__funnelshift_r(sp[0], sp[32], ((desc >> 18) & 7u) * 4u) & mA) | (padnib & ~mA);  // trailing pad (:248-253)
+                    v = A;
+                    if (x1 < 8) {
+                        uint32_t B = A;
+                        if (x1 > 0) {
+                            const uint32_t mB = nib_mask((desc >> 14) & 15);
+                            B = (__funnelshift_r(sp[64], sp[96], ((desc >> 21) & 7u) * 4u) & mB) | (padnib & ~mB);
+                        }
+                        uint32_t alt = padnib;  // leading pad (src/reconstruct/mod.rs:75-80)
+                        if (!(desc & (1u << 27))) alt = __funnelshift_r(sp[128], sp[160], ((desc >> 24) & 7u) * 4u);
+                        const uint32_t m1 = nib_mask(x1), m2 = nib_mask(x2);
+                        v = (A & m1) | ((alt << (4 * x1)) & m2 & ~m1) | (B & ~m2);
+                    }
+                } else {
+                    const uint2 meta = s_grp[g];
+                    const int idx = meta.y & 0xff, cnt = (meta.y >> 8) & 0xff;
+                    const int32_t p_lo = pg0 + pg_step * g + lane_off;
+                    const int32_t ps = max(p_lo, cur);
+                    int il = idx;
+                    for (int q = 1; q <= cnt; q++) il += (S.a[idx + q] <= ps);
+                    v = oh_slow_unit(S, P.alt, P.ref, P.ref_packed, rp.ref_base, rp.contig_len, padnib, il, p_lo, ps,
+                                     min(p_lo + 8, seg_end));
+                }
                 if (rc) v = __brev(v);
                 uint8_t *dst = out_lane + (int64_t)g * (4 * OH_GROUP);
                 if (j >= jo_lo && j + 8 <= jo_hi) {

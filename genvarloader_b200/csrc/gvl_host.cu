@@ -213,6 +213,7 @@ static int resolve_tables(gvl_ctx *ctx, const int64_t *geno_offsets, int64_t n_g
         t->alt_offsets = (const int64_t *)d;
         if ((rc = static_dev(ctx, alt_alleles, alt_offsets[n_variants], 13, &d))) return rc;
         t->alt_alleles = (const uint8_t *)d;
+        if ((rc = packed_ref(ctx, alt_alleles, t->alt_alleles, alt_offsets[n_variants], &t->alt_packed))) return rc;
     }
     if (ref_offsets) {
         if ((rc = static_dev(ctx, ref_offsets, sizeof(int64_t) * (n_contigs + 1), 14, &d))) return rc;
@@ -305,6 +306,7 @@ int gvl_reconstruct_haplotypes_from_svar2_begin(
     t.alt_offsets = (const int64_t *)d;
     if ((rc = static_dev(ctx, key_alt, key_alt_off[n_keys], 13, &d))) return rc;
     t.alt_alleles = (const uint8_t *)d;
+    if ((rc = packed_ref(ctx, key_alt, t.alt_alleles, key_alt_off[n_keys], &t.alt_packed))) return rc;
     if ((rc = static_dev(ctx, ref_offsets, sizeof(int64_t) * (n_contigs + 1), 14, &d))) return rc;
     t.ref_offsets = (const int64_t *)d;
     if ((rc = static_dev(ctx, ref_, ref_offsets[n_contigs], 15, &d))) return rc;

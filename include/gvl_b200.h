@@ -86,6 +86,9 @@ typedef struct {
      * base.  When present, GVL_MODE_ONEHOT executes over it (8 positions per lane, 256-bit stores); results are
      * identical with and without it. */
     const uint32_t *ref_packed;  /* u32[gvl_packed_reference_words(ref_offsets[n_contigs])], 16-byte aligned */
+    /* Optional: alt_alleles packed the same way (gvl_dev_pack_reference over the allele buffer); lets units that
+     * contain an ALT be assembled from packed codes too instead of byte by byte. */
+    const uint32_t *alt_packed;  /* u32[gvl_packed_reference_words(alt_offsets[n_variants])], 16-byte aligned */
 } gvl_sparse_tables;
 
 /* Packed form of the reference for the one-hot execute path: base r of the concatenated reference is nibble r&7

@@ -41,15 +41,17 @@ def _check(K, O, d, args, rc, tag):
     exp = O.onehot(e_out)
     g_b, g_oo = K.reconstruct_haplotypes_fused(*args, None, None, rc, mode="onehot")  # reference not pinned: bytes kernel
     assert _last_kernel(K) == 0
-    K.pin_static(d.reference)
-    try:
-        g_p, g_oo2 = K.reconstruct_haplotypes_fused(*args, None, None, rc, mode="onehot")
-        assert _last_kernel(K) == 1, "packed one-hot kernel did not run"
-    finally:
-        K.unpin_static(d.reference)
-    _golden.eq(tag + ".offsets", 0, g_oo2, e_oo)
     _golden.eq(tag + ".bytes_kernel", 0, g_b, exp)
-    _golden.eq(tag + ".packed_kernel", 0, g_p, exp)
+    # packed reference only (units with ALT bytes take the piecewise path), then packed reference + packed alleles
+    for pinned in ((d.reference,), (d.reference, d.alt_alleles)):
+        K.pin_static(*pinned)
+        try:
+            g_p, g_oo2 = K.reconstruct_haplotypes_fused(*args, None, None, rc, mode="onehot")
+            assert _last_kernel(K) == 1, "packed one-hot kernel did not run"
+        finally:
+            K.unpin_static(*pinned)
+        _golden.eq(tag + ".offsets", 0, g_oo2, e_oo)
+        _golden.eq(tag + f".packed_kernel[{len(pinned)}]", 0, g_p, exp)
 
 
 @pytest.mark.parametrize("vkb,L,out_len,shifts", [(1.0, 2000, 2000, False), (10.0, 3000, -1, False),
@@ -151,7 +153,7 @@ def test_packed_onehot_svar2_pure_deletion_anchor(K, O):
     regions, goi, to_rc, ds_idx = synth.batch_args(d, r_idx, s_idx)
     ch = synth.to_svar2_channels(d, regions, ds_idx, dense_frac=0.5, seed=3)
     shifts = np.zeros(goi.shape, np.int32)
-    K.pin_static(d.reference)
+    K.pin_static(d.reference, ch["key_alt"])
     try:
         for out_len in (-1, L - 100):
             exp, _ = _oracle(O, d, ch, regions, shifts, out_len, to_rc)
@@ -162,7 +164,7 @@ def test_packed_onehot_svar2_pure_deletion_anchor(K, O):
             assert _last_kernel(K) == 1
             assert (oh == O.onehot(exp)).all()
     finally:
-        K.unpin_static(d.reference)
+        K.unpin_static(d.reference, ch["key_alt"])
 
 
 def test_engine_packs_reference_by_default(cuda_device):

@@ -1082,7 +1082,7 @@ int gvl_dev_hap_exec(gvl_ctx *ctx, const gvl_sparse_tables *tab, int mode, uint8
     P.rec = ctx->hap.rec;
     P.ref = tab->ref;
     P.ref_packed = tab->ref_packed;
-    P.alt_packed = ((uintptr_t)tab->alt_packed & 15) ? nullptr : tab->alt_packed;
+    P.alt_packed = tab->alt_packed;
     P.dir = ctx->dir_stride > 0 ? ctx->hap.dir : nullptr;
     P.dir_stride = ctx->dir_stride;
     P.fixed_len = ctx->fixed_len;
@@ -1098,8 +1098,8 @@ int gvl_dev_hap_exec(gvl_ctx *ctx, const gvl_sparse_tables *tab, int mode, uint8
         const char *e = getenv("GVL_EXEC");
         return e && e[0] == 'b';
     }();
-    const bool packed = mode == GVL_MODE_ONEHOT && tab->ref_packed && !force_bytes && !((uintptr_t)out & 31) &&
-                        !((uintptr_t)tab->ref_packed & 15);
+    const bool packed = mode == GVL_MODE_ONEHOT && tab->ref_packed && tab->alt_packed && !force_bytes &&
+                        !((uintptr_t)out & 31) && !((uintptr_t)tab->ref_packed & 15) && !((uintptr_t)tab->alt_packed & 15);
     int64_t grid;
     if (ctx->fixed_len >= 0 && packed) {
         // one wave of CTAs when it can be; whole 256-position groups for each of the 4 warps

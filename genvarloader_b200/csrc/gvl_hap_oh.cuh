@@ -128,35 +128,33 @@ __device__ __noinline__ uint32_t oh_slow_unit(const OhRecs &S, const uint8_t *__
 }
 
 
-// ---- one unit (8 haplotype positions from p_lo) of a group that is not plain reference ----
-enum { U_SKIP = 0, U_FAST = 1, U_PATCH = 2, U_SLOW = 3 };
+// ---- EDGE units: units of 8 positions with a record boundary strictly inside --------------------------
+// Every staged record owns two "boundaries" (its ALT start a and its ALT end e); one thread per boundary
+// assembles the unit that contains it (if no earlier boundary lies in the same unit).  All other units of the
+// pass are a single run (reference or ALT interior) and are streamed by the lanes of the group loop.
+enum { U_SKIP = 0, U_PATCH = 2, U_SLOW = 3 };
 
 // Shape of a PATCH unit: [0, x1) reference with delta dlA | [x1, x2) ALT codes starting at base index `alt` of the
 // packed allele buffer (ALT_PAD: pad codes; < 0: ~index into the packed reference, the svar2 pure-deletion
-// anchor) | [x2, 8) reference with delta dlB.  x1 == 8: reference only (a unit that merely runs past the contig end).
+// anchor) | [x2, 8) reference with delta dlB.
 struct UnitShape {
-    int il, x1, x2;
+    int x1, x2;
     int32_t dlA, dlB;
     int64_t alt;
 };
 
 __device__ __forceinline__ uint32_t nib_mask(int k) { return k >= 8 ? 0xffffffffu : ((1u << (4 * k)) - 1u); }
 
-__device__ __forceinline__ int oh_classify(const OhRecs &S, int idx, int cnt, int32_t p_lo, int32_t ps, bool inside,
-                                           bool anyin, int64_t ref_base, int32_t contig_len, bool alt_packed,
-                                           UnitShape &U) {
-    if (!anyin) return U_SKIP;
-    int il = idx;
-    for (int q = 1; q <= cnt; q++) il += (S.a[idx + q] <= ps);
-    U.il = il;
-    if (!inside) return U_SLOW;
+// valid leading codes of an 8-code window that starts at reference position rpos (trailing pad past the contig end)
+__device__ __forceinline__ int n_valid(int32_t contig_len, int64_t rpos) {
+    return (int)imax64(0, imin64((int64_t)contig_len - rpos, 8));
+}
+
+// il = last staged record with a <= p_lo; the unit [p_lo, p_lo + 8) lies inside the pass
+__device__ __forceinline__ int oh_classify(const OhRecs &S, int il, int32_t p_lo, int64_t ref_base, UnitShape &U) {
     const int32_t end = p_lo + 8, e_i = S.e[il], a1 = S.a[il + 1];
     U.dlA = S.resume[il] - e_i;
-    if (p_lo >= e_i) {
-        if (a1 >= end) {  // one reference run
-            U.x1 = U.x2 = 8;
-            return ((int64_t)p_lo + U.dlA + 8 <= contig_len) ? U_FAST : U_PATCH;
-        }
+    if (p_lo >= e_i) {  // starts in the reference run of record il; record il+1 starts inside
         if (S.a[il + 2] < end) return U_SLOW;  // two records start inside the unit
         const int32_t e1 = S.e[il + 1];
         U.x1 = a1 - p_lo;
@@ -164,16 +162,15 @@ __device__ __forceinline__ int oh_classify(const OhRecs &S, int idx, int cnt, in
         U.dlB = S.resume[il + 1] - e1;
         U.alt = S.src[il + 1];
         if (ref_base + p_lo + U.dlB < 0) return U_SLOW;  // (the 8-code window would start before the buffer)
-    } else {  // the unit starts inside the ALT of record il
+    } else {  // starts inside the ALT of record il, which ends inside
         if (a1 < end) return U_SLOW;
         U.x1 = 0;
-        U.x2 = min(e_i, end) - p_lo;
+        U.x2 = e_i - p_lo;
         U.dlB = U.dlA;
         const int64_t src = S.src[il], off = p_lo - S.a[il];
         U.alt = src == ALT_PAD ? ALT_PAD : (src >= 0 ? src + off : ~(~src + off));
         if (ref_base + p_lo + U.dlA < 0) return U_SLOW;
     }
-    if (!alt_packed && U.alt >= 0) return U_SLOW;  // ASCII alleles only: the piecewise path reads them
     return U_PATCH;
 }
 
@@ -209,7 +206,6 @@ __global__ void __launch_bounds__(EXEC_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(
     __shared__ OhRecs S;
     __shared__ __align__(16) uint2 s_lut[256];         // byte (2 codes) -> 8 one-hot bytes
     __shared__ __align__(8) uint2 s_grp[OH_MAX_GROUPS];  // per group: {reference delta, idx | cnt << 8 | plain << 31}
-    __shared__ uint32_t s_patch[EXEC_THREADS / 32][OH_UNROLL][7][32];  // per lane and mixed group: 6 staged code words + descriptor
     __shared__ int64_t s_lo, s_hi;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -383,137 +379,181 @@ __global__ void __launch_bounds__(EXEC_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(
         uint8_t *const out_lane = out_row + 4 * ((int64_t)j0 + 8 * lane);
         const int32_t pg0 = rc ? (L - OH_GROUP - j0) : j0;  // lowest haplotype position of group 0
         const int32_t pg_step = rc ? -OH_GROUP : OH_GROUP;
+        const int32_t gofs = (rc ? L - j0 : j0) & 7;        // units start at haplotype positions == gofs (mod 8)
 
-        for (int gb = warp; gb < n_groups; gb += OH_UNROLL * (EXEC_THREADS / 32)) {
-            // ---- phase 0 (rolled): groups with variants / pads / edges.  Every lane classifies its own unit
-            //      (oh_classify) and starts ASYNCHRONOUS 4-byte copies of the code words it will need -- first
-            //      reference window, second reference window, ALT codes -- into its private scratch slots; the
-            //      blend happens in phase 3, after the plain groups have been streamed. ----
-            unsigned mixmask = 0;  // warp-uniform
-#pragma unroll 1
-            for (int u = 0; u < OH_UNROLL; u++) {
-                const int g = gb + u * (EXEC_THREADS / 32);
-                if (g >= n_groups) break;
-                const uint2 meta = s_grp[g];
-                if ((GVL_EXP & 2) || (meta.y & 0x80000000u)) continue;
-                mixmask |= 1u << u;
-                const int32_t j = j0 + OH_GROUP * g + 8 * lane;  // first output position of the lane's unit
-                const int32_t p_lo = pg0 + pg_step * g + lane_off;
+        // ---- edge slots, part 1: classify + start the loads.  Slot s < 2m is the boundary a (s even) / e (s odd)
+        //      of staged record s >> 1; slots 2m and 2m+1 are the units cut by the two ends of the pass. ----
+        const int n_slots = 2 * m + 2;
+        int e_kind = U_SKIP, e_il = 0;
+        int32_t e_p = 0;
+        uint32_t e_desc = 0, ea0 = 0, ea1 = 0, eb0 = 0, eb1 = 0, ec0 = 0, ec1 = 0;
+        auto edge_locate = [&](int s_, int &kind, int32_t &p_lo, int &il) {
+            kind = U_SKIP;
+            if (s_ >= 2 * m) {  // partial units at the pass ends (first: s_ == 2m, last: 2m+1)
+                const int32_t jf = j0, jl = j0 + (((jo_hi - 1 - j0) >> 3) << 3);
+                const int32_t j = s_ == 2 * m ? jf : jl;
+                if ((s_ == 2 * m + 1 && jl == jf) || (j >= jo_lo && j + 8 <= jo_hi)) return;
+                p_lo = rc ? L - 8 - j : j;
+                kind = U_SLOW;
+            } else {
+                const int32_t b = (s_ & 1) ? S.e[s_ >> 1] : S.a[s_ >> 1];
+                const int32_t in = (b - gofs) & 7;
+                if (in == 0) return;  // boundary on a unit edge: both neighbours are single runs
+                p_lo = b - in;
+                const int32_t j = rc ? L - 8 - p_lo : p_lo;
+                if (!(j >= jo_lo && j + 8 <= jo_hi)) return;  // outside this pass, or cut by it (slots 2m, 2m+1)
+                if (s_ > 0 && (((s_ - 1) & 1) ? S.e[(s_ - 1) >> 1] : S.a[(s_ - 1) >> 1]) > p_lo) return;  // an earlier boundary owns the unit
+                kind = U_PATCH;
+            }
+            il = min(s_ >> 1, m - 1);
+            const int32_t ps = max(p_lo, cur);
+            while (il > 0 && S.a[il] > ps) il--;
+        };
+        if (tid < n_slots) {
+            edge_locate(tid, e_kind, e_p, e_il);
+            if (e_kind == U_PATCH) {
                 UnitShape U;
-                const int kind = oh_classify(S, meta.y & 0xff, (meta.y >> 8) & 0xff, p_lo, max(p_lo, cur),
-                                             j >= jo_lo && j + 8 <= jo_hi, j + 8 > jo_lo && j < jo_hi, rp.ref_base,
-                                             rp.contig_len, P.alt_packed != nullptr, U);
-                uint32_t desc = (uint32_t)kind;
-                if (kind == U_FAST || kind == U_PATCH) {
-                    const uint32_t slot = smem_u32(&s_patch[warp][u][0][lane]);
-                    const int64_t nA = rp.ref_base + p_lo + U.dlA;
-                    const int vA = (int)imax64(0, imin64((int64_t)rp.contig_len - ((int64_t)p_lo + U.dlA), 8));
-                    desc |= (uint32_t)U.x1 << 2 | (uint32_t)U.x2 << 6 | (uint32_t)vA << 10 | ((uint32_t)nA & 7u) << 18;
+                e_kind = oh_classify(S, e_il, e_p, rp.ref_base, U);
+                if (e_kind == U_PATCH) {
+                    const int64_t nA = rp.ref_base + e_p + U.dlA;
+                    const int vA = n_valid(rp.contig_len, (int64_t)e_p + U.dlA);
+                    e_desc = (uint32_t)U.x1 << 2 | (uint32_t)U.x2 << 6 | (uint32_t)vA << 10 | ((uint32_t)nA & 7u) << 18;
                     if (vA > 0 && (U.x1 > 0 || U.x2 < 8)) {
                         const uint32_t *w = P.ref_packed + (nA >> 3);
-                        cp_async4(slot, w);
-                        cp_async4(slot + 128, w + 1);
+                        ea0 = __ldg(w);
+                        ea1 = __ldg(w + 1);
                     }
-                    if (U.x1 < 8) {
-                        if (U.x1 > 0 && U.x2 < 8) {  // a record starts inside the unit: reference resumes with its own delta
-                            const int64_t nB = rp.ref_base + p_lo + U.dlB;
-                            const int vB = (int)imax64(0, imin64((int64_t)rp.contig_len - ((int64_t)p_lo + U.dlB), 8));
-                            desc |= (uint32_t)vB << 14 | ((uint32_t)nB & 7u) << 21;
-                            if (vB > 0) {
-                                const uint32_t *w = P.ref_packed + (nB >> 3);
-                                cp_async4(slot + 256, w);
-                                cp_async4(slot + 384, w + 1);
-                            }
+                    if (U.x1 > 0 && U.x2 < 8) {  // a record starts inside the unit: reference resumes with its own delta
+                        const int64_t nB = rp.ref_base + e_p + U.dlB;
+                        const int vB = n_valid(rp.contig_len, (int64_t)e_p + U.dlB);
+                        e_desc |= (uint32_t)vB << 14 | ((uint32_t)nB & 7u) << 21;
+                        if (vB > 0) {
+                            const uint32_t *w = P.ref_packed + (nB >> 3);
+                            eb0 = __ldg(w);
+                            eb1 = __ldg(w + 1);
                         }
-                        if (U.alt == ALT_PAD) {
-                            desc |= 1u << 27;
-                        } else {  // ALT codes, or the svar2 pure-deletion anchor from the packed reference
-                            const int64_t nC = U.alt >= 0 ? U.alt : ~U.alt;
-                            const uint32_t *w = (U.alt >= 0 ? P.alt_packed : P.ref_packed) + (nC >> 3);
-                            desc |= ((uint32_t)nC & 7u) << 24;
-                            cp_async4(slot + 512, w);
-                            cp_async4(slot + 640, w + 1);
-                        }
+                    }
+                    if (U.alt == ALT_PAD) {
+                        e_desc |= 1u << 27;
+                    } else {  // ALT codes, or the svar2 pure-deletion anchor from the packed reference
+                        const int64_t nC = U.alt >= 0 ? U.alt : ~U.alt;
+                        const uint32_t *w = (U.alt >= 0 ? P.alt_packed : P.ref_packed) + (nC >> 3);
+                        e_desc |= ((uint32_t)nC & 7u) << 24;
+                        ec0 = __ldg(w);
+                        ec1 = __ldg(w + 1);
                     }
                 }
-                s_patch[warp][u][6][lane] = desc;
             }
-            cp_async_commit();
+        }
 
-            // ---- phase 1: the two loads of every plain group (up to 2 * OH_UNROLL in flight per lane) ----
+        // ---- the group loop: every lane streams the units that are a single run ----
+        for (int gb = warp; gb < n_groups; gb += OH_UNROLL * (EXEC_THREADS / 32)) {
+            // phase 1: all loads of the warp's next OH_UNROLL groups (2 per lane and group in flight)
             uint32_t w0[OH_UNROLL], w1[OH_UNROLL], sh[OH_UNROLL];
-            unsigned plainmask = 0;
+            unsigned nvs = 0;      // per LANE, 4 bits per group: valid codes 0..8, 15 = not this lane's unit
+            unsigned mixmask = 0;  // per warp
 #pragma unroll
             for (int u = 0; u < OH_UNROLL; u++) {
                 const int g = gb + u * (EXEC_THREADS / 32);
-                if (g < n_groups && !(mixmask & (1u << u))) {
-                    plainmask |= 1u << u;
-                    const int64_t x = nb2 + (int32_t)(pg0 + pg_step * g + (int32_t)s_grp[g].x);
-                    const uint32_t *w = reinterpret_cast<const uint32_t *>((uintptr_t)(x >> 1) & ~(uintptr_t)3);
-                    w0[u] = __ldg(w);
-                    w1[u] = __ldg(w + 1);
-                    sh[u] = (uint32_t)x << 2;
+                w0[u] = w1[u] = sh[u] = 0;
+                unsigned nv = 15;
+                if (g < n_groups) {
+                    const uint2 meta = s_grp[g];
+                    if ((GVL_EXP & 2) || (meta.y & 0x80000000u)) {  // plain: one delta for the whole group
+                        nv = 8;
+                        const int64_t x = nb2 + (int32_t)(pg0 + pg_step * g + (int32_t)meta.x);
+                        const uint32_t *w = reinterpret_cast<const uint32_t *>((uintptr_t)(x >> 1) & ~(uintptr_t)3);
+                        w0[u] = __ldg(w);
+                        w1[u] = __ldg(w + 1);
+                        sh[u] = (uint32_t)x << 2;
+                    } else {  // variants / pads / edges: the lane looks at its own unit
+                        mixmask |= 1u << u;
+                        const int32_t j = j0 + OH_GROUP * g + 8 * lane;  // first output position of the lane's unit
+                        const int32_t p_lo = pg0 + pg_step * g + lane_off;
+                        if (j >= jo_lo && j + 8 <= jo_hi) {
+                            const int idx = meta.y & 0xff, cnt = (meta.y >> 8) & 0xff;
+                            int il = idx;
+                            for (int q = 1; q <= cnt; q++) il += (S.a[idx + q] <= p_lo);
+                            const int32_t e_i = S.e[il];
+                            const uint32_t *base = P.ref_packed;
+                            int64_t n = -1;
+                            if (p_lo >= e_i) {
+                                if (p_lo + 8 <= S.a[il + 1]) {  // reference run (trailing pad past the contig end, :248-253)
+                                    const int64_t rpos = (int64_t)p_lo + (S.resume[il] - e_i);
+                                    nv = (unsigned)n_valid(rp.contig_len, rpos);
+                                    n = rp.ref_base + rpos;
+                                }
+                            } else if (p_lo + 8 <= e_i) {  // interior of an ALT (long insertion, leading pad)
+                                const int64_t src = S.src[il];
+                                nv = src == ALT_PAD ? 0 : 8;  // (pad codes need no load)
+                                n = (src >= 0 ? src : ~src) + (p_lo - S.a[il]);
+                                if (src >= 0) base = P.alt_packed;
+                            }
+                            if (nv >= 1 && nv <= 8) {
+                                const uint32_t *w = base + (n >> 3);
+                                w0[u] = __ldg(w);
+                                w1[u] = __ldg(w + 1);
+                                sh[u] = (uint32_t)n << 2;
+                            }
+                        }
+                    }
                 }
+                nvs |= nv << (4 * u);
             }
-            // ---- phase 2: encode + store the plain groups ----
+            // phase 2: encode + store
 #pragma unroll
             for (int u = 0; u < OH_UNROLL; u++) {
-                if (plainmask & (1u << u)) {
+                const unsigned nv = (nvs >> (4 * u)) & 15u;
+                if (nv != 15) {
                     const int g = gb + u * (EXEC_THREADS / 32);
                     uint32_t v = __funnelshift_r(w0[u], w1[u], sh[u]);  // nibble t = haplotype position p_lo + t
-                    if (rc) v = __brev(v);                               // nibble t = output position j + t, complemented
+                    if (mixmask & (1u << u)) {
+                        const uint32_t mk = nib_mask((int)nv);
+                        v = (v & mk) | (padnib & ~mk);
+                    }
+                    if (rc) v = __brev(v);  // nibble t = output position j + t, complemented
                     emit8(out_lane + (int64_t)g * (4 * OH_GROUP), v);
                 }
             }
-            // ---- phase 3 (rolled): blend the units of the mixed groups from the staged code words ----
-            if (mixmask) cp_async_wait<0>();
+        }
+
+        // ---- edge slots, part 2: blend (the loads were issued before the group loop) + store ----
 #pragma unroll 1
-            for (int u = 0; u < OH_UNROLL; u++) {
-                if (!(mixmask & (1u << u))) continue;
-                const uint32_t desc = s_patch[warp][u][6][lane];
-                const int kind = desc & 3u;
-                if (kind == U_SKIP) continue;
-                const int g = gb + u * (EXEC_THREADS / 32);
-                const int32_t j = j0 + OH_GROUP * g + 8 * lane;
-                uint32_t v;
-                if (kind != U_SLOW) {
-                    const uint32_t *sp = &s_patch[warp][u][0][lane];
-                    const int x1 = (desc >> 2) & 15, x2 = (desc >> 6) & 15;
-                    const uint32_t mA = nib_mask((desc >> 10) & 15);
-                    const uint32_t A = (__funnelshift_r(sp[0], sp[32], ((desc >> 18) & 7u) * 4u) & mA) | (padnib & ~mA);  // trailing pad (:248-253)
-                    v = A;
-                    if (x1 < 8) {
-                        uint32_t B = A;
-                        if (x1 > 0) {
-                            const uint32_t mB = nib_mask((desc >> 14) & 15);
-                            B = (__funnelshift_r(sp[64], sp[96], ((desc >> 21) & 7u) * 4u) & mB) | (padnib & ~mB);
-                        }
-                        uint32_t alt = padnib;  // leading pad (src/reconstruct/mod.rs:75-80)
-                        if (!(desc & (1u << 27))) alt = __funnelshift_r(sp[128], sp[160], ((desc >> 24) & 7u) * 4u);
-                        const uint32_t m1 = nib_mask(x1), m2 = nib_mask(x2);
-                        v = (A & m1) | ((alt << (4 * x1)) & m2 & ~m1) | (B & ~m2);
-                    }
-                } else {
-                    const uint2 meta = s_grp[g];
-                    const int idx = meta.y & 0xff, cnt = (meta.y >> 8) & 0xff;
-                    const int32_t p_lo = pg0 + pg_step * g + lane_off;
-                    const int32_t ps = max(p_lo, cur);
-                    int il = idx;
-                    for (int q = 1; q <= cnt; q++) il += (S.a[idx + q] <= ps);
-                    v = oh_slow_unit(S, P.alt, P.ref, P.ref_packed, rp.ref_base, rp.contig_len, padnib, il, p_lo, ps,
-                                     min(p_lo + 8, seg_end));
+        for (int s_ = tid; s_ < n_slots; s_ += EXEC_THREADS) {
+            if (s_ != tid) {  // more than 128 slots: later ones are done start to finish here
+                edge_locate(s_, e_kind, e_p, e_il);
+                if (e_kind == U_PATCH) e_kind = U_SLOW;
+            }
+            if (e_kind == U_SKIP) continue;
+            const int32_t j = rc ? L - 8 - e_p : e_p;
+            uint32_t v;
+            if (e_kind == U_PATCH) {
+                const int x1 = (e_desc >> 2) & 15, x2 = (e_desc >> 6) & 15;
+                const uint32_t mA = nib_mask((e_desc >> 10) & 15);
+                const uint32_t A = (__funnelshift_r(ea0, ea1, ((e_desc >> 18) & 7u) * 4u) & mA) | (padnib & ~mA);
+                uint32_t B = A;
+                if (x1 > 0) {
+                    const uint32_t mB = nib_mask((e_desc >> 14) & 15);
+                    B = (__funnelshift_r(eb0, eb1, ((e_desc >> 21) & 7u) * 4u) & mB) | (padnib & ~mB);
                 }
-                if (rc) v = __brev(v);
-                uint8_t *dst = out_lane + (int64_t)g * (4 * OH_GROUP);
-                if (j >= jo_lo && j + 8 <= jo_hi) {
-                    emit8(dst, v);
-                } else {  // unit cut by a pass / tile / row boundary: position-wise stores
+                uint32_t alt = padnib;  // leading pad (src/reconstruct/mod.rs:75-80)
+                if (!(e_desc & (1u << 27))) alt = __funnelshift_r(ec0, ec1, ((e_desc >> 24) & 7u) * 4u);
+                const uint32_t m1 = nib_mask(x1), m2 = nib_mask(x2);
+                v = (A & m1) | ((alt << (4 * x1)) & m2 & ~m1) | (B & ~m2);
+            } else {
+                v = oh_slow_unit(S, P.alt, P.ref, P.ref_packed, rp.ref_base, rp.contig_len, padnib, e_il, e_p,
+                                 max(e_p, cur), min(e_p + 8, seg_end));
+            }
+            if (rc) v = __brev(v);
+            uint8_t *dst = out_row + 4 * (int64_t)j;
+            if (j >= jo_lo && j + 8 <= jo_hi) {
+                emit8(dst, v);
+            } else {  // unit cut by a pass / tile / row boundary: position-wise stores
 #pragma unroll 1
-                    for (int q = 0; q < 8; q++) {
-                        const int32_t jj = j + q;
-                        if (jj >= jo_lo && jj < jo_hi)
-                            *reinterpret_cast<uint32_t *>(dst + 4 * q) = (((v >> (4 * q)) & 15u) * 0x204081u) & 0x01010101u;
-                    }
+                for (int q = 0; q < 8; q++) {
+                    const int32_t jj = j + q;
+                    if (jj >= jo_lo && jj < jo_hi)
+                        *reinterpret_cast<uint32_t *>(dst + 4 * q) = (((v >> (4 * q)) & 15u) * 0x204081u) & 0x01010101u;
                 }
             }
         }

@@ -82,12 +82,10 @@ typedef struct {
     const int64_t *geno_starts;  /* i64[n_geno]  row 0 of the (2,n) offsets    */
     const int64_t *geno_stops;   /* i64[n_geno]  row 1                         */
     int64_t n_geno;
-    /* Optional (NULL = absent): the reference re-encoded by gvl_dev_pack_reference, one 4-bit one-hot code per
-     * base.  When present, GVL_MODE_ONEHOT executes over it (8 positions per lane, 256-bit stores); results are
-     * identical with and without it. */
+    /* Optional (NULL = absent): the reference and the ALT alleles re-encoded by gvl_dev_pack_reference, one 4-bit
+     * one-hot code per base.  When BOTH are present, GVL_MODE_ONEHOT executes over them (8 positions per lane,
+     * 256-bit stores); results are identical with and without them. */
     const uint32_t *ref_packed;  /* u32[gvl_packed_reference_words(ref_offsets[n_contigs])], 16-byte aligned */
-    /* Optional: alt_alleles packed the same way (gvl_dev_pack_reference over the allele buffer); lets units that
-     * contain an ALT be assembled from packed codes too instead of byte by byte. */
     const uint32_t *alt_packed;  /* u32[gvl_packed_reference_words(alt_offsets[n_variants])], 16-byte aligned */
 } gvl_sparse_tables;
 

@@ -937,7 +937,7 @@ static int64_t exec_capacity_oh(gvl_ctx *ctx) {
     if (ctx->device < 8 && cache[ctx->device]) return cache[ctx->device];
     int sms = 148, per_sm = OH_MIN_CTAS;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hap_exec_oh_kernel, EXEC_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hap_exec_oh_kernel, OH_THREADS, 0);
     const int64_t cap = (int64_t)sms * (per_sm > 0 ? per_sm : 1);
     if (ctx->device < 8) cache[ctx->device] = cap;
     return cap;
@@ -1107,7 +1107,7 @@ int gvl_dev_hap_exec(gvl_ctx *ctx, const gvl_sparse_tables *tab, int mode, uint8
             const char *e = getenv("GVL_OH_TILE");
             return e ? (int64_t)atoll(e) : (int64_t)0;
         }();
-        const int64_t q = 4 * OH_GROUP;
+        const int64_t q = imax64((OH_THREADS / 32) * OH_GROUP, DIR_Q);  // whole groups per warp, whole directory quanta
         const int64_t tiles_target = imax64(1, exec_capacity_oh(ctx) / ctx->n_work);
         int64_t tl = (ctx->fixed_len + tiles_target - 1) / tiles_target;
         if (tile_env > 0) tl = tile_env;
@@ -1147,7 +1147,7 @@ int gvl_dev_hap_exec(gvl_ctx *ctx, const gvl_sparse_tables *tab, int mode, uint8
     switch (mode) {
         case GVL_MODE_U8: hap_exec_kernel<GVL_MODE_U8><<<grid3, EXEC_THREADS, 0, st>>>(P); break;
         case GVL_MODE_ONEHOT:
-            if (packed) hap_exec_oh_kernel<<<grid3, EXEC_THREADS, 0, st>>>(P);
+            if (packed) hap_exec_oh_kernel<<<grid3, OH_THREADS, 0, st>>>(P);
             else hap_exec_kernel<GVL_MODE_ONEHOT><<<grid3, EXEC_THREADS, 0, st>>>(P);
             break;
         case GVL_MODE_ONEHOT_CF: hap_exec_kernel<GVL_MODE_ONEHOT_CF><<<grid3, EXEC_THREADS, 0, st>>>(P); break;

@@ -23,7 +23,14 @@ namespace gvl {
 constexpr int OH_GROUP = 256;                                  // positions per warp step (8 per lane)
 constexpr int OH_MAX_TILE = EXEC_MAX_UNITS * EXEC_UNIT;        // 8192
 constexpr int OH_MAX_GROUPS = OH_MAX_TILE / OH_GROUP + 2;      // groups a pass can touch (+ misaligned edges)
-constexpr int OH_MIN_CTAS = 8;
+#ifndef GVL_OH_THREADS
+#define GVL_OH_THREADS 128
+#endif
+#ifndef GVL_OH_MIN_CTAS
+#define GVL_OH_MIN_CTAS 8
+#endif
+constexpr int OH_THREADS = GVL_OH_THREADS;                     // threads per CTA of the packed kernel
+constexpr int OH_MIN_CTAS = GVL_OH_MIN_CTAS;
 constexpr int OH_UNROLL = 4;                                   // groups per warp whose loads are issued together
 
 struct OhRecs {
@@ -192,7 +199,7 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define GVL_TR(slot) do { } while (0)
 #endif
 
-__global__ void __launch_bounds__(EXEC_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(HapExecParams P) {
+__global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(HapExecParams P) {
 #if GVL_TRACE
     const unsigned long long tr_cta = blockIdx.x + (unsigned long long)gridDim.x * (blockIdx.y + (unsigned long long)gridDim.y * blockIdx.z);
     if (g_trace && threadIdx.x == 0) {
@@ -256,7 +263,7 @@ __global__ void __launch_bounds__(EXEC_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(
     }
 
     // spread(n): byte c = bit c of the 4-bit code n   (n * 0x204081 puts bit c at bit 8c, no carries)
-    for (int i = tid; i < 256; i += EXEC_THREADS)
+    for (int i = tid; i < 256; i += OH_THREADS)
         s_lut[i] = make_uint2(((i & 15) * 0x204081u) & 0x01010101u, ((i >> 4) * 0x204081u) & 0x01010101u);
 
     const int32_t *__restrict__ ra = P.rec.a + rp.rec_off;
@@ -324,7 +331,7 @@ __global__ void __launch_bounds__(EXEC_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(
         const int m = m_new + 1;
         const int32_t seg_end = (r + 1 + m_new < r_hi) ? ra[r + 1 + m_new] : h1;
         __syncthreads();  // previous pass finished reading S
-        for (int i = tid; i < m; i += EXEC_THREADS) {
+        for (int i = tid; i < m; i += OH_THREADS) {
             const int64_t idx = r + i;
             if (idx < 0) {  // virtual record: leading pad, then reference from ref0
                 S.a[0] = 0;
@@ -447,14 +454,14 @@ __global__ void __launch_bounds__(EXEC_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(
         }
 
         // ---- the group loop: every lane streams the units that are a single run ----
-        for (int gb = warp; gb < n_groups; gb += OH_UNROLL * (EXEC_THREADS / 32)) {
+        for (int gb = warp; gb < n_groups; gb += OH_UNROLL * (OH_THREADS / 32)) {
             // phase 1: all loads of the warp's next OH_UNROLL groups (2 per lane and group in flight)
             uint32_t w0[OH_UNROLL], w1[OH_UNROLL], sh[OH_UNROLL];
             unsigned nvs = 0;      // per LANE, 4 bits per group: valid codes 0..8, 15 = not this lane's unit
             unsigned mixmask = 0;  // per warp
 #pragma unroll
             for (int u = 0; u < OH_UNROLL; u++) {
-                const int g = gb + u * (EXEC_THREADS / 32);
+                const int g = gb + u * (OH_THREADS / 32);
                 w0[u] = w1[u] = sh[u] = 0;
                 unsigned nv = 15;
                 if (g < n_groups) {
@@ -505,7 +512,7 @@ __global__ void __launch_bounds__(EXEC_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(
             for (int u = 0; u < OH_UNROLL; u++) {
                 const unsigned nv = (nvs >> (4 * u)) & 15u;
                 if (nv != 15) {
-                    const int g = gb + u * (EXEC_THREADS / 32);
+                    const int g = gb + u * (OH_THREADS / 32);
                     uint32_t v = __funnelshift_r(w0[u], w1[u], sh[u]);  // nibble t = haplotype position p_lo + t
                     if (mixmask & (1u << u)) {
                         const uint32_t mk = nib_mask((int)nv);
@@ -519,7 +526,7 @@ __global__ void __launch_bounds__(EXEC_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(
 
         // ---- edge slots, part 2: blend (the loads were issued before the group loop) + store ----
 #pragma unroll 1
-        for (int s_ = tid; s_ < n_slots; s_ += EXEC_THREADS) {
+        for (int s_ = tid; s_ < n_slots; s_ += OH_THREADS) {
             if (s_ != tid) {  // more than 128 slots: later ones are done start to finish here
                 edge_locate(s_, e_kind, e_p, e_il);
                 if (e_kind == U_PATCH) e_kind = U_SLOW;

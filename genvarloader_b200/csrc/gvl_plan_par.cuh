@@ -103,17 +103,24 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) hap_plan_par_kernel(HapPl
     const bool sized = P.output_length == -1;
     const bool want_diff = sized || (P.diffs != nullptr);
 
+    // record workspace of the row: one atomic per row.  Its round trip overlaps with the first gathers: the value
+    // stays in thread 0 until the first chunk's loads are in flight (bcast_off below).
     int64_t rec_off = 0;
     if (t == 0) rec_off = (int64_t)atomicAdd((unsigned long long *)&P.words[W_CURSOR], (unsigned long long)(nvar + 1));
-    if (NT == 32) {
-        rec_off = __shfl_sync(0xffffffffu, rec_off, 0);
-    } else {
-        if (t == 0) S.warp[NT / 32] = rec_off;
-        __syncthreads();
-        rec_off = S.warp[NT / 32];
-    }
-    const bool overflow = rec_off + nvar + 1 > P.rec_cap;
-    if (overflow && t == 0) atomicMax((unsigned long long *)&P.words[W_STATUS], (unsigned long long)(rec_off + nvar + 1));
+    bool have_off = false, overflow = false;
+    auto bcast_off = [&]() {
+        if (have_off) return;
+        if (NT == 32) {
+            rec_off = __shfl_sync(0xffffffffu, rec_off, 0);
+        } else {
+            if (t == 0) S.warp[NT / 32] = rec_off;
+            __syncthreads();
+            rec_off = S.warp[NT / 32];
+        }
+        overflow = rec_off + nvar + 1 > P.rec_cap;
+        if (overflow && t == 0) atomicMax((unsigned long long *)&P.words[W_STATUS], (unsigned long long)(rec_off + nvar + 1));
+        have_off = true;
+    };
 
     // ---------------------------------------------------------------- pass 1: diffs (only if needed)
     bool unsorted = false;
@@ -162,7 +169,8 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) hap_plan_par_kernel(HapPl
             if (head || t == 0) {
                 int64_t cur = head ? end : d_ref;
                 int u = head ? t + 1 : 0;
-                for (; u < NT && !S.head[u]; u++) {
+                const int nv = (int)imin64(NT, nvar - base);  // entries past the list end are idle: do not walk them
+                for (; u < nv && !S.head[u]; u++) {
                     const int e = S.elig[u];
                     if (e == 0) continue;
                     if (e == 2) {
@@ -239,6 +247,7 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) hap_plan_par_kernel(HapPl
             kept = has_keep ? (P.keep[keep_base + i] != 0) : true;
             if (rv.mpos) vi = (int32_t)i;  // svar2 annotates with the LOCAL index (src/reconstruct/mod.rs:734)
         }
+        bcast_off();  // (first chunk only; the gathers above are already in flight)
         const int64_t end = (i < nvar) ? pos - imin64(il, 0) + 1 : INT64_MIN;
         grp_sync<NT>();
         S.pos[t] = (int32_t)imin64(pos, INT32_MAX);
@@ -315,7 +324,8 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) hap_plan_par_kernel(HapPl
         if (head || t == 0) {
             int64_t cur = head ? end : R;
             int u = head ? t + 1 : 0;
-            for (; u < NT && !S.head[u]; u++) {
+            const int nv = (int)imin64(NT, nvar - base);  // entries past the list end are idle: do not walk them
+            for (; u < nv && !S.head[u]; u++) {
                 if (S.elig[u] && (int64_t)S.pos[u] >= cur) {  // :108-110
                     S.applied[u] = 1;
                     cur = S.end[u];
@@ -374,6 +384,7 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) hap_plan_par_kernel(HapPl
         if (any_broke || O >= length) done = true;  // :154-158, :195-197
     }
 
+    bcast_off();
     if (unsorted) {
         // exact replan in list order by one warp (rare; out of the writers' contract)
         if (NT == 32 || threadIdx.x < 32) plan_row_serial(P, k, rec_off);

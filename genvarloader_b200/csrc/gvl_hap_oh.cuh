@@ -213,6 +213,7 @@ __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(Ha
     __shared__ OhRecs S;
     __shared__ __align__(16) uint2 s_lut[256];         // byte (2 codes) -> 8 one-hot bytes
     __shared__ __align__(8) uint2 s_grp[OH_MAX_GROUPS];  // per group: {reference delta, idx | cnt << 8 | plain << 31}
+    __shared__ uint32_t s_edge[8][OH_THREADS];  // per thread: 6 staged code words of its edge unit, descriptor, position
     __shared__ int64_t s_lo, s_hi;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -305,7 +306,6 @@ __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(Ha
     int64_t r = s_lo;
     int32_t cur = h0;
     uint8_t *__restrict__ out_row = P.out + 4 * rp.out_off;  // position j of the row lives at out_row[4*j]
-    const uint32_t lut_a = smem_u32(s_lut);
     const uint32_t padnib = nib_code(P.pad_char) * 0x11111111u;
     const int32_t lane_off = 8 * (rc ? 31 - lane : lane);  // haplotype offset of the lane's unit inside its group
     // (reference base index + 2 * table address): (x >> 1) & ~3 is then the byte address of the word that holds
@@ -318,11 +318,18 @@ __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(Ha
         stg_256(dst, make_uint2(v, v >> 1), make_uint2(v >> 2, v >> 3), make_uint2(v >> 4, v >> 5), make_uint2(v >> 6, v >> 7));
         return;
 #endif
-        const uint2 o0 = lds_u64(lut_a + ((v << 3) & 0x7f8u));
-        const uint2 o1 = lds_u64(lut_a + ((v >> 5) & 0x7f8u));
-        const uint2 o2 = lds_u64(lut_a + ((v >> 13) & 0x7f8u));
-        const uint2 o3 = lds_u64(lut_a + ((v >> 21) & 0x7f8u));
+        const char *lut = reinterpret_cast<const char *>(s_lut);  // (a link-time constant: folds into the LDS offset)
+        const uint2 o0 = *reinterpret_cast<const uint2 *>(lut + ((v << 3) & 0x7f8u));
+        const uint2 o1 = *reinterpret_cast<const uint2 *>(lut + ((v >> 5) & 0x7f8u));
+        const uint2 o2 = *reinterpret_cast<const uint2 *>(lut + ((v >> 13) & 0x7f8u));
+        const uint2 o3 = *reinterpret_cast<const uint2 *>(lut + ((v >> 21) & 0x7f8u));
         stg_256(dst, o0, o1, o2, o3);
+    };
+    // reverse-complement of 8 codes = bit reversal of the word (rows that are not reversed pass through)
+    auto rc8 = [&](uint32_t v) {
+        uint32_t r_;
+        asm("brev.b32 %0, %1;" : "=r"(r_) : "r"(v));
+        return rc ? r_ : v;
     };
 
     while (cur < h1) {
@@ -391,9 +398,6 @@ __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(Ha
         // ---- edge slots, part 1: classify + start the loads.  Slot s < 2m is the boundary a (s even) / e (s odd)
         //      of staged record s >> 1; slots 2m and 2m+1 are the units cut by the two ends of the pass. ----
         const int n_slots = 2 * m + 2;
-        int e_kind = U_SKIP, e_il = 0;
-        int32_t e_p = 0;
-        uint32_t e_desc = 0, ea0 = 0, ea1 = 0, eb0 = 0, eb1 = 0, ec0 = 0, ec1 = 0;
         auto edge_locate = [&](int s_, int &kind, int32_t &p_lo, int &il) {
             kind = U_SKIP;
             if (s_ >= 2 * m) {  // partial units at the pass ends (first: s_ == 2m, last: 2m+1)
@@ -416,19 +420,25 @@ __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(Ha
             const int32_t ps = max(p_lo, cur);
             while (il > 0 && S.a[il] > ps) il--;
         };
+        // (the code words travel with asynchronous 4-byte copies into the thread's own shared-memory slots, so no
+        //  register stays live across the group loop; part 2 reads them back after it)
         if (tid < n_slots) {
+            int e_kind, e_il = 0;
+            int32_t e_p = 0;
+            uint32_t e_desc = 0;
             edge_locate(tid, e_kind, e_p, e_il);
             if (e_kind == U_PATCH) {
                 UnitShape U;
                 e_kind = oh_classify(S, e_il, e_p, rp.ref_base, U);
                 if (e_kind == U_PATCH) {
+                    const uint32_t slot = smem_u32(&s_edge[0][tid]);
                     const int64_t nA = rp.ref_base + e_p + U.dlA;
                     const int vA = n_valid(rp.contig_len, (int64_t)e_p + U.dlA);
                     e_desc = (uint32_t)U.x1 << 2 | (uint32_t)U.x2 << 6 | (uint32_t)vA << 10 | ((uint32_t)nA & 7u) << 18;
                     if (vA > 0 && (U.x1 > 0 || U.x2 < 8)) {
                         const uint32_t *w = P.ref_packed + (nA >> 3);
-                        ea0 = __ldg(w);
-                        ea1 = __ldg(w + 1);
+                        cp_async4(slot, w);
+                        cp_async4(slot + 4 * OH_THREADS, w + 1);
                     }
                     if (U.x1 > 0 && U.x2 < 8) {  // a record starts inside the unit: reference resumes with its own delta
                         const int64_t nB = rp.ref_base + e_p + U.dlB;
@@ -436,8 +446,8 @@ __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(Ha
                         e_desc |= (uint32_t)vB << 14 | ((uint32_t)nB & 7u) << 21;
                         if (vB > 0) {
                             const uint32_t *w = P.ref_packed + (nB >> 3);
-                            eb0 = __ldg(w);
-                            eb1 = __ldg(w + 1);
+                            cp_async4(slot + 8 * OH_THREADS, w);
+                            cp_async4(slot + 12 * OH_THREADS, w + 1);
                         }
                     }
                     if (U.alt == ALT_PAD) {
@@ -446,15 +456,19 @@ __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(Ha
                         const int64_t nC = U.alt >= 0 ? U.alt : ~U.alt;
                         const uint32_t *w = (U.alt >= 0 ? P.alt_packed : P.ref_packed) + (nC >> 3);
                         e_desc |= ((uint32_t)nC & 7u) << 24;
-                        ec0 = __ldg(w);
-                        ec1 = __ldg(w + 1);
+                        cp_async4(slot + 16 * OH_THREADS, w);
+                        cp_async4(slot + 20 * OH_THREADS, w + 1);
                     }
                 }
             }
+            s_edge[6][tid] = e_desc | (uint32_t)e_kind;
+            s_edge[7][tid] = (uint32_t)e_p;
         }
+        cp_async_commit();
 
         // ---- the group loop: every lane streams the units that are a single run ----
         for (int gb = warp; gb < n_groups; gb += OH_UNROLL * (OH_THREADS / 32)) {
+            uint8_t *const out_it = out_lane + (int64_t)gb * (4 * OH_GROUP);  // the lane's unit in group gb
             // phase 1: all loads of the warp's next OH_UNROLL groups (2 per lane and group in flight)
             uint32_t w0[OH_UNROLL], w1[OH_UNROLL], sh[OH_UNROLL];
             unsigned nvs = 0;      // per LANE, 4 bits per group: valid codes 0..8, 15 = not this lane's unit
@@ -518,16 +532,23 @@ __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(Ha
                         const uint32_t mk = nib_mask((int)nv);
                         v = (v & mk) | (padnib & ~mk);
                     }
-                    if (rc) v = __brev(v);  // nibble t = output position j + t, complemented
-                    emit8(out_lane + (int64_t)g * (4 * OH_GROUP), v);
+                    emit8(out_it + u * (OH_THREADS / 32) * (4 * OH_GROUP), rc8(v));  // rc: nibble t = output position j + t, complemented
                 }
             }
         }
 
-        // ---- edge slots, part 2: blend (the loads were issued before the group loop) + store ----
+        // ---- edge slots, part 2: blend (the copies were started before the group loop) + store ----
+        cp_async_wait<0>();
 #pragma unroll 1
         for (int s_ = tid; s_ < n_slots; s_ += OH_THREADS) {
-            if (s_ != tid) {  // more than 128 slots: later ones are done start to finish here
+            int e_kind, e_il = 0;
+            int32_t e_p;
+            uint32_t e_desc = 0;
+            e_desc = s_edge[6][tid];
+            e_kind = e_desc & 3u;
+            e_p = (int32_t)s_edge[7][tid];
+            if (s_ != tid || e_kind == U_SLOW) {
+                // piecewise units (and, with more slots than threads, all later slots) are done start to finish here
                 edge_locate(s_, e_kind, e_p, e_il);
                 if (e_kind == U_PATCH) e_kind = U_SLOW;
             }
@@ -537,21 +558,21 @@ __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(Ha
             if (e_kind == U_PATCH) {
                 const int x1 = (e_desc >> 2) & 15, x2 = (e_desc >> 6) & 15;
                 const uint32_t mA = nib_mask((e_desc >> 10) & 15);
-                const uint32_t A = (__funnelshift_r(ea0, ea1, ((e_desc >> 18) & 7u) * 4u) & mA) | (padnib & ~mA);
+                const uint32_t A = (__funnelshift_r(s_edge[0][tid], s_edge[1][tid], ((e_desc >> 18) & 7u) * 4u) & mA) | (padnib & ~mA);
                 uint32_t B = A;
                 if (x1 > 0) {
                     const uint32_t mB = nib_mask((e_desc >> 14) & 15);
-                    B = (__funnelshift_r(eb0, eb1, ((e_desc >> 21) & 7u) * 4u) & mB) | (padnib & ~mB);
+                    B = (__funnelshift_r(s_edge[2][tid], s_edge[3][tid], ((e_desc >> 21) & 7u) * 4u) & mB) | (padnib & ~mB);
                 }
                 uint32_t alt = padnib;  // leading pad (src/reconstruct/mod.rs:75-80)
-                if (!(e_desc & (1u << 27))) alt = __funnelshift_r(ec0, ec1, ((e_desc >> 24) & 7u) * 4u);
+                if (!(e_desc & (1u << 27))) alt = __funnelshift_r(s_edge[4][tid], s_edge[5][tid], ((e_desc >> 24) & 7u) * 4u);
                 const uint32_t m1 = nib_mask(x1), m2 = nib_mask(x2);
                 v = (A & m1) | ((alt << (4 * x1)) & m2 & ~m1) | (B & ~m2);
             } else {
                 v = oh_slow_unit(S, P.alt, P.ref, P.ref_packed, rp.ref_base, rp.contig_len, padnib, e_il, e_p,
                                  max(e_p, cur), min(e_p + 8, seg_end));
             }
-            if (rc) v = __brev(v);
+            v = rc8(v);
             uint8_t *dst = out_row + 4 * (int64_t)j;
             if (j >= jo_lo && j + 8 <= jo_hi) {
                 emit8(dst, v);

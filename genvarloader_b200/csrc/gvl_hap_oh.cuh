@@ -21,7 +21,7 @@
 namespace gvl {
 
 constexpr int OH_GROUP = 256;                                  // positions per warp step (8 per lane)
-constexpr int OH_MAX_TILE = EXEC_MAX_UNITS * EXEC_UNIT;        // 8192
+constexpr int OH_MAX_TILE = 16384;                             // haplotype positions per CTA, at most
 constexpr int OH_MAX_GROUPS = OH_MAX_TILE / OH_GROUP + 2;      // groups a pass can touch (+ misaligned edges)
 #ifndef GVL_OH_THREADS
 #define GVL_OH_THREADS 128

@@ -1102,16 +1102,25 @@ int gvl_dev_hap_exec(gvl_ctx *ctx, const gvl_sparse_tables *tab, int mode, uint8
                         !((uintptr_t)out & 31) && !((uintptr_t)tab->ref_packed & 15) && !((uintptr_t)tab->alt_packed & 15);
     int64_t grid;
     if (ctx->fixed_len >= 0 && packed) {
-        // one wave of CTAs when it can be; whole 256-position groups for each of the 4 warps
+        // Tiles as long as they can be (<= OH_MAX_TILE) while the batch still gives every SM ~3 CTAs: a CTA's fixed
+        // cost (two dependent round trips before its first store) is amortised over more positions, and a launch
+        // that leaves CTA slots free lets the next batch's launch (another stream) overlap its latency phases
+        // with this one's store stream (measured: profiles/r1_packed.md).  GVL_OH_TILE overrides (A/B runs).
         static const int64_t tile_env = [] {
             const char *e = getenv("GVL_OH_TILE");
             return e ? (int64_t)atoll(e) : (int64_t)0;
         }();
         const int64_t q = imax64((OH_THREADS / 32) * OH_GROUP, DIR_Q);  // whole groups per warp, whole directory quanta
-        const int64_t tiles_target = imax64(1, exec_capacity_oh(ctx) / ctx->n_work);
-        int64_t tl = (ctx->fixed_len + tiles_target - 1) / tiles_target;
+        static const int sms = [] {
+            int n = 148, dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+            return n;
+        }();
+        const int64_t target_ctas = 3 * (int64_t)sms;
+        int64_t tl = ctx->fixed_len * ctx->n_work / target_ctas;
         if (tile_env > 0) tl = tile_env;
-        tl = imax64(q, imin64((tl + q - 1) / q * q, OH_MAX_TILE));
+        tl = imax64(q, imin64(tl / q * q, OH_MAX_TILE));
         P.tile_len = (int32_t)tl;
         P.tiles_per_row = (ctx->fixed_len + P.tile_len - 1) / P.tile_len;
         P.tile_off = nullptr;

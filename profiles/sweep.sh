@@ -8,6 +8,6 @@ for l in sys.stdin:
     l=l.strip()
     if not l.startswith('{'): continue
     j=json.loads(l); r=j['roofline']
-    print('$tag', '$w', 'Gbp/s=%.1f'%(j['value']/1e9), 'step_us=%.2f'%(j['ms_per_step']*1e3), 'exec_us=%.2f'%(r['launch_ms']*1e3), 'plan_us=%.2f'%(r['plan_kernel_ms']*1e3), 'iso_us=%.2f'%(r['launch_ms_isolated_after_l2_flush']*1e3), 'frac=%.3f'%r['frac'], 'step_frac=%.3f'%r['whole_step_frac'])
+    print('$tag', '$w', 'Gbp/s=%.1f'%(j['value']/1e9), 'step_us=%.2f'%(j['ms_per_step']*1e3), 'exec_us=%.2f'%(r['launch_ms']*1e3), 'exec1s_us=%.2f'%(r.get('launch_ms_one_stream',0)*1e3), 'plan_us=%.2f'%(r['plan_kernel_ms']*1e3), 'iso_us=%.2f'%(r['launch_ms_isolated_after_l2_flush']*1e3), 'frac=%.3f'%r['frac'], 'step_frac=%.3f'%r['whole_step_frac'])
 "
 done

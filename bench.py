@@ -494,6 +494,9 @@ def run_b200(args):
                                 f"own stream, {n_slots} in flight), replayed back to back; event time / launches.  launch_ms_one_stream: same "
                                 "launches serialised on a single stream (adds the ~3 us stream-order gap a 33 MB fill kernel also pays)",
                          "frac_of_nominal_8TBps": achieved / 8000.0,
+                         "frac_layout_bytes": (ab - 0.5 * rows * L) / (exec_ms * 1e-3) / 1e9 / peak,
+                         "bytes_note": "algorithmic bytes = SURVEY.md 8d (5 B/bp: 1 reference byte + 4 one-hot bytes); the packed reference "
+                                       "moves 0.5 B/bp, frac_layout_bytes counts 4.5 B/bp instead",
                          "whole_step_frac": step_achieved / peak},
             "cpu_baseline": {"value": cpu_v, "unit": "bp/s", "cores": threads, "kind": "port",
                              "sample": f"{cpu_n} batches ({cpu_s:.1f} s) of the same workload; C restatement of the reference's "

@@ -16,8 +16,12 @@
 
 namespace gvl {
 
-constexpr int TRK_TILE = 2048;             // output values per execute CTA
-constexpr int TRK_WIN = TRK_TILE + 512;    // source-window values staged in shared memory
+constexpr int TRK_TILE = 8192;             // output values per pass of an execute CTA (one staged source window)
+constexpr int TRK_WIN = TRK_TILE + 1024;   // source-window values staged in shared memory (room for net deletions)
+#ifndef GVL_TRK_SEG_TILES
+#define GVL_TRK_SEG_TILES 8
+#endif
+constexpr int TRK_SEG = GVL_TRK_SEG_TILES * TRK_TILE;       // output values per execute CTA: up to 8 tiles, walked in haplotype order
 constexpr int TRK_MARGIN = 16;             // window starts a little before the first needed value
 constexpr int TRK_THREADS = 256;
 constexpr int TRK_REC_CAP = 128;
@@ -80,7 +84,9 @@ __global__ void __launch_bounds__(TPLAN_WARPS * 32) trk_plan_kernel(TrkPlanParam
             il = P.tab.ilens[vi];
             kp = has_keep ? (P.keep[keep_base + i] != 0) : true;
         }
-        unsigned mask = __ballot_sync(0xffffffffu, kp);
+        // once the shift is consumed a SNP (ilen 0) changes nothing (src/tracks/mod.rs:277-314: skipped or
+        // "writes nothing"), so only indels take a serial step
+        unsigned mask = __ballot_sync(0xffffffffu, kp && (il != 0 || ts.shifted < ts.shift));
         while (mask && !done) {
             int t = __ffs(mask) - 1;
             mask &= mask - 1;
@@ -178,7 +184,7 @@ __global__ void paint_plan_kernel(int64_t n, const int32_t *__restrict__ starts,
     row_len[q] = (int32_t)length;
 }
 
-// tile map for TRK_TILE-sized tiles (same scan as the haplotype path, different tile size)
+// tile map for TRK_SEG-sized segments (same scan as the haplotype path, different tile size)
 __global__ void __launch_bounds__(1024) trk_tile_scan_kernel(int64_t n_work, const int32_t *__restrict__ row_len,
                                                              int64_t *tile_off) {
     __shared__ int64_t s_tile[32];
@@ -188,7 +194,7 @@ __global__ void __launch_bounds__(1024) trk_tile_scan_kernel(int64_t n_work, con
     __syncthreads();
     for (int64_t base = 0; base < n_work; base += 1024) {
         int64_t k = base + tid;
-        int64_t til = (k < n_work) ? ((int64_t)row_len[k] + TRK_TILE - 1) / TRK_TILE : 0;
+        int64_t til = (k < n_work) ? ((int64_t)row_len[k] + TRK_SEG - 1) / TRK_SEG : 0;
         int64_t x = til;
         for (int o = 1; o < 32; o <<= 1) {
             int64_t y = __shfl_up_sync(0xffffffffu, x, o);
@@ -328,9 +334,12 @@ __device__ float insertion_fill_value(const TrkSrc &S, int strategy, double para
     }
 }
 
-__global__ void __launch_bounds__(TRK_THREADS) trk_exec_kernel(TrkExecParams P) {
+__global__ void __launch_bounds__(TRK_THREADS, 4) trk_exec_kernel(TrkExecParams P) {
     __shared__ TrkTileRecs S;
     __shared__ float s_win[TRK_WIN];
+    __shared__ uint32_t s_flag[TRK_WIN / 32 + 4];  // positions of s_win that hold a run start (interval start / end)
+    __shared__ float s_cval[TRK_THREADS / 32];
+    __shared__ int s_chas[TRK_THREADS / 32];
     __shared__ int64_t s_lo, s_hi, s_itv_first;
 
     const int64_t track = blockIdx.x / P.grid_per_track;
@@ -348,9 +357,9 @@ __global__ void __launch_bounds__(TRK_THREADS) trk_exec_kernel(TrkExecParams P) 
     const int64_t tile = b - P.tile_off[row];
     const RowPlan rp = P.rows[row];
     const int32_t L = rp.length;
-    const int32_t t0 = (int32_t)(tile * TRK_TILE);
+    const int32_t t0 = (int32_t)(tile * TRK_SEG);
     if (t0 >= L) return;
-    const int32_t t1 = min(t0 + TRK_TILE, L);
+    const int32_t t1 = (int32_t)imin64((int64_t)t0 + TRK_SEG, L);
     const bool rc = rp.rc != 0;
     const int32_t h0 = rc ? L - t1 : t0;
     const int32_t h1 = rc ? L - t0 : t1;
@@ -374,8 +383,31 @@ __global__ void __launch_bounds__(TRK_THREADS) trk_exec_kernel(TrkExecParams P) 
 
     const int32_t *__restrict__ ra = P.rec.a + rp.rec_off;
     if (threadIdx.x < 32) {
-        int64_t r_lo = warp_upper_le(ra, 0, rp.n_rec, h0);
-        int64_t r_hi = warp_upper_le(ra, imax64(r_lo, 0), rp.n_rec, h1 - 1) + 1;
+        // r_lo = last record with a <= h0 (or -1), r_hi = first with a >= h1: counts over the sorted array,
+        // 8 independent loads per lane and round trip
+        const int lane = threadIdx.x;
+        int64_t r_lo, r_hi;
+        if (rp.n_rec <= 2048) {
+            int c0 = 0, c1 = 0;
+            for (int i0 = 0; i0 < rp.n_rec; i0 += 256) {
+                int32_t a[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int i = i0 + 32 * u + lane;
+                    a[u] = i < rp.n_rec ? ra[i] : INT32_MAX;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    c0 += (a[u] <= h0);
+                    c1 += (a[u] < h1);
+                }
+            }
+            r_lo = (int64_t)__reduce_add_sync(0xffffffffu, c0) - 1;
+            r_hi = __reduce_add_sync(0xffffffffu, c1);
+        } else {
+            r_lo = warp_upper_le(ra, 0, rp.n_rec, h0);
+            r_hi = warp_upper_le(ra, imax64(r_lo, 0), rp.n_rec, h1 - 1) + 1;
+        }
         if (threadIdx.x == 0) {
             s_lo = r_lo;
             s_hi = r_hi;
@@ -385,11 +417,19 @@ __global__ void __launch_bounds__(TRK_THREADS) trk_exec_kernel(TrkExecParams P) 
     const int64_t r_hi = s_hi;
     int64_t r = s_lo;
     int32_t cur = h0;
+    int64_t itv_prev = -1;  // first interval of the previous pass's window (-1: none yet)
+    int32_t tgt_prev = INT32_MIN;
 
     while (cur < h1) {
         const int m_new = (int)imin64(TRK_REC_CAP - 1, r_hi - (r + 1));
         const int m = m_new + 1;
-        const int32_t seg_end = (r + 1 + m_new < r_hi) ? ra[r + 1 + m_new] : h1;
+        const int32_t seg_end_rec = (r + 1 + m_new < r_hi) ? ra[r + 1 + m_new] : h1;
+        // a pass ends at the first unstaged record, after TRK_TILE values (one source window), or at the segment end
+        const int32_t seg_end = (int32_t)imin64(seg_end_rec, (int64_t)cur + TRK_TILE);
+        if (seg_end <= cur) {  // (only with > 127 records at one position: skip them, nothing to write)
+            r += m_new;
+            continue;
+        }
         __syncthreads();
         for (int i = threadIdx.x; i < m; i += TRK_THREADS) {
             int64_t idx = r + i;
@@ -424,35 +464,159 @@ __global__ void __launch_bounds__(TRK_THREADS) trk_exec_kernel(TrkExecParams P) 
         if (T.dense) {
             for (int64_t i = threadIdx.x; i < w1 - w0; i += TRK_THREADS) s_win[i] = T.dense[itv_lo + w0 + i];
         } else {
-            for (int i = threadIdx.x; i < TRK_WIN; i += TRK_THREADS) s_win[i] = 0.0f;
+            for (int i = threadIdx.x; i < TRK_WIN / 32 + 4; i += TRK_THREADS) s_flag[i] = 0u;
         }
         if (!T.dense && threadIdx.x < 32) {
-            // first interval whose end is > q_start + w0  (ends are sorted: intervals do not overlap)
-            int64_t first = warp_upper_le(T.itv_ends, itv_lo, itv_hi, (int32_t)imin64(q_start + w0, INT32_MAX)) + 1;
+            // first interval whose end is > q_start + w0  (ends are sorted: intervals do not overlap).  The first pass
+            // searches the slot; later passes (the window only moves forward) count over the next 256 ends.
+            const int32_t target = (int32_t)imin64(q_start + w0, INT32_MAX);
+            int64_t first;
+            if (itv_prev < 0 || target < tgt_prev) {  // (unsorted lists can move the window backwards)
+                first = warp_upper_le(T.itv_ends, itv_lo, itv_hi, target) + 1;
+            } else {
+                int cnt = 0;
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int64_t it = itv_prev + 32 * u + threadIdx.x;
+                    cnt += (it < itv_hi && T.itv_ends[it] <= target) ? 1 : 0;
+                }
+                cnt = __reduce_add_sync(0xffffffffu, cnt);
+                first = itv_prev + cnt;
+                if (cnt == 256) first = warp_upper_le(T.itv_ends, first, itv_hi, target) + 1;
+            }
             if (threadIdx.x == 0) s_itv_first = first;
         }
         __syncthreads();
         if (!T.dense && w1 > w0) {
-            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-            for (int64_t it = s_itv_first + warp; it < itv_hi; it += TRK_THREADS / 32) {
-                const int64_t s = (int64_t)T.itv_starts[it] - q_start;
-                if (s >= w1) break;  // sorted starts (also covers src/intervals.rs:72-76: start >= length)
-                const int64_t e = (int64_t)T.itv_ends[it] - q_start;
-                const float v = T.itv_values[it];
-                const int64_t ps = imax64(s, w0), pe = imin64(e, w1);
-                for (int64_t x = ps + lane; x < pe; x += 32) s_win[x - w0] = v;
+            // Paint the window as a run-length expansion (src/intervals.rs:19-126 restated for one window):
+            //  1. every thread fetches ONE interval (coalesced) and drops two markers: 0 at its end, its value at
+            //     its (clipped) start -- ends first, so that an adjacent interval's start wins;
+            //  2. every thread then owns 37 consecutive window positions (odd stride: no bank conflicts), finds the
+            //     value in effect at its first position with a block-wide scan over "last marker" pairs, and fills.
+            const int nwin = (int)(w1 - w0);
+            for (int64_t base = s_itv_first; base < itv_hi; base += TRK_THREADS) {
+                const int64_t it = base + threadIdx.x;
+                int64_t st_ = INT64_MAX, en_ = 0;
+                float v_ = 0.0f;
+                if (it < itv_hi) {
+                    st_ = (int64_t)T.itv_starts[it] - q_start;
+                    en_ = (int64_t)T.itv_ends[it] - q_start;
+                    v_ = T.itv_values[it];
+                }
+                const bool live = st_ < w1 && en_ > w0 && en_ > st_;  // overlaps the window (also :72-76: start >= length)
+                if (live && en_ < w1) {
+                    const int x = (int)(en_ - w0);
+                    s_win[x] = 0.0f;
+                    atomicOr(&s_flag[x >> 5], 1u << (x & 31));
+                }
+                __syncthreads();
+                if (live) {
+                    const int x = (int)(imax64(st_, w0) - w0);
+                    s_win[x] = v_;
+                    atomicOr(&s_flag[x >> 5], 1u << (x & 31));
+                }
+                // the block stops once its LAST interval starts at or beyond the window end (sorted starts)
+                if (__syncthreads_or(threadIdx.x == TRK_THREADS - 1 && st_ >= w1)) break;
+            }
+            __syncthreads();
+            constexpr int CH = 37;
+            static_assert(CH * TRK_THREADS >= TRK_WIN, "fill chunks must cover the window");
+            const int b0 = CH * (int)threadIdx.x;
+            uint64_t mk = 0;  // marker bits of positions b0 .. b0 + 36
+            if (b0 < nwin) {
+                const int w = b0 >> 5, sft = b0 & 31;
+                mk = (((uint64_t)s_flag[w + 1] << 32) | s_flag[w]) >> sft;
+                if (sft) mk |= (uint64_t)s_flag[w + 2] << (64 - sft);
+                mk &= (1ull << CH) - 1;
+            }
+            // (has, value) of the last marker in the chunk; scan with "right operand wins if it has one"
+            int has = mk != 0;
+            float val = has ? s_win[b0 + 63 - __clzll((long long)mk)] : 0.0f;
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            int h_in = has;
+            float v_in = val;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int h2 = __shfl_up_sync(0xffffffffu, h_in, o);
+                const float v2 = __shfl_up_sync(0xffffffffu, v_in, o);
+                if (lane >= o && !h_in) {
+                    h_in = h2;
+                    v_in = v2;
+                }
+            }
+            if (lane == 31) {
+                s_chas[warp] = h_in;
+                s_cval[warp] = v_in;
+            }
+            int h_ex = __shfl_up_sync(0xffffffffu, h_in, 1);
+            float v_ex = __shfl_up_sync(0xffffffffu, v_in, 1);
+            if (lane == 0) h_ex = 0;
+            __syncthreads();
+            float carry = 0.0f;  // no marker before: nothing covers the window start
+            int found = h_ex;
+            if (found) carry = v_ex;
+            for (int w = warp - 1; w >= 0 && !found; w--) {
+                if (s_chas[w]) {
+                    carry = s_cval[w];
+                    found = 1;
+                }
+            }
+            if (b0 < nwin) {
+                const int n_ = min(CH, nwin - b0);
+                float cur_v = carry;
+                int i = 0;
+                while (i < n_) {  // runs between markers
+                    const uint64_t rest = mk >> i;
+                    const int nxt = rest ? min(n_, i + (__ffsll((long long)rest) - 1)) : n_;
+                    for (; i < nxt; i++) s_win[b0 + i] = cur_v;
+                    if (i < n_) cur_v = s_win[b0 + i++];
+                }
             }
         }
         __syncthreads();
+        itv_prev = T.dense ? -1 : s_itv_first;
+        tgt_prev = (int32_t)imin64(q_start + w0, INT32_MAX);
         TrkSrc src{s_win, w0, w1, track_n, &T, itv_lo, itv_hi, q_start};
 
         const int32_t jo_lo = rc ? L - seg_end : cur;
         const int32_t jo_hi = rc ? L - cur : seg_end;
         const int64_t g0 = (row_base + jo_lo) & ~(int64_t)3;
         const int32_t n_chunks = (int32_t)((row_base + jo_hi - g0 + 3) >> 2);
-        for (int32_t c = threadIdx.x; c < n_chunks; c += TRK_THREADS) {
+        // a GROUP is 32 chunks of 4 values (one chunk per lane); warp w owns groups w, w+8, ...  A group that lies
+        // inside ONE reference span and inside the staged window is a straight (possibly reversed) copy out of
+        // shared memory; everything else resolves each value against the records.
+        const int warp_ = threadIdx.x >> 5, lane_ = threadIdx.x & 31;
+        const int32_t n_groups = (n_chunks + 31) >> 5;
+        int ic = rc ? (m - 1) : 0;  // warp-uniform record cursor (groups are visited in monotone order)
+        for (int32_t grp = warp_; grp < n_groups; grp += TRK_THREADS / 32) {
+            const int32_t c = grp * 32 + lane_;
             const int64_t g = g0 + 4 * (int64_t)c;
             const int32_t j = (int32_t)(g - row_base);
+            const int32_t jg = (int32_t)(g0 + 128 * (int64_t)grp - row_base);
+            if (jg >= jo_lo && jg + 128 <= jo_hi) {
+                const int32_t p_lo = rc ? (L - 128 - jg) : jg;  // lowest haplotype position of the group
+                if (!rc) {
+                    while (S.a[ic + 1] <= p_lo) ic++;
+                } else {
+                    while (S.a[ic] > p_lo) ic--;
+                }
+                const int32_t e_i = S.e[ic];
+                const int64_t tp_lo = (int64_t)S.resume[ic] + (p_lo - e_i);
+                if (p_lo >= e_i && p_lo + 128 <= S.a[ic + 1] && tp_lo >= w0 && tp_lo + 128 <= w1) {
+                    const float *ws = s_win + (tp_lo - w0);
+                    float4 o;
+                    if (!rc) {
+                        ws += 4 * lane_;
+                        o = make_float4(ws[0], ws[1], ws[2], ws[3]);
+                    } else {
+                        ws += 124 - 4 * lane_;
+                        o = make_float4(ws[3], ws[2], ws[1], ws[0]);
+                    }
+                    *reinterpret_cast<float4 *>(out + g) = o;
+                    continue;
+                }
+            }
+            if (c >= n_chunks) continue;
             float vals[4];
             bool valid[4];
             int i = 0;
@@ -495,8 +659,16 @@ __global__ void __launch_bounds__(TRK_THREADS) trk_exec_kernel(TrkExecParams P) 
                     if (valid[q]) out[g + q] = vals[q];
             }
         }
+        // records consumed by this pass: staged entries 1..m_new with a < seg_end (the rest are staged again)
+        {
+            int lo = 0, hi = m;  // last staged entry with a < seg_end
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (S.a[mid] < seg_end) lo = mid; else hi = mid;
+            }
+            r += lo;
+        }
         cur = seg_end;
-        r += m_new;
     }
 }
 
@@ -523,7 +695,7 @@ static int launch_trk_exec(gvl_ctx *ctx, int64_t n_work, int64_t ploidy, int64_t
     P.tile_off = ctx->trk.tile_off;
     P.n_work = n_work;
     P.ploidy = ploidy;
-    P.grid_per_track = total_per_track / TRK_TILE + n_work;
+    P.grid_per_track = total_per_track / TRK_SEG + n_work;
     P.total_per_track = total_per_track;
     P.offset_idxs = offset_idxs;
     P.n_queries = n_queries;

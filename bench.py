@@ -46,6 +46,9 @@ WORKLOADS = {
                  contig_len=50_000_000, n_samples=2504, n_regions=16, window=131_072, pairs=32, vkb=1.0),
     "cfg3": dict(desc="configs[2] (haplotype part): 524,288-bp indel-bearing windows, 32 haplotypes/batch, 50% negative strand",
                  contig_len=20_000_000, n_samples=16, n_regions=16, window=524_288, pairs=16, vkb=1.0, neg=0.5),
+    "cfg3t": dict(desc="configs[2]: 524,288-bp indel-bearing windows, 32 haplotypes/batch, 50% negative strand, PLUS 2 realigned "
+                       "float tracks per haplotype (intervals with a mean run of 50 bp; fills Repeat5p and Interpolate(1))",
+                  contig_len=20_000_000, n_samples=16, n_regions=16, window=524_288, pairs=16, vkb=1.0, neg=0.5, tracks=2),
     "cfg4": dict(desc="configs[3] (one-hot instead of annotated): 6,144-bp windows, 4,096 haplotypes/batch",
                  contig_len=5_000_000, n_samples=64, n_regions=512, window=6_144, pairs=2048, vkb=1.0),
 }
@@ -56,7 +59,7 @@ def build_workload(name: str, seed: int):
 
     w = WORKLOADS[name]
     d = synth.make_dataset(seed, w["contig_len"], w["n_samples"], w["n_regions"], w["window"], w["vkb"],
-                           neg_strand_frac=w.get("neg", 0.0), straddle_ends=False)
+                           neg_strand_frac=w.get("neg", 0.0), straddle_ends=False, n_tracks=w.get("tracks", 0))
     return w, d
 
 
@@ -73,10 +76,10 @@ def make_batches(d, w, n_batches: int, seed: int, rank: int = 0, world: int = 1)
         lo, hi = shard_bounds(w["pairs"] * world, rank, world)
         r_idx = rng.integers(0, d.n_regions, w["pairs"] * world)[lo:hi]
         s_idx = rng.integers(0, d.n_samples, w["pairs"] * world)[lo:hi]
-        regions, goi, to_rc, _ = synth.batch_args(d, r_idx, s_idx)
+        regions, goi, to_rc, ds_idx = synth.batch_args(d, r_idx, s_idx)
         shifts = np.zeros(goi.shape, np.int32)
         nvar = int((d.geno_offsets[1, goi.ravel()] - d.geno_offsets[0, goi.ravel()]).sum())
-        out.append(dict(regions=regions, goi=goi, to_rc=to_rc, shifts=shifts, nvar=nvar))
+        out.append(dict(regions=regions, goi=goi, to_rc=to_rc, shifts=shifts, nvar=nvar, ds_idx=ds_idx))
     return out
 
 
@@ -141,6 +144,11 @@ def measured_peak_gbs() -> tuple[float, str]:
 def alg_bytes(w, nvar: int) -> float:
     rows = w["pairs"] * 2
     return rows * w["window"] * ALG_BYTES_PER_BP + nvar * ALG_BYTES_PER_VARIANT + rows * ALG_BYTES_PER_ROW
+
+
+def track_bytes(w) -> float:
+    """4 B per realigned value written (the intervals read add 12 B each, not counted)."""
+    return 4.0 * w.get("tracks", 0) * w["pairs"] * 2 * w["window"]
 
 
 # ----------------------------------------------------------------------------------------------
@@ -232,6 +240,9 @@ def run_b200(args):
     eng0 = Engine(dev, d.reference, d.ref_offsets, d.v_starts, d.ilens, d.alt_alleles, d.alt_offsets, d.geno_v_idxs,
                   d.geno_offsets)
     step_bytes_out = rows * L * 4
+    track_names = sorted(d.tracks)
+    for nm in track_names:
+        eng0.add_track(nm, *d.tracks[nm])
 
     # ---- per-batch device inputs + output ring (ring > L2 so writes cannot stay cache-resident) ----
     streams = [torch.cuda.Stream(dev) for _ in range(max(1, n_slots))]
@@ -243,11 +254,19 @@ def run_b200(args):
                  goi=torch.from_numpy(b["goi"]).to(dev), to_rc=torch.from_numpy(b["to_rc"]).to(dev),
                  out_offsets=torch.empty(rows + 1, dtype=torch.int64, device=dev),
                  out=torch.empty(step_bytes_out, dtype=torch.uint8, device=dev), nvar=b["nvar"], graph=None)
+        if track_names:  # realigned tracks of the same batch: (n_tracks, rows, L) float32
+            s["oidx"] = torch.from_numpy(np.tile(b["ds_idx"], (len(track_names), 1))).to(dev)
+            s["tlen"] = torch.full((b["regions"].shape[0],), L + 4096, dtype=torch.int32, device=dev)  # window + room for deletions
+            s["tout"] = torch.empty(len(track_names) * rows * L, dtype=torch.float32, device=dev)
         slots.append(s)
 
     def step(s):
         s["eng"].plan(s["regions"], s["shifts"], s["goi"], L, s["nvar"], to_rc=s["to_rc"], out_offsets=s["out_offsets"])
         s["eng"].execute("onehot", out=s["out"])
+        if track_names:
+            s["eng"].realign_tracks(track_names, s["regions"], s["shifts"], s["goi"], s["oidx"], s["tlen"], s["out_offsets"],
+                                    rows * L, [0, 4][: len(track_names)], [0.0, 1.0][: len(track_names)], 7, s["nvar"],
+                                    to_rc=s["to_rc"], out=s["tout"])
 
     # warm every slot once outside any capture (workspace growth may allocate)
     for s in slots:
@@ -435,7 +454,7 @@ def run_b200(args):
         del flush
         ab = alg_bytes(w, s["nvar"])
         achieved = ab / (exec_ms * 1e-3) / 1e9
-        step_achieved = ab * args.steps / (ms * 1e-3) / 1e9  # per GPU (every rank runs `steps` steps of its shard)
+        step_achieved = (ab + track_bytes(w)) * args.steps / (ms * 1e-3) / 1e9  # per GPU (every rank runs `steps` steps of its shard)
         traffic = None
         tp = ROOT / "profiles" / "ncu_exec_traffic.json"
         if tp.exists():
@@ -478,7 +497,8 @@ def run_b200(args):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {w['desc']}", "window_bp": L, "haplotypes_per_batch": rows,
-                       "variants_per_batch": s["nvar"], "output": "uint8 one-hot (L,4)", "source": "SVAR1-style sparse CSR",
+                       "variants_per_batch": s["nvar"],
+                       "output": "uint8 one-hot (L,4)" + (f" + {len(track_names)} float32 tracks (n_tracks, rows, L)" if track_names else ""), "source": "SVAR1-style sparse CSR",
                        "batches_in_flight": n_slots, "cuda_graph": use_graph,
                        "l2": f"ring of {len(slots)} distinct batches/outputs = {len(slots) * step_bytes_out >> 20} MiB written per cycle "
                              "(> 126 MB L2); roofline launches are preceded by a 512 MiB L2 flush",

@@ -247,7 +247,8 @@ struct TrkExecParams {
     const int64_t *query_seed;   // optional [n_queries]
     uint64_t base_seed;
     float *out;
-    const TrkDesc *tracks;       // device array [n_tracks]
+    const TrkDesc *tracks;       // device array [n_tracks], or NULL: the descriptors travel in `inl`
+    TrkDesc inl[8];              // (kernel parameters are captured by value: CUDA-graph safe)
 };
 
 struct TrkTileRecs {
@@ -366,7 +367,7 @@ __global__ void __launch_bounds__(TRK_THREADS, 4) trk_exec_kernel(TrkExecParams 
     const int64_t query = row / P.ploidy;
     const uint64_t hap = (uint64_t)(row % P.ploidy);
     const uint64_t qseed = P.query_seed ? (uint64_t)P.query_seed[query] : (uint64_t)query;
-    const TrkDesc T = P.tracks[track];
+    const TrkDesc T = P.tracks ? P.tracks[track] : P.inl[track];
     int64_t itv_lo, itv_hi;
     if (T.dense) {
         itv_lo = T.dense_offsets[query];
@@ -685,8 +686,11 @@ static int launch_trk_exec(gvl_ctx *ctx, int64_t n_work, int64_t ploidy, int64_t
                            const int64_t *query_seed, uint64_t base_seed, float *out, cudaStream_t st) {
     if (n_tracks > MAX_TRACKS) return fail(GVL_ERR_ARG, "at most %d tracks per call", MAX_TRACKS);
     static_assert(sizeof(TrkDesc) * MAX_TRACKS <= GVL_TRK_DESC_BYTES, "descriptor buffer too small");
-    TrkDesc *d_desc = reinterpret_cast<TrkDesc *>(ctx->trk_desc);
-    GVL_CUDA(cudaMemcpyAsync(d_desc, host_desc, sizeof(TrkDesc) * (size_t)n_tracks, cudaMemcpyHostToDevice, st));
+    TrkDesc *d_desc = nullptr;
+    if (n_tracks > 8) {  // (not CUDA-graph safe: the copy reads the caller's host array at replay time)
+        d_desc = reinterpret_cast<TrkDesc *>(ctx->trk_desc);
+        GVL_CUDA(cudaMemcpyAsync(d_desc, host_desc, sizeof(TrkDesc) * (size_t)n_tracks, cudaMemcpyHostToDevice, st));
+    }
     trk_tile_scan_kernel<<<1, 1024, 0, st>>>(n_work, ctx->trk.row_len, ctx->trk.tile_off);
     GVL_LAUNCH_CHECK();
     TrkExecParams P;
@@ -703,6 +707,8 @@ static int launch_trk_exec(gvl_ctx *ctx, int64_t n_work, int64_t ploidy, int64_t
     P.base_seed = base_seed;
     P.out = out;
     P.tracks = d_desc;
+    if (!d_desc)
+        for (int64_t t = 0; t < n_tracks; t++) P.inl[t] = host_desc[t];
     const int64_t grid = P.grid_per_track * n_tracks;
     if (grid > INT32_MAX) return fail(GVL_ERR_ARG, "too many track tiles");
     trk_exec_kernel<<<(unsigned)grid, TRK_THREADS, 0, st>>>(P);

@@ -222,6 +222,27 @@ def shift_and_realign_tracks_sparse(out, out_offsets, regions, shifts, geno_offs
         c_i64(int(strategy_id)), c_u64(int(base_seed))))
 
 
+def shift_and_realign_tracks_from_svar2(out, out_offsets, regions, shifts, vk_pos, vk_key, vk_off, dense_pos, dense_key,
+                                        dense_range, dense_present, dense_present_off, key_ilen, tracks, track_offsets,
+                                        params, strategy_id=0, base_seed=0, query_seed=None, parallel=True, *, ctx=None):
+    """src/tracks/mod.rs:705-856 (the core behind src/ffi/mod.rs:1836-1960): dense f32 source windows realigned with the
+    svar2 two-channel variant source; ``key_ilen`` is the decoded key table.  Writes ``out`` in place; rows are sized
+    by ``out_offsets`` (the offsets `reconstruct_haplotypes_from_svar2(..., output_length=-1)` returns)."""
+    ctx = ctx or default_ctx()
+    assert out.dtype == np.float32 and out.flags.c_contiguous
+    oo, rg, sh = _c(out_offsets, np.int64), _c(regions, np.int32), _c(shifts, np.int32)
+    batch, ploidy = sh.shape
+    vp, vk, vo = _c(vk_pos, np.int32), _c(vk_key, np.int32), _c(vk_off, np.int64)
+    dp, dk, dr = _c(dense_pos, np.int32), _c(dense_key, np.int32), _c(dense_range, np.int32)
+    db, do_, ki = _c(dense_present, np.uint8), _c(dense_present_off, np.int64), _c(key_ilen, np.int32)
+    tr, to, pa = _c(tracks, np.float32), _c(track_offsets, np.int64), _c(params, np.float64)
+    qs = _c(query_seed, np.int64)
+    check(lib.gvl_shift_and_realign_tracks_from_svar2(
+        ctx.handle, _p(out), _p(oo), _p(rg), _p(sh), c_i64(batch), c_i64(ploidy), _p(vp), _p(vk), _p(vo), _p(dp), _p(dk),
+        c_i64(dp.size), _p(dr), _p(db), _p(do_), _p(ki), c_i64(ki.size), _p(tr), _p(to), _p(pa), c_i64(int(strategy_id)),
+        c_u64(int(base_seed)), _p(qs)))
+
+
 def intervals_and_realign_track_fused(out, out_offsets, regions, shifts, geno_offset_idx, geno_v_idxs, geno_offsets,
                                       v_starts, ilens, offset_idxs, itv_starts, itv_ends, itv_values, itv_offsets,
                                       track_offsets, params, strategy_id, base_seed, keep=None, keep_offsets=None,

@@ -944,8 +944,8 @@ static int64_t exec_capacity_oh(gvl_ctx *ctx) {
 }
 
 // Merge of the svar2 two-channel source (gvl_svar2.cu); fills ctx->hap.m_* for n_work rows.
-int gvl_svar2_merge_launch(gvl_ctx *ctx, const gvl_svar2_channels *ch, int64_t batch, int64_t ploidy, int64_t max_merged,
-                           cudaStream_t st);
+int gvl_svar2_merge_launch(gvl_ctx *ctx, gvl_workspace *ws, int64_t *words, const gvl_svar2_channels *ch, int64_t batch,
+                           int64_t ploidy, int64_t max_merged, cudaStream_t st);
 
 static int hap_plan_impl(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_svar2_channels *svar2,
                          const int32_t *regions, const int32_t *shifts, const int64_t *geno_offset_idx, int64_t batch,
@@ -978,7 +978,7 @@ static int hap_plan_impl(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_s
     P.merged = MergedLists{nullptr, nullptr, nullptr, nullptr};
     if (svar2) {
         if ((rc = ensure_merged(ctx, ctx->hap, max_records))) return rc;
-        if ((rc = gvl_svar2_merge_launch(ctx, svar2, batch, ploidy, max_records, st))) return rc;
+        if ((rc = gvl_svar2_merge_launch(ctx, &ctx->hap, ctx->dev_words, svar2, batch, ploidy, max_records, st))) return rc;
         P.merged = MergedLists{ctx->hap.m_pos, ctx->hap.m_key, ctx->hap.m_off, ctx->hap.m_len};
     }
     P.regions = regions;

@@ -548,6 +548,74 @@ int gvl_shift_and_realign_tracks_sparse(
     return gvl_ctx_check(ctx, ctx->own_stream);
 }
 
+int gvl_shift_and_realign_tracks_from_svar2(
+    gvl_ctx *ctx, float *out, const int64_t *out_offsets, const int32_t *regions, const int32_t *shifts, int64_t batch,
+    int64_t ploidy, const int32_t *vk_pos, const int32_t *vk_key, const int64_t *vk_off, const int32_t *dense_pos,
+    const int32_t *dense_key, int64_t n_dense, const int32_t *dense_range, const uint8_t *dense_present,
+    const int64_t *dense_present_off, const int32_t *key_ilen, int64_t n_keys, const float *tracks,
+    const int64_t *track_offsets, const double *params, int64_t strategy_id, uint64_t base_seed,
+    const int64_t *query_seed) {
+    if (!ctx || !out_offsets || !regions || !shifts || !vk_off || !dense_range || !dense_present_off || !key_ilen ||
+        !track_offsets || !params)
+        return fail(GVL_ERR_ARG, "gvl_shift_and_realign_tracks_from_svar2: NULL argument");
+    GVL_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    const int64_t n_work = batch * ploidy;
+    const int64_t total = out_offsets[n_work];
+    if (n_work == 0 || total == 0) return GVL_OK;
+    if (!out || !tracks) return fail(GVL_ERR_ARG, "gvl_shift_and_realign_tracks_from_svar2: NULL buffer");
+    const void *d;
+    gvl_sparse_tables t;
+    memset(&t, 0, sizeof(t));
+    if ((rc = static_dev(ctx, key_ilen, sizeof(int32_t) * n_keys, 11, &d))) return rc;
+    t.ilens = (const int32_t *)d;
+    t.v_starts = t.ilens;  // unused by the merged-list source
+    t.n_variants = n_keys;
+    gvl_svar2_channels ch;
+    if ((rc = static_dev(ctx, dense_pos, sizeof(int32_t) * n_dense, 16, &d))) return rc;
+    ch.dense_pos = (const int32_t *)d;
+    if ((rc = static_dev(ctx, dense_key, sizeof(int32_t) * n_dense, 17, &d))) return rc;
+    ch.dense_key = (const int32_t *)d;
+    const void *d_tracks;
+    if ((rc = static_dev(ctx, tracks, sizeof(float) * track_offsets[batch], 18, &d_tracks))) return rc;
+    const int64_t n_vk = vk_off[n_work];
+    const int64_t n_bits = dense_present_off[n_work];
+    int64_t max_merged = n_vk;
+    for (int64_t q = 0; q < batch; q++)
+        max_merged += ploidy * (int64_t)(dense_range[2 * q + 1] - dense_range[2 * q] > 0 ? dense_range[2 * q + 1] - dense_range[2 * q] : 0);
+    std::vector<int32_t> tl((size_t)batch);
+    for (int64_t q = 0; q < batch; q++) tl[q] = (int32_t)(track_offsets[q + 1] - track_offsets[q]);
+    Packer pk;
+    size_t i_reg = pk.add(regions, sizeof(int32_t) * 3 * batch);
+    size_t i_sh = pk.add(shifts, sizeof(int32_t) * n_work);
+    size_t i_vp = pk.add(vk_pos ? (const void *)vk_pos : (const void *)vk_off, sizeof(int32_t) * n_vk);
+    size_t i_vkk = pk.add(vk_key ? (const void *)vk_key : (const void *)vk_off, sizeof(int32_t) * n_vk);
+    size_t i_vo = pk.add(vk_off, sizeof(int64_t) * (n_work + 1));
+    size_t i_dr = pk.add(dense_range, sizeof(int32_t) * 2 * batch);
+    size_t i_dp = pk.add(dense_present ? (const void *)dense_present : (const void *)vk_off, (n_bits + 7) / 8);
+    size_t i_do = pk.add(dense_present_off, sizeof(int64_t) * (n_work + 1));
+    size_t i_to = pk.add(track_offsets, sizeof(int64_t) * (batch + 1));
+    size_t i_tl = pk.add(tl.data(), sizeof(int32_t) * batch);
+    size_t i_oo = pk.add(out_offsets, sizeof(int64_t) * (n_work + 1));
+    size_t i_qs = pk.add(query_seed, sizeof(int64_t) * batch);
+    if ((rc = pk.upload(ctx, 0))) return rc;
+    ch.vk_pos = pk.ptr<int32_t>(i_vp);
+    ch.vk_key = pk.ptr<int32_t>(i_vkk);
+    ch.vk_off = pk.ptr<int64_t>(i_vo);
+    ch.dense_range = pk.ptr<int32_t>(i_dr);
+    ch.dense_present = pk.ptr<uint8_t>(i_dp);
+    ch.dense_present_off = pk.ptr<int64_t>(i_do);
+    void *d_out;
+    if ((rc = scratch(ctx, 2, total * 4, &d_out))) return rc;
+    if ((rc = gvl_dev_shift_and_realign_tracks_svar2(
+             ctx, &t, &ch, pk.ptr<int32_t>(i_reg), pk.ptr<int32_t>(i_sh), batch, ploidy, nullptr, (const float *)d_tracks,
+             pk.ptr<int64_t>(i_to), pk.ptr<int32_t>(i_tl), pk.ptr<int64_t>(i_oo), total, (int32_t)strategy_id, params[0],
+             base_seed, query_seed ? pk.ptr<int64_t>(i_qs) : nullptr, max_merged, (float *)d_out, ctx->own_stream)))
+        return rc;
+    GVL_CUDA(cudaMemcpyAsync(out, d_out, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->own_stream));
+    return gvl_ctx_check(ctx, ctx->own_stream);
+}
+
 int gvl_intervals_to_tracks(gvl_ctx *ctx, const int64_t *offset_idxs, const int32_t *starts, int64_t n_queries,
                             const int32_t *itv_starts, const int32_t *itv_ends, const float *itv_values,
                             int64_t n_itv, const int64_t *itv_offsets, int64_t n_slots, float *out,

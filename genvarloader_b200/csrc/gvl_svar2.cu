@@ -104,20 +104,21 @@ __global__ void __launch_bounds__(MERGE_WARPS * 32) svar2_merge_kernel(MergePara
 
 using namespace gvl;
 
-int gvl_svar2_merge_launch(gvl_ctx *ctx, const gvl_svar2_channels *ch, int64_t batch, int64_t ploidy, int64_t max_merged,
-                           cudaStream_t st) {
+int gvl_svar2_merge_launch(gvl_ctx *ctx, gvl_workspace *ws, int64_t *words, const gvl_svar2_channels *ch, int64_t batch,
+                           int64_t ploidy, int64_t max_merged, cudaStream_t st) {
+    (void)ctx;
     const int64_t n_work = batch * ploidy;
     if (n_work == 0) return GVL_OK;
     MergeParams P;
     P.ch = *ch;
     P.n_work = n_work;
     P.ploidy = ploidy;
-    P.cap = ctx->hap.m_cap;
-    P.m_pos = ctx->hap.m_pos;
-    P.m_key = ctx->hap.m_key;
-    P.m_off = ctx->hap.m_off;
-    P.m_len = ctx->hap.m_len;
-    P.words = ctx->dev_words;
+    P.cap = ws->m_cap;
+    P.m_pos = ws->m_pos;
+    P.m_key = ws->m_key;
+    P.m_off = ws->m_off;
+    P.m_len = ws->m_len;
+    P.words = words;
     (void)max_merged;
     svar2_merge_kernel<<<(unsigned)((n_work + MERGE_WARPS - 1) / MERGE_WARPS), MERGE_WARPS * 32, 0, st>>>(P);
     GVL_LAUNCH_CHECK();

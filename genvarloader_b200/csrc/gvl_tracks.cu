@@ -716,9 +716,13 @@ static int launch_trk_exec(gvl_ctx *ctx, int64_t n_work, int64_t ploidy, int64_t
     return GVL_OK;
 }
 
+// svar2 two-channel merge (gvl_svar2.cu)
+int gvl_svar2_merge_launch(gvl_ctx *ctx, gvl_workspace *ws, int64_t *words, const gvl_svar2_channels *ch, int64_t batch,
+                           int64_t ploidy, int64_t max_merged, cudaStream_t st);
+
 extern "C" {
 
-static int realign_impl(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_t *regions,
+static int realign_impl(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_svar2_channels *svar2, const int32_t *regions,
                         const int32_t *shifts, const int64_t *geno_offset_idx, int64_t batch, int64_t ploidy,
                         const uint8_t *keep, const int64_t *keep_offsets, const uint8_t *to_rc,
                         int64_t n_tracks, const gvl_intervals *itv, const int64_t *offset_idxs,
@@ -726,7 +730,7 @@ static int realign_impl(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_
                         const int32_t *track_lengths, const int64_t *out_offsets, int64_t total_per_track,
                         const int32_t *strategy_ids, const double *params, uint64_t base_seed,
                         const int64_t *query_seed, int64_t max_records, float *out, gvl_stream stream) {
-    if (!ctx || !tab || !regions || !shifts || !geno_offset_idx || !(itv || dense) || !(offset_idxs || dense) ||
+    if (!ctx || !tab || !regions || !shifts || !(geno_offset_idx || svar2) || !(itv || dense) || !(offset_idxs || dense) ||
         !track_lengths || !out_offsets || !strategy_ids || !params)
         return fail(GVL_ERR_ARG, "gvl_dev_realign_tracks: NULL argument");
     cudaStream_t st = (cudaStream_t)stream;
@@ -738,10 +742,15 @@ static int realign_impl(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_
     if ((rc = ensure_rows(ctx, ctx->trk, n_work))) return rc;
     if ((rc = ensure_records(ctx, ctx->trk, max_records + n_work))) return rc;
     int64_t *words = ctx->dev_words + W_COUNT;
-    GVL_CUDA(cudaMemsetAsync(words, 0, sizeof(int64_t) * 4, st));
+    GVL_CUDA(cudaMemsetAsync(words, 0, sizeof(int64_t) * W_COUNT, st));
     TrkPlanParams PP;
     PP.tab = *tab;
     PP.merged = MergedLists{nullptr, nullptr, nullptr, nullptr};
+    if (svar2) {  // merged two-channel variant lists (src/svar2/mod.rs:45-66), same merge as the haplotype path
+        if ((rc = ensure_merged(ctx, ctx->trk, max_records))) return rc;
+        if ((rc = gvl_svar2_merge_launch(ctx, &ctx->trk, words, svar2, batch, ploidy, max_records, st))) return rc;
+        PP.merged = MergedLists{ctx->trk.m_pos, ctx->trk.m_key, ctx->trk.m_off, ctx->trk.m_len};
+    }
     PP.regions = regions;
     PP.shifts = shifts;
     PP.goi = geno_offset_idx;
@@ -787,7 +796,7 @@ int gvl_dev_realign_tracks(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int
                            const int32_t *strategy_ids, const double *params, uint64_t base_seed,
                            const int64_t *query_seed, int64_t max_records, float *out, gvl_stream stream) {
     if (!itv || !offset_idxs) return fail(GVL_ERR_ARG, "gvl_dev_realign_tracks: NULL argument");
-    return realign_impl(ctx, tab, regions, shifts, geno_offset_idx, batch, ploidy, keep, keep_offsets, to_rc, n_tracks,
+    return realign_impl(ctx, tab, nullptr, regions, shifts, geno_offset_idx, batch, ploidy, keep, keep_offsets, to_rc, n_tracks,
                         itv, offset_idxs, nullptr, nullptr, track_lengths, out_offsets, total_per_track, strategy_ids,
                         params, base_seed, query_seed, max_records, out, stream);
 }
@@ -800,9 +809,22 @@ int gvl_dev_shift_and_realign_tracks(gvl_ctx *ctx, const gvl_sparse_tables *tab,
                                      int32_t strategy_id, double param, uint64_t base_seed,
                                      const int64_t *query_seed, int64_t max_records, float *out, gvl_stream stream) {
     if (!tracks || !track_offsets) return fail(GVL_ERR_ARG, "gvl_dev_shift_and_realign_tracks: NULL argument");
-    return realign_impl(ctx, tab, regions, shifts, geno_offset_idx, batch, ploidy, keep, keep_offsets, to_rc, 1, nullptr,
+    return realign_impl(ctx, tab, nullptr, regions, shifts, geno_offset_idx, batch, ploidy, keep, keep_offsets, to_rc, 1, nullptr,
                         nullptr, tracks, track_offsets, track_lengths, out_offsets, total, &strategy_id, &param,
                         base_seed, query_seed, max_records, out, stream);
+}
+
+int gvl_dev_shift_and_realign_tracks_svar2(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_svar2_channels *ch,
+                                           const int32_t *regions, const int32_t *shifts, int64_t batch, int64_t ploidy,
+                                           const uint8_t *to_rc, const float *tracks, const int64_t *track_offsets,
+                                           const int32_t *track_lengths, const int64_t *out_offsets, int64_t total,
+                                           int32_t strategy_id, double param, uint64_t base_seed,
+                                           const int64_t *query_seed, int64_t max_merged, float *out, gvl_stream stream) {
+    if (!ch || !ch->vk_off || !ch->dense_range || !ch->dense_present_off || !tracks || !track_offsets)
+        return fail(GVL_ERR_ARG, "gvl_dev_shift_and_realign_tracks_svar2: NULL argument");
+    return realign_impl(ctx, tab, ch, regions, shifts, nullptr, batch, ploidy, nullptr, nullptr, to_rc, 1, nullptr, nullptr,
+                        tracks, track_offsets, track_lengths, out_offsets, total, &strategy_id, &param, base_seed,
+                        query_seed, max_merged, out, stream);
 }
 
 int gvl_dev_intervals_to_tracks(gvl_ctx *ctx, const gvl_intervals *itv, const int64_t *offset_idxs,

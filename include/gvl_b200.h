@@ -211,6 +211,17 @@ int gvl_dev_shift_and_realign_tracks(gvl_ctx *ctx, const gvl_sparse_tables *tab,
                                      int32_t strategy_id, double param, uint64_t base_seed,
                                      const int64_t *query_seed, int64_t max_records, float *out, gvl_stream stream);
 
+/* shift_and_realign_tracks_from_svar2 on device (src/tracks/mod.rs:705-856, src/ffi/mod.rs `shift_and_realign_tracks_from_svar2`):
+ * gvl_dev_shift_and_realign_tracks with the svar2 two-channel variant source (merged on the device like
+ * gvl_dev_hap_plan_svar2; `tab` carries the decoded key table in ilens / n_variants).
+ *   max_merged = sum over rows of (var_key entries + dense window size) */
+int gvl_dev_shift_and_realign_tracks_svar2(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_svar2_channels *ch,
+                                           const int32_t *regions, const int32_t *shifts, int64_t batch, int64_t ploidy,
+                                           const uint8_t *to_rc, const float *tracks, const int64_t *track_offsets,
+                                           const int32_t *track_lengths, const int64_t *out_offsets, int64_t total,
+                                           int32_t strategy_id, double param, uint64_t base_seed,
+                                           const int64_t *query_seed, int64_t max_merged, float *out, gvl_stream stream);
+
 /* intervals_to_tracks on device (src/ffi/mod.rs:190-201): out f32[total = out_offsets[n]] fully written. */
 int gvl_dev_intervals_to_tracks(gvl_ctx *ctx, const gvl_intervals *itv, const int64_t *offset_idxs,
                                 const int32_t *starts, int64_t n_queries, const int64_t *out_offsets,
@@ -281,6 +292,18 @@ int gvl_intervals_and_realign_track_fused(
     const int64_t *offset_idxs, const int32_t *itv_starts, const int32_t *itv_ends, const float *itv_values,
     int64_t n_itv, const int64_t *itv_offsets, int64_t n_slots, const int64_t *track_offsets, const double *params,
     int64_t strategy_id, uint64_t base_seed, const uint8_t *keep, const int64_t *keep_offsets, const uint8_t *to_rc);
+
+/* shift_and_realign_tracks_from_svar2: the core behind src/ffi/mod.rs:1836-1960 (src/tracks/mod.rs:705-856) -- dense f32
+ * source windows, svar2 two-channel variant source, decoded key table (key_ilen) instead of the codec's LUT.  Rows are
+ * sized by the caller (`out_offsets` is an input, e.g. the offsets gvl_reconstruct_haplotypes_from_svar2_begin returns
+ * for output_length = -1, which are hap_diffs_svar2's); `out` is written in place.  query_seed optional (i64[batch]). */
+int gvl_shift_and_realign_tracks_from_svar2(
+    gvl_ctx *ctx, float *out, const int64_t *out_offsets, const int32_t *regions, const int32_t *shifts, int64_t batch,
+    int64_t ploidy, const int32_t *vk_pos, const int32_t *vk_key, const int64_t *vk_off, const int32_t *dense_pos,
+    const int32_t *dense_key, int64_t n_dense, const int32_t *dense_range, const uint8_t *dense_present,
+    const int64_t *dense_present_off, const int32_t *key_ilen, int64_t n_keys, const float *tracks,
+    const int64_t *track_offsets, const double *params, int64_t strategy_id, uint64_t base_seed,
+    const int64_t *query_seed);
 
 /* shift_and_realign_tracks_sparse, src/ffi/mod.rs:2439-2458 (dense source, writes `out` in place). */
 int gvl_shift_and_realign_tracks_sparse(

@@ -74,3 +74,40 @@ def test_svar2_tie_order_known_answer(cuda_device):
     assert h0[10] == ord("T") and h0[18] == ord("G")  # SNP T@10; after the 2-bp deletion the vk SNP 'G' wins at pos 20
     assert h0[15] == ref[15]                          # pure-DEL anchor comes from the reference
     assert out[38:].tobytes()[5:8] == b"CAA"          # hap1: insertion at 5
+
+
+@pytest.mark.parametrize("strategy,param", [(0, 0.0), (1, 0.0), (2, 3.5), (3, 4.0), (4, 1.0), (4, 3.0)])
+def test_svar2_tracks_vs_oracle(cuda_device, strategy, param):
+    """shift_and_realign_tracks_from_svar2 (src/tracks/mod.rs:705-856): dense source windows + the svar2 variant
+    source, all five insertion fills, shifts, the global-query seed of FlankSample -- bit-exact vs the oracle."""
+    from genvarloader_b200 import _kernels as K
+    from genvarloader_b200 import synth
+    from oracle import oracle as O
+
+    L = 4000
+    d = synth.make_dataset(91, 150_000, 3, 12, L, 12.0, max_indel=14, snp_frac=0.5)
+    rng = np.random.default_rng(strategy * 7 + 1)
+    b = 7
+    r_idx, s_idx = rng.integers(0, d.n_regions, b), rng.integers(0, d.n_samples, b)
+    regions, goi, _, ds_idx = synth.batch_args(d, r_idx, s_idx)
+    ch = synth.to_svar2_channels(d, regions, ds_idx, dense_frac=0.5, seed=5)
+    p = goi.shape[1]
+    diffs = O.hap_diffs_svar2(regions, p, ch["vk_pos"], ch["vk_key"], ch["vk_off"], ch["dense_pos"], ch["dense_key"],
+                              ch["dense_range"], ch["dense_present"], ch["dense_present_off"], ch["key_ilen"])
+    lens = np.maximum((regions[:, 2] - regions[:, 1])[:, None] + diffs, 0).ravel()
+    oo = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    # source windows: the region, room for net deletions (_reconstruct.py:191) and for the largest shift used below
+    tlen = (regions[:, 2] - regions[:, 1]) - np.minimum(diffs.min(1), 0) + 40
+    to = np.concatenate([[0], np.cumsum(tlen)]).astype(np.int64)
+    tracks = rng.standard_normal(int(to[-1])).astype(np.float32)
+    qseed = rng.integers(0, 1000, b).astype(np.int64)
+    for shifts in (np.zeros(goi.shape, np.int32), rng.integers(0, 30, goi.shape).astype(np.int32)):
+        for qs in (None, qseed):
+            args = (oo, regions, shifts, ch["vk_pos"], ch["vk_key"], ch["vk_off"], ch["dense_pos"], ch["dense_key"],
+                    ch["dense_range"], ch["dense_present"], ch["dense_present_off"], ch["key_ilen"], tracks, to,
+                    np.array([param]), strategy, 1234, qs)
+            exp = np.zeros(int(oo[-1]), np.float32)
+            got = np.full(int(oo[-1]), 7.0, np.float32)
+            O.shift_and_realign_tracks_from_svar2(exp, *args)
+            K.shift_and_realign_tracks_from_svar2(got, *args)
+            assert (exp.view(np.uint32) == got.view(np.uint32)).all()

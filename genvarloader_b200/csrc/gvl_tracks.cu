@@ -335,11 +335,32 @@ __device__ float insertion_fill_value(const TrkSrc &S, int strategy, double para
     }
 }
 
+#ifndef GVL_TRACE
+#define GVL_TRACE 0
+#endif
+#if GVL_TRACE
+__device__ unsigned long long *g_trk_trace = nullptr;  // [n_ctas][64]: per pass 6 globaltimer stamps (trace builds only)
+#define TRK_TR(slot)                                                                                        \
+    do {                                                                                                    \
+        if (g_trk_trace && threadIdx.x == 0 && tr_pass < 10) {                                              \
+            unsigned long long t_;                                                                          \
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_));                                           \
+            g_trk_trace[(unsigned long long)blockIdx.x * 64 + tr_pass * 6 + (slot)] = t_;                     \
+        }                                                                                                   \
+    } while (0)
+#else
+#define TRK_TR(slot) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(TRK_THREADS, 4) trk_exec_kernel(TrkExecParams P) {
+#if GVL_TRACE
+    int tr_pass = 0;
+#endif
     __shared__ TrkTileRecs S;
-    __shared__ float s_win[TRK_WIN];
+    __shared__ __align__(16) float s_win[TRK_WIN];
     __shared__ uint32_t s_flag[TRK_WIN / 32 + 4];  // positions of s_win that hold a run start (interval start / end)
     __shared__ float s_cval[TRK_THREADS / 32];
+    __shared__ int32_t s_gt[TRK_TILE / 128 + 2];  // per group of the pass: window offset of a plain group, or -1
     __shared__ int s_chas[TRK_THREADS / 32];
     __shared__ int64_t s_lo, s_hi, s_itv_first;
 
@@ -422,6 +443,7 @@ __global__ void __launch_bounds__(TRK_THREADS, 4) trk_exec_kernel(TrkExecParams 
     int32_t tgt_prev = INT32_MIN;
 
     while (cur < h1) {
+        TRK_TR(0);
         const int m_new = (int)imin64(TRK_REC_CAP - 1, r_hi - (r + 1));
         const int m = m_new + 1;
         const int32_t seg_end_rec = (r + 1 + m_new < r_hi) ? ra[r + 1 + m_new] : h1;
@@ -455,6 +477,7 @@ __global__ void __launch_bounds__(TRK_THREADS, 4) trk_exec_kernel(TrkExecParams 
         if (threadIdx.x == 0) S.a[m] = INT32_MAX;
         __syncthreads();
 
+        TRK_TR(1);
         // ---- source window: starts at the source position of `cur` (minus a margin) ----
         // source position feeding `cur`: inside the carry record's own values the reads go to
         // track[v_rel_pos] and then continue at its resume point; otherwise we are in its span.
@@ -488,6 +511,7 @@ __global__ void __launch_bounds__(TRK_THREADS, 4) trk_exec_kernel(TrkExecParams 
             if (threadIdx.x == 0) s_itv_first = first;
         }
         __syncthreads();
+        TRK_TR(2);
         if (!T.dense && w1 > w0) {
             // Paint the window as a run-length expansion (src/intervals.rs:19-126 restated for one window):
             //  1. every thread fetches ONE interval (coalesced) and drops two markers: 0 at its end, its value at
@@ -520,19 +544,34 @@ __global__ void __launch_bounds__(TRK_THREADS, 4) trk_exec_kernel(TrkExecParams 
                 if (__syncthreads_or(threadIdx.x == TRK_THREADS - 1 && st_ >= w1)) break;
             }
             __syncthreads();
-            constexpr int CH = 37;
-            static_assert(CH * TRK_THREADS >= TRK_WIN, "fill chunks must cover the window");
+            TRK_TR(3);
+            constexpr int CH = 36;  // 9 float4 per thread: conflict-free 128-bit accesses, 36 * 256 = TRK_WIN
+            static_assert(CH * TRK_THREADS >= TRK_WIN && CH % 4 == 0, "fill chunks must cover the window");
             const int b0 = CH * (int)threadIdx.x;
-            uint64_t mk = 0;  // marker bits of positions b0 .. b0 + 36
-            if (b0 < nwin) {
+            const bool act = b0 < nwin;
+            uint64_t mk = 0;  // marker bits of positions b0 .. b0 + 35
+            if (act) {
                 const int w = b0 >> 5, sft = b0 & 31;
                 mk = (((uint64_t)s_flag[w + 1] << 32) | s_flag[w]) >> sft;
                 if (sft) mk |= (uint64_t)s_flag[w + 2] << (64 - sft);
                 mk &= (1ull << CH) - 1;
             }
+            float x[CH];
+            if (act) {
+#pragma unroll
+                for (int q = 0; q < CH / 4; q++) {
+                    const float4 v4 = *reinterpret_cast<const float4 *>(&s_win[b0 + 4 * q]);
+                    x[4 * q] = v4.x, x[4 * q + 1] = v4.y, x[4 * q + 2] = v4.z, x[4 * q + 3] = v4.w;
+                }
+            }
             // (has, value) of the last marker in the chunk; scan with "right operand wins if it has one"
             int has = mk != 0;
-            float val = has ? s_win[b0 + 63 - __clzll((long long)mk)] : 0.0f;
+            float val = 0.0f;
+            if (has) {
+#pragma unroll
+                for (int q = 0; q < CH; q++)
+                    if ((mk >> q) & 1) val = x[q];
+            }
             const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
             int h_in = has;
             float v_in = val;
@@ -562,19 +601,20 @@ __global__ void __launch_bounds__(TRK_THREADS, 4) trk_exec_kernel(TrkExecParams 
                     found = 1;
                 }
             }
-            if (b0 < nwin) {
-                const int n_ = min(CH, nwin - b0);
+            if (act) {
                 float cur_v = carry;
-                int i = 0;
-                while (i < n_) {  // runs between markers
-                    const uint64_t rest = mk >> i;
-                    const int nxt = rest ? min(n_, i + (__ffsll((long long)rest) - 1)) : n_;
-                    for (; i < nxt; i++) s_win[b0 + i] = cur_v;
-                    if (i < n_) cur_v = s_win[b0 + i++];
+#pragma unroll
+                for (int q = 0; q < CH; q++) {
+                    cur_v = ((mk >> q) & 1) ? x[q] : cur_v;
+                    x[q] = cur_v;
                 }
+#pragma unroll
+                for (int q = 0; q < CH / 4; q++)
+                    *reinterpret_cast<float4 *>(&s_win[b0 + 4 * q]) = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
             }
         }
         __syncthreads();
+        TRK_TR(4);
         itv_prev = T.dense ? -1 : s_itv_first;
         tgt_prev = (int32_t)imin64(q_start + w0, INT32_MAX);
         TrkSrc src{s_win, w0, w1, track_n, &T, itv_lo, itv_hi, q_start};
@@ -585,39 +625,56 @@ __global__ void __launch_bounds__(TRK_THREADS, 4) trk_exec_kernel(TrkExecParams 
         const int32_t n_chunks = (int32_t)((row_base + jo_hi - g0 + 3) >> 2);
         // a GROUP is 32 chunks of 4 values (one chunk per lane); warp w owns groups w, w+8, ...  A group that lies
         // inside ONE reference span and inside the staged window is a straight (possibly reversed) copy out of
-        // shared memory; everything else resolves each value against the records.
+        // shared memory: one thread per group decides that up front (group table), so the copy loop itself is a
+        // table read, four shared-memory reads and one 16-byte store per lane.
         const int warp_ = threadIdx.x >> 5, lane_ = threadIdx.x & 31;
         const int32_t n_groups = (n_chunks + 31) >> 5;
-        int ic = rc ? (m - 1) : 0;  // warp-uniform record cursor (groups are visited in monotone order)
+        if ((int)threadIdx.x < n_groups) {
+            const int32_t jg = (int32_t)(g0 + 128 * (int64_t)threadIdx.x - row_base);
+            int32_t off = -1;
+            if (jg >= jo_lo && jg + 128 <= jo_hi) {
+                const int32_t p_lo = rc ? (L - 128 - jg) : jg;  // lowest haplotype position of the group
+                int lo = 0, hi = m;
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (S.a[mid] <= p_lo) lo = mid; else hi = mid;
+                }
+                const int32_t e_i = S.e[lo];
+                const int64_t tp_lo = (int64_t)S.resume[lo] + (p_lo - e_i);
+                if (p_lo >= e_i && p_lo + 128 <= S.a[lo + 1] && tp_lo >= w0 && tp_lo + 128 <= w1) off = (int32_t)(tp_lo - w0);
+            }
+            s_gt[threadIdx.x] = off;
+        }
+        __syncthreads();
         for (int32_t grp = warp_; grp < n_groups; grp += TRK_THREADS / 32) {
             const int32_t c = grp * 32 + lane_;
             const int64_t g = g0 + 4 * (int64_t)c;
             const int32_t j = (int32_t)(g - row_base);
-            const int32_t jg = (int32_t)(g0 + 128 * (int64_t)grp - row_base);
-            if (jg >= jo_lo && jg + 128 <= jo_hi) {
-                const int32_t p_lo = rc ? (L - 128 - jg) : jg;  // lowest haplotype position of the group
-                if (!rc) {
-                    while (S.a[ic + 1] <= p_lo) ic++;
-                } else {
-                    while (S.a[ic] > p_lo) ic--;
+            const int32_t off = s_gt[grp];
+            if (off >= 0) {
+                const float *ws = s_win + off + (rc ? 124 - 4 * lane_ : 4 * lane_);
+                *reinterpret_cast<float4 *>(out + g) =
+                    rc ? make_float4(ws[3], ws[2], ws[1], ws[0]) : make_float4(ws[0], ws[1], ws[2], ws[3]);
+                continue;
+            }
+            if (c >= n_chunks) continue;
+            // lane-level fast path: the lane's 4 values lie inside one reference span and inside the window
+            if (j >= jo_lo && j + 4 <= jo_hi) {
+                const int32_t p4 = rc ? (L - 4 - j) : j;  // lowest haplotype position of the chunk
+                int lo = 0, hi = m;
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (S.a[mid] <= p4) lo = mid; else hi = mid;
                 }
-                const int32_t e_i = S.e[ic];
-                const int64_t tp_lo = (int64_t)S.resume[ic] + (p_lo - e_i);
-                if (p_lo >= e_i && p_lo + 128 <= S.a[ic + 1] && tp_lo >= w0 && tp_lo + 128 <= w1) {
-                    const float *ws = s_win + (tp_lo - w0);
-                    float4 o;
-                    if (!rc) {
-                        ws += 4 * lane_;
-                        o = make_float4(ws[0], ws[1], ws[2], ws[3]);
-                    } else {
-                        ws += 124 - 4 * lane_;
-                        o = make_float4(ws[3], ws[2], ws[1], ws[0]);
-                    }
-                    *reinterpret_cast<float4 *>(out + g) = o;
+                const int32_t e_l = S.e[lo];
+                const int64_t tp4 = (int64_t)S.resume[lo] + (p4 - e_l);
+                if (p4 >= e_l && p4 + 4 <= S.a[lo + 1] && tp4 >= w0 && tp4 + 4 <= w1) {
+                    const float *ws = s_win + (tp4 - w0);
+                    *reinterpret_cast<float4 *>(out + g) =
+                        rc ? make_float4(ws[3], ws[2], ws[1], ws[0]) : make_float4(ws[0], ws[1], ws[2], ws[3]);
                     continue;
                 }
             }
-            if (c >= n_chunks) continue;
             float vals[4];
             bool valid[4];
             int i = 0;
@@ -660,6 +717,11 @@ __global__ void __launch_bounds__(TRK_THREADS, 4) trk_exec_kernel(TrkExecParams 
                     if (valid[q]) out[g + q] = vals[q];
             }
         }
+#if GVL_TRACE
+        __syncthreads();
+        TRK_TR(5);
+        tr_pass++;
+#endif
         // records consumed by this pass: staged entries 1..m_new with a < seg_end (the rest are staged again)
         {
             int lo = 0, hi = m;  // last staged entry with a < seg_end
@@ -813,6 +875,14 @@ int gvl_dev_shift_and_realign_tracks(gvl_ctx *ctx, const gvl_sparse_tables *tab,
                         nullptr, tracks, track_offsets, track_lengths, out_offsets, total, &strategy_id, &param,
                         base_seed, query_seed, max_records, out, stream);
 }
+
+#if GVL_TRACE
+__attribute__((visibility("default"))) int gvl_debug_set_trk_trace(void *dev_buf) {
+    unsigned long long *p = (unsigned long long *)dev_buf;
+    GVL_CUDA(cudaMemcpyToSymbol(g_trk_trace, &p, sizeof(p)));
+    return GVL_OK;
+}
+#endif
 
 int gvl_dev_shift_and_realign_tracks_svar2(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_svar2_channels *ch,
                                            const int32_t *regions, const int32_t *shifts, int64_t batch, int64_t ploidy,

@@ -62,3 +62,23 @@ byts = 4.0 * vals  # + 12 B per interval actually read (a fraction of the stored
 print(f"tracks cfg3: {len(names)} tracks x {2 * b} rows x {L} values = {vals / 1e6:.1f} M values, {byts / 1e6:.0f} MB written per call")
 print(f"realign_tracks (plan + execute, one stream, back to back): {us:.1f} us per call -> {byts / us / 1e3:.0f} GB/s written, "
       f"{vals / us / 1e3:.1f} G values/s")
+
+if os.environ.get("GVL_LIB_NAME", "").startswith("libgvl_trace"):
+    import ctypes as C
+    from genvarloader_b200 import _ffi
+    tr = torch.zeros(4096 * 64, dtype=torch.int64, device=dev)
+    _ffi.check(_ffi.lib.gvl_debug_set_trk_trace(C.c_void_p(tr.data_ptr())))
+    call(ring[0])
+    torch.cuda.synchronize()
+    a = tr.cpu().numpy().reshape(-1, 64)
+    a = a[a[:, 0] > 0]
+    t0 = a[:, 0].min()
+    print(f"trace: {len(a)} CTAs; kernel span {(a[:, :60].max() - t0) / 1e3:.1f} us")
+    names_ = ["stage records", "window/interval search", "markers", "scan+fill", "group loop (output)"]
+    for ps in range(8):
+        st = a[:, ps * 6:ps * 6 + 6]
+        ok = st[:, 5] > 0
+        if not ok.any():
+            break
+        d_ = np.diff(st[ok], axis=1) / 1e3
+        print(f"pass {ps}: start p50 {(np.median(st[ok, 0]) - t0) / 1e3:7.1f} us | " + " | ".join(f"{n} {np.median(d_[:, i]):.2f}" for i, n in enumerate(names_)) + f" | total {np.median(d_.sum(1)):.2f} us")

@@ -49,6 +49,8 @@ WORKLOADS = {
     "cfg3t": dict(desc="configs[2]: 524,288-bp indel-bearing windows, 32 haplotypes/batch, 50% negative strand, PLUS 2 realigned "
                        "float tracks per haplotype (intervals with a mean run of 50 bp; fills Repeat5p and Interpolate(1))",
                   contig_len=20_000_000, n_samples=16, n_regions=16, window=524_288, pairs=16, vkb=1.0, neg=0.5, tracks=2),
+    "cfg2d": dict(desc="configs[4] dense cell: 131,072-bp windows, 64 haplotypes/batch, ~10 variants/kb/haplotype",
+                  contig_len=8_000_000, n_samples=16, n_regions=16, window=131_072, pairs=32, vkb=10.0, neg=0.5),
     "cfg4": dict(desc="configs[3] (one-hot instead of annotated): 6,144-bp windows, 4,096 haplotypes/batch",
                  contig_len=5_000_000, n_samples=64, n_regions=512, window=6_144, pairs=2048, vkb=1.0),
 }

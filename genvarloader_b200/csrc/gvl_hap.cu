@@ -1015,8 +1015,10 @@ static int hap_plan_impl(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_s
         hap_plan_serial_kernel<<<grid, PLAN_WARPS * 32, 0, st>>>(P);
     } else if (max_records <= 40 * n_work) {  // short lists: one warp per row, 4 rows per CTA
         hap_plan_par_kernel<32><<<(unsigned)((n_work + 3) / 4), 128, 0, st>>>(P);
-    } else {  // one 256-thread CTA per row
+    } else if (max_records <= 384 * n_work) {  // one 256-thread CTA per row
         hap_plan_par_kernel<256><<<(unsigned)n_work, 256, 0, st>>>(P);
+    } else {  // long lists: 512 variants per sequential chunk
+        hap_plan_par_kernel<512><<<(unsigned)n_work, 512, 0, st>>>(P);
     }
     GVL_LAUNCH_CHECK();
     if (output_length >= 0) {

@@ -422,11 +422,11 @@ __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(Ha
         };
         // (the code words travel with asynchronous 4-byte copies into the thread's own shared-memory slots, so no
         //  register stays live across the group loop; part 2 reads them back after it)
-        if (tid < n_slots) {
+        auto edge_begin = [&](int s_) {
             int e_kind, e_il = 0;
             int32_t e_p = 0;
             uint32_t e_desc = 0;
-            edge_locate(tid, e_kind, e_p, e_il);
+            edge_locate(s_, e_kind, e_p, e_il);
             if (e_kind == U_PATCH) {
                 UnitShape U;
                 e_kind = oh_classify(S, e_il, e_p, rp.ref_base, U);
@@ -463,7 +463,8 @@ __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(Ha
             }
             s_edge[6][tid] = e_desc | (uint32_t)e_kind;
             s_edge[7][tid] = (uint32_t)e_p;
-        }
+        };
+        if (tid < n_slots) edge_begin(tid);
         cp_async_commit();
 
         // ---- the group loop: every lane streams the units that are a single run ----
@@ -544,11 +545,15 @@ __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(Ha
             int e_kind, e_il = 0;
             int32_t e_p;
             uint32_t e_desc = 0;
+            if (s_ != tid) {  // more slots than threads (dense variants): later rounds start their copies here
+                edge_begin(s_);
+                cp_async_commit();
+                cp_async_wait<0>();
+            }
             e_desc = s_edge[6][tid];
             e_kind = e_desc & 3u;
             e_p = (int32_t)s_edge[7][tid];
-            if (s_ != tid || e_kind == U_SLOW) {
-                // piecewise units (and, with more slots than threads, all later slots) are done start to finish here
+            if (e_kind == U_SLOW) {  // piecewise units are done start to finish here
                 edge_locate(s_, e_kind, e_p, e_il);
                 if (e_kind == U_PATCH) e_kind = U_SLOW;
             }

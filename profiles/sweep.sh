@@ -1,7 +1,7 @@
 #!/bin/bash
 # usage: profiles/sweep.sh <tag> <env assignments...> ; runs bench cfg2+cfg3 quickly and prints the key numbers
 tag=$1; shift
-for w in cfg2 cfg3; do
+for w in ${WL:-cfg2 cfg3}; do
   env "$@" timeout 300 python bench.py --workload $w --steps 2000 --warmup 20 --cpu-seconds 0.3 2>/dev/null | python -c "
 import json,sys
 for l in sys.stdin:

@@ -3,7 +3,7 @@
 from ._insertion_fill import Constant, FlankSample, InsertionFill, Interpolate, Repeat5p, Repeat5pNormalized
 
 __all__ = ["Dataset", "Engine", "AnnotatedHaps", "Ragged", "RaggedAnnotatedHaps", "InsertionFill", "Repeat5p",
-           "Repeat5pNormalized", "Constant", "FlankSample", "Interpolate"]
+           "Repeat5pNormalized", "Constant", "FlankSample", "Interpolate", "Reference"]
 
 
 def __getattr__(name):  # torch + the CUDA library are loaded on first use
@@ -11,6 +11,10 @@ def __getattr__(name):  # torch + the CUDA library are loaded on first use
         from ._dataset import Dataset
 
         return Dataset
+    if name == "Reference":
+        from ._open import Reference
+
+        return Reference
     if name == "Engine":
         from ._engine import Engine
 

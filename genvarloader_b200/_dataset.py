@@ -68,6 +68,7 @@ class Dataset:
     rng: np.random.Generator = field(default_factory=np.random.default_rng)
     region_subset: object = None
     sample_subset: object = None
+    region_map: object = None                         # input-BED row -> storage row (datasets opened from disk)
 
     # ------------------------------------------------------------------ construction
     @classmethod
@@ -97,10 +98,39 @@ class Dataset:
                                rng=rng)
 
     @classmethod
-    def open(cls, path, *a, **k):
-        raise NotImplementedError(
-            "Reading the on-disk GVL dataset layout is the next scope row (SURVEY.md 8f-1); build an in-memory "
-            "dataset with Dataset.from_arrays(...) for now.")
+    def open(cls, path, reference=None, device="cuda", jitter: int = 0, rng=None, deterministic: bool = True,
+             rc_neg: bool = True) -> "Dataset":
+        """Open a dataset directory written by `gvl.write` (reference `Dataset.open`, _impl.py:164-226 ->
+        `_open.py:62-345`; layout: docs/source/format.md:8-49) and upload it to `device`.
+
+        `reference`: FASTA path (plain / gzip / bgzip) or a `genvarloader_b200.Reference`; required when the dataset
+        has genotypes.  Regions are addressed in the ORDER OF THE INPUT BED, like the reference (`r_idx_map`).
+        Datasets that back-reference a `.svar` / `.svar2` store are refused (third-party store format)."""
+        from ._open import Reference, read_dataset_arrays
+
+        a = read_dataset_arrays(path, reference)
+        ref = a["reference"]
+        n_regions, samples = len(a["full_regions"]), a["samples"]
+        has_geno = "geno_v_idxs" in a
+        ploidy = int(a["ploidy"]) if has_geno else 1
+        if has_geno and ref is None:
+            raise ValueError("this dataset has genotypes: pass `reference=` (FASTA path or Reference) to reconstruct haplotypes")
+        if ref is None:  # tracks only: contig extents are never read
+            ref = Reference.from_arrays(np.zeros(0, np.uint8), np.zeros(len(a["contigs"]) + 1, np.int64), a["contigs"])
+        if has_geno:
+            eng = Engine(device, ref.reference, ref.offsets, a["v_starts"], a["ilens"], a["alt_alleles"], a["alt_offsets"],
+                         a["geno_v_idxs"], a["geno_offsets"], pad_char=ref.pad_char)
+        else:
+            eng = Engine(device, ref.reference, ref.offsets, np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.uint8),
+                         np.zeros(1, np.int64), np.zeros(0, np.int32), np.zeros(n_regions * len(samples) * ploidy + 1, np.int64),
+                         pad_char=ref.pad_char)
+        for name, t in a["tracks"].items():
+            eng.add_track(name, *t)
+        ds = cls(engine=eng, full_regions=a["full_regions"], sample_names=tuple(samples), ploidy=ploidy,
+                 max_jitter=a["max_jitter"], track_kinds=dict(a["track_kinds"]), active_tracks=tuple(a["track_kinds"]),
+                 sequence_type="haplotypes" if has_geno else None, rng=np.random.default_rng(rng),
+                 region_map=np.ascontiguousarray(a["region_map"], np.int64))
+        return ds.with_settings(jitter=jitter, deterministic=deterministic, rc_neg=rc_neg)
 
     # ------------------------------------------------------------------ properties (reference: _impl.py:954-1110)
     @property
@@ -140,7 +170,9 @@ class Dataset:
 
     @property
     def _r_idx(self) -> np.ndarray:
-        return np.arange(len(self.full_regions)) if self.region_subset is None else self.region_subset
+        if self.region_subset is not None:
+            return self.region_subset
+        return np.arange(len(self.full_regions)) if self.region_map is None else self.region_map
 
     @property
     def _s_idx(self) -> np.ndarray:

@@ -6,6 +6,7 @@ torch is plumbing here (device memory, streams); all compute is in the CUDA libr
 from __future__ import annotations
 
 import ctypes as C
+import warnings
 
 import numpy as np
 import torch
@@ -30,7 +31,9 @@ def _dev(a, dtype, device, pad: int = 0) -> torch.Tensor:
     if pad:
         t[a.size:].zero_()
     if a.size:
-        t[: a.size].copy_(torch.from_numpy(a.reshape(-1)), non_blocking=False)
+        with warnings.catch_warnings():  # read-only memmaps (datasets opened from disk) are only read here
+            warnings.filterwarnings("ignore", message="The given NumPy array is not writable")
+            t[: a.size].copy_(torch.from_numpy(a.reshape(-1)), non_blocking=False)
     return t
 
 

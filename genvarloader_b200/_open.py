@@ -1,0 +1,228 @@
+"""Read a GenVarLoader dataset directory (written by `gvl.write`) into the GPU-resident `Dataset`.
+
+Layout followed (reference `docs/source/format.md:8-49`):
+
+    metadata.json                      samples, contigs, n_regions, ploidy, max_jitter, version, svar_link, svar2_link
+    input_regions.arrow                the caller's BED rows + `r_idx_map` (input row -> sorted storage row)
+    genotypes/variants.arrow           POS (1-based from 0.18.0, _haps.py:462-468), ILEN, ALT[, REF]
+    genotypes/variant_idxs.npy         raw int32 memmap (no .npy header, _haps.py:469-473)
+    genotypes/offsets.npy              raw int64 memmap, R*S*P + 1 offsets (_haps.py:474-478)
+    intervals/<track>/{starts,ends,values,offsets}.npy         raw int32 / int32 / float32 / int64, R*S + 1 offsets
+    annot_intervals/<track>/...                                 same, R + 1 offsets (_tracks.py:327-339)
+
+Only numpy + pyarrow are used.  Datasets that back-reference a `.svar` / `.svar2` store (`svar_link`,
+`svar2_link`) need the third-party genoray store format and are refused with a clear error.
+"""
+from __future__ import annotations
+
+import gzip
+import json
+from dataclasses import dataclass
+from pathlib import Path
+
+import numpy as np
+
+
+@dataclass
+class Reference:
+    """In-memory reference genome: contigs concatenated, upper-cased (reference `Reference`,
+    python/genvarloader/_dataset/_reference.py:32-127; the FASTA cache upper-cases, _fasta_cache.py:115)."""
+
+    reference: np.ndarray  # uint8
+    offsets: np.ndarray    # int64 (n_contigs + 1)
+    contigs: list
+    pad_char: int = ord("N")
+
+    @classmethod
+    def from_arrays(cls, reference, offsets, contigs, pad_char: int = ord("N")) -> "Reference":
+        return cls(np.ascontiguousarray(reference, np.uint8), np.ascontiguousarray(offsets, np.int64), list(contigs), pad_char)
+
+    @classmethod
+    def from_path(cls, fasta, contigs=None) -> "Reference":
+        """Plain, gzip or bgzip FASTA.  `contigs` selects and orders contigs ("chr1" and "1" match either way)."""
+        path = Path(fasta)
+        opener = gzip.open if path.suffix in (".gz", ".bgz") else open
+        seqs: dict = {}
+        name, chunks = None, []
+        with opener(path, "rb") as f:
+            for line in f:
+                if line.startswith(b">"):
+                    if name is not None:
+                        seqs[name] = b"".join(chunks)
+                    name, chunks = line[1:].split()[0].decode(), []
+                else:
+                    chunks.append(line.strip().upper())
+        if name is not None:
+            seqs[name] = b"".join(chunks)
+        if contigs is None:
+            contigs = list(seqs)
+        norm = _ContigMap(list(seqs))
+        missing = [c for c in contigs if norm.get(c) is None]
+        if missing:
+            raise ValueError(f"Some of the given contig names are not present in reference file: {missing}")
+        parts = [np.frombuffer(seqs[norm.get(c)], np.uint8) for c in contigs]
+        offsets = np.concatenate([[0], np.cumsum([p.size for p in parts])]).astype(np.int64)
+        return cls(np.concatenate(parts) if parts else np.zeros(0, np.uint8), offsets, list(contigs))
+
+
+class _ContigMap:
+    """UCSC / Ensembl tolerant contig lookup (reference `ContigNormalizer`, python/genvarloader/_utils.py)."""
+
+    def __init__(self, contigs):
+        self.contigs = list(contigs)
+        self._m = {}
+        for c in self.contigs:
+            self._m[c] = c
+            self._m[c[3:] if c.startswith("chr") else "chr" + c] = c
+
+    def get(self, name):
+        return self._m.get(name)
+
+    def index(self, name) -> int:
+        c = self.get(name)
+        if c is None:
+            raise ValueError(f"contig {name!r} is not among the dataset's contigs {self.contigs}")
+        return self.contigs.index(c)
+
+
+def _version_tuple(v) -> tuple | None:
+    if v is None:
+        return None
+    if isinstance(v, dict):
+        return (int(v.get("major", 0)), int(v.get("minor", 0)), int(v.get("patch", 0)))
+    core = str(v).split("+")[0].split("-")[0]
+    parts = (core.split(".") + ["0", "0"])[:3]
+    return tuple(int("".join(ch for ch in p if ch.isdigit()) or 0) for p in parts)
+
+
+def _first_of_lists(col):
+    import pyarrow as pa
+    import pyarrow.compute as pc
+
+    col = col.combine_chunks() if isinstance(col, pa.ChunkedArray) else col
+    if pa.types.is_list(col.type) or pa.types.is_large_list(col.type):
+        col = pc.list_element(col, 0)
+    return col
+
+
+def _utf8_to_bytes_offsets(col) -> tuple:
+    """Arrow (large_)utf8 array -> (uint8 bytes, int64 offsets) without a Python loop."""
+    import pyarrow as pa
+
+    col = _first_of_lists(col)
+    if pa.types.is_dictionary(col.type):
+        col = col.dictionary_decode()
+    if not (pa.types.is_string(col.type) or pa.types.is_large_string(col.type)):
+        col = col.cast(pa.large_utf8())
+    if col.null_count:
+        raise ValueError("ALT contains nulls")
+    bufs = col.buffers()
+    odt = np.int64 if pa.types.is_large_string(col.type) else np.int32
+    offs = np.frombuffer(bufs[1], odt)[col.offset: col.offset + len(col) + 1].astype(np.int64)
+    data = np.frombuffer(bufs[2], np.uint8) if bufs[2] is not None else np.zeros(0, np.uint8)
+    lo, hi = int(offs[0]), int(offs[-1])
+    return np.ascontiguousarray(data[lo:hi]), offs - lo
+
+
+def read_dataset_arrays(path, reference=None) -> dict:
+    """Parse the directory into the arrays `Dataset.from_arrays` takes (host side, numpy memmaps where possible)."""
+    import pyarrow as pa
+    import pyarrow.ipc as ipc
+
+    path = Path(path)
+    meta = json.loads((path / "metadata.json").read_text())
+    if meta.get("svar_link") or meta.get("svar2_link") or (path / "genotypes" / "svar_meta.json").exists() \
+            or (path / "genotypes" / "svar2_ranges").exists():
+        raise NotImplementedError(
+            "this dataset back-references a .svar/.svar2 store; reading genoray stores is outside the current scope "
+            "(SURVEY.md 8f-2).  Datasets written from VCF/PGEN (genotypes/variants.arrow present) can be opened.")
+    samples, contigs = list(meta["samples"]), list(meta["contigs"])
+    ploidy = meta.get("ploidy")
+    max_jitter = int(meta.get("max_jitter") or 0)
+    cmap = _ContigMap(contigs)
+
+    # ---- regions: the un-padded BED rows, stored in sorted order (r_idx_map: input row -> storage row) ----
+    with pa.memory_map(str(path / "input_regions.arrow"), "r") as src:
+        bed = ipc.open_file(src).read_all()
+    cols = {n: bed.column(n) for n in bed.column_names}
+    chrom = [str(c) for c in _first_of_lists(cols["chrom"]).cast(pa.large_utf8()).to_pylist()] \
+        if not pa.types.is_dictionary(cols["chrom"].type) else [str(c) for c in cols["chrom"].to_pylist()]
+    c_idx = np.array([cmap.index(c) for c in chrom], np.int32)
+    starts = cols["chromStart"].to_numpy().astype(np.int32)
+    ends = cols["chromEnd"].to_numpy().astype(np.int32)
+    if "strand" in cols:
+        st = cols["strand"]
+        if pa.types.is_integer(st.type):
+            strand = st.to_numpy().astype(np.int32)
+        else:
+            strand = np.array([1 if str(x) == "+" else -1 for x in st.to_pylist()], np.int32)
+    else:
+        strand = np.ones(len(starts), np.int32)
+    r_idx_map = cols["r_idx_map"].to_numpy().astype(np.int64)
+    n_regions = len(starts)
+    if sorted(r_idx_map.tolist()) != list(range(n_regions)):
+        raise ValueError("input_regions.arrow: r_idx_map is not a permutation of the region indices")
+    full_regions = np.empty((n_regions, 4), np.int32)
+    full_regions[r_idx_map] = np.stack([c_idx, starts, ends, strand], 1)
+    out = dict(samples=samples, contigs=contigs, ploidy=ploidy, max_jitter=max_jitter, full_regions=full_regions,
+               region_map=r_idx_map, tracks={}, track_kinds={})
+
+    # ---- genotypes ----
+    gdir = path / "genotypes"
+    if gdir.exists():
+        if ploidy is None:
+            raise ValueError("metadata.json has genotypes but no ploidy")
+        with pa.memory_map(str(gdir / "variants.arrow"), "r") as src:
+            vt = ipc.open_file(src).read_all()
+        ver = _version_tuple(meta.get("version"))
+        one_based = ver is not None and ver >= (0, 18, 0)
+        pos = _first_of_lists(vt.column("POS")).to_numpy(zero_copy_only=False).astype(np.int64) - int(one_based)
+        alt, alt_off = _utf8_to_bytes_offsets(vt.column("ALT"))
+        if "ILEN" in vt.column_names:
+            ilen = _first_of_lists(vt.column("ILEN")).to_numpy(zero_copy_only=False).astype(np.int32)
+        else:  # ALT length - REF length (_haps.py:127-134)
+            _, ref_off = _utf8_to_bytes_offsets(vt.column("REF"))
+            ilen = (np.diff(alt_off) - np.diff(ref_off)).astype(np.int32)
+        out.update(v_starts=pos.astype(np.int32), ilens=ilen, alt_alleles=alt, alt_offsets=alt_off,
+                   geno_v_idxs=np.memmap(gdir / "variant_idxs.npy", dtype=np.int32, mode="r"),
+                   geno_offsets=np.memmap(gdir / "offsets.npy", dtype=np.int64, mode="r"))
+        n_slots = n_regions * len(samples) * int(ploidy)
+        if out["geno_offsets"].size != n_slots + 1:
+            raise ValueError(f"genotypes/offsets.npy holds {out['geno_offsets'].size} offsets, expected {n_slots + 1} "
+                             f"(regions x samples x ploidy + 1)")
+    # ---- tracks ----
+    for sub, kind, n_slots in (("intervals", "sample", n_regions * len(samples)), ("annot_intervals", "annot", n_regions)):
+        tdir = path / sub
+        if not tdir.exists():
+            continue
+        for p in sorted(tdir.iterdir()):
+            if not p.is_dir() or ".tmp." in p.name or ".old." in p.name or p.name.endswith(".lock") or not any(p.iterdir()):
+                continue
+            if p.name in out["tracks"]:
+                raise ValueError(f"Found sample and annotation tracks with the same name: {{{p.name!r}}}")
+            offs = np.memmap(p / "offsets.npy", dtype=np.int64, mode="r")
+            if offs.size != n_slots + 1:
+                raise ValueError(f"{sub}/{p.name}/offsets.npy holds {offs.size} offsets, expected {n_slots + 1}")
+            out["tracks"][p.name] = (np.memmap(p / "starts.npy", dtype=np.int32, mode="r"),
+                                     np.memmap(p / "ends.npy", dtype=np.int32, mode="r"),
+                                     np.memmap(p / "values.npy", dtype=np.float32, mode="r"), offs)
+            out["track_kinds"][p.name] = kind
+    # ---- reference ----
+    if reference is not None:
+        if not isinstance(reference, Reference):
+            reference = Reference.from_path(reference, contigs)
+        else:
+            rmap = _ContigMap(reference.contigs)
+            if [rmap.get(c) for c in contigs] != list(reference.contigs[: len(contigs)]) or len(reference.contigs) != len(contigs):
+                # re-order / subset to the dataset's contig order
+                parts = []
+                for c in contigs:
+                    rc = rmap.get(c)
+                    if rc is None:
+                        raise ValueError(f"Some of the given contig names are not present in reference file: [{c!r}]")
+                    i = reference.contigs.index(rc)
+                    parts.append(reference.reference[reference.offsets[i]: reference.offsets[i + 1]])
+                reference = Reference.from_arrays(np.concatenate(parts), np.concatenate([[0], np.cumsum([p.size for p in parts])]),
+                                                  contigs, reference.pad_char)
+    out["reference"] = reference
+    return out

@@ -1,0 +1,63 @@
+"""Host-side parsing of the on-disk GenVarLoader dataset layout (no GPU): `_open.read_dataset_arrays`, `Reference`."""
+import numpy as np
+import pytest
+
+from tests._gvl_disk import write_fasta, write_gvl_dataset
+
+
+@pytest.fixture(scope="module")
+def disk(tmp_path_factory):
+    from genvarloader_b200 import synth
+
+    d = synth.make_dataset(17, 120_000, 3, 9, 1500 + 2 * 8, 6.0, max_jitter=8, neg_strand_frac=0.5, straddle_ends=False,
+                           n_tracks=2, max_indel=9)
+    root = tmp_path_factory.mktemp("gvl")
+    order = np.random.default_rng(0).permutation(d.n_regions)
+    write_gvl_dataset(root / "ds", d, ["chr1"], ["s2", "s0", "s1"], order)
+    write_fasta(root / "ref.fa", d.reference, d.ref_offsets, ["1"], lower_every=37)
+    return d, root, order
+
+
+def test_read_dataset_arrays_roundtrip(disk):
+    from genvarloader_b200._open import Reference, read_dataset_arrays
+
+    d, root, order = disk
+    a = read_dataset_arrays(root / "ds", root / "ref.fa")
+    assert a["samples"] == ["s2", "s0", "s1"] and a["ploidy"] == d.ploidy and a["max_jitter"] == 8
+    assert (a["full_regions"] == d.regions).all()          # storage order restored through r_idx_map
+    assert (a["region_map"] == order).all()
+    assert (a["v_starts"] == d.v_starts).all() and (a["ilens"] == d.ilens).all()  # 1-based POS from version 0.18.0
+    assert (a["alt_alleles"] == d.alt_alleles).all() and (a["alt_offsets"] == d.alt_offsets).all()
+    go = np.asarray(d.geno_offsets)
+    assert a["geno_offsets"].size == go.shape[1] + 1
+    for k in (0, 5, go.shape[1] - 1):
+        got = a["geno_v_idxs"][a["geno_offsets"][k]: a["geno_offsets"][k + 1]]
+        assert (got == d.geno_v_idxs[go[0, k]: go[1, k]]).all()
+    assert sorted(a["tracks"]) == sorted(d.tracks) and set(a["track_kinds"].values()) == {"sample"}
+    ref = a["reference"]
+    assert isinstance(ref, Reference) and ref.contigs == ["chr1"]
+    assert (ref.reference == d.reference).all() and (ref.offsets == d.ref_offsets).all()  # upper-cased, "1" == "chr1"
+
+
+def test_version_and_errors(disk, tmp_path):
+    import json
+
+    from genvarloader_b200._open import _version_tuple, read_dataset_arrays
+
+    d, root, order = disk
+    assert _version_tuple("0.18.0") == (0, 18, 0) and _version_tuple("0.21.3+dev") == (0, 21, 3)
+    assert _version_tuple({"major": 1, "minor": 2, "patch": 3}) == (1, 2, 3) and _version_tuple(None) is None
+    old = tmp_path / "old"
+    write_gvl_dataset(old, d, ["chr1"], ["a", "b", "c"], order, version="0.17.2", pos_one_based=False, strand_as_str=False)
+    a = read_dataset_arrays(old)
+    assert (a["v_starts"] == d.v_starts).all() and a["reference"] is None and (a["full_regions"] == d.regions).all()
+    meta = json.loads((old / "metadata.json").read_text())
+    meta["svar_link"] = {"relative_path": "../x.svar", "absolute_path": "/x.svar", "fingerprint": {}}
+    (old / "metadata.json").write_text(json.dumps(meta))
+    with pytest.raises(NotImplementedError, match="svar"):
+        read_dataset_arrays(old)
+    with pytest.raises(ValueError, match="not present in reference"):
+        read_dataset_arrays(root / "ds", root / "ref.fa").get  # ok
+        from genvarloader_b200._open import Reference
+
+        Reference.from_path(root / "ref.fa", ["chr7"])

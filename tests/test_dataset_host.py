@@ -72,5 +72,5 @@ def test_validation_like_reference():
     with pytest.raises(ValueError):
         ds.with_encoding("onehot_cf")  # ragged length
     assert ds.with_len(64).with_encoding("onehot_cf").encoding == "onehot_cf"
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(FileNotFoundError):
         Dataset.open("/nowhere")

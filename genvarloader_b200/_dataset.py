@@ -353,6 +353,18 @@ class Dataset:
                 out_reshape = flat.shape
         return np.asarray(flat, np.int64).ravel(), squeeze, out_reshape
 
+    # ------------------------------------------------------------------ iteration (reference: to_dataloader, _impl.py:1963-2072)
+    def to_dataloader(self, batch_size: int = 1, shuffle: bool = False, sampler=None, num_workers: int = 0, collate_fn=None,
+                      pin_memory: bool = False, drop_last: bool = False, generator=None, *, return_indices: bool = False,
+                      transform=None, **ignored) -> "BatchLoader":
+        """Batches over the flat `(region, sample)` index like the reference's DataLoader (which wraps its sampler in a
+        `BatchSampler` so that the dataset is indexed with lists of indices).  The batches are born on the GPU, so
+        there are no workers, no pinning and no collation: `num_workers`, `pin_memory`, `collate_fn` and the
+        buffered modes are accepted and ignored.  `generator`: seed / numpy Generator / torch.Generator for `shuffle`."""
+        if sampler is not None and shuffle:
+            raise ValueError("sampler option is mutually exclusive with shuffle")
+        return BatchLoader(self, int(batch_size), bool(shuffle), sampler, bool(drop_last), generator, bool(return_indices), transform)
+
     # ------------------------------------------------------------------ the hot path
     def __getitem__(self, idx):
         """Reference: `Dataset.__getitem__` _impl.py:2074-2121 -> `_query.getitem` _query.py:66-204."""
@@ -586,3 +598,42 @@ class _Packer:
         a, off = self.items[i]
         tdt = torch.from_numpy(np.empty(0, a.dtype)).dtype
         return self.dev[off: off + a.nbytes].view(tdt).view(a.shape)
+
+
+class BatchLoader:
+    """Re-iterable batch iterator over a `Dataset` (see `Dataset.to_dataloader`)."""
+
+    def __init__(self, ds: Dataset, batch_size: int, shuffle: bool, sampler, drop_last: bool, generator, return_indices: bool,
+                 transform):
+        if batch_size < 1:
+            raise ValueError("batch_size must be a positive integer")
+        self.ds, self.batch_size, self.shuffle, self.sampler = ds, batch_size, shuffle, sampler
+        self.drop_last, self.return_indices, self.transform = drop_last, return_indices, transform
+        if generator is None or isinstance(generator, (int, np.integer)):
+            self._rng = np.random.default_rng(generator)
+        elif isinstance(generator, np.random.Generator):
+            self._rng = generator
+        else:  # torch.Generator
+            self._rng = np.random.default_rng(int(generator.initial_seed()))
+
+    def __len__(self) -> int:
+        n = len(self.sampler) if self.sampler is not None else len(self.ds)
+        return n // self.batch_size if self.drop_last else -(-n // self.batch_size)
+
+    def __iter__(self):
+        if self.sampler is not None:
+            order = np.fromiter(iter(self.sampler), np.int64)
+        elif self.shuffle:
+            order = self._rng.permutation(len(self.ds))
+        else:
+            order = np.arange(len(self.ds), dtype=np.int64)
+        n_s = self.ds.n_samples
+        for lo in range(0, len(order), self.batch_size):
+            idx = order[lo: lo + self.batch_size]
+            if len(idx) < self.batch_size and self.drop_last:
+                return
+            r, s_ = idx // n_s, idx % n_s
+            batch = self.ds[r, s_]
+            if self.return_indices:  # indices into the NON-subset dataset, like the reference
+                batch = (*batch, self.ds._r_idx[r], self.ds._s_idx[s_]) if isinstance(batch, tuple) else (batch, self.ds._r_idx[r], self.ds._s_idx[s_])
+            yield self.transform(batch) if self.transform is not None else batch

@@ -74,3 +74,36 @@ def test_validation_like_reference():
     assert ds.with_len(64).with_encoding("onehot_cf").encoding == "onehot_cf"
     with pytest.raises(FileNotFoundError):
         Dataset.open("/nowhere")
+
+
+def test_batch_loader_host_logic():
+    """BatchLoader: lengths, ordering, drop_last, sampler exclusivity (no GPU: a stub dataset records the indices)."""
+    from genvarloader_b200._dataset import BatchLoader
+
+    class Stub:
+        n_samples = 3
+        _r_idx = np.arange(10, 14)
+        _s_idx = np.array([2, 0, 1])
+
+        def __len__(self):
+            return 12
+
+        def __getitem__(self, idx):
+            return idx
+
+    ds = Stub()
+    bl = BatchLoader(ds, 5, False, None, False, None, False, None)
+    got = list(bl)
+    assert len(bl) == 3 and [len(b[0]) for b in got] == [5, 5, 2]
+    assert (np.concatenate([b[0] * 3 + b[1] for b in got]) == np.arange(12)).all()
+    assert len(BatchLoader(ds, 5, False, None, True, None, False, None)) == 2
+    sh = BatchLoader(ds, 4, True, None, False, 7, True, None)
+    a, b = list(sh), list(sh)
+    flat = np.sort(np.concatenate([x[0] * 3 + x[1] for x in a]))  # (the stub's batch is the (r, s) tuple; indices are appended)
+    assert (flat == np.arange(12)).all() and a[0][2].min() >= 10   # epoch covers everything; indices are non-subset ones
+    assert any((x[0] != y[0]).any() for x, y in zip(a, b))          # reshuffled every epoch
+    smp = BatchLoader(ds, 2, False, [3, 1, 0], False, None, False, lambda t: ("x", t))
+    out = list(smp)
+    assert len(smp) == 2 and out[0][0] == "x" and (out[0][1][0] == np.array([1, 0])).all()
+    with pytest.raises(ValueError):
+        BatchLoader(ds, 0, False, None, False, None, False, None)

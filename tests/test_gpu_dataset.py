@@ -180,3 +180,20 @@ def test_exonic_filter_and_subset(env):
     keep, ko = O.choose_exonic_variants(regions[:, 1], regions[:, 2], goi, d.geno_v_idxs, d.geno_offsets, d.v_starts, d.ilens)
     exp, eoo = O.reconstruct_haplotypes_fused(*_hap_args(d, regions, np.zeros(goi.shape, np.int32), goi, -1), keep, ko, to_rc)
     assert (out.offsets.cpu().numpy() == eoo).all() and (out.data.cpu().numpy() == exp).all()
+
+
+def test_to_dataloader_batches_match_direct_indexing(env):
+    """`to_dataloader` (reference _impl.py:1963-2072): batches over the flat (region, sample) index, born on the GPU."""
+    d, ds, O, _ = env
+    dsl = ds.with_len(1024).with_tracks(False).with_encoding("onehot")
+    dl = dsl.to_dataloader(batch_size=7, shuffle=False, return_indices=True, num_workers=4, pin_memory=True)
+    n = 0
+    for k, (x, r, s) in enumerate(dl):
+        assert x.is_cuda and x.shape[1:] == (d.ploidy, 1024, 4)
+        idx = np.arange(k * 7, min((k + 1) * 7, len(dsl)))
+        assert (r == idx // dsl.n_samples).all() and (s == idx % dsl.n_samples).all()
+        assert (x == dsl[idx // dsl.n_samples, idx % dsl.n_samples]).all()
+        n += x.shape[0]
+    assert n == len(dsl) and len(dl) == -(-len(dsl) // 7)
+    sh = dsl.to_dataloader(batch_size=16, shuffle=True, drop_last=True, generator=3)
+    assert sum(b.shape[0] for b in sh) == (len(dsl) // 16) * 16

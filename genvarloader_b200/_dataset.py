@@ -69,6 +69,9 @@ class Dataset:
     region_subset: object = None
     sample_subset: object = None
     region_map: object = None                         # input-BED row -> storage row (datasets opened from disk)
+    splice_rows: object = None                        # spliced: tuple of int64 arrays of STORAGE region indices, one per splice row
+    splice_names: object = None                       # spliced: names of the splice rows (or None)
+    bed_columns: object = None                        # opened datasets: extra input-BED columns (name -> array, input order)
 
     # ------------------------------------------------------------------ construction
     @classmethod
@@ -129,13 +132,14 @@ class Dataset:
         ds = cls(engine=eng, full_regions=a["full_regions"], sample_names=tuple(samples), ploidy=ploidy,
                  max_jitter=a["max_jitter"], track_kinds=dict(a["track_kinds"]), active_tracks=tuple(a["track_kinds"]),
                  sequence_type="haplotypes" if has_geno else None, rng=np.random.default_rng(rng),
-                 region_map=np.ascontiguousarray(a["region_map"], np.int64))
+                 region_map=np.ascontiguousarray(a["region_map"], np.int64), bed_columns=a.get("bed_columns"))
         return ds.with_settings(jitter=jitter, deterministic=deterministic, rc_neg=rc_neg)
 
     # ------------------------------------------------------------------ properties (reference: _impl.py:954-1110)
     @property
     def n_regions(self) -> int:
-        return len(self._r_idx)
+        """Number of regions -- of SPLICE ROWS when the dataset is spliced (reference _impl.py:1001-1005)."""
+        return len(self.splice_rows) if self.splice_rows is not None else len(self._r_idx)
 
     @property
     def n_samples(self) -> int:
@@ -213,11 +217,13 @@ class Dataset:
         """Reference: `Dataset.with_settings`, _impl.py:228-499 (hot-path settings only)."""
         if min_af not in (None, False) or max_af not in (None, False):
             raise NotImplementedError("Filtering by AF is not supported for haplotype output yet.")  # _haps.py:695-698
-        if splice_info not in (None, False):
-            raise NotImplementedError("Splicing is outside the scope of the B200 hot path (SURVEY.md 8f-3).")
+        kw = {}
+        if splice_info is False:
+            kw["splice_rows"], kw["splice_names"] = None, None
+        elif splice_info is not None:
+            kw["splice_rows"], kw["splice_names"] = self._build_splice_rows(splice_info)
         if unsupported:
             raise NotImplementedError(f"settings outside the hot-path scope: {sorted(unsupported)}")
-        kw = {}
         if jitter is not None:
             kw["jitter"] = int(jitter)
         if rng is not None:
@@ -353,6 +359,113 @@ class Dataset:
                 out_reshape = flat.shape
         return np.asarray(flat, np.int64).ravel(), squeeze, out_reshape
 
+    # ------------------------------------------------------------------ splicing (reference: _splice.py, _query.py:206-330)
+    def _build_splice_rows(self, splice_info):
+        """Splice rows = ordered lists of regions (e.g. the exons of a transcript) whose haplotypes are concatenated.
+
+        `splice_info` follows the reference (`SpliceMap.from_bed`, _splice.py:163-230) for datasets opened from disk:
+        a column name of the input BED (rows with the same value form a splice row, in BED order) or a
+        `(id_column, order_column)` pair (elements sorted by the second column).  In-memory datasets -- and any
+        dataset -- may pass the mapping directly: `{name: [region indices]}` or a sequence of index sequences
+        (indices address regions like `ds[r, s]` does)."""
+        r_map = self._r_idx
+        names = None
+        if isinstance(splice_info, (str, tuple)) and all(isinstance(x, str) for x in np.atleast_1d(splice_info)):
+            cols = self.bed_columns or {}
+            id_col, order_col = (splice_info, None) if isinstance(splice_info, str) else splice_info
+            for c in (id_col, order_col):
+                if c is not None and c not in cols:
+                    raise ValueError(f"column {c!r} is not in the dataset's input BED (available: {sorted(cols)})")
+            ids = np.asarray(cols[id_col])
+            groups: dict = {}
+            for i, v in enumerate(ids.tolist()):
+                groups.setdefault(v, []).append(i)
+            if order_col is not None:
+                order = np.asarray(cols[order_col])
+                groups = {k: sorted(v, key=lambda i: order[i]) for k, v in groups.items()}
+            names, lists = list(groups), list(groups.values())
+        elif isinstance(splice_info, dict):
+            names, lists = list(splice_info), list(splice_info.values())
+        else:
+            lists = list(splice_info)
+        rows = []
+        for l in lists:
+            a = _idx_to_array(np.asarray(l, np.int64), len(r_map))
+            if a.ndim != 1 or a.size == 0:
+                raise ValueError("every splice row needs at least one region index")
+            rows.append(np.ascontiguousarray(r_map[a], np.int64))
+        return tuple(rows), (tuple(names) if names is not None else None)
+
+    @property
+    def is_spliced(self) -> bool:
+        return self.splice_rows is not None
+
+    def _getitem_spliced(self, idx):
+        """One ragged haplotype per (splice row, sample, ploid): the row's elements are reconstructed as separate
+        kernel rows, laid out in (row, sample, ploid, element) order (the reference's permuted write,
+        _splice.py:56-160 / _haps.py:872-919), so the concatenation is free and the group offsets are the kernel's
+        row offsets sampled at cell boundaries.  Negative-strand elements are reverse-complemented one by one
+        (_query.py:269-288); jitter and fixed lengths do not apply to spliced output."""
+        if self.sequence_type not in ("haplotypes", "annotated"):
+            raise NotImplementedError("spliced output is implemented for 'haplotypes' and 'annotated' sequences")
+        if self.jitter or isinstance(self.output_length, (int, np.integer)):
+            raise ValueError("spliced datasets return ragged haplotypes: use with_len('ragged') and jitter=0")
+        rows_all = self.splice_rows
+        n_rows_all, n_s_all = len(rows_all), len(self._s_idx)
+        if not isinstance(idx, tuple):
+            idx = (idx, slice(None))
+        r_sel, s_sel = idx
+        ri = np.atleast_1d(_idx_to_array(r_sel, n_rows_all))
+        si = np.atleast_1d(self._s_idx[_idx_to_array(s_sel, n_s_all)])
+        is_int = lambda x: isinstance(x, (int, np.integer))
+        is_basic = lambda x: isinstance(x, (int, np.integer, slice))
+        if not is_basic(r_sel) and not is_basic(s_sel):  # paired
+            ri, si = np.broadcast_arrays(ri, si)
+            pairs = list(zip(ri.ravel().tolist(), si.ravel().tolist()))
+            outer = (len(pairs),)
+        else:
+            pairs = [(r, s_) for r in ri.ravel().tolist() for s_ in si.ravel().tolist()]
+            outer = (ri.size, si.size)
+        eng, dev, p, S = self.engine, self.engine.device, self.ploidy, len(self.sample_names)
+        q_reg, q_goi, cell_len = [], [], []
+        for r, s_ in pairs:
+            elems = rows_all[r]
+            for e in range(p):
+                q_reg.append(elems)
+                q_goi.append((elems * S + s_) * p + e)
+                cell_len.append(len(elems))
+        q_reg = np.concatenate(q_reg)
+        goi = np.concatenate(q_goi)[:, None].astype(np.int64)
+        regions = self.full_regions[q_reg]
+        to_rc = (regions[:, 3] == -1) if self.rc_neg else None
+        pk = _Packer(dev)
+        i_reg, i_goi = pk.add(regions[:, :3], np.int32), pk.add(goi, np.int64)
+        i_sh = pk.add(np.zeros((len(goi), 1), np.int32), np.int32)
+        i_rc = pk.add(to_rc, np.uint8) if to_rc is not None else None
+        cell_starts = np.concatenate([[0], np.cumsum(cell_len)]).astype(np.int64)
+        i_cs = pk.add(cell_starts, np.int64)
+        pk.upload()
+        keep = keep_off = None
+        if self.var_filter == "exonic":
+            keep, keep_off = self._exonic_keep(goi, regions)
+        oo = eng.plan(pk.get(i_reg), pk.get(i_sh), pk.get(i_goi), -1, eng.max_records(goi), keep, keep_off,
+                      pk.get(i_rc) if i_rc is not None else None)
+        total = eng.total()
+        group_offsets = oo[pk.get(i_cs)]
+        shape = (*outer, p, None)
+        if self.sequence_type == "annotated":
+            h, av, ap = eng.execute("annotated")
+            out = RaggedAnnotatedHaps(Ragged(h, group_offsets, shape), Ragged(av, group_offsets, shape), Ragged(ap, group_offsets, shape))
+        elif self.encoding == "onehot":
+            out = Ragged(eng.execute("onehot").view(total, 4), group_offsets, shape)
+        elif self.encoding == "bytes":
+            out = Ragged(eng.execute("haplotypes"), group_offsets, shape)
+        else:
+            raise ValueError("channels-first one-hot needs a fixed output length; spliced output is ragged")
+        if is_int(r_sel) and is_int(s_sel):
+            out = out.squeeze(0).squeeze(0) if hasattr(out, "squeeze") else out
+        return out
+
     # ------------------------------------------------------------------ iteration (reference: to_dataloader, _impl.py:1963-2072)
     def to_dataloader(self, batch_size: int = 1, shuffle: bool = False, sampler=None, num_workers: int = 0, collate_fn=None,
                       pin_memory: bool = False, drop_last: bool = False, generator=None, *, return_indices: bool = False,
@@ -370,6 +483,8 @@ class Dataset:
         """Reference: `Dataset.__getitem__` _impl.py:2074-2121 -> `_query.getitem` _query.py:66-204."""
         if self.sequence_type is None and not self.active_tracks:
             raise ValueError("Dataset has neither sequences nor tracks active.")
+        if self.splice_rows is not None:
+            return self._getitem_spliced(idx)
         ds_idx, squeeze, out_reshape = self._parse_idx(idx)
         S = len(self.sample_names)
         r_idx, s_idx = ds_idx // S, ds_idx % S

@@ -164,8 +164,10 @@ def read_dataset_arrays(path, reference=None) -> dict:
         raise ValueError("input_regions.arrow: r_idx_map is not a permutation of the region indices")
     full_regions = np.empty((n_regions, 4), np.int32)
     full_regions[r_idx_map] = np.stack([c_idx, starts, ends, strand], 1)
+    extra = {n: np.asarray(c.to_pylist()) for n, c in cols.items()
+             if n not in ("chrom", "chromStart", "chromEnd", "strand", "r_idx_map")}  # e.g. transcript ids for splicing
     out = dict(samples=samples, contigs=contigs, ploidy=ploidy, max_jitter=max_jitter, full_regions=full_regions,
-               region_map=r_idx_map, tracks={}, track_kinds={})
+               region_map=r_idx_map, tracks={}, track_kinds={}, bed_columns=extra)
 
     # ---- genotypes ----
     gdir = path / "genotypes"

@@ -39,3 +39,70 @@ def test_open_matches_in_memory_dataset(cuda_device, tmp_path):
     # subset by input-order region indices
     sub = dsk.subset_to(regions=[2, 5], samples=["c"]).with_len(L).with_tracks(False)
     assert (sub[:, :] == mem.with_len(L).with_tracks(False)[order[[2, 5]], [2]].reshape(sub[:, :].shape)).all()
+
+
+def test_spliced_haplotypes_are_concatenated_elements(cuda_device, tmp_path):
+    """Spliced output (reference _splice.py / _query.py:206-330): the haplotype of a splice row is the concatenation of
+    its elements' haplotypes, element by element reverse-complemented on negative strands -- checked against the
+    unspliced (oracle-verified) output; splice rows from an explicit mapping and from input-BED columns."""
+    import pyarrow as pa
+    import pyarrow.ipc as ipc
+
+    from genvarloader_b200 import Dataset, synth
+
+    d = synth.make_dataset(29, 150_000, 3, 12, 900, 8.0, neg_strand_frac=0.5, straddle_ends=False, max_indel=9)
+    mem = Dataset.from_synth(cuda_device, d, rng=5).with_tracks(False)
+    rows = {"tA": [3, 0, 7], "tB": [5], "tC": [11, 10, 9, 8]}
+    sp = mem.with_settings(splice_info=rows)
+    assert sp.is_spliced and sp.n_regions == 3 and len(sp) == 3 * mem.n_samples
+
+    def expect(ds_plain, row, s, e):
+        parts = []
+        for r in row:
+            x = ds_plain[r, s]          # Ragged (ploidy, ~len)
+            o = x.offsets.cpu().numpy()
+            parts.append(x.data[o[e]: o[e + 1]].cpu().numpy())
+        return np.concatenate(parts)
+
+    for enc in ("bytes", "onehot"):
+        a = sp.with_encoding(enc)
+        plain = mem.with_encoding(enc)
+        out = a[:, :]
+        assert out.shape == (3, mem.n_samples, d.ploidy, None)
+        o = out.offsets.cpu().numpy()
+        k = 0
+        for ri, row in enumerate(rows.values()):
+            for s in range(mem.n_samples):
+                for e in range(d.ploidy):
+                    got = out.data[o[k]: o[k + 1]].cpu().numpy()
+                    assert (got == expect(plain, row, s, e)).all(), (enc, ri, s, e)
+                    k += 1
+    one = sp[1, 2]
+    assert one.shape == (d.ploidy, None)
+    assert (one.data.cpu().numpy() == np.concatenate([expect(mem, rows["tB"], 2, e) for e in range(d.ploidy)])).all()
+    pair = sp[[2, 0], [1, 1]]
+    assert pair.shape == (2, d.ploidy, None)
+    ann = sp.with_seqs("annotated")[0, 0]
+    assert (ann.haps.data.cpu().numpy() == sp[0, 0].data.cpu().numpy()).all()
+    # the same rows from BED columns of an opened dataset: (id column, order column)
+    order = np.arange(d.n_regions)
+    write_gvl_dataset(tmp_path / "ds", d, ["chr1"], ["a", "b", "c"], order)
+    with pa.memory_map(str(tmp_path / "ds" / "input_regions.arrow"), "r") as src:
+        bed = ipc.open_file(src).read_all()
+    tid = ["x"] * d.n_regions
+    rank = [0] * d.n_regions
+    for name, idxs in rows.items():
+        for k, r in enumerate(idxs):
+            tid[r], rank[r] = name, k
+    bed = bed.append_column("transcript", pa.array(tid)).append_column("exon", pa.array(rank))
+    with pa.OSFile(str(tmp_path / "bed.new"), "wb") as f, ipc.new_file(f, bed.schema) as w:  # (bed is a view of the mapped file)
+        w.write_table(bed)
+    del bed
+    (tmp_path / "bed.new").replace(tmp_path / "ds" / "input_regions.arrow")
+    write_fasta(tmp_path / "ref.fa", d.reference, d.ref_offsets, ["chr1"])
+    dsk = Dataset.open(tmp_path / "ds", tmp_path / "ref.fa", device=cuda_device).with_tracks(False)
+    spd = dsk.with_settings(splice_info=("transcript", "exon"))
+    names = list(spd.splice_names)
+    assert set(names) == {"tA", "tB", "tC", "x"}
+    got = spd[names.index("tC"), 1]
+    assert (got.data.cpu().numpy() == sp[2, 1].data.cpu().numpy()).all() and (got.offsets.cpu().numpy() == sp[2, 1].offsets.cpu().numpy()).all()

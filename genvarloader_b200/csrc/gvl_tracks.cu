@@ -289,6 +289,33 @@ struct TrkSrc {
     }
 };
 
+// Lagrange interpolation through K anchors on each side of the insertion (src/tracks/mod.rs:138-188), evaluated at
+// index i of the written values; same operation order as the reference (term = y_a * prod_b (x - x_b) / (x_a - x_b)).
+template <int K>
+__device__ __forceinline__ float lagrange_fill(const TrkSrc &S, int64_t v_len, int64_t v_rel_pos, int64_t i) {
+    double xs[2 * K], ys[2 * K];
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        xs[j] = -(double)j;
+        ys[j] = (double)S.at(imax64(v_rel_pos - j, 0));
+        xs[K + j] = (double)v_len + (double)j;
+        ys[K + j] = (double)S.at(imin64(v_rel_pos + 1 + j, S.track_n - 1));
+    }
+    const double x = (double)i;
+    double acc = 0.0;
+#pragma unroll
+    for (int a = 0; a < 2 * K; a++) {
+        double term = ys[a];
+#pragma unroll
+        for (int b = 0; b < 2 * K; b++) {
+            if (b == a) continue;
+            term = __dmul_rn(term, __ddiv_rn(__dsub_rn(x, xs[b]), __dsub_rn(xs[a], xs[b])));
+        }
+        acc = __dadd_rn(acc, term);
+    }
+    return (float)acc;
+}
+
 // apply_insertion_fill, src/tracks/mod.rs:87-190, for ONE written value (index i within the write).
 __device__ float insertion_fill_value(const TrkSrc &S, int strategy, double param, int64_t v_len, int64_t v_rel_pos,
                                       int64_t i, int64_t out_pos, uint64_t base_seed, uint64_t query, uint64_t hap) {
@@ -307,31 +334,11 @@ __device__ float insertion_fill_value(const TrkSrc &S, int strategy, double para
         int64_t offset = (int64_t)(seed % pool_size);
         return S.at(pool_lo + offset);
     } else {  // GVL_FILL_INTERPOLATE :138-188
-        int64_t order = (int64_t)param;
-        int64_t k = (order + 1 + 1) / 2;
-        int n_anchors = (int)(2 * k);
-        double xs[8], ys[8];
-        for (int j = 0; j < (int)k; j++) {
-            int64_t ri = imax64(v_rel_pos - j, 0);
-            xs[j] = -(double)j;
-            ys[j] = (double)S.at(ri);
-        }
-        for (int j = 0; j < (int)k; j++) {
-            int64_t ri = imin64(v_rel_pos + 1 + j, S.track_n - 1);
-            xs[k + j] = (double)v_len + (double)j;
-            ys[k + j] = (double)S.at(ri);
-        }
-        double x = (double)i;
-        double acc = 0.0;
-        for (int a = 0; a < n_anchors; a++) {
-            double term = ys[a];
-            for (int b = 0; b < n_anchors; b++) {
-                if (b == a) continue;
-                term = __dmul_rn(term, __ddiv_rn(__dsub_rn(x, xs[b]), __dsub_rn(xs[a], xs[b])));
-            }
-            acc = __dadd_rn(acc, term);
-        }
-        return (float)acc;
+        const int64_t order = (int64_t)param;
+        const int64_t k = (order + 1 + 1) / 2;
+        // k anchors on each side: 2 anchors for order 1, 4 for orders 2 and 3 -- fixed-size instantiations keep the
+        // anchors in registers and let the divisions overlap; the operation order is the reference's
+        return k == 1 ? lagrange_fill<1>(S, v_len, v_rel_pos, i) : lagrange_fill<2>(S, v_len, v_rel_pos, i);
     }
 }
 
@@ -453,6 +460,17 @@ __global__ void __launch_bounds__(TRK_THREADS, 4) trk_exec_kernel(TrkExecParams 
             r += m_new;
             continue;
         }
+        // Later passes: the window only moves forward, so the intervals it needs start at the previous pass's
+        // cursor.  Their loads are issued here, together with the record loads below (one round trip, not three).
+        int32_t pre_st = INT32_MAX, pre_en = 0;
+        float pre_v = 0.0f;
+        const bool pre_ok = !T.dense && itv_prev >= 0;
+        if (pre_ok && itv_prev + (int64_t)threadIdx.x < itv_hi) {
+            const int64_t it = itv_prev + threadIdx.x;
+            pre_st = T.itv_starts[it];
+            pre_en = T.itv_ends[it];
+            pre_v = T.itv_values[it];
+        }
         __syncthreads();
         for (int i = threadIdx.x; i < m; i += TRK_THREADS) {
             int64_t idx = r + i;
@@ -490,59 +508,59 @@ __global__ void __launch_bounds__(TRK_THREADS, 4) trk_exec_kernel(TrkExecParams 
         } else {
             for (int i = threadIdx.x; i < TRK_WIN / 32 + 4; i += TRK_THREADS) s_flag[i] = 0u;
         }
-        if (!T.dense && threadIdx.x < 32) {
-            // first interval whose end is > q_start + w0  (ends are sorted: intervals do not overlap).  The first pass
-            // searches the slot; later passes (the window only moves forward) count over the next 256 ends.
-            const int32_t target = (int32_t)imin64(q_start + w0, INT32_MAX);
-            int64_t first;
-            if (itv_prev < 0 || target < tgt_prev) {  // (unsorted lists can move the window backwards)
-                first = warp_upper_le(T.itv_ends, itv_lo, itv_hi, target) + 1;
-            } else {
-                int cnt = 0;
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int64_t it = itv_prev + 32 * u + threadIdx.x;
-                    cnt += (it < itv_hi && T.itv_ends[it] <= target) ? 1 : 0;
-                }
-                cnt = __reduce_add_sync(0xffffffffu, cnt);
-                first = itv_prev + cnt;
-                if (cnt == 256) first = warp_upper_le(T.itv_ends, first, itv_hi, target) + 1;
-            }
+        const int32_t target = (int32_t)imin64(q_start + w0, INT32_MAX);  // intervals ending at or before it are behind the window
+        const bool spec = pre_ok && target >= tgt_prev;  // (unsorted lists can move the window backwards: search again)
+        if (!T.dense && !spec && threadIdx.x < 32) {
+            // first interval whose end is > q_start + w0 (ends are sorted: intervals do not overlap)
+            const int64_t first = warp_upper_le(T.itv_ends, itv_lo, itv_hi, target) + 1;
             if (threadIdx.x == 0) s_itv_first = first;
         }
         __syncthreads();
         TRK_TR(2);
         if (!T.dense && w1 > w0) {
             // Paint the window as a run-length expansion (src/intervals.rs:19-126 restated for one window):
-            //  1. every thread fetches ONE interval (coalesced) and drops two markers: 0 at its end, its value at
+            //  1. every thread holds ONE interval (coalesced loads) and drops two markers: 0 at its end, its value at
             //     its (clipped) start -- ends first, so that an adjacent interval's start wins;
-            //  2. every thread then owns 37 consecutive window positions (odd stride: no bank conflicts), finds the
-            //     value in effect at its first position with a block-wide scan over "last marker" pairs, and fills.
+            //  2. every thread then owns 36 consecutive window positions, finds the value in effect at its first
+            //     position with a block-wide scan over "last marker" pairs, and fills.
             const int nwin = (int)(w1 - w0);
-            for (int64_t base = s_itv_first; base < itv_hi; base += TRK_THREADS) {
+            int64_t base = spec ? itv_prev : s_itv_first;
+            int64_t first = base;      // cursor for the next pass: intervals before it end at or before `target`
+            bool counting = true;
+            for (bool use_pre = spec;; use_pre = false) {
                 const int64_t it = base + threadIdx.x;
-                int64_t st_ = INT64_MAX, en_ = 0;
+                int32_t st_a = INT32_MAX, en_a = 0;
                 float v_ = 0.0f;
-                if (it < itv_hi) {
-                    st_ = (int64_t)T.itv_starts[it] - q_start;
-                    en_ = (int64_t)T.itv_ends[it] - q_start;
+                if (use_pre) {
+                    st_a = pre_st, en_a = pre_en, v_ = pre_v;
+                } else if (it < itv_hi) {
+                    st_a = T.itv_starts[it];
+                    en_a = T.itv_ends[it];
                     v_ = T.itv_values[it];
                 }
-                const bool live = st_ < w1 && en_ > w0 && en_ > st_;  // overlaps the window (also :72-76: start >= length)
+                const int64_t st_ = (int64_t)st_a - q_start, en_ = (int64_t)en_a - q_start;
+                const bool have = it < itv_hi;
+                const bool live = have && st_ < w1 && en_ > w0 && en_ > st_;  // overlaps the window (also :72-76: start >= length)
                 if (live && en_ < w1) {
                     const int x = (int)(en_ - w0);
                     s_win[x] = 0.0f;
                     atomicOr(&s_flag[x >> 5], 1u << (x & 31));
                 }
-                __syncthreads();
+                const int behind = __syncthreads_count(have && en_a <= target);  // (also orders the two marker phases)
+                if (counting) {
+                    first += behind;
+                    counting = behind == TRK_THREADS;
+                }
                 if (live) {
                     const int x = (int)(imax64(st_, w0) - w0);
                     s_win[x] = v_;
                     atomicOr(&s_flag[x >> 5], 1u << (x & 31));
                 }
                 // the block stops once its LAST interval starts at or beyond the window end (sorted starts)
-                if (__syncthreads_or(threadIdx.x == TRK_THREADS - 1 && st_ >= w1)) break;
+                if (__syncthreads_or(threadIdx.x == TRK_THREADS - 1 && (!have || st_ >= w1))) break;
+                base += TRK_THREADS;
             }
+            if (threadIdx.x == 0) s_itv_first = first;
             __syncthreads();
             TRK_TR(3);
             constexpr int CH = 36;  // 9 float4 per thread: conflict-free 128-bit accesses, 36 * 256 = TRK_WIN

@@ -74,6 +74,14 @@ if os.environ.get("GVL_LIB_NAME", "").startswith("libgvl_trace"):
     a = a[a[:, 0] > 0]
     t0 = a[:, 0].min()
     print(f"trace: {len(a)} CTAs; kernel span {(a[:, :60].max() - t0) / 1e3:.1f} us")
+    full = tr.cpu().numpy().reshape(-1, 64)
+    n_cta = full.shape[0]
+    ends = full[:, :60].max(1)
+    live = full[:, 0] > 0
+    half = np.flatnonzero(live).max() // 2 + 1
+    for nm, sel in (("track 0 (Repeat5p)", live & (np.arange(n_cta) < half)), ("track 1 (Interpolate)", live & (np.arange(n_cta) >= half))):
+        e_ = (ends[sel] - t0) / 1e3
+        print(f"  {nm}: CTA end p10 {np.percentile(e_, 10):.1f} p50 {np.percentile(e_, 50):.1f} p90 {np.percentile(e_, 90):.1f} max {e_.max():.1f} us")
     names_ = ["stage records", "window/interval search", "markers", "scan+fill", "group loop (output)"]
     for ps in range(8):
         st = a[:, ps * 6:ps * 6 + 6]

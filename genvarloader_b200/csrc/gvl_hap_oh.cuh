@@ -21,8 +21,8 @@
 namespace gvl {
 
 constexpr int OH_GROUP = 256;                                  // positions per warp step (8 per lane)
-constexpr int OH_MAX_TILE = 16384;                             // haplotype positions per CTA, at most
-constexpr int OH_MAX_GROUPS = OH_MAX_TILE / OH_GROUP + 2;      // groups a pass can touch (+ misaligned edges)
+constexpr int OH_MAX_TILE_WANTED = 16384;                      // haplotype positions per CTA, at most
+
 #ifndef GVL_OH_THREADS
 #define GVL_OH_THREADS 128
 #endif
@@ -31,6 +31,10 @@ constexpr int OH_MAX_GROUPS = OH_MAX_TILE / OH_GROUP + 2;      // groups a pass 
 #endif
 constexpr int OH_THREADS = GVL_OH_THREADS;                     // threads per CTA of the packed kernel
 constexpr int OH_MIN_CTAS = GVL_OH_MIN_CTAS;
+// one thread per group builds the group table: a pass may not touch more groups than the CTA has threads
+constexpr int OH_MAX_TILE = OH_MAX_TILE_WANTED < (OH_THREADS - 2) * OH_GROUP ? OH_MAX_TILE_WANTED : (OH_THREADS - 2) * OH_GROUP / 1024 * 1024;
+constexpr int OH_MAX_GROUPS = OH_MAX_TILE / OH_GROUP + 2;      // groups a pass can touch (+ misaligned edges)
+static_assert(OH_MAX_GROUPS <= OH_THREADS && OH_MAX_TILE >= 1024, "group table: one thread per group");
 constexpr int OH_UNROLL = 4;                                   // groups per warp whose loads are issued together
 
 struct OhRecs {

@@ -369,11 +369,22 @@ __global__ void __launch_bounds__(TRK_THREADS, 4) trk_exec_kernel(TrkExecParams 
     __shared__ float s_cval[TRK_THREADS / 32];
     __shared__ int32_t s_gt[TRK_TILE / 128 + 2];  // per group of the pass: window offset of a plain group, or -1
     __shared__ int s_chas[TRK_THREADS / 32];
+    __shared__ int s_stop;
     __shared__ int64_t s_lo, s_hi, s_itv_first;
 
     const int64_t track = blockIdx.x / P.grid_per_track;
     const int64_t b = blockIdx.x % P.grid_per_track;
     if (b >= P.tile_off[P.n_work]) return;
+#ifdef GVL_TRK_STAGGER_NS
+    // CTAs that share an SM start GVL_TRK_STAGGER_NS apart, so that one CTA's preparation phases (latency) overlap
+    // another's output phase (bandwidth) instead of all CTAs of the GPU marching in lock-step
+    {
+        unsigned nsm;
+        asm volatile("mov.u32 %0, %nsmid;" : "=r"(nsm));
+        const unsigned phase = (blockIdx.x / nsm) & 3u;
+        if (phase) __nanosleep(phase * GVL_TRK_STAGGER_NS);
+    }
+#endif
     int64_t row;
     {
         int64_t lo = 0, hi = P.n_work;
@@ -546,6 +557,7 @@ __global__ void __launch_bounds__(TRK_THREADS, 4) trk_exec_kernel(TrkExecParams 
                     s_win[x] = 0.0f;
                     atomicOr(&s_flag[x >> 5], 1u << (x & 31));
                 }
+                if (threadIdx.x == TRK_THREADS - 1) s_stop = (!have || st_ >= w1);  // sorted starts: the block's last interval decides
                 const int behind = __syncthreads_count(have && en_a <= target);  // (also orders the two marker phases)
                 if (counting) {
                     first += behind;
@@ -556,8 +568,8 @@ __global__ void __launch_bounds__(TRK_THREADS, 4) trk_exec_kernel(TrkExecParams 
                     s_win[x] = v_;
                     atomicOr(&s_flag[x >> 5], 1u << (x & 31));
                 }
-                // the block stops once its LAST interval starts at or beyond the window end (sorted starts)
-                if (__syncthreads_or(threadIdx.x == TRK_THREADS - 1 && (!have || st_ >= w1))) break;
+                if (s_stop) break;  // the block's LAST interval starts at or beyond the window end
+                __syncthreads();    // (rare second block: s_stop is rewritten)
                 base += TRK_THREADS;
             }
             if (threadIdx.x == 0) s_itv_first = first;
@@ -583,13 +595,8 @@ __global__ void __launch_bounds__(TRK_THREADS, 4) trk_exec_kernel(TrkExecParams 
                 }
             }
             // (has, value) of the last marker in the chunk; scan with "right operand wins if it has one"
-            int has = mk != 0;
-            float val = 0.0f;
-            if (has) {
-#pragma unroll
-                for (int q = 0; q < CH; q++)
-                    if ((mk >> q) & 1) val = x[q];
-            }
+            const int has = mk != 0;
+            const float val = has ? s_win[b0 + 63 - __clzll((long long)mk)] : 0.0f;
             const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
             int h_in = has;
             float v_in = val;
@@ -670,9 +677,16 @@ __global__ void __launch_bounds__(TRK_THREADS, 4) trk_exec_kernel(TrkExecParams 
             const int32_t j = (int32_t)(g - row_base);
             const int32_t off = s_gt[grp];
             if (off >= 0) {
-                const float *ws = s_win + off + (rc ? 124 - 4 * lane_ : 4 * lane_);
-                *reinterpret_cast<float4 *>(out + g) =
-                    rc ? make_float4(ws[3], ws[2], ws[1], ws[0]) : make_float4(ws[0], ws[1], ws[2], ws[3]);
+                // lane l moves values l, l+32, l+64, l+96 of the group: every shared-memory read and every store is one
+                // contiguous 128-byte warp access (4 consecutive values per lane would be a 4-way bank conflict)
+                float *og = out + (g0 + 128 * (int64_t)grp);
+                const float *ws = s_win + off + (rc ? 127 - lane_ : lane_);
+                const int stp = rc ? -32 : 32;
+                const float v0 = ws[0], v1 = ws[stp], v2 = ws[2 * stp], v3 = ws[3 * stp];
+                og[lane_] = v0;
+                og[lane_ + 32] = v1;
+                og[lane_ + 64] = v2;
+                og[lane_ + 96] = v3;
                 continue;
             }
             if (c >= n_chunks) continue;

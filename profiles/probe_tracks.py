@@ -13,7 +13,8 @@ from genvarloader_b200._engine import Engine  # noqa: E402
 
 dev = torch.device("cuda", 0)
 L = 524_288
-d = synth.cfg3(n_samples=8)
+import os
+d = synth.cfg3(n_samples=8, variants_per_kb=float(os.environ.get('PROBE_VKB', 1.0)))
 eng = Engine(dev, d.reference, d.ref_offsets, d.v_starts, d.ilens, d.alt_alleles, d.alt_offsets, d.geno_v_idxs, d.geno_offsets)
 names = sorted(d.tracks)
 n_itv = 0

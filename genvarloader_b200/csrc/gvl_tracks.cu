@@ -74,19 +74,75 @@ __global__ void __launch_bounds__(TPLAN_WARPS * 32) trk_plan_kernel(TrkPlanParam
     trk_init(ts, shift, length);
     int64_t n_emit = 0, track0 = 0, prev_resume = 0;
     bool done = false;
-    for (int64_t base = 0; base < nvar && !done; base += 32) {
-        int64_t i = base + lane;
-        int32_t pos = 0, il = 0;
-        bool kp = false;
+    // chunk loader: variant i = base + lane of the row (positions, ilens, keep flag)
+    auto load_chunk = [&](int64_t base, int32_t &pos, int32_t &il, bool &kp) {
+        pos = 0, il = 0, kp = false;
+        const int64_t i = base + lane;
         if (i < nvar) {
-            int32_t vi = gv[i];
+            const int32_t vi = gv[i];
             pos = (int32_t)var_pos(P.tab, rv, i, vi);
             il = P.tab.ilens[vi];
             kp = has_keep ? (P.keep[keep_base + i] != 0) : true;
         }
+    };
+    int32_t pos, il, n_pos = 0, n_il = 0;
+    bool kp, n_kp = false;
+    load_chunk(0, pos, il, kp);
+    for (int64_t base = 0; base < nvar && !done; base += 32) {
+        if (base + 32 < nvar) load_chunk(base + 32, n_pos, n_il, n_kp);  // next chunk's gathers fly during this one
         // once the shift is consumed a SNP (ilen 0) changes nothing (src/tracks/mod.rs:277-314: skipped or
-        // "writes nothing"), so only indels take a serial step
-        unsigned mask = __ballot_sync(0xffffffffu, kp && (il != 0 || ts.shifted < ts.shift));
+        // "writes nothing"), so only indels take part
+        const bool part = kp && (il != 0 || ts.shifted < ts.shift);
+        unsigned mask = __ballot_sync(0xffffffffu, part);
+        const int64_t rel = (int64_t)pos - q_start;                        // v_rel_pos (:264)
+        const int64_t v_end = rel - imin64(il, 0) + 1;                     // v_rel_end (:267)
+        // ---- whole chunk at once: shift consumed, nothing left of the window, and every participating indel starts
+        //      at or after the end of the previous one (no overlap -> every one is applied, :277-279) ----
+        bool fast = mask != 0 && ts.shifted >= ts.shift && (n_emit == 0 || ts.track_idx == prev_resume) &&
+                    !__any_sync(0xffffffffu, part && rel < 0);
+        int64_t prev_end = ts.track_idx;
+        if (fast) {
+            const unsigned below = mask & ((1u << lane) - 1u);
+            const int pl = below ? 31 - __clz(below) : 0;
+            const int64_t pe = __shfl_sync(0xffffffffu, v_end, pl);
+            if (below) prev_end = pe;
+            fast = !__any_sync(0xffffffffu, part && rel < prev_end);
+        }
+        if (fast) {
+            const int64_t v_len = imax64(il, 0) + 1;                         // :282
+            const int64_t ref_len = part ? rel - prev_end : 0;               // track_len (:317)
+            int64_t inc = part ? ref_len + v_len : 0, scan = inc;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int64_t y = __shfl_up_sync(0xffffffffu, scan, o);
+                if (lane >= o) scan += y;
+            }
+            const int64_t a = ts.out_idx + (scan - inc) + ref_len;           // out_idx after the span copy
+            const bool valid = part && a < ts.length;                        // :319-321 (positions grow: a prefix)
+            const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+            const bool broke = __any_sync(0xffffffffu, part && !valid);
+            const int64_t n = valid ? imin64(v_len, ts.length - a) : 0;      // writable_length (:329)
+            if (vmask) {
+                const int last = 31 - __clz(vmask);
+                if (n_emit == 0) track0 = ts.track_idx;  // span_src of the first record
+                if (valid && !overflow) {
+                    const int64_t w = rec_off + n_emit + __popc(vmask & ((1u << lane) - 1u));
+                    P.rec.a[w] = (int32_t)a;
+                    P.rec.n[w] = (int32_t)n;
+                    P.rec.src[w] = il;
+                    P.rec.resume[w] = (int32_t)v_end;
+                    P.rec.vidx[w] = (int32_t)v_len;
+                    P.rec.vpos[w] = (int32_t)rel;
+                }
+                n_emit += __popc(vmask);
+                ts.out_idx = __shfl_sync(0xffffffffu, a + n, last);
+                ts.track_idx = __shfl_sync(0xffffffffu, v_end, last);
+                prev_resume = ts.track_idx;
+                if (ts.out_idx >= ts.length) done = true;  // :359-361
+            }
+            if (broke) done = true;
+            mask = 0;
+        }
         while (mask && !done) {
             int t = __ffs(mask) - 1;
             mask &= mask - 1;
@@ -124,6 +180,7 @@ __global__ void __launch_bounds__(TPLAN_WARPS * 32) trk_plan_kernel(TrkPlanParam
                 if (ts.out_idx >= ts.length) done = true;  // :359-361
             }
         }
+        pos = n_pos, il = n_il, kp = n_kp;
     }
     if (nvar == 0) {
         track0 = 0;  // :240-246: an EMPTY variant list copies track[:length], whatever the shift

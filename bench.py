@@ -143,9 +143,10 @@ def measured_peak_gbs() -> tuple[float, str]:
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def alg_bytes(w, nvar: int) -> float:
+def alg_bytes(w, nvar: int, mode: str = "onehot") -> float:
     rows = w["pairs"] * 2
-    return rows * w["window"] * ALG_BYTES_PER_BP + nvar * ALG_BYTES_PER_VARIANT + rows * ALG_BYTES_PER_ROW
+    per_bp = {"onehot": ALG_BYTES_PER_BP, "u8": 2.0, "annotated": 10.0}[mode]
+    return rows * w["window"] * per_bp + nvar * ALG_BYTES_PER_VARIANT + rows * ALG_BYTES_PER_ROW
 
 
 def track_bytes(w) -> float:
@@ -241,7 +242,7 @@ def run_b200(args):
     batches = make_batches(d, w, n_batches, args.seed + 1, rank, world)  # this rank's shard of every global batch
     eng0 = Engine(dev, d.reference, d.ref_offsets, d.v_starts, d.ilens, d.alt_alleles, d.alt_offsets, d.geno_v_idxs,
                   d.geno_offsets)
-    step_bytes_out = rows * L * 4
+    step_bytes_out = rows * L * {"onehot": 4, "u8": 1, "annotated": 1}[args.mode]
     track_names = sorted(d.tracks)
     for nm in track_names:
         eng0.add_track(nm, *d.tracks[nm])
@@ -256,15 +257,27 @@ def run_b200(args):
                  goi=torch.from_numpy(b["goi"]).to(dev), to_rc=torch.from_numpy(b["to_rc"]).to(dev),
                  out_offsets=torch.empty(rows + 1, dtype=torch.int64, device=dev),
                  out=torch.empty(step_bytes_out, dtype=torch.uint8, device=dev), nvar=b["nvar"], graph=None)
+        if args.mode == "annotated":
+            s["av"] = torch.empty(rows * L, dtype=torch.int32, device=dev)
+            s["ap"] = torch.empty(rows * L, dtype=torch.int32, device=dev)
         if track_names:  # realigned tracks of the same batch: (n_tracks, rows, L) float32
             s["oidx"] = torch.from_numpy(np.tile(b["ds_idx"], (len(track_names), 1))).to(dev)
             s["tlen"] = torch.full((b["regions"].shape[0],), L + 4096, dtype=torch.int32, device=dev)  # window + room for deletions
             s["tout"] = torch.empty(len(track_names) * rows * L, dtype=torch.float32, device=dev)
         slots.append(s)
 
+    MODE = args.mode
+
+    def exec_(s_, out=None):
+        o = s_["out"] if out is None else out
+        if MODE == "annotated":
+            s_["eng"].execute("annotated", out=o, annot_v=s_["av"], annot_pos=s_["ap"])
+        else:
+            s_["eng"].execute("onehot" if MODE == "onehot" else "haplotypes", out=o)
+
     def step(s):
         s["eng"].plan(s["regions"], s["shifts"], s["goi"], L, s["nvar"], to_rc=s["to_rc"], out_offsets=s["out_offsets"])
-        s["eng"].execute("onehot", out=s["out"])
+        exec_(s)
         if track_names:
             s["eng"].realign_tracks(track_names, s["regions"], s["shifts"], s["goi"], s["oidx"], s["tlen"], s["out_offsets"],
                                     rows * L, [0, 4][: len(track_names)], [0.0, 1.0][: len(track_names)], 7, s["nvar"],
@@ -389,7 +402,7 @@ def run_b200(args):
         cap_stream = torch.cuda.Stream(dev)
         with torch.cuda.graph(g_exec, stream=cap_stream):
             for s_ in slots:
-                s_["eng"].execute("onehot", out=s_["out"])
+                exec_(s_)
         reps = max(4, 256 // len(slots))
         with torch.cuda.stream(cap_stream):
             for _ in range(3):
@@ -412,7 +425,7 @@ def run_b200(args):
                 st.wait_event(ev0)
             for s_ in slots:
                 with torch.cuda.stream(s_["stream"]):
-                    s_["eng"].execute("onehot", out=s_["out"])
+                    exec_(s_)
             for st in streams:
                 ev = torch.cuda.Event()
                 ev.record(st)
@@ -447,14 +460,14 @@ def run_b200(args):
             flush.zero_()
             a3, b3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a3.record(main)
-            s["eng"].execute("onehot", out=slots[i % len(slots)]["out"])
+            exec_(s, out=slots[i % len(slots)]["out"])
             b3.record(main)
             torch.cuda.synchronize()
             if i >= 5:
                 durs.append(a3.elapsed_time(b3))
         exec_ms_isolated = float(np.mean(durs))
         del flush
-        ab = alg_bytes(w, s["nvar"])
+        ab = alg_bytes(w, s["nvar"], args.mode)
         achieved = ab / (exec_ms * 1e-3) / 1e9
         step_achieved = (ab + track_bytes(w)) * args.steps / (ms * 1e-3) / 1e9  # per GPU (every rank runs `steps` steps of its shard)
         traffic = None
@@ -468,7 +481,8 @@ def run_b200(args):
         # ---- e2e: the reference-shaped host-buffer call (numpy in, pinned numpy out), copies included ----
         _kernels.pin_static(d.geno_offsets, d.geno_v_idxs, d.v_starts, d.ilens, d.alt_alleles, d.alt_offsets,
                             d.reference, d.ref_offsets, ctx=eng0.ctx)
-        pinned = _kernels.PinnedBuffer(step_bytes_out)
+        e2e_bytes_out = rows * L * 4  # the e2e leg always returns the one-hot (the headline metric)
+        pinned = _kernels.PinnedBuffer(e2e_bytes_out)
         def e2e_step(b):
             _kernels.reconstruct_haplotypes_fused(b["regions"], b["shifts"], b["goi"], d.geno_offsets, d.geno_v_idxs,
                                                   d.v_starts, d.ilens, d.alt_alleles, d.alt_offsets, d.reference,
@@ -476,14 +490,14 @@ def run_b200(args):
                                                   out=pinned.array, ctx=eng0.ctx)
         for i in range(3):
             e2e_step(batches[i % len(batches)])
-        n_e2e = max(3, min(args.steps, int(2.0 / max(step_bytes_out / 20e9, 1e-4))))
+        n_e2e = max(3, min(args.steps, int(2.0 / max(e2e_bytes_out / 20e9, 1e-4))))
         t0 = time.perf_counter()
         for i in range(n_e2e):
             e2e_step(batches[i % len(batches)])
         e2e_s = time.perf_counter() - t0
         h2d = int(sum(batches[0][k].nbytes for k in ("regions", "shifts", "goi", "to_rc")))
         e2e = {"value": n_e2e * bp_per_step / e2e_s, "unit": "bp/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": int(step_bytes_out + (rows + 1) * 8), "steps": n_e2e,
+               "d2h_bytes_per_step": int(e2e_bytes_out + (rows + 1) * 8), "steps": n_e2e,
                "path": "genvarloader_b200._kernels.reconstruct_haplotypes_fused(mode='onehot') -> gvl_reconstruct_haplotypes_fused_begin/_finish, "
                        "host numpy in, pinned host numpy out"}
 
@@ -495,18 +509,19 @@ def run_b200(args):
         cpu1_v, cpu1_n, _ = cpu_arm(d, w, batches, budget_s=min(args.cpu_seconds, 4.0), threads=1)
 
         line = {
-            "metric": "haplotype bp/s (one-hot)", "value": value, "unit": "bp/s", "n_gpus": world, "steps": args.steps,
+            "metric": "haplotype bp/s (%s)" % {"onehot": "one-hot", "u8": "uint8 bytes", "annotated": "annotated"}[args.mode],
+            "value": value, "unit": "bp/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {w['desc']}", "window_bp": L, "haplotypes_per_batch": rows,
                        "variants_per_batch": s["nvar"],
-                       "output": "uint8 one-hot (L,4)" + (f" + {len(track_names)} float32 tracks (n_tracks, rows, L)" if track_names else ""), "source": "SVAR1-style sparse CSR",
+                       "output": {"onehot": "uint8 one-hot (L,4)", "u8": "uint8 haplotype bytes", "annotated": "uint8 bytes + int32 variant index + int32 reference coordinate"}[args.mode] + (f" + {len(track_names)} float32 tracks (n_tracks, rows, L)" if track_names else ""), "source": "SVAR1-style sparse CSR",
                        "batches_in_flight": n_slots, "cuda_graph": use_graph,
                        "l2": f"ring of {len(slots)} distinct batches/outputs = {len(slots) * step_bytes_out >> 20} MiB written per cycle "
                              "(> 126 MB L2); roofline launches are preceded by a 512 MiB L2 flush",
                        "parallelism": f"dp{world} (replicated tables, (region,sample) shards, no collective)"},
-            "output_GBps": value * 4 / 1e9, "algorithmic_GBps": step_achieved * world,
-            "roofline": {"bound": "hbm", "kernel": "hap_exec_oh_kernel (one-hot over the packed reference)", "achieved": achieved,
+            "output_GBps": value * {"onehot": 4, "u8": 1, "annotated": 9}[args.mode] / 1e9, "algorithmic_GBps": step_achieved * world,
+            "roofline": {"bound": "hbm", "kernel": "hap_exec_oh_kernel (one-hot over the packed reference)" if args.mode == "onehot" else f"hap_exec_kernel<{args.mode}>", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "alg_bytes_per_launch": ab, "launch_ms": exec_ms, "plan_kernel_ms": plan_ms,
                          "launch_ms_one_stream": exec_ms_one_stream,
@@ -516,7 +531,7 @@ def run_b200(args):
                                 f"own stream, {n_slots} in flight), replayed back to back; event time / launches.  launch_ms_one_stream: same "
                                 "launches serialised on a single stream (adds the ~3 us stream-order gap a 33 MB fill kernel also pays)",
                          "frac_of_nominal_8TBps": achieved / 8000.0,
-                         "frac_layout_bytes": (ab - 0.5 * rows * L) / (exec_ms * 1e-3) / 1e9 / peak,
+                         "frac_layout_bytes": (ab - (0.5 * rows * L if args.mode == "onehot" else 0.0)) / (exec_ms * 1e-3) / 1e9 / peak,
                          "bytes_note": "algorithmic bytes = SURVEY.md 8d (5 B/bp: 1 reference byte + 4 one-hot bytes); the packed reference "
                                        "moves 0.5 B/bp, frac_layout_bytes counts 4.5 B/bp instead",
                          "whole_step_frac": step_achieved / peak},
@@ -541,6 +556,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--seed", type=int, default=2)
+    ap.add_argument("--mode", default="onehot", choices=["onehot", "u8", "annotated"],
+                    help="output of the execute kernel (the headline metric is one-hot)")
     ap.add_argument("--slots", type=int, default=8, help="batches in flight (streams)")
     ap.add_argument("--ring", type=int, default=32, help="distinct batches / output buffers cycled through (one graph launch)")
     ap.add_argument("--no-graph", action="store_true")

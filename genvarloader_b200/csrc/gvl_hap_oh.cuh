@@ -35,6 +35,7 @@ constexpr int OH_MIN_CTAS = GVL_OH_MIN_CTAS;
 constexpr int OH_MAX_TILE = OH_MAX_TILE_WANTED < (OH_THREADS - 2) * OH_GROUP ? OH_MAX_TILE_WANTED : (OH_THREADS - 2) * OH_GROUP / 1024 * 1024;
 constexpr int OH_MAX_GROUPS = OH_MAX_TILE / OH_GROUP + 2;      // groups a pass can touch (+ misaligned edges)
 static_assert(OH_MAX_GROUPS <= OH_THREADS && OH_MAX_TILE >= 1024, "group table: one thread per group");
+constexpr int OH_EDGE_ROUNDS = (2 * REC_CAP + 2 + GVL_OH_THREADS - 1) / GVL_OH_THREADS;  // edge slots per thread and pass
 constexpr int OH_UNROLL = 4;                                   // groups per warp whose loads are issued together
 
 struct OhRecs {
@@ -217,7 +218,8 @@ __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(Ha
     __shared__ OhRecs S;
     __shared__ __align__(16) uint2 s_lut[256];         // byte (2 codes) -> 8 one-hot bytes
     __shared__ __align__(8) uint2 s_grp[OH_MAX_GROUPS];  // per group: {reference delta, idx | cnt << 8 | plain << 31}
-    __shared__ uint32_t s_edge[8][OH_THREADS];  // per thread: 6 staged code words of its edge unit, descriptor, position
+    // per thread and round (2 * REC_CAP + 2 slots over OH_THREADS threads): 6 staged code words of an edge unit, descriptor, position
+    __shared__ uint32_t s_edge[OH_EDGE_ROUNDS][8][OH_THREADS];
     __shared__ int64_t s_lo, s_hi;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -426,7 +428,7 @@ __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(Ha
         };
         // (the code words travel with asynchronous 4-byte copies into the thread's own shared-memory slots, so no
         //  register stays live across the group loop; part 2 reads them back after it)
-        auto edge_begin = [&](int s_) {
+        auto edge_begin = [&](int s_, int rd) {
             int e_kind, e_il = 0;
             int32_t e_p = 0;
             uint32_t e_desc = 0;
@@ -435,7 +437,7 @@ __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(Ha
                 UnitShape U;
                 e_kind = oh_classify(S, e_il, e_p, rp.ref_base, U);
                 if (e_kind == U_PATCH) {
-                    const uint32_t slot = smem_u32(&s_edge[0][tid]);
+                    const uint32_t slot = smem_u32(&s_edge[rd][0][tid]);
                     const int64_t nA = rp.ref_base + e_p + U.dlA;
                     const int vA = n_valid(rp.contig_len, (int64_t)e_p + U.dlA);
                     e_desc = (uint32_t)U.x1 << 2 | (uint32_t)U.x2 << 6 | (uint32_t)vA << 10 | ((uint32_t)nA & 7u) << 18;
@@ -465,10 +467,10 @@ __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(Ha
                     }
                 }
             }
-            s_edge[6][tid] = e_desc | (uint32_t)e_kind;
-            s_edge[7][tid] = (uint32_t)e_p;
+            s_edge[rd][6][tid] = e_desc | (uint32_t)e_kind;
+            s_edge[rd][7][tid] = (uint32_t)e_p;
         };
-        if (tid < n_slots) edge_begin(tid);
+        for (int s_ = tid, rd = 0; s_ < n_slots; s_ += OH_THREADS, rd++) edge_begin(s_, rd);  // (one round unless variants are dense)
         cp_async_commit();
 
         // ---- the group loop: every lane streams the units that are a single run ----
@@ -545,18 +547,14 @@ __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(Ha
         // ---- edge slots, part 2: blend (the copies were started before the group loop) + store ----
         cp_async_wait<0>();
 #pragma unroll 1
-        for (int s_ = tid; s_ < n_slots; s_ += OH_THREADS) {
+        for (int s_ = tid, rd = 0; s_ < n_slots; s_ += OH_THREADS, rd++) {
             int e_kind, e_il = 0;
             int32_t e_p;
             uint32_t e_desc = 0;
-            if (s_ != tid) {  // more slots than threads (dense variants): later rounds start their copies here
-                edge_begin(s_);
-                cp_async_commit();
-                cp_async_wait<0>();
-            }
-            e_desc = s_edge[6][tid];
+            const uint32_t(*sl)[OH_THREADS] = s_edge[rd];
+            e_desc = sl[6][tid];
             e_kind = e_desc & 3u;
-            e_p = (int32_t)s_edge[7][tid];
+            e_p = (int32_t)sl[7][tid];
             if (e_kind == U_SLOW) {  // piecewise units are done start to finish here
                 edge_locate(s_, e_kind, e_p, e_il);
                 if (e_kind == U_PATCH) e_kind = U_SLOW;
@@ -567,14 +565,14 @@ __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(Ha
             if (e_kind == U_PATCH) {
                 const int x1 = (e_desc >> 2) & 15, x2 = (e_desc >> 6) & 15;
                 const uint32_t mA = nib_mask((e_desc >> 10) & 15);
-                const uint32_t A = (__funnelshift_r(s_edge[0][tid], s_edge[1][tid], ((e_desc >> 18) & 7u) * 4u) & mA) | (padnib & ~mA);
+                const uint32_t A = (__funnelshift_r(sl[0][tid], sl[1][tid], ((e_desc >> 18) & 7u) * 4u) & mA) | (padnib & ~mA);
                 uint32_t B = A;
                 if (x1 > 0) {
                     const uint32_t mB = nib_mask((e_desc >> 14) & 15);
-                    B = (__funnelshift_r(s_edge[2][tid], s_edge[3][tid], ((e_desc >> 21) & 7u) * 4u) & mB) | (padnib & ~mB);
+                    B = (__funnelshift_r(sl[2][tid], sl[3][tid], ((e_desc >> 21) & 7u) * 4u) & mB) | (padnib & ~mB);
                 }
                 uint32_t alt = padnib;  // leading pad (src/reconstruct/mod.rs:75-80)
-                if (!(e_desc & (1u << 27))) alt = __funnelshift_r(s_edge[4][tid], s_edge[5][tid], ((e_desc >> 24) & 7u) * 4u);
+                if (!(e_desc & (1u << 27))) alt = __funnelshift_r(sl[4][tid], sl[5][tid], ((e_desc >> 24) & 7u) * 4u);
                 const uint32_t m1 = nib_mask(x1), m2 = nib_mask(x2);
                 v = (A & m1) | ((alt << (4 * x1)) & m2 & ~m1) | (B & ~m2);
             } else {

@@ -36,7 +36,10 @@ constexpr int OH_MAX_TILE = OH_MAX_TILE_WANTED < (OH_THREADS - 2) * OH_GROUP ? O
 constexpr int OH_MAX_GROUPS = OH_MAX_TILE / OH_GROUP + 2;      // groups a pass can touch (+ misaligned edges)
 static_assert(OH_MAX_GROUPS <= OH_THREADS && OH_MAX_TILE >= 1024, "group table: one thread per group");
 constexpr int OH_EDGE_ROUNDS = (2 * REC_CAP + 2 + GVL_OH_THREADS - 1) / GVL_OH_THREADS;  // edge slots per thread and pass
-constexpr int OH_UNROLL = 4;                                   // groups per warp whose loads are issued together
+#ifndef GVL_OH_UNROLL
+#define GVL_OH_UNROLL 4
+#endif
+constexpr int OH_UNROLL = GVL_OH_UNROLL;                                   // groups per warp whose loads are issued together
 
 struct OhRecs {
     int32_t a[REC_CAP + 2];   // ALT start (haplotype coordinate); a[m], a[m+1] sentinels

@@ -685,9 +685,11 @@ __global__ void __launch_bounds__(TRK_THREADS, 4) trk_exec_kernel(TrkExecParams 
             }
             if (act) {
                 float cur_v = carry;
+                const uint32_t mk_lo = (uint32_t)mk, mk_hi = (uint32_t)(mk >> 32);
 #pragma unroll
                 for (int q = 0; q < CH; q++) {
-                    cur_v = ((mk >> q) & 1) ? x[q] : cur_v;
+                    const bool f = q < 32 ? ((mk_lo >> q) & 1u) : ((mk_hi >> (q - 32)) & 1u);
+                    cur_v = f ? x[q] : cur_v;
                     x[q] = cur_v;
                 }
 #pragma unroll
@@ -728,24 +730,40 @@ __global__ void __launch_bounds__(TRK_THREADS, 4) trk_exec_kernel(TrkExecParams 
             s_gt[threadIdx.x] = off;
         }
         __syncthreads();
+        // copy loop of the plain groups: lane l moves values l, l+32, l+64, l+96 of a group, so every shared-memory
+        // read and every store is one contiguous 128-byte warp access (4 consecutive values per lane would be a 4-way
+        // bank conflict); pointers are hoisted, the two directions are separate loops (constant offsets)
+        {
+            float *const og_lane = out + g0 + lane_;
+            if (!rc) {
+                const float *const ws_lane = s_win + lane_;
+#pragma unroll 2
+                for (int32_t grp = warp_; grp < n_groups; grp += TRK_THREADS / 32) {
+                    const int32_t off = s_gt[grp];
+                    if (off < 0) continue;
+                    const float *ws = ws_lane + off;
+                    const float v0 = ws[0], v1 = ws[32], v2 = ws[64], v3 = ws[96];
+                    float *og = og_lane + 128 * grp;
+                    og[0] = v0, og[32] = v1, og[64] = v2, og[96] = v3;
+                }
+            } else {
+                const float *const ws_lane = s_win + 127 - lane_;
+#pragma unroll 2
+                for (int32_t grp = warp_; grp < n_groups; grp += TRK_THREADS / 32) {
+                    const int32_t off = s_gt[grp];
+                    if (off < 0) continue;
+                    const float *ws = ws_lane + off;
+                    const float v0 = ws[0], v1 = ws[-32], v2 = ws[-64], v3 = ws[-96];
+                    float *og = og_lane + 128 * grp;
+                    og[0] = v0, og[32] = v1, og[64] = v2, og[96] = v3;
+                }
+            }
+        }
         for (int32_t grp = warp_; grp < n_groups; grp += TRK_THREADS / 32) {
+            if (s_gt[grp] >= 0) continue;  // copied above
             const int32_t c = grp * 32 + lane_;
             const int64_t g = g0 + 4 * (int64_t)c;
             const int32_t j = (int32_t)(g - row_base);
-            const int32_t off = s_gt[grp];
-            if (off >= 0) {
-                // lane l moves values l, l+32, l+64, l+96 of the group: every shared-memory read and every store is one
-                // contiguous 128-byte warp access (4 consecutive values per lane would be a 4-way bank conflict)
-                float *og = out + (g0 + 128 * (int64_t)grp);
-                const float *ws = s_win + off + (rc ? 127 - lane_ : lane_);
-                const int stp = rc ? -32 : 32;
-                const float v0 = ws[0], v1 = ws[stp], v2 = ws[2 * stp], v3 = ws[3 * stp];
-                og[lane_] = v0;
-                og[lane_ + 32] = v1;
-                og[lane_ + 64] = v2;
-                og[lane_ + 96] = v3;
-                continue;
-            }
             if (c >= n_chunks) continue;
             // lane-level fast path: the lane's 4 values lie inside one reference span and inside the window
             if (j >= jo_lo && j + 4 <= jo_hi) {

@@ -16,14 +16,20 @@
 
 namespace gvl {
 
-constexpr int TRK_TILE = 8192;             // output values per pass of an execute CTA (one staged source window)
-constexpr int TRK_WIN = TRK_TILE + 1024;   // source-window values staged in shared memory (room for net deletions)
+#ifndef GVL_TRK_TILE
+#define GVL_TRK_TILE 8192
+#endif
+#ifndef GVL_TRK_THREADS
+#define GVL_TRK_THREADS 256
+#endif
+constexpr int TRK_TILE = GVL_TRK_TILE;             // output values per pass of an execute CTA (one staged source window)
+constexpr int TRK_WIN = TRK_TILE + TRK_TILE / 8;   // source-window values staged in shared memory (room for net deletions)
 #ifndef GVL_TRK_SEG_TILES
 #define GVL_TRK_SEG_TILES 8
 #endif
 constexpr int TRK_SEG = GVL_TRK_SEG_TILES * TRK_TILE;       // output values per execute CTA: up to 8 tiles, walked in haplotype order
 constexpr int TRK_MARGIN = 16;             // window starts a little before the first needed value
-constexpr int TRK_THREADS = 256;
+constexpr int TRK_THREADS = GVL_TRK_THREADS;
 constexpr int TRK_REC_CAP = 128;
 
 // =====================================================================================
@@ -416,12 +422,12 @@ __device__ unsigned long long *g_trk_trace = nullptr;  // [n_ctas][64]: per pass
 #define TRK_TR(slot) do { } while (0)
 #endif
 
-__global__ void __launch_bounds__(TRK_THREADS, 4) trk_exec_kernel(TrkExecParams P) {
+__global__ void __launch_bounds__(TRK_THREADS, 1024 / TRK_THREADS) trk_exec_kernel(TrkExecParams P) {
 #if GVL_TRACE
     int tr_pass = 0;
 #endif
     __shared__ TrkTileRecs S;
-    __shared__ __align__(16) float s_win[TRK_WIN];
+    extern __shared__ __align__(16) float s_win[];  // TRK_WIN floats (dynamic: larger than 48 KB in big-pass builds)
     __shared__ uint32_t s_flag[TRK_WIN / 32 + 4];  // positions of s_win that hold a run start (interval start / end)
     __shared__ float s_cval[TRK_THREADS / 32];
     __shared__ int32_t s_gt[TRK_TILE / 128 + 2];  // per group of the pass: window offset of a plain group, or -1
@@ -585,7 +591,10 @@ __global__ void __launch_bounds__(TRK_THREADS, 4) trk_exec_kernel(TrkExecParams 
         }
         __syncthreads();
         TRK_TR(2);
-        if (!T.dense && w1 > w0) {
+#ifndef GVL_TRK_EXP
+#define GVL_TRK_EXP 0
+#endif
+        if (!(GVL_TRK_EXP & 1) && !T.dense && w1 > w0) {
             // Paint the window as a run-length expansion (src/intervals.rs:19-126 restated for one window):
             //  1. every thread holds ONE interval (coalesced loads) and drops two markers: 0 at its end, its value at
             //     its (clipped) start -- ends first, so that an adjacent interval's start wins;
@@ -744,6 +753,7 @@ __global__ void __launch_bounds__(TRK_THREADS, 4) trk_exec_kernel(TrkExecParams 
                     const float *ws = ws_lane + off;
                     const float v0 = ws[0], v1 = ws[32], v2 = ws[64], v3 = ws[96];
                     float *og = og_lane + 128 * grp;
+                    if ((GVL_TRK_EXP & 2) && v0 != 123.456f) continue;
                     og[0] = v0, og[32] = v1, og[64] = v2, og[96] = v3;
                 }
             } else {
@@ -755,6 +765,7 @@ __global__ void __launch_bounds__(TRK_THREADS, 4) trk_exec_kernel(TrkExecParams 
                     const float *ws = ws_lane + off;
                     const float v0 = ws[0], v1 = ws[-32], v2 = ws[-64], v3 = ws[-96];
                     float *og = og_lane + 128 * grp;
+                    if ((GVL_TRK_EXP & 2) && v0 != 123.456f) continue;
                     og[0] = v0, og[32] = v1, og[64] = v2, og[96] = v3;
                 }
             }
@@ -880,7 +891,11 @@ static int launch_trk_exec(gvl_ctx *ctx, int64_t n_work, int64_t ploidy, int64_t
         for (int64_t t = 0; t < n_tracks; t++) P.inl[t] = host_desc[t];
     const int64_t grid = P.grid_per_track * n_tracks;
     if (grid > INT32_MAX) return fail(GVL_ERR_ARG, "too many track tiles");
-    trk_exec_kernel<<<(unsigned)grid, TRK_THREADS, 0, st>>>(P);
+    static const bool smem_ok = [] {
+        return cudaFuncSetAttribute(trk_exec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * TRK_WIN)) == cudaSuccess;
+    }();
+    if (!smem_ok) return fail(GVL_ERR_CUDA, "trk_exec_kernel: cannot reserve %d bytes of shared memory", (int)(sizeof(float) * TRK_WIN));
+    trk_exec_kernel<<<(unsigned)grid, TRK_THREADS, sizeof(float) * TRK_WIN, st>>>(P);
     GVL_LAUNCH_CHECK();
     return GVL_OK;
 }

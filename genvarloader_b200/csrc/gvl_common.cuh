@@ -57,7 +57,6 @@ constexpr int EXEC_UNIT = EXEC_THREADS * 4;  // positions covered by one CTA-wid
 constexpr int TILE = 4096;       // haplotype positions per execute CTA for ragged plans (fixed plans pick theirs)
 constexpr int REC_CAP = 128;     // records staged in shared memory per pass
 constexpr int EXEC_MAX_UNITS = 16;  // <= 8192 haplotype positions per CTA: its reference window fits shared memory
-constexpr int WIN_CAP = EXEC_MAX_UNITS * EXEC_THREADS * 4 + 1024;  // bytes of reference staged per pass (TMA bulk copy)
 constexpr int DIR_Q = 1024;      // haplotype positions per directory entry (execute tiles are multiples of it)
 constexpr int64_t ALT_PAD = INT64_MIN;  // RecArrays.src sentinel: "ALT piece" is padding (leading pad)
 

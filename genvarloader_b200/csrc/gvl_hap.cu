@@ -22,14 +22,8 @@
 
 #include "gvl_internal.cuh"
 
-#ifndef GVL_TMA_WINDOW
-#define GVL_TMA_WINDOW 0  // 1: stage each pass's reference window in shared memory with one cp.async.bulk
-#endif
 #ifndef GVL_LUT_ASM
 #define GVL_LUT_ASM 1     // 1: hand-written shared-memory addressing for the one-hot table (+2 %, profiles/)
-#endif
-#ifndef GVL_PREFETCH
-#define GVL_PREFETCH 0    // 1: each warp prefetches its plain-reference blocks with cp.async (-9 %, profiles/)
 #endif
 
 namespace gvl {
@@ -396,12 +390,7 @@ __global__ void __launch_bounds__(EXEC_THREADS, EXEC_MIN_CTAS) hap_exec_kernel(H
     constexpr bool OH = (MODE == GVL_MODE_ONEHOT || MODE == GVL_MODE_ONEHOT_CF);
     __shared__ TileRecs S;
     __shared__ __align__(16) uint32_t s_lut[OH ? 512 : 4];  // [0,256): one-hot(b); [256,512): one-hot(complement(b))
-    __shared__ __align__(16) uint8_t s_win[GVL_TMA_WINDOW ? WIN_CAP + 16 : 16];  // reference bytes of the pass (TMA bulk copy)
-    __shared__ __align__(8) uint64_t s_bar;
-    __shared__ __align__(16) uint8_t s_slab[GVL_PREFETCH ? EXEC_THREADS / 32 : 1][GVL_PREFETCH ? 4 : 1][GVL_PREFETCH ? 560 : 16];
-    __shared__ int32_t s_qmeta[EXEC_THREADS / 32][4][2];  // per warp and block slot: record cursor, first reference position
-    __shared__ int64_t s_lo, s_hi, s_wabs;
-    __shared__ int32_t s_wbytes;
+    __shared__ int64_t s_lo, s_hi;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     // ---- tile -> (row, tile-in-row) ----
@@ -431,7 +420,6 @@ __global__ void __launch_bounds__(EXEC_THREADS, EXEC_MIN_CTAS) hap_exec_kernel(H
     const bool rc = rp.rc != 0;
 
     if (OH) reinterpret_cast<uint4 *>(s_lut)[tid] = make_uint4(0u, 0u, 0u, 0u);  // 128 threads x 16 B = the whole table
-    if (tid == 0) mbar_init(&s_bar, 1);
     __syncthreads();
     if (OH && tid < 8) {  // the only non-zero entries: ACGT (and their complements in the second half)
         const int i = tid & 3;
@@ -470,7 +458,6 @@ __global__ void __launch_bounds__(EXEC_THREADS, EXEC_MIN_CTAS) hap_exec_kernel(H
     uint8_t *__restrict__ out_row = P.out + (OH ? 4 : 1) * rp.out_off;  // position j of the row lives at out_row[(4*)j]
     const uint32_t lut_a = smem_u32(s_lut);   // byte address of the table in shared memory
     const uint32_t lut_rc = rc ? 1024u : 0u;  // second half = one-hot of the complement
-    uint32_t win_phase = 0;
 
     // one 4-position chunk made only of reference bytes: v holds the bytes in OUTPUT order (not yet
     // complemented), r0 = reference position of the chunk's lowest haplotype position
@@ -544,53 +531,6 @@ __global__ void __launch_bounds__(EXEC_THREADS, EXEC_MIN_CTAS) hap_exec_kernel(H
         if (tid == 0) S.a[m] = INT32_MAX;
         __syncthreads();
 
-        // ---- stage the pass's reference window with ONE TMA bulk copy (cp.async.bulk -> mbarrier) ----
-        // window = [first reference position read, last + 1) of the spans of this pass, clipped to the contig
-        // and to WIN_CAP; anything outside (huge deletions, unsorted jumps) is read from global memory instead
-        if (GVL_TMA_WINDOW && warp == 0) {
-            int64_t lo = INT64_MAX, hi = INT64_MIN;
-            for (int i = lane; i < m; i += 32) {
-                const int32_t s0 = max(S.e[i], cur), s1 = min(S.a[i + 1], seg_end);  // span of entry i inside the pass
-                if (s1 > s0) {
-                    const int64_t r0 = (int64_t)S.resume[i] + (s0 - S.e[i]);
-                    lo = imin64(lo, r0);
-                    hi = imax64(hi, r0 + (s1 - s0));
-                }
-            }
-            for (int o = 16; o > 0; o >>= 1) {
-                lo = imin64(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-                hi = imax64(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-            }
-            if (lane == 0) {
-                hi = imin64(hi, rp.contig_len);
-                lo = imax64(lo, 0);
-                int64_t abs0 = 0;
-                int32_t bytes = 0;
-                if (hi > lo) {
-                    abs0 = (rp.ref_base + lo) & ~(int64_t)15;
-                    const int64_t abs1 = (rp.ref_base + hi + 4 + 15) & ~(int64_t)15;  // +4: the 32-bit pair read overruns
-                    bytes = (int32_t)imin64(abs1 - abs0, WIN_CAP);
-                }
-                s_wabs = abs0;
-                s_wbytes = bytes;
-                if (bytes > 0) {
-                    mbar_expect_tx(&s_bar, (uint32_t)bytes);
-                    bulk_g2s(s_win, P.ref + abs0, (uint32_t)bytes, &s_bar);
-                }
-            }
-            if (lane == 0 && s_wbytes > 0) mbar_wait(&s_bar, win_phase);  // one thread polls; the CTA sleeps at the barrier
-        }
-#if GVL_TMA_WINDOW
-        __syncthreads();
-        const int64_t w_abs0 = s_wabs;
-        const int64_t w_abs1 = w_abs0 + s_wbytes;
-        if (s_wbytes > 0) win_phase ^= 1;
-        const uint32_t win_a = smem_u32(s_win);
-#else
-        const int64_t w_abs0 = 0, w_abs1 = 0;  // nothing staged: every span is read from global memory
-        const uint32_t win_a = 0;
-#endif
-
         // ---- output range of this pass, chunked by 4 on the GLOBAL flat index ----
         // chunk c covers row positions j0+4c .. j0+4c+3; a GROUP is 32 chunks (one per lane: 128
         // positions, one 512-byte one-hot store per warp), a BLOCK is 4 groups.  Warp w owns blocks
@@ -603,73 +543,6 @@ __global__ void __launch_bounds__(EXEC_THREADS, EXEC_MIN_CTAS) hap_exec_kernel(H
         const int32_t n_blocks = (n_chunks + 127) >> 7;
         int ic = rc ? (m - 1) : 0;  // warp-uniform record cursor (blocks are visited in monotone order)
 
-#if GVL_PREFETCH
-        // ---- phase A: classify this warp's blocks (<= 4 per pass) and start asynchronous copies
-        //      (cp.async, 16 B per lane) of the ones that are 512 plain reference bytes ----
-        unsigned fastmask = 0;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            int icq = -1;
-            int32_t rq = 0;
-            const int32_t blk = warp + 4 * q;
-            const int32_t jb = j0 + 512 * blk;
-            if (blk < n_blocks && jb >= jo_lo && jb + 512 <= jo_hi) {
-                const int32_t p_lo = rc ? (L - 512 - jb) : jb;  // lowest haplotype position of the block
-                if (!rc) {
-                    while (S.a[ic + 1] <= p_lo) ic++;
-                } else {
-                    while (S.a[ic] > p_lo) ic--;
-                }
-                icq = ic;
-                const int32_t e_i = S.e[ic];
-                const int64_t rpos_lo = (int64_t)S.resume[ic] + (p_lo - e_i);
-                if (p_lo >= e_i && p_lo + 511 < S.a[ic + 1] && rpos_lo + 511 < rp.contig_len) {
-                    fastmask |= 1u << q;
-                    rq = (int32_t)rpos_lo;
-                    const int64_t abs_lo = rp.ref_base + rpos_lo;
-                    const int64_t a16 = abs_lo & ~(int64_t)15;
-                    const int32_t n16 = (int32_t)(((abs_lo + 516 + 15) & ~(int64_t)15) - a16);  // <= 544 bytes
-                    const uint32_t dst = smem_u32(&s_slab[warp][q][0]);
-#pragma unroll
-                    for (int c = 0; c < 2; c++) {
-                        const int o = (lane + 32 * c) * 16;
-                        if (o < n16) cp_async16(dst + o, P.ref + a16 + o);
-                    }
-                }
-            }
-            cp_async_commit();  // one group per slot, empty or not: group indices stay static
-            if (lane == 0) {
-                s_qmeta[warp][q][0] = icq;
-                s_qmeta[warp][q][1] = rq;
-            }
-        }
-        __syncwarp();
-        // ---- phase B: encode + store (not unrolled: the generic path below is large) ----
-#pragma unroll 1
-        for (int q = 0; q < 4; q++) {
-            const int32_t blk = warp + 4 * q;
-            if (blk >= n_blocks) break;
-            const int32_t jb = j0 + 512 * blk;  // first row position of the block
-            if (fastmask & (1u << q)) {
-                if (q == 0) cp_async_wait<3>(); else if (q == 1) cp_async_wait<2>(); else if (q == 2) cp_async_wait<1>(); else cp_async_wait<0>();
-                __syncwarp();
-                const int32_t rq = s_qmeta[warp][q][1];
-                const int32_t r_lane = rq + (rc ? 508 - 4 * lane : 4 * lane);
-                const int32_t off = r_lane - rq + (int32_t)((rp.ref_base + rq) & 15);  // byte offset inside the slab
-                const uint32_t sa = smem_u32(&s_slab[warp][q][0]) + (uint32_t)(off & ~3);
-                const unsigned sh = (unsigned)(off & 3) * 8u;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int o = rc ? -128 * k : 128 * k;  // group k of the OUTPUT lies 128 bytes further (back)
-                    uint32_t v = __funnelshift_r(lds_u32(sa + o), lds_u32(sa + o + 4), sh);  // byte i = haplotype position p0+i
-                    if (rc) v = __byte_perm(v, 0, 0x0123);                                     // byte i = output position j+i
-                    emit_ref4(jb + 128 * k + 4 * lane, v, r_lane + (rc ? -128 * k : 128 * k));
-                }
-                continue;
-            }
-            {
-                const int ic = s_qmeta[warp][q][0];  // (shadows the walk cursor: the block's own record index, -1 = unknown)
-#else
         for (int32_t blk = warp; blk < n_blocks; blk += EXEC_THREADS / 32) {
             const int32_t jb = j0 + 512 * blk;  // first row position of the block
             if (jb >= jo_lo && jb + 512 <= jo_hi) {
@@ -685,28 +558,15 @@ __global__ void __launch_bounds__(EXEC_THREADS, EXEC_MIN_CTAS) hap_exec_kernel(H
                 if (p_lo >= e_i && p_lo + 511 < S.a[ic + 1] && rpos_lo + 511 < rp.contig_len) {
                     // 512 reference bytes in a row: all 8 loads first, then 4 encodes + stores
                     const int32_t r_lane = (int32_t)rpos_lo + (rc ? 508 - 4 * lane : 4 * lane);
-                    const int64_t abs_lo = rp.ref_base + rpos_lo;  // absolute offset of the block's first reference byte
                     const uintptr_t addr = reinterpret_cast<uintptr_t>(refrow + r_lane);
                     const unsigned sh = (unsigned)(addr & 3) * 8u;
                     uint32_t w0[4], w1[4];
-                    if (abs_lo >= w_abs0 && abs_lo + 512 + 4 <= w_abs1) {
-                        // staged: two aligned 32-bit shared-memory loads per chunk (P.ref is 16-byte aligned, so the
-                        // low address bits of the staged copy equal those of the global address)
-                        const uint32_t sa = win_a + (uint32_t)((rp.ref_base + r_lane - w_abs0) & ~(int64_t)3);
+                    const uint32_t *w = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
 #pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            const int off = rc ? -128 * k : 128 * k;
-                            w0[k] = lds_u32(sa + off);
-                            w1[k] = lds_u32(sa + off + 4);
-                        }
-                    } else {
-                        const uint32_t *w = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
-#pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            const int off = rc ? -32 * k : 32 * k;  // group k of the OUTPUT lies 128 bytes further (back)
-                            w0[k] = __ldg(w + off);
-                            w1[k] = __ldg(w + off + 1);  // (readable: buffers carry >= 16 B of slack)
-                        }
+                    for (int k = 0; k < 4; k++) {
+                        const int off = rc ? -32 * k : 32 * k;  // group k of the OUTPUT lies 128 bytes further (back)
+                        w0[k] = __ldg(w + off);
+                        w1[k] = __ldg(w + off + 1);  // (readable: buffers carry >= 16 B of slack)
                     }
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
@@ -718,7 +578,6 @@ __global__ void __launch_bounds__(EXEC_THREADS, EXEC_MIN_CTAS) hap_exec_kernel(H
                 }
             }
             {
-#endif
             // ---- block with variants / pads / pass edges: group by group ----
             int ig = (jb >= jo_lo && jb + 512 <= jo_hi) ? ic : -1;  // cursor for the block's lowest position, if known
 #pragma unroll 1
@@ -736,18 +595,11 @@ __global__ void __launch_bounds__(EXEC_THREADS, EXEC_MIN_CTAS) hap_exec_kernel(H
                     const int64_t rpos_lo = (int64_t)S.resume[ig] + (p_lo - e_i);
                     if (p_lo >= e_i && p_lo + 127 < S.a[ig + 1] && rpos_lo + 127 < rp.contig_len) {
                         const int32_t r_lane = (int32_t)rpos_lo + (rc ? 124 - 4 * lane : 4 * lane);
-                        const int64_t abs_lo = rp.ref_base + rpos_lo;
                         const uintptr_t addr = reinterpret_cast<uintptr_t>(refrow + r_lane);
                         uint32_t x0, x1;
-                        if (abs_lo >= w_abs0 && abs_lo + 128 + 4 <= w_abs1) {
-                            const uint32_t sa = win_a + (uint32_t)((rp.ref_base + r_lane - w_abs0) & ~(int64_t)3);
-                            x0 = lds_u32(sa);
-                            x1 = lds_u32(sa + 4);
-                        } else {
-                            const uint32_t *w = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
-                            x0 = __ldg(w);
-                            x1 = __ldg(w + 1);
-                        }
+                        const uint32_t *w = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
+                        x0 = __ldg(w);
+                        x1 = __ldg(w + 1);
                         uint32_t v = __funnelshift_r(x0, x1, (unsigned)(addr & 3) * 8u);
                         if (rc) v = __byte_perm(v, 0, 0x0123);
                         emit_ref4(j, v, r_lane);
@@ -929,17 +781,6 @@ static int64_t exec_capacity(gvl_ctx *ctx, int mode) {
     }
     int64_t cap = (int64_t)sms * (per_sm > 0 ? per_sm : 1);
     if (ctx->device < 8) cache[ctx->device][mode & 3] = cap;
-    return cap;
-}
-
-static int64_t exec_capacity_oh(gvl_ctx *ctx) {
-    static int64_t cache[8] = {};
-    if (ctx->device < 8 && cache[ctx->device]) return cache[ctx->device];
-    int sms = 148, per_sm = OH_MIN_CTAS;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hap_exec_oh_kernel, OH_THREADS, 0);
-    const int64_t cap = (int64_t)sms * (per_sm > 0 ? per_sm : 1);
-    if (ctx->device < 8) cache[ctx->device] = cap;
     return cap;
 }
 

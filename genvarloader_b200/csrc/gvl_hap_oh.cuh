@@ -536,7 +536,6 @@ __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(Ha
             for (int u = 0; u < OH_UNROLL; u++) {
                 const unsigned nv = (nvs >> (4 * u)) & 15u;
                 if (nv != 15) {
-                    const int g = gb + u * (OH_THREADS / 32);
                     uint32_t v = __funnelshift_r(w0[u], w1[u], sh[u]);  // nibble t = haplotype position p_lo + t
                     if (mixmask & (1u << u)) {
                         const uint32_t mk = nib_mask((int)nv);

@@ -470,11 +470,15 @@ def run_b200(args):
         ab = alg_bytes(w, s["nvar"], args.mode)
         achieved = ab / (exec_ms * 1e-3) / 1e9
         step_achieved = (ab + track_bytes(w)) * args.steps / (ms * 1e-3) / 1e9  # per GPU (every rank runs `steps` steps of its shard)
-        traffic = None
+        packed_ran = int(_ffi.lib.gvl_debug_last_exec_kernel(eng0.ctx.handle)) == 1  # which execute kernel the step launched
+        kernel_name = "hap_exec_oh_kernel (one-hot over the packed reference)" if packed_ran else f"hap_exec_kernel<{args.mode}> (byte reference)"
+        traffic, traffic_note = None, None
         tp = ROOT / "profiles" / "ncu_exec_traffic.json"
-        if tp.exists():
+        if tp.exists() and packed_ran:  # (the committed capture is of the packed kernel)
             try:
-                traffic = json.loads(tp.read_text()).get(args.workload)
+                tj = json.loads(tp.read_text())
+                traffic = tj.get(args.workload)
+                traffic_note = (tj.get(args.workload + "_detail") or {}).get("note")
             except Exception:
                 traffic = None
 
@@ -521,8 +525,8 @@ def run_b200(args):
                              "(> 126 MB L2); roofline launches are preceded by a 512 MiB L2 flush",
                        "parallelism": f"dp{world} (replicated tables, (region,sample) shards, no collective)"},
             "output_GBps": value * {"onehot": 4, "u8": 1, "annotated": 9}[args.mode] / 1e9, "algorithmic_GBps": step_achieved * world,
-            "roofline": {"bound": "hbm", "kernel": "hap_exec_oh_kernel (one-hot over the packed reference)" if args.mode == "onehot" else f"hap_exec_kernel<{args.mode}>", "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
                          "alg_bytes_per_launch": ab, "launch_ms": exec_ms, "plan_kernel_ms": plan_ms,
                          "launch_ms_one_stream": exec_ms_one_stream,
                          "frac_one_stream": ab / (exec_ms_one_stream * 1e-3) / 1e9 / peak,

@@ -447,7 +447,7 @@ class Dataset:
         pk.upload()
         keep = keep_off = None
         if self.var_filter == "exonic":
-            keep, keep_off = self._exonic_keep(goi, regions)
+            keep, keep_off = self._exonic_keep(pk.get(i_goi), pk.get(i_reg), goi)
         oo = eng.plan(pk.get(i_reg), pk.get(i_sh), pk.get(i_goi), -1, eng.max_records(goi), keep, keep_off,
                       pk.get(i_rc) if i_rc is not None else None)
         total = eng.total()
@@ -539,7 +539,7 @@ class Dataset:
         max_rec = 0 if is_ref else eng.max_records(goi)
         keep = keep_off = None
         if self.var_filter == "exonic" and not is_ref:
-            keep, keep_off = self._exonic_keep(goi, regions)
+            keep, keep_off = self._exonic_keep(t_goi, t_reg, goi)
 
         results = []
         oo = total = diffs = None
@@ -611,28 +611,10 @@ class Dataset:
                 results.append(Ragged(out, offsets, (b, t, None)))
         return tuple(results)
 
-    def _exonic_keep(self, goi, regions):
-        """choose_exonic_variants (src/genotypes/mod.rs:132-176): variants fully inside the query.  O(selected
-        variants) host numpy over the host copy of the CSR offsets + device gather of positions."""
+    def _exonic_keep(self, t_goi, t_reg, goi):
+        """choose_exonic_variants (src/genotypes/mod.rs:132-176): variants fully inside the query, on the device."""
         eng = self.engine
-        go = eng.geno_offsets_host
-        starts, stops = go[0, goi.ravel()], go[1, goi.ravel()]
-        sizes = np.maximum(stops - starts, 0)
-        keep_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
-        n = int(keep_off[-1])
-        dev = eng.device
-        if n == 0:
-            return torch.zeros(1, dtype=torch.uint8, device=dev), torch.from_numpy(keep_off).to(dev)
-        row = np.repeat(np.arange(goi.size), sizes)
-        src = np.repeat(starts, sizes) + (np.arange(n) - np.repeat(keep_off[:-1], sizes))
-        vi = eng.geno_v_idxs[torch.from_numpy(src).to(dev)].to(torch.int64)
-        pos = eng.v_starts[vi].to(torch.int64)
-        end = pos - eng.ilens[vi].to(torch.int64).clamp(max=0) + 1
-        q = torch.from_numpy(row // goi.shape[1]).to(dev)
-        rs = torch.from_numpy(regions[:, 1].astype(np.int64)).to(dev)[q]
-        re = torch.from_numpy(regions[:, 2].astype(np.int64)).to(dev)[q]
-        keep = ((pos >= rs) & (end <= re)).to(torch.uint8)
-        return keep, torch.from_numpy(keep_off).to(dev)
+        return eng.choose_exonic_variants(t_reg[:, 1].contiguous(), t_reg[:, 2].contiguous(), t_goi, eng.max_records(goi))
 
     # ---- output shaping, _query.py:94-127 ----
     def _shape_output(self, o, out_reshape, squeeze):

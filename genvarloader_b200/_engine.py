@@ -105,6 +105,17 @@ class Engine:
         e._n_work, e._fixed = 0, -1
         return e
 
+    def choose_exonic_variants(self, starts, ends, geno_offset_idx, keep_cap: int):
+        """gvl_dev_choose_exonic_variants (src/genotypes/mod.rs:132-176): keep mask of the variants that lie fully
+        inside [starts, ends).  `keep_cap` = `max_records(geno_offset_idx)`; returns device (keep u8, keep_offsets i64)."""
+        n_q, ploidy = geno_offset_idx.shape
+        keep = torch.empty(max(int(keep_cap), 1), dtype=torch.uint8, device=self.device)
+        keep_offsets = torch.empty(n_q * ploidy + 1, dtype=torch.int64, device=self.device)
+        check(lib.gvl_dev_choose_exonic_variants(self.ctx.handle, C.byref(self.tab), ptr(starts), ptr(ends),
+                                                 ptr(geno_offset_idx), c_i64(n_q), c_i64(ploidy), ptr(keep),
+                                                 c_i64(int(keep_cap)), ptr(keep_offsets), _stream()))
+        return keep, keep_offsets
+
     # ------------------------------------------------------------------ tracks
     def add_track(self, name: str, itv_starts, itv_ends, itv_values, itv_offsets) -> None:
         with torch.cuda.device(self.device):

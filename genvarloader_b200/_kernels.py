@@ -171,6 +171,94 @@ def reconstruct_haplotypes_from_sparse(out, out_offsets, regions, shifts, geno_o
         c_u8(int(pad_char)), _p(kp), _p(ko), _p(annot_v_idxs), _p(annot_ref_pos)))
 
 
+def reconstruct_haplotypes_spliced_fused(permuted_regions, flat_shifts, flat_geno_offset_idx, out_offsets, geno_offsets,
+                                         geno_v_idxs, v_starts, ilens, alt_alleles, alt_offsets, ref_, ref_offsets, pad_char,
+                                         keep=None, keep_offsets=None, to_rc=None, parallel=True, *, _annotated=False,
+                                         ctx=None):
+    """src/ffi/mod.rs:1983-2071.  The splice plan's permuted elements as rows of ploidy 1 sized by the caller's
+    ``out_offsets``; returns ``out_data`` only (the caller holds the offsets)."""
+    ctx = ctx or default_ctx()
+    oo = _c(out_offsets, np.int64)
+    rg, sh = _c(permuted_regions, np.int32), _c(flat_shifts, np.int32).reshape(-1)
+    goi = _c(flat_geno_offset_idx, np.int64).reshape(-1)
+    n_perm = goi.size
+    assert oo.size == n_perm + 1 and rg.shape == (n_perm, 3) and sh.size == n_perm
+    go = _starts_stops(geno_offsets)
+    gv, vs, il = _c(geno_v_idxs, np.int32), _c(v_starts, np.int32), _c(ilens, np.int32)
+    aa, ao = _c(alt_alleles, np.uint8), _c(alt_offsets, np.int64)
+    rf, ro = _c(ref_, np.uint8), _c(ref_offsets, np.int64)
+    kp, ko, rc = _c(keep, np.bool_), _c(keep_offsets, np.int64), _c(to_rc, np.bool_)
+    total = int(oo[-1])
+    out = np.empty(total, np.uint8)
+    av = np.empty(total, np.int32) if _annotated else None
+    ap = np.empty(total, np.int32) if _annotated else None
+    check(lib.gvl_reconstruct_haplotypes_spliced_fused(
+        ctx.handle, _p(out), _p(av), _p(ap), _p(rg), _p(sh), _p(goi), c_i64(n_perm), _p(oo), _p(go), c_i64(go.shape[1]),
+        _p(gv), c_i64(gv.size), _p(vs), _p(il), c_i64(vs.size), _p(aa), _p(ao), _p(rf), _p(ro), c_i64(ro.size - 1),
+        c_u8(int(pad_char)), _p(kp), _p(ko), _p(rc)))
+    return (out, av, ap) if _annotated else out
+
+
+def reconstruct_annotated_haplotypes_spliced_fused(permuted_regions, flat_shifts, flat_geno_offset_idx, out_offsets,
+                                                   geno_offsets, geno_v_idxs, v_starts, ilens, alt_alleles, alt_offsets,
+                                                   ref_, ref_offsets, pad_char, keep=None, keep_offsets=None, to_rc=None,
+                                                   parallel=True, *, ctx=None):
+    """src/ffi/mod.rs:2097-2211.  Returns ``(out_data, annot_v, annot_pos)``."""
+    return reconstruct_haplotypes_spliced_fused(permuted_regions, flat_shifts, flat_geno_offset_idx, out_offsets,
+                                                geno_offsets, geno_v_idxs, v_starts, ilens, alt_alleles, alt_offsets, ref_,
+                                                ref_offsets, pad_char, keep, keep_offsets, to_rc, parallel,
+                                                _annotated=True, ctx=ctx)
+
+
+def choose_exonic_variants(starts, ends, geno_offset_idx, geno_v_idxs, geno_offsets, v_starts, ilens, *, ctx=None):
+    """src/ffi/mod.rs:229-238.  Returns ``(keep bool[n], keep_offsets i64[n_rows + 1])``."""
+    ctx = ctx or default_ctx()
+    goi = _c(geno_offset_idx, np.int64)
+    n_q, ploidy = goi.shape
+    go = _starts_stops(geno_offsets)
+    st, en = _c(starts, np.int32), _c(ends, np.int32)
+    gv, vs, il = _c(geno_v_idxs, np.int32), _c(v_starts, np.int32), _c(ilens, np.int32)
+    flat = goi.reshape(-1)
+    n = int(np.maximum(go[1, flat] - go[0, flat], 0).sum()) if flat.size else 0  # the allocation size (O(batch) host work)
+    keep = np.zeros(n, np.bool_)
+    koff = np.zeros(n_q * ploidy + 1, np.int64)
+    check(lib.gvl_choose_exonic_variants(ctx.handle, _p(st), _p(en), _p(goi), c_i64(n_q), c_i64(ploidy), _p(gv),
+                                         c_i64(gv.size), _p(go), c_i64(go.shape[1]), _p(vs), _p(il), c_i64(vs.size),
+                                         _p(keep), c_i64(n), _p(koff)))
+    return keep, koff
+
+
+def get_reference(regions, out_offsets, reference, ref_offsets, pad_char, parallel=True, to_rc=None, *, mode="u8",
+                  ctx=None):
+    """src/ffi/mod.rs:2402-2411.  Returns the flat padded reference rows (``mode="onehot"``: (total, 4) uint8)."""
+    ctx = ctx or default_ctx()
+    m = _MODES[mode]
+    if m not in (MODE_U8, MODE_ONEHOT):
+        raise ValueError("get_reference: mode must be 'u8' or 'onehot'")
+    rg, oo = _c(regions, np.int32), _c(out_offsets, np.int64)
+    rf, ro, rc = _c(reference, np.uint8), _c(ref_offsets, np.int64), _c(to_rc, np.bool_)
+    n = rg.shape[0]
+    assert oo.size == n + 1
+    total = int(oo[-1])
+    out = np.zeros(total * (4 if m == MODE_ONEHOT else 1), np.uint8)  # (zeros like the reference's allocation)
+    check(lib.gvl_get_reference(ctx.handle, _p(rg), _p(oo), c_i64(n), _p(rf), _p(ro), c_i64(ro.size - 1),
+                                c_u8(int(pad_char)), _p(rc), C.c_int(m), _p(out)))
+    return out.reshape(total, 4) if m == MODE_ONEHOT else out
+
+
+def ragged_to_padded(data, offsets, out, itemsize, out_len, *, ctx=None):
+    """src/ragged/mod.rs:7-23.  Copies each ragged row into the PRE-FILLED ``(n_rows, out_len)`` buffer ``out`` in place."""
+    ctx = ctx or default_ctx()
+    d, oo = np.ascontiguousarray(data), _c(offsets, np.int64)
+    if not out.flags.c_contiguous:
+        raise ValueError("out must be contiguous")  # (PyValueError at src/ragged/mod.rs:18)
+    n_rows = oo.size - 1
+    if out.nbytes != n_rows * int(out_len) * int(itemsize):
+        raise ValueError("out holds %d bytes, (n_rows, out_len) x itemsize needs %d" % (out.nbytes, n_rows * out_len * itemsize))
+    check(lib.gvl_ragged_to_padded(ctx.handle, _p(d), _p(oo), c_i64(n_rows), _p(out), c_i64(int(itemsize)),
+                                   c_i64(int(out_len))))
+
+
 def get_diffs_sparse(geno_offset_idx, geno_v_idxs, geno_offsets, ilens, keep=None, keep_offsets=None, q_starts=None,
                      q_ends=None, v_starts=None, parallel=True, *, ctx=None):
     """src/ffi/mod.rs:145-157.  Returns int32 ``(n_queries, ploidy)``."""

@@ -55,16 +55,26 @@ class Ragged:
 
     def to_padded(self, pad_value: Any) -> torch.Tensor:
         """Right-pad every row to the longest one (reference `to_padded`, _ragged.py:281-314 ->
-        src/ragged/mod.rs:7-23).  Runs on the device with torch indexing (not a hot path)."""
+        src/ragged/mod.rs:7-23): pre-fill with the pad value, then gvl_dev_ragged_to_padded copies the rows."""
+        import ctypes as C
+
+        from ._engine import _stream
+        from ._ffi import check, lib, ptr
+        from ._kernels import default_ctx
+
         outer = tuple(d for d in self.shape if d is not None)
         lens = self.offsets[1:] - self.offsets[:-1]
         n_rows = lens.numel()
         max_len = int(lens.max().item()) if n_rows else 0
-        out = torch.full((n_rows, max_len, *self.data.shape[1:]), pad_value, dtype=self.data.dtype, device=self.data.device)
-        if self.data.shape[0]:
-            row = torch.repeat_interleave(torch.arange(n_rows, device=self.data.device), lens)
-            col = torch.arange(self.data.shape[0], device=self.data.device) - self.offsets[:-1][row]
-            out[row, col] = self.data
+        dev = self.data.device
+        out = torch.full((n_rows, max_len, *self.data.shape[1:]), pad_value, dtype=self.data.dtype, device=dev)
+        if n_rows and max_len:
+            data, offsets = self.data.contiguous(), self.offsets.contiguous()
+            itemsize = data.element_size() * int(np.prod(data.shape[1:], dtype=np.int64))  # one-hot rows: 4 bytes per position
+            with torch.cuda.device(dev):
+                check(lib.gvl_dev_ragged_to_padded(default_ctx(dev.index or 0).handle, ptr(data), ptr(offsets),
+                                                   C.c_int64(n_rows), ptr(out), C.c_int64(itemsize), C.c_int64(max_len),
+                                                   _stream()))
         return out.reshape(*outer, max_len, *self.data.shape[1:])
 
     def to_numpy(self):

@@ -131,6 +131,9 @@ int gvl_ctx_create(int device, gvl_ctx **out) {
     ctx->fixed_len = -1;
     ctx->total = -1;
     ctx->plan_out_offsets = nullptr;
+    ctx->last_exec_kernel = 0;
+    ctx->zeros = nullptr;
+    ctx->zeros_bytes = 0;
     ctx->pinned = nullptr;
     ctx->pinned_bytes = 0;
     ctx->host_out_offsets_dev = nullptr;
@@ -156,6 +159,7 @@ void gvl_ctx_destroy(gvl_ctx *ctx) {
     free_workspace(ctx->trk);
     cudaFree(ctx->dev_words);
     cudaFree(ctx->trk_desc);
+    cudaFree(ctx->zeros);
     if (ctx->host_words) cudaFreeHost(ctx->host_words);
     for (auto &kv : ctx->statics) cudaFree(kv.second.dev);
     for (auto &kv : ctx->packed_refs) cudaFree(kv.second);

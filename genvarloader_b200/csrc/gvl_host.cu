@@ -400,6 +400,133 @@ int gvl_reconstruct_haplotypes_fused_finish(gvl_ctx *ctx, int mode, uint8_t pad_
     return GVL_OK;
 }
 
+int gvl_reconstruct_haplotypes_spliced_fused(
+    gvl_ctx *ctx, uint8_t *out, int32_t *annot_v, int32_t *annot_pos, const int32_t *permuted_regions,
+    const int32_t *flat_shifts, const int64_t *flat_geno_offset_idx, int64_t n_perm, const int64_t *out_offsets,
+    const int64_t *geno_offsets, int64_t n_geno, const int32_t *geno_v_idxs, int64_t n_geno_v, const int32_t *v_starts,
+    const int32_t *ilens, int64_t n_variants, const uint8_t *alt_alleles, const int64_t *alt_offsets, const uint8_t *ref_,
+    const int64_t *ref_offsets, int64_t n_contigs, uint8_t pad_char, const uint8_t *keep, const int64_t *keep_offsets,
+    const uint8_t *to_rc) {
+    if ((annot_v == nullptr) != (annot_pos == nullptr))
+        return fail(GVL_ERR_ARG, "gvl_reconstruct_haplotypes_spliced_fused: annot_v and annot_pos go together");
+    int64_t total = 0;
+    int rc = hap_begin(ctx, permuted_regions, flat_shifts, flat_geno_offset_idx, n_perm, 1, geno_offsets, n_geno,
+                       geno_v_idxs, n_geno_v, v_starts, ilens, n_variants, alt_alleles, alt_offsets, ref_, ref_offsets,
+                       n_contigs, -2, keep, keep_offsets, to_rc, const_cast<int64_t *>(out_offsets), &total);
+    if (rc) return rc;
+    return gvl_reconstruct_haplotypes_fused_finish(ctx, annot_v ? GVL_MODE_ANNOTATED : GVL_MODE_U8, pad_char, out, annot_v,
+                                                   annot_pos);
+}
+
+int gvl_choose_exonic_variants(gvl_ctx *ctx, const int32_t *starts, const int32_t *ends, const int64_t *geno_offset_idx,
+                               int64_t n_queries, int64_t ploidy, const int32_t *geno_v_idxs, int64_t n_geno_v,
+                               const int64_t *geno_offsets, int64_t n_geno, const int32_t *v_starts, const int32_t *ilens,
+                               int64_t n_variants, uint8_t *keep, int64_t keep_cap, int64_t *keep_offsets) {
+    if (!ctx || !geno_offsets || !keep_offsets) return fail(GVL_ERR_ARG, "gvl_choose_exonic_variants: NULL argument");
+    if (n_queries < 0 || ploidy < 1 || keep_cap < 0) return fail(GVL_ERR_ARG, "gvl_choose_exonic_variants: bad sizes");
+    const int64_t n_work = n_queries * ploidy;
+    if (n_work && (!starts || !ends || !geno_offset_idx || !geno_v_idxs || !v_starts || !ilens))
+        return fail(GVL_ERR_ARG, "gvl_choose_exonic_variants: NULL argument");
+    GVL_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    gvl_sparse_tables t;
+    if ((rc = resolve_tables(ctx, geno_offsets, n_geno, geno_v_idxs, n_geno_v, v_starts, ilens, n_variants, nullptr,
+                             nullptr, nullptr, nullptr, 0, &t)))
+        return rc;
+    Packer pk;
+    size_t i_st = pk.add(starts, sizeof(int32_t) * n_queries);
+    size_t i_en = pk.add(ends, sizeof(int32_t) * n_queries);
+    size_t i_goi = pk.add(geno_offset_idx, sizeof(int64_t) * n_work);
+    if ((rc = pk.upload(ctx, 0))) return rc;
+    void *d_ko, *d_keep = nullptr;
+    if ((rc = scratch(ctx, 1, sizeof(int64_t) * (n_work + 1), &d_ko))) return rc;
+    if (keep && keep_cap && (rc = scratch(ctx, 2, keep_cap, &d_keep))) return rc;
+    if ((rc = gvl_dev_choose_exonic_variants(ctx, &t, pk.ptr<int32_t>(i_st), pk.ptr<int32_t>(i_en), pk.ptr<int64_t>(i_goi),
+                                             n_queries, ploidy, (uint8_t *)d_keep, d_keep ? keep_cap : 0, (int64_t *)d_ko,
+                                             ctx->own_stream)))
+        return rc;
+    GVL_CUDA(cudaMemcpyAsync(keep_offsets, d_ko, sizeof(int64_t) * (n_work + 1), cudaMemcpyDeviceToHost, ctx->own_stream));
+    GVL_CUDA(cudaStreamSynchronize(ctx->own_stream));
+    const int64_t n = keep_offsets[n_work];
+    if (n > (d_keep ? keep_cap : 0))
+        return fail(GVL_ERR_CAPACITY, "gvl_choose_exonic_variants: keep holds %lld entries, %lld needed", (long long)keep_cap,
+                    (long long)n);
+    if (n) {
+        GVL_CUDA(cudaMemcpyAsync(keep, d_keep, (size_t)n, cudaMemcpyDeviceToHost, ctx->own_stream));
+        GVL_CUDA(cudaStreamSynchronize(ctx->own_stream));
+    }
+    return GVL_OK;
+}
+
+int gvl_get_reference(gvl_ctx *ctx, const int32_t *regions, const int64_t *out_offsets, int64_t n_regions,
+                      const uint8_t *reference, const int64_t *ref_offsets, int64_t n_contigs, uint8_t pad_char,
+                      const uint8_t *to_rc, int mode, uint8_t *out) {
+    if (!ctx || !out_offsets || !reference || !ref_offsets) return fail(GVL_ERR_ARG, "gvl_get_reference: NULL argument");
+    if (n_regions < 0 || n_contigs < 0) return fail(GVL_ERR_ARG, "gvl_get_reference: bad sizes");
+    if (n_regions && !regions) return fail(GVL_ERR_ARG, "gvl_get_reference: regions is NULL");
+    if (mode != GVL_MODE_U8 && mode != GVL_MODE_ONEHOT) return fail(GVL_ERR_ARG, "gvl_get_reference: mode must be u8 or one-hot");
+    GVL_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    const void *d;
+    gvl_sparse_tables t;
+    memset(&t, 0, sizeof(t));
+    if ((rc = static_dev(ctx, ref_offsets, sizeof(int64_t) * (n_contigs + 1), 14, &d))) return rc;
+    t.ref_offsets = (const int64_t *)d;
+    if ((rc = static_dev(ctx, reference, ref_offsets[n_contigs], 15, &d))) return rc;
+    t.ref = (const uint8_t *)d;
+    t.n_contigs = n_contigs;
+    if ((rc = packed_ref(ctx, reference, t.ref, ref_offsets[n_contigs], &t.ref_packed))) return rc;
+    const int64_t total = out_offsets[n_regions];
+    if (total == 0) return GVL_OK;
+    if (!out) return fail(GVL_ERR_ARG, "gvl_get_reference: out is NULL");
+    // equal rows take the fixed-length plan (no sync between plan and execute, packed one-hot kernel eligible)
+    int64_t row_length = out_offsets[1] - out_offsets[0];
+    for (int64_t i = 1; i < n_regions && row_length >= 0; i++)
+        if (out_offsets[i + 1] - out_offsets[i] != row_length) row_length = -1;
+    Packer pk;
+    size_t i_reg = pk.add(regions, sizeof(int32_t) * 3 * n_regions);
+    size_t i_oo = pk.add(out_offsets, sizeof(int64_t) * (n_regions + 1));
+    size_t i_rc = pk.add(to_rc, n_regions);
+    if ((rc = pk.upload(ctx, 0))) return rc;
+    const int64_t out_bytes = mode == GVL_MODE_ONEHOT ? total * 4 : total;
+    void *d_out;
+    if ((rc = scratch(ctx, 2, out_bytes, &d_out))) return rc;
+    if ((rc = gvl_dev_get_reference(ctx, &t, pk.ptr<int32_t>(i_reg), const_cast<int64_t *>(pk.ptr<int64_t>(i_oo)), n_regions,
+                                    row_length, pk.ptr<uint8_t>(i_rc), mode, pad_char, (uint8_t *)d_out, ctx->own_stream)))
+        return rc;
+    GVL_CUDA(cudaMemcpyAsync(out, d_out, (size_t)out_bytes, cudaMemcpyDeviceToHost, ctx->own_stream));
+    GVL_CUDA(cudaStreamSynchronize(ctx->own_stream));
+    return GVL_OK;
+}
+
+int gvl_ragged_to_padded(gvl_ctx *ctx, const void *data, const int64_t *offsets, int64_t n_rows, void *out,
+                         int64_t itemsize, int64_t out_len) {
+    if (!ctx) return fail(GVL_ERR_ARG, "gvl_ragged_to_padded: ctx is NULL");
+    if (n_rows < 0 || itemsize < 1 || out_len < 0) return fail(GVL_ERR_ARG, "gvl_ragged_to_padded: bad sizes");
+    if (n_rows == 0 || out_len == 0) return GVL_OK;
+    if (!data || !offsets || !out) return fail(GVL_ERR_ARG, "gvl_ragged_to_padded: NULL argument");
+    GVL_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    const int64_t lo = offsets[0], hi = offsets[n_rows];  // only [lo, hi) of `data` is read
+    const int64_t out_bytes = n_rows * out_len * itemsize;
+    void *d_data, *d_off, *d_out;
+    if ((rc = scratch(ctx, 0, (hi - lo) * itemsize + 16, &d_data))) return rc;
+    if ((rc = scratch(ctx, 1, sizeof(int64_t) * (n_rows + 1), &d_off))) return rc;
+    if ((rc = scratch(ctx, 2, out_bytes, &d_out))) return rc;
+    if (hi > lo)
+        GVL_CUDA(cudaMemcpyAsync(d_data, (const char *)data + lo * itemsize, (size_t)((hi - lo) * itemsize),
+                                 cudaMemcpyHostToDevice, ctx->own_stream));
+    GVL_CUDA(cudaMemcpyAsync(d_off, offsets, sizeof(int64_t) * (n_rows + 1), cudaMemcpyHostToDevice, ctx->own_stream));
+    GVL_CUDA(cudaMemcpyAsync(d_out, out, (size_t)out_bytes, cudaMemcpyHostToDevice, ctx->own_stream));  // the pre-fill
+    // the device copy of `data` starts at item lo: shift the base pointer instead of rewriting the offsets
+    if ((rc = gvl_dev_ragged_to_padded(ctx, (const char *)d_data - lo * itemsize, (const int64_t *)d_off, n_rows, d_out,
+                                       itemsize, out_len, ctx->own_stream)))
+        return rc;
+    GVL_CUDA(cudaMemcpyAsync(out, d_out, (size_t)out_bytes, cudaMemcpyDeviceToHost, ctx->own_stream));
+    GVL_CUDA(cudaStreamSynchronize(ctx->own_stream));
+    return GVL_OK;
+}
+
 int gvl_get_diffs_sparse(gvl_ctx *ctx, const int64_t *geno_offset_idx, int64_t n_queries, int64_t ploidy,
                          const int32_t *geno_v_idxs, int64_t n_geno_v, const int64_t *geno_offsets, int64_t n_geno,
                          const int32_t *ilens, int64_t n_variants, const uint8_t *keep, const int64_t *keep_offsets,

@@ -227,6 +227,35 @@ int gvl_dev_intervals_to_tracks(gvl_ctx *ctx, const gvl_intervals *itv, const in
                                 const int32_t *starts, int64_t n_queries, const int64_t *out_offsets,
                                 int64_t total, float *out, gvl_stream stream);
 
+/* ---- device layer: the small entries either side of reconstruction ------------------ */
+/* choose_exonic_variants, src/ffi/mod.rs:229-238 -> src/genotypes/mod.rs:132-176: for every (query, hap) row,
+ * keep_offsets[k+1] - keep_offsets[k] = size of its genotype slice and keep[keep_offsets[k] + i] = 1 iff variant i
+ * lies fully inside [starts[q], ends[q]) (v_pos >= start && v_pos - min(ilen,0) + 1 <= end).
+ *   starts/ends i32[n_queries], geno_offset_idx i64[n_queries*ploidy], keep u8[keep_cap] (may be NULL: offsets only),
+ *   keep_offsets i64[n_queries*ploidy + 1].  Entries beyond keep_cap are not written; the caller compares
+ *   keep_offsets[n_work] with keep_cap (the host entry below does).  No host sync. */
+int gvl_dev_choose_exonic_variants(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_t *starts, const int32_t *ends,
+                                   const int64_t *geno_offset_idx, int64_t n_queries, int64_t ploidy, uint8_t *keep,
+                                   int64_t keep_cap, int64_t *keep_offsets, gvl_stream stream);
+
+/* get_reference, src/ffi/mod.rs:2402-2411 -> src/reference/mod.rs:56-120: row i = contig regions[i,0] from
+ * regions[i,1] on, positions outside the contig filled with pad_char, masked rows reverse-complemented
+ * (src/reverse.rs:45-69).  Runs as the zero-variant case of the haplotype plan + execute kernels, so GVL_MODE_ONEHOT
+ * (with tab->ref_packed: the packed kernel) is available besides GVL_MODE_U8.  Only tab->{ref, ref_offsets,
+ * n_contigs, ref_packed} are read.
+ *   row_length >= 0: every row has that length, out_offsets (device i64[n+1]) is written, no host sync;
+ *   row_length == -1: rows are sized by the caller's out_offsets (an input; the reference requires
+ *                     out_offsets[i+1] - out_offsets[i] == end - start), one stream sync like every ragged plan. */
+int gvl_dev_get_reference(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_t *regions, int64_t *out_offsets,
+                          int64_t n_regions, int64_t row_length, const uint8_t *to_rc, int mode, uint8_t pad_char,
+                          uint8_t *out, gvl_stream stream);
+
+/* ragged_to_padded, src/ragged/mod.rs:7-23 (seqpro-core Ragged::to_padded_into): copies min(len_r, out_len) items of
+ * row r to out[r, :]; `out` is (n_rows, out_len) items of `itemsize` bytes PRE-FILLED with the pad value by the
+ * caller, exactly like the reference.  Device pointers, any alignment. */
+int gvl_dev_ragged_to_padded(gvl_ctx *ctx, const void *data, const int64_t *offsets, int64_t n_rows, void *out,
+                             int64_t itemsize, int64_t out_len, gvl_stream stream);
+
 /* ---- host layer: reference-shaped entries (host pointers in, host pointers out) ------ */
 /* Upload (or refresh) a static array and cache it by host address; later gvl_* calls that see
  * the same (ptr, bytes) use the device copy.  The caller must not mutate or free the host array
@@ -276,6 +305,34 @@ int gvl_reconstruct_haplotypes_from_sparse(
     const uint8_t *alt_alleles, const int64_t *alt_offsets, const uint8_t *ref_, const int64_t *ref_offsets,
     int64_t n_contigs, uint8_t pad_char, const uint8_t *keep, const int64_t *keep_offsets, int32_t *annot_v_idxs,
     int32_t *annot_ref_pos);
+
+/* reconstruct_haplotypes_spliced_fused, src/ffi/mod.rs:1983-2071, and (annot_v/annot_pos non-NULL)
+ * reconstruct_annotated_haplotypes_spliced_fused, src/ffi/mod.rs:2097-2211: the splice plan's permuted elements are
+ * rows of ploidy 1 sized by the caller's out_offsets (i64[n_perm+1], input); masked elements are reverse-complemented
+ * (annotation rows reversed).  out: host u8[out_offsets[n_perm]]; annotations host i32 of the same length. */
+int gvl_reconstruct_haplotypes_spliced_fused(
+    gvl_ctx *ctx, uint8_t *out, int32_t *annot_v, int32_t *annot_pos, const int32_t *permuted_regions,
+    const int32_t *flat_shifts, const int64_t *flat_geno_offset_idx, int64_t n_perm, const int64_t *out_offsets,
+    const int64_t *geno_offsets, int64_t n_geno, const int32_t *geno_v_idxs, int64_t n_geno_v, const int32_t *v_starts,
+    const int32_t *ilens, int64_t n_variants, const uint8_t *alt_alleles, const int64_t *alt_offsets, const uint8_t *ref_,
+    const int64_t *ref_offsets, int64_t n_contigs, uint8_t pad_char, const uint8_t *keep, const int64_t *keep_offsets,
+    const uint8_t *to_rc);
+
+/* choose_exonic_variants, src/ffi/mod.rs:229-238.  keep: host u8[keep_cap] with keep_cap >= the summed slice sizes
+ * (GVL_ERR_CAPACITY otherwise; keep_offsets is valid either way, so a caller may size with keep_cap = 0 first). */
+int gvl_choose_exonic_variants(gvl_ctx *ctx, const int32_t *starts, const int32_t *ends, const int64_t *geno_offset_idx,
+                               int64_t n_queries, int64_t ploidy, const int32_t *geno_v_idxs, int64_t n_geno_v,
+                               const int64_t *geno_offsets, int64_t n_geno, const int32_t *v_starts, const int32_t *ilens,
+                               int64_t n_variants, uint8_t *keep, int64_t keep_cap, int64_t *keep_offsets);
+
+/* get_reference, src/ffi/mod.rs:2402-2411.  out: host u8[out_offsets[n_regions]] (x4 for GVL_MODE_ONEHOT). */
+int gvl_get_reference(gvl_ctx *ctx, const int32_t *regions, const int64_t *out_offsets, int64_t n_regions,
+                      const uint8_t *reference, const int64_t *ref_offsets, int64_t n_contigs, uint8_t pad_char,
+                      const uint8_t *to_rc, int mode, uint8_t *out);
+
+/* ragged_to_padded, src/ragged/mod.rs:7-23.  out: host, (n_rows, out_len) items, pre-filled by the caller. */
+int gvl_ragged_to_padded(gvl_ctx *ctx, const void *data, const int64_t *offsets, int64_t n_rows, void *out,
+                         int64_t itemsize, int64_t out_len);
 
 /* get_diffs_sparse, src/ffi/mod.rs:145-157.  diffs: host i32[n_queries*ploidy]. */
 int gvl_get_diffs_sparse(gvl_ctx *ctx, const int64_t *geno_offset_idx, int64_t n_queries, int64_t ploidy,

@@ -326,15 +326,10 @@ struct TrkTileRecs {
 // value of the painted source track at relative position tp (0 <= tp < track_n), straight from the
 // interval SoA: last interval with start <= q_start + tp, if it also ends after it (intervals are
 // sorted and non-overlapping, src/intervals.rs contract).
-__device__ __forceinline__ float track_at_global(const TrkDesc &T, int64_t lo, int64_t hi, int64_t q_start, int64_t tp,
-                                                 int64_t hint_lo = 0, int64_t hint_hi = 0) {
+__device__ __forceinline__ float track_at_global(const TrkDesc &T, int64_t lo, int64_t hi, int64_t q_start, int64_t tp) {
     if (T.dense) return T.dense[lo + tp];  // dense source: `lo` is the window's offset
     const int64_t g = q_start + tp;
     int64_t a = lo, b = hi;  // find last i in [lo,hi) with starts[i] <= g
-    if (hint_hi > hint_lo) {  // the caller's cursor neighbourhood [hint_lo, hint_hi): narrow the search when it brackets g
-        if ((int64_t)T.itv_starts[hint_lo] <= g) a = hint_lo + 1;
-        if (hint_hi < hi && (int64_t)T.itv_starts[hint_hi] > g) b = hint_hi;
-    }
     while (a < b) {
         int64_t mid = (a + b) >> 1;
         if ((int64_t)T.itv_starts[mid] <= g) a = mid + 1; else b = mid;
@@ -350,11 +345,10 @@ struct TrkSrc {
     int64_t track_n;
     const TrkDesc *T;
     int64_t itv_lo, itv_hi, q_start;
-    int64_t hint_lo, hint_hi;  // optional cursor neighbourhood for the interval search (0, 0: none)
     __device__ __forceinline__ float at(int64_t tp) const {  // 0 <= tp < track_n expected
         if (tp >= w0 && tp < w1) return win[tp - w0];
         if (tp < 0 || tp >= track_n) return 0.0f;  // out of contract in the reference (index panic)
-        return track_at_global(*T, itv_lo, itv_hi, q_start, tp, hint_lo, hint_hi);
+        return track_at_global(*T, itv_lo, itv_hi, q_start, tp);
     }
 };
 
@@ -716,7 +710,7 @@ __global__ void __launch_bounds__(TRK_THREADS, 1024 / TRK_THREADS) trk_exec_kern
         TRK_TR(4);
         itv_prev = T.dense ? -1 : s_itv_first;
         tgt_prev = (int32_t)imin64(q_start + w0, INT32_MAX);
-        TrkSrc src{s_win, w0, w1, track_n, &T, itv_lo, itv_hi, q_start, 0, 0};
+        TrkSrc src{s_win, w0, w1, track_n, &T, itv_lo, itv_hi, q_start};
 
         const int32_t jo_lo = rc ? L - seg_end : cur;
         const int32_t jo_hi = rc ? L - cur : seg_end;
@@ -859,8 +853,6 @@ __global__ void __launch_bounds__(TRK_THREADS, 1024 / TRK_THREADS) trk_exec_kern
     }
 }
 
-#include "gvl_tracks_direct.cuh"
-
 __global__ void prng_kernel(uint64_t a, uint64_t b, uint64_t c, uint64_t d, int which, uint64_t *out) {
     *out = which ? hash4(a, b, c, d) : xorshift64(a);
 }
@@ -899,17 +891,6 @@ static int launch_trk_exec(gvl_ctx *ctx, int64_t n_work, int64_t ploidy, int64_t
         for (int64_t t = 0; t < n_tracks; t++) P.inl[t] = host_desc[t];
     const int64_t grid = P.grid_per_track * n_tracks;
     if (grid > INT32_MAX) return fail(GVL_ERR_ARG, "too many track tiles");
-    // GVL_TRK_EXEC=direct selects the output-coordinate kernel (gvl_tracks_direct.cuh): bit-exact, but measured slower
-    // (profiles/r1_packed.md), so the windowed kernel stays the default
-    static const bool use_direct = [] {
-        const char *e = getenv("GVL_TRK_EXEC");
-        return e && e[0] == 'd';
-    }();
-    if (use_direct) {
-        trk_exec_direct_kernel<<<(unsigned)grid, TRKD_THREADS, 0, st>>>(P);
-        GVL_LAUNCH_CHECK();
-        return GVL_OK;
-    }
     static const bool smem_ok = [] {
         return cudaFuncSetAttribute(trk_exec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * TRK_WIN)) == cudaSuccess;
     }();

@@ -372,6 +372,22 @@ def _debug_hash4(a: int, b: int, c: int, d: int, *, ctx=None) -> int:
 
 
 # ---------------------------------------------------------------------------------- svar2 source
+def hap_diffs_svar2(regions, ploidy, vk_pos, vk_key, vk_off, dense_pos, dense_key, dense_range, dense_present,
+                    dense_present_off, key_ilen, *, ctx=None):
+    """src/svar2/mod.rs:73-146 (the core of hap_diffs_from_svar2_readbound, src/ffi/mod.rs:1414-1427) over the decoded key
+    table's ILEN column.  Returns int32 ``(batch, ploidy)``."""
+    ctx = ctx or default_ctx()
+    rg = _c(regions, np.int32)
+    batch = rg.shape[0]
+    vp, vk, vo = _c(vk_pos, np.int32), _c(vk_key, np.int32), _c(vk_off, np.int64)
+    dp, dk, dr = _c(dense_pos, np.int32), _c(dense_key, np.int32), _c(dense_range, np.int32)
+    db, do, ki = _c(dense_present, np.uint8), _c(dense_present_off, np.int64), _c(key_ilen, np.int32)
+    diffs = np.zeros((batch, int(ploidy)), np.int32)
+    check(lib.gvl_hap_diffs_svar2(ctx.handle, _p(rg), c_i64(batch), c_i64(int(ploidy)), _p(vp), _p(vk), _p(vo), _p(dp), _p(dk),
+                                  c_i64(dp.size), _p(dr), _p(db), _p(do), _p(ki), c_i64(ki.size), _p(diffs)))
+    return diffs
+
+
 def reconstruct_haplotypes_from_svar2(regions, shifts, vk_pos, vk_key, vk_off, dense_pos, dense_key, dense_range,
                                       dense_present, dense_present_off, key_ilen, key_alt, key_alt_off, ref_,
                                       ref_offsets, pad_char, output_length, parallel=True, *, to_rc=None, mode="u8",

@@ -702,6 +702,8 @@ namespace gvl {
 // standalone get_diffs_sparse (all four branches of src/genotypes/mod.rs:46-104)
 struct DiffParams {
     gvl_sparse_tables tab;
+    MergedLists merged;  // svar2 source: merged per-row lists (key == NULL: SVAR1 CSR through goi)
+    int64_t q_stride;    // element stride of q_starts / q_ends (3: columns 1 and 2 of a (b,3) regions array)
     const int64_t *goi;
     const uint8_t *keep;
     const int64_t *keep_off;
@@ -717,8 +719,7 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) diffs_kernel(DiffParams P) {
     const int64_t k = (int64_t)blockIdx.x * PLAN_WARPS + (threadIdx.x >> 5);
     if (k >= P.n_work) return;
     const int64_t query = k / P.ploidy;
-    const MergedLists no_merge{nullptr, nullptr, nullptr, nullptr};
-    const RowVars rv = row_vars(P.tab, no_merge, P.goi, k);
+    const RowVars rv = row_vars(P.tab, P.merged, P.goi, k);
     const int64_t nvar = rv.nvar;
     const bool has_query = P.q_starts && P.q_ends && P.use_v_starts;
     const bool has_keep = P.keep && P.keep_off;
@@ -727,7 +728,7 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) diffs_kernel(DiffParams P) {
     int64_t acc = 0;
     if (has_query) {
         DiffState ds;
-        diff_init(ds, P.q_starts[query], P.q_ends[query]);
+        diff_init(ds, P.q_starts[query * P.q_stride], P.q_ends[query * P.q_stride]);
         bool live = true;
         for (int64_t base = 0; base < nvar && live; base += 32) {
             int64_t i = base + lane;
@@ -735,7 +736,7 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) diffs_kernel(DiffParams P) {
             bool kp = false;
             if (i < nvar) {
                 int32_t vi = gv[i];
-                pos = P.tab.v_starts[vi];
+                pos = rv.mpos ? rv.mpos[i] : P.tab.v_starts[vi];
                 il = P.tab.ilens[vi];
                 kp = has_keep ? (P.keep[keep_base + i] != 0) : true;
             }
@@ -1048,12 +1049,50 @@ int gvl_dev_get_diffs_sparse(gvl_ctx *ctx, const gvl_sparse_tables *tab, const i
     if (n_work == 0) return GVL_OK;
     DiffParams P;
     P.tab = *tab;
+    P.merged = MergedLists{nullptr, nullptr, nullptr, nullptr};
+    P.q_stride = 1;
     P.goi = geno_offset_idx;
     P.keep = keep;
     P.keep_off = keep_offsets;
     P.q_starts = q_starts;
     P.q_ends = q_ends;
     P.use_v_starts = use_v_starts;
+    P.n_work = n_work;
+    P.ploidy = ploidy;
+    P.diffs = diffs;
+    diffs_kernel<<<(unsigned)((n_work + PLAN_WARPS - 1) / PLAN_WARPS), PLAN_WARPS * 32, 0, st>>>(P);
+    GVL_LAUNCH_CHECK();
+    return GVL_OK;
+}
+
+int gvl_dev_hap_diffs_svar2(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_svar2_channels *ch, const int32_t *regions,
+                            int64_t batch, int64_t ploidy, int64_t max_merged, int32_t *diffs, gvl_stream stream) {
+    if (!ctx || !tab || !tab->ilens || !ch || !ch->vk_off || !ch->dense_range || !ch->dense_present_off)
+        return fail(GVL_ERR_ARG, "gvl_dev_hap_diffs_svar2: NULL argument");
+    if (batch < 0 || ploidy < 1 || max_merged < 0) return fail(GVL_ERR_ARG, "gvl_dev_hap_diffs_svar2: bad sizes");
+    const int64_t n_work = batch * ploidy;
+    if (n_work == 0) return GVL_OK;
+    if (!regions || !diffs) return fail(GVL_ERR_ARG, "gvl_dev_hap_diffs_svar2: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    GVL_CUDA(cudaSetDevice(ctx->device));
+    // merged lists go to the TRACK workspace (never holds a plan across calls), so a haplotype plan that has not been
+    // executed yet stays valid
+    int rc;
+    if ((rc = ensure_rows(ctx, ctx->trk, n_work))) return rc;
+    if ((rc = ensure_merged(ctx, ctx->trk, max_merged))) return rc;
+    int64_t *words = ctx->dev_words + W_COUNT;
+    GVL_CUDA(cudaMemsetAsync(words, 0, sizeof(int64_t) * W_COUNT, st));
+    if ((rc = gvl_svar2_merge_launch(ctx, &ctx->trk, words, ch, batch, ploidy, max_merged, st))) return rc;
+    DiffParams P;
+    P.tab = *tab;
+    P.merged = MergedLists{ctx->trk.m_pos, ctx->trk.m_key, ctx->trk.m_off, ctx->trk.m_len};
+    P.q_stride = 3;
+    P.goi = nullptr;
+    P.keep = nullptr;
+    P.keep_off = nullptr;
+    P.q_starts = regions + 1;
+    P.q_ends = regions + 2;
+    P.use_v_starts = 1;
     P.n_work = n_work;
     P.ploidy = ploidy;
     P.diffs = diffs;

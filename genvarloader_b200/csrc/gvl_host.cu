@@ -353,6 +353,61 @@ int gvl_reconstruct_haplotypes_from_svar2_begin(
     return GVL_OK;
 }
 
+int gvl_hap_diffs_svar2(gvl_ctx *ctx, const int32_t *regions, int64_t batch, int64_t ploidy, const int32_t *vk_pos,
+                        const int32_t *vk_key, const int64_t *vk_off, const int32_t *dense_pos, const int32_t *dense_key,
+                        int64_t n_dense, const int32_t *dense_range, const uint8_t *dense_present,
+                        const int64_t *dense_present_off, const int32_t *key_ilen, int64_t n_keys, int32_t *diffs) {
+    if (!ctx || !vk_off || !dense_range || !dense_present_off || !key_ilen)
+        return fail(GVL_ERR_ARG, "gvl_hap_diffs_svar2: NULL argument");
+    if (batch < 0 || ploidy < 1) return fail(GVL_ERR_ARG, "gvl_hap_diffs_svar2: bad sizes");
+    const int64_t n_work = batch * ploidy;
+    if (n_work == 0) return GVL_OK;
+    if (!regions || !diffs) return fail(GVL_ERR_ARG, "gvl_hap_diffs_svar2: NULL argument");
+    GVL_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    const void *d;
+    gvl_sparse_tables t;
+    memset(&t, 0, sizeof(t));
+    if ((rc = static_dev(ctx, key_ilen, sizeof(int32_t) * n_keys, 11, &d))) return rc;
+    t.ilens = (const int32_t *)d;
+    t.v_starts = t.ilens;  // unused by the merged-list source
+    t.n_variants = n_keys;
+    gvl_svar2_channels ch;
+    if ((rc = static_dev(ctx, dense_pos, sizeof(int32_t) * n_dense, 16, &d))) return rc;
+    ch.dense_pos = (const int32_t *)d;
+    if ((rc = static_dev(ctx, dense_key, sizeof(int32_t) * n_dense, 17, &d))) return rc;
+    ch.dense_key = (const int32_t *)d;
+    const int64_t n_vk = vk_off[n_work];
+    const int64_t n_bits = dense_present_off[n_work];
+    int64_t max_merged = n_vk;
+    for (int64_t q = 0; q < batch; q++) {
+        const int64_t w = (int64_t)dense_range[2 * q + 1] - dense_range[2 * q];
+        if (w > 0) max_merged += ploidy * w;
+    }
+    Packer pk;
+    size_t i_reg = pk.add(regions, sizeof(int32_t) * 3 * batch);
+    size_t i_vp = pk.add(vk_pos ? (const void *)vk_pos : (const void *)vk_off, sizeof(int32_t) * n_vk);
+    size_t i_vkk = pk.add(vk_key ? (const void *)vk_key : (const void *)vk_off, sizeof(int32_t) * n_vk);
+    size_t i_vo = pk.add(vk_off, sizeof(int64_t) * (n_work + 1));
+    size_t i_dr = pk.add(dense_range, sizeof(int32_t) * 2 * batch);
+    size_t i_dp = pk.add(dense_present ? (const void *)dense_present : (const void *)vk_off, (n_bits + 7) / 8);
+    size_t i_do = pk.add(dense_present_off, sizeof(int64_t) * (n_work + 1));
+    if ((rc = pk.upload(ctx, 0))) return rc;
+    ch.vk_pos = pk.ptr<int32_t>(i_vp);
+    ch.vk_key = pk.ptr<int32_t>(i_vkk);
+    ch.vk_off = pk.ptr<int64_t>(i_vo);
+    ch.dense_range = pk.ptr<int32_t>(i_dr);
+    ch.dense_present = pk.ptr<uint8_t>(i_dp);
+    ch.dense_present_off = pk.ptr<int64_t>(i_do);
+    void *d_diffs;
+    if ((rc = scratch(ctx, 1, sizeof(int32_t) * n_work, &d_diffs))) return rc;
+    if ((rc = gvl_dev_hap_diffs_svar2(ctx, &t, &ch, pk.ptr<int32_t>(i_reg), batch, ploidy, max_merged, (int32_t *)d_diffs,
+                                      ctx->own_stream)))
+        return rc;
+    GVL_CUDA(cudaMemcpyAsync(diffs, d_diffs, sizeof(int32_t) * n_work, cudaMemcpyDeviceToHost, ctx->own_stream));
+    return gvl_ctx_check(ctx, ctx->own_stream);  // syncs; reports a merged-list overflow
+}
+
 int gvl_reconstruct_haplotypes_from_sparse(
     gvl_ctx *ctx, uint8_t *out, const int64_t *out_offsets, const int32_t *regions, const int32_t *shifts,
     const int64_t *geno_offset_idx, int64_t batch, int64_t ploidy, const int64_t *geno_offsets, int64_t n_geno,

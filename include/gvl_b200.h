@@ -150,6 +150,12 @@ int gvl_dev_hap_plan_svar2(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl
                            const uint8_t *to_rc, int64_t output_length, int64_t max_merged, int64_t *out_offsets,
                            int32_t *diffs, gvl_stream stream);
 
+/* hap_diffs_svar2, src/svar2/mod.rs:73-146 (the core of hap_diffs_from_svar2_readbound, src/ffi/mod.rs:1414-1427): the
+ * clipped length differences of get_diffs_sparse over each row's MERGED two-channel list.  Only tab->ilens (the decoded
+ * key table's ILEN column) is read.  diffs: device i32[batch*ploidy].  Leaves the current haplotype plan intact. */
+int gvl_dev_hap_diffs_svar2(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_svar2_channels *ch, const int32_t *regions,
+                            int64_t batch, int64_t ploidy, int64_t max_merged, int32_t *diffs, gvl_stream stream);
+
 /* Total number of output positions of the current plan (= out_offsets[-1]).  Fixed-length plans
  * answer from the host; ragged plans synchronise the stream once (the reference sizes its
  * allocation at the same point, src/ffi/mod.rs:814). */
@@ -295,6 +301,12 @@ int gvl_reconstruct_haplotypes_from_svar2_begin(
     const int32_t *dense_range, const uint8_t *dense_present, const int64_t *dense_present_off, const int32_t *key_ilen,
     const uint8_t *key_alt, const int64_t *key_alt_off, int64_t n_keys, const uint8_t *ref_, const int64_t *ref_offsets,
     int64_t n_contigs, int64_t output_length, const uint8_t *to_rc, int64_t *out_offsets, int64_t *total);
+
+/* hap_diffs_svar2 (see gvl_dev_hap_diffs_svar2), host pointers.  diffs: host i32[batch*ploidy]. */
+int gvl_hap_diffs_svar2(gvl_ctx *ctx, const int32_t *regions, int64_t batch, int64_t ploidy, const int32_t *vk_pos,
+                        const int32_t *vk_key, const int64_t *vk_off, const int32_t *dense_pos, const int32_t *dense_key,
+                        int64_t n_dense, const int32_t *dense_range, const uint8_t *dense_present,
+                        const int64_t *dense_present_off, const int32_t *key_ilen, int64_t n_keys, int32_t *diffs);
 
 /* reconstruct_haplotypes_from_sparse, src/ffi/mod.rs:634-655: caller-sized rows, writes `out`
  * (and the optional annotation buffers) in place.  out: host u8[out_offsets[b*p]]. */

@@ -39,6 +39,10 @@ def test_svar2_source_vs_oracle(cuda_device, vkb, L, dense_frac):
     r_idx, s_idx = rng.integers(0, d.n_regions, 9), rng.integers(0, d.n_samples, 9)
     regions, goi, to_rc, ds_idx = synth.batch_args(d, r_idx, s_idx)
     ch = synth.to_svar2_channels(d, regions, ds_idx, dense_frac=dense_frac, seed=3)
+    cargs = (regions, d.ploidy, ch["vk_pos"], ch["vk_key"], ch["vk_off"], ch["dense_pos"], ch["dense_key"], ch["dense_range"],
+             ch["dense_present"], ch["dense_present_off"], ch["key_ilen"])
+    e_diffs, g_diffs = O.hap_diffs_svar2(*cargs), K.hap_diffs_svar2(*cargs)  # src/svar2/mod.rs:73-146
+    assert g_diffs.dtype == e_diffs.dtype and g_diffs.shape == e_diffs.shape and (g_diffs == e_diffs).all()
     for out_len, use_shift in ((-1, False), (L - 500, True), (L + 40, False)):
         shifts = rng.integers(0, 60, goi.shape).astype(np.int32) if use_shift else np.zeros(goi.shape, np.int32)
         for rc in (None, to_rc):

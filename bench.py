@@ -204,7 +204,9 @@ def run_reference(args):
         "impl": "reference", "metric": "haplotype bp/s (one-hot)", "value": v, "unit": "bp/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {w['desc']}", "window_bp": w["window"], "haplotypes_per_batch": w["pairs"] * 2},
+        "config": {"workload": f"{args.workload}: {w['desc']}", "window_bp": w["window"], "haplotypes_per_batch": w["pairs"] * 2,
+                   "variants_per_batch": batches[0]["nvar"], "output": "uint8 one-hot (L,4)", "source": "SVAR1-style sparse CSR",
+                   "parallelism": f"{threads} host threads, one task per (query, hap) row"},
         "cpu_baseline": {"value": v, "unit": "bp/s", "cores": threads, "kind": "port",
                          "sample": f"{args.steps} batches of {w['pairs'] * 2} haplotypes x {w['window']} bp: C restatement of "
                                    "reconstruct_haplotypes_fused + separate one-hot pass, one task per (query, hap)"},

@@ -578,13 +578,11 @@ class Dataset:
                     base_seed = int(np.bitwise_xor.reduce(ds_idx.astype(np.uint64)))  # :215-218
                 else:
                     base_seed = int(self.rng.integers(0, np.iinfo(np.uint64).max, dtype=np.uint64))  # :219-222
+                # the reference's flat buffer is track-major (_reconstruct.py:238) while its offsets describe
+                # (b, t, p, ~l) (:292-300); the kernel writes the latter directly so data and offsets agree for t > 1
                 out = eng.realign_tracks(names, t_reg, t_shifts, t_goi, pk.get(i_tr), track_lengths, oo, total, ids, params,
-                                         base_seed, max_rec, keep, keep_off, t_rc)
-                # the flat buffer is track-major (_reconstruct.py:238); reorder to the (b, t, p, ~l) layout the
-                # reference's offsets describe (:292-300) so data and offsets agree for t > 1
+                                         base_seed, max_rec, keep, keep_off, t_rc, layout="btp")
                 lens_bp = (oo[1:] - oo[:-1]).view(b, p)
-                if t > 1:
-                    out = _track_major_to_btp(out, oo, t, b, p, total)
                 lens = lens_bp.view(b, 1, p).expand(b, t, p).reshape(-1)
                 offsets = torch.zeros(b * t * p + 1, dtype=torch.int64, device=dev)
                 torch.cumsum(lens, 0, out=offsets[1:])

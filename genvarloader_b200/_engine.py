@@ -179,9 +179,11 @@ class Engine:
     # ------------------------------------------------------------------ tracks
     def realign_tracks(self, names, regions, shifts, geno_offset_idx, offset_idxs, track_lengths, out_offsets,
                        total_per_track: int, strategy_ids, params, base_seed: int, max_records: int, keep=None,
-                       keep_offsets=None, to_rc=None, query_seed=None, out=None):
+                       keep_offsets=None, to_rc=None, query_seed=None, out=None, layout="tbp"):
         """gvl_dev_realign_tracks: all `names` in one plan + one execute launch.
-        offset_idxs: int64 (n_tracks, batch) device; out: float32 (n_tracks * total_per_track,) track-major."""
+        offset_idxs: int64 (n_tracks, batch) device; out: float32 (n_tracks * total_per_track,), track-major
+        (layout="tbp", the reference's flat buffer) or with every query's tracks adjacent (layout="btp",
+        gvl_dev_realign_tracks_btp: the order the reference's (b, t, p, ~l) offsets describe)."""
         batch, ploidy = geno_offset_idx.shape
         n_tracks = len(names)
         itv = (Intervals * n_tracks)(*[self.tracks[n][4] for n in names])
@@ -189,7 +191,8 @@ class Engine:
         par = (C.c_double * n_tracks)(*[float(p) for p in params])
         if out is None:
             out = torch.empty(n_tracks * total_per_track, dtype=torch.float32, device=self.device)
-        check(lib.gvl_dev_realign_tracks(
+        fn = lib.gvl_dev_realign_tracks_btp if layout == "btp" else lib.gvl_dev_realign_tracks
+        check(fn(
             self.ctx.handle, C.byref(self.tab), ptr(regions), ptr(shifts), ptr(geno_offset_idx), c_i64(batch),
             c_i64(ploidy), ptr(keep), ptr(keep_offsets), ptr(to_rc), c_i64(n_tracks), itv, ptr(offset_idxs),
             ptr(track_lengths), ptr(out_offsets), c_i64(int(total_per_track)), sid, par, c_u64(int(base_seed)),

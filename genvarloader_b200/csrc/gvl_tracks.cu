@@ -305,6 +305,8 @@ struct TrkExecParams {
     int64_t n_work, ploidy;
     int64_t grid_per_track;    // CTAs per track (upper bound on tiles)
     int64_t total_per_track;   // output values per track
+    int64_t n_tracks;
+    int32_t layout_btp;        // 0: out is track-major (t, b, p, ~l); 1: (b, t, p, ~l), every query's tracks adjacent
     const int64_t *offset_idxs;  // [n_tracks * n_queries]
     int64_t n_queries;
     const int64_t *query_seed;   // optional [n_queries]
@@ -482,7 +484,13 @@ __global__ void __launch_bounds__(TRK_THREADS, 1024 / TRK_THREADS) trk_exec_kern
     const int64_t track_n = rp.contig_len;
     const int64_t q_start = rp.q_start;
     float *__restrict__ out = P.out;
-    const int64_t row_base = track * P.total_per_track + rp.out_off;  // flat index of the row's first value
+    int64_t row_base = track * P.total_per_track + rp.out_off;  // flat index of the row's first value
+    if (P.layout_btp) {  // all tracks of a query are adjacent: block of the query, then track, then the row inside the block
+        const int64_t k0 = query * P.ploidy;
+        const int64_t blk0 = P.rows[k0].out_off;
+        const int64_t blk_len = P.rows[k0 + P.ploidy - 1].out_off + P.rows[k0 + P.ploidy - 1].length - blk0;
+        row_base = P.n_tracks * blk0 + track * blk_len + (rp.out_off - blk0);
+    }
 
     const int32_t *__restrict__ ra = P.rec.a + rp.rec_off;
     if (threadIdx.x < 32) {
@@ -863,7 +871,7 @@ using namespace gvl;
 
 static int launch_trk_exec(gvl_ctx *ctx, int64_t n_work, int64_t ploidy, int64_t n_queries, int64_t n_tracks,
                            const TrkDesc *host_desc, const int64_t *offset_idxs, int64_t total_per_track,
-                           const int64_t *query_seed, uint64_t base_seed, float *out, cudaStream_t st) {
+                           const int64_t *query_seed, uint64_t base_seed, float *out, int layout_btp, cudaStream_t st) {
     if (n_tracks > MAX_TRACKS) return fail(GVL_ERR_ARG, "at most %d tracks per call", MAX_TRACKS);
     static_assert(sizeof(TrkDesc) * MAX_TRACKS <= GVL_TRK_DESC_BYTES, "descriptor buffer too small");
     TrkDesc *d_desc = nullptr;
@@ -881,6 +889,8 @@ static int launch_trk_exec(gvl_ctx *ctx, int64_t n_work, int64_t ploidy, int64_t
     P.ploidy = ploidy;
     P.grid_per_track = total_per_track / TRK_SEG + n_work;
     P.total_per_track = total_per_track;
+    P.n_tracks = n_tracks;
+    P.layout_btp = layout_btp;
     P.offset_idxs = offset_idxs;
     P.n_queries = n_queries;
     P.query_seed = query_seed;
@@ -913,7 +923,8 @@ static int realign_impl(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_sv
                         const float *dense, const int64_t *dense_offsets,
                         const int32_t *track_lengths, const int64_t *out_offsets, int64_t total_per_track,
                         const int32_t *strategy_ids, const double *params, uint64_t base_seed,
-                        const int64_t *query_seed, int64_t max_records, float *out, gvl_stream stream) {
+                        const int64_t *query_seed, int64_t max_records, float *out, gvl_stream stream,
+                        int layout_btp = 0) {
     if (!ctx || !tab || !regions || !shifts || !(geno_offset_idx || svar2) || !(itv || dense) || !(offset_idxs || dense) ||
         !track_lengths || !out_offsets || !strategy_ids || !params)
         return fail(GVL_ERR_ARG, "gvl_dev_realign_tracks: NULL argument");
@@ -969,7 +980,7 @@ static int realign_impl(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_sv
             return fail(GVL_ERR_ARG, "Interpolate order must be 1, 2 or 3");
     }
     return launch_trk_exec(ctx, n_work, ploidy, batch, n_tracks, desc, offset_idxs, total_per_track, query_seed,
-                           base_seed, out, st);
+                           base_seed, out, layout_btp, st);
 }
 
 int gvl_dev_realign_tracks(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_t *regions,
@@ -983,6 +994,19 @@ int gvl_dev_realign_tracks(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int
     return realign_impl(ctx, tab, nullptr, regions, shifts, geno_offset_idx, batch, ploidy, keep, keep_offsets, to_rc, n_tracks,
                         itv, offset_idxs, nullptr, nullptr, track_lengths, out_offsets, total_per_track, strategy_ids,
                         params, base_seed, query_seed, max_records, out, stream);
+}
+
+int gvl_dev_realign_tracks_btp(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_t *regions,
+                               const int32_t *shifts, const int64_t *geno_offset_idx, int64_t batch, int64_t ploidy,
+                               const uint8_t *keep, const int64_t *keep_offsets, const uint8_t *to_rc,
+                               int64_t n_tracks, const gvl_intervals *itv, const int64_t *offset_idxs,
+                               const int32_t *track_lengths, const int64_t *out_offsets, int64_t total_per_track,
+                               const int32_t *strategy_ids, const double *params, uint64_t base_seed,
+                               const int64_t *query_seed, int64_t max_records, float *out, gvl_stream stream) {
+    if (!itv || !offset_idxs) return fail(GVL_ERR_ARG, "gvl_dev_realign_tracks_btp: NULL argument");
+    return realign_impl(ctx, tab, nullptr, regions, shifts, geno_offset_idx, batch, ploidy, keep, keep_offsets, to_rc, n_tracks,
+                        itv, offset_idxs, nullptr, nullptr, track_lengths, out_offsets, total_per_track, strategy_ids,
+                        params, base_seed, query_seed, max_records, out, stream, 1);
 }
 
 int gvl_dev_shift_and_realign_tracks(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_t *regions,
@@ -1043,7 +1067,7 @@ int gvl_dev_intervals_to_tracks(gvl_ctx *ctx, const gvl_intervals *itv, const in
     desc.dense_offsets = nullptr;
     desc.strategy = GVL_FILL_REPEAT_5P;
     desc.param = 0.0;
-    return launch_trk_exec(ctx, n_queries, 1, n_queries, 1, &desc, offset_idxs, total, nullptr, 0, out, st);
+    return launch_trk_exec(ctx, n_queries, 1, n_queries, 1, &desc, offset_idxs, total, nullptr, 0, out, 0, st);
 }
 
 static int run_prng(gvl_ctx *ctx, uint64_t a, uint64_t b, uint64_t c, uint64_t d, int which, uint64_t *out) {

@@ -206,6 +206,18 @@ int gvl_dev_realign_tracks(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int
                            const int32_t *strategy_ids, const double *params, uint64_t base_seed,
                            const int64_t *query_seed, int64_t max_records, float *out, gvl_stream stream);
 
+/* gvl_dev_realign_tracks writing the layout the reference's offsets describe, (b, t, p, ~l) (_reconstruct.py:292-300):
+ * all tracks of a query adjacent, so the flat buffer and lengths_to_offsets(repeat(out_lengths, "b p -> b t p")) agree
+ * for any number of tracks.  Row (q, t, h) starts at n_tracks * out_offsets[q*p] + t * (out_offsets[(q+1)*p] -
+ * out_offsets[q*p]) + out_offsets[q*p + h] - out_offsets[q*p].  Same arguments; out_offsets must be gap-free. */
+int gvl_dev_realign_tracks_btp(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_t *regions,
+                               const int32_t *shifts, const int64_t *geno_offset_idx, int64_t batch, int64_t ploidy,
+                               const uint8_t *keep, const int64_t *keep_offsets, const uint8_t *to_rc,
+                               int64_t n_tracks, const gvl_intervals *itv, const int64_t *offset_idxs,
+                               const int32_t *track_lengths, const int64_t *out_offsets, int64_t total_per_track,
+                               const int32_t *strategy_ids, const double *params, uint64_t base_seed,
+                               const int64_t *query_seed, int64_t max_records, float *out, gvl_stream stream);
+
 /* shift_and_realign_tracks_sparse on device (src/ffi/mod.rs:2439-2458): ONE track whose source is
  * a dense f32 window per query (`tracks` ragged by `track_offsets` i64[b+1]) instead of intervals.
  * track_lengths[q] = track_offsets[q+1]-track_offsets[q] as device i32[b]. */

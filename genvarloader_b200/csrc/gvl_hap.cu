@@ -852,12 +852,16 @@ static int hap_plan_impl(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_s
         const char *e = getenv("GVL_PLAN");
         return e && e[0] == 's';
     }();
+    static const int force_nt = [] {  // GVL_PLAN_NT=32|256|512: A/B runs of the plan kernel's width
+        const char *e = getenv("GVL_PLAN_NT");
+        return e ? atoi(e) : 0;
+    }();
     if (force_serial) {
         const unsigned grid = (unsigned)((n_work + PLAN_WARPS - 1) / PLAN_WARPS);
         hap_plan_serial_kernel<<<grid, PLAN_WARPS * 32, 0, st>>>(P);
-    } else if (max_records <= 40 * n_work) {  // short lists: one warp per row, 4 rows per CTA
+    } else if (force_nt == 32 || (!force_nt && max_records <= 40 * n_work)) {  // short lists: one warp per row, 4 rows per CTA
         hap_plan_par_kernel<32><<<(unsigned)((n_work + 3) / 4), 128, 0, st>>>(P);
-    } else if (max_records <= 384 * n_work) {  // one 256-thread CTA per row
+    } else if (force_nt == 256 || (!force_nt && max_records <= 384 * n_work)) {  // one 256-thread CTA per row
         hap_plan_par_kernel<256><<<(unsigned)n_work, 256, 0, st>>>(P);
     } else {  // long lists: 512 variants per sequential chunk
         hap_plan_par_kernel<512><<<(unsigned)n_work, 512, 0, st>>>(P);

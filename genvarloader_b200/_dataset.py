@@ -594,15 +594,9 @@ class Dataset:
                 d_off = torch.from_numpy(offs).to(dev)
                 starts = t_reg[:, 1].contiguous()
                 per = int(offs[-1])
-                flat = torch.empty(t * per, dtype=torch.float32, device=dev)
-                tr_idx = pk.get(i_tr)
-                for ti, n in enumerate(names):
-                    eng.intervals_to_tracks(n, tr_idx[ti].contiguous(), starts, d_off, per, flat[ti * per:(ti + 1) * per])
-                flat = flat.view(t, per)
-                if i_trc is not None:
-                    flat = _reverse_rows(flat, d_off, pk.get(i_trc).bool())
+                # all tracks in one launch, written in (b, t, ~l) order, negative-strand rows reversed
+                out = eng.paint_tracks(names, pk.get(i_tr), starts, d_off, per, pk.get(i_trc) if i_trc is not None else None)
                 lens_q = d_off[1:] - d_off[:-1]
-                out = _track_major_to_btp(flat.reshape(-1), d_off, t, b, 1, per) if t > 1 else flat.reshape(-1)
                 lens = lens_q.view(b, 1).expand(b, t).reshape(-1)
                 offsets = torch.zeros(b * t + 1, dtype=torch.int64, device=dev)
                 torch.cumsum(lens, 0, out=offsets[1:])
@@ -637,33 +631,6 @@ class Dataset:
         if squeeze:
             res = res.squeeze(0)  # (1 [p] l) -> ([p] l), _query.py:120-122
         return res
-
-
-def _reverse_rows(x: torch.Tensor, offsets: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
-    """Reverse the masked rows of a (t, flat) ragged buffer (un-realigned tracks on negative strands)."""
-    lens = offsets[1:] - offsets[:-1]
-    n = int(offsets[-1])
-    row = torch.repeat_interleave(torch.arange(lens.numel(), device=x.device), lens)
-    start = offsets[:-1][row]
-    col = torch.arange(n, device=x.device) - start
-    src = torch.where(mask[row], start + lens[row] - 1 - col, start + col)
-    return x[:, src]
-
-
-def _track_major_to_btp(flat: torch.Tensor, row_offsets: torch.Tensor, t: int, b: int, p: int, per: int) -> torch.Tensor:
-    """(t, rows...) track-major flat buffer -> (b, t, p, ~l) order.  rows = b*p, row_offsets (rows+1,)."""
-    dev = flat.device
-    lens = (row_offsets[1:] - row_offsets[:-1]).view(b, p)
-    # destination order: for q in b, for ti in t, for h in p
-    src_row = torch.arange(b * p, device=dev).view(b, 1, p).expand(b, t, p).reshape(-1)
-    src_trk = torch.arange(t, device=dev).view(1, t, 1).expand(b, t, p).reshape(-1)
-    l = lens.view(b, 1, p).expand(b, t, p).reshape(-1)
-    seg = torch.repeat_interleave(torch.arange(l.numel(), device=dev), l)
-    dst_off = torch.zeros(l.numel() + 1, dtype=torch.int64, device=dev)
-    torch.cumsum(l, 0, out=dst_off[1:])
-    within = torch.arange(int(dst_off[-1]), device=dev) - dst_off[:-1][seg]
-    src = src_trk[seg] * per + row_offsets[:-1][src_row[seg]] + within
-    return flat[src]
 
 
 class _Packer:

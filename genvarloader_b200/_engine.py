@@ -208,6 +208,17 @@ class Engine:
                                               c_i64(n_q), ptr(out_offsets), c_i64(int(total)), ptr(out), _stream()))
         return out
 
+    def paint_tracks(self, names, offset_idxs, starts, out_offsets, total_per_track: int, to_rc=None, out=None):
+        """gvl_dev_paint_tracks: stored intervals of all `names` painted in one launch, (b, t, ~l) order,
+        masked rows reversed.  offset_idxs: int64 (n_tracks, batch) device."""
+        n_tracks, n_q = len(names), int(starts.numel())
+        itv = (Intervals * n_tracks)(*[self.tracks[n][4] for n in names])
+        if out is None:
+            out = torch.empty(n_tracks * int(total_per_track), dtype=torch.float32, device=self.device)
+        check(lib.gvl_dev_paint_tracks(self.ctx.handle, c_i64(n_tracks), itv, ptr(offset_idxs), ptr(starts), c_i64(n_q),
+                                       ptr(out_offsets), c_i64(int(total_per_track)), ptr(to_rc), ptr(out), _stream()))
+        return out
+
     def check(self) -> None:
         """Synchronise and surface device-side status flags (workspace overflow)."""
         self.ctx.check(torch.cuda.current_stream().cuda_stream)

@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(TPLAN_WARPS * 32) trk_plan_kernel(TrkPlanParam
 
 // identity plan for intervals_to_tracks: one row per query, no records, source window = row
 __global__ void paint_plan_kernel(int64_t n, const int32_t *__restrict__ starts, const int64_t *__restrict__ out_offsets,
-                                  RowPlan *rows, int32_t *row_len) {
+                                  const uint8_t *__restrict__ to_rc, RowPlan *rows, int32_t *row_len) {
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
     int64_t length = imax64(out_offsets[q + 1] - out_offsets[q], 0);
@@ -240,7 +240,7 @@ __global__ void paint_plan_kernel(int64_t n, const int32_t *__restrict__ starts,
     rp.lead_pad = 0;
     rp.ref0 = 0;
     rp.n_rec = 0;
-    rp.rc = 0;
+    rp.rc = (to_rc && to_rc[q]) ? 1 : 0;  // negative-strand rows come out reversed (src/reverse.rs:25-38)
     rp.diff = 0;
     rp.q_start = starts[q];
     rows[q] = rp;
@@ -1055,8 +1055,8 @@ int gvl_dev_intervals_to_tracks(gvl_ctx *ctx, const gvl_intervals *itv, const in
     int rc;
     if ((rc = ensure_rows(ctx, ctx->trk, n_queries))) return rc;
     if ((rc = ensure_records(ctx, ctx->trk, 1))) return rc;
-    paint_plan_kernel<<<(unsigned)((n_queries + 255) / 256), 256, 0, st>>>(n_queries, starts, out_offsets, ctx->trk.rows,
-                                                                            ctx->trk.row_len);
+    paint_plan_kernel<<<(unsigned)((n_queries + 255) / 256), 256, 0, st>>>(n_queries, starts, out_offsets, nullptr,
+                                                                            ctx->trk.rows, ctx->trk.row_len);
     GVL_LAUNCH_CHECK();
     TrkDesc desc;
     desc.itv_starts = itv->itv_starts;
@@ -1068,6 +1068,36 @@ int gvl_dev_intervals_to_tracks(gvl_ctx *ctx, const gvl_intervals *itv, const in
     desc.strategy = GVL_FILL_REPEAT_5P;
     desc.param = 0.0;
     return launch_trk_exec(ctx, n_queries, 1, n_queries, 1, &desc, offset_idxs, total, nullptr, 0, out, 0, st);
+}
+
+int gvl_dev_paint_tracks(gvl_ctx *ctx, int64_t n_tracks, const gvl_intervals *itv, const int64_t *offset_idxs,
+                         const int32_t *starts, int64_t n_queries, const int64_t *out_offsets, int64_t total_per_track,
+                         const uint8_t *to_rc, float *out, gvl_stream stream) {
+    if (!ctx || !itv || !offset_idxs || !starts || !out_offsets)
+        return fail(GVL_ERR_ARG, "gvl_dev_paint_tracks: NULL argument");
+    if (n_tracks < 0 || n_tracks > MAX_TRACKS) return fail(GVL_ERR_ARG, "gvl_dev_paint_tracks: 0..%d tracks per call", MAX_TRACKS);
+    cudaStream_t st = (cudaStream_t)stream;
+    GVL_CUDA(cudaSetDevice(ctx->device));
+    if (n_queries == 0 || n_tracks == 0 || total_per_track == 0) return GVL_OK;
+    if (!out || ((uintptr_t)out & 15)) return fail(GVL_ERR_ARG, "gvl_dev_paint_tracks: out must be 16-byte aligned");
+    int rc;
+    if ((rc = ensure_rows(ctx, ctx->trk, n_queries))) return rc;
+    if ((rc = ensure_records(ctx, ctx->trk, 1))) return rc;
+    paint_plan_kernel<<<(unsigned)((n_queries + 255) / 256), 256, 0, st>>>(n_queries, starts, out_offsets, to_rc,
+                                                                            ctx->trk.rows, ctx->trk.row_len);
+    GVL_LAUNCH_CHECK();
+    TrkDesc desc[MAX_TRACKS];
+    for (int64_t t = 0; t < n_tracks; t++) {
+        desc[t].itv_starts = itv[t].itv_starts;
+        desc[t].itv_ends = itv[t].itv_ends;
+        desc[t].itv_values = itv[t].itv_values;
+        desc[t].itv_offsets = itv[t].itv_offsets;
+        desc[t].dense = nullptr;
+        desc[t].dense_offsets = nullptr;
+        desc[t].strategy = GVL_FILL_REPEAT_5P;
+        desc[t].param = 0.0;
+    }
+    return launch_trk_exec(ctx, n_queries, 1, n_queries, n_tracks, desc, offset_idxs, total_per_track, nullptr, 0, out, 1, st);
 }
 
 static int run_prng(gvl_ctx *ctx, uint64_t a, uint64_t b, uint64_t c, uint64_t d, int which, uint64_t *out) {

@@ -245,6 +245,15 @@ int gvl_dev_intervals_to_tracks(gvl_ctx *ctx, const gvl_intervals *itv, const in
                                 const int32_t *starts, int64_t n_queries, const int64_t *out_offsets,
                                 int64_t total, float *out, gvl_stream stream);
 
+/* intervals_to_tracks for ALL tracks of a batch in one launch (the un-realigned track read, Tracks._call_float32
+ * python/genvarloader/_dataset/_tracks.py:370-420): itv is a HOST array of n_tracks descriptors, offset_idxs device
+ * i64[n_tracks*n_queries], out_offsets device i64[n_queries+1] (per track, gap-free), to_rc optional device u8[n_queries]
+ * (masked rows are written reversed, src/reverse.rs:25-38).  out: device f32[n_tracks*total_per_track] in (b, t, ~l)
+ * order: row (q, t) starts at n_tracks*out_offsets[q] + t*(out_offsets[q+1]-out_offsets[q]). */
+int gvl_dev_paint_tracks(gvl_ctx *ctx, int64_t n_tracks, const gvl_intervals *itv, const int64_t *offset_idxs,
+                         const int32_t *starts, int64_t n_queries, const int64_t *out_offsets, int64_t total_per_track,
+                         const uint8_t *to_rc, float *out, gvl_stream stream);
+
 /* ---- device layer: the small entries either side of reconstruction ------------------ */
 /* choose_exonic_variants, src/ffi/mod.rs:229-238 -> src/genotypes/mod.rs:132-176: for every (query, hap) row,
  * keep_offsets[k+1] - keep_offsets[k] = size of its genotype slice and keep[keep_offsets[k] + i] = 1 iff variant i

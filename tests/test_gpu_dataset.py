@@ -163,11 +163,30 @@ def test_reference_sequences_and_unrealigned_tracks(env):
     reg_fixed[:, 2] = reg_fixed[:, 1] + L
     e_ref = O.get_reference(reg_fixed, oo, d.reference, d.ref_offsets, N, False, d.regions[r_idx, 3] == -1)
     assert (seq.cpu().numpy().ravel() == e_ref).all()
-    s, e, v, io = d.tracks["track1"]
-    e_trk = np.zeros(5 * L, np.float32)
-    O.intervals_to_tracks(ds_idx, regions[:, 1], s, e, v, io, e_trk, oo)
-    O.reverse_flat_rows_inplace(e_trk, oo, d.regions[r_idx, 3] == -1)
-    assert (trk.cpu().numpy().ravel().view(np.uint32) == e_trk.view(np.uint32)).all()
+    def paint(name, offs):
+        s, e, v, io = d.tracks[name]
+        buf = np.zeros(int(offs[-1]), np.float32)
+        O.intervals_to_tracks(ds_idx, regions[:, 1], s, e, v, io, buf, offs)
+        O.reverse_flat_rows_inplace(buf, offs, d.regions[r_idx, 3] == -1)
+        return buf
+
+    assert (trk.cpu().numpy().ravel().view(np.uint32) == paint("track1", oo).view(np.uint32)).all()
+    # two tracks in one launch, (b, t, l) order; then ragged rows (lengths = region lengths)
+    _, trk2 = ds.with_seqs("reference").with_len(L).with_tracks(["track1", "track0"])[:5, 2]
+    got2 = trk2.cpu().numpy()
+    assert got2.shape == (5, 2, L)
+    for ti, name in enumerate(("track1", "track0")):
+        assert (got2[:, ti].ravel().view(np.uint32) == paint(name, oo).view(np.uint32)).all()
+    _, trk3 = ds.with_seqs("reference").with_tracks(["track0", "track1"])[:5, 2]
+    lens = (regions[:, 2] - regions[:, 1]).astype(np.int64)
+    ro = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    data, offs = trk3.data.cpu().numpy(), trk3.offsets.cpu().numpy()
+    exp3 = [paint("track0", ro), paint("track1", ro)]
+    assert trk3.shape == (5, 2, None) and offs[-1] == 2 * ro[-1]
+    for q in range(5):
+        for ti in range(2):
+            seg = data[offs[q * 2 + ti]:offs[q * 2 + ti + 1]]
+            assert (seg.view(np.uint32) == exp3[ti][ro[q]:ro[q + 1]].view(np.uint32)).all()
 
 
 def test_exonic_filter_and_subset(env):

@@ -240,7 +240,10 @@ def run_b200(args):
     w, d = build_workload(args.workload, args.seed)  # every rank holds a full replica
     L, rows = w["window"], w["pairs"] * 2
     n_slots = args.slots
-    n_batches = max(args.ring, n_slots)
+    # ring length: as asked, but never longer than the timed run (a run shorter than the ring would fall back to one
+    # host launch per batch, which the host cannot issue as fast as the device finishes them)
+    ring = min(args.ring, max(n_slots, (args.steps // max(n_slots, 1)) * max(n_slots, 1)))
+    n_batches = max(ring, n_slots)
     batches = make_batches(d, w, n_batches, args.seed + 1, rank, world)  # this rank's shard of every global batch
     eng0 = Engine(dev, d.reference, d.ref_offsets, d.v_starts, d.ilens, d.alt_alleles, d.alt_offsets, d.geno_v_idxs,
                   d.geno_offsets)
@@ -557,15 +560,15 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=640)
-    ap.add_argument("--warmup", type=int, default=32)
+    ap.add_argument("--steps", type=int, default=1280)
+    ap.add_argument("--warmup", type=int, default=128)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--seed", type=int, default=2)
     ap.add_argument("--mode", default="onehot", choices=["onehot", "u8", "annotated"],
                     help="output of the execute kernel (the headline metric is one-hot)")
     ap.add_argument("--slots", type=int, default=8, help="batches in flight (streams)")
-    ap.add_argument("--ring", type=int, default=32, help="distinct batches / output buffers cycled through (one graph launch)")
+    ap.add_argument("--ring", type=int, default=128, help="distinct batches / output buffers cycled through (one graph launch)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()

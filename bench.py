@@ -458,6 +458,30 @@ def run_b200(args):
             b2.record(cap_stream)
         torch.cuda.synchronize()
         plan_ms = a2.elapsed_time(b2) / (reps * len(slots))
+        # (c) the plans of the whole ring issued like the product issues them (slot streams, 8 in flight): what the plan
+        #     costs the GPU per batch when its latency is overlapped
+        g_plan_par = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_plan_par, stream=cap_stream):
+            ev0 = torch.cuda.Event()
+            ev0.record(cap_stream)
+            for st in streams:
+                st.wait_event(ev0)
+            for s_ in slots:
+                with torch.cuda.stream(s_["stream"]):
+                    s_["eng"].plan(s_["regions"], s_["shifts"], s_["goi"], L, s_["nvar"], to_rc=s_["to_rc"], out_offsets=s_["out_offsets"])
+            for st in streams:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                cap_stream.wait_event(ev)
+        with torch.cuda.stream(cap_stream):
+            g_plan_par.replay()
+            a4, b4 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a4.record(cap_stream)
+            for _ in range(reps):
+                g_plan_par.replay()
+            b4.record(cap_stream)
+        torch.cuda.synchronize()
+        plan_ms_slots = a4.elapsed_time(b4) / (reps * len(slots))
         flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
         s = slots[0]
         durs = []
@@ -532,7 +556,7 @@ def run_b200(args):
             "output_GBps": value * {"onehot": 4, "u8": 1, "annotated": 9}[args.mode] / 1e9, "algorithmic_GBps": step_achieved * world,
             "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
-                         "alg_bytes_per_launch": ab, "launch_ms": exec_ms, "plan_kernel_ms": plan_ms,
+                         "alg_bytes_per_launch": ab, "launch_ms": exec_ms, "plan_kernel_ms": plan_ms, "plan_kernel_ms_slot_streams": plan_ms_slots,
                          "launch_ms_one_stream": exec_ms_one_stream,
                          "frac_one_stream": ab / (exec_ms_one_stream * 1e-3) / 1e9 / peak,
                          "launch_ms_isolated_after_l2_flush": exec_ms_isolated,

@@ -49,7 +49,7 @@ struct MergedLists {
 };
 
 // Device status words (ctx->dev_words).
-enum { W_CURSOR = 0, W_STATUS = 1, W_TOTAL = 2, W_TILES = 3, W_COUNT = 8 };
+enum { W_CURSOR = 0, W_STATUS = 1, W_TOTAL = 2, W_TILES = 3, W_MERGE_CURSOR = 4, W_DONE = 5, W_COUNT = 8 };
 
 constexpr int EXEC_THREADS = 128;
 constexpr int EXEC_MIN_CTAS = 12;        // resident CTAs per SM the execute kernels are compiled for (<= 40 registers)

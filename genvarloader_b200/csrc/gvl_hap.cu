@@ -252,6 +252,7 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) hap_plan_serial_kernel(HapPla
     const int64_t k = (int64_t)blockIdx.x * PLAN_WARPS + (threadIdx.x >> 5);
     if (k >= P.n_work) return;
     plan_row_serial(P, k);
+    if (lane_id() == 0) plan_row_done(P.words, P.n_work);
 }
 
 #include "gvl_plan_par.cuh"
@@ -789,6 +790,13 @@ static int64_t exec_capacity(gvl_ctx *ctx, int mode) {
 int gvl_svar2_merge_launch(gvl_ctx *ctx, gvl_workspace *ws, int64_t *words, const gvl_svar2_channels *ch, int64_t batch,
                            int64_t ploidy, int64_t max_merged, cudaStream_t st);
 
+// merge-only callers (no plan kernel follows that would do it): put the cursors back to zero, keep the status word
+__global__ void reset_cursors_kernel(int64_t *words) {
+    words[W_CURSOR] = 0;
+    words[W_MERGE_CURSOR] = 0;
+    words[W_DONE] = 0;
+}
+
 static int hap_plan_impl(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_svar2_channels *svar2,
                          const int32_t *regions, const int32_t *shifts, const int64_t *geno_offset_idx, int64_t batch,
                          int64_t ploidy, const uint8_t *keep, const int64_t *keep_offsets, const uint8_t *to_rc,
@@ -805,7 +813,7 @@ static int hap_plan_impl(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_s
     int rc;
     if ((rc = ensure_rows(ctx, ctx->hap, n_work))) return rc;
     if ((rc = ensure_records(ctx, ctx->hap, max_records + n_work))) return rc;
-    GVL_CUDA(cudaMemsetAsync(ctx->dev_words, 0, sizeof(int64_t) * W_COUNT, st));
+    // (no memset of the status words: every plan leaves its cursors at zero, see plan_row_done)
     ctx->n_work = n_work;
     ctx->fixed_len = output_length >= 0 ? output_length : -1;
     ctx->plan_out_offsets = out_offsets;
@@ -1084,8 +1092,7 @@ int gvl_dev_hap_diffs_svar2(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gv
     int rc;
     if ((rc = ensure_rows(ctx, ctx->trk, n_work))) return rc;
     if ((rc = ensure_merged(ctx, ctx->trk, max_merged))) return rc;
-    int64_t *words = ctx->dev_words + W_COUNT;
-    GVL_CUDA(cudaMemsetAsync(words, 0, sizeof(int64_t) * W_COUNT, st));
+    int64_t *words = ctx->dev_words + W_COUNT;  // (cursors are zero between calls, see plan_row_done)
     if ((rc = gvl_svar2_merge_launch(ctx, &ctx->trk, words, ch, batch, ploidy, max_merged, st))) return rc;
     DiffParams P;
     P.tab = *tab;
@@ -1101,6 +1108,8 @@ int gvl_dev_hap_diffs_svar2(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gv
     P.ploidy = ploidy;
     P.diffs = diffs;
     diffs_kernel<<<(unsigned)((n_work + PLAN_WARPS - 1) / PLAN_WARPS), PLAN_WARPS * 32, 0, st>>>(P);
+    GVL_LAUNCH_CHECK();
+    reset_cursors_kernel<<<1, 1, 0, st>>>(words);
     GVL_LAUNCH_CHECK();
     return GVL_OK;
 }

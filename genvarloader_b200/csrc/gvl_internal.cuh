@@ -27,6 +27,21 @@ int ensure_zeros(gvl_ctx *ctx, int64_t bytes, cudaStream_t st);
         gvl::count_launch();                                                                            \
     } while (0)
 
+// A plan kernel's rows take their record space from words[W_CURSOR] (and the svar2 merge from words[W_MERGE_CURSOR]).
+// The row that finishes LAST puts both cursors and the counter back to zero, so the words need no memset (or zeroing
+// kernel) before the next plan: one node less per batch on the stream, and safe under CUDA-graph replay because every
+// launch leaves the words as it found them.  Called by one thread per row, after the row's last global write.
+__device__ __forceinline__ void plan_row_done(int64_t *words, int64_t n_work) {
+    __threadfence();
+    const unsigned long long prev = atomicAdd((unsigned long long *)&words[W_DONE], 1ull);
+    if (prev + 1 == (unsigned long long)n_work) {
+        words[W_CURSOR] = 0;
+        words[W_MERGE_CURSOR] = 0;
+        words[W_DONE] = 0;
+        __threadfence();
+    }
+}
+
 // ---- where a row's variant list comes from -------------------------------------------
 struct RowVars {
     const int32_t *gv;    // SVAR1: variant indices of the row; merged lists: keys of the row

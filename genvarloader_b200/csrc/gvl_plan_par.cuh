@@ -388,6 +388,7 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) hap_plan_par_kernel(HapPl
     if (unsorted) {
         // exact replan in list order by one warp (rare; out of the writers' contract)
         if (NT == 32 || threadIdx.x < 32) plan_row_serial(P, k, rec_off);
+        if (t == 0) plan_row_done(P.words, P.n_work);
         return;
     }
 
@@ -418,5 +419,6 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) hap_plan_par_kernel(HapPl
         }
     }
     write_dir<NT>(P, k, rec_off, overflow ? 0 : n_emit, t);
+    if (t == 0) plan_row_done(P.words, P.n_work);
 }
 

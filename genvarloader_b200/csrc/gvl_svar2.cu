@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(MERGE_WARPS * 32) svar2_merge_kernel(MergePara
     const int32_t *__restrict__ dkey = P.ch.dense_key + ds;
 
     int64_t off = 0;
-    if (lane == 0) off = (int64_t)atomicAdd((unsigned long long *)&P.words[4], (unsigned long long)(n_vk + nd));
+    if (lane == 0) off = (int64_t)atomicAdd((unsigned long long *)&P.words[W_MERGE_CURSOR], (unsigned long long)(n_vk + nd));
     off = __shfl_sync(0xffffffffu, off, 0);
     const bool overflow = off + n_vk + nd > P.cap;
     if (overflow) {

@@ -222,6 +222,7 @@ __global__ void __launch_bounds__(TPLAN_WARPS * 32) trk_plan_kernel(TrkPlanParam
         rp.q_start = (int32_t)q_start;
         P.rows[k] = rp;
         P.row_len[k] = (int32_t)length;
+        plan_row_done(P.words, P.n_work);
     }
 }
 
@@ -936,8 +937,7 @@ static int realign_impl(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_sv
     int rc;
     if ((rc = ensure_rows(ctx, ctx->trk, n_work))) return rc;
     if ((rc = ensure_records(ctx, ctx->trk, max_records + n_work))) return rc;
-    int64_t *words = ctx->dev_words + W_COUNT;
-    GVL_CUDA(cudaMemsetAsync(words, 0, sizeof(int64_t) * W_COUNT, st));
+    int64_t *words = ctx->dev_words + W_COUNT;  // (left at zero by the previous plan, see plan_row_done)
     TrkPlanParams PP;
     PP.tab = *tab;
     PP.merged = MergedLists{nullptr, nullptr, nullptr, nullptr};

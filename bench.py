@@ -458,7 +458,7 @@ def run_b200(args):
             b2.record(cap_stream)
         torch.cuda.synchronize()
         plan_ms = a2.elapsed_time(b2) / (reps * len(slots))
-        # (c) the plans of the whole ring issued like the product issues them (slot streams, 8 in flight): what the plan
+        # (c) the plans of the whole ring issued like the product issues them (slot streams, --slots in flight): what the plan
         #     costs the GPU per batch when its latency is overlapped
         g_plan_par = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g_plan_par, stream=cap_stream):
@@ -591,7 +591,7 @@ def main():
     ap.add_argument("--seed", type=int, default=2)
     ap.add_argument("--mode", default="onehot", choices=["onehot", "u8", "annotated"],
                     help="output of the execute kernel (the headline metric is one-hot)")
-    ap.add_argument("--slots", type=int, default=8, help="batches in flight (streams)")
+    ap.add_argument("--slots", type=int, default=12, help="batches in flight (streams)")
     ap.add_argument("--ring", type=int, default=128, help="distinct batches / output buffers cycled through (one graph launch)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

@@ -566,7 +566,8 @@ def run_b200(args):
                          "frac_of_nominal_8TBps": achieved / 8000.0,
                          "frac_layout_bytes": (ab - (0.5 * rows * L if args.mode == "onehot" else 0.0)) / (exec_ms * 1e-3) / 1e9 / peak,
                          "bytes_note": "algorithmic bytes = SURVEY.md 8d (5 B/bp: 1 reference byte + 4 one-hot bytes); the packed reference "
-                                       "moves 0.5 B/bp, frac_layout_bytes counts 4.5 B/bp instead",
+                                       "moves 0.5 B/bp, frac_layout_bytes counts 4.5 B/bp instead; the peak is a read+write copy figure, so a nearly "
+                                       "write-only kernel can land a little above 1.0",
                          "whole_step_frac": step_achieved / peak},
             "cpu_baseline": {"value": cpu_v, "unit": "bp/s", "cores": threads, "kind": "port",
                              "sample": f"{cpu_n} batches ({cpu_s:.1f} s) of the same workload; C restatement of the reference's "

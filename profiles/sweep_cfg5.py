@@ -1,6 +1,8 @@
 """BASELINE.json configs[4] on one GPU: window length x variant density sweep of the one-hot haplotype path
-(plan + execute per step, 8 batches in flight, whole-ring CUDA graph, >= 1 GiB written per measurement).
+(plan + execute per step, SWEEP_SLOTS = 12 batches in flight, one CUDA graph per ring of SWEEP_RING = 64 batches,
+>= 1 GiB written per measurement).
 Prints a markdown table (profiles/r1_cfg5_sweep.md).  Multi-GPU: run under torchrun via bench.py --gpus N per cell."""
+import os
 import sys
 from pathlib import Path
 
@@ -23,12 +25,13 @@ for L in (16_384, 65_536, 131_072, 524_288):
         n_regions = 16
         d = synth.make_dataset(5, max(4 * L, 2_000_000) * 4, 8, n_regions, L, vkb, neg_strand_frac=0.5, straddle_ends=False)
         w = dict(window=L, pairs=pairs)
-        batches = bench.make_batches(d, w, 16, 6)
+        batches = bench.make_batches(d, w, int(os.environ.get("SWEEP_RING", 64)), 6)
         eng0 = Engine(dev, d.reference, d.ref_offsets, d.v_starts, d.ilens, d.alt_alleles, d.alt_offsets, d.geno_v_idxs, d.geno_offsets)
-        streams = [torch.cuda.Stream(dev) for _ in range(8)]
+        n_streams = int(os.environ.get("SWEEP_SLOTS", 12))
+        streams = [torch.cuda.Stream(dev) for _ in range(n_streams)]
         slots = []
         for i, b in enumerate(batches):
-            slots.append(dict(eng=eng0 if i == 0 else eng0.fork(), stream=streams[i % 8],
+            slots.append(dict(eng=eng0 if i == 0 else eng0.fork(), stream=streams[i % n_streams],
                               t={k: torch.from_numpy(b[k]).to(dev) for k in ("regions", "shifts", "goi", "to_rc")}, nvar=b["nvar"],
                               oo=torch.empty(rows + 1, dtype=torch.int64, device=dev),
                               out=torch.empty(rows * L * 4, dtype=torch.uint8, device=dev)))

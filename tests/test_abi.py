@@ -40,3 +40,18 @@ def test_only_tests_and_harness_touch_the_oracle():
     pkg = ROOT / "genvarloader_b200"
     for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")):
         assert "oracle" not in f.read_text().lower().replace("the oracle", ""), f
+
+
+def test_header_is_plain_c():
+    """include/gvl_b200.h is the boundary a cgo / Rust / C caller compiles against: it must be valid C99 on its own."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        import pytest
+
+        pytest.skip("gcc not found")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c",
+                        str(ROOT / "include" / "gvl_b200.h")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

@@ -148,6 +148,62 @@ static int64_t sum_variants(const int64_t *geno_offsets, int64_t n_geno, const i
     return s;
 }
 
+// ---- svar2 two-channel source: host arrays -> device channel struct (three entries share this) ----
+struct Svar2Host {
+    const int32_t *vk_pos, *vk_key;
+    const int64_t *vk_off;
+    const int32_t *dense_pos, *dense_key;
+    int64_t n_dense;
+    const int32_t *dense_range;
+    const uint8_t *dense_present;
+    const int64_t *dense_present_off;
+};
+
+struct Svar2Slots {
+    size_t vp, vk, vo, dr, dp, dpo;
+    int64_t max_merged;  // sum over rows of (var_key entries + dense window size): the merge workspace
+};
+
+// the shared dense channel is sample-scale: pinned copy when registered, per-call upload otherwise
+static int svar2_static(gvl_ctx *ctx, const Svar2Host &h, gvl_svar2_channels *ch) {
+    int rc;
+    const void *d;
+    if ((rc = static_dev(ctx, h.dense_pos, sizeof(int32_t) * h.n_dense, 16, &d))) return rc;
+    ch->dense_pos = (const int32_t *)d;
+    if ((rc = static_dev(ctx, h.dense_key, sizeof(int32_t) * h.n_dense, 17, &d))) return rc;
+    ch->dense_key = (const int32_t *)d;
+    return GVL_OK;
+}
+
+// the O(batch) channel arrays join the call's single staged upload (NULL arrays of empty channels get a placeholder)
+static Svar2Slots svar2_add(Packer &pk, const Svar2Host &h, int64_t batch, int64_t ploidy) {
+    const int64_t n_work = batch * ploidy;
+    const int64_t n_vk = h.vk_off[n_work];
+    const int64_t n_bits = h.dense_present_off[n_work];
+    Svar2Slots s;
+    s.max_merged = n_vk;
+    for (int64_t q = 0; q < batch; q++) {
+        const int64_t w = (int64_t)h.dense_range[2 * q + 1] - h.dense_range[2 * q];
+        if (w > 0) s.max_merged += ploidy * w;
+    }
+    s.vp = pk.add(h.vk_pos ? (const void *)h.vk_pos : (const void *)h.vk_off, sizeof(int32_t) * n_vk);
+    s.vk = pk.add(h.vk_key ? (const void *)h.vk_key : (const void *)h.vk_off, sizeof(int32_t) * n_vk);
+    s.vo = pk.add(h.vk_off, sizeof(int64_t) * (n_work + 1));
+    s.dr = pk.add(h.dense_range, sizeof(int32_t) * 2 * batch);
+    s.dp = pk.add(h.dense_present ? (const void *)h.dense_present : (const void *)h.vk_off, (n_bits + 7) / 8);
+    s.dpo = pk.add(h.dense_present_off, sizeof(int64_t) * (n_work + 1));
+    return s;
+}
+
+static void svar2_resolve(const Packer &pk, const Svar2Slots &s, gvl_svar2_channels *ch) {
+    ch->vk_pos = pk.ptr<int32_t>(s.vp);
+    ch->vk_key = pk.ptr<int32_t>(s.vk);
+    ch->vk_off = pk.ptr<int64_t>(s.vo);
+    ch->dense_range = pk.ptr<int32_t>(s.dr);
+    ch->dense_present = pk.ptr<uint8_t>(s.dp);
+    ch->dense_present_off = pk.ptr<int64_t>(s.dpo);
+}
+
 }  // namespace gvl
 
 using namespace gvl;
@@ -313,32 +369,17 @@ int gvl_reconstruct_haplotypes_from_svar2_begin(
     t.ref = (const uint8_t *)d;
     if ((rc = packed_ref(ctx, ref_, t.ref, ref_offsets[n_contigs], &t.ref_packed))) return rc;
     t.n_contigs = n_contigs;
+    const Svar2Host sh{vk_pos, vk_key, vk_off, dense_pos, dense_key, n_dense, dense_range, dense_present, dense_present_off};
     gvl_svar2_channels ch;
-    if ((rc = static_dev(ctx, dense_pos, sizeof(int32_t) * n_dense, 16, &d))) return rc;
-    ch.dense_pos = (const int32_t *)d;
-    if ((rc = static_dev(ctx, dense_key, sizeof(int32_t) * n_dense, 17, &d))) return rc;
-    ch.dense_key = (const int32_t *)d;
-    const int64_t n_vk = vk_off[n_work];
-    const int64_t n_bits = dense_present_off[n_work];
-    int64_t max_merged = n_vk;
-    for (int64_t q = 0; q < batch; q++) max_merged += ploidy * (int64_t)(dense_range[2 * q + 1] - dense_range[2 * q] > 0 ? dense_range[2 * q + 1] - dense_range[2 * q] : 0);
+    if ((rc = svar2_static(ctx, sh, &ch))) return rc;
     Packer pk;
     size_t i_reg = pk.add(regions, sizeof(int32_t) * 3 * batch);
     size_t i_sh = pk.add(shifts, sizeof(int32_t) * n_work);
     size_t i_rc = pk.add(to_rc, n_work);
-    size_t i_vp = pk.add(vk_pos ? (const void *)vk_pos : (const void *)vk_off, sizeof(int32_t) * n_vk);
-    size_t i_vkk = pk.add(vk_key ? (const void *)vk_key : (const void *)vk_off, sizeof(int32_t) * n_vk);
-    size_t i_vo = pk.add(vk_off, sizeof(int64_t) * (n_work + 1));
-    size_t i_dr = pk.add(dense_range, sizeof(int32_t) * 2 * batch);
-    size_t i_dp = pk.add(dense_present ? (const void *)dense_present : (const void *)vk_off, (n_bits + 7) / 8);
-    size_t i_do = pk.add(dense_present_off, sizeof(int64_t) * (n_work + 1));
+    const Svar2Slots ss = svar2_add(pk, sh, batch, ploidy);
+    const int64_t max_merged = ss.max_merged;
     if ((rc = pk.upload(ctx, 0))) return rc;
-    ch.vk_pos = pk.ptr<int32_t>(i_vp);
-    ch.vk_key = pk.ptr<int32_t>(i_vkk);
-    ch.vk_off = pk.ptr<int64_t>(i_vo);
-    ch.dense_range = pk.ptr<int32_t>(i_dr);
-    ch.dense_present = pk.ptr<uint8_t>(i_dp);
-    ch.dense_present_off = pk.ptr<int64_t>(i_do);
+    svar2_resolve(pk, ss, &ch);
     void *oo_dev;
     if ((rc = scratch(ctx, 1, sizeof(int64_t) * (n_work + 1), &oo_dev))) return rc;
     ctx->host_out_offsets_dev = (int64_t *)oo_dev;
@@ -372,33 +413,15 @@ int gvl_hap_diffs_svar2(gvl_ctx *ctx, const int32_t *regions, int64_t batch, int
     t.ilens = (const int32_t *)d;
     t.v_starts = t.ilens;  // unused by the merged-list source
     t.n_variants = n_keys;
+    const Svar2Host sh{vk_pos, vk_key, vk_off, dense_pos, dense_key, n_dense, dense_range, dense_present, dense_present_off};
     gvl_svar2_channels ch;
-    if ((rc = static_dev(ctx, dense_pos, sizeof(int32_t) * n_dense, 16, &d))) return rc;
-    ch.dense_pos = (const int32_t *)d;
-    if ((rc = static_dev(ctx, dense_key, sizeof(int32_t) * n_dense, 17, &d))) return rc;
-    ch.dense_key = (const int32_t *)d;
-    const int64_t n_vk = vk_off[n_work];
-    const int64_t n_bits = dense_present_off[n_work];
-    int64_t max_merged = n_vk;
-    for (int64_t q = 0; q < batch; q++) {
-        const int64_t w = (int64_t)dense_range[2 * q + 1] - dense_range[2 * q];
-        if (w > 0) max_merged += ploidy * w;
-    }
+    if ((rc = svar2_static(ctx, sh, &ch))) return rc;
     Packer pk;
     size_t i_reg = pk.add(regions, sizeof(int32_t) * 3 * batch);
-    size_t i_vp = pk.add(vk_pos ? (const void *)vk_pos : (const void *)vk_off, sizeof(int32_t) * n_vk);
-    size_t i_vkk = pk.add(vk_key ? (const void *)vk_key : (const void *)vk_off, sizeof(int32_t) * n_vk);
-    size_t i_vo = pk.add(vk_off, sizeof(int64_t) * (n_work + 1));
-    size_t i_dr = pk.add(dense_range, sizeof(int32_t) * 2 * batch);
-    size_t i_dp = pk.add(dense_present ? (const void *)dense_present : (const void *)vk_off, (n_bits + 7) / 8);
-    size_t i_do = pk.add(dense_present_off, sizeof(int64_t) * (n_work + 1));
+    const Svar2Slots ss = svar2_add(pk, sh, batch, ploidy);
+    const int64_t max_merged = ss.max_merged;
     if ((rc = pk.upload(ctx, 0))) return rc;
-    ch.vk_pos = pk.ptr<int32_t>(i_vp);
-    ch.vk_key = pk.ptr<int32_t>(i_vkk);
-    ch.vk_off = pk.ptr<int64_t>(i_vo);
-    ch.dense_range = pk.ptr<int32_t>(i_dr);
-    ch.dense_present = pk.ptr<uint8_t>(i_dp);
-    ch.dense_present_off = pk.ptr<int64_t>(i_do);
+    svar2_resolve(pk, ss, &ch);
     void *d_diffs;
     if ((rc = scratch(ctx, 1, sizeof(int32_t) * n_work, &d_diffs))) return rc;
     if ((rc = gvl_dev_hap_diffs_svar2(ctx, &t, &ch, pk.ptr<int32_t>(i_reg), batch, ploidy, max_merged, (int32_t *)d_diffs,
@@ -753,40 +776,24 @@ int gvl_shift_and_realign_tracks_from_svar2(
     t.ilens = (const int32_t *)d;
     t.v_starts = t.ilens;  // unused by the merged-list source
     t.n_variants = n_keys;
+    const Svar2Host sh{vk_pos, vk_key, vk_off, dense_pos, dense_key, n_dense, dense_range, dense_present, dense_present_off};
     gvl_svar2_channels ch;
-    if ((rc = static_dev(ctx, dense_pos, sizeof(int32_t) * n_dense, 16, &d))) return rc;
-    ch.dense_pos = (const int32_t *)d;
-    if ((rc = static_dev(ctx, dense_key, sizeof(int32_t) * n_dense, 17, &d))) return rc;
-    ch.dense_key = (const int32_t *)d;
+    if ((rc = svar2_static(ctx, sh, &ch))) return rc;
     const void *d_tracks;
     if ((rc = static_dev(ctx, tracks, sizeof(float) * track_offsets[batch], 18, &d_tracks))) return rc;
-    const int64_t n_vk = vk_off[n_work];
-    const int64_t n_bits = dense_present_off[n_work];
-    int64_t max_merged = n_vk;
-    for (int64_t q = 0; q < batch; q++)
-        max_merged += ploidy * (int64_t)(dense_range[2 * q + 1] - dense_range[2 * q] > 0 ? dense_range[2 * q + 1] - dense_range[2 * q] : 0);
     std::vector<int32_t> tl((size_t)batch);
     for (int64_t q = 0; q < batch; q++) tl[q] = (int32_t)(track_offsets[q + 1] - track_offsets[q]);
     Packer pk;
     size_t i_reg = pk.add(regions, sizeof(int32_t) * 3 * batch);
     size_t i_sh = pk.add(shifts, sizeof(int32_t) * n_work);
-    size_t i_vp = pk.add(vk_pos ? (const void *)vk_pos : (const void *)vk_off, sizeof(int32_t) * n_vk);
-    size_t i_vkk = pk.add(vk_key ? (const void *)vk_key : (const void *)vk_off, sizeof(int32_t) * n_vk);
-    size_t i_vo = pk.add(vk_off, sizeof(int64_t) * (n_work + 1));
-    size_t i_dr = pk.add(dense_range, sizeof(int32_t) * 2 * batch);
-    size_t i_dp = pk.add(dense_present ? (const void *)dense_present : (const void *)vk_off, (n_bits + 7) / 8);
-    size_t i_do = pk.add(dense_present_off, sizeof(int64_t) * (n_work + 1));
+    const Svar2Slots ss = svar2_add(pk, sh, batch, ploidy);
+    const int64_t max_merged = ss.max_merged;
     size_t i_to = pk.add(track_offsets, sizeof(int64_t) * (batch + 1));
     size_t i_tl = pk.add(tl.data(), sizeof(int32_t) * batch);
     size_t i_oo = pk.add(out_offsets, sizeof(int64_t) * (n_work + 1));
     size_t i_qs = pk.add(query_seed, sizeof(int64_t) * batch);
     if ((rc = pk.upload(ctx, 0))) return rc;
-    ch.vk_pos = pk.ptr<int32_t>(i_vp);
-    ch.vk_key = pk.ptr<int32_t>(i_vkk);
-    ch.vk_off = pk.ptr<int64_t>(i_vo);
-    ch.dense_range = pk.ptr<int32_t>(i_dr);
-    ch.dense_present = pk.ptr<uint8_t>(i_dp);
-    ch.dense_present_off = pk.ptr<int64_t>(i_do);
+    svar2_resolve(pk, ss, &ch);
     void *d_out;
     if ((rc = scratch(ctx, 2, total * 4, &d_out))) return rc;
     if ((rc = gvl_dev_shift_and_realign_tracks_svar2(

@@ -102,16 +102,17 @@ class Dataset:
 
     @classmethod
     def open(cls, path, reference=None, device="cuda", jitter: int = 0, rng=None, deterministic: bool = True,
-             rc_neg: bool = True) -> "Dataset":
+             rc_neg: bool = True, svar=None) -> "Dataset":
         """Open a dataset directory written by `gvl.write` (reference `Dataset.open`, _impl.py:164-226 ->
         `_open.py:62-345`; layout: docs/source/format.md:8-49) and upload it to `device`.
 
         `reference`: FASTA path (plain / gzip / bgzip) or a `genvarloader_b200.Reference`; required when the dataset
         has genotypes.  Regions are addressed in the ORDER OF THE INPUT BED, like the reference (`r_idx_map`).
-        Datasets that back-reference a `.svar` / `.svar2` store are refused (third-party store format)."""
+        Datasets linked to a `.svar` (SVAR1) store are followed (`svar=` overrides the stored path, like the reference);
+        `.svar2`-backed datasets are refused (third-party store format)."""
         from ._open import Reference, read_dataset_arrays
 
-        a = read_dataset_arrays(path, reference)
+        a = read_dataset_arrays(path, reference, svar)
         ref = a["reference"]
         n_regions, samples = len(a["full_regions"]), a["samples"]
         has_geno = "geno_v_idxs" in a

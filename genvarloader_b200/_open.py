@@ -10,8 +10,14 @@ Layout followed (reference `docs/source/format.md:8-49`):
     intervals/<track>/{starts,ends,values,offsets}.npy         raw int32 / int32 / float32 / int64, R*S + 1 offsets
     annot_intervals/<track>/...                                 same, R + 1 offsets (_tracks.py:327-339)
 
-Only numpy + pyarrow are used.  Datasets that back-reference a `.svar` / `.svar2` store (`svar_link`,
-`svar2_link`) need the third-party genoray store format and are refused with a clear error.
+    genotypes/svar_meta.json           present when the genotypes live in a linked `.svar` store (SVAR1): offsets.npy is
+                                       then a raw (2, R, S, P) starts/stops memmap into the store's variant_idxs.npy and
+                                       the variant table is the store's index.arrow (_haps.py:389-446)
+
+Only numpy + pyarrow are used.  `.svar` (SVAR1) links are followed: the store is resolved like the reference does
+(`svar=` override, stored relative path, stored absolute path, a unique sibling `*.svar`; legacy `link.svar` symlink) and its
+fingerprint is verified (_svar_link.py:24-103).  Datasets that back-reference a `.svar2` store need the third-party genoray
+store format and are refused with a clear error.
 """
 from __future__ import annotations
 
@@ -124,18 +130,61 @@ def _utf8_to_bytes_offsets(col) -> tuple:
     return np.ascontiguousarray(data[lo:hi]), offs - lo
 
 
-def read_dataset_arrays(path, reference=None) -> dict:
+def _resolve_svar(gvl_path: Path, link, override) -> Path:
+    """The `.svar` directory a dataset points at (reference `_resolve_svar`, _svar_link.py:24-61): override, stored
+    relative path, stored absolute path, a unique sibling `*.svar`; legacy datasets carry a `genotypes/link.svar` symlink."""
+    if override is not None:
+        p = Path(override)
+        if not p.is_dir():
+            raise FileNotFoundError(f"svar override path does not exist or is not a directory: {p}")
+        return p
+    if link:
+        rel = (gvl_path / link["relative_path"]).resolve()
+        if rel.is_dir():
+            return rel
+        absp = Path(link["absolute_path"])
+        if absp.is_dir():
+            return absp
+    else:
+        legacy = gvl_path / "genotypes" / "link.svar"
+        if legacy.exists():
+            return legacy.resolve()
+    siblings = sorted(gvl_path.parent.glob("*.svar"))
+    if len(siblings) == 1:
+        return siblings[0]
+    expected = Path(link["absolute_path"]).name if link else "<unknown>.svar"
+    raise FileNotFoundError(f"Could not locate svar '{expected}' for GVL dataset at {gvl_path}. Tried: stored relative path, "
+                            "stored absolute path, sibling *.svar. Pass `svar=` to `Dataset.open(...)` to override.")
+
+
+def _verify_svar_fingerprint(svar_path: Path, link, n_variants: int) -> None:
+    """reference `_verify_fingerprint`, _svar_link.py:64-103 (no-op for legacy datasets without a link record)."""
+    if not link:
+        return
+    vi = svar_path / "variant_idxs.npy"
+    if not vi.exists():
+        raise FileNotFoundError(f"Expected variant_idxs.npy at {vi}; resolved svar is malformed.")
+    exp = link.get("fingerprint") or {}
+    bad = []
+    if "n_variants" in exp and int(exp["n_variants"]) != n_variants:
+        bad.append(f"n_variants: expected {exp['n_variants']}, observed {n_variants}")
+    if "variant_idxs_bytes" in exp and int(exp["variant_idxs_bytes"]) != vi.stat().st_size:
+        bad.append(f"variant_idxs_bytes: expected {exp['variant_idxs_bytes']}, observed {vi.stat().st_size}")
+    if bad:
+        raise ValueError(f"svar fingerprint mismatch at {svar_path}: " + "; ".join(bad))
+
+
+def read_dataset_arrays(path, reference=None, svar=None) -> dict:
     """Parse the directory into the arrays `Dataset.from_arrays` takes (host side, numpy memmaps where possible)."""
     import pyarrow as pa
     import pyarrow.ipc as ipc
 
     path = Path(path)
     meta = json.loads((path / "metadata.json").read_text())
-    if meta.get("svar_link") or meta.get("svar2_link") or (path / "genotypes" / "svar_meta.json").exists() \
-            or (path / "genotypes" / "svar2_ranges").exists():
+    if meta.get("svar2_link") or (path / "genotypes" / "svar2_ranges").exists():
         raise NotImplementedError(
-            "this dataset back-references a .svar/.svar2 store; reading genoray stores is outside the current scope "
-            "(SURVEY.md 8f-2).  Datasets written from VCF/PGEN (genotypes/variants.arrow present) can be opened.")
+            "this dataset back-references a .svar2 store; reading genoray's svar2 store format is outside the current scope "
+            "(SURVEY.md 8f-2).  Datasets written from VCF/PGEN or linked to a .svar (SVAR1) store can be opened.")
     samples, contigs = list(meta["samples"]), list(meta["contigs"])
     ploidy = meta.get("ploidy")
     max_jitter = int(meta.get("max_jitter") or 0)
@@ -174,10 +223,16 @@ def read_dataset_arrays(path, reference=None) -> dict:
     if gdir.exists():
         if ploidy is None:
             raise ValueError("metadata.json has genotypes but no ploidy")
-        with pa.memory_map(str(gdir / "variants.arrow"), "r") as src:
+        svar_meta = gdir / "svar_meta.json"
+        linked = svar_meta.exists()
+        if linked:  # genotypes live in a .svar store: its variant table, its variant_idxs.npy, our (2, R, S, P) offsets
+            svar_path = _resolve_svar(path, meta.get("svar_link"), svar)
+            table_path, one_based = svar_path / "index.arrow", True  # (`_Variants.from_table` default, _haps.py:106-110)
+        else:
+            ver = _version_tuple(meta.get("version"))
+            table_path, one_based = gdir / "variants.arrow", ver is not None and ver >= (0, 18, 0)
+        with pa.memory_map(str(table_path), "r") as src:
             vt = ipc.open_file(src).read_all()
-        ver = _version_tuple(meta.get("version"))
-        one_based = ver is not None and ver >= (0, 18, 0)
         pos = _first_of_lists(vt.column("POS")).to_numpy(zero_copy_only=False).astype(np.int64) - int(one_based)
         alt, alt_off = _utf8_to_bytes_offsets(vt.column("ALT"))
         if "ILEN" in vt.column_names:
@@ -185,13 +240,23 @@ def read_dataset_arrays(path, reference=None) -> dict:
         else:  # ALT length - REF length (_haps.py:127-134)
             _, ref_off = _utf8_to_bytes_offsets(vt.column("REF"))
             ilen = (np.diff(alt_off) - np.diff(ref_off)).astype(np.int32)
-        out.update(v_starts=pos.astype(np.int32), ilens=ilen, alt_alleles=alt, alt_offsets=alt_off,
-                   geno_v_idxs=np.memmap(gdir / "variant_idxs.npy", dtype=np.int32, mode="r"),
-                   geno_offsets=np.memmap(gdir / "offsets.npy", dtype=np.int64, mode="r"))
         n_slots = n_regions * len(samples) * int(ploidy)
-        if out["geno_offsets"].size != n_slots + 1:
-            raise ValueError(f"genotypes/offsets.npy holds {out['geno_offsets'].size} offsets, expected {n_slots + 1} "
-                             f"(regions x samples x ploidy + 1)")
+        if linked:
+            _verify_svar_fingerprint(svar_path, meta.get("svar_link"), len(pos))
+            sm = json.loads(svar_meta.read_text())
+            shape = tuple(int(x) for x in sm["shape"])  # (2, r, s, p)
+            if len(shape) != 4 or shape[0] != 2 or int(np.prod(shape[1:])) != n_slots:
+                raise ValueError(f"genotypes/svar_meta.json: shape {shape} does not match (2, {n_regions}, {len(samples)}, {ploidy})")
+            go = np.memmap(gdir / "offsets.npy", shape=shape, dtype=np.dtype(sm["dtype"]), mode="r").reshape(2, -1)
+            out.update(v_starts=pos.astype(np.int32), ilens=ilen, alt_alleles=alt, alt_offsets=alt_off, geno_offsets=go,
+                       geno_v_idxs=np.memmap(svar_path / "variant_idxs.npy", dtype=np.int32, mode="r"), svar_path=svar_path)
+        else:
+            out.update(v_starts=pos.astype(np.int32), ilens=ilen, alt_alleles=alt, alt_offsets=alt_off,
+                       geno_v_idxs=np.memmap(gdir / "variant_idxs.npy", dtype=np.int32, mode="r"),
+                       geno_offsets=np.memmap(gdir / "offsets.npy", dtype=np.int64, mode="r"))
+            if out["geno_offsets"].size != n_slots + 1:
+                raise ValueError(f"genotypes/offsets.npy holds {out['geno_offsets'].size} offsets, expected {n_slots + 1} "
+                                 f"(regions x samples x ploidy + 1)")
     # ---- tracks ----
     for sub, kind, n_slots in (("intervals", "sample", n_regions * len(samples)), ("annot_intervals", "annot", n_regions)):
         tdir = path / sub

@@ -8,8 +8,29 @@ from pathlib import Path
 import numpy as np
 
 
+def write_svar_store(svar_dir, d, with_ilen=False):
+    """A `.svar` (SVAR1 / genoray SparseVar) directory as far as GenVarLoader reads it (_haps.py:428-446): the global
+    sparse genotype array `variant_idxs.npy` (raw int32) and the variant table `index.arrow` (1-based POS, REF, ALT as a
+    list column; ILEN optional -- without it the reader derives it from the allele lengths)."""
+    import pyarrow as pa
+    import pyarrow.ipc as ipc
+
+    svar_dir = Path(svar_dir)
+    svar_dir.mkdir(parents=True)
+    np.asarray(d.geno_v_idxs, np.int32).tofile(svar_dir / "variant_idxs.npy")
+    alts = [d.alt_alleles[d.alt_offsets[i]: d.alt_offsets[i + 1]].tobytes().decode() for i in range(d.v_starts.size)]
+    refs = ["N" * (len(a) - int(il)) for a, il in zip(alts, d.ilens)]  # len(ALT) - len(REF) = ILEN
+    cols = {"POS": d.v_starts.astype(np.int64) + 1, "REF": refs, "ALT": pa.array([[a] for a in alts], pa.list_(pa.utf8()))}
+    if with_ilen:
+        cols["ILEN"] = pa.array([[int(x)] for x in d.ilens], pa.list_(pa.int32()))
+    vt = pa.table(cols)
+    with pa.OSFile(str(svar_dir / "index.arrow"), "wb") as f, ipc.new_file(f, vt.schema) as w:
+        w.write_table(vt)
+    return dict(n_variants=int(d.v_starts.size), variant_idxs_bytes=int((svar_dir / "variant_idxs.npy").stat().st_size))
+
+
 def write_gvl_dataset(path, d, contigs, samples, input_order, version="0.19.0", strand_as_str=True, pos_one_based=True,
-                      annot_tracks=()):
+                      annot_tracks=(), svar_dir=None, svar_fingerprint=None):
     import pyarrow as pa
     import pyarrow.ipc as ipc
 
@@ -28,19 +49,32 @@ def write_gvl_dataset(path, d, contigs, samples, input_order, version="0.19.0", 
                     "r_idx_map": order.astype(np.int64)})
     with pa.OSFile(str(path / "input_regions.arrow"), "wb") as f, ipc.new_file(f, bed.schema) as w:
         w.write_table(bed)
-    alts = [d.alt_alleles[d.alt_offsets[i]: d.alt_offsets[i + 1]].tobytes().decode() for i in range(d.v_starts.size)]
-    vt = pa.table({"POS": (d.v_starts.astype(np.int64) + int(pos_one_based)), "ILEN": d.ilens.astype(np.int32), "ALT": alts,
-                   "AF": np.linspace(0, 1, d.v_starts.size)})
-    with pa.OSFile(str(path / "genotypes" / "variants.arrow"), "wb") as f, ipc.new_file(f, vt.schema) as w:
-        w.write_table(vt)
-    # sparse genotypes: contiguous CSR over (region, sample, ploid)
     go = np.asarray(d.geno_offsets)
-    starts, stops = go[0], go[1]
-    lens = np.maximum(stops - starts, 0)
-    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
-    v_idx = np.concatenate([d.geno_v_idxs[s:e] for s, e in zip(starts, stops)] + [np.zeros(0, np.int32)]).astype(np.int32)
-    v_idx.tofile(path / "genotypes" / "variant_idxs.npy")
-    offs.tofile(path / "genotypes" / "offsets.npy")
+    if svar_dir is not None:
+        # genotypes stay in the linked .svar store (_write.py: svar-backed datasets): only the (2, r, s, p) starts/stops
+        # into its variant_idxs.npy are stored here, plus the link record in metadata.json
+        import os
+
+        n_samples = len(samples)
+        (path / "genotypes" / "svar_meta.json").write_text(json.dumps(
+            {"shape": [2, n_regions, n_samples, d.ploidy], "dtype": "int64"}))
+        np.ascontiguousarray(go, np.int64).tofile(path / "genotypes" / "offsets.npy")
+        meta["svar_link"] = dict(relative_path=os.path.relpath(svar_dir, start=path).replace(os.sep, "/"),
+                                 absolute_path=str(Path(svar_dir).resolve()), fingerprint=svar_fingerprint)
+        (path / "metadata.json").write_text(json.dumps(meta))
+    else:
+        alts = [d.alt_alleles[d.alt_offsets[i]: d.alt_offsets[i + 1]].tobytes().decode() for i in range(d.v_starts.size)]
+        vt = pa.table({"POS": (d.v_starts.astype(np.int64) + int(pos_one_based)), "ILEN": d.ilens.astype(np.int32), "ALT": alts,
+                       "AF": np.linspace(0, 1, d.v_starts.size)})
+        with pa.OSFile(str(path / "genotypes" / "variants.arrow"), "wb") as f, ipc.new_file(f, vt.schema) as w:
+            w.write_table(vt)
+        # sparse genotypes: contiguous CSR over (region, sample, ploid)
+        starts, stops = go[0], go[1]
+        lens = np.maximum(stops - starts, 0)
+        offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        v_idx = np.concatenate([d.geno_v_idxs[s:e] for s, e in zip(starts, stops)] + [np.zeros(0, np.int32)]).astype(np.int32)
+        v_idx.tofile(path / "genotypes" / "variant_idxs.npy")
+        offs.tofile(path / "genotypes" / "offsets.npy")
     for name, (s, e, v, o) in d.tracks.items():
         sub = "annot_intervals" if name in annot_tracks else "intervals"
         tdir = path / sub / name

@@ -106,3 +106,31 @@ def test_spliced_haplotypes_are_concatenated_elements(cuda_device, tmp_path):
     assert set(names) == {"tA", "tB", "tC", "x"}
     got = spd[names.index("tC"), 1]
     assert (got.data.cpu().numpy() == sp[2, 1].data.cpu().numpy()).all() and (got.offsets.cpu().numpy() == sp[2, 1].offsets.cpu().numpy()).all()
+
+
+def test_open_svar_linked_dataset(cuda_device, tmp_path):
+    """A dataset whose genotypes live in a linked .svar store (strided (2, r, s, p) offsets into the store's sparse genotype
+    array) gives the same batches as the self-contained dataset."""
+    from genvarloader_b200 import Dataset, synth
+    from tests._gvl_disk import write_svar_store
+
+    d = synth.make_dataset(29, 150_000, 3, 10, 2000 + 2 * 8, 6.0, max_jitter=8, neg_strand_frac=0.5, straddle_ends=False,
+                           n_tracks=1, max_indel=9)
+    order = np.random.default_rng(2).permutation(d.n_regions)
+    fp = write_svar_store(tmp_path / "cohort.svar", d, with_ilen=True)
+    write_gvl_dataset(tmp_path / "linked", d, ["chr1"], ["a", "b", "c"], order, svar_dir=tmp_path / "cohort.svar", svar_fingerprint=fp)
+    write_gvl_dataset(tmp_path / "plain", d, ["chr1"], ["a", "b", "c"], order)
+    write_fasta(tmp_path / "ref.fa", d.reference, d.ref_offsets, ["chr1"])
+    a = Dataset.open(tmp_path / "plain", tmp_path / "ref.fa", device=cuda_device)
+    b = Dataset.open(tmp_path / "linked", tmp_path / "ref.fa", device=cuda_device, svar=tmp_path / "cohort.svar")
+    L = 1800
+    for seqs in ("haplotypes", "annotated"):
+        x, y = a.with_len(L).with_seqs(seqs).with_tracks(False)[:, :], b.with_len(L).with_seqs(seqs).with_tracks(False)[:, :]
+        if seqs == "annotated":
+            # variant indices are GLOBAL table indices in both datasets (same table, same order)
+            assert (x.haps == y.haps).all() and (x.var_idxs == y.var_idxs).all() and (x.ref_coords == y.ref_coords).all()
+        else:
+            assert (x == y).all()
+    hx, tx = a.with_seqs("haplotypes")[[1, 4], [0, 2]]
+    hy, ty = b.with_seqs("haplotypes")[[1, 4], [0, 2]]
+    assert (hx.data == hy.data).all() and (hx.offsets == hy.offsets).all() and (tx.data == ty.data).all()

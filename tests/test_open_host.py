@@ -52,12 +52,52 @@ def test_version_and_errors(disk, tmp_path):
     a = read_dataset_arrays(old)
     assert (a["v_starts"] == d.v_starts).all() and a["reference"] is None and (a["full_regions"] == d.regions).all()
     meta = json.loads((old / "metadata.json").read_text())
-    meta["svar_link"] = {"relative_path": "../x.svar", "absolute_path": "/x.svar", "fingerprint": {}}
+    meta["svar2_link"] = {"relative_path": "../x.svar2", "absolute_path": "/x.svar2", "fingerprint": {}}
     (old / "metadata.json").write_text(json.dumps(meta))
-    with pytest.raises(NotImplementedError, match="svar"):
+    with pytest.raises(NotImplementedError, match="svar2"):
         read_dataset_arrays(old)
     with pytest.raises(ValueError, match="not present in reference"):
         read_dataset_arrays(root / "ds", root / "ref.fa").get  # ok
         from genvarloader_b200._open import Reference
 
         Reference.from_path(root / "ref.fa", ["chr7"])
+
+
+def test_svar_linked_dataset(disk, tmp_path):
+    """Genotypes in a linked .svar store (reference _haps.py:389-446, _svar_link.py): resolution order, fingerprint,
+    ILEN derived from the allele lengths, (2, r, s, p) offsets into the store's variant_idxs.npy."""
+    import json
+    import shutil
+
+    from genvarloader_b200._open import read_dataset_arrays
+    from tests._gvl_disk import write_svar_store
+
+    d, root, order = disk
+    fp = write_svar_store(tmp_path / "cohort.svar", d)
+    write_gvl_dataset(tmp_path / "ds", d, ["chr1"], ["s2", "s0", "s1"], order, svar_dir=tmp_path / "cohort.svar", svar_fingerprint=fp)
+    a = read_dataset_arrays(tmp_path / "ds")
+    assert (a["v_starts"] == d.v_starts).all() and (a["ilens"] == d.ilens).all()
+    assert (a["alt_alleles"] == d.alt_alleles).all() and (a["alt_offsets"] == d.alt_offsets).all()
+    go = np.asarray(d.geno_offsets)
+    assert a["geno_offsets"].shape == go.shape and (np.asarray(a["geno_offsets"]) == go).all()
+    assert (np.asarray(a["geno_v_idxs"]) == d.geno_v_idxs).all() and a["svar_path"] == (tmp_path / "cohort.svar").resolve()
+    # moved store: the stored paths dangle, a unique sibling *.svar is found; two siblings are ambiguous; svar= overrides
+    moved = tmp_path / "moved"
+    moved.mkdir()
+    shutil.move(str(tmp_path / "ds"), str(moved / "ds"))
+    shutil.move(str(tmp_path / "cohort.svar"), str(moved / "renamed.svar"))
+    meta = json.loads((moved / "ds" / "metadata.json").read_text())
+    meta["svar_link"]["absolute_path"] = str(tmp_path / "gone.svar")
+    (moved / "ds" / "metadata.json").write_text(json.dumps(meta))
+    assert read_dataset_arrays(moved / "ds")["svar_path"] == moved / "renamed.svar"
+    (moved / "other.svar").mkdir()
+    with pytest.raises(FileNotFoundError, match="gone.svar"):
+        read_dataset_arrays(moved / "ds")
+    assert (read_dataset_arrays(moved / "ds", svar=moved / "renamed.svar")["ilens"] == d.ilens).all()
+    with pytest.raises(FileNotFoundError, match="override"):
+        read_dataset_arrays(moved / "ds", svar=moved / "nope.svar")
+    # fingerprint mismatch
+    meta["svar_link"]["fingerprint"]["n_variants"] += 1
+    (moved / "ds" / "metadata.json").write_text(json.dumps(meta))
+    with pytest.raises(ValueError, match="fingerprint mismatch"):
+        read_dataset_arrays(moved / "ds", svar=moved / "renamed.svar")

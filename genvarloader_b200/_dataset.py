@@ -72,6 +72,7 @@ class Dataset:
     splice_rows: object = None                        # spliced: tuple of int64 arrays of STORAGE region indices, one per splice row
     splice_names: object = None                       # spliced: names of the splice rows (or None)
     bed_columns: object = None                        # opened datasets: extra input-BED columns (name -> array, input order)
+    _cache: dict = field(default_factory=dict, compare=False, repr=False)  # per-state lazies (fixed-length pipeline)
 
     # ------------------------------------------------------------------ construction
     @classmethod
@@ -205,11 +206,14 @@ class Dataset:
             raise ValueError(f"Output length must be 'ragged', 'variable' or a positive integer, got {self.output_length!r}")
         if self.encoding != "bytes" and self.sequence_type not in ("haplotypes", "reference"):
             raise ValueError("one-hot encoding applies to 'haplotypes' / 'reference' sequences only")
-        if self.encoding == "onehot_cf" and not isinstance(self.output_length, (int, np.integer)):
-            raise ValueError("channels-first one-hot needs a fixed output length")
+        if self.encoding == "onehot_cf":
+            if not isinstance(self.output_length, (int, np.integer)):
+                raise ValueError("channels-first one-hot needs a fixed output length")
+            if int(self.output_length) % 4:
+                raise ValueError("channels-first one-hot needs an output length that is a multiple of 4")
 
     def _evolve(self, **kw) -> "Dataset":
-        ds = replace(self, **kw)
+        ds = replace(self, **kw, _cache={})
         ds._check_valid_state()
         return ds
 
@@ -282,6 +286,16 @@ class Dataset:
 
     def with_insertion_fill(self, strategy) -> "Dataset":
         """Reference: `Dataset.with_insertion_fill`, _impl.py:841-878 (one strategy for all tracks or a dict)."""
+        if not self.track_kinds:
+            raise ValueError("Dataset has no tracks; cannot configure insertion fill.")
+        if self.sequence_type not in ("haplotypes", "annotated"):
+            raise ValueError("with_insertion_fill is only meaningful for datasets with both haplotypes and tracks "
+                             "(use with_seqs to activate haplotypes first).")
+        if not self.active_tracks:
+            raise ValueError("with_insertion_fill is only meaningful when tracks are active (use with_tracks to activate tracks first).")
+        if not self.realign_tracks:
+            raise ValueError("with_insertion_fill has no effect when realign_tracks=False (insertion fill only applies during "
+                             "track re-alignment). Set with_settings(realign_tracks=True) first, or drop the call.")
         if isinstance(strategy, InsertionFill):
             fills = {name: strategy for name in self.track_kinds}
         else:
@@ -470,13 +484,30 @@ class Dataset:
     # ------------------------------------------------------------------ iteration (reference: to_dataloader, _impl.py:1963-2072)
     def to_dataloader(self, batch_size: int = 1, shuffle: bool = False, sampler=None, num_workers: int = 0, collate_fn=None,
                       pin_memory: bool = False, drop_last: bool = False, generator=None, *, return_indices: bool = False,
-                      transform=None, **ignored) -> "BatchLoader":
+                      transform=None, mode=None, copy: bool = True, ring: int = 0, **ignored):
         """Batches over the flat `(region, sample)` index like the reference's DataLoader (which wraps its sampler in a
-        `BatchSampler` so that the dataset is indexed with lists of indices).  The batches are born on the GPU, so
-        there are no workers, no pinning and no collation: `num_workers`, `pin_memory`, `collate_fn` and the
-        buffered modes are accepted and ignored.  `generator`: seed / numpy Generator / torch.Generator for `shuffle`."""
+        `BatchSampler` so that the dataset is indexed with lists of indices, _torch.py:160-228).  The batches are born on
+        the GPU, so there are no workers, no pinning and no collation: `num_workers`, `pin_memory`, `collate_fn`,
+        `buffer_bytes` ... are accepted and ignored.  `generator`: seed / numpy Generator / torch.Generator for `shuffle`.
+
+        `mode=None`: one synchronous `ds[r, s]` per batch (any output kind).
+        `mode="buffered"` / `"double_buffered"` (reference: `_impl.py:2029-2046`, prefetching producers): the GPU-side
+        analogue for fixed-length output -- the loader reads `ring` batches ahead with ONE device call per ring (0: sized
+        for ~256 MiB of output), two ring halves produced alternately while the other is consumed (`_pipeline.py`).  `copy=False` hands out zero-copy
+        views into the ring that stay valid until `ring` more batches have been drawn (the reference's `copy=False`
+        contract: "only valid until the next batch is yielded"); `copy=True` (default) clones every batch.
+        Datasets the pipeline cannot serve (ragged / variable lengths, random shifts, splicing, var_filter) fall back to
+        `mode=None`."""
         if sampler is not None and shuffle:
             raise ValueError("sampler option is mutually exclusive with shuffle")
+        if mode not in (None, "buffered", "double_buffered"):
+            raise ValueError(f"Unknown dataloader mode {mode!r}")
+        if mode is not None:
+            from . import _pipeline
+
+            if _pipeline.supports(self) is None:
+                return _pipeline.PipelinedLoader(self, int(batch_size), bool(shuffle), sampler, bool(drop_last), generator,
+                                                 bool(return_indices), transform, bool(copy), ring)
         return BatchLoader(self, int(batch_size), bool(shuffle), sampler, bool(drop_last), generator, bool(return_indices), transform)
 
     # ------------------------------------------------------------------ the hot path
@@ -487,6 +518,14 @@ class Dataset:
         if self.splice_rows is not None:
             return self._getitem_spliced(idx)
         ds_idx, squeeze, out_reshape = self._parse_idx(idx)
+        pipe = self._eager_pipeline(len(ds_idx))
+        if pipe is not None:
+            # fixed-length fast path: the O(batch) prep runs on the device (gvl_dev_batch_prep), one small H2D copy per call
+            jit = self.rng.integers(-self.jitter, self.jitter + 1, size=len(ds_idx), dtype=np.int32) if self.jitter else None
+            out = pipe.run_eager(ds_idx, jit)
+            out = out if isinstance(out, tuple) else (out,)
+            out = tuple(self._shape_output(o, out_reshape, squeeze) for o in out)
+            return out[0] if len(out) == 1 else out
         S = len(self.sample_names)
         r_idx, s_idx = ds_idx // S, ds_idx % S
 
@@ -500,6 +539,23 @@ class Dataset:
         out = self._reconstruct(ds_idx, r_idx, s_idx, regions)
         out = tuple(self._shape_output(o, out_reshape, squeeze) for o in out)
         return out[0] if len(out) == 1 else out
+
+    def _eager_pipeline(self, n: int):
+        """The fixed-length pipeline serving `__getitem__` (None when this dataset state needs the general path)."""
+        c = self._cache
+        if "fast" not in c:
+            from . import _pipeline
+
+            c["fast"] = _pipeline.supports(self) is None
+        if not c["fast"] or n == 0:
+            return None
+        pipe = c.get("pipe")
+        if pipe is None or pipe.b < n:
+            from . import _pipeline
+
+            cap = max(n, 2 * pipe.b if pipe is not None else 0)
+            pipe = c["pipe"] = _pipeline.FixedPipeline(self, cap, ring=0)
+        return pipe
 
     # ---- reconstructors: Haps / HapsTracks / Tracks (_haps.py:578-870, _reconstruct.py:132-307, _tracks.py:370-420)
     def _reconstruct(self, ds_idx, r_idx, s_idx, regions):
@@ -611,8 +667,8 @@ class Dataset:
 
     # ---- output shaping, _query.py:94-127 ----
     def _shape_output(self, o, out_reshape, squeeze):
-        if isinstance(o, torch.Tensor) or self.output_format == "flat" or self.output_length == "ragged":
-            res = o  # channels-first one-hot is already dense; "flat"/"ragged" hand the flat triple back
+        if isinstance(o, (torch.Tensor, AnnotatedHaps)) or self.output_format == "flat" or self.output_length == "ragged":
+            res = o  # already dense (fixed-length pipeline, channels-first one-hot); "flat"/"ragged" hand the flat triple back
         elif self.output_length == "variable":
             if isinstance(o, RaggedAnnotatedHaps):
                 res = o.to_padded()
@@ -695,8 +751,14 @@ class BatchLoader:
             idx = order[lo: lo + self.batch_size]
             if len(idx) < self.batch_size and self.drop_last:
                 return
-            r, s_ = idx // n_s, idx % n_s
+            r, s_ = idx // n_s, idx % n_s  # np.unravel_index(idx, dataset.shape), _torch.py:293
             batch = self.ds[r, s_]
-            if self.return_indices:  # indices into the NON-subset dataset, like the reference
-                batch = (*batch, self.ds._r_idx[r], self.ds._s_idx[s_]) if isinstance(batch, tuple) else (batch, self.ds._r_idx[r], self.ds._s_idx[s_])
-            yield self.transform(batch) if self.transform is not None else batch
+            if not isinstance(batch, tuple):
+                batch = (batch,)
+            if self.return_indices:  # the (region, sample) indices the dataset was indexed with, _torch.py:299-300
+                batch = (*batch, r, s_)
+            if self.transform is not None:
+                batch = self.transform(*batch)  # _torch.py:302-303
+            elif len(batch) == 1:
+                batch = batch[0]
+            yield batch

@@ -12,8 +12,8 @@ import numpy as np
 import torch
 
 from . import _ffi
-from ._ffi import (MODE_ANNOTATED, MODE_ONEHOT, MODE_ONEHOT_CF, MODE_U8, Intervals, SparseTables, c_i32, c_i64, c_u8,
-                   c_u64, c_vp, check, lib, ptr)
+from ._ffi import (MODE_ANNOTATED, MODE_ONEHOT, MODE_ONEHOT_CF, MODE_U8, DatasetView, Intervals, SparseTables, c_i32,
+                   c_i64, c_u8, c_u64, c_vp, check, lib, ptr)
 
 MODES = {"haplotypes": MODE_U8, "u8": MODE_U8, "onehot": MODE_ONEHOT, "onehot_cf": MODE_ONEHOT_CF,
          "annotated": MODE_ANNOTATED}
@@ -64,6 +64,9 @@ class Engine:
         go = np.concatenate([np.ascontiguousarray(go, np.int64), np.zeros((2, 1), np.int64)], 1)
         self.empty_slot = go.shape[1] - 1
         self.geno_offsets_host = np.ascontiguousarray(go, np.int64)  # O(batch) capacity sums stay on the host
+        # longest variant list of any (region, sample, ploid) slot: workspace capacity of graph-replayed batches
+        self.max_slot_len = int(np.maximum(go[1] - go[0], 0).max()) if go.shape[1] else 0
+        self._views: dict = {}
         with torch.cuda.device(self.device):
             self.ref = _dev(reference, np.uint8, self.device, pad=32)
             self.ref_offsets = _dev(ref_offsets, np.int64, self.device)
@@ -104,6 +107,27 @@ class Engine:
         e.ctx = _ffi.Ctx(self.device.index)
         e._n_work, e._fixed = 0, -1
         return e
+
+    # ------------------------------------------------------------------ device-side batch preparation
+    def dataset_view(self, full_regions: np.ndarray, n_samples: int, ploidy: int, rc_neg: bool) -> DatasetView:
+        """gvl_dataset_view over a device copy of `full_regions` (uploaded once per distinct table)."""
+        key = (full_regions.ctypes.data, full_regions.shape)
+        ent = self._views.get(key)
+        if ent is None:
+            ent = self._views[key] = (_dev(np.ascontiguousarray(full_regions, np.int32).reshape(-1, 4), np.int32, self.device, pad=4),
+                                      full_regions)
+        return DatasetView(ptr(ent[0]), int(full_regions.shape[0]), int(n_samples), int(ploidy), 1 if rc_neg else 0)
+
+    def batch_prep(self, view: DatasetView, ds_idx, jitter, batch: int, ref_slot: int, n_tracks: int, annot_mask: int, args,
+                   sub_batch: int = 0):
+        """gvl_dev_batch_prep: regions / genotype slots / strand masks / interval slots / fill seed from flat indices."""
+        check(lib.gvl_dev_batch_prep(self.ctx.handle, C.byref(view), ptr(ds_idx), ptr(jitter), c_i64(int(batch)),
+                                     c_i64(int(sub_batch)), c_i64(int(ref_slot)), c_i64(int(n_tracks)), C.c_uint32(int(annot_mask)), C.byref(args),
+                                     _stream()))
+
+    def track_lengths(self, regions, diffs, batch: int, ploidy: int, out):
+        check(lib.gvl_dev_track_lengths(self.ctx.handle, ptr(regions), ptr(diffs), c_i64(int(batch)), c_i64(int(ploidy)),
+                                        ptr(out), _stream()))
 
     def choose_exonic_variants(self, starts, ends, geno_offset_idx, keep_cap: int):
         """gvl_dev_choose_exonic_variants (src/genotypes/mod.rs:132-176): keep mask of the variants that lie fully
@@ -179,12 +203,14 @@ class Engine:
     # ------------------------------------------------------------------ tracks
     def realign_tracks(self, names, regions, shifts, geno_offset_idx, offset_idxs, track_lengths, out_offsets,
                        total_per_track: int, strategy_ids, params, base_seed: int, max_records: int, keep=None,
-                       keep_offsets=None, to_rc=None, query_seed=None, out=None, layout="tbp"):
+                       keep_offsets=None, to_rc=None, query_seed=None, out=None, layout="tbp", base_seed_dev=None,
+                       batch=None, sub_batch: int = 0):
         """gvl_dev_realign_tracks: all `names` in one plan + one execute launch.
         offset_idxs: int64 (n_tracks, batch) device; out: float32 (n_tracks * total_per_track,), track-major
         (layout="tbp", the reference's flat buffer) or with every query's tracks adjacent (layout="btp",
         gvl_dev_realign_tracks_btp: the order the reference's (b, t, p, ~l) offsets describe)."""
-        batch, ploidy = geno_offset_idx.shape
+        b_cap, ploidy = geno_offset_idx.shape
+        batch = b_cap if batch is None else int(batch)  # (a prefix of preallocated buffers)
         n_tracks = len(names)
         itv = (Intervals * n_tracks)(*[self.tracks[n][4] for n in names])
         sid = (c_i32 * n_tracks)(*[int(s) for s in strategy_ids])
@@ -196,7 +222,7 @@ class Engine:
             self.ctx.handle, C.byref(self.tab), ptr(regions), ptr(shifts), ptr(geno_offset_idx), c_i64(batch),
             c_i64(ploidy), ptr(keep), ptr(keep_offsets), ptr(to_rc), c_i64(n_tracks), itv, ptr(offset_idxs),
             ptr(track_lengths), ptr(out_offsets), c_i64(int(total_per_track)), sid, par, c_u64(int(base_seed)),
-            ptr(query_seed), c_i64(int(max_records)), ptr(out), _stream()))
+            ptr(base_seed_dev), c_i64(int(sub_batch)), ptr(query_seed), c_i64(int(max_records)), ptr(out), _stream()))
         return out
 
     def intervals_to_tracks(self, name, offset_idxs, starts, out_offsets, total: int, out=None):
@@ -208,10 +234,11 @@ class Engine:
                                               c_i64(n_q), ptr(out_offsets), c_i64(int(total)), ptr(out), _stream()))
         return out
 
-    def paint_tracks(self, names, offset_idxs, starts, out_offsets, total_per_track: int, to_rc=None, out=None):
+    def paint_tracks(self, names, offset_idxs, starts, out_offsets, total_per_track: int, to_rc=None, out=None,
+                     n_queries=None):
         """gvl_dev_paint_tracks: stored intervals of all `names` painted in one launch, (b, t, ~l) order,
         masked rows reversed.  offset_idxs: int64 (n_tracks, batch) device."""
-        n_tracks, n_q = len(names), int(starts.numel())
+        n_tracks, n_q = len(names), int(starts.numel() if n_queries is None else n_queries)
         itv = (Intervals * n_tracks)(*[self.tracks[n][4] for n in names])
         if out is None:
             out = torch.empty(n_tracks * int(total_per_track), dtype=torch.float32, device=self.device)

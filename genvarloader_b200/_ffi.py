@@ -46,6 +46,19 @@ class Intervals(C.Structure):
                 ("n_slots", c_i64)]
 
 
+class DatasetView(C.Structure):
+    """gvl_dataset_view (include/gvl_b200.h)."""
+
+    _fields_ = [("full_regions", c_vp), ("n_regions", c_i64), ("n_samples", c_i64), ("ploidy", c_i64), ("rc_neg", c_i32)]
+
+
+class BatchArgs(C.Structure):
+    """gvl_batch_args (include/gvl_b200.h)."""
+
+    _fields_ = [("regions", c_vp), ("shifts", c_vp), ("goi", c_vp), ("to_rc", c_vp), ("to_rc_q", c_vp),
+                ("offset_idxs", c_vp), ("base_seed", c_vp), ("starts", c_vp)]
+
+
 def _load() -> C.CDLL:
     if not LIB_PATH.exists():
         raise ImportError(

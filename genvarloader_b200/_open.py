@@ -204,7 +204,13 @@ def read_dataset_arrays(path, reference=None, svar=None) -> dict:
         if pa.types.is_integer(st.type):
             strand = st.to_numpy().astype(np.int32)
         else:
-            strand = np.array([1 if str(x) == "+" else -1 for x in st.to_pylist()], np.int32)
+            # write side maps {"+": 1, "-": -1, ".": 1} (_write.py:566-571); open side is strict (_utils.py:105-109)
+            smap = {"+": 1, "-": -1, ".": 1}
+            vals = st.to_pylist()
+            bad = sorted({repr(x) for x in vals if x is None or str(x) not in smap})
+            if bad:
+                raise ValueError(f"input_regions.arrow: unknown strand value(s) {', '.join(bad)} (expected '+', '-' or '.')")
+            strand = np.array([smap[str(x)] for x in vals], np.int32)
     else:
         strand = np.ones(len(starts), np.int32)
     r_idx_map = cols["r_idx_map"].to_numpy().astype(np.int64)

@@ -1,0 +1,403 @@
+"""Fixed-length batch pipeline: the GPU-side analogue of the reference's buffered / double-buffered loaders
+(`Dataset.to_dataloader(mode=...)`, python/genvarloader/_dataset/_impl.py:1963-2072, `_double_buffered_loader.py`).
+
+A fixed-length, deterministic batch needs nothing from the host but its flat dataset indices (and the jitter draws):
+`gvl_dev_batch_prep` derives the regions, genotype slots, strand masks, interval slots and the fill seeds on the device,
+then plan -> execute (-> tracks) run as in `Dataset.__getitem__`.  Two users:
+
+  * `FixedPipeline.run_eager`  -- one batch on the current stream: the fast path of `Dataset.__getitem__` (one small
+                                  H2D copy, no per-call pinned allocation).
+  * `FixedPipeline` rings      -- the loader reads AHEAD: `ring` consecutive batches are reconstructed as ONE device
+                                  call (rows of all batches in one plan launch and one execute launch, so every launch
+                                  fills the GPU for hundreds of microseconds instead of ~10), into two buffer halves
+                                  that are produced alternately on two streams: while the consumer reads the batches
+                                  of one half, the other is being produced.  Rows are independent
+                                  (src/reconstruct/mod.rs:374-422), so batch i of a ring is simply rows
+                                  [i*b*p, (i+1)*b*p) of the ring's output.  `PipelinedLoader` drives it.
+
+Batches of a ring are views into the ring's output buffers (zero-copy, like `copy=False` of the reference's
+double-buffered mode: valid until the ring is refilled); `copy=True` hands out clones.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _ffi
+from ._engine import MODES, Engine, _stream
+from ._ffi import BatchArgs, DatasetView, c_i32, c_i64, c_u8, c_u64, c_vp, check, lib, ptr
+from ._insertion_fill import Repeat5p, lower
+from ._types import AnnotatedHaps
+
+
+class PinnedArray:
+    """Page-locked host array (gvl_host_alloc) viewed as numpy."""
+
+    def __init__(self, shape, dtype):
+        self.nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+        self._p = c_vp(0)
+        check(lib.gvl_host_alloc(c_i64(max(self.nbytes, 16)), C.byref(self._p)))
+        raw = np.ctypeslib.as_array(C.cast(self._p, C.POINTER(C.c_uint8)), shape=(max(self.nbytes, 16),))
+        self.array = raw[: self.nbytes].view(dtype).reshape(shape)
+        self.ptr = int(self._p.value)
+
+    def close(self):
+        if self._p:
+            lib.gvl_host_free(self._p)
+            self._p = c_vp(0)
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _Spec:
+    """What a dataset state asks of a fixed-length batch (resolved once per pipeline)."""
+
+    def __init__(self, ds):
+        self.L = int(ds.output_length)
+        self.p = int(ds.ploidy)
+        self.want_seqs = ds.sequence_type is not None
+        self.is_ref = ds.sequence_type == "reference"
+        self.annotated = ds.sequence_type == "annotated"
+        self.names = list(ds.active_tracks)
+        self.t = len(self.names)
+        self.realign = self.t > 0 and self.want_seqs and not self.is_ref and ds.realign_tracks
+        self.rows_p = 1 if (self.is_ref or not self.want_seqs) else self.p
+        self.rc_neg = bool(ds.rc_neg)
+        self.jitter = int(ds.jitter)
+        if self.annotated:
+            self.mode = "annotated"
+        elif ds.encoding == "bytes":
+            self.mode = "haplotypes"
+        else:
+            self.mode = ds.encoding  # "onehot" | "onehot_cf"
+        self.annot_mask = 0
+        for i, n in enumerate(self.names):
+            if ds.track_kinds[n] == "annot":
+                self.annot_mask |= 1 << i
+        self.fill_ids, self.fill_params = lower([ds.insertion_fill.get(n, Repeat5p()) for n in self.names]) if self.t else ([], [])
+
+
+def supports(ds) -> str | None:
+    """None when `ds` can use the fixed pipeline, else the reason it cannot."""
+    if not isinstance(ds.output_length, (int, np.integer)) or isinstance(ds.output_length, bool):
+        return "output_length is not fixed"
+    if ds.splice_rows is not None:
+        return "spliced output"
+    if ds.var_filter is not None:
+        return "var_filter needs per-batch keep masks"
+    if not ds.deterministic and ds.sequence_type in ("haplotypes", "annotated"):
+        return "random shifts (deterministic=False) are drawn on the host from the batch's diffs"
+    if ds.sequence_type is None and not ds.active_tracks:
+        return "nothing to read"
+    if len(ds.active_tracks) > 8:
+        return "more than 8 tracks"
+    if getattr(ds.engine, "svar2", None) is not None:
+        return "svar2 source"
+    return None
+
+
+class _Scratch:
+    """Device buffers holding the prepared arguments of ONE batch in flight."""
+
+    def __init__(self, spec: _Spec, b: int, dev, n_sub: int = 1):
+        rp, t = spec.rows_p, spec.t
+        i32, i64, u8 = torch.int32, torch.int64, torch.uint8
+        self.regions = torch.empty((b, 3), dtype=i32, device=dev)
+        self.starts = torch.empty(b, dtype=i32, device=dev)
+        self.shifts = torch.empty((b, rp), dtype=i32, device=dev)
+        self.goi = torch.empty((b, rp), dtype=i64, device=dev)
+        self.to_rc = torch.empty(b * rp, dtype=u8, device=dev)
+        self.to_rc_q = torch.empty(b, dtype=u8, device=dev)
+        self.offset_idxs = torch.empty((max(t, 1), b), dtype=i64, device=dev)
+        self.base_seed = torch.zeros(max(n_sub, 1), dtype=i64, device=dev)  # one fill seed per logical batch
+        self.out_offsets = torch.empty(b * rp + 1, dtype=i64, device=dev)
+        self.diffs = torch.empty((b, rp), dtype=i32, device=dev) if spec.realign else None
+        self.track_lengths = torch.empty(b, dtype=i32, device=dev) if spec.realign else None
+        self.args = BatchArgs(ptr(self.regions), ptr(self.shifts), ptr(self.goi), ptr(self.to_rc), ptr(self.to_rc_q),
+                              ptr(self.offset_idxs) if t else c_vp(0), ptr(self.base_seed), ptr(self.starts))
+
+
+class _Out:
+    """Output buffers of one batch + the objects handed to the user."""
+
+    def __init__(self, spec: _Spec, b: int, dev):
+        L, p, rp, t = spec.L, spec.p, spec.rows_p, spec.t
+        self.seq = self.av = self.ap = self.trk = None
+        if spec.want_seqs:
+            mult = 4 if spec.mode in ("onehot", "onehot_cf") else 1
+            self.seq = torch.empty(b * rp * L * mult, dtype=torch.uint8, device=dev)
+            if spec.annotated:
+                self.av = torch.empty(b * rp * L, dtype=torch.int32, device=dev)
+                self.ap = torch.empty(b * rp * L, dtype=torch.int32, device=dev)
+        if t:
+            self.trk = torch.empty(b * t * (p if spec.realign else 1) * L, dtype=torch.float32, device=dev)
+        self.spec, self.b = spec, b
+
+    def result(self, lo: int = 0, n: int | None = None, clone: bool = False):
+        """Queries [lo, lo + n) as `Dataset.__getitem__` returns them for array indices: dense tensors, `(seqs, tracks)`
+        when both are active."""
+        sp, b = self.spec, self.b
+        L, p, t = sp.L, sp.p, sp.t
+        n = b - lo if n is None else n
+        f = (lambda x: x[lo: lo + n].clone()) if clone else (lambda x: x[lo: lo + n])
+        res = []
+        if sp.want_seqs:
+            lead = (b,) if sp.is_ref else (b, p)
+            if sp.mode == "onehot":
+                s = f(self.seq.view(*lead, L, 4))
+            elif sp.mode == "onehot_cf":
+                s = f(self.seq.view(*lead, 4, L))
+            else:
+                s = f(self.seq.view(*lead, L))
+            if sp.annotated:
+                s = AnnotatedHaps(s, f(self.av.view(*lead, L)), f(self.ap.view(*lead, L)))
+            res.append(s)
+        if t:
+            res.append(f(self.trk.view(b, t, p, L) if sp.realign else self.trk.view(b, t, L)))
+        return res[0] if len(res) == 1 else tuple(res)
+
+
+class FixedPipeline:
+    """See the module docstring.  `batch_size` = queries per logical batch, `ring` = batches per device call (0: eager
+    single batches only), `halves` = ring buffers produced alternately."""
+
+    def __init__(self, ds, batch_size: int, ring: int = 0, halves: int = 2, graph: bool = True):
+        why = supports(ds)
+        if why is not None:
+            raise ValueError(f"the fixed-length pipeline does not apply: {why}")
+        self.ds, self.b = ds, int(batch_size)
+        self.eng: Engine = ds.engine
+        self.dev = self.eng.device
+        self.spec = sp = _Spec(ds)
+        self.view = self.eng.dataset_view(ds.full_regions, len(ds.sample_names), ds.ploidy, ds.rc_neg)
+        self.ref_slot = self.eng.empty_slot if (sp.is_ref or not sp.want_seqs) else -1
+        self.ring, self.n_halves, self.use_graph = int(ring), int(halves), bool(graph)
+        b, dev = self.b, self.dev
+        with torch.cuda.device(dev):
+            # eager path (Dataset.__getitem__): one scratch set, one pinned index buffer
+            self._scr0 = _Scratch(sp, b, dev)
+            self._pin0 = PinnedArray((b + (b + 1) // 2,), np.int64)  # [ds_idx i64[b]][jitter i32[b]]: one copy per call
+            self._pin0_jit = self._pin0.array[b:].view(np.int32)
+            self._idx0 = torch.zeros(b + (b + 1) // 2, dtype=torch.int64, device=dev)
+            self._jit0 = self._idx0[b:].view(torch.int32)
+            self._pin_ev = None
+            self._paint_off = torch.arange(max(self.ring, 1) * b + 1, dtype=torch.int64, device=dev) * sp.L
+        self.halves = []
+        if self.ring > 0:
+            self._build_rings()
+
+    def _cap(self, n_queries: int) -> int:
+        return n_queries * self.spec.rows_p * max(self.eng.max_slot_len, 1) if self.ref_slot < 0 else 0
+
+    # ------------------------------------------------------------------ one device call over n queries
+    def _step(self, eng: Engine, scr: _Scratch, idx_dev, jit_dev, out: _Out, n: int, sub_batch: int = 0):
+        sp = self.spec
+        eng.batch_prep(self.view, idx_dev, jit_dev, n, self.ref_slot, sp.t, sp.annot_mask, scr.args, sub_batch=sub_batch)
+        rc = scr.to_rc if sp.rc_neg else None
+        if sp.want_seqs:
+            eng.plan(scr.regions, scr.shifts, scr.goi[:n], sp.L, self._cap(n), to_rc=rc, out_offsets=scr.out_offsets,
+                     diffs=scr.diffs)
+            eng.execute(sp.mode, out=out.seq, annot_v=out.av, annot_pos=out.ap)
+        if sp.t:
+            if sp.realign:
+                eng.track_lengths(scr.regions, scr.diffs, n, sp.p, scr.track_lengths)
+                eng.realign_tracks(sp.names, scr.regions, scr.shifts, scr.goi, scr.offset_idxs, scr.track_lengths,
+                                   scr.out_offsets, n * sp.p * sp.L, sp.fill_ids, sp.fill_params, 0, self._cap(n), to_rc=rc,
+                                   out=out.trk, layout="btp", base_seed_dev=scr.base_seed, batch=n, sub_batch=sub_batch)
+            else:
+                eng.paint_tracks(sp.names, scr.offset_idxs, scr.starts, self._paint_off, n * sp.L,
+                                 scr.to_rc_q if sp.rc_neg else None, out=out.trk, n_queries=n)
+
+    def run_eager(self, ds_idx: np.ndarray, jitter: np.ndarray | None):
+        """One batch (len(ds_idx) <= batch_size) on the current stream; returns freshly allocated outputs."""
+        n = len(ds_idx)
+        if n > self.b:
+            raise ValueError("batch larger than the pipeline's batch size")
+        host = self._pin0.array
+        with torch.cuda.device(self.dev):
+            if self._pin_ev is not None:
+                self._pin_ev.synchronize()  # the previous call's copy out of the pinned buffer has finished
+            host[:n] = ds_idx
+            if jitter is not None:
+                self._pin0_jit[:n] = jitter
+            check(lib.gvl_dev_upload(self.eng.ctx.handle, ptr(self._idx0), c_vp(self._pin0.ptr), c_i64(self._pin0.nbytes), _stream()))
+            if self._pin_ev is None:
+                self._pin_ev = torch.cuda.Event()
+            self._pin_ev.record()
+            out = _Out(self.spec, n, self.dev)
+            self._step(self.eng, self._scr0, self._idx0, self._jit0 if jitter is not None else None, out, n)
+        return out.result()
+
+    # ------------------------------------------------------------------ rings
+    def _build_rings(self):
+        sp, b, dev, K = self.spec, self.b, self.dev, self.ring
+        n = K * b
+        with torch.cuda.device(dev):
+            for h in range(self.n_halves):
+                H = type("Half", (), {})()
+                H.stream = torch.cuda.Stream(dev)
+                H.eng = self.eng.fork()
+                H.scr = _Scratch(sp, n, dev, n_sub=K)
+                H.out = _Out(sp, n, dev)
+                H.pin = PinnedArray((n + (n + 1) // 2,), np.int64)  # [ds_idx i64[n]][jitter i32[n]]
+                H.pin_jit = H.pin.array[n:].view(np.int32)
+                H.idx = torch.zeros(n + (n + 1) // 2, dtype=torch.int64, device=dev)
+                H.jit = H.idx[n:].view(torch.int32)
+                H.done = torch.cuda.Event()
+                H.uploaded = torch.cuda.Event()
+                H.free = None
+                H.graph = None
+                self.halves.append(H)
+            # warm once outside capture: workspace growth allocates
+            for H in self.halves:
+                with torch.cuda.stream(H.stream):
+                    self._step(H.eng, H.scr, H.idx, H.jit if sp.jitter else None, H.out, n, sub_batch=b)
+            torch.cuda.synchronize(dev)
+            for H in self.halves:
+                H.eng.check()
+            _ffi.launch_count(reset=True)
+            H = self.halves[0]
+            with torch.cuda.stream(H.stream):
+                self._step(H.eng, H.scr, H.idx, H.jit if sp.jitter else None, H.out, n, sub_batch=b)
+            self.launches_per_ring = _ffi.launch_count()
+            torch.cuda.synchronize(dev)
+            if self.use_graph:
+                for H in self.halves:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=H.stream):
+                        self._step(H.eng, H.scr, H.idx, H.jit if sp.jitter else None, H.out, n, sub_batch=b)
+                    H.graph = g
+
+    def submit(self, h: int, ds_idx: np.ndarray | None, jitter: np.ndarray | None = None):
+        """Produce half `h`: `ds_idx` int64 (ring * b) host indices (None: replay with the indices already on the device),
+        optional jitter int32 (ring * b)."""
+        H = self.halves[h]
+        n = self.ring * self.b
+        with torch.cuda.device(self.dev):
+            if H.free is not None:
+                H.stream.wait_event(H.free)  # the consumer has let go of this half's buffers
+            if ds_idx is not None:
+                H.uploaded.synchronize()  # the previous copy out of the pinned buffer has finished
+                H.pin.array[:n] = ds_idx
+                if jitter is not None:
+                    H.pin_jit[:n] = jitter
+                check(lib.gvl_dev_upload(self.eng.ctx.handle, ptr(H.idx), c_vp(H.pin.ptr), c_i64(H.pin.nbytes),
+                                         c_vp(H.stream.cuda_stream)))
+                H.uploaded.record(H.stream)
+            with torch.cuda.stream(H.stream):
+                if H.graph is not None:
+                    H.graph.replay()
+                else:
+                    self._step(H.eng, H.scr, H.idx, H.jit if self.spec.jitter else None, H.out, n, sub_batch=self.b)
+            H.done.record(H.stream)
+
+    def acquire(self, h: int) -> _Out:
+        """Make the current stream wait for half `h`; returns its `_Out` (batch i = queries [i*b, (i+1)*b))."""
+        H = self.halves[h]
+        torch.cuda.current_stream(self.dev).wait_event(H.done)
+        return H.out
+
+    def release(self, h: int):
+        """The consumer is done with half `h` (everything it enqueued so far on the current stream)."""
+        H = self.halves[h]
+        if H.free is None:
+            H.free = torch.cuda.Event()
+        H.free.record(torch.cuda.current_stream(self.dev))
+
+    def check(self):
+        for H in self.halves:
+            H.eng.check()
+        self.eng.check()
+
+
+class PipelinedLoader:
+    """Re-iterable loader over a `Dataset` backed by a `FixedPipeline` (see `Dataset.to_dataloader(mode=...)`)."""
+
+    def __init__(self, ds, batch_size, shuffle, sampler, drop_last, generator, return_indices, transform, copy, ring):
+        self.ds, self.batch_size, self.shuffle, self.sampler = ds, int(batch_size), shuffle, sampler
+        self.drop_last, self.return_indices, self.transform, self.copy = drop_last, return_indices, transform, copy
+        self._rng = _as_rng(generator)
+        n_batches = len(self)
+        if not ring:  # ~256 MiB of output per half, at least one batch, no more than half an epoch
+            per_batch = self.batch_size * max(ds.ploidy, 1) * int(ds.output_length) * (4 + 4 * len(ds.active_tracks))
+            ring = max(1, min((256 << 20) // max(per_batch, 1), 64))
+        ring = max(1, min(int(ring), -(-n_batches // 2)))
+        self.pipe = FixedPipeline(ds, self.batch_size, ring=ring)
+
+    def __len__(self) -> int:
+        n = len(self.sampler) if self.sampler is not None else len(self.ds)
+        return n // self.batch_size if self.drop_last else -(-n // self.batch_size)
+
+    def __iter__(self):
+        ds, pipe, b, K = self.ds, self.pipe, self.batch_size, self.pipe.ring
+        order = epoch_order(ds, self.sampler, self.shuffle, self._rng)
+        n_batches = len(self)
+        if self.drop_last:
+            order = order[: n_batches * b]
+        n_s, S_full = ds.n_samples, len(ds.sample_names)
+        r_map, s_map = ds._r_idx, ds._s_idx
+        n_rings = -(-n_batches // K)
+        jit = ds.jitter
+
+        def fill(ring_i):
+            chunk = order[ring_i * K * b: (ring_i + 1) * K * b]
+            r, s = chunk // n_s, chunk % n_s
+            flat = np.zeros(K * b, np.int64)
+            flat[: len(chunk)] = r_map[r] * S_full + s_map[s]
+            j = None
+            if jit:
+                j = np.zeros(K * b, np.int32)
+                for lo in range(0, len(chunk), b):  # one draw per batch, like the reference (_query.py:165-171)
+                    m = min(b, len(chunk) - lo)
+                    j[lo: lo + m] = ds.rng.integers(-jit, jit + 1, size=m, dtype=np.int32)
+            return flat, j, chunk
+
+        chunks = {}
+        for ring_i in range(min(pipe.n_halves, n_rings)):
+            flat, j, chunks[ring_i] = fill(ring_i)
+            pipe.submit(ring_i % pipe.n_halves, flat, j)
+        plain = not self.return_indices and self.transform is None
+        for ring_i in range(n_rings):
+            h = ring_i % pipe.n_halves
+            out = pipe.acquire(h)
+            chunk = chunks.pop(ring_i)
+            for lo in range(0, len(chunk), b):
+                m = min(b, len(chunk) - lo)
+                batch = out.result(lo, m, clone=self.copy)
+                if not plain:
+                    batch = batch if isinstance(batch, tuple) else (batch,)
+                    if self.return_indices:  # the (region, sample) indices the dataset was indexed with, _torch.py:293-300
+                        c = chunk[lo: lo + m]
+                        batch = (*batch, c // n_s, c % n_s)
+                    if self.transform is not None:
+                        batch = self.transform(*batch)  # _torch.py:302-303
+                    elif len(batch) == 1:
+                        batch = batch[0]
+                yield batch
+            pipe.release(h)
+            nxt = ring_i + pipe.n_halves
+            if nxt < n_rings:
+                flat, j, chunks[nxt] = fill(nxt)
+                pipe.submit(h, flat, j)
+
+
+def _as_rng(generator):
+    if generator is None or isinstance(generator, (int, np.integer)):
+        return np.random.default_rng(generator)
+    if isinstance(generator, np.random.Generator):
+        return generator
+    return np.random.default_rng(int(generator.initial_seed()))  # torch.Generator
+
+
+def epoch_order(ds, sampler, shuffle, rng) -> np.ndarray:
+    if sampler is not None:
+        return np.fromiter(iter(sampler), np.int64)
+    if shuffle:
+        return rng.permutation(len(ds)).astype(np.int64)
+    return np.arange(len(ds), dtype=np.int64)

@@ -1,0 +1,147 @@
+// gvl_batch.cu -- device-side preparation of a (region, sample) batch.
+//
+// The reference prepares every batch on the host with numpy: region rows + read-time jitter
+// (python/genvarloader/_dataset/_query.py:161-175), geno_offset_idx = ravel of (region, sample, ploid)
+// (_dataset/_haps.py:757-768), the per-row strand mask (_haps.py:838-843, _reconstruct.py:251-256) and the
+// interval slot of every (track, query) (_reconstruct.py:233-236).  Here the same O(batch) arithmetic is one
+// small kernel over the flat dataset indices, so a batch needs ONE host->device copy (its indices) and the
+// whole chain prep -> plan -> execute can be captured in a CUDA graph and replayed with new indices.
+#include "gvl_internal.cuh"
+
+using namespace gvl;
+
+namespace {
+
+struct PrepParams {
+    const int32_t *full_regions;  // (R, 4)
+    const int64_t *ds_idx;        // (b) flat index r * n_samples + s over the FULL grid
+    const int32_t *jitter;        // (b) or NULL
+    int64_t batch, n_samples, ploidy, rows_p, ref_slot, n_tracks, sub_batch;
+    uint32_t annot_mask;
+    int32_t rc_neg;
+    int32_t *regions;
+    int32_t *shifts;
+    int64_t *goi;
+    uint8_t *to_rc;
+    uint8_t *to_rc_q;
+    int64_t *offset_idxs;
+    uint64_t *base_seed;
+    int32_t *starts;
+};
+
+__global__ void __launch_bounds__(128) batch_prep_kernel(PrepParams P) {
+    if (P.base_seed) {
+        // deterministic fill seed of every logical batch: xor-reduce of its dataset indices as u64
+        // (_reconstruct.py:215-218); one warp per logical batch, warps stride over them
+        const int lane = threadIdx.x & 31;
+        const int64_t n_sub = (P.batch + P.sub_batch - 1) / P.sub_batch;
+        const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+        for (int64_t sb = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); sb < n_sub; sb += n_warps) {
+            const int64_t lo = sb * P.sub_batch, hi = imin64(lo + P.sub_batch, P.batch);
+            uint64_t x = 0;
+            for (int64_t i = lo + lane; i < hi; i += 32) x ^= (uint64_t)P.ds_idx[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x ^= __shfl_xor_sync(0xffffffffu, x, o);
+            if (lane == 0) P.base_seed[sb] = x;
+        }
+    }
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= P.batch) return;
+    const int64_t idx = P.ds_idx[q];
+    const int64_t r = idx / P.n_samples;
+    const int4 reg = *reinterpret_cast<const int4 *>(P.full_regions + 4 * r);  // contig, start, end, strand
+    const int32_t len = reg.z - reg.y;
+    const int32_t start = reg.y + (P.jitter ? P.jitter[q] : 0);  // _query.py:165-171
+    P.regions[3 * q + 0] = reg.x;
+    P.regions[3 * q + 1] = start;
+    P.regions[3 * q + 2] = start + len;
+    if (P.starts) P.starts[q] = start;
+    const uint8_t rc = (P.rc_neg && reg.w == -1) ? 1 : 0;  // _query.py:173-175
+    if (P.to_rc_q) P.to_rc_q[q] = rc;
+    for (int64_t h = 0; h < P.rows_p; h++) {
+        const int64_t k = q * P.rows_p + h;
+        P.goi[k] = P.ref_slot >= 0 ? P.ref_slot : idx * P.ploidy + h;  // _haps.py:757-768
+        P.shifts[k] = 0;
+        P.to_rc[k] = rc;                                                  // _haps.py:838-843
+    }
+    for (int64_t t = 0; t < P.n_tracks; t++)  // SAMPLE tracks: dataset index; ANNOT tracks: region index (_reconstruct.py:233-236)
+        P.offset_idxs[t * P.batch + q] = ((P.annot_mask >> t) & 1u) ? r : idx;
+}
+
+__global__ void __launch_bounds__(128) track_lengths_kernel(const int32_t *__restrict__ regions,
+                                                            const int32_t *__restrict__ diffs, int64_t batch,
+                                                            int64_t ploidy, int32_t *__restrict__ out) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= batch) return;
+    int32_t m = 0;
+    for (int64_t h = 0; h < ploidy; h++) m = min(m, diffs[q * ploidy + h]);
+    out[q] = regions[3 * q + 2] - regions[3 * q + 1] - m;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gvl_dev_batch_prep(gvl_ctx *ctx, const gvl_dataset_view *view, const int64_t *ds_idx, const int32_t *jitter,
+                       int64_t batch, int64_t sub_batch, int64_t ref_slot, int64_t n_tracks, uint32_t annot_mask,
+                       const gvl_batch_args *args, gvl_stream stream) {
+    if (!ctx || !view || !args) return fail(GVL_ERR_ARG, "gvl_dev_batch_prep: NULL argument");
+    if (batch == 0) return GVL_OK;
+    if (!ds_idx || !view->full_regions || !args->regions || !args->shifts || !args->goi || !args->to_rc)
+        return fail(GVL_ERR_ARG, "gvl_dev_batch_prep: NULL buffer");
+    if (n_tracks < 0 || n_tracks > 32 || (n_tracks > 0 && !args->offset_idxs))
+        return fail(GVL_ERR_ARG, "gvl_dev_batch_prep: 0..32 tracks, offset_idxs required when n_tracks > 0");
+    if (view->n_samples < 1 || view->ploidy < 1) return fail(GVL_ERR_ARG, "gvl_dev_batch_prep: bad dataset view");
+    if ((uintptr_t)view->full_regions & 15) return fail(GVL_ERR_ARG, "gvl_dev_batch_prep: full_regions must be 16-byte aligned");
+    GVL_CUDA(cudaSetDevice(ctx->device));
+    PrepParams P;
+    P.full_regions = view->full_regions;
+    P.ds_idx = ds_idx;
+    P.jitter = jitter;
+    P.batch = batch;
+    P.sub_batch = (sub_batch > 0 && sub_batch < batch) ? sub_batch : batch;
+    P.n_samples = view->n_samples;
+    P.ploidy = view->ploidy;
+    P.rows_p = ref_slot >= 0 ? 1 : view->ploidy;
+    P.ref_slot = ref_slot;
+    P.n_tracks = n_tracks;
+    P.annot_mask = annot_mask;
+    P.rc_neg = view->rc_neg;
+    P.regions = args->regions;
+    P.shifts = args->shifts;
+    P.goi = args->goi;
+    P.to_rc = args->to_rc;
+    P.to_rc_q = args->to_rc_q;
+    P.offset_idxs = args->offset_idxs;
+    P.base_seed = args->base_seed;
+    P.starts = args->starts;
+    batch_prep_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, (cudaStream_t)stream>>>(P);
+    GVL_LAUNCH_CHECK();
+    return GVL_OK;
+}
+
+// track_lengths[q] = (end - start) - min(0, min_h diffs[q, h]): the source window of a realigned track grows by the
+// longest net deletion among the query's haplotypes (HapsTracks.__call__, _dataset/_reconstruct.py:191-196)
+int gvl_dev_track_lengths(gvl_ctx *ctx, const int32_t *regions, const int32_t *diffs, int64_t batch, int64_t ploidy,
+                          int32_t *track_lengths, gvl_stream stream) {
+    if (!ctx || batch < 0 || ploidy < 1) return fail(GVL_ERR_ARG, "gvl_dev_track_lengths: bad argument");
+    if (batch == 0) return GVL_OK;
+    if (!regions || !diffs || !track_lengths) return fail(GVL_ERR_ARG, "gvl_dev_track_lengths: NULL argument");
+    GVL_CUDA(cudaSetDevice(ctx->device));
+    track_lengths_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, (cudaStream_t)stream>>>(regions, diffs, batch, ploidy,
+                                                                                            track_lengths);
+    GVL_LAUNCH_CHECK();
+    return GVL_OK;
+}
+
+// Asynchronous host -> device copy on the caller's stream (the pipelined loader stages a ring's indices with one copy;
+// `host` should be page-locked, gvl_host_alloc).
+int gvl_dev_upload(gvl_ctx *ctx, void *dev, const void *host, int64_t bytes, gvl_stream stream) {
+    if (!ctx || (bytes > 0 && (!dev || !host)) || bytes < 0) return fail(GVL_ERR_ARG, "gvl_dev_upload: bad argument");
+    if (bytes == 0) return GVL_OK;
+    GVL_CUDA(cudaSetDevice(ctx->device));
+    GVL_CUDA(cudaMemcpyAsync(dev, host, (size_t)bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return GVL_OK;
+}
+
+}  // extern "C"

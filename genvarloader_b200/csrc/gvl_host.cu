@@ -701,7 +701,7 @@ int gvl_intervals_and_realign_track_fused(
                                      ploidy, keep && keep_offsets ? pk.ptr<uint8_t>(i_kp) : nullptr,
                                      keep && keep_offsets ? pk.ptr<int64_t>(i_ko) : nullptr, pk.ptr<uint8_t>(i_rc), 1, &iv,
                                      pk.ptr<int64_t>(i_oi), pk.ptr<int32_t>(i_tl), pk.ptr<int64_t>(i_oo), total, &strat,
-                                     params, base_seed, nullptr, max_rec, (float *)d_out, ctx->own_stream)))
+                                     params, base_seed, nullptr, 0, nullptr, max_rec, (float *)d_out, ctx->own_stream)))
         return rc;
     GVL_CUDA(cudaMemcpyAsync(out, d_out, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->own_stream));
     return gvl_ctx_check(ctx, ctx->own_stream);

@@ -312,6 +312,8 @@ struct TrkExecParams {
     int64_t n_queries;
     const int64_t *query_seed;   // optional [n_queries]
     uint64_t base_seed;
+    const uint64_t *base_seed_dev;  // optional: the seed(s) live in device memory (CUDA-graph replays with new batches)
+    int64_t sub_batch;              // > 0: queries per logical batch (seed and FlankSample row index are per logical batch)
     float *out;
     const TrkDesc *tracks;       // device array [n_tracks], or NULL: the descriptors travel in `inl`
     TrkDesc inl[8];              // (kernel parameters are captured by value: CUDA-graph safe)
@@ -471,7 +473,9 @@ __global__ void __launch_bounds__(TRK_THREADS, 1024 / TRK_THREADS) trk_exec_kern
     const int32_t h1 = rc ? L - t0 : t1;
     const int64_t query = row / P.ploidy;
     const uint64_t hap = (uint64_t)(row % P.ploidy);
-    const uint64_t qseed = P.query_seed ? (uint64_t)P.query_seed[query] : (uint64_t)query;
+    const uint64_t qseed = P.query_seed ? (uint64_t)P.query_seed[query]
+                                        : (uint64_t)(P.sub_batch > 0 ? query % P.sub_batch : query);
+    const uint64_t base_seed = P.base_seed_dev ? P.base_seed_dev[P.sub_batch > 0 ? query / P.sub_batch : 0] : P.base_seed;
     const TrkDesc T = P.tracks ? P.tracks[track] : P.inl[track];
     int64_t itv_lo, itv_hi;
     if (T.dense) {
@@ -827,7 +831,7 @@ __global__ void __launch_bounds__(TRK_THREADS, 1024 / TRK_THREADS) trk_exec_kern
                     const int64_t vrel = S.vrel[i];
                     if (S.vdiff[i] > 0 && T.strategy != GVL_FILL_REPEAT_5P) {
                         vals[q] = insertion_fill_value(src, T.strategy, T.param, S.vlen[i], vrel, p - S.a[i], p,
-                                                       P.base_seed, qseed, hap);
+                                                       base_seed, qseed, hap);
                     } else {
                         vals[q] = src.at(vrel);
                     }
@@ -872,7 +876,8 @@ using namespace gvl;
 
 static int launch_trk_exec(gvl_ctx *ctx, int64_t n_work, int64_t ploidy, int64_t n_queries, int64_t n_tracks,
                            const TrkDesc *host_desc, const int64_t *offset_idxs, int64_t total_per_track,
-                           const int64_t *query_seed, uint64_t base_seed, float *out, int layout_btp, cudaStream_t st) {
+                           const int64_t *query_seed, uint64_t base_seed, float *out, int layout_btp, cudaStream_t st,
+                           const uint64_t *base_seed_dev = nullptr, int64_t sub_batch = 0) {
     if (n_tracks > MAX_TRACKS) return fail(GVL_ERR_ARG, "at most %d tracks per call", MAX_TRACKS);
     static_assert(sizeof(TrkDesc) * MAX_TRACKS <= GVL_TRK_DESC_BYTES, "descriptor buffer too small");
     TrkDesc *d_desc = nullptr;
@@ -896,6 +901,8 @@ static int launch_trk_exec(gvl_ctx *ctx, int64_t n_work, int64_t ploidy, int64_t
     P.n_queries = n_queries;
     P.query_seed = query_seed;
     P.base_seed = base_seed;
+    P.base_seed_dev = base_seed_dev;
+    P.sub_batch = sub_batch;
     P.out = out;
     P.tracks = d_desc;
     if (!d_desc)
@@ -925,7 +932,7 @@ static int realign_impl(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_sv
                         const int32_t *track_lengths, const int64_t *out_offsets, int64_t total_per_track,
                         const int32_t *strategy_ids, const double *params, uint64_t base_seed,
                         const int64_t *query_seed, int64_t max_records, float *out, gvl_stream stream,
-                        int layout_btp = 0) {
+                        int layout_btp = 0, const uint64_t *base_seed_dev = nullptr, int64_t sub_batch = 0) {
     if (!ctx || !tab || !regions || !shifts || !(geno_offset_idx || svar2) || !(itv || dense) || !(offset_idxs || dense) ||
         !track_lengths || !out_offsets || !strategy_ids || !params)
         return fail(GVL_ERR_ARG, "gvl_dev_realign_tracks: NULL argument");
@@ -980,7 +987,7 @@ static int realign_impl(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_sv
             return fail(GVL_ERR_ARG, "Interpolate order must be 1, 2 or 3");
     }
     return launch_trk_exec(ctx, n_work, ploidy, batch, n_tracks, desc, offset_idxs, total_per_track, query_seed,
-                           base_seed, out, layout_btp, st);
+                           base_seed, out, layout_btp, st, base_seed_dev, sub_batch);
 }
 
 int gvl_dev_realign_tracks(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_t *regions,
@@ -989,11 +996,12 @@ int gvl_dev_realign_tracks(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int
                            int64_t n_tracks, const gvl_intervals *itv, const int64_t *offset_idxs,
                            const int32_t *track_lengths, const int64_t *out_offsets, int64_t total_per_track,
                            const int32_t *strategy_ids, const double *params, uint64_t base_seed,
-                           const int64_t *query_seed, int64_t max_records, float *out, gvl_stream stream) {
+                           const uint64_t *base_seed_dev, int64_t sub_batch, const int64_t *query_seed, int64_t max_records,
+                           float *out, gvl_stream stream) {
     if (!itv || !offset_idxs) return fail(GVL_ERR_ARG, "gvl_dev_realign_tracks: NULL argument");
     return realign_impl(ctx, tab, nullptr, regions, shifts, geno_offset_idx, batch, ploidy, keep, keep_offsets, to_rc, n_tracks,
                         itv, offset_idxs, nullptr, nullptr, track_lengths, out_offsets, total_per_track, strategy_ids,
-                        params, base_seed, query_seed, max_records, out, stream);
+                        params, base_seed, query_seed, max_records, out, stream, 0, base_seed_dev, sub_batch);
 }
 
 int gvl_dev_realign_tracks_btp(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_t *regions,
@@ -1002,11 +1010,12 @@ int gvl_dev_realign_tracks_btp(gvl_ctx *ctx, const gvl_sparse_tables *tab, const
                                int64_t n_tracks, const gvl_intervals *itv, const int64_t *offset_idxs,
                                const int32_t *track_lengths, const int64_t *out_offsets, int64_t total_per_track,
                                const int32_t *strategy_ids, const double *params, uint64_t base_seed,
-                               const int64_t *query_seed, int64_t max_records, float *out, gvl_stream stream) {
+                               const uint64_t *base_seed_dev, int64_t sub_batch, const int64_t *query_seed,
+                               int64_t max_records, float *out, gvl_stream stream) {
     if (!itv || !offset_idxs) return fail(GVL_ERR_ARG, "gvl_dev_realign_tracks_btp: NULL argument");
     return realign_impl(ctx, tab, nullptr, regions, shifts, geno_offset_idx, batch, ploidy, keep, keep_offsets, to_rc, n_tracks,
                         itv, offset_idxs, nullptr, nullptr, track_lengths, out_offsets, total_per_track, strategy_ids,
-                        params, base_seed, query_seed, max_records, out, stream, 1);
+                        params, base_seed, query_seed, max_records, out, stream, 1, base_seed_dev, sub_batch);
 }
 
 int gvl_dev_shift_and_realign_tracks(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_t *regions,

@@ -117,10 +117,31 @@ def make_track(rng, regions, n_slots_per_region, max_jitter=0, mean_run=50, head
             np.concatenate(values).astype(np.float32), off)
 
 
+def make_track_fast(rng, regions, n_slots_per_region, max_jitter=0, mean_run=50, headroom=64):
+    """`make_track` for large tables (millions of intervals): the same kind of track -- contiguous runs of mean length
+    `mean_run` over the expanded region, ~25% of them omitted -- drawn for all slots of a region at once."""
+    starts, ends, values, counts = [], [], [], []
+    for r in range(regions.shape[0]):
+        s0 = int(regions[r, 1]) - max_jitter
+        T = int(regions[r, 2]) + max_jitter + headroom - s0
+        n_runs = max(1, T // mean_run)
+        cuts = np.sort(rng.integers(1, T, size=(n_slots_per_region, n_runs - 1), dtype=np.int32), axis=1)
+        b = np.concatenate([np.zeros((n_slots_per_region, 1), np.int32), cuts, np.full((n_slots_per_region, 1), T, np.int32)], 1)
+        keep = (b[:, 1:] > b[:, :-1]) & (rng.random((n_slots_per_region, n_runs)) > 0.25)
+        starts.append((b[:, :-1] + s0)[keep])
+        ends.append((b[:, 1:] + s0)[keep])
+        counts.append(keep.sum(1))
+        values.append(rng.gamma(2.0, 2.0, int(keep.sum())).astype(np.float32))
+    off = np.concatenate([[0], np.cumsum(np.concatenate(counts))]).astype(np.int64)
+    return (np.concatenate(starts).astype(np.int32), np.concatenate(ends).astype(np.int32),
+            np.concatenate(values).astype(np.float32), off)
+
+
 def make_dataset(seed: int, contig_len: int, n_samples: int, n_regions: int, region_len: int,
                  variants_per_kb: float = 1.0, ploidy: int = 2, max_jitter: int = 0, snp_frac: float = 0.8,
                  neg_strand_frac: float = 0.0, straddle_ends: bool = True, n_tracks: int = 0,
-                 sample_tracks: bool = True, dense_af: float | None = None, max_indel: int = 20) -> SynthData:
+                 sample_tracks: bool = True, dense_af: float | None = None, max_indel: int = 20,
+                 fast_tracks: bool = False) -> SynthData:
     # `variants_per_kb` is the density PER HAPLOTYPE (what the kernels see); the table is denser by
     # 1/E[AF] so that Bernoulli(AF ~ Beta(0.5, 5)) carriers hit that density.
     rng = np.random.default_rng(seed)
@@ -138,7 +159,8 @@ def make_dataset(seed: int, contig_len: int, n_samples: int, n_regions: int, reg
     gv, go = make_genotypes(rng, regions, v_starts, n_samples, ploidy, max_jitter, dense_af=dense_af)
     d = SynthData(ref, ref_offsets, v_starts, ilens, alt, alt_off, gv, go, regions, n_samples, ploidy, max_jitter)
     for t in range(n_tracks):
-        d.tracks[f"track{t}"] = make_track(rng, regions, n_samples if sample_tracks else 1, max_jitter)
+        d.tracks[f"track{t}"] = (make_track_fast if fast_tracks else make_track)(rng, regions, n_samples if sample_tracks else 1,
+                                                                              max_jitter)
     return d
 
 

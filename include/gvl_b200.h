@@ -193,6 +193,11 @@ int gvl_dev_get_diffs_sparse(gvl_ctx *ctx, const gvl_sparse_tables *tab, const i
  *   out_offsets          device i64[b*p+1] per-track row offsets (same for every track), input
  *   total_per_track      out_offsets[b*p] (host value)
  *   strategy_ids/params  HOST arrays, one per track (python/genvarloader/_dataset/_insertion_fill.py:89)
+ *   base_seed_dev        optional device u64[1]: when non-NULL the seed is read from device memory at run time instead of
+ *                        `base_seed` (a CUDA graph captured once then serves batches with different seeds)
+ *   sub_batch            > 0: the call holds several logical batches of this many queries: query q belongs to batch
+ *                        q / sub_batch, its FlankSample row index is q % sub_batch and its seed base_seed_dev[q / sub_batch];
+ *                        <= 0: one batch (seed base_seed_dev[0] or base_seed)
  *   query_seed           optional device i64[b]: global batch row used as the FlankSample seed
  *                        component when one logical batch is split over several calls / GPUs
  *                        (src/tracks/mod.rs:696-702); NULL = local row index
@@ -204,7 +209,8 @@ int gvl_dev_realign_tracks(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int
                            int64_t n_tracks, const gvl_intervals *itv, const int64_t *offset_idxs,
                            const int32_t *track_lengths, const int64_t *out_offsets, int64_t total_per_track,
                            const int32_t *strategy_ids, const double *params, uint64_t base_seed,
-                           const int64_t *query_seed, int64_t max_records, float *out, gvl_stream stream);
+                           const uint64_t *base_seed_dev, int64_t sub_batch, const int64_t *query_seed, int64_t max_records,
+                           float *out, gvl_stream stream);
 
 /* gvl_dev_realign_tracks writing the layout the reference's offsets describe, (b, t, p, ~l) (_reconstruct.py:292-300):
  * all tracks of a query adjacent, so the flat buffer and lengths_to_offsets(repeat(out_lengths, "b p -> b t p")) agree
@@ -216,7 +222,8 @@ int gvl_dev_realign_tracks_btp(gvl_ctx *ctx, const gvl_sparse_tables *tab, const
                                int64_t n_tracks, const gvl_intervals *itv, const int64_t *offset_idxs,
                                const int32_t *track_lengths, const int64_t *out_offsets, int64_t total_per_track,
                                const int32_t *strategy_ids, const double *params, uint64_t base_seed,
-                               const int64_t *query_seed, int64_t max_records, float *out, gvl_stream stream);
+                               const uint64_t *base_seed_dev, int64_t sub_batch, const int64_t *query_seed,
+                               int64_t max_records, float *out, gvl_stream stream);
 
 /* shift_and_realign_tracks_sparse on device (src/ffi/mod.rs:2439-2458): ONE track whose source is
  * a dense f32 window per query (`tracks` ragged by `track_offsets` i64[b+1]) instead of intervals.
@@ -282,6 +289,47 @@ int gvl_dev_get_reference(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int3
  * caller, exactly like the reference.  Device pointers, any alignment. */
 int gvl_dev_ragged_to_padded(gvl_ctx *ctx, const void *data, const int64_t *offsets, int64_t n_rows, void *out,
                              int64_t itemsize, int64_t out_len, gvl_stream stream);
+
+/* ---- device layer: batch preparation (the host prep of the reference, on the device) --- */
+/* Per-replica region table for gvl_dev_batch_prep: the reference's `_full_regions` (int32 (R,4): contig index, start,
+ * end, strand in {+1,-1}; python/genvarloader/_dataset/_open.py:146-164) resident in HBM. */
+typedef struct {
+    const int32_t *full_regions; /* device i32[n_regions*4], 16-byte aligned */
+    int64_t n_regions, n_samples, ploidy;
+    int32_t rc_neg;              /* reverse(-complement) negative-strand regions (Dataset.with_settings(rc_neg=)) */
+} gvl_dataset_view;
+
+/* Device buffers of one prepared batch (caller-owned; b = batch, p = ploidy, or 1 when ref_slot >= 0). */
+typedef struct {
+    int32_t *regions;     /* i32[b*3]   contig, start (+ jitter), end                    */
+    int32_t *shifts;      /* i32[b*p]   zero (deterministic shifts, _haps.py:720-730)    */
+    int64_t *goi;         /* i64[b*p]   geno_offset_idx                                  */
+    uint8_t *to_rc;       /* u8[b*p]    per-row strand mask                              */
+    uint8_t *to_rc_q;     /* u8[b]      per-query strand mask (un-realigned tracks), may be NULL */
+    int64_t *offset_idxs; /* i64[n_tracks*b] interval slot per (track, query), NULL when n_tracks == 0 */
+    uint64_t *base_seed;  /* u64[n logical batches] xor-reduce of ds_idx: the deterministic insertion-fill seed (_reconstruct.py:215-218), may be NULL */
+    int32_t *starts;      /* i32[b] = regions[:,1], contiguous (gvl_dev_paint_tracks takes it), may be NULL */
+} gvl_batch_args;
+
+/* O(batch) arguments of plan / realign / paint from flat dataset indices, on the device: what
+ * `_getitem_unspliced` (_dataset/_query.py:161-175), `Haps._get_geno_offset_idx` (_haps.py:757-768), the strand masks
+ * (_haps.py:838-843, _reconstruct.py:251-256) and the interval-slot choice (_reconstruct.py:233-236) compute with numpy.
+ *   ds_idx      device i64[batch]: r * n_samples + s over the FULL (regions, samples) grid (_indexing.py:237-245)
+ *   jitter      optional device i32[batch]: per-query start offset drawn by the caller's generator (_query.py:165-171)
+ *   sub_batch   > 0: the call holds several LOGICAL batches of this many queries (a loader reading ahead); fill seeds
+ *               are then per logical batch (args->base_seed has ceil(batch / sub_batch) words); <= 0: one batch
+ *   ref_slot    >= 0: "reference" rows -- one row per query that points at this (empty) genotype slot; < 0: haplotypes
+ *   annot_mask  bit t set: track t is an ANNOT track (slot = region index) instead of a SAMPLE track (dataset index)
+ * No host sync; safe to capture in a CUDA graph (all arguments are captured by value). */
+int gvl_dev_batch_prep(gvl_ctx *ctx, const gvl_dataset_view *view, const int64_t *ds_idx, const int32_t *jitter,
+                       int64_t batch, int64_t sub_batch, int64_t ref_slot, int64_t n_tracks, uint32_t annot_mask,
+                       const gvl_batch_args *args, gvl_stream stream);
+/* track_lengths[q] = (end - start) - min(0, min_h diffs[q,h]) (HapsTracks.__call__, _dataset/_reconstruct.py:191-196): the
+ * source-window length of every query of a realigned-track call.  regions i32[b*3], diffs i32[b*p], out i32[b]; device. */
+int gvl_dev_track_lengths(gvl_ctx *ctx, const int32_t *regions, const int32_t *diffs, int64_t batch, int64_t ploidy,
+                          int32_t *track_lengths, gvl_stream stream);
+/* cudaMemcpyAsync(host -> device) on the caller's stream: one copy stages the indices of a whole ring of batches. */
+int gvl_dev_upload(gvl_ctx *ctx, void *dev, const void *host, int64_t bytes, gvl_stream stream);
 
 /* ---- host layer: reference-shaped entries (host pointers in, host pointers out) ------ */
 /* Upload (or refresh) a static array and cache it by host address; later gvl_* calls that see

@@ -31,9 +31,12 @@ static inline int64_t i64min(int64_t a, int64_t b) { return a < b ? a : b; }
 static inline int64_t i64max(int64_t a, int64_t b) { return a > b ? a : b; }
 
 /* ------------------------------------------------------------------------------------
- * tiny fork-join pool: one task per work item pulled from an atomic counter.  Same
+ * persistent fork-join pool: one task per work item pulled from an atomic counter.  Same
  * decomposition as rayon `into_par_iter` over (query, hap) items
- * (src/reconstruct/mod.rs:531-538); scheduling never affects results (disjoint outputs).
+ * (src/reconstruct/mod.rs:531-538); like rayon's process-global pool
+ * (python/genvarloader/_threads.py:102-115) the workers are created once and parked between
+ * calls, so a call pays a wake-up, not a thread creation.  Scheduling never affects results
+ * (disjoint outputs).
  * ---------------------------------------------------------------------------------- */
 typedef void (*gvl_task_fn)(void *ctx, int64_t k);
 typedef struct {
@@ -44,20 +47,47 @@ typedef struct {
     int64_t grain;
 } gvl_job;
 
-static void *gvl_worker(void *p) {
-    gvl_job *job = (gvl_job *)p;
+static void gvl_run_job(gvl_job *job) {
     for (;;) {
         int64_t s = atomic_fetch_add(&job->next, job->grain);
         if (s >= job->n) break;
         int64_t e = i64min(s + job->grain, job->n);
         for (int64_t k = s; k < e; k++) job->fn(job->ctx, k);
     }
+}
+
+#define GVL_MAX_THREADS 256
+static int g_threads = 1;
+static struct {
+    pthread_mutex_t mu;
+    pthread_cond_t wake, done;
+    pthread_t th[GVL_MAX_THREADS];
+    int n_workers;        /* threads alive (excluding the caller) */
+    int n_active;         /* workers that take part in the current job */
+    int n_running;        /* workers that have not finished the current job yet */
+    unsigned generation;  /* bumped once per job */
+    gvl_job *job;
+    int init;
+} g_pool = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER, {0}, 0, 0, 0, 0, NULL, 0};
+
+static void *gvl_pool_worker(void *p) {
+    const int id = (int)(intptr_t)p;
+    unsigned seen = 0;
+    pthread_mutex_lock(&g_pool.mu);
+    for (;;) {
+        while (g_pool.generation == seen) pthread_cond_wait(&g_pool.wake, &g_pool.mu);
+        seen = g_pool.generation;
+        if (id >= g_pool.n_active) continue; /* this job uses fewer threads */
+        gvl_job *job = g_pool.job;
+        pthread_mutex_unlock(&g_pool.mu);
+        gvl_run_job(job);
+        pthread_mutex_lock(&g_pool.mu);
+        if (--g_pool.n_running == 0) pthread_cond_signal(&g_pool.done);
+    }
     return NULL;
 }
 
-static int g_threads = 1;
-
-GVL_API void gvl_oracle_set_threads(int n) { g_threads = n < 1 ? 1 : n; }
+GVL_API void gvl_oracle_set_threads(int n) { g_threads = n < 1 ? 1 : (n > GVL_MAX_THREADS ? GVL_MAX_THREADS : n); }
 GVL_API int gvl_oracle_get_threads(void) { return g_threads; }
 
 static void gvl_parallel_for(gvl_task_fn fn, void *ctx, int64_t n, int parallel, int64_t grain) {
@@ -73,11 +103,25 @@ static void gvl_parallel_for(gvl_task_fn fn, void *ctx, int64_t n, int parallel,
     job.n = n;
     job.grain = grain < 1 ? 1 : grain;
     atomic_init(&job.next, 0);
-    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nt);
-    for (int t = 1; t < nt; t++) pthread_create(&th[t], NULL, gvl_worker, &job);
-    gvl_worker(&job);
-    for (int t = 1; t < nt; t++) pthread_join(th[t], NULL);
-    free(th);
+    pthread_mutex_lock(&g_pool.mu);
+    while (g_pool.n_workers < nt - 1) { /* grow the pool on demand; workers never exit */
+        const int id = g_pool.n_workers;
+        if (pthread_create(&g_pool.th[id], NULL, gvl_pool_worker, (void *)(intptr_t)id) != 0) break;
+        pthread_detach(g_pool.th[id]);
+        g_pool.n_workers++;
+    }
+    const int helpers = g_pool.n_workers < nt - 1 ? g_pool.n_workers : nt - 1;
+    g_pool.job = &job;
+    g_pool.n_active = helpers;
+    g_pool.n_running = helpers;
+    g_pool.generation++;
+    pthread_cond_broadcast(&g_pool.wake);
+    pthread_mutex_unlock(&g_pool.mu);
+    gvl_run_job(&job); /* the caller works too */
+    pthread_mutex_lock(&g_pool.mu);
+    while (g_pool.n_running > 0) pthread_cond_wait(&g_pool.done, &g_pool.mu);
+    g_pool.job = NULL;
+    pthread_mutex_unlock(&g_pool.mu);
 }
 
 /* ====================================================================================

@@ -1,0 +1,150 @@
+"""The fixed-length pipeline (device-side batch prep, `Dataset.__getitem__` fast path, read-ahead loader) against the
+general `Dataset` path -- which the other suites pin to the oracle -- and against the oracle directly.
+Reference behaviour mirrored: `Dataset.to_dataloader` modes (_impl.py:1963-2072), `TorchDataset.__getitem__`
+(_torch.py:290-306: `transform(*batch)`, `(r_idx, s_idx)` in dataset index space)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+N = ord("N")
+
+
+@pytest.fixture(scope="module")
+def env(cuda_device):
+    from genvarloader_b200 import synth
+    from genvarloader_b200._dataset import Dataset
+    from oracle import oracle as O
+
+    d = synth.make_dataset(91, 300_000, 4, 11, 2000 + 2 * 12, 6.0, max_jitter=12, neg_strand_frac=0.5,
+                           straddle_ends=False, n_tracks=2, max_indel=15, snp_frac=0.5)
+    ds = Dataset.from_synth(cuda_device, d, rng=5)
+    return d, ds, O
+
+
+def _slow(ds):
+    """The same dataset state with the fast path switched off (general numpy-prep path)."""
+    import dataclasses
+
+    s = dataclasses.replace(ds, _cache={"fast": False})
+    return s
+
+
+def _eq(a, b):
+    import torch
+
+    from genvarloader_b200._types import AnnotatedHaps
+
+    if isinstance(a, tuple):
+        return len(a) == len(b) and all(_eq(x, y) for x, y in zip(a, b))
+    if isinstance(a, AnnotatedHaps):
+        return _eq(a.haps, b.haps) and _eq(a.var_idxs, b.var_idxs) and _eq(a.ref_coords, b.ref_coords)
+    if a.dtype == torch.float32:
+        return a.shape == b.shape and bool((a.view(torch.int32) == b.contiguous().view(torch.int32)).all())
+    return a.shape == b.shape and bool((a == b).all())
+
+
+@pytest.mark.parametrize("kind", ["bytes", "onehot", "onehot_cf", "annotated", "reference", "reference_onehot"])
+def test_getitem_fast_path_matches_general_path(env, kind):
+    d, ds, O = env
+    L = 1536
+    base = ds.with_tracks(False).with_len(L)
+    if kind in ("onehot", "onehot_cf"):
+        base = base.with_encoding(kind)
+    elif kind == "annotated":
+        base = base.with_seqs("annotated")
+    elif kind.startswith("reference"):
+        base = base.with_seqs("reference")
+        if kind.endswith("onehot"):
+            base = base.with_encoding("onehot")
+    assert base._eager_pipeline(3) is not None
+    for idx in [([1, 7, 10, 3, 3], [0, 3, 1, 2, 2]), (slice(2, 6), slice(0, 3)), (4, 1), ([9, 0], 2)]:
+        got, exp = base[idx], _slow(base)[idx]
+        assert _eq(got, exp), (kind, idx)
+
+
+def test_getitem_fast_path_vs_oracle_with_jitter(env):
+    d, ds, O = env
+    L, J = 1800, 12
+    dsj = ds.with_tracks(False).with_len(L).with_settings(jitter=J, rng=77)
+    idx = (np.array([0, 5, 10, 2]), np.array([3, 1, 0, 2]))
+    out = dsj[idx]
+    ds_idx = idx[0] * d.n_samples + idx[1]
+    rng = np.random.default_rng(77)
+    regions = d.regions[idx[0]].copy()
+    lengths = regions[:, 2] - regions[:, 1]
+    regions[:, 1] += rng.integers(-J, J + 1, size=4, dtype=np.int32)
+    regions[:, 2] = regions[:, 1] + lengths
+    goi = ds_idx[:, None] * d.ploidy + np.arange(d.ploidy)[None, :]
+    to_rc = np.repeat(d.regions[idx[0], 3] == -1, d.ploidy)
+    exp, _ = O.reconstruct_haplotypes_fused(np.ascontiguousarray(regions[:, :3]), np.zeros(goi.shape, np.int32), goi,
+                                            d.geno_offsets, d.geno_v_idxs, d.v_starts, d.ilens, d.alt_alleles, d.alt_offsets,
+                                            d.reference, d.ref_offsets, N, L, None, None, to_rc)
+    assert (out.cpu().numpy().ravel() == exp).all()
+
+
+@pytest.mark.parametrize("realign", [True, False])
+def test_getitem_fast_path_tracks(env, realign):
+    from genvarloader_b200 import FlankSample, Interpolate
+
+    d, ds, O = env
+    L = 1700
+    dst = ds.with_len(L)
+    if realign:
+        dst = dst.with_insertion_fill({"track0": FlankSample(4), "track1": Interpolate(1)})
+    else:
+        dst = dst.with_settings(realign_tracks=False)
+    for idx in [([2, 5, 5, 8], [0, 3, 1, 1]), (slice(0, 3), slice(1, 4)), (6, 0)]:
+        got, exp = dst[idx], _slow(dst)[idx]
+        assert _eq(got, exp), idx
+    only = ds.with_seqs(None).with_len(L).with_tracks(["track1"])
+    assert _eq(only[[1, 4], [2, 2]], _slow(only)[[1, 4], [2, 2]])
+
+
+@pytest.mark.parametrize("copy", [False, True])
+def test_pipelined_loader_matches_indexing(env, copy):
+    from genvarloader_b200 import FlankSample
+
+    d, ds, O = env
+    L, B = 1024, 5
+    dsl = ds.with_len(L).with_encoding("onehot").with_insertion_fill(FlankSample(3))
+    dl = dsl.to_dataloader(batch_size=B, mode="double_buffered", copy=copy, ring=3, return_indices=True)
+    from genvarloader_b200._pipeline import PipelinedLoader
+
+    assert isinstance(dl, PipelinedLoader) and len(dl) == -(-len(dsl) // B)
+    ref = _slow(dsl)
+    n = 0
+    for k, (x, t, r, s) in enumerate(dl):
+        idx = np.arange(k * B, min((k + 1) * B, len(dsl)))
+        assert (r == idx // dsl.n_samples).all() and (s == idx % dsl.n_samples).all()
+        ex, et = ref[r, s]
+        assert _eq(x, ex) and _eq(t, et), k  # (per-batch FlankSample seeds: xor of the batch's dataset indices)
+        n += x.shape[0]
+    assert n == len(dsl)
+    # second epoch over the same loader, shuffled, transform(*batch), drop_last
+    seen = []
+    dl2 = dsl.with_tracks(False).to_dataloader(batch_size=4, mode="buffered", shuffle=True, generator=9, drop_last=True, copy=copy,
+                                               ring=2, return_indices=True, transform=lambda x, r, s: (x, r, s))
+    for x, r, s in dl2:
+        assert x.shape[0] == 4 and _eq(x, ref.with_tracks(False)[r, s])
+        seen.extend((r * dsl.n_samples + s).tolist())
+    assert len(seen) == (len(dsl) // 4) * 4 and len(set(seen)) == len(seen)
+
+
+def test_pipelined_loader_subset_jitter_and_fallback(env):
+    d, ds, O = env
+    sub = ds.with_tracks(False).with_len(900).subset_to(regions=[7, 2, 9], samples=[3, 0])
+    got = [x for x in sub.to_dataloader(batch_size=4, mode="double_buffered", copy=True)]
+    exp = _slow(sub)[:, :].reshape(6, d.ploidy, 900)
+    assert _eq(__import__("torch").cat(got), exp)
+    # jitter: one draw per batch from the dataset's generator, in batch order
+    a = ds.with_tracks(False).with_len(800).with_settings(jitter=7, rng=11)
+    b = ds.with_tracks(False).with_len(800).with_settings(jitter=7, rng=11)
+    xs = list(a.to_dataloader(batch_size=6, mode="double_buffered", ring=2))
+    n_s = a.n_samples
+    for k, x in enumerate(xs):
+        idx = np.arange(k * 6, min((k + 1) * 6, len(a)))
+        assert _eq(x, _slow(b)[idx // n_s, idx % n_s])
+    # ragged output cannot be pipelined: falls back to the synchronous loader
+    from genvarloader_b200._dataset import BatchLoader
+
+    assert isinstance(ds.with_tracks(False).to_dataloader(batch_size=3, mode="double_buffered"), BatchLoader)

@@ -293,8 +293,7 @@ def run_b200(args):
     # ---- ring geometry: K steps = n_sub device calls of `ring` batches each, alternating between two halves ----
     out_bytes_step = bp_per_step * ({"onehot": 4, "u8": 1, "annotated": 9}[mode] + 4 * n_tracks_main)
     ring_cap = max(1, min(args.ring, int(args.ring_gib * (1 << 30)) // (2 * out_bytes_step)))
-    ring = max((r for r in range(1, ring_cap + 1) if args.steps % r == 0 and (args.steps // r >= 2 or r == args.steps == 1)),
-               default=1)
+    ring = max((r for r in range(1, ring_cap + 1) if args.steps % r == 0 and args.steps // r >= min(4, args.steps)), default=1)
     n_sub = args.steps // ring
     pipe = FixedPipeline(ds, pairs, ring=ring)
     n_q = ring * pairs
@@ -313,15 +312,10 @@ def run_b200(args):
 
     def submit_resident(pl, h):
         """One device call of half h over the next resident index set (a device-to-device copy of the indices, then the
-        captured prep -> plan -> execute [-> tracks] chain)."""
-        H = pl.halves[h]
+        captured prep -> plan chain on the plan stream and execute [-> tracks] on the execute stream)."""
         k = set_i[0] % n_sets
         set_i[0] += 1
-        with torch.cuda.stream(H.stream):
-            H.idx[:n_q].copy_(idx_sets[k], non_blocking=True)
-            if jit_sets is not None:
-                H.jit[:n_q].copy_(jit_sets[k], non_blocking=True)
-        pl.submit(h, None)
+        pl.submit(h, idx_sets[k], jit_sets[k] if jit_sets is not None else None)
 
     def timed_block(pl, sync_ranks=True) -> float:
         """Exactly `steps` steps: n_sub device calls alternating between the two halves; device time between one start
@@ -332,12 +326,11 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize()
         e0.record(main)
-        for H in pl.halves:
-            H.stream.wait_event(e0)
+        pl.s_plan.wait_event(e0)
+        pl.s_exec.wait_event(e0)
         for i in range(n_sub):
             submit_resident(pl, i % pl.n_halves)
-        for H in pl.halves:
-            main.wait_event(H.done)
+        main.wait_event(pl.halves[(n_sub - 1) % pl.n_halves].done)  # (the execute stream runs the calls in order)
         e1.record(main)
         torch.cuda.synchronize()
         return e0.elapsed_time(e1)  # ms
@@ -371,7 +364,7 @@ def run_b200(args):
     # ---- roofline of the dominant kernel: ONE execute launch over a ring (events on its own stream) ----
     H = pipe.halves[0]
     exec_ms = plan_ms = None
-    with torch.cuda.stream(H.stream):
+    with torch.cuda.stream(pipe.s_exec):
         sp = pipe.spec
         durs, pdurs = [], []
         for i in range(12):
@@ -382,13 +375,13 @@ def run_b200(args):
             H.eng.batch_prep(pipe.view, H.idx, H.jit if sp.jitter else None, n_q, pipe.ref_slot, sp.t, sp.annot_mask, H.scr.args,
                              sub_batch=pairs)
             a0, a1, a2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-            a0.record(H.stream)
+            a0.record(pipe.s_exec)
             H.eng.plan(H.scr.regions, H.scr.shifts, H.scr.goi[:n_q], L, pipe._cap(n_q), to_rc=H.scr.to_rc if sp.rc_neg else None,
                        out_offsets=H.scr.out_offsets, diffs=H.scr.diffs)
-            a1.record(H.stream)
+            a1.record(pipe.s_exec)
             H.eng.execute(sp.mode, out=H.out.seq, annot_v=H.out.av, annot_pos=H.out.ap)
-            a2.record(H.stream)
-            H.stream.synchronize()
+            a2.record(pipe.s_exec)
+            pipe.s_exec.synchronize()
             if i >= 2:
                 pdurs.append(a0.elapsed_time(a1))
                 durs.append(a1.elapsed_time(a2))
@@ -416,7 +409,7 @@ def run_b200(args):
     if not n_tracks_main and w.get("tracks_avail", 0) and mode == "onehot" and not args.no_tracks:
         nt = w["tracks_avail"]
         dst = ds0.with_tracks([f"track{i}" for i in range(nt)]).with_insertion_fill({"track0": Repeat5p(), "track1": Interpolate(1)})
-        ring_t = max((r for r in range(1, ring + 1) if args.steps % r == 0 and args.steps // r >= 2 and
+        ring_t = max((r for r in range(1, ring + 1) if args.steps % r == 0 and args.steps // r >= min(4, args.steps) and
                       r * 2 * bp_per_step * (4 + 4 * nt) <= args.ring_gib * (1 << 30)), default=1)
         if ring_t == ring:
             pipe_t = FixedPipeline(dst, pairs, ring=ring_t)

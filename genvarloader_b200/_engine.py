@@ -142,6 +142,20 @@ class Engine:
 
     # ------------------------------------------------------------------ tracks
     def add_track(self, name: str, itv_starts, itv_ends, itv_values, itv_offsets) -> None:
+        """Upload one track's interval SoA.  Slots whose intervals overlap (legal: the reference paints in stored order,
+        last write wins, src/intervals.rs:64-85) are flattened into the equivalent disjoint list first."""
+        st, en = np.ascontiguousarray(itv_starts, np.int32), np.ascontiguousarray(itv_ends, np.int32)
+        off = np.ascontiguousarray(itv_offsets, np.int64)
+        n_bad = c_i64(0)
+        check(lib.gvl_intervals_overlap(ptr(st), ptr(en), ptr(off), c_i64(off.size - 1), C.byref(n_bad)))
+        if n_bad.value:
+            va = np.ascontiguousarray(itv_values, np.float32)
+            cap = 2 * st.size + 16
+            o_s, o_e, o_v = np.empty(cap, np.int32), np.empty(cap, np.int32), np.empty(cap, np.float32)
+            o_off, n_out = np.empty(off.size, np.int64), c_i64(0)
+            check(lib.gvl_flatten_intervals(ptr(st), ptr(en), ptr(va), ptr(off), c_i64(off.size - 1), ptr(o_s), ptr(o_e), ptr(o_v),
+                                            ptr(o_off), c_i64(cap), C.byref(n_out)))
+            itv_starts, itv_ends, itv_values, itv_offsets = o_s[: n_out.value], o_e[: n_out.value], o_v[: n_out.value], o_off
         with torch.cuda.device(self.device):
             t = (_dev(itv_starts, np.int32, self.device, pad=4), _dev(itv_ends, np.int32, self.device, pad=4),
                  _dev(itv_values, np.float32, self.device, pad=4), _dev(itv_offsets, np.int64, self.device))

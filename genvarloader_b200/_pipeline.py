@@ -196,17 +196,25 @@ class FixedPipeline:
         return n_queries * self.spec.rows_p * max(self.eng.max_slot_len, 1) if self.ref_slot < 0 else 0
 
     # ------------------------------------------------------------------ one device call over n queries
-    def _step(self, eng: Engine, scr: _Scratch, idx_dev, jit_dev, out: _Out, n: int, sub_batch: int = 0):
+    # Stage P ("plan"): batch prep + variant plan.  Stage E ("execute"): the bandwidth-bound kernels.  The eager path
+    # runs both on the current stream; rings run P on a plan stream and E on an execute stream, so the plan of ring
+    # k+1 (latency-bound, few CTAs) overlaps the execute launch of ring k.
+    def _stage_plan(self, eng: Engine, scr: _Scratch, idx_dev, jit_dev, n: int, sub_batch: int = 0):
         sp = self.spec
         eng.batch_prep(self.view, idx_dev, jit_dev, n, self.ref_slot, sp.t, sp.annot_mask, scr.args, sub_batch=sub_batch)
+        if sp.want_seqs:
+            eng.plan(scr.regions, scr.shifts, scr.goi[:n], sp.L, self._cap(n), to_rc=scr.to_rc if sp.rc_neg else None,
+                     out_offsets=scr.out_offsets, diffs=scr.diffs)
+        if sp.realign:
+            eng.track_lengths(scr.regions, scr.diffs, n, sp.p, scr.track_lengths)
+
+    def _stage_exec(self, eng: Engine, scr: _Scratch, out: _Out, n: int, sub_batch: int = 0):
+        sp = self.spec
         rc = scr.to_rc if sp.rc_neg else None
         if sp.want_seqs:
-            eng.plan(scr.regions, scr.shifts, scr.goi[:n], sp.L, self._cap(n), to_rc=rc, out_offsets=scr.out_offsets,
-                     diffs=scr.diffs)
             eng.execute(sp.mode, out=out.seq, annot_v=out.av, annot_pos=out.ap)
         if sp.t:
             if sp.realign:
-                eng.track_lengths(scr.regions, scr.diffs, n, sp.p, scr.track_lengths)
                 eng.realign_tracks(sp.names, scr.regions, scr.shifts, scr.goi, scr.offset_idxs, scr.track_lengths,
                                    scr.out_offsets, n * sp.p * sp.L, sp.fill_ids, sp.fill_params, 0, self._cap(n), to_rc=rc,
                                    out=out.trk, layout="btp", base_seed_dev=scr.base_seed, batch=n, sub_batch=sub_batch)
@@ -231,7 +239,8 @@ class FixedPipeline:
                 self._pin_ev = torch.cuda.Event()
             self._pin_ev.record()
             out = _Out(self.spec, n, self.dev)
-            self._step(self.eng, self._scr0, self._idx0, self._jit0 if jitter is not None else None, out, n)
+            self._stage_plan(self.eng, self._scr0, self._idx0, self._jit0 if jitter is not None else None, n)
+            self._stage_exec(self.eng, self._scr0, out, n)
         return out.result()
 
     # ------------------------------------------------------------------ rings
@@ -239,9 +248,9 @@ class FixedPipeline:
         sp, b, dev, K = self.spec, self.b, self.dev, self.ring
         n = K * b
         with torch.cuda.device(dev):
+            self.s_plan, self.s_exec = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
             for h in range(self.n_halves):
                 H = type("Half", (), {})()
-                H.stream = torch.cuda.Stream(dev)
                 H.eng = self.eng.fork()
                 H.scr = _Scratch(sp, n, dev, n_sub=K)
                 H.out = _Out(sp, n, dev)
@@ -249,53 +258,66 @@ class FixedPipeline:
                 H.pin_jit = H.pin.array[n:].view(np.int32)
                 H.idx = torch.zeros(n + (n + 1) // 2, dtype=torch.int64, device=dev)
                 H.jit = H.idx[n:].view(torch.int32)
-                H.done = torch.cuda.Event()
-                H.uploaded = torch.cuda.Event()
+                H.planned, H.done, H.uploaded = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
                 H.free = None
-                H.graph = None
+                H.g_plan = H.g_exec = None
                 self.halves.append(H)
+            jit = (lambda H: H.jit if sp.jitter else None)
             # warm once outside capture: workspace growth allocates
+            _ffi.launch_count(reset=True)
             for H in self.halves:
-                with torch.cuda.stream(H.stream):
-                    self._step(H.eng, H.scr, H.idx, H.jit if sp.jitter else None, H.out, n, sub_batch=b)
+                with torch.cuda.stream(self.s_plan):
+                    self._stage_plan(H.eng, H.scr, H.idx, jit(H), n, sub_batch=b)
+                    self._stage_exec(H.eng, H.scr, H.out, n, sub_batch=b)
+            self.launches_per_ring = _ffi.launch_count() // max(len(self.halves), 1)
             torch.cuda.synchronize(dev)
             for H in self.halves:
                 H.eng.check()
-            _ffi.launch_count(reset=True)
-            H = self.halves[0]
-            with torch.cuda.stream(H.stream):
-                self._step(H.eng, H.scr, H.idx, H.jit if sp.jitter else None, H.out, n, sub_batch=b)
-            self.launches_per_ring = _ffi.launch_count()
-            torch.cuda.synchronize(dev)
             if self.use_graph:
                 for H in self.halves:
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g, stream=H.stream):
-                        self._step(H.eng, H.scr, H.idx, H.jit if sp.jitter else None, H.out, n, sub_batch=b)
-                    H.graph = g
+                    H.g_plan, H.g_exec = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(H.g_plan, stream=self.s_plan):
+                        self._stage_plan(H.eng, H.scr, H.idx, jit(H), n, sub_batch=b)
+                    with torch.cuda.graph(H.g_exec, stream=self.s_exec):
+                        self._stage_exec(H.eng, H.scr, H.out, n, sub_batch=b)
 
-    def submit(self, h: int, ds_idx: np.ndarray | None, jitter: np.ndarray | None = None):
-        """Produce half `h`: `ds_idx` int64 (ring * b) host indices (None: replay with the indices already on the device),
-        optional jitter int32 (ring * b)."""
+    def submit(self, h: int, ds_idx=None, jitter=None):
+        """Produce half `h`.  `ds_idx`: int64 (ring * b) indices -- a numpy array (staged through pinned memory, one H2D
+        copy), a device tensor (device-to-device copy) or None (replay with the indices already in place); `jitter`
+        likewise (int32)."""
         H = self.halves[h]
         n = self.ring * self.b
+        sp = self.spec
         with torch.cuda.device(self.dev):
-            if H.free is not None:
-                H.stream.wait_event(H.free)  # the consumer has let go of this half's buffers
-            if ds_idx is not None:
+            self.s_plan.wait_event(H.done)  # this half's previous execute has finished with the plan workspace / scratch
+            if isinstance(ds_idx, np.ndarray):
                 H.uploaded.synchronize()  # the previous copy out of the pinned buffer has finished
                 H.pin.array[:n] = ds_idx
                 if jitter is not None:
                     H.pin_jit[:n] = jitter
                 check(lib.gvl_dev_upload(self.eng.ctx.handle, ptr(H.idx), c_vp(H.pin.ptr), c_i64(H.pin.nbytes),
-                                         c_vp(H.stream.cuda_stream)))
-                H.uploaded.record(H.stream)
-            with torch.cuda.stream(H.stream):
-                if H.graph is not None:
-                    H.graph.replay()
+                                         c_vp(self.s_plan.cuda_stream)))
+                H.uploaded.record(self.s_plan)
+            elif ds_idx is not None:
+                with torch.cuda.stream(self.s_plan):
+                    H.idx[:n].copy_(ds_idx, non_blocking=True)
+                    if jitter is not None:
+                        H.jit[:n].copy_(jitter, non_blocking=True)
+            with torch.cuda.stream(self.s_plan):
+                if H.g_plan is not None:
+                    H.g_plan.replay()
                 else:
-                    self._step(H.eng, H.scr, H.idx, H.jit if self.spec.jitter else None, H.out, n, sub_batch=self.b)
-            H.done.record(H.stream)
+                    self._stage_plan(H.eng, H.scr, H.idx, H.jit if sp.jitter else None, n, sub_batch=self.b)
+            H.planned.record(self.s_plan)
+            self.s_exec.wait_event(H.planned)
+            if H.free is not None:
+                self.s_exec.wait_event(H.free)  # the consumer has let go of this half's output buffers
+            with torch.cuda.stream(self.s_exec):
+                if H.g_exec is not None:
+                    H.g_exec.replay()
+                else:
+                    self._stage_exec(H.eng, H.scr, H.out, n, sub_batch=self.b)
+            H.done.record(self.s_exec)
 
     def acquire(self, h: int) -> _Out:
         """Make the current stream wait for half `h`; returns its `_Out` (batch i = queries [i*b, (i+1)*b))."""

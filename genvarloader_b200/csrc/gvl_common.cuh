@@ -86,6 +86,9 @@ struct gvl_workspace {
     // fixed-length plans: per-row checkpoint directory, dir[row * stride + q] = records with a < q * DIR_Q
     int32_t *dir;
     int64_t dir_cap;
+    // track plans: 32-byte AoS records (gvl_tracks.cu: TrkRec)
+    void *trecs;
+    int64_t trec_cap;
 };
 
 struct gvl_ctx {

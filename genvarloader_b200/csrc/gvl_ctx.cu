@@ -83,7 +83,20 @@ int ensure_dir(gvl_ctx *ctx, gvl_workspace &ws, int64_t n) {
     return GVL_OK;
 }
 
+int ensure_trecs(gvl_ctx *ctx, gvl_workspace &ws, int64_t n) {
+    (void)ctx;
+    if (n <= ws.trec_cap) return GVL_OK;
+    GVL_CUDA(cudaDeviceSynchronize());
+    int64_t cap = n + n / 2 + 1024;
+    if (ws.trecs) GVL_CUDA(cudaFree(ws.trecs));
+    ws.trecs = nullptr;
+    GVL_CUDA(cudaMalloc(&ws.trecs, 32 * (size_t)cap + 64));  // (32-byte records + slack for aligned bulk copies)
+    ws.trec_cap = cap;
+    return GVL_OK;
+}
+
 static void free_workspace(gvl_workspace &ws) {
+    cudaFree(ws.trecs);
     cudaFree(ws.dir);
     cudaFree(ws.m_pos);
     cudaFree(ws.m_key);

@@ -208,7 +208,92 @@ static void svar2_resolve(const Packer &pk, const Svar2Slots &s, gvl_svar2_chann
 
 using namespace gvl;
 
+namespace gvl {
+// ---- overlapping intervals ---------------------------------------------------------------------------------
+// The reference paints a slot's intervals in stored order, later intervals overwriting earlier ones
+// (src/intervals.rs:64-85); annotation tables are sorted by start but never merged, so overlaps are legal data.  The
+// execute kernel paints a run-length code and needs disjoint intervals: a slot with overlaps is replaced by the
+// equivalent disjoint, sorted list ("last write wins" resolved once, here on the host).
+static bool slot_overlaps(const int32_t *s, const int32_t *e, int64_t n) {
+    int32_t reach = INT32_MIN;  // furthest end of the non-empty intervals seen so far
+    for (int64_t i = 0; i < n; i++) {
+        if (e[i] <= s[i]) continue;
+        if (s[i] < reach) return true;
+        reach = e[i] > reach ? e[i] : reach;
+    }
+    return false;
+}
+
+static void flatten_slot(const int32_t *s, const int32_t *e, const float *v, int64_t n, std::vector<int32_t> &os,
+                         std::vector<int32_t> &oe, std::vector<float> &ov) {
+    const size_t base = os.size();  // pieces of this slot live in [base, os.size()): sorted, disjoint
+    std::vector<int32_t> ts, te;
+    std::vector<float> tv;
+    for (int64_t i = 0; i < n; i++) {
+        const int32_t a = s[i], b = e[i];
+        if (b <= a) continue;
+        size_t k = os.size();  // first piece whose end lies beyond a (ends are sorted: search from the tail)
+        while (k > base && oe[k - 1] > a) k--;
+        ts.clear(), te.clear(), tv.clear();
+        for (size_t j = k; j < os.size(); j++) {  // what the new interval leaves of the pieces it meets
+            if (os[j] < a) ts.push_back(os[j]), te.push_back(a), tv.push_back(ov[j]);
+        }
+        ts.push_back(a), te.push_back(b), tv.push_back(v[i]);
+        for (size_t j = k; j < os.size(); j++) {
+            if (oe[j] > b) ts.push_back(os[j] > b ? os[j] : b), te.push_back(oe[j]), tv.push_back(ov[j]);
+        }
+        os.resize(k), oe.resize(k), ov.resize(k);
+        os.insert(os.end(), ts.begin(), ts.end());
+        oe.insert(oe.end(), te.begin(), te.end());
+        ov.insert(ov.end(), tv.begin(), tv.end());
+    }
+}
+
+}  // namespace gvl
+using namespace gvl;
+
 extern "C" {
+
+int gvl_intervals_overlap(const int32_t *itv_starts, const int32_t *itv_ends, const int64_t *itv_offsets, int64_t n_slots,
+                          int64_t *n_overlapping) {
+    if (!itv_offsets || !n_overlapping || (n_slots > 0 && itv_offsets[n_slots] > 0 && (!itv_starts || !itv_ends)))
+        return fail(GVL_ERR_ARG, "gvl_intervals_overlap: NULL argument");
+    int64_t c = 0;
+    for (int64_t k = 0; k < n_slots; k++)
+        c += slot_overlaps(itv_starts + itv_offsets[k], itv_ends + itv_offsets[k], itv_offsets[k + 1] - itv_offsets[k]) ? 1 : 0;
+    *n_overlapping = c;
+    return GVL_OK;
+}
+
+int gvl_flatten_intervals(const int32_t *itv_starts, const int32_t *itv_ends, const float *itv_values,
+                          const int64_t *itv_offsets, int64_t n_slots, int32_t *out_starts, int32_t *out_ends,
+                          float *out_values, int64_t *out_offsets, int64_t out_cap, int64_t *out_n) {
+    if (!itv_offsets || !out_offsets || !out_n) return fail(GVL_ERR_ARG, "gvl_flatten_intervals: NULL argument");
+    std::vector<int32_t> os, oe;
+    std::vector<float> ov;
+    out_offsets[0] = 0;
+    for (int64_t k = 0; k < n_slots; k++) {
+        const int64_t lo = itv_offsets[k], n = itv_offsets[k + 1] - lo;
+        if (slot_overlaps(itv_starts + lo, itv_ends + lo, n)) {
+            flatten_slot(itv_starts + lo, itv_ends + lo, itv_values + lo, n, os, oe, ov);
+        } else {
+            os.insert(os.end(), itv_starts + lo, itv_starts + lo + n);
+            oe.insert(oe.end(), itv_ends + lo, itv_ends + lo + n);
+            ov.insert(ov.end(), itv_values + lo, itv_values + lo + n);
+        }
+        out_offsets[k + 1] = (int64_t)os.size();
+    }
+    *out_n = (int64_t)os.size();
+    if ((int64_t)os.size() > out_cap) return fail(GVL_ERR_CAPACITY, "gvl_flatten_intervals: %lld intervals, capacity %lld",
+                                                  (long long)os.size(), (long long)out_cap);
+    if (!os.empty()) {
+        if (!out_starts || !out_ends || !out_values) return fail(GVL_ERR_ARG, "gvl_flatten_intervals: NULL output");
+        memcpy(out_starts, os.data(), sizeof(int32_t) * os.size());
+        memcpy(out_ends, oe.data(), sizeof(int32_t) * oe.size());
+        memcpy(out_values, ov.data(), sizeof(float) * ov.size());
+    }
+    return GVL_OK;
+}
 
 int gvl_host_alloc(int64_t bytes, void **out) {
     if (!out) return fail(GVL_ERR_ARG, "gvl_host_alloc: out is NULL");
@@ -658,6 +743,39 @@ static int resolve_intervals(gvl_ctx *ctx, const int32_t *itv_starts, const int3
     return GVL_OK;
 }
 
+// Intervals of ONE call: the caller's arrays when none of the slots the call touches overlaps (the normal case:
+// one scan of those slots, O(the call's own work)); otherwise a private, flattened copy of the touched slots -- one
+// slot per query, `flat_idx` = 0..n_queries-1 replaces the caller's offset_idxs (see the flatten helpers above).
+struct CallIntervals {
+    gvl_intervals iv;
+    std::vector<int32_t> s, e;
+    std::vector<float> v;
+    std::vector<int64_t> off, flat_idx;
+    bool flattened = false;
+};
+
+static int resolve_call_intervals(gvl_ctx *ctx, const int64_t *offset_idxs, int64_t n_queries, const int32_t *itv_starts,
+                                  const int32_t *itv_ends, const float *itv_values, int64_t n_itv,
+                                  const int64_t *itv_offsets, int64_t n_slots, CallIntervals *ci) {
+    bool any = false;
+    for (int64_t q = 0; q < n_queries && !any; q++) {
+        const int64_t k = offset_idxs[q];
+        if (k < 0 || k >= n_slots) return fail(GVL_ERR_ARG, "interval slot %lld of %lld", (long long)k, (long long)n_slots);
+        any = slot_overlaps(itv_starts + itv_offsets[k], itv_ends + itv_offsets[k], itv_offsets[k + 1] - itv_offsets[k]);
+    }
+    if (!any) return resolve_intervals(ctx, itv_starts, itv_ends, itv_values, n_itv, itv_offsets, n_slots, &ci->iv);
+    ci->flattened = true;
+    ci->off.assign(1, 0);
+    for (int64_t q = 0; q < n_queries; q++) {
+        const int64_t k = offset_idxs[q], lo = itv_offsets[k];
+        flatten_slot(itv_starts + lo, itv_ends + lo, itv_values + lo, itv_offsets[k + 1] - lo, ci->s, ci->e, ci->v);
+        ci->off.push_back((int64_t)ci->s.size());
+        ci->flat_idx.push_back(q);
+    }
+    return resolve_intervals(ctx, ci->s.data(), ci->e.data(), ci->v.data(), (int64_t)ci->s.size(), ci->off.data(), n_queries,
+                             &ci->iv);
+}
+
 int gvl_intervals_and_realign_track_fused(
     gvl_ctx *ctx, float *out, const int64_t *out_offsets, const int32_t *regions, const int32_t *shifts,
     const int64_t *geno_offset_idx, int64_t batch, int64_t ploidy, const int32_t *geno_v_idxs, int64_t n_geno_v,
@@ -678,8 +796,11 @@ int gvl_intervals_and_realign_track_fused(
     if ((rc = resolve_tables(ctx, geno_offsets, n_geno, geno_v_idxs, n_geno_v, v_starts, ilens, n_variants, nullptr,
                              nullptr, nullptr, nullptr, 0, &t)))
         return rc;
-    gvl_intervals iv;
-    if ((rc = resolve_intervals(ctx, itv_starts, itv_ends, itv_values, n_itv, itv_offsets, n_slots, &iv))) return rc;
+    CallIntervals ci;
+    if ((rc = resolve_call_intervals(ctx, offset_idxs, batch, itv_starts, itv_ends, itv_values, n_itv, itv_offsets, n_slots, &ci)))
+        return rc;
+    const gvl_intervals &iv = ci.iv;
+    if (ci.flattened) offset_idxs = ci.flat_idx.data();
     std::vector<int32_t> tl((size_t)batch);
     for (int64_t q = 0; q < batch; q++) tl[q] = (int32_t)(track_offsets[q + 1] - track_offsets[q]);
     Packer pk;
@@ -816,8 +937,12 @@ int gvl_intervals_to_tracks(gvl_ctx *ctx, const int64_t *offset_idxs, const int3
     const int64_t total = out_offsets[n_queries];
     if (n_queries == 0 || total == 0) return GVL_OK;
     if (!out) return fail(GVL_ERR_ARG, "gvl_intervals_to_tracks: out is NULL");
-    gvl_intervals iv;
-    if ((rc = resolve_intervals(ctx, itv_starts, itv_ends, itv_values, n_itv, itv_offsets, n_slots, &iv))) return rc;
+    CallIntervals ci;
+    if ((rc = resolve_call_intervals(ctx, offset_idxs, n_queries, itv_starts, itv_ends, itv_values, n_itv, itv_offsets, n_slots,
+                                     &ci)))
+        return rc;
+    const gvl_intervals &iv = ci.iv;
+    if (ci.flattened) offset_idxs = ci.flat_idx.data();
     Packer pk;
     size_t i_oi = pk.add(offset_idxs, sizeof(int64_t) * n_queries);
     size_t i_st = pk.add(starts, sizeof(int32_t) * n_queries);

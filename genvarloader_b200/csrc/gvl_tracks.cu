@@ -16,21 +16,20 @@
 
 namespace gvl {
 
-#ifndef GVL_TRK_TILE
-#define GVL_TRK_TILE 8192
-#endif
-#ifndef GVL_TRK_THREADS
-#define GVL_TRK_THREADS 256
-#endif
-constexpr int TRK_TILE = GVL_TRK_TILE;             // output values per pass of an execute CTA (one staged source window)
-constexpr int TRK_WIN = TRK_TILE + TRK_TILE / 8;   // source-window values staged in shared memory (room for net deletions)
-#ifndef GVL_TRK_SEG_TILES
-#define GVL_TRK_SEG_TILES 8
-#endif
-constexpr int TRK_SEG = GVL_TRK_SEG_TILES * TRK_TILE;       // output values per execute CTA: up to 8 tiles, walked in haplotype order
-constexpr int TRK_MARGIN = 16;             // window starts a little before the first needed value
-constexpr int TRK_THREADS = GVL_TRK_THREADS;
-constexpr int TRK_REC_CAP = 128;
+constexpr int TRK_SEG = 65536;  // output values per execute CTA: 8 passes of 8,192, walked in haplotype order
+
+// One record of a track row (32 bytes, AoS so that a pass's records arrive with ONE bulk copy): the variant writes
+// output positions [a, e) -- DEL: track[vrel] once; INS: e - a of vlen fill values -- and the source resumes at `resume`.
+struct __align__(16) TRec {
+    int32_t a;       // output (haplotype) position of the variant's values
+    int32_t e;       // a + values written (writable_length, src/tracks/mod.rs:329)
+    int32_t resume;  // source position after the variant (v_rel_end, :267)
+    int32_t vrel;    // v_rel_pos (:264)
+    int32_t vlen;    // (possibly shift-trimmed) v_len handed to the fill (:306, :338)
+    int32_t vdiff;   // ilen
+    int32_t pad0, pad1;
+};
+static_assert(sizeof(TRec) == 32, "TRec is a 32-byte record");
 
 // =====================================================================================
 // plan: shift_and_realign_track_core state machine (src/tracks/mod.rs:224-406), one warp per row
@@ -48,12 +47,20 @@ struct TrkPlanParams {
     const int64_t *out_offsets;    // [n_work+1]
     int64_t n_work, ploidy, rec_cap;
     RowPlan *rows;
-    RecArrays rec;
+    TRec *trecs;
     int64_t *words;
     int32_t *row_len;
 };
 
 constexpr int TPLAN_WARPS = 4;
+constexpr int FLAG_JUMPS_PLAN = 1;  // == FLAG_JUMPS of the execute kernel
+
+__device__ __forceinline__ void put_trec(TRec *t, int64_t a, int64_t n, int64_t resume, int64_t vrel, int64_t vlen, int64_t vdiff) {
+    TRec r;
+    r.a = (int32_t)a, r.e = (int32_t)(a + n), r.resume = (int32_t)resume, r.vrel = (int32_t)vrel, r.vlen = (int32_t)vlen;
+    r.vdiff = (int32_t)vdiff, r.pad0 = 0, r.pad1 = 0;
+    *t = r;
+}
 
 __global__ void __launch_bounds__(TPLAN_WARPS * 32) trk_plan_kernel(TrkPlanParams P) {
     const int lane = lane_id();
@@ -79,7 +86,7 @@ __global__ void __launch_bounds__(TPLAN_WARPS * 32) trk_plan_kernel(TrkPlanParam
     TrkState ts;
     trk_init(ts, shift, length);
     int64_t n_emit = 0, track0 = 0, prev_resume = 0;
-    bool done = false;
+    bool done = false, jumps = false;  // jumps: an unsorted list moved the source cursor between emissions
     // chunk loader: variant i = base + lane of the row (positions, ilens, keep flag)
     auto load_chunk = [&](int64_t base, int32_t &pos, int32_t &il, bool &kp) {
         pos = 0, il = 0, kp = false;
@@ -133,12 +140,7 @@ __global__ void __launch_bounds__(TPLAN_WARPS * 32) trk_plan_kernel(TrkPlanParam
                 if (n_emit == 0) track0 = ts.track_idx;  // span_src of the first record
                 if (valid && !overflow) {
                     const int64_t w = rec_off + n_emit + __popc(vmask & ((1u << lane) - 1u));
-                    P.rec.a[w] = (int32_t)a;
-                    P.rec.n[w] = (int32_t)n;
-                    P.rec.src[w] = il;
-                    P.rec.resume[w] = (int32_t)v_end;
-                    P.rec.vidx[w] = (int32_t)v_len;
-                    P.rec.vpos[w] = (int32_t)rel;
+                    put_trec(P.trecs + w, a, n, v_end, rel, v_len, il);
                 }
                 n_emit += __popc(vmask);
                 ts.out_idx = __shfl_sync(0xffffffffu, a + n, last);
@@ -161,26 +163,11 @@ __global__ void __launch_bounds__(TPLAN_WARPS * 32) trk_plan_kernel(TrkPlanParam
             } else if (act == STEP_EMIT) {
                 if (n_emit == 0) track0 = r.span_src;
                 if (n_emit > 0 && r.span_src != prev_resume) {  // unsorted input: jump record
-                    if (lane == t && !overflow) {
-                        int64_t w = rec_off + n_emit;
-                        P.rec.a[w] = (int32_t)(r.a - (r.v_rel_pos - r.span_src));
-                        P.rec.n[w] = 0;
-                        P.rec.src[w] = 0;
-                        P.rec.resume[w] = (int32_t)r.span_src;
-                        P.rec.vidx[w] = 1;
-                        P.rec.vpos[w] = 0;
-                    }
+                    if (lane == t && !overflow) put_trec(P.trecs + rec_off + n_emit, r.a - (r.v_rel_pos - r.span_src), 0, r.span_src, 0, 1, 0);
                     n_emit++;
+                    jumps = true;
                 }
-                if (lane == t && !overflow) {
-                    int64_t w = rec_off + n_emit;
-                    P.rec.a[w] = (int32_t)r.a;
-                    P.rec.n[w] = (int32_t)r.n;
-                    P.rec.src[w] = r.v_diff;
-                    P.rec.resume[w] = (int32_t)r.resume;
-                    P.rec.vidx[w] = (int32_t)r.v_len;
-                    P.rec.vpos[w] = (int32_t)r.v_rel_pos;
-                }
+                if (lane == t && !overflow) put_trec(P.trecs + rec_off + n_emit, r.a, r.n, r.resume, r.v_rel_pos, r.v_len, r.v_diff);
                 n_emit++;
                 prev_resume = r.resume;
                 if (ts.out_idx >= ts.length) done = true;  // :359-361
@@ -195,16 +182,9 @@ __global__ void __launch_bounds__(TPLAN_WARPS * 32) trk_plan_kernel(TrkPlanParam
         if (n_emit == 0) {
             track0 = ts.track_idx;
         } else if (ts.track_idx != prev_resume) {
-            if (lane == 0 && !overflow) {
-                int64_t w = rec_off + n_emit;
-                P.rec.a[w] = (int32_t)imin64(ts.out_idx, length);
-                P.rec.n[w] = 0;
-                P.rec.src[w] = 0;
-                P.rec.resume[w] = (int32_t)ts.track_idx;
-                P.rec.vidx[w] = 1;
-                P.rec.vpos[w] = 0;
-            }
+            if (lane == 0 && !overflow) put_trec(P.trecs + rec_off + n_emit, imin64(ts.out_idx, length), 0, ts.track_idx, 0, 1, 0);
             n_emit++;
+            jumps = true;
         }
     }
     if (lane == 0) {
@@ -214,7 +194,7 @@ __global__ void __launch_bounds__(TPLAN_WARPS * 32) trk_plan_kernel(TrkPlanParam
         rp.rec_off = rec_off;
         rp.length = (int32_t)length;
         rp.contig_len = (int32_t)track_n;
-        rp.lead_pad = 0;
+        rp.lead_pad = jumps ? FLAG_JUMPS_PLAN : 0;  // (track rows carry flags here: see gvl_tracks_exec.cuh)
         rp.ref0 = (int32_t)track0;
         rp.n_rec = overflow ? 0 : (int32_t)n_emit;
         rp.rc = (P.to_rc && P.to_rc[k]) ? 1 : 0;
@@ -301,7 +281,7 @@ struct TrkDesc {
 
 struct TrkExecParams {
     const RowPlan *rows;
-    RecArrays rec;
+    const TRec *trecs;
     const int64_t *tile_off;   // [n_work+1]
     int64_t n_work, ploidy;
     int64_t grid_per_track;    // CTAs per track (upper bound on tiles)
@@ -319,552 +299,7 @@ struct TrkExecParams {
     TrkDesc inl[8];              // (kernel parameters are captured by value: CUDA-graph safe)
 };
 
-struct TrkTileRecs {
-    int32_t a[TRK_REC_CAP + 1];
-    int32_t e[TRK_REC_CAP];
-    int32_t resume[TRK_REC_CAP];
-    int32_t vlen[TRK_REC_CAP];
-    int32_t vrel[TRK_REC_CAP];
-    int32_t vdiff[TRK_REC_CAP];
-};
-
-// value of the painted source track at relative position tp (0 <= tp < track_n), straight from the
-// interval SoA: last interval with start <= q_start + tp, if it also ends after it (intervals are
-// sorted and non-overlapping, src/intervals.rs contract).
-__device__ __forceinline__ float track_at_global(const TrkDesc &T, int64_t lo, int64_t hi, int64_t q_start, int64_t tp) {
-    if (T.dense) return T.dense[lo + tp];  // dense source: `lo` is the window's offset
-    const int64_t g = q_start + tp;
-    int64_t a = lo, b = hi;  // find last i in [lo,hi) with starts[i] <= g
-    while (a < b) {
-        int64_t mid = (a + b) >> 1;
-        if ((int64_t)T.itv_starts[mid] <= g) a = mid + 1; else b = mid;
-    }
-    const int64_t i = a - 1;
-    if (i < lo) return 0.0f;
-    return ((int64_t)T.itv_ends[i] > g) ? T.itv_values[i] : 0.0f;
-}
-
-struct TrkSrc {
-    const float *win;   // shared-memory window
-    int64_t w0, w1;     // window covers source positions [w0, w1)
-    int64_t track_n;
-    const TrkDesc *T;
-    int64_t itv_lo, itv_hi, q_start;
-    __device__ __forceinline__ float at(int64_t tp) const {  // 0 <= tp < track_n expected
-        if (tp >= w0 && tp < w1) return win[tp - w0];
-        if (tp < 0 || tp >= track_n) return 0.0f;  // out of contract in the reference (index panic)
-        return track_at_global(*T, itv_lo, itv_hi, q_start, tp);
-    }
-};
-
-// Lagrange interpolation through K anchors on each side of the insertion (src/tracks/mod.rs:138-188), evaluated at
-// index i of the written values; same operation order as the reference (term = y_a * prod_b (x - x_b) / (x_a - x_b)).
-template <int K>
-__device__ __forceinline__ float lagrange_fill(const TrkSrc &S, int64_t v_len, int64_t v_rel_pos, int64_t i) {
-    double xs[2 * K], ys[2 * K];
-#pragma unroll
-    for (int j = 0; j < K; j++) {
-        xs[j] = -(double)j;
-        ys[j] = (double)S.at(imax64(v_rel_pos - j, 0));
-        xs[K + j] = (double)v_len + (double)j;
-        ys[K + j] = (double)S.at(imin64(v_rel_pos + 1 + j, S.track_n - 1));
-    }
-    const double x = (double)i;
-    double acc = 0.0;
-#pragma unroll
-    for (int a = 0; a < 2 * K; a++) {
-        double term = ys[a];
-#pragma unroll
-        for (int b = 0; b < 2 * K; b++) {
-            if (b == a) continue;
-            term = __dmul_rn(term, __ddiv_rn(__dsub_rn(x, xs[b]), __dsub_rn(xs[a], xs[b])));
-        }
-        acc = __dadd_rn(acc, term);
-    }
-    return (float)acc;
-}
-
-// apply_insertion_fill, src/tracks/mod.rs:87-190, for ONE written value (index i within the write).
-__device__ float insertion_fill_value(const TrkSrc &S, int strategy, double param, int64_t v_len, int64_t v_rel_pos,
-                                      int64_t i, int64_t out_pos, uint64_t base_seed, uint64_t query, uint64_t hap) {
-    if (strategy == GVL_FILL_REPEAT_5P) {
-        return S.at(v_rel_pos);
-    } else if (strategy == GVL_FILL_REPEAT_5P_NORM) {
-        return __fdiv_rn(S.at(v_rel_pos), (float)v_len);  // :115
-    } else if (strategy == GVL_FILL_CONSTANT) {
-        return (float)param;  // :121
-    } else if (strategy == GVL_FILL_FLANK_SAMPLE) {  // :125-137
-        int64_t width = (int64_t)param;
-        int64_t pool_lo = imax64(v_rel_pos - width, 0);
-        int64_t pool_hi = imin64(v_rel_pos + width, S.track_n - 1);
-        uint64_t pool_size = (uint64_t)(pool_hi - pool_lo + 1);
-        uint64_t seed = hash4(base_seed, query, hap, (uint64_t)out_pos);
-        int64_t offset = (int64_t)(seed % pool_size);
-        return S.at(pool_lo + offset);
-    } else {  // GVL_FILL_INTERPOLATE :138-188
-        const int64_t order = (int64_t)param;
-        const int64_t k = (order + 1 + 1) / 2;
-        // k anchors on each side: 2 anchors for order 1, 4 for orders 2 and 3 -- fixed-size instantiations keep the
-        // anchors in registers and let the divisions overlap; the operation order is the reference's
-        return k == 1 ? lagrange_fill<1>(S, v_len, v_rel_pos, i) : lagrange_fill<2>(S, v_len, v_rel_pos, i);
-    }
-}
-
-#ifndef GVL_TRACE
-#define GVL_TRACE 0
-#endif
-#if GVL_TRACE
-__device__ unsigned long long *g_trk_trace = nullptr;  // [n_ctas][64]: per pass 6 globaltimer stamps (trace builds only)
-#define TRK_TR(slot)                                                                                        \
-    do {                                                                                                    \
-        if (g_trk_trace && threadIdx.x == 0 && tr_pass < 10) {                                              \
-            unsigned long long t_;                                                                          \
-            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_));                                           \
-            g_trk_trace[(unsigned long long)blockIdx.x * 64 + tr_pass * 6 + (slot)] = t_;                     \
-        }                                                                                                   \
-    } while (0)
-#else
-#define TRK_TR(slot) do { } while (0)
-#endif
-
-__global__ void __launch_bounds__(TRK_THREADS, 1024 / TRK_THREADS) trk_exec_kernel(TrkExecParams P) {
-#if GVL_TRACE
-    int tr_pass = 0;
-#endif
-    __shared__ TrkTileRecs S;
-    extern __shared__ __align__(16) float s_win[];  // TRK_WIN floats (dynamic: larger than 48 KB in big-pass builds)
-    __shared__ uint32_t s_flag[TRK_WIN / 32 + 4];  // positions of s_win that hold a run start (interval start / end)
-    __shared__ float s_cval[TRK_THREADS / 32];
-    __shared__ int32_t s_gt[TRK_TILE / 128 + 2];  // per group of the pass: window offset of a plain group, or -1
-    __shared__ int s_chas[TRK_THREADS / 32];
-    __shared__ int s_stop;
-    __shared__ int64_t s_lo, s_hi, s_itv_first;
-
-    const int64_t track = blockIdx.x / P.grid_per_track;
-    const int64_t b = blockIdx.x % P.grid_per_track;
-    if (b >= P.tile_off[P.n_work]) return;
-#ifdef GVL_TRK_STAGGER_NS
-    // CTAs that share an SM start GVL_TRK_STAGGER_NS apart, so that one CTA's preparation phases (latency) overlap
-    // another's output phase (bandwidth) instead of all CTAs of the GPU marching in lock-step
-    {
-        unsigned nsm;
-        asm volatile("mov.u32 %0, %nsmid;" : "=r"(nsm));
-        const unsigned phase = (blockIdx.x / nsm) & 3u;
-        if (phase) __nanosleep(phase * GVL_TRK_STAGGER_NS);
-    }
-#endif
-    int64_t row;
-    {
-        int64_t lo = 0, hi = P.n_work;
-        while (hi - lo > 1) {
-            int64_t mid = (lo + hi) >> 1;
-            if (P.tile_off[mid] <= b) lo = mid; else hi = mid;
-        }
-        row = lo;
-    }
-    const int64_t tile = b - P.tile_off[row];
-    const RowPlan rp = P.rows[row];
-    const int32_t L = rp.length;
-    const int32_t t0 = (int32_t)(tile * TRK_SEG);
-    if (t0 >= L) return;
-    const int32_t t1 = (int32_t)imin64((int64_t)t0 + TRK_SEG, L);
-    const bool rc = rp.rc != 0;
-    const int32_t h0 = rc ? L - t1 : t0;
-    const int32_t h1 = rc ? L - t0 : t1;
-    const int64_t query = row / P.ploidy;
-    const uint64_t hap = (uint64_t)(row % P.ploidy);
-    const uint64_t qseed = P.query_seed ? (uint64_t)P.query_seed[query]
-                                        : (uint64_t)(P.sub_batch > 0 ? query % P.sub_batch : query);
-    const uint64_t base_seed = P.base_seed_dev ? P.base_seed_dev[P.sub_batch > 0 ? query / P.sub_batch : 0] : P.base_seed;
-    const TrkDesc T = P.tracks ? P.tracks[track] : P.inl[track];
-    int64_t itv_lo, itv_hi;
-    if (T.dense) {
-        itv_lo = T.dense_offsets[query];
-        itv_hi = T.dense_offsets[query + 1];
-    } else {
-        const int64_t slot = P.offset_idxs[track * P.n_queries + query];
-        itv_lo = T.itv_offsets[slot];
-        itv_hi = T.itv_offsets[slot + 1];
-    }
-    const int64_t track_n = rp.contig_len;
-    const int64_t q_start = rp.q_start;
-    float *__restrict__ out = P.out;
-    int64_t row_base = track * P.total_per_track + rp.out_off;  // flat index of the row's first value
-    if (P.layout_btp) {  // all tracks of a query are adjacent: block of the query, then track, then the row inside the block
-        const int64_t k0 = query * P.ploidy;
-        const int64_t blk0 = P.rows[k0].out_off;
-        const int64_t blk_len = P.rows[k0 + P.ploidy - 1].out_off + P.rows[k0 + P.ploidy - 1].length - blk0;
-        row_base = P.n_tracks * blk0 + track * blk_len + (rp.out_off - blk0);
-    }
-
-    const int32_t *__restrict__ ra = P.rec.a + rp.rec_off;
-    if (threadIdx.x < 32) {
-        // r_lo = last record with a <= h0 (or -1), r_hi = first with a >= h1: counts over the sorted array,
-        // 8 independent loads per lane and round trip
-        const int lane = threadIdx.x;
-        int64_t r_lo, r_hi;
-        if (rp.n_rec <= 2048) {
-            int c0 = 0, c1 = 0;
-            for (int i0 = 0; i0 < rp.n_rec; i0 += 256) {
-                int32_t a[8];
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int i = i0 + 32 * u + lane;
-                    a[u] = i < rp.n_rec ? ra[i] : INT32_MAX;
-                }
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    c0 += (a[u] <= h0);
-                    c1 += (a[u] < h1);
-                }
-            }
-            r_lo = (int64_t)__reduce_add_sync(0xffffffffu, c0) - 1;
-            r_hi = __reduce_add_sync(0xffffffffu, c1);
-        } else {
-            r_lo = warp_upper_le(ra, 0, rp.n_rec, h0);
-            r_hi = warp_upper_le(ra, imax64(r_lo, 0), rp.n_rec, h1 - 1) + 1;
-        }
-        if (threadIdx.x == 0) {
-            s_lo = r_lo;
-            s_hi = r_hi;
-        }
-    }
-    __syncthreads();
-    const int64_t r_hi = s_hi;
-    int64_t r = s_lo;
-    int32_t cur = h0;
-    int64_t itv_prev = -1;  // first interval of the previous pass's window (-1: none yet)
-    int32_t tgt_prev = INT32_MIN;
-
-    while (cur < h1) {
-        TRK_TR(0);
-        const int m_new = (int)imin64(TRK_REC_CAP - 1, r_hi - (r + 1));
-        const int m = m_new + 1;
-        const int32_t seg_end_rec = (r + 1 + m_new < r_hi) ? ra[r + 1 + m_new] : h1;
-        // a pass ends at the first unstaged record, after TRK_TILE values (one source window), or at the segment end
-        const int32_t seg_end = (int32_t)imin64(seg_end_rec, (int64_t)cur + TRK_TILE);
-        if (seg_end <= cur) {  // (only with > 127 records at one position: skip them, nothing to write)
-            r += m_new;
-            continue;
-        }
-        // Later passes: the window only moves forward, so the intervals it needs start at the previous pass's
-        // cursor.  Their loads are issued here, together with the record loads below (one round trip, not three).
-        int32_t pre_st = INT32_MAX, pre_en = 0;
-        float pre_v = 0.0f;
-        const bool pre_ok = !T.dense && itv_prev >= 0;
-        if (pre_ok && itv_prev + (int64_t)threadIdx.x < itv_hi) {
-            const int64_t it = itv_prev + threadIdx.x;
-            pre_st = T.itv_starts[it];
-            pre_en = T.itv_ends[it];
-            pre_v = T.itv_values[it];
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < m; i += TRK_THREADS) {
-            int64_t idx = r + i;
-            if (idx < 0) {
-                S.a[0] = 0;
-                S.e[0] = 0;
-                S.resume[0] = rp.ref0;
-                S.vlen[0] = 1;
-                S.vrel[0] = 0;
-                S.vdiff[0] = 0;
-            } else {
-                int64_t g = rp.rec_off + idx;
-                int32_t a = P.rec.a[g], n = P.rec.n[g];
-                S.a[i] = a;
-                S.e[i] = a + n;
-                S.resume[i] = P.rec.resume[g];
-                S.vlen[i] = P.rec.vidx[g];
-                S.vrel[i] = P.rec.vpos[g];
-                S.vdiff[i] = (int32_t)P.rec.src[g];
-            }
-        }
-        if (threadIdx.x == 0) S.a[m] = INT32_MAX;
-        __syncthreads();
-
-        TRK_TR(1);
-        // ---- source window: starts at the source position of `cur` (minus a margin) ----
-        // source position feeding `cur`: inside the carry record's own values the reads go to
-        // track[v_rel_pos] and then continue at its resume point; otherwise we are in its span.
-        const int64_t src_cur = (cur < S.e[0]) ? imin64((int64_t)S.vrel[0], (int64_t)S.resume[0])
-                                               : (int64_t)S.resume[0] + (cur - S.e[0]);
-        const int64_t w0 = imax64(src_cur - TRK_MARGIN, 0);
-        const int64_t w1 = imin64(w0 + TRK_WIN, track_n);
-        if (T.dense) {
-            for (int64_t i = threadIdx.x; i < w1 - w0; i += TRK_THREADS) s_win[i] = T.dense[itv_lo + w0 + i];
-        } else {
-            for (int i = threadIdx.x; i < TRK_WIN / 32 + 4; i += TRK_THREADS) s_flag[i] = 0u;
-        }
-        const int32_t target = (int32_t)imin64(q_start + w0, INT32_MAX);  // intervals ending at or before it are behind the window
-        const bool spec = pre_ok && target >= tgt_prev;  // (unsorted lists can move the window backwards: search again)
-        if (!T.dense && !spec && threadIdx.x < 32) {
-            // first interval whose end is > q_start + w0 (ends are sorted: intervals do not overlap)
-            const int64_t first = warp_upper_le(T.itv_ends, itv_lo, itv_hi, target) + 1;
-            if (threadIdx.x == 0) s_itv_first = first;
-        }
-        __syncthreads();
-        TRK_TR(2);
-#ifndef GVL_TRK_EXP
-#define GVL_TRK_EXP 0
-#endif
-        if (!(GVL_TRK_EXP & 1) && !T.dense && w1 > w0) {
-            // Paint the window as a run-length expansion (src/intervals.rs:19-126 restated for one window):
-            //  1. every thread holds ONE interval (coalesced loads) and drops two markers: 0 at its end, its value at
-            //     its (clipped) start -- ends first, so that an adjacent interval's start wins;
-            //  2. every thread then owns 36 consecutive window positions, finds the value in effect at its first
-            //     position with a block-wide scan over "last marker" pairs, and fills.
-            const int nwin = (int)(w1 - w0);
-            int64_t base = spec ? itv_prev : s_itv_first;
-            int64_t first = base;      // cursor for the next pass: intervals before it end at or before `target`
-            bool counting = true;
-            for (bool use_pre = spec;; use_pre = false) {
-                const int64_t it = base + threadIdx.x;
-                int32_t st_a = INT32_MAX, en_a = 0;
-                float v_ = 0.0f;
-                if (use_pre) {
-                    st_a = pre_st, en_a = pre_en, v_ = pre_v;
-                } else if (it < itv_hi) {
-                    st_a = T.itv_starts[it];
-                    en_a = T.itv_ends[it];
-                    v_ = T.itv_values[it];
-                }
-                const int64_t st_ = (int64_t)st_a - q_start, en_ = (int64_t)en_a - q_start;
-                const bool have = it < itv_hi;
-                const bool live = have && st_ < w1 && en_ > w0 && en_ > st_;  // overlaps the window (also :72-76: start >= length)
-                if (live && en_ < w1) {
-                    const int x = (int)(en_ - w0);
-                    s_win[x] = 0.0f;
-                    atomicOr(&s_flag[x >> 5], 1u << (x & 31));
-                }
-                if (threadIdx.x == TRK_THREADS - 1) s_stop = (!have || st_ >= w1);  // sorted starts: the block's last interval decides
-                const int behind = __syncthreads_count(have && en_a <= target);  // (also orders the two marker phases)
-                if (counting) {
-                    first += behind;
-                    counting = behind == TRK_THREADS;
-                }
-                if (live) {
-                    const int x = (int)(imax64(st_, w0) - w0);
-                    s_win[x] = v_;
-                    atomicOr(&s_flag[x >> 5], 1u << (x & 31));
-                }
-                if (s_stop) break;  // the block's LAST interval starts at or beyond the window end
-                __syncthreads();    // (rare second block: s_stop is rewritten)
-                base += TRK_THREADS;
-            }
-            if (threadIdx.x == 0) s_itv_first = first;
-            __syncthreads();
-            TRK_TR(3);
-            constexpr int CH = 36;  // 9 float4 per thread: conflict-free 128-bit accesses, 36 * 256 = TRK_WIN
-            static_assert(CH * TRK_THREADS >= TRK_WIN && CH % 4 == 0, "fill chunks must cover the window");
-            const int b0 = CH * (int)threadIdx.x;
-            const bool act = b0 < nwin;
-            uint64_t mk = 0;  // marker bits of positions b0 .. b0 + 35
-            if (act) {
-                const int w = b0 >> 5, sft = b0 & 31;
-                mk = (((uint64_t)s_flag[w + 1] << 32) | s_flag[w]) >> sft;
-                if (sft) mk |= (uint64_t)s_flag[w + 2] << (64 - sft);
-                mk &= (1ull << CH) - 1;
-            }
-            float x[CH];
-            if (act) {
-#pragma unroll
-                for (int q = 0; q < CH / 4; q++) {
-                    const float4 v4 = *reinterpret_cast<const float4 *>(&s_win[b0 + 4 * q]);
-                    x[4 * q] = v4.x, x[4 * q + 1] = v4.y, x[4 * q + 2] = v4.z, x[4 * q + 3] = v4.w;
-                }
-            }
-            // (has, value) of the last marker in the chunk; scan with "right operand wins if it has one"
-            const int has = mk != 0;
-            const float val = has ? s_win[b0 + 63 - __clzll((long long)mk)] : 0.0f;
-            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-            int h_in = has;
-            float v_in = val;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int h2 = __shfl_up_sync(0xffffffffu, h_in, o);
-                const float v2 = __shfl_up_sync(0xffffffffu, v_in, o);
-                if (lane >= o && !h_in) {
-                    h_in = h2;
-                    v_in = v2;
-                }
-            }
-            if (lane == 31) {
-                s_chas[warp] = h_in;
-                s_cval[warp] = v_in;
-            }
-            int h_ex = __shfl_up_sync(0xffffffffu, h_in, 1);
-            float v_ex = __shfl_up_sync(0xffffffffu, v_in, 1);
-            if (lane == 0) h_ex = 0;
-            __syncthreads();
-            float carry = 0.0f;  // no marker before: nothing covers the window start
-            int found = h_ex;
-            if (found) carry = v_ex;
-            for (int w = warp - 1; w >= 0 && !found; w--) {
-                if (s_chas[w]) {
-                    carry = s_cval[w];
-                    found = 1;
-                }
-            }
-            if (act) {
-                float cur_v = carry;
-                const uint32_t mk_lo = (uint32_t)mk, mk_hi = (uint32_t)(mk >> 32);
-#pragma unroll
-                for (int q = 0; q < CH; q++) {
-                    const bool f = q < 32 ? ((mk_lo >> q) & 1u) : ((mk_hi >> (q - 32)) & 1u);
-                    cur_v = f ? x[q] : cur_v;
-                    x[q] = cur_v;
-                }
-#pragma unroll
-                for (int q = 0; q < CH / 4; q++)
-                    *reinterpret_cast<float4 *>(&s_win[b0 + 4 * q]) = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
-            }
-        }
-        __syncthreads();
-        TRK_TR(4);
-        itv_prev = T.dense ? -1 : s_itv_first;
-        tgt_prev = (int32_t)imin64(q_start + w0, INT32_MAX);
-        TrkSrc src{s_win, w0, w1, track_n, &T, itv_lo, itv_hi, q_start};
-
-        const int32_t jo_lo = rc ? L - seg_end : cur;
-        const int32_t jo_hi = rc ? L - cur : seg_end;
-        const int64_t g0 = (row_base + jo_lo) & ~(int64_t)3;
-        const int32_t n_chunks = (int32_t)((row_base + jo_hi - g0 + 3) >> 2);
-        // a GROUP is 32 chunks of 4 values (one chunk per lane); warp w owns groups w, w+8, ...  A group that lies
-        // inside ONE reference span and inside the staged window is a straight (possibly reversed) copy out of
-        // shared memory: one thread per group decides that up front (group table), so the copy loop itself is a
-        // table read, four shared-memory reads and one 16-byte store per lane.
-        const int warp_ = threadIdx.x >> 5, lane_ = threadIdx.x & 31;
-        const int32_t n_groups = (n_chunks + 31) >> 5;
-        if ((int)threadIdx.x < n_groups) {
-            const int32_t jg = (int32_t)(g0 + 128 * (int64_t)threadIdx.x - row_base);
-            int32_t off = -1;
-            if (jg >= jo_lo && jg + 128 <= jo_hi) {
-                const int32_t p_lo = rc ? (L - 128 - jg) : jg;  // lowest haplotype position of the group
-                int lo = 0, hi = m;
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (S.a[mid] <= p_lo) lo = mid; else hi = mid;
-                }
-                const int32_t e_i = S.e[lo];
-                const int64_t tp_lo = (int64_t)S.resume[lo] + (p_lo - e_i);
-                if (p_lo >= e_i && p_lo + 128 <= S.a[lo + 1] && tp_lo >= w0 && tp_lo + 128 <= w1) off = (int32_t)(tp_lo - w0);
-            }
-            s_gt[threadIdx.x] = off;
-        }
-        __syncthreads();
-        // copy loop of the plain groups: lane l moves values l, l+32, l+64, l+96 of a group, so every shared-memory
-        // read and every store is one contiguous 128-byte warp access (4 consecutive values per lane would be a 4-way
-        // bank conflict); pointers are hoisted, the two directions are separate loops (constant offsets)
-        {
-            float *const og_lane = out + g0 + lane_;
-            if (!rc) {
-                const float *const ws_lane = s_win + lane_;
-#pragma unroll 2
-                for (int32_t grp = warp_; grp < n_groups; grp += TRK_THREADS / 32) {
-                    const int32_t off = s_gt[grp];
-                    if (off < 0) continue;
-                    const float *ws = ws_lane + off;
-                    const float v0 = ws[0], v1 = ws[32], v2 = ws[64], v3 = ws[96];
-                    float *og = og_lane + 128 * grp;
-                    if ((GVL_TRK_EXP & 2) && v0 != 123.456f) continue;
-                    og[0] = v0, og[32] = v1, og[64] = v2, og[96] = v3;
-                }
-            } else {
-                const float *const ws_lane = s_win + 127 - lane_;
-#pragma unroll 2
-                for (int32_t grp = warp_; grp < n_groups; grp += TRK_THREADS / 32) {
-                    const int32_t off = s_gt[grp];
-                    if (off < 0) continue;
-                    const float *ws = ws_lane + off;
-                    const float v0 = ws[0], v1 = ws[-32], v2 = ws[-64], v3 = ws[-96];
-                    float *og = og_lane + 128 * grp;
-                    if ((GVL_TRK_EXP & 2) && v0 != 123.456f) continue;
-                    og[0] = v0, og[32] = v1, og[64] = v2, og[96] = v3;
-                }
-            }
-        }
-        for (int32_t grp = warp_; grp < n_groups; grp += TRK_THREADS / 32) {
-            if (s_gt[grp] >= 0) continue;  // copied above
-            const int32_t c = grp * 32 + lane_;
-            const int64_t g = g0 + 4 * (int64_t)c;
-            const int32_t j = (int32_t)(g - row_base);
-            if (c >= n_chunks) continue;
-            // lane-level fast path: the lane's 4 values lie inside one reference span and inside the window
-            if (j >= jo_lo && j + 4 <= jo_hi) {
-                const int32_t p4 = rc ? (L - 4 - j) : j;  // lowest haplotype position of the chunk
-                int lo = 0, hi = m;
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (S.a[mid] <= p4) lo = mid; else hi = mid;
-                }
-                const int32_t e_l = S.e[lo];
-                const int64_t tp4 = (int64_t)S.resume[lo] + (p4 - e_l);
-                if (p4 >= e_l && p4 + 4 <= S.a[lo + 1] && tp4 >= w0 && tp4 + 4 <= w1) {
-                    const float *ws = s_win + (tp4 - w0);
-                    *reinterpret_cast<float4 *>(out + g) =
-                        rc ? make_float4(ws[3], ws[2], ws[1], ws[0]) : make_float4(ws[0], ws[1], ws[2], ws[3]);
-                    continue;
-                }
-            }
-            float vals[4];
-            bool valid[4];
-            int i = 0;
-            bool have_i = false;
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int32_t jj = j + q;
-                valid[q] = (jj >= jo_lo) && (jj < jo_hi);
-                vals[q] = 0.0f;
-                if (!valid[q]) continue;
-                const int32_t p = rc ? (L - 1 - jj) : jj;
-                if (!have_i || p < S.a[i] || p >= S.a[i + 1]) {
-                    int lo = 0, hi = m;
-                    while (hi - lo > 1) {
-                        int mid = (lo + hi) >> 1;
-                        if (S.a[mid] <= p) lo = mid; else hi = mid;
-                    }
-                    i = lo;
-                    have_i = true;
-                }
-                if (p < S.e[i]) {
-                    // values written by the variant itself (:329-354)
-                    const int64_t vrel = S.vrel[i];
-                    if (S.vdiff[i] > 0 && T.strategy != GVL_FILL_REPEAT_5P) {
-                        vals[q] = insertion_fill_value(src, T.strategy, T.param, S.vlen[i], vrel, p - S.a[i], p,
-                                                       base_seed, qseed, hap);
-                    } else {
-                        vals[q] = src.at(vrel);
-                    }
-                } else {
-                    const int64_t tp = (int64_t)S.resume[i] + (p - S.e[i]);
-                    vals[q] = (tp < track_n) ? src.at(tp) : 0.0f;  // :381-404 trailing zeros
-                }
-            }
-            if (valid[0] && valid[1] && valid[2] && valid[3]) {
-                *reinterpret_cast<float4 *>(out + g) = make_float4(vals[0], vals[1], vals[2], vals[3]);
-            } else {
-#pragma unroll
-                for (int q = 0; q < 4; q++)
-                    if (valid[q]) out[g + q] = vals[q];
-            }
-        }
-#if GVL_TRACE
-        __syncthreads();
-        TRK_TR(5);
-        tr_pass++;
-#endif
-        // records consumed by this pass: staged entries 1..m_new with a < seg_end (the rest are staged again)
-        {
-            int lo = 0, hi = m;  // last staged entry with a < seg_end
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (S.a[mid] < seg_end) lo = mid; else hi = mid;
-            }
-            r += lo;
-        }
-        cur = seg_end;
-    }
-}
+#include "gvl_tracks_exec.cuh"
 
 __global__ void prng_kernel(uint64_t a, uint64_t b, uint64_t c, uint64_t d, int which, uint64_t *out) {
     *out = which ? hash4(a, b, c, d) : xorshift64(a);
@@ -889,7 +324,7 @@ static int launch_trk_exec(gvl_ctx *ctx, int64_t n_work, int64_t ploidy, int64_t
     GVL_LAUNCH_CHECK();
     TrkExecParams P;
     P.rows = ctx->trk.rows;
-    P.rec = ctx->trk.rec;
+    P.trecs = (const TRec *)ctx->trk.trecs;
     P.tile_off = ctx->trk.tile_off;
     P.n_work = n_work;
     P.ploidy = ploidy;
@@ -910,10 +345,13 @@ static int launch_trk_exec(gvl_ctx *ctx, int64_t n_work, int64_t ploidy, int64_t
     const int64_t grid = P.grid_per_track * n_tracks;
     if (grid > INT32_MAX) return fail(GVL_ERR_ARG, "too many track tiles");
     static const bool smem_ok = [] {
-        return cudaFuncSetAttribute(trk_exec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * TRK_WIN)) == cudaSuccess;
+        return cudaFuncSetAttribute(trk_exec2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(T2Smem)) == cudaSuccess;
     }();
-    if (!smem_ok) return fail(GVL_ERR_CUDA, "trk_exec_kernel: cannot reserve %d bytes of shared memory", (int)(sizeof(float) * TRK_WIN));
-    trk_exec_kernel<<<(unsigned)grid, TRK_THREADS, sizeof(float) * TRK_WIN, st>>>(P);
+    if (!smem_ok) return fail(GVL_ERR_CUDA, "trk_exec2_kernel: cannot reserve %d bytes of shared memory", (int)sizeof(T2Smem));
+    for (int64_t t = 0; t < n_tracks; t++)  // the staged slices travel by 16-byte aligned bulk copies
+        if (!host_desc[t].dense && (((uintptr_t)host_desc[t].itv_starts | (uintptr_t)host_desc[t].itv_ends | (uintptr_t)host_desc[t].itv_values) & 15))
+            return fail(GVL_ERR_ARG, "interval arrays must be 16-byte aligned");
+    trk_exec2_kernel<<<(unsigned)grid, T2_THREADS, sizeof(T2Smem), st>>>(P);
     GVL_LAUNCH_CHECK();
     return GVL_OK;
 }
@@ -943,7 +381,7 @@ static int realign_impl(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_sv
     if (!out || ((uintptr_t)out & 15)) return fail(GVL_ERR_ARG, "gvl_dev_realign_tracks: out must be 16-byte aligned");
     int rc;
     if ((rc = ensure_rows(ctx, ctx->trk, n_work))) return rc;
-    if ((rc = ensure_records(ctx, ctx->trk, max_records + n_work))) return rc;
+    if ((rc = ensure_trecs(ctx, ctx->trk, max_records + n_work))) return rc;
     int64_t *words = ctx->dev_words + W_COUNT;  // (left at zero by the previous plan, see plan_row_done)
     TrkPlanParams PP;
     PP.tab = *tab;
@@ -963,9 +401,9 @@ static int realign_impl(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_sv
     PP.out_offsets = out_offsets;
     PP.n_work = n_work;
     PP.ploidy = ploidy;
-    PP.rec_cap = ctx->trk.rec_cap;
+    PP.rec_cap = ctx->trk.trec_cap;
     PP.rows = ctx->trk.rows;
-    PP.rec = ctx->trk.rec;
+    PP.trecs = (TRec *)ctx->trk.trecs;
     PP.words = words;
     PP.row_len = ctx->trk.row_len;
     trk_plan_kernel<<<(unsigned)((n_work + TPLAN_WARPS - 1) / TPLAN_WARPS), TPLAN_WARPS * 32, 0, st>>>(PP);
@@ -1063,7 +501,7 @@ int gvl_dev_intervals_to_tracks(gvl_ctx *ctx, const gvl_intervals *itv, const in
     if (!out || ((uintptr_t)out & 15)) return fail(GVL_ERR_ARG, "gvl_dev_intervals_to_tracks: out must be 16-byte aligned");
     int rc;
     if ((rc = ensure_rows(ctx, ctx->trk, n_queries))) return rc;
-    if ((rc = ensure_records(ctx, ctx->trk, 1))) return rc;
+    if ((rc = ensure_trecs(ctx, ctx->trk, 1))) return rc;
     paint_plan_kernel<<<(unsigned)((n_queries + 255) / 256), 256, 0, st>>>(n_queries, starts, out_offsets, nullptr,
                                                                             ctx->trk.rows, ctx->trk.row_len);
     GVL_LAUNCH_CHECK();
@@ -1091,7 +529,7 @@ int gvl_dev_paint_tracks(gvl_ctx *ctx, int64_t n_tracks, const gvl_intervals *it
     if (!out || ((uintptr_t)out & 15)) return fail(GVL_ERR_ARG, "gvl_dev_paint_tracks: out must be 16-byte aligned");
     int rc;
     if ((rc = ensure_rows(ctx, ctx->trk, n_queries))) return rc;
-    if ((rc = ensure_records(ctx, ctx->trk, 1))) return rc;
+    if ((rc = ensure_trecs(ctx, ctx->trk, 1))) return rc;
     paint_plan_kernel<<<(unsigned)((n_queries + 255) / 256), 256, 0, st>>>(n_queries, starts, out_offsets, to_rc,
                                                                             ctx->trk.rows, ctx->trk.row_len);
     GVL_LAUNCH_CHECK();

@@ -95,7 +95,9 @@ typedef struct {
 int64_t gvl_packed_reference_words(int64_t n_bases);
 int gvl_dev_pack_reference(gvl_ctx *ctx, const uint8_t *ref, int64_t n_bases, uint32_t *ref_packed, gvl_stream stream);
 
-/* Per-track interval SoA (python/genvarloader/_dataset/_tracks.py:327-339). */
+/* Per-track interval SoA (python/genvarloader/_dataset/_tracks.py:327-339).  Device layer: the three arrays are 16-byte
+ * aligned and readable up to the next multiple of 16 bytes; every slot is sorted by start and free of overlaps
+ * (gvl_flatten_intervals). */
 typedef struct {
     const int32_t *itv_starts;
     const int32_t *itv_ends;
@@ -339,6 +341,18 @@ int gvl_dev_upload(gvl_ctx *ctx, void *dev, const void *host, int64_t bytes, gvl
  * `_ffi_array` guards (python/genvarloader/_dataset/_utils.py:13-35). */
 int gvl_pin_static(gvl_ctx *ctx, const void *host_ptr, int64_t bytes);
 int gvl_unpin_static(gvl_ctx *ctx, const void *host_ptr);
+/* Overlapping intervals.  The reference paints a slot's intervals in stored order, later ones overwriting earlier ones
+ * (src/intervals.rs:64-85), so overlaps are legal data (annotation tables are sorted by start, never merged).  The
+ * execute kernel paints a run-length code over DISJOINT intervals: gvl_flatten_intervals rewrites every overlapping slot
+ * as the equivalent disjoint, sorted list (other slots are copied).  Host arrays; out arrays need room for out_cap
+ * intervals (2 * n_itv always suffices; GVL_ERR_CAPACITY with *out_n = the size needed otherwise), out_offsets i64[n_slots+1].
+ * The gvl_* host entries do this themselves for the slots a call touches; callers of gvl_dev_* upload flattened tables
+ * (`Engine.add_track` does). */
+int gvl_intervals_overlap(const int32_t *itv_starts, const int32_t *itv_ends, const int64_t *itv_offsets, int64_t n_slots,
+                          int64_t *n_overlapping);
+int gvl_flatten_intervals(const int32_t *itv_starts, const int32_t *itv_ends, const float *itv_values,
+                          const int64_t *itv_offsets, int64_t n_slots, int32_t *out_starts, int32_t *out_ends,
+                          float *out_values, int64_t *out_offsets, int64_t out_cap, int64_t *out_n);
 /* Page-locked host memory for per-call inputs/outputs (full PCIe rate on the D2H copies). */
 int gvl_host_alloc(int64_t bytes, void **out);
 int gvl_host_free(void *p);

@@ -33,7 +33,7 @@ def _workload(name):
     import bench
 
     w, d = bench.build_workload(name, 2)
-    b = bench.make_batches(d, w, 1, 3)[0]
+    b = bench.host_batches(d, w, 1, 3)[0]
     args = (b["regions"], b["shifts"], b["goi"], d.geno_offsets, d.geno_v_idxs, d.v_starts, d.ilens, d.alt_alleles,
             d.alt_offsets, d.reference, d.ref_offsets, N)
     return w, d, b, args

@@ -89,6 +89,8 @@ struct gvl_workspace {
     // track plans: 32-byte AoS records (gvl_tracks.cu: TrkRec)
     void *trecs;
     int64_t trec_cap;
+    void *tdesc;        // per (track, tile) descriptors of the track execute kernel (96 bytes each)
+    int64_t tdesc_cap;
 };
 
 struct gvl_ctx {

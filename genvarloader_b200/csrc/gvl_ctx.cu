@@ -95,7 +95,20 @@ int ensure_trecs(gvl_ctx *ctx, gvl_workspace &ws, int64_t n) {
     return GVL_OK;
 }
 
+int ensure_tdesc(gvl_ctx *ctx, gvl_workspace &ws, int64_t n) {
+    (void)ctx;
+    if (n <= ws.tdesc_cap) return GVL_OK;
+    GVL_CUDA(cudaDeviceSynchronize());
+    int64_t cap = n + n / 2 + 256;
+    if (ws.tdesc) GVL_CUDA(cudaFree(ws.tdesc));
+    ws.tdesc = nullptr;
+    GVL_CUDA(cudaMalloc(&ws.tdesc, 96 * (size_t)cap));
+    ws.tdesc_cap = cap;
+    return GVL_OK;
+}
+
 static void free_workspace(gvl_workspace &ws) {
+    cudaFree(ws.tdesc);
     cudaFree(ws.trecs);
     cudaFree(ws.dir);
     cudaFree(ws.m_pos);

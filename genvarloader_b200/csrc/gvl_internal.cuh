@@ -11,6 +11,7 @@ int ensure_records(gvl_ctx *ctx, gvl_workspace &ws, int64_t n_rec);
 int ensure_merged(gvl_ctx *ctx, gvl_workspace &ws, int64_t n);
 int ensure_dir(gvl_ctx *ctx, gvl_workspace &ws, int64_t n);
 int ensure_trecs(gvl_ctx *ctx, gvl_workspace &ws, int64_t n);
+int ensure_tdesc(gvl_ctx *ctx, gvl_workspace &ws, int64_t n);
 int ensure_zeros(gvl_ctx *ctx, int64_t bytes, cudaStream_t st);
 
 #define GVL_CUDA(expr)                                                                                  \

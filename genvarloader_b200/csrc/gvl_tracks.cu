@@ -16,7 +16,7 @@
 
 namespace gvl {
 
-constexpr int TRK_SEG = 65536;  // output values per execute CTA: 8 passes of 8,192, walked in haplotype order
+constexpr int TRK_TILE = 8192;  // output values per execute CTA (one tile of one (track, row))
 
 // One record of a track row (32 bytes, AoS so that a pass's records arrive with ONE bulk copy): the variant writes
 // output positions [a, e) -- DEL: track[vrel] once; INS: e - a of vlen fill values -- and the source resumes at `resume`.
@@ -228,7 +228,7 @@ __global__ void paint_plan_kernel(int64_t n, const int32_t *__restrict__ starts,
     row_len[q] = (int32_t)length;
 }
 
-// tile map for TRK_SEG-sized segments (same scan as the haplotype path, different tile size)
+// tile map for TRK_TILE-sized tiles (same scan as the haplotype path, different tile size)
 __global__ void __launch_bounds__(1024) trk_tile_scan_kernel(int64_t n_work, const int32_t *__restrict__ row_len,
                                                              int64_t *tile_off) {
     __shared__ int64_t s_tile[32];
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(1024) trk_tile_scan_kernel(int64_t n_work, con
     __syncthreads();
     for (int64_t base = 0; base < n_work; base += 1024) {
         int64_t k = base + tid;
-        int64_t til = (k < n_work) ? ((int64_t)row_len[k] + TRK_SEG - 1) / TRK_SEG : 0;
+        int64_t til = (k < n_work) ? ((int64_t)row_len[k] + TRK_TILE - 1) / TRK_TILE : 0;
         int64_t x = til;
         for (int o = 1; o < 32; o <<= 1) {
             int64_t y = __shfl_up_sync(0xffffffffu, x, o);
@@ -328,7 +328,7 @@ static int launch_trk_exec(gvl_ctx *ctx, int64_t n_work, int64_t ploidy, int64_t
     P.tile_off = ctx->trk.tile_off;
     P.n_work = n_work;
     P.ploidy = ploidy;
-    P.grid_per_track = total_per_track / TRK_SEG + n_work;
+    P.grid_per_track = total_per_track / TRK_TILE + n_work;
     P.total_per_track = total_per_track;
     P.n_tracks = n_tracks;
     P.layout_btp = layout_btp;
@@ -344,14 +344,12 @@ static int launch_trk_exec(gvl_ctx *ctx, int64_t n_work, int64_t ploidy, int64_t
         for (int64_t t = 0; t < n_tracks; t++) P.inl[t] = host_desc[t];
     const int64_t grid = P.grid_per_track * n_tracks;
     if (grid > INT32_MAX) return fail(GVL_ERR_ARG, "too many track tiles");
-    static const bool smem_ok = [] {
-        return cudaFuncSetAttribute(trk_exec2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(T2Smem)) == cudaSuccess;
-    }();
-    if (!smem_ok) return fail(GVL_ERR_CUDA, "trk_exec2_kernel: cannot reserve %d bytes of shared memory", (int)sizeof(T2Smem));
-    for (int64_t t = 0; t < n_tracks; t++)  // the staged slices travel by 16-byte aligned bulk copies
-        if (!host_desc[t].dense && (((uintptr_t)host_desc[t].itv_starts | (uintptr_t)host_desc[t].itv_ends | (uintptr_t)host_desc[t].itv_values) & 15))
-            return fail(GVL_ERR_ARG, "interval arrays must be 16-byte aligned");
-    trk_exec2_kernel<<<(unsigned)grid, T2_THREADS, sizeof(T2Smem), st>>>(P);
+    int rc;
+    if ((rc = ensure_tdesc(ctx, ctx->trk, grid))) return rc;
+    TileDesc *tdesc = (TileDesc *)ctx->trk.tdesc;
+    trk_tile_prep_kernel<<<(unsigned)((grid + 127) / 128), 128, 0, st>>>(P, tdesc);
+    GVL_LAUNCH_CHECK();
+    trk_exec3_kernel<<<(unsigned)grid, T2_THREADS, 0, st>>>(P, tdesc);
     GVL_LAUNCH_CHECK();
     return GVL_OK;
 }

@@ -1,69 +1,72 @@
-// gvl_tracks_exec.cuh -- execute kernel of the track path (included by gvl_tracks.cu, inside `namespace gvl`).
+// gvl_tracks_exec.cuh -- tile preparation + execute kernels of the track path (included by gvl_tracks.cu, inside
+// `namespace gvl`).
 //
 // Reference path replaced: intervals_to_tracks (src/intervals.rs:19-126) into a dense scratch, then
 // shift_and_realign_track_core (src/tracks/mod.rs:224-406) + apply_insertion_fill (:87-190) + the reversal of
 // negative-strand rows (src/reverse.rs:25-38).
 //
-// One CTA owns a segment of up to T2_SEG output values of one (track, row) and walks it in haplotype order in passes
-// of T2_PASS values.  A pass never materialises the source window: the stored intervals are painted DIRECTLY IN
-// OUTPUT COORDINATES as a run-length code --
+// The output of one (track, row) is cut into TILES of T3_TILE values; every tile is independent:
 //
-//   inputs   the pass's records (32-byte AoS written by the plan) and its slice of the interval SoA arrive in shared
-//            memory by 1-D TMA bulk copies (cp.async.bulk + mbarrier) that thread 0 issued during the PREVIOUS pass,
-//            so no thread waits on a global load;
-//   markers  one thread per stored interval maps its two boundaries from source to haplotype coordinates (a
-//            translation per reference span; boundaries inside a deletion vanish) and drops a marker -- the value in
-//            effect from there on -- into `val[]` plus a bit into a two-level bitmap; one thread per record drops the
-//            value in effect right after the variant (found by a search of the staged intervals) and flags the
-//            positions an insertion fill has to compute;
-//   output   every lane owns chunks of 8 consecutive output values: it finds the last marker before its chunk with
-//            two bitmap probes (no block-wide scan), walks its 8 marker bits in registers, and writes the chunk with
-//            ONE 256-bit store (a warp instruction writes 1 KiB of contiguous output).  Flagged positions (insertion
-//            fills other than Repeat5p) are computed in place by the owning lane.
-//
-// Two CTA barriers per pass; the values themselves never travel through shared memory.
+//   trk_tile_prep_kernel   one THREAD per (track, tile): finds the tile's record cursor, the first stored interval that
+//                          reaches into it and the value in effect at its first position (binary searches, thousands
+//                          of them in parallel) and leaves a 112-byte descriptor.  All searching of the path lives here.
+//   trk_exec3_kernel       one CTA per tile, no loop, two barriers.  It never materialises the source window: the stored
+//                          intervals are painted DIRECTLY IN OUTPUT COORDINATES as a run-length code --
+//       load     the descriptor (one broadcast load), then the tile's records and its slice of the interval SoA
+//                (coalesced, two intervals per thread, kept in registers and mirrored in shared memory);
+//       markers  one thread per stored interval maps its two boundaries from source to haplotype coordinates (a
+//                translation per reference span; boundaries inside a deletion vanish) and drops a marker -- the value
+//                in effect from there on -- into `val[]` plus a bit into a two-level bitmap; one thread per record
+//                drops the value in effect right after the variant; insertion fills other than Repeat5p are computed
+//                one value per thread and dropped as markers too;
+//       output   every lane owns chunks of 8 consecutive output values: it finds the last marker before its chunk with
+//                two bitmap probes (no block-wide scan), walks its 8 marker bits in registers, and writes the chunk
+//                with ONE 256-bit store (a warp instruction writes 1 KiB of contiguous output).
+//     The values themselves never travel through shared memory.  A tile whose source range holds more stored intervals
+//     (or records) than are staged at once is finished in further sub-passes (rare: intervals of a few bp).
 // Rows that need the reference's sequential semantics literally (variant lists that are not position-sorted leave
 // "jump" records) and dense f32 sources (shift_and_realign_tracks_sparse) take `t2_generic_segment`: every value
 // resolved on its own against the row's records and the source -- slow, exact for any input.
 #pragma once
 
-constexpr int T2_PASS = 8192;               // output values per pass
+constexpr int T3_TILE = TRK_TILE;           // output values per execute CTA
 constexpr int T2_THREADS = 256;
-constexpr int T2_SEG = TRK_SEG;             // output values per CTA (8 passes)
-constexpr int T2_ITV = 384;                 // stored intervals staged per pass
-constexpr int T2_REC = 96;                  // records staged per pass (carry + new ones + sentinel)
-constexpr int T2_WORDS = T2_PASS / 32;
+constexpr int T3_ITV = 512;                 // stored intervals staged per sub-pass (two per thread)
+constexpr int T3_REC = 96;                  // records staged per sub-pass (carry + new ones + sentinel)
+constexpr int T3_WORDS = T3_TILE / 32;
 constexpr int FLAG_JUMPS = 1;               // RowPlan.lead_pad of a track row: the row has jump records
+constexpr int TD_RC = 1, TD_GENERIC = 2, TD_BIG = 4;  // TileDesc.flags
 
-struct __align__(16) T2Smem {
-    float val[T2_PASS];                 // marker values by pass-relative haplotype position
-    TRec rec[2][T2_REC];              // staged records (double-buffered: pass n+1 loads while pass n reads)
-    int32_t its[2][T2_ITV + 8];         // staged interval starts / ends / values (+ alignment slack)
-    int32_t ite[2][T2_ITV + 8];
-    float itv[2][T2_ITV + 8];
-    uint32_t mk[2][T2_WORDS + 1];       // marker bitmap (+ one zero word so that a funnel shift may read past the end)
-    uint32_t fl[2][T2_WORDS + 1];       // "insertion fill computes this position" bitmap
-    uint32_t mk2[2][T2_WORDS / 32];     // second level of mk: bit w = word w is non-zero
-    uint64_t bar[2];                    // TMA completion barriers
-    // what thread 0 staged for each buffer
-    int64_t d_r[2], d_it0[2];           // record cursor (index of the carry record, -1 = virtual) / first staged interval
-    int32_t d_m[2], d_more_rec[2];      // staged records; 1 = more records follow (the last staged one is only a sentinel)
-    int32_t d_cnt[2], d_off[2], d_more_itv[2];  // staged intervals, index of the first one inside its[] (alignment), more follow
+// What trk_tile_prep_kernel leaves for one (track, tile); row < 0 = no such tile.
+struct __align__(16) TileDesc {
+    int64_t out_base;   // flat index of the row's value 0 in the output buffer
+    int64_t it0;        // first stored interval (absolute index) whose end lies beyond the source position feeding h0
+    int64_t it_lo, it_hi;  // the slot's intervals (dense source: the query's window offsets)
+    int64_t rec_base;   // absolute index of the row's first record
+    int32_t n_rec, r;   // records of the row; carry record of the tile (last with a <= h0, -1: none)
+    int32_t L, h0, h1;  // row length; the tile in haplotype coordinates
+    int32_t q_start, track_n, ref0;
+    int32_t flags, row;
+    float val0;         // value in effect at h0
+    int32_t src_lo, src_hi;  // relative source positions feeding h0 / h1 (sources in [src_lo, src_hi) reach the tile)
+    int32_t m, cnt;     // records (carry included) / stored intervals the tile needs; TD_BIG when either exceeds the staging
+    int32_t pad;
 };
+static_assert(sizeof(TileDesc) == 112, "TileDesc is 112 bytes");
 
-__device__ __forceinline__ bool t2_try_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
+struct T3Smem {
+    float val[T3_TILE];             // marker values by tile-relative haplotype position
+    TRec rec[T3_REC];               // staged records
+    int32_t its[T3_ITV], ite[T3_ITV];  // staged intervals (the record threads and the fills search them)
+    float itv[T3_ITV];
+    uint32_t mk[T3_WORDS + 1];      // marker bitmap (+ one zero word so that a funnel shift may read past the end)
+    uint32_t mk2[T3_WORDS / 32];    // second level: bit w = word w of mk is non-zero
+    int32_t fill_list[T3_REC];      // staged records whose insertion fill has to be computed
+    int32_t n_fill;
+    int32_t bc_i32[4];              // broadcast slots of the (rare) sub-pass hand-over
+    int64_t bc_i64[2];
+    float bc_f32;
+};
 
 __device__ __forceinline__ void stg_f8(float *p, float a, float b, float c, float d, float e, float f, float g, float h) {
     asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "f"(e),
@@ -72,29 +75,26 @@ __device__ __forceinline__ void stg_f8(float *p, float a, float b, float c, floa
 }
 
 // ---- sources ---------------------------------------------------------------------------------------------
-// value of the painted source track at relative position tp, straight from the global arrays: dense windows, or the
-// last interval with start <= q_start + tp if it also ends after it (intervals of a slot are sorted by start and do
-// not overlap: overlapping slots are flattened when the track is uploaded, gvl_flatten_intervals)
-__device__ __forceinline__ float track_at_global(const TrkDesc &T, int64_t lo, int64_t hi, int64_t q_start, int64_t tp) {
-    if (T.dense) return T.dense[lo + tp];  // dense source: `lo` is the window's offset
-    const int64_t g = q_start + tp;
-    int64_t a = lo, b = hi;  // find last i in [lo,hi) with starts[i] <= g
-    while (a < b) {
-        int64_t mid = (a + b) >> 1;
-        if ((int64_t)T.itv_starts[mid] <= g) a = mid + 1; else b = mid;
-    }
-    const int64_t i = a - 1;
-    if (i < lo) return 0.0f;
-    return ((int64_t)T.itv_ends[i] > g) ? T.itv_values[i] : 0.0f;
-}
-
-// source seen by the generic path: global arrays only
+// source seen by the generic path and the fall-backs: the global arrays.  Value of the painted source track at relative
+// position tp: dense windows, or the last interval with start <= q_start + tp if it also ends after it (intervals of a
+// slot are sorted by start and do not overlap: overlapping slots are flattened when the track is uploaded)
 struct SrcGlobal {
-    const TrkDesc *T;
+    const int32_t *its, *ite;  // the track's interval SoA (global memory)
+    const float *itv;
+    const float *dense;        // non-NULL: dense f32 source windows instead
     int64_t itv_lo, itv_hi, q_start, track_n;
     __device__ __forceinline__ float at(int64_t tp) const {
         if (tp < 0 || tp >= track_n) return 0.0f;  // out of contract in the reference (index panic)
-        return track_at_global(*T, itv_lo, itv_hi, q_start, tp);
+        if (dense) return dense[itv_lo + tp];      // dense source: `itv_lo` is the window's offset
+        const int64_t g = q_start + tp;
+        int64_t a = itv_lo, b = itv_hi;  // last i in [lo, hi) with starts[i] <= g
+        while (a < b) {
+            const int64_t mid = (a + b) >> 1;
+            if ((int64_t)its[mid] <= g) a = mid + 1; else b = mid;
+        }
+        const int64_t i = a - 1;
+        if (i < itv_lo) return 0.0f;
+        return ((int64_t)ite[i] > g) ? itv[i] : 0.0f;
     }
 };
 
@@ -219,22 +219,22 @@ __device__ void t2_generic_segment(const TRec *__restrict__ recs, int32_t n_rec,
 // haplotype position at which relative source position x appears, given the staged records R[0..m) (R[0] = carry).
 // dropped = x is not copied (inside a deletion, or behind the carry span); the returned position is then the first
 // one whose source lies beyond x.
-__device__ __forceinline__ int32_t t2_map(const TRec *R, int m, int64_t x, bool &dropped) {
-    if (x < (int64_t)R[0].resume) {
+__device__ __forceinline__ int32_t t2_map(const TRec *R, int m, int32_t x, bool &dropped) {
+    if (x < R[0].resume) {
         dropped = true;
         return R[0].e;
     }
     int lo = 0, hi = m;  // last staged record with resume <= x
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
-        if ((int64_t)R[mid].resume <= x) lo = mid; else hi = mid;
+        if (R[mid].resume <= x) lo = mid; else hi = mid;
     }
-    if (lo + 1 < m && x > (int64_t)R[lo + 1].vrel) {  // deleted by the next record
+    if (lo + 1 < m && x > R[lo + 1].vrel) {  // deleted by the next record
         dropped = true;
         return R[lo + 1].e;
     }
     dropped = false;
-    return R[lo].e + (int32_t)(x - (int64_t)R[lo].resume);
+    return R[lo].e + (x - R[lo].resume);
 }
 
 __device__ __forceinline__ void t2_set_bit(uint32_t *mk, uint32_t *mk2, int u) {
@@ -242,260 +242,281 @@ __device__ __forceinline__ void t2_set_bit(uint32_t *mk, uint32_t *mk2, int u) {
     if (old == 0) atomicOr(&mk2[u >> 10], 1u << ((u >> 5) & 31));
 }
 
-// set bits [lo, hi) of a bitmap (hi > lo)
-__device__ __forceinline__ void t2_set_range(uint32_t *bm, int lo, int hi) {
-    for (int w = lo >> 5; w <= (hi - 1) >> 5; w++) {
-        const int b0 = max(lo - 32 * w, 0), b1 = min(hi - 32 * w, 32);
-        const uint32_t m = (b1 >= 32 ? 0xffffffffu : ((1u << b1) - 1u)) & ~((1u << b0) - 1u);
-        atomicOr(&bm[w], m);
-    }
-}
-
-__global__ void __launch_bounds__(T2_THREADS, 4) trk_exec2_kernel(TrkExecParams P) {
-    extern __shared__ __align__(16) unsigned char t2_raw[];
-    T2Smem &S = *reinterpret_cast<T2Smem *>(t2_raw);
-    const int tid = threadIdx.x;
-
-    // ---- CTA -> (track, row, segment) ----
-    const int64_t track = blockIdx.x / P.grid_per_track;
-    const int64_t b = blockIdx.x % P.grid_per_track;
-    if (b >= P.tile_off[P.n_work]) return;
-    int64_t row;
-    {
-        int64_t lo = 0, hi = P.n_work;
+// =====================================================================================
+// tile preparation: one thread per (track, tile)
+// =====================================================================================
+__global__ void __launch_bounds__(128) trk_tile_prep_kernel(TrkExecParams P, TileDesc *__restrict__ tdesc) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= P.grid_per_track * P.n_tracks) return;
+    const int64_t track = g / P.grid_per_track;
+    const int64_t b = g % P.grid_per_track;
+    TileDesc D;
+    D.row = -1;
+    if (b < P.tile_off[P.n_work]) {
+        int64_t lo = 0, hi = P.n_work;  // row of the tile: last row with tile_off[row] <= b
         while (hi - lo > 1) {
-            int64_t mid = (lo + hi) >> 1;
+            const int64_t mid = (lo + hi) >> 1;
             if (P.tile_off[mid] <= b) lo = mid; else hi = mid;
         }
-        row = lo;
+        const int64_t row = lo, tile = b - P.tile_off[row];
+        const RowPlan rp = P.rows[row];
+        const int32_t L = rp.length;
+        const int32_t t0 = (int32_t)(tile * T3_TILE);
+        if (t0 < L) {
+            const int32_t t1 = (int32_t)imin64((int64_t)t0 + T3_TILE, L);
+            const bool rc = rp.rc != 0;
+            const int64_t query = row / P.ploidy;
+            const TrkDesc &T = P.tracks ? P.tracks[track] : P.inl[track];
+            D.row = (int32_t)row;
+            D.L = L;
+            D.h0 = rc ? L - t1 : t0;  // the tile in haplotype coordinates
+            D.h1 = rc ? L - t0 : t1;
+            D.q_start = rp.q_start;
+            D.track_n = rp.contig_len;
+            D.ref0 = rp.ref0;
+            D.rec_base = rp.rec_off;
+            D.n_rec = rp.n_rec;
+            D.flags = (rc ? TD_RC : 0) | ((T.dense || (rp.lead_pad & FLAG_JUMPS)) ? TD_GENERIC : 0);
+            D.pad = 0;
+            D.src_lo = D.src_hi = 0;
+            D.m = 1;
+            D.cnt = 0;
+            int64_t row_base = track * P.total_per_track + rp.out_off;  // flat index of the row's first value
+            if (P.layout_btp) {  // all tracks of a query adjacent: block of the query, then track, then the row inside the block
+                const int64_t k0 = query * P.ploidy;
+                const int64_t blk0 = P.rows[k0].out_off;
+                const int64_t blk_len = P.rows[k0 + P.ploidy - 1].out_off + P.rows[k0 + P.ploidy - 1].length - blk0;
+                row_base = P.n_tracks * blk0 + track * blk_len + (rp.out_off - blk0);
+            }
+            D.out_base = row_base;
+            if (T.dense) {
+                D.it_lo = T.dense_offsets[query];
+                D.it_hi = T.dense_offsets[query + 1];
+                D.it0 = D.it_lo;
+                D.r = -1;
+                D.val0 = 0.0f;
+            } else {
+                const int64_t slot = P.offset_idxs[track * P.n_queries + query];
+                D.it_lo = T.itv_offsets[slot];
+                D.it_hi = T.itv_offsets[slot + 1];
+                // carry record: last record with a <= h0
+                const TRec *__restrict__ recs = P.trecs + rp.rec_off;
+                int32_t rl = -1, rh = rp.n_rec;
+                while (rh - rl > 1) {
+                    const int32_t mid = (rl + rh) >> 1;
+                    if (recs[mid].a <= D.h0) rl = mid; else rh = mid;
+                }
+                D.r = rl;
+                int64_t src = (int64_t)rp.ref0 + D.h0;  // source position that feeds h0
+                if (rl >= 0) {
+                    const TRec cr = recs[rl];
+                    src = D.h0 < cr.e ? (int64_t)cr.vrel : (int64_t)cr.resume + (D.h0 - cr.e);
+                }
+                // records that start inside the tile, and the source position that feeds h1
+                int32_t el = rl, eh = rp.n_rec;  // last record with a < h1
+                while (eh - el > 1) {
+                    const int32_t mid = (el + eh) >> 1;
+                    if (recs[mid].a < D.h1) el = mid; else eh = mid;
+                }
+                D.m = 1 + (el - rl);
+                int64_t src_hi = (int64_t)rp.ref0 + D.h1;
+                if (el >= 0) {
+                    const TRec cr = recs[el];
+                    src_hi = D.h1 <= cr.e ? (int64_t)cr.vrel + 1 : (int64_t)cr.resume + (D.h1 - cr.e);
+                }
+                D.src_lo = (int32_t)src;
+                D.src_hi = (int32_t)src_hi;
+                // first interval whose end lies beyond src (ends are sorted: the slot's intervals do not overlap)
+                const int64_t gpos = (int64_t)rp.q_start + src;
+                int64_t a = D.it_lo, bb = D.it_hi;
+                while (a < bb) {
+                    const int64_t mid = (a + bb) >> 1;
+                    if ((int64_t)T.itv_ends[mid] <= gpos) a = mid + 1; else bb = mid;
+                }
+                D.it0 = a;
+                D.val0 = (src >= 0 && src < (int64_t)rp.contig_len && a < D.it_hi && (int64_t)T.itv_starts[a] <= gpos) ? T.itv_values[a] : 0.0f;
+                // ... and the first one that starts at or beyond src_hi: the tile needs the intervals in between
+                const int64_t ghi = (int64_t)rp.q_start + src_hi;
+                int64_t c = a;
+                bb = D.it_hi;
+                while (c < bb) {
+                    const int64_t mid = (c + bb) >> 1;
+                    if ((int64_t)T.itv_starts[mid] < ghi) c = mid + 1; else bb = mid;
+                }
+                D.cnt = (int32_t)imin64(c - a, INT32_MAX);
+                if (D.m > T3_REC || c - a > T3_ITV) D.flags |= TD_BIG;
+            }
+        }
     }
-    const int64_t tile = b - P.tile_off[row];
-    const RowPlan rp = P.rows[row];
-    const int32_t L = rp.length;
-    const int32_t t0 = (int32_t)(tile * T2_SEG);
-    if (t0 >= L) return;
-    const int32_t t1 = (int32_t)imin64((int64_t)t0 + T2_SEG, L);
-    const bool rc = rp.rc != 0;
-    const int32_t h0 = rc ? L - t1 : t0;  // the segment in haplotype coordinates
-    const int32_t h1 = rc ? L - t0 : t1;
-    const int64_t query = row / P.ploidy;
-    const uint64_t hap = (uint64_t)(row % P.ploidy);
+    tdesc[g] = D;
+}
+
+// =====================================================================================
+// execute: one CTA per tile
+// =====================================================================================
+// One tile.  BIG = false: everything the tile needs fits the staging (the descriptor says how much of it): one pass,
+// extents known.  BIG = true: sub-passes, each as long as the staged records / intervals reach.
+template <bool BIG>
+__device__ __forceinline__ void t3_tile(const TrkExecParams &P, const TileDesc &D, const TrkDesc &T, T3Smem &S) {
+    const int tid = threadIdx.x;
+    const int32_t L = D.L;
+    const bool rc = (D.flags & TD_RC) != 0;
+    const int64_t query = D.row / P.ploidy;
+    const uint64_t hap = (uint64_t)(D.row % P.ploidy);
     const uint64_t qseed = P.query_seed ? (uint64_t)P.query_seed[query]
                                         : (uint64_t)(P.sub_batch > 0 ? query % P.sub_batch : query);
     const uint64_t base_seed = P.base_seed_dev ? P.base_seed_dev[P.sub_batch > 0 ? query / P.sub_batch : 0] : P.base_seed;
-    const TrkDesc T = P.tracks ? P.tracks[track] : P.inl[track];
-    int64_t itv_lo, itv_hi;
-    if (T.dense) {
-        itv_lo = T.dense_offsets[query];
-        itv_hi = T.dense_offsets[query + 1];
-    } else {
-        const int64_t slot = P.offset_idxs[track * P.n_queries + query];
-        itv_lo = T.itv_offsets[slot];
-        itv_hi = T.itv_offsets[slot + 1];
-    }
-    const int64_t track_n = rp.contig_len;
-    const int64_t q_start = rp.q_start;
-    int64_t row_base = track * P.total_per_track + rp.out_off;  // flat index of the row's first value
-    if (P.layout_btp) {  // all tracks of a query are adjacent: block of the query, then track, then the row inside the block
-        const int64_t k0 = query * P.ploidy;
-        const int64_t blk0 = P.rows[k0].out_off;
-        const int64_t blk_len = P.rows[k0 + P.ploidy - 1].out_off + P.rows[k0 + P.ploidy - 1].length - blk0;
-        row_base = P.n_tracks * blk0 + track * blk_len + (rp.out_off - blk0);
-    }
-    const TRec *__restrict__ recs = P.trecs + rp.rec_off;
-    const int32_t n_rec = rp.n_rec;
-    const SrcGlobal srcg{&T, itv_lo, itv_hi, q_start, track_n};
+    const int64_t track_n = D.track_n, q_start = D.q_start;
+    const TRec *__restrict__ recs = P.trecs + D.rec_base;  // the row's records
+    const SrcGlobal srcg{T.itv_starts, T.itv_ends, T.itv_values, T.dense, D.it_lo, D.it_hi, q_start, track_n};
+    float *__restrict__ out_row = P.out + D.out_base;
 
-    if (T.dense || (rp.lead_pad & FLAG_JUMPS)) {
-        t2_generic_segment(recs, n_rec, rp.ref0, srcg, T, P.out + row_base, L, rc, t0, t1, base_seed, qseed, hap);
-        return;
-    }
-
-    // ---- thread 0 stages a pass: carry record + following records, the interval slice from it0 on ----
-    auto issue_loads = [&](int buf, int64_t r, int64_t it0) {
-        int dst0 = 0;
-        int64_t src0 = r;
-        if (r < 0) {  // virtual carry: nothing written yet, the span starts at ref0
-            TRec v;
-            v.a = 0, v.e = 0, v.resume = rp.ref0, v.vrel = rp.ref0, v.vlen = 1, v.vdiff = 0, v.pad0 = 0, v.pad1 = 0;
-            S.rec[buf][0] = v;
-            dst0 = 1;
-            src0 = 0;
-        }
-        const int n = (int)imin64((int64_t)(T2_REC - dst0), imax64((int64_t)n_rec - src0, 0));
-        S.d_m[buf] = dst0 + n;
-        S.d_more_rec[buf] = (src0 + n < (int64_t)n_rec) ? 1 : 0;
-        const int64_t it_al = it0 & ~(int64_t)3;
-        const int cnt = (int)imin64((int64_t)T2_ITV, imax64(itv_hi - it0, 0));
-        const int n_al = ((int)(it0 - it_al) + cnt + 3) & ~3;
-        S.d_cnt[buf] = cnt;
-        S.d_off[buf] = (int)(it0 - it_al);
-        S.d_more_itv[buf] = (it0 + cnt < itv_hi) ? 1 : 0;
-        S.d_r[buf] = r;
-        S.d_it0[buf] = it0;
-        const uint32_t bytes = (uint32_t)n * (uint32_t)sizeof(TRec) + (cnt > 0 ? 3u * (uint32_t)n_al * 4u : 0u);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy accesses of the buffer come first
-        mbar_expect_tx(&S.bar[buf], bytes);
-        if (n > 0) bulk_g2s(&S.rec[buf][dst0], recs + src0, (uint32_t)n * (uint32_t)sizeof(TRec), &S.bar[buf]);
-        if (cnt > 0) {
-            bulk_g2s(S.its[buf], T.itv_starts + it_al, (uint32_t)n_al * 4u, &S.bar[buf]);
-            bulk_g2s(S.ite[buf], T.itv_ends + it_al, (uint32_t)n_al * 4u, &S.bar[buf]);
-            bulk_g2s(S.itv[buf], T.itv_values + it_al, (uint32_t)n_al * 4u, &S.bar[buf]);
-        }
-    };
-    // first interval of [itv_lo, itv_hi) whose end lies beyond relative source position x (ends are sorted)
-    auto first_itv_after = [&](int64_t from, int64_t x) -> int64_t {
-        int64_t a = from, bb = itv_hi;
-        const int64_t g = q_start + x;
-        while (a < bb) {
-            const int64_t mid = (a + bb) >> 1;
-            if ((int64_t)T.itv_ends[mid] <= g) a = mid + 1; else bb = mid;
-        }
-        return a;
-    };
-
-    // ---- prologue: barriers, bitmaps, cursors of the first pass ----
-    if (tid == 0) {
-        mbar_init(&S.bar[0], 1);
-        mbar_init(&S.bar[1], 1);
-    }
-    for (int i = tid; i < T2_WORDS + 1; i += T2_THREADS) S.mk[0][i] = S.mk[1][i] = S.fl[0][i] = S.fl[1][i] = 0u;
-    if (tid < T2_WORDS / 32) S.mk2[0][tid] = S.mk2[1][tid] = 0u;
-    if (tid < 32) {
-        // r = last record with a <= h0 (-1: none): a count over the sorted array (independent loads), a search when long
-        int c = 0;
-        if (n_rec <= 4096) {
-            for (int i = tid; i < n_rec; i += 32) c += (recs[i].a <= h0);
-            c = __reduce_add_sync(0xffffffffu, c);
-        } else {
-            int lo = -1, hi = n_rec;
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (recs[mid].a <= h0) lo = mid; else hi = mid;
+    const int64_t base_elems = (int64_t)(reinterpret_cast<uintptr_t>(P.out) >> 2) + D.out_base;  // address of out_row[0] in floats
+    const int32_t h1 = D.h1;
+    int32_t cur = D.h0;
+    int64_t r = D.r, it0 = D.it0;  // cursors: carry record (relative to the row, -1 = virtual), first staged interval
+    float val0 = D.val0;
+    for (;;) {
+        // ---- load: two intervals per thread (registers + shared memory), the records, clean bitmaps ----
+        const int cnt = BIG ? (int)imin64((int64_t)T3_ITV, imax64(D.it_hi - it0, 0)) : D.cnt;
+        const bool more_itv = BIG && it0 + cnt < D.it_hi;  // (BIG = false: what follows the staged intervals lies beyond the tile)
+        int32_t is[2], ie[2];
+        float iv[2];
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int k = tid + q * T2_THREADS;
+            is[q] = ie[q] = 0, iv[q] = 0.0f;
+            if (k < cnt) {
+                is[q] = __ldg(T.itv_starts + it0 + k);
+                ie[q] = __ldg(T.itv_ends + it0 + k);
+                iv[q] = __ldg(T.itv_values + it0 + k);
             }
-            c = lo + 1;
         }
-        const int64_t r = (int64_t)c - 1;
-        int64_t src = (int64_t)rp.ref0 + h0;
-        if (r >= 0) {
-            const TRec cr = recs[r];
-            src = h0 < cr.e ? (int64_t)cr.vrel : (int64_t)cr.resume + (h0 - cr.e);
+        const int dst0 = r < 0 ? 1 : 0;
+        const int64_t src0 = r < 0 ? 0 : r;
+        const int n_ld = BIG ? (int)imin64((int64_t)(T3_REC - dst0), imax64((int64_t)D.n_rec - src0, 0)) : D.m - 1 + (1 - dst0);
+        const int m = dst0 + n_ld;
+        const bool more_rec = BIG && src0 + n_ld < (int64_t)D.n_rec;
+        if (tid < n_ld) S.rec[dst0 + tid] = recs[src0 + tid];
+        if (tid == 0 && dst0) {  // virtual carry: nothing written yet, the span starts at ref0
+            TRec v;
+            v.a = 0, v.e = 0, v.resume = D.ref0, v.vrel = D.ref0, v.vlen = 1, v.vdiff = 0, v.pad0 = 0, v.pad1 = 0;
+            S.rec[0] = v;
         }
-        // first interval whose end lies beyond the source position that feeds h0: warp-wide 32-ary search (ends are sorted)
-        const int64_t first = warp_upper_le(T.itv_ends, itv_lo, itv_hi, (int32_t)imin64(q_start + src, INT32_MAX)) + 1;
-        if (tid == 0) issue_loads(0, r, first);
-    }
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int k = tid + q * T2_THREADS;
+            S.its[k] = is[q], S.ite[k] = ie[q], S.itv[k] = iv[q];
+        }
+        for (int i = tid; i < T3_WORDS + 1; i += T2_THREADS) S.mk[i] = 0u;
+        if (tid < T3_WORDS / 32) S.mk2[tid] = 0u;
+        if (tid == 0) S.n_fill = 0;
+        __syncthreads();
 
-    float *__restrict__ out_row = P.out + row_base;
-    const int64_t base_elems = (int64_t)(reinterpret_cast<uintptr_t>(P.out) >> 2) + row_base;  // address of out_row[0] in floats
-    int32_t cur = h0;
-    for (int pass = 0; cur < h1; pass++) {
-        const int buf = pass & 1;
-        __syncthreads();  // the previous pass's readers are done with val[]; thread 0's descriptors are visible
-        while (!t2_try_wait(&S.bar[buf], (uint32_t)(pass >> 1) & 1u)) {
-        }
-        const TRec *R = S.rec[buf];
-        const int m = S.d_m[buf], cnt = S.d_cnt[buf], off = S.d_off[buf];
-        const bool more_itv = S.d_more_itv[buf] != 0;
-        const int64_t it0 = S.d_it0[buf];
-        uint32_t *mk = S.mk[buf], *fl = S.fl[buf], *mk2 = S.mk2[buf];
-        const int32_t *its = S.its[buf] + off, *ite = S.ite[buf] + off;
-        const float *itv = S.itv[buf] + off;
-
-        // ---- extent of the pass ----
-        int32_t pass_end = (int32_t)imin64((int64_t)cur + T2_PASS, h1);
+        // ---- extent of the sub-pass ----
+        const TRec *R = S.rec;
+        int32_t pass_end = h1;
         int m_eff = m;
-        if (S.d_more_rec[buf]) {  // the last staged record is a sentinel: the pass stops where it starts
+        if (more_rec) {  // the last staged record is a sentinel: the sub-pass stops where it starts
             m_eff = m - 1;
             pass_end = min(pass_end, R[m - 1].a);
         }
-        const int32_t e0 = R[0].e;
-        const int64_t src_lo = cur < e0 ? (int64_t)R[0].vrel : (int64_t)R[0].resume + (cur - e0);
-        if (more_itv) {  // likewise the last staged interval: nothing beyond its start is known yet
-            bool dr;
-            const int32_t hl = t2_map(R, m_eff, imax64((int64_t)its[cnt - 1] - q_start, 0), dr);
-            pass_end = min(pass_end, max(hl, cur + 1));
+        int32_t src_lo = D.src_lo, src_hi = D.src_hi;  // sources in [src_lo, src_hi) reach the (sub-)pass
+        int m_pass = m;  // staged records that start inside the sub-pass (+ the carry): the only ones the mapping needs
+        if (BIG) {
+            const int32_t e0 = R[0].e;
+            src_lo = cur < e0 ? R[0].vrel : R[0].resume + (cur - e0);
+            if (more_itv) {  // likewise the last staged interval: nothing beyond its start is known
+                bool dr;
+                const int32_t hl = t2_map(R, m_eff, (int32_t)imax64((int64_t)S.its[cnt - 1] - q_start, 0), dr);
+                pass_end = min(pass_end, max(hl, cur + 1));
+            }
+            int lo = 0, hi = m_eff;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (R[mid].a < pass_end) lo = mid; else hi = mid;
+            }
+            m_pass = lo + 1;
+            const TRec rl = R[m_pass - 1];
+            src_hi = pass_end <= rl.e ? rl.vrel + 1 : rl.resume + (pass_end - rl.e);
         }
         const int32_t plen = pass_end - cur;
-        const SrcStaged src{its, ite, itv, cnt, more_itv, it0 == itv_lo, srcg, track_n};
+        const SrcStaged src{S.its, S.ite, S.itv, cnt, BIG ? more_itv : (it0 + cnt < D.it_hi), it0 == D.it_lo, srcg, track_n};
+        uint32_t *mk = S.mk, *mk2 = S.mk2;
 
         // ---- markers: intervals ----
-        auto place = [&](int64_t x, float v) {
+        auto place = [&](int32_t x, float v) {
             bool dr;
-            const int32_t h = t2_map(R, m_eff, x, dr);
+            const int32_t h = t2_map(R, m_pass, x, dr);
             const int32_t u = h - cur;
             if (dr || u <= 0 || u >= plen) return;
             S.val[u] = v;
             t2_set_bit(mk, mk2, u);
         };
-        for (int k = tid; k < cnt; k += T2_THREADS) {
-            const int64_t s = imax64((int64_t)its[k] - q_start, 0);
-            const int64_t e = imin64((int64_t)ite[k] - q_start, track_n);
-            if (e <= s || e <= src_lo) continue;  // empty after clipping, or wholly behind the pass
-            if (s > src_lo) place(s, itv[k]);     // (an interval that covers the pass start is the pass-start marker's)
-            const bool adjacent = (k + 1 < cnt) && ((int64_t)its[k + 1] - q_start == e);  // the next interval starts right there
-            if (!adjacent) place(e, 0.0f);
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int k = tid + q * T2_THREADS;
+            if (k >= cnt) continue;
+            // (clipped to the source window in 64 bits, 32-bit arithmetic from here on)
+            const int32_t s = (int32_t)imin64(imax64((int64_t)is[q] - q_start, 0), track_n);
+            const int32_t e = (int32_t)imax64(imin64((int64_t)ie[q] - q_start, track_n), 0);
+            if (e <= s || e <= src_lo || s >= src_hi) continue;  // empty after clipping, behind the sub-pass, beyond it
+            if (s > src_lo) place(s, iv[q]);  // (an interval that covers the first position is the start marker's)
+            const bool adjacent = (k + 1 < cnt) && ((int64_t)S.its[k + 1] - q_start == (int64_t)e);  // the next interval starts right there
+            if (!adjacent && e < src_hi) place(e, 0.0f);
         }
-        // ---- markers: records (threads from the top of the CTA) + the pass start ----
+        // ---- markers: records (threads from the top of the CTA) + the first position ----
+        bool need_fill = false;
         {
             const int i = T2_THREADS - 1 - tid;
-            if (i < m_eff) {
-                const TRec r = R[i];
-                const bool live = i == 0 ? (cur < r.e) : (r.a < pass_end);
+            if (i < m_pass) {
+                const TRec rr = R[i];
+                const bool live = i == 0 ? (cur < rr.e) : true;
                 if (live) {
-                    if (r.vdiff > 0 && T.strategy != GVL_FILL_REPEAT_5P)
-                        t2_set_range(fl, max(r.a, cur) - cur, min(r.e, pass_end) - cur);
-                    if (r.e < pass_end && r.e > cur) {  // value in effect right after the variant
-                        S.val[r.e - cur] = src.at(r.resume);
-                        t2_set_bit(mk, mk2, r.e - cur);
+                    if (rr.vdiff > 0 && T.strategy != GVL_FILL_REPEAT_5P) {
+                        S.fill_list[atomicAdd(&S.n_fill, 1)] = i;
+                        need_fill = true;
+                    }
+                    if (rr.e < pass_end && rr.e > cur) {  // value in effect right after the variant
+                        S.val[rr.e - cur] = src.at(rr.resume);
+                        t2_set_bit(mk, mk2, rr.e - cur);
                     }
                 }
-            } else if (i == m_eff) {
-                S.val[0] = src.at(cur < e0 ? (int64_t)R[0].vrel : src_lo);
+            } else if (i == m_pass) {
+                S.val[0] = val0;
                 t2_set_bit(mk, mk2, 0);
             }
         }
-        __syncthreads();
-
-        // ---- thread 0: cursors + loads of the next pass (they land while this pass is written out) ----
-        if (tid == 0 && pass_end < h1) {
-            int lo = 0, hi = m;  // next carry: last staged record with a <= pass_end
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (R[mid].a <= pass_end) lo = mid; else hi = mid;
+        // ---- insertion fills other than Repeat5p: one value per thread, dropped as markers ----
+        if (__syncthreads_or(need_fill)) {
+            const int warp = tid >> 5, lane = tid & 31;
+            for (int f = warp; f < S.n_fill; f += T2_THREADS / 32) {
+                const TRec rr = R[S.fill_list[f]];
+                const int32_t lo = max(rr.a, cur), hi = min(rr.e, pass_end);
+                for (int32_t p = lo + lane; p < hi; p += 32) {
+                    S.val[p - cur] = insertion_fill_value(src, T.strategy, T.param, rr.vlen, rr.vrel, p - rr.a, p, base_seed, qseed, hap);
+                    t2_set_bit(mk, mk2, p - cur);
+                }
             }
-            const TRec cr = R[lo];
-            const int64_t src_next = pass_end < cr.e ? (int64_t)cr.vrel : (int64_t)cr.resume + (pass_end - cr.e);
-            int a = 0, bb = cnt;  // staged intervals that end at or before src_next are history
-            while (a < bb) {
-                const int mid = (a + bb) >> 1;
-                if ((int64_t)ite[mid] - q_start <= src_next) a = mid + 1; else bb = mid;
-            }
-            int64_t it_next = it0 + a;
-            if (a == cnt && more_itv) it_next = first_itv_after(it_next, src_next);  // (a long deletion skipped them all)
-            issue_loads(buf ^ 1, S.d_r[buf] + lo, it_next);
+            __syncthreads();
         }
-        // the other buffer's bitmaps were last read in the previous pass: clear them for the next one
-        S.mk[buf ^ 1][tid] = 0u;
-        S.fl[buf ^ 1][tid] = 0u;
-        if (tid < T2_WORDS / 32) S.mk2[buf ^ 1][tid] = 0u;
 
         // ---- output: chunks of 8 values on 32-byte aligned addresses ----
         const int32_t jo_lo = rc ? L - pass_end : cur;
         const int32_t jo_hi = rc ? L - cur : pass_end;
         const int32_t j0 = (int32_t)(((base_elems + jo_lo) & ~(int64_t)7) - base_elems);  // may be < jo_lo
         const int32_t n_chunks = (jo_hi - j0 + 7) >> 3;
-        for (int32_t c = tid; c < n_chunks; c += T2_THREADS) {
-            const int32_t j = j0 + 8 * c;
-            const int32_t u_lo = (rc ? (L - 8 - j) : j) - cur;  // lowest pass-relative haplotype position of the chunk
-            uint32_t bits, fbits;
+        int32_t j = j0 + 8 * tid;                                // first output position of the thread's chunk
+        int32_t u_lo = (rc ? (L - 8 - j) : j) - cur;             // its lowest tile-relative haplotype position
+        const int32_t du = rc ? -8 * T2_THREADS : 8 * T2_THREADS;
+        float *dst = out_row + j;
+        for (int32_t c = tid; c < n_chunks; c += T2_THREADS, j += 8 * T2_THREADS, u_lo += du, dst += 8 * T2_THREADS) {
+            uint32_t bits;
             if (u_lo >= 0) {
-                const int w = u_lo >> 5, sh = u_lo & 31;
-                bits = __funnelshift_r(mk[w], mk[w + 1], sh) & 0xffu;
-                fbits = __funnelshift_r(fl[w], fl[w + 1], sh) & 0xffu;
+                const int w = u_lo >> 5;
+                bits = __funnelshift_r(mk[w], mk[w + 1], u_lo & 31) & 0xffu;
             } else {
                 bits = (mk[0] << (-u_lo)) & 0xffu;
-                fbits = (fl[0] << (-u_lo)) & 0xffu;
             }
             float cv = 0.0f;
             const int q = max(u_lo, 0) - 1;  // last position before the chunk (position 0 always holds a marker)
@@ -517,25 +538,10 @@ __global__ void __launch_bounds__(T2_THREADS, 4) trk_exec2_kernel(TrkExecParams 
                 if ((bits >> t) & 1u) cv = S.val[u_lo + t];
                 x[t] = cv;
             }
-            if (fbits) {  // insertion fills other than Repeat5p: computed by the owning lane
-#pragma unroll
-                for (int t = 0; t < 8; t++) {  // (unrolled: x[] stays in registers)
-                    if (!((fbits >> t) & 1u)) continue;
-                    const int32_t p = cur + u_lo + t;
-                    int lo = 0, hi = m_eff;  // the staged record whose values cover p
-                    while (hi - lo > 1) {
-                        const int mid = (lo + hi) >> 1;
-                        if (R[mid].a <= p) lo = mid; else hi = mid;
-                    }
-                    const TRec r = R[lo];
-                    x[t] = insertion_fill_value(src, T.strategy, T.param, r.vlen, r.vrel, p - r.a, p, base_seed, qseed, hap);
-                }
-            }
-            float *dst = out_row + j;
             if (j >= jo_lo && j + 8 <= jo_hi) {
                 if (rc) stg_f8(dst, x[7], x[6], x[5], x[4], x[3], x[2], x[1], x[0]);
                 else stg_f8(dst, x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
-            } else {  // chunk cut by the pass / row ends
+            } else {  // chunk cut by the tile / row ends
 #pragma unroll
                 for (int t = 0; t < 8; t++) {
                     const int32_t jj = j + t;
@@ -543,6 +549,70 @@ __global__ void __launch_bounds__(T2_THREADS, 4) trk_exec2_kernel(TrkExecParams 
                 }
             }
         }
+        if (!BIG || pass_end >= h1) break;
+
+        // ---- (rare) the tile goes on: cursors of the next sub-pass ----
+        // next carry = last staged record with a <= pass_end; staged intervals that end at or before the source
+        // position feeding pass_end are history
+        int lo = 0;
+        {
+            int hi = m;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (R[mid].a <= pass_end) lo = mid; else hi = mid;
+            }
+        }
+        const TRec cr = R[lo];
+        const int64_t src_next = pass_end < cr.e ? (int64_t)cr.vrel : (int64_t)cr.resume + (pass_end - cr.e);
+        src_lo = (int32_t)src_next;
+        int behind = 0;
+#pragma unroll
+        for (int q = 0; q < 2; q++)
+            behind += (tid + q * T2_THREADS < cnt && (int64_t)ie[q] - q_start <= src_next) ? 1 : 0;
+        const int n_behind = __syncthreads_count(behind > 0) + __syncthreads_count(behind > 1);  // (also: everyone is done with S)
+        if (tid == 0) {
+            int64_t it_next = it0 + n_behind;
+            if (n_behind == cnt && more_itv) {  // a long deletion skipped every staged interval: search the slot
+                int64_t a = it_next, bb = D.it_hi;
+                const int64_t gpos = q_start + src_next;
+                while (a < bb) {
+                    const int64_t mid = (a + bb) >> 1;
+                    if ((int64_t)T.itv_ends[mid] <= gpos) a = mid + 1; else bb = mid;
+                }
+                it_next = a;
+            }
+            S.bc_i64[0] = it_next;
+            S.bc_f32 = srcg.at(src_next);  // value in effect at the first position of the next sub-pass
+        }
+        __syncthreads();
+        it0 = S.bc_i64[0];
+        val0 = S.bc_f32;
+        r += lo;  // staged index i <-> row index r + i (staged[0] is the carry, also when it is the virtual one, r = -1)
         cur = pass_end;
+        __syncthreads();  // the broadcast slots are read before the next sub-pass rewrites shared memory
     }
 }
+
+__global__ void __launch_bounds__(T2_THREADS, 5) trk_exec3_kernel(TrkExecParams P, const TileDesc *__restrict__ tdesc) {
+    __shared__ __align__(16) T3Smem S;
+    const TileDesc D = tdesc[blockIdx.x];  // (same address in every thread: one broadcast load)
+    if (D.row < 0) return;
+    const int64_t track = blockIdx.x / P.grid_per_track;
+    const TrkDesc T = P.tracks ? P.tracks[track] : P.inl[track];
+    if (D.flags & TD_GENERIC) {
+        const int32_t L = D.L;
+        const bool rc = (D.flags & TD_RC) != 0;
+        const int64_t query = D.row / P.ploidy;
+        const uint64_t qseed = P.query_seed ? (uint64_t)P.query_seed[query]
+                                            : (uint64_t)(P.sub_batch > 0 ? query % P.sub_batch : query);
+        const uint64_t base_seed = P.base_seed_dev ? P.base_seed_dev[P.sub_batch > 0 ? query / P.sub_batch : 0] : P.base_seed;
+        const SrcGlobal srcg{T.itv_starts, T.itv_ends, T.itv_values, T.dense, D.it_lo, D.it_hi, D.q_start, D.track_n};
+        const int32_t t0 = rc ? L - D.h1 : D.h0, t1 = rc ? L - D.h0 : D.h1;
+        t2_generic_segment(P.trecs + D.rec_base, D.n_rec, D.ref0, srcg, T, P.out + D.out_base, L, rc, t0, t1, base_seed, qseed,
+                           (uint64_t)(D.row % P.ploidy));
+        return;
+    }
+    if (D.flags & TD_BIG) t3_tile<true>(P, D, T, S);
+    else t3_tile<false>(P, D, T, S);
+}
+

@@ -349,7 +349,7 @@ static int launch_trk_exec(gvl_ctx *ctx, int64_t n_work, int64_t ploidy, int64_t
     TileDesc *tdesc = (TileDesc *)ctx->trk.tdesc;
     trk_tile_prep_kernel<<<(unsigned)((grid + 127) / 128), 128, 0, st>>>(P, tdesc);
     GVL_LAUNCH_CHECK();
-    trk_exec3_kernel<<<(unsigned)grid, T2_THREADS, 0, st>>>(P, tdesc);
+    trk_exec3_kernel<<<dim3((unsigned)P.grid_per_track, (unsigned)n_tracks), T2_THREADS, 0, st>>>(P, tdesc);
     GVL_LAUNCH_CHECK();
     return GVL_OK;
 }

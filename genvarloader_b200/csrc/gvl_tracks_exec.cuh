@@ -50,7 +50,7 @@ struct __align__(16) TileDesc {
     float val0;         // value in effect at h0
     int32_t src_lo, src_hi;  // relative source positions feeding h0 / h1 (sources in [src_lo, src_hi) reach the tile)
     int32_t m, cnt;     // records (carry included) / stored intervals the tile needs; TD_BIG when either exceeds the staging
-    int32_t pad;
+    int32_t query;      // row / ploidy (hap = row - query * ploidy)
 };
 static_assert(sizeof(TileDesc) == 112, "TileDesc is 112 bytes");
 
@@ -66,6 +66,7 @@ struct T3Smem {
     int32_t bc_i32[4];              // broadcast slots of the (rare) sub-pass hand-over
     int64_t bc_i64[2];
     float bc_f32;
+    alignas(16) unsigned char big_ctx[128];  // TileCtx handed to the out-of-line sub-pass variant
 };
 
 __device__ __forceinline__ void stg_f8(float *p, float a, float b, float c, float d, float e, float f, float g, float h) {
@@ -104,7 +105,7 @@ struct SrcStaged {
     const float *itv;
     int cnt;
     bool more, from_first;     // intervals follow the staged ones / the staged ones start at the slot's first interval
-    SrcGlobal G;
+    const SrcGlobal &G;
     int64_t track_n;
     __device__ __forceinline__ float at(int64_t tp) const {
         if (tp < 0 || tp >= track_n) return 0.0f;
@@ -153,7 +154,7 @@ __device__ __forceinline__ float lagrange_fill(const Src &S, int64_t v_len, int6
 
 // apply_insertion_fill, src/tracks/mod.rs:87-190, for ONE written value (index i within the write).
 template <class Src>
-__device__ __noinline__ float insertion_fill_value(const Src &S, int strategy, double param, int64_t v_len, int64_t v_rel_pos,
+__device__ __forceinline__ float insertion_fill_value(const Src &S, int strategy, double param, int64_t v_len, int64_t v_rel_pos,
                                                    int64_t i, int64_t out_pos, uint64_t base_seed, uint64_t query, uint64_t hap) {
     if (strategy == GVL_FILL_REPEAT_5P) {
         return S.at(v_rel_pos);
@@ -182,7 +183,7 @@ __device__ __noinline__ float insertion_fill_value(const Src &S, int strategy, d
 // output value at haplotype position p of a row, resolved against the row's records in GLOBAL memory.  `hint` caches
 // the record found last (positions of one thread advance monotonically).
 __device__ float t2_generic_value(const TRec *__restrict__ recs, int32_t n_rec, int32_t ref0, const SrcGlobal &src,
-                                  const TrkDesc &T, int32_t p, uint64_t base_seed, uint64_t qseed, uint64_t hap, int32_t &hint) {
+                                  int strategy, double param, int32_t p, uint64_t base_seed, uint64_t qseed, uint64_t hap, int32_t &hint) {
     // i = last record with a <= p, -1 = before every record (the virtual record: span from ref0)
     int32_t i = hint;
     if (!(i >= -1 && i < n_rec && (i < 0 || recs[i].a <= p) && (i + 1 >= n_rec || recs[i + 1].a > p))) {
@@ -197,21 +198,21 @@ __device__ float t2_generic_value(const TRec *__restrict__ recs, int32_t n_rec, 
     if (i < 0) return src.at((int64_t)ref0 + p);
     const TRec r = recs[i];
     if (p < r.e) {  // values written by the variant itself (src/tracks/mod.rs:329-354)
-        if (r.vdiff > 0 && T.strategy != GVL_FILL_REPEAT_5P)
-            return insertion_fill_value(src, T.strategy, T.param, r.vlen, r.vrel, p - r.a, p, base_seed, qseed, hap);
+        if (r.vdiff > 0 && strategy != GVL_FILL_REPEAT_5P)
+            return insertion_fill_value(src, strategy, param, r.vlen, r.vrel, p - r.a, p, base_seed, qseed, hap);
         return src.at(r.vrel);
     }
     const int64_t tp = (int64_t)r.resume + (p - r.e);
     return tp < src.track_n ? src.at(tp) : 0.0f;  // :381-404 trailing zeros
 }
 
-__device__ void t2_generic_segment(const TRec *__restrict__ recs, int32_t n_rec, int32_t ref0, const SrcGlobal &src,
-                                   const TrkDesc &T, float *__restrict__ out_row, int32_t L, bool rc, int32_t t0, int32_t t1,
+__device__ __noinline__ void t2_generic_segment(const TRec *__restrict__ recs, int32_t n_rec, int32_t ref0, SrcGlobal src,
+                                                int strategy, double param, float *__restrict__ out_row, int32_t L, bool rc, int32_t t0, int32_t t1,
                                    uint64_t base_seed, uint64_t qseed, uint64_t hap) {
     int32_t hint = -2;
     for (int32_t j = t0 + (int32_t)threadIdx.x; j < t1; j += T2_THREADS) {
         const int32_t p = rc ? (L - 1 - j) : j;
-        out_row[j] = t2_generic_value(recs, n_rec, ref0, src, T, p, base_seed, qseed, hap, hint);
+        out_row[j] = t2_generic_value(recs, n_rec, ref0, src, strategy, param, p, base_seed, qseed, hap, hint);
     }
 }
 
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(128) trk_tile_prep_kernel(TrkExecParams P, Til
             D.rec_base = rp.rec_off;
             D.n_rec = rp.n_rec;
             D.flags = (rc ? TD_RC : 0) | ((T.dense || (rp.lead_pad & FLAG_JUMPS)) ? TD_GENERIC : 0);
-            D.pad = 0;
+            D.query = (int32_t)query;
             D.src_lo = D.src_hi = 0;
             D.m = 1;
             D.cnt = 0;
@@ -345,6 +346,13 @@ __global__ void __launch_bounds__(128) trk_tile_prep_kernel(TrkExecParams P, Til
                 }
                 D.cnt = (int32_t)imin64(c - a, INT32_MAX);
                 if (D.m > T3_REC || c - a > T3_ITV) D.flags |= TD_BIG;
+                // the execute CTA of this tile reads these next: have them in L2 by then
+                const int64_t n_pf = imin64(c - a, T3_ITV);
+                for (int64_t o = (a * 4) & ~(int64_t)127; o < (a + n_pf) * 4; o += 128) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"((const char *)T.itv_starts + o));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"((const char *)T.itv_ends + o));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"((const char *)T.itv_values + o));
+                }
             }
         }
     }
@@ -354,24 +362,80 @@ __global__ void __launch_bounds__(128) trk_tile_prep_kernel(TrkExecParams P, Til
 // =====================================================================================
 // execute: one CTA per tile
 // =====================================================================================
+// the output phase of a (sub-)pass: see the header comment
+template <bool RC>
+__device__ __forceinline__ void t3_write_chunks(const T3Smem &S, float *__restrict__ out_row, int32_t j0, int32_t n_chunks,
+                                                int32_t jo_lo, int32_t jo_hi, int32_t L, int32_t cur) {
+    const uint32_t *mk = S.mk, *mk2 = S.mk2;
+    const int tid = threadIdx.x;
+    int32_t j = j0 + 8 * tid;                          // first output position of the thread's chunk
+    int32_t u_lo = (RC ? (L - 8 - j) : j) - cur;       // its lowest tile-relative haplotype position
+    float *dst = out_row + j;
+    for (int32_t c = tid; c < n_chunks; c += T2_THREADS, j += 8 * T2_THREADS, u_lo += RC ? -8 * T2_THREADS : 8 * T2_THREADS,
+                 dst += 8 * T2_THREADS) {
+        uint32_t bits;
+        if (u_lo >= 0) {
+            const int w = u_lo >> 5;
+            bits = __funnelshift_r(mk[w], mk[w + 1], u_lo & 31) & 0xffu;
+        } else {
+            bits = (mk[0] << (-u_lo)) & 0xffu;
+        }
+        float cv = 0.0f;
+        const int q = max(u_lo, 0) - 1;  // last position before the chunk (position 0 always holds a marker)
+        if (q >= 0) {
+            int w = q >> 5;
+            uint32_t mm = mk[w] & (0xffffffffu >> (31 - (q & 31)));
+            if (mm == 0u) {
+                int w2 = w >> 5;
+                uint32_t m2 = mk2[w2] & ((1u << (w & 31)) - 1u);
+                while (m2 == 0u) m2 = mk2[--w2];
+                w = 32 * w2 + 31 - __clz(m2);
+                mm = mk[w];
+            }
+            cv = S.val[32 * w + 31 - __clz(mm)];
+        }
+        float x[8];  // in OUTPUT order: haplotype position u_lo + t is output RC ? 7 - t : t
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            if ((bits >> t) & 1u) cv = S.val[u_lo + t];
+            x[RC ? 7 - t : t] = cv;
+        }
+        if (j >= jo_lo && j + 8 <= jo_hi) {
+            stg_f8(dst, x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
+        } else {  // chunk cut by the tile / row ends
+#pragma unroll
+            for (int t = 0; t < 8; t++) {
+                const int32_t jj = j + t;
+                if (jj >= jo_lo && jj < jo_hi) dst[t] = x[t];
+            }
+        }
+    }
+}
+
+// what a tile needs beyond its descriptor (built once by the kernel; small enough to travel by value)
+struct TileCtx {
+    const TRec *recs;      // the row's records
+    float *out_row;        // the row's value 0
+    int64_t base_elems;    // its address in floats (32-byte alignment of the chunks)
+    SrcGlobal srcg;
+    uint64_t base_seed, qseed, hap;
+    double param;
+    int32_t strategy;
+};
+
 // One tile.  BIG = false: everything the tile needs fits the staging (the descriptor says how much of it): one pass,
 // extents known.  BIG = true: sub-passes, each as long as the staged records / intervals reach.
 template <bool BIG>
-__device__ __forceinline__ void t3_tile(const TrkExecParams &P, const TileDesc &D, const TrkDesc &T, T3Smem &S) {
+__device__ __forceinline__ void t3_tile(const TileCtx &X, const TileDesc &D, T3Smem &S) {
     const int tid = threadIdx.x;
     const int32_t L = D.L;
     const bool rc = (D.flags & TD_RC) != 0;
-    const int64_t query = D.row / P.ploidy;
-    const uint64_t hap = (uint64_t)(D.row % P.ploidy);
-    const uint64_t qseed = P.query_seed ? (uint64_t)P.query_seed[query]
-                                        : (uint64_t)(P.sub_batch > 0 ? query % P.sub_batch : query);
-    const uint64_t base_seed = P.base_seed_dev ? P.base_seed_dev[P.sub_batch > 0 ? query / P.sub_batch : 0] : P.base_seed;
+    const uint64_t hap = X.hap, qseed = X.qseed, base_seed = X.base_seed;
     const int64_t track_n = D.track_n, q_start = D.q_start;
-    const TRec *__restrict__ recs = P.trecs + D.rec_base;  // the row's records
-    const SrcGlobal srcg{T.itv_starts, T.itv_ends, T.itv_values, T.dense, D.it_lo, D.it_hi, q_start, track_n};
-    float *__restrict__ out_row = P.out + D.out_base;
-
-    const int64_t base_elems = (int64_t)(reinterpret_cast<uintptr_t>(P.out) >> 2) + D.out_base;  // address of out_row[0] in floats
+    const TRec *__restrict__ recs = X.recs;
+    const SrcGlobal &srcg = X.srcg;
+    float *__restrict__ out_row = X.out_row;
+    const int64_t base_elems = X.base_elems;
     const int32_t h1 = D.h1;
     int32_t cur = D.h0;
     int64_t r = D.r, it0 = D.it0;  // cursors: carry record (relative to the row, -1 = virtual), first staged interval
@@ -387,9 +451,9 @@ __device__ __forceinline__ void t3_tile(const TrkExecParams &P, const TileDesc &
             const int k = tid + q * T2_THREADS;
             is[q] = ie[q] = 0, iv[q] = 0.0f;
             if (k < cnt) {
-                is[q] = __ldg(T.itv_starts + it0 + k);
-                ie[q] = __ldg(T.itv_ends + it0 + k);
-                iv[q] = __ldg(T.itv_values + it0 + k);
+                is[q] = __ldg(srcg.its + it0 + k);
+                ie[q] = __ldg(srcg.ite + it0 + k);
+                iv[q] = __ldg(srcg.itv + it0 + k);
             }
         }
         const int dst0 = r < 0 ? 1 : 0;
@@ -473,7 +537,7 @@ __device__ __forceinline__ void t3_tile(const TrkExecParams &P, const TileDesc &
                 const TRec rr = R[i];
                 const bool live = i == 0 ? (cur < rr.e) : true;
                 if (live) {
-                    if (rr.vdiff > 0 && T.strategy != GVL_FILL_REPEAT_5P) {
+                    if (rr.vdiff > 0 && X.strategy != GVL_FILL_REPEAT_5P) {
                         S.fill_list[atomicAdd(&S.n_fill, 1)] = i;
                         need_fill = true;
                     }
@@ -494,7 +558,7 @@ __device__ __forceinline__ void t3_tile(const TrkExecParams &P, const TileDesc &
                 const TRec rr = R[S.fill_list[f]];
                 const int32_t lo = max(rr.a, cur), hi = min(rr.e, pass_end);
                 for (int32_t p = lo + lane; p < hi; p += 32) {
-                    S.val[p - cur] = insertion_fill_value(src, T.strategy, T.param, rr.vlen, rr.vrel, p - rr.a, p, base_seed, qseed, hap);
+                    S.val[p - cur] = insertion_fill_value(src, X.strategy, X.param, rr.vlen, rr.vrel, p - rr.a, p, base_seed, qseed, hap);
                     t2_set_bit(mk, mk2, p - cur);
                 }
             }
@@ -506,49 +570,9 @@ __device__ __forceinline__ void t3_tile(const TrkExecParams &P, const TileDesc &
         const int32_t jo_hi = rc ? L - cur : pass_end;
         const int32_t j0 = (int32_t)(((base_elems + jo_lo) & ~(int64_t)7) - base_elems);  // may be < jo_lo
         const int32_t n_chunks = (jo_hi - j0 + 7) >> 3;
-        int32_t j = j0 + 8 * tid;                                // first output position of the thread's chunk
-        int32_t u_lo = (rc ? (L - 8 - j) : j) - cur;             // its lowest tile-relative haplotype position
-        const int32_t du = rc ? -8 * T2_THREADS : 8 * T2_THREADS;
-        float *dst = out_row + j;
-        for (int32_t c = tid; c < n_chunks; c += T2_THREADS, j += 8 * T2_THREADS, u_lo += du, dst += 8 * T2_THREADS) {
-            uint32_t bits;
-            if (u_lo >= 0) {
-                const int w = u_lo >> 5;
-                bits = __funnelshift_r(mk[w], mk[w + 1], u_lo & 31) & 0xffu;
-            } else {
-                bits = (mk[0] << (-u_lo)) & 0xffu;
-            }
-            float cv = 0.0f;
-            const int q = max(u_lo, 0) - 1;  // last position before the chunk (position 0 always holds a marker)
-            if (q >= 0) {
-                int w = q >> 5;
-                uint32_t mm = mk[w] & (0xffffffffu >> (31 - (q & 31)));
-                if (mm == 0u) {
-                    int w2 = w >> 5;
-                    uint32_t m2 = mk2[w2] & ((1u << (w & 31)) - 1u);
-                    while (m2 == 0u) m2 = mk2[--w2];
-                    w = 32 * w2 + 31 - __clz(m2);
-                    mm = mk[w];
-                }
-                cv = S.val[32 * w + 31 - __clz(mm)];
-            }
-            float x[8];
-#pragma unroll
-            for (int t = 0; t < 8; t++) {
-                if ((bits >> t) & 1u) cv = S.val[u_lo + t];
-                x[t] = cv;
-            }
-            if (j >= jo_lo && j + 8 <= jo_hi) {
-                if (rc) stg_f8(dst, x[7], x[6], x[5], x[4], x[3], x[2], x[1], x[0]);
-                else stg_f8(dst, x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
-            } else {  // chunk cut by the tile / row ends
-#pragma unroll
-                for (int t = 0; t < 8; t++) {
-                    const int32_t jj = j + t;
-                    if (jj >= jo_lo && jj < jo_hi) dst[t] = rc ? x[7 - t] : x[t];
-                }
-            }
-        }
+        // (the two directions are separate instantiations: the walk then writes its registers in output order)
+        if (rc) t3_write_chunks<true>(S, out_row, j0, n_chunks, jo_lo, jo_hi, L, cur);
+        else t3_write_chunks<false>(S, out_row, j0, n_chunks, jo_lo, jo_hi, L, cur);
         if (!BIG || pass_end >= h1) break;
 
         // ---- (rare) the tile goes on: cursors of the next sub-pass ----
@@ -577,7 +601,7 @@ __device__ __forceinline__ void t3_tile(const TrkExecParams &P, const TileDesc &
                 const int64_t gpos = q_start + src_next;
                 while (a < bb) {
                     const int64_t mid = (a + bb) >> 1;
-                    if ((int64_t)T.itv_ends[mid] <= gpos) a = mid + 1; else bb = mid;
+                    if ((int64_t)srcg.ite[mid] <= gpos) a = mid + 1; else bb = mid;
                 }
                 it_next = a;
             }
@@ -593,26 +617,64 @@ __device__ __forceinline__ void t3_tile(const TrkExecParams &P, const TileDesc &
     }
 }
 
-__global__ void __launch_bounds__(T2_THREADS, 5) trk_exec3_kernel(TrkExecParams P, const TileDesc *__restrict__ tdesc) {
+// (the rare sub-pass variant is kept out of line: its register needs must not weigh on the common path)
+// (it takes its context from shared memory and re-reads the descriptor: structs passed by value or reference would
+//  make every thread of EVERY tile spill them to local memory before the branch)
+__device__ __noinline__ void t3_tile_big(T3Smem *S, const TileDesc *__restrict__ dp) {
+    const TileCtx X = *reinterpret_cast<const TileCtx *>(S->big_ctx);
+    const TileDesc D = *dp;
+    __syncthreads();  // everyone holds its copy before shared memory is reused
+    t3_tile<true>(X, D, *S);
+}
+static_assert(sizeof(TileCtx) <= 128, "TileCtx must fit T3Smem::big_ctx");
+
+#ifndef GVL_T3_MINB
+#define GVL_T3_MINB 4
+#endif
+__global__ void __launch_bounds__(T2_THREADS, GVL_T3_MINB) trk_exec3_kernel(TrkExecParams P, const TileDesc *__restrict__ tdesc) {
     __shared__ __align__(16) T3Smem S;
-    const TileDesc D = tdesc[blockIdx.x];  // (same address in every thread: one broadcast load)
+    const unsigned track = blockIdx.y;
+    const TileDesc *dp = tdesc + ((size_t)track * (size_t)P.grid_per_track + blockIdx.x);
+    const TileDesc D = *dp;  // (same address in every thread: one broadcast load)
     if (D.row < 0) return;
-    const int64_t track = blockIdx.x / P.grid_per_track;
-    const TrkDesc T = P.tracks ? P.tracks[track] : P.inl[track];
+    const TrkDesc *Tp = P.tracks ? P.tracks + track : nullptr;
+    TileCtx X;
+    {
+        const int64_t query = D.query;
+        const int64_t sub = P.sub_batch;
+        X.hap = (uint64_t)(D.row - D.query * (int32_t)P.ploidy);
+        X.qseed = P.query_seed ? (uint64_t)P.query_seed[query] : (uint64_t)(sub > 0 ? query % sub : query);
+        X.base_seed = P.base_seed_dev ? P.base_seed_dev[sub > 0 ? query / sub : 0] : P.base_seed;
+        X.recs = P.trecs + D.rec_base;
+        X.out_row = P.out + D.out_base;
+        X.base_elems = (int64_t)(reinterpret_cast<uintptr_t>(P.out) >> 2) + D.out_base;
+        // (kernel parameters are indexed with a compile-time subscript: a run-time one would copy them to local memory)
+        const TrkDesc *T = Tp;
+#define GVL_TRK_PICK(i) case i: if (!Tp) { X.srcg.its = P.inl[i].itv_starts; X.srcg.ite = P.inl[i].itv_ends; X.srcg.itv = P.inl[i].itv_values; \
+                                           X.srcg.dense = P.inl[i].dense; X.strategy = P.inl[i].strategy; X.param = P.inl[i].param; } break;
+        switch (track) {
+            GVL_TRK_PICK(0) GVL_TRK_PICK(1) GVL_TRK_PICK(2) GVL_TRK_PICK(3) GVL_TRK_PICK(4) GVL_TRK_PICK(5) GVL_TRK_PICK(6) GVL_TRK_PICK(7)
+            default: break;
+        }
+#undef GVL_TRK_PICK
+        if (T) {
+            X.srcg.its = T->itv_starts, X.srcg.ite = T->itv_ends, X.srcg.itv = T->itv_values, X.srcg.dense = T->dense;
+            X.strategy = T->strategy, X.param = T->param;
+        }
+        X.srcg.itv_lo = D.it_lo, X.srcg.itv_hi = D.it_hi, X.srcg.q_start = D.q_start, X.srcg.track_n = D.track_n;
+    }
     if (D.flags & TD_GENERIC) {
         const int32_t L = D.L;
         const bool rc = (D.flags & TD_RC) != 0;
-        const int64_t query = D.row / P.ploidy;
-        const uint64_t qseed = P.query_seed ? (uint64_t)P.query_seed[query]
-                                            : (uint64_t)(P.sub_batch > 0 ? query % P.sub_batch : query);
-        const uint64_t base_seed = P.base_seed_dev ? P.base_seed_dev[P.sub_batch > 0 ? query / P.sub_batch : 0] : P.base_seed;
-        const SrcGlobal srcg{T.itv_starts, T.itv_ends, T.itv_values, T.dense, D.it_lo, D.it_hi, D.q_start, D.track_n};
         const int32_t t0 = rc ? L - D.h1 : D.h0, t1 = rc ? L - D.h0 : D.h1;
-        t2_generic_segment(P.trecs + D.rec_base, D.n_rec, D.ref0, srcg, T, P.out + D.out_base, L, rc, t0, t1, base_seed, qseed,
-                           (uint64_t)(D.row % P.ploidy));
+        t2_generic_segment(X.recs, D.n_rec, D.ref0, X.srcg, X.strategy, X.param, X.out_row, L, rc, t0, t1, X.base_seed, X.qseed, X.hap);
         return;
     }
-    if (D.flags & TD_BIG) t3_tile<true>(P, D, T, S);
-    else t3_tile<false>(P, D, T, S);
+    if (D.flags & TD_BIG) {
+        if (threadIdx.x == 0) *reinterpret_cast<TileCtx *>(S.big_ctx) = X;
+        __syncthreads();
+        t3_tile_big(&S, dp);
+    } else {
+        t3_tile<false>(X, D, S);
+    }
 }
-

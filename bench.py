@@ -293,7 +293,7 @@ def run_b200(args):
     # ---- ring geometry: K steps = n_sub device calls of `ring` batches each, alternating between two halves ----
     out_bytes_step = bp_per_step * ({"onehot": 4, "u8": 1, "annotated": 9}[mode] + 4 * n_tracks_main)
     ring_cap = max(1, min(args.ring, int(args.ring_gib * (1 << 30)) // (2 * out_bytes_step)))
-    ring = max((r for r in range(1, ring_cap + 1) if args.steps % r == 0 and args.steps // r >= min(4, args.steps)), default=1)
+    ring = max((r for r in range(1, ring_cap + 1) if args.steps % r == 0 and args.steps // r >= min(args.min_calls, args.steps)), default=1)
     n_sub = args.steps // ring
     pipe = FixedPipeline(ds, pairs, ring=ring)
     n_q = ring * pairs
@@ -409,7 +409,7 @@ def run_b200(args):
     if not n_tracks_main and w.get("tracks_avail", 0) and mode == "onehot" and not args.no_tracks:
         nt = w["tracks_avail"]
         dst = ds0.with_tracks([f"track{i}" for i in range(nt)]).with_insertion_fill({"track0": Repeat5p(), "track1": Interpolate(1)})
-        ring_t = max((r for r in range(1, ring + 1) if args.steps % r == 0 and args.steps // r >= min(4, args.steps) and
+        ring_t = max((r for r in range(1, ring + 1) if args.steps % r == 0 and args.steps // r >= min(args.min_calls, args.steps) and
                       r * 2 * bp_per_step * (4 + 4 * nt) <= args.ring_gib * (1 << 30)), default=1)
         if ring_t == ring:
             pipe_t = FixedPipeline(dst, pairs, ring=ring_t)
@@ -572,6 +572,7 @@ def main():
     ap.add_argument("--mode", default="onehot", choices=["onehot", "u8", "annotated"],
                     help="output of the execute kernel (the headline metric is one-hot)")
     ap.add_argument("--ring", type=int, default=32, help="batches per device call, at most (must divide --steps)")
+    ap.add_argument("--min-calls", type=int, default=1, help="device calls per timed block, at least")
     ap.add_argument("--ring-gib", type=float, default=12.0, help="output memory of the two ring halves, at most")
     ap.add_argument("--no-tracks", action="store_true", help="skip the cfg3t extra leg")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

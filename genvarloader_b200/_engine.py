@@ -239,6 +239,28 @@ class Engine:
             ptr(base_seed_dev), c_i64(int(sub_batch)), ptr(query_seed), c_i64(int(max_records)), ptr(out), _stream()))
         return out
 
+    def realign_tracks_plan(self, names, regions, shifts, geno_offset_idx, offset_idxs, track_lengths, out_offsets,
+                            total_per_track: int, strategy_ids, params, base_seed: int, max_records: int, keep=None,
+                            keep_offsets=None, to_rc=None, query_seed=None, layout="tbp", base_seed_dev=None, batch=None,
+                            sub_batch: int = 0):
+        """gvl_dev_realign_tracks_plan: everything of `realign_tracks` but the execute launch (variant plan, tile map,
+        per-tile searches); `realign_tracks_exec(out)` writes the values, possibly on another stream."""
+        b_cap, ploidy = geno_offset_idx.shape
+        batch = b_cap if batch is None else int(batch)
+        n_tracks = len(names)
+        itv = (Intervals * n_tracks)(*[self.tracks[n][4] for n in names])
+        sid = (c_i32 * n_tracks)(*[int(s) for s in strategy_ids])
+        par = (C.c_double * n_tracks)(*[float(p) for p in params])
+        check(lib.gvl_dev_realign_tracks_plan(
+            self.ctx.handle, C.byref(self.tab), ptr(regions), ptr(shifts), ptr(geno_offset_idx), c_i64(batch), c_i64(ploidy),
+            ptr(keep), ptr(keep_offsets), ptr(to_rc), c_i64(n_tracks), itv, ptr(offset_idxs), ptr(track_lengths),
+            ptr(out_offsets), c_i64(int(total_per_track)), sid, par, c_u64(int(base_seed)), ptr(base_seed_dev),
+            c_i64(int(sub_batch)), ptr(query_seed), c_i64(int(max_records)), C.c_int(1 if layout == "btp" else 0), _stream()))
+
+    def realign_tracks_exec(self, out):
+        check(lib.gvl_dev_realign_tracks_exec(self.ctx.handle, ptr(out), _stream()))
+        return out
+
     def intervals_to_tracks(self, name, offset_idxs, starts, out_offsets, total: int, out=None):
         """gvl_dev_intervals_to_tracks: paint one track's stored intervals into dense windows."""
         n_q = int(starts.numel())

@@ -207,6 +207,10 @@ class FixedPipeline:
                      out_offsets=scr.out_offsets, diffs=scr.diffs)
         if sp.realign:
             eng.track_lengths(scr.regions, scr.diffs, n, sp.p, scr.track_lengths)
+            eng.realign_tracks_plan(sp.names, scr.regions, scr.shifts, scr.goi, scr.offset_idxs, scr.track_lengths,
+                                    scr.out_offsets, n * sp.p * sp.L, sp.fill_ids, sp.fill_params, 0, self._cap(n),
+                                    to_rc=scr.to_rc if sp.rc_neg else None, layout="btp", base_seed_dev=scr.base_seed, batch=n,
+                                    sub_batch=sub_batch)
 
     def _stage_exec(self, eng: Engine, scr: _Scratch, out: _Out, n: int, sub_batch: int = 0):
         sp = self.spec
@@ -215,9 +219,7 @@ class FixedPipeline:
             eng.execute(sp.mode, out=out.seq, annot_v=out.av, annot_pos=out.ap)
         if sp.t:
             if sp.realign:
-                eng.realign_tracks(sp.names, scr.regions, scr.shifts, scr.goi, scr.offset_idxs, scr.track_lengths,
-                                   scr.out_offsets, n * sp.p * sp.L, sp.fill_ids, sp.fill_params, 0, self._cap(n), to_rc=rc,
-                                   out=out.trk, layout="btp", base_seed_dev=scr.base_seed, batch=n, sub_batch=sub_batch)
+                eng.realign_tracks_exec(out.trk)
             else:
                 eng.paint_tracks(sp.names, scr.offset_idxs, scr.starts, self._paint_off, n * sp.L,
                                  scr.to_rc_q if sp.rc_neg else None, out=out.trk, n_queries=n)

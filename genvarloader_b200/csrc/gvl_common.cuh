@@ -108,6 +108,8 @@ struct gvl_ctx {
     int64_t total;      // -1 = unknown (ragged before sync)
     int64_t *plan_out_offsets;  // device pointer supplied at plan time
     int last_exec_kernel;       // 0 byte-oriented, 1 packed one-hot (gvl_debug_last_exec_kernel)
+    void *trk_params;           // parameters of the pending track execute launch (gvl_tracks.cu)
+    bool trk_plan_valid;
     void *zeros;                // device zeros (gvl_aux.cu: rows without genotypes)
     int64_t zeros_bytes;
     // host layer

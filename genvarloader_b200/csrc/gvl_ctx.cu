@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "gvl_internal.cuh"
@@ -159,6 +160,8 @@ int gvl_ctx_create(int device, gvl_ctx **out) {
     ctx->plan_out_offsets = nullptr;
     ctx->last_exec_kernel = 0;
     ctx->zeros = nullptr;
+    ctx->trk_params = nullptr;
+    ctx->trk_plan_valid = false;
     ctx->zeros_bytes = 0;
     ctx->pinned = nullptr;
     ctx->pinned_bytes = 0;
@@ -186,6 +189,7 @@ void gvl_ctx_destroy(gvl_ctx *ctx) {
     cudaFree(ctx->dev_words);
     cudaFree(ctx->trk_desc);
     cudaFree(ctx->zeros);
+    free(ctx->trk_params);
     if (ctx->host_words) cudaFreeHost(ctx->host_words);
     for (auto &kv : ctx->statics) cudaFree(kv.second.dev);
     for (auto &kv : ctx->packed_refs) cudaFree(kv.second);

@@ -12,6 +12,9 @@
 // HBM), then every thread produces 4 consecutive output values per step (source span copies,
 // deletion/insertion fills, trailing zeros, reversal for negative strands) and writes them with one
 // 16-byte store.
+#include <cstdlib>
+#include <cstring>
+
 #include "gvl_internal.cuh"
 
 namespace gvl {
@@ -309,6 +312,17 @@ __global__ void prng_kernel(uint64_t a, uint64_t b, uint64_t c, uint64_t d, int 
 
 using namespace gvl;
 
+static int trk_execute(gvl_ctx *ctx, float *out, cudaStream_t st) {
+    if (!ctx->trk_plan_valid || !ctx->trk_params) return fail(GVL_ERR_STATE, "track execute without a track plan");
+    if (!out || ((uintptr_t)out & 3)) return fail(GVL_ERR_ARG, "track output must be a float buffer");
+    TrkExecParams P;
+    memcpy(&P, ctx->trk_params, sizeof(P));
+    P.out = out;
+    trk_exec3_kernel<<<dim3((unsigned)P.grid_per_track, (unsigned)P.n_tracks), T2_THREADS, 0, st>>>(P, (const TileDesc *)ctx->trk.tdesc);
+    GVL_LAUNCH_CHECK();
+    return GVL_OK;
+}
+
 static int launch_trk_exec(gvl_ctx *ctx, int64_t n_work, int64_t ploidy, int64_t n_queries, int64_t n_tracks,
                            const TrkDesc *host_desc, const int64_t *offset_idxs, int64_t total_per_track,
                            const int64_t *query_seed, uint64_t base_seed, float *out, int layout_btp, cudaStream_t st,
@@ -349,9 +363,13 @@ static int launch_trk_exec(gvl_ctx *ctx, int64_t n_work, int64_t ploidy, int64_t
     TileDesc *tdesc = (TileDesc *)ctx->trk.tdesc;
     trk_tile_prep_kernel<<<(unsigned)((grid + 127) / 128), 128, 0, st>>>(P, tdesc);
     GVL_LAUNCH_CHECK();
-    trk_exec3_kernel<<<dim3((unsigned)P.grid_per_track, (unsigned)n_tracks), T2_THREADS, 0, st>>>(P, tdesc);
-    GVL_LAUNCH_CHECK();
-    return GVL_OK;
+    // the execute launch may follow later, on another stream (gvl_dev_realign_tracks_exec): keep its parameters
+    if (!ctx->trk_params) ctx->trk_params = malloc(sizeof(TrkExecParams));
+    if (!ctx->trk_params) return fail(GVL_ERR_ARG, "out of host memory");
+    memcpy(ctx->trk_params, &P, sizeof(P));
+    ctx->trk_plan_valid = true;
+    if (!out) return GVL_OK;  // plan only
+    return trk_execute(ctx, out, st);
 }
 
 // svar2 two-channel merge (gvl_svar2.cu)
@@ -368,15 +386,18 @@ static int realign_impl(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_sv
                         const int32_t *track_lengths, const int64_t *out_offsets, int64_t total_per_track,
                         const int32_t *strategy_ids, const double *params, uint64_t base_seed,
                         const int64_t *query_seed, int64_t max_records, float *out, gvl_stream stream,
-                        int layout_btp = 0, const uint64_t *base_seed_dev = nullptr, int64_t sub_batch = 0) {
+                        int layout_btp = 0, const uint64_t *base_seed_dev = nullptr, int64_t sub_batch = 0,
+                        bool plan_only = false) {
     if (!ctx || !tab || !regions || !shifts || !(geno_offset_idx || svar2) || !(itv || dense) || !(offset_idxs || dense) ||
         !track_lengths || !out_offsets || !strategy_ids || !params)
         return fail(GVL_ERR_ARG, "gvl_dev_realign_tracks: NULL argument");
     cudaStream_t st = (cudaStream_t)stream;
     GVL_CUDA(cudaSetDevice(ctx->device));
     const int64_t n_work = batch * ploidy;
+    ctx->trk_plan_valid = false;
     if (n_work == 0 || n_tracks == 0 || total_per_track == 0) return GVL_OK;
-    if (!out || ((uintptr_t)out & 15)) return fail(GVL_ERR_ARG, "gvl_dev_realign_tracks: out must be 16-byte aligned");
+    if (!plan_only && (!out || ((uintptr_t)out & 15))) return fail(GVL_ERR_ARG, "gvl_dev_realign_tracks: out must be 16-byte aligned");
+    if (plan_only) out = nullptr;
     int rc;
     if ((rc = ensure_rows(ctx, ctx->trk, n_work))) return rc;
     if ((rc = ensure_trecs(ctx, ctx->trk, max_records + n_work))) return rc;
@@ -452,6 +473,28 @@ int gvl_dev_realign_tracks_btp(gvl_ctx *ctx, const gvl_sparse_tables *tab, const
     return realign_impl(ctx, tab, nullptr, regions, shifts, geno_offset_idx, batch, ploidy, keep, keep_offsets, to_rc, n_tracks,
                         itv, offset_idxs, nullptr, nullptr, track_lengths, out_offsets, total_per_track, strategy_ids,
                         params, base_seed, query_seed, max_records, out, stream, 1, base_seed_dev, sub_batch);
+}
+
+int gvl_dev_realign_tracks_plan(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_t *regions, const int32_t *shifts,
+                                const int64_t *geno_offset_idx, int64_t batch, int64_t ploidy, const uint8_t *keep,
+                                const int64_t *keep_offsets, const uint8_t *to_rc, int64_t n_tracks, const gvl_intervals *itv,
+                                const int64_t *offset_idxs, const int32_t *track_lengths, const int64_t *out_offsets,
+                                int64_t total_per_track, const int32_t *strategy_ids, const double *params, uint64_t base_seed,
+                                const uint64_t *base_seed_dev, int64_t sub_batch, const int64_t *query_seed,
+                                int64_t max_records, int layout_btp, gvl_stream stream) {
+    if (!itv || !offset_idxs) return fail(GVL_ERR_ARG, "gvl_dev_realign_tracks_plan: NULL argument");
+    return realign_impl(ctx, tab, nullptr, regions, shifts, geno_offset_idx, batch, ploidy, keep, keep_offsets, to_rc, n_tracks,
+                        itv, offset_idxs, nullptr, nullptr, track_lengths, out_offsets, total_per_track, strategy_ids,
+                        params, base_seed, query_seed, max_records, nullptr, stream, layout_btp ? 1 : 0, base_seed_dev, sub_batch,
+                        true);
+}
+
+int gvl_dev_realign_tracks_exec(gvl_ctx *ctx, float *out, gvl_stream stream) {
+    if (!ctx) return fail(GVL_ERR_ARG, "gvl_dev_realign_tracks_exec: ctx is NULL");
+    GVL_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->trk_plan_valid) return GVL_OK;  // (the plan was empty: nothing to write)
+    if ((uintptr_t)out & 15) return fail(GVL_ERR_ARG, "gvl_dev_realign_tracks_exec: out must be 16-byte aligned");
+    return trk_execute(ctx, out, (cudaStream_t)stream);
 }
 
 int gvl_dev_shift_and_realign_tracks(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_t *regions,

@@ -227,6 +227,19 @@ int gvl_dev_realign_tracks_btp(gvl_ctx *ctx, const gvl_sparse_tables *tab, const
                                const uint64_t *base_seed_dev, int64_t sub_batch, const int64_t *query_seed,
                                int64_t max_records, float *out, gvl_stream stream);
 
+/* gvl_dev_realign_tracks in two steps, so that a pipeline can run the latency-bound part (variant plan, tile map, per-tile
+ * searches) on one stream and the bandwidth-bound execute launch on another: _plan takes the arguments of
+ * gvl_dev_realign_tracks (layout_btp selects the (b, t, p, ~l) order) except `out`; _exec writes the planned call into
+ * `out` (device f32[n_tracks * total_per_track], 16-byte aligned).  The caller orders the two (stream / event). */
+int gvl_dev_realign_tracks_plan(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_t *regions, const int32_t *shifts,
+                                const int64_t *geno_offset_idx, int64_t batch, int64_t ploidy, const uint8_t *keep,
+                                const int64_t *keep_offsets, const uint8_t *to_rc, int64_t n_tracks, const gvl_intervals *itv,
+                                const int64_t *offset_idxs, const int32_t *track_lengths, const int64_t *out_offsets,
+                                int64_t total_per_track, const int32_t *strategy_ids, const double *params, uint64_t base_seed,
+                                const uint64_t *base_seed_dev, int64_t sub_batch, const int64_t *query_seed,
+                                int64_t max_records, int layout_btp, gvl_stream stream);
+int gvl_dev_realign_tracks_exec(gvl_ctx *ctx, float *out, gvl_stream stream);
+
 /* shift_and_realign_tracks_sparse on device (src/ffi/mod.rs:2439-2458): ONE track whose source is
  * a dense f32 window per query (`tracks` ragged by `track_offsets` i64[b+1]) instead of intervals.
  * track_lengths[q] = track_offsets[q+1]-track_offsets[q] as device i32[b]. */

@@ -95,11 +95,35 @@ class Dataset:
                    track_kinds=kinds, active_tracks=tuple(kinds), rng=np.random.default_rng(rng))
 
     @classmethod
-    def from_synth(cls, device, d, rng=None) -> "Dataset":
-        """From a `genvarloader_b200.synth.SynthData`."""
+    def from_synth(cls, device, d, rng=None, svar2=None) -> "Dataset":
+        """From a `genvarloader_b200.synth.SynthData`; `svar2`: a `synth.to_svar2_dataset(d)` dict = keep the variants as
+        a resident svar2 two-channel source instead of the SVAR1 CSR."""
+        if svar2 is not None:
+            return cls.from_svar2_arrays(device, d.reference, d.ref_offsets, svar2, d.regions, d.n_samples, d.ploidy,
+                                         d.max_jitter, d.tracks, rng=rng)
         return cls.from_arrays(device, d.reference, d.ref_offsets, d.v_starts, d.ilens, d.alt_alleles, d.alt_offsets,
                                d.geno_v_idxs, d.geno_offsets, d.regions, d.n_samples, d.ploidy, d.max_jitter, d.tracks,
                                rng=rng)
+
+    @classmethod
+    def from_svar2_arrays(cls, device, reference, ref_offsets, sv: dict, regions, n_samples: int, ploidy: int,
+                          max_jitter: int = 0, tracks: dict | None = None, track_kinds: dict | None = None,
+                          sample_names=None, rng=None) -> "Dataset":
+        """In-memory dataset over a resident svar2 two-channel variant source -- the GPU counterpart of `Svar2Haps`
+        (python/genvarloader/_dataset/_svar2_haps.py:183): per-(region, sample, ploid) var_key ranges, per-region dense
+        windows and presence bits (docs/source/format.md:88-96) stay in HBM, every read merges the two channels on the
+        device (src/svar2/mod.rs:45-66).  `sv`: see `synth.to_svar2_dataset` for the arrays."""
+        regions = np.ascontiguousarray(regions, np.int32)
+        eng = Engine.from_svar2(device, reference, ref_offsets, sv, len(regions) * int(n_samples) * int(ploidy))
+        kinds = {}
+        for name, t in (tracks or {}).items():
+            eng.add_track(name, *t)
+            kinds[name] = (track_kinds or {}).get(name, "sample")
+        if regions.shape[1] == 3:
+            regions = np.concatenate([regions, np.ones((len(regions), 1), np.int32)], 1)
+        names = tuple(sample_names) if sample_names is not None else tuple(f"s{i}" for i in range(n_samples))
+        return cls(engine=eng, full_regions=regions, sample_names=names, ploidy=int(ploidy), max_jitter=int(max_jitter),
+                   track_kinds=kinds, active_tracks=tuple(kinds), rng=np.random.default_rng(rng))
 
     @classmethod
     def open(cls, path, reference=None, device="cuda", jitter: int = 0, rng=None, deterministic: bool = True,
@@ -237,6 +261,8 @@ class Dataset:
             kw["deterministic"] = bool(deterministic)
         if rc_neg is not None:
             kw["rc_neg"] = bool(rc_neg)
+        if var_filter not in (None, False) and self.engine.svar2 is not None:
+            raise NotImplementedError("var_filter is not supported with the svar2 source")
         if var_filter is not None:
             if var_filter not in (False, "exonic"):
                 raise ValueError(f"var_filter must be False or 'exonic', got {var_filter!r}")
@@ -605,12 +631,13 @@ class Dataset:
             if fixed and not self.deterministic and not is_ref:
                 # random shifts need the diffs first (_haps.py:720-730): one extra device pass + sync; the
                 # draw itself stays on the host generator so seeded runs follow the reference's RNG order
-                dd = eng.get_diffs(t_goi, t_reg[:, 1].contiguous(), t_reg[:, 2].contiguous(), keep, keep_off).cpu().numpy()
+                dd = eng.get_diffs(t_goi, t_reg[:, 1].contiguous(), t_reg[:, 2].contiguous(), keep, keep_off, regions=t_reg,
+                                   max_records=max_rec).cpu().numpy()
                 max_shift = dd.clip(min=0) + (lengths - out_len).clip(min=0)[:, None]
                 t_shifts = torch.from_numpy(self.rng.integers(0, max_shift + 1, dtype=np.int32)).to(dev)
             if realign:
                 diffs = torch.empty((b, rows_p), dtype=torch.int32, device=dev)
-            oo = eng.plan(t_reg, t_shifts, t_goi, out_len, max_rec, keep, keep_off, t_rc, diffs=diffs)
+            oo = eng.plan(t_reg, t_shifts, t_goi, out_len, max_rec, keep, keep_off, t_rc, diffs=diffs, use_svar2=not is_ref)
             total = eng.total()
             shape = (b, None) if is_ref else (b, p, None)  # Ref has no ploidy axis (_dataset/_ref.py)
             if self.sequence_type == "annotated":

@@ -12,8 +12,8 @@ import numpy as np
 import torch
 
 from . import _ffi
-from ._ffi import (MODE_ANNOTATED, MODE_ONEHOT, MODE_ONEHOT_CF, MODE_U8, DatasetView, Intervals, SparseTables, c_i32,
-                   c_i64, c_u8, c_u64, c_vp, check, lib, ptr)
+from ._ffi import (MODE_ANNOTATED, MODE_ONEHOT, MODE_ONEHOT_CF, MODE_U8, DatasetView, Intervals, SparseTables, Svar2Channels,
+                   c_i32, c_i64, c_u8, c_u64, c_vp, check, lib, ptr)
 
 MODES = {"haplotypes": MODE_U8, "u8": MODE_U8, "onehot": MODE_ONEHOT, "onehot_cf": MODE_ONEHOT_CF,
          "annotated": MODE_ANNOTATED}
@@ -96,8 +96,42 @@ class Engine:
             ptr(self.geno_starts), ptr(self.geno_stops), int(self.geno_starts.numel()), ptr(self.ref_packed),
             ptr(self.alt_packed))
         self.tracks: dict[str, tuple] = {}
+        self.svar2 = None  # resident svar2 two-channel source (set_svar2)
         self._n_work = 0
         self._fixed = -1
+
+    # ------------------------------------------------------------------ svar2 source
+    @classmethod
+    def from_svar2(cls, device, reference, ref_offsets, sv: dict, n_slots: int, pad_char: int = ord("N")) -> "Engine":
+        """Engine over a RESIDENT svar2 two-channel source (`synth.to_svar2_dataset` layout; the reference keeps the same
+        information as range tables into the .svar2 store, docs/source/format.md:88-96, `_svar2_haps.py:1269-1313`).
+        The variant table of the engine is the DECODED key table (ilen, ALT bytes); the SVAR1 genotype CSR is empty."""
+        eng = cls(device, reference, ref_offsets, np.zeros(sv["key_ilen"].size, np.int32), sv["key_ilen"], sv["key_alt"],
+                  sv["key_alt_off"], np.zeros(0, np.int32), np.zeros(n_slots + 1, np.int64), pad_char=pad_char)
+        eng.set_svar2(sv)
+        return eng
+
+    def set_svar2(self, sv: dict) -> None:
+        d = self.device
+        with torch.cuda.device(d):
+            t = dict(vk_pos=_dev(sv["vk_pos"], np.int32, d, pad=4), vk_key=_dev(sv["vk_key"], np.int32, d, pad=4),
+                     vk_lo=_dev(sv["vk_range"][0], np.int64, d), vk_hi=_dev(sv["vk_range"][1], np.int64, d),
+                     dense_pos=_dev(sv["dense_pos"], np.int32, d, pad=4), dense_key=_dev(sv["dense_key"], np.int32, d, pad=4),
+                     dense_range=_dev(sv["dense_range"], np.int32, d, pad=2), dense_present=_dev(sv["dense_present"], np.uint8, d, pad=16),
+                     present_off=_dev(sv["present_off"], np.int64, d))
+        vk_len = np.asarray(sv["vk_range"][1] - sv["vk_range"][0], np.int64)
+        win = np.asarray(sv["dense_range"][:, 1] - sv["dense_range"][:, 0], np.int64)
+        spr = int(sv["slots_per_region"])
+        self.svar2 = dict(t=t, spr=spr, vk_len=vk_len, win=win)
+        # longest merged list of any slot (var_key entries + the whole dense window): workspace capacity per row
+        self.max_slot_len = int((vk_len.max() if vk_len.size else 0) + (win.max() if win.size else 0))
+
+    def svar2_channels(self, geno_offset_idx) -> Svar2Channels:
+        """gvl_svar2_channels over the resident tables; row k reads slot geno_offset_idx[k] (device i64 (b, p))."""
+        t, spr = self.svar2["t"], self.svar2["spr"]
+        return Svar2Channels(ptr(t["vk_pos"]), ptr(t["vk_key"]), ptr(t["vk_lo"]), ptr(t["dense_pos"]), ptr(t["dense_key"]),
+                             ptr(t["dense_range"]), ptr(t["dense_present"]), ptr(t["present_off"]), ptr(t["vk_hi"]),
+                             ptr(geno_offset_idx), spr)
 
     def fork(self) -> "Engine":
         """A second planning context (own workspace) over the SAME device tables -- one per pipeline
@@ -165,17 +199,29 @@ class Engine:
     def max_records(self, geno_offset_idx_host: np.ndarray) -> int:
         """Upper bound on the summed per-row variant counts (host O(batch) gather)."""
         g = np.asarray(geno_offset_idx_host).reshape(-1)
+        if self.svar2 is not None and g.size and int(g.max()) < self.empty_slot:
+            sv = self.svar2  # merged lists: own var_key entries + the region's whole dense window
+            return int(sv["vk_len"][g].sum() + sv["win"][g // sv["spr"]].sum())
         d = self.geno_offsets_host[1, g] - self.geno_offsets_host[0, g]
         return int(np.maximum(d, 0).sum())
 
     # ------------------------------------------------------------------ haplotypes
     def plan(self, regions: torch.Tensor, shifts: torch.Tensor, geno_offset_idx: torch.Tensor, output_length: int,
-             max_records: int, keep=None, keep_offsets=None, to_rc=None, out_offsets=None, diffs=None):
+             max_records: int, keep=None, keep_offsets=None, to_rc=None, out_offsets=None, diffs=None, use_svar2=True):
         """gvl_dev_hap_plan.  All tensors live on this engine's device; nothing synchronises."""
         batch, ploidy = geno_offset_idx.shape
         n_work = batch * ploidy
         if out_offsets is None:
             out_offsets = torch.empty(n_work + 1, dtype=torch.int64, device=self.device)
+        if self.svar2 is not None and use_svar2:
+            if keep is not None:
+                raise NotImplementedError("keep masks (var_filter) are not supported with the svar2 source")
+            ch = self.svar2_channels(geno_offset_idx)
+            check(lib.gvl_dev_hap_plan_svar2(self.ctx.handle, C.byref(self.tab), C.byref(ch), ptr(regions), ptr(shifts),
+                                             c_i64(batch), c_i64(ploidy), ptr(to_rc), c_i64(int(output_length)),
+                                             c_i64(int(max_records)), ptr(out_offsets), ptr(diffs), _stream()))
+            self._n_work, self._fixed = n_work, int(output_length)
+            return out_offsets
         check(lib.gvl_dev_hap_plan(self.ctx.handle, C.byref(self.tab), ptr(regions), ptr(shifts), ptr(geno_offset_idx),
                                    c_i64(batch), c_i64(ploidy), ptr(keep), ptr(keep_offsets), ptr(to_rc),
                                    c_i64(int(output_length)), c_i64(int(max_records)), ptr(out_offsets), ptr(diffs),
@@ -206,9 +252,15 @@ class Engine:
             return out, annot_v, annot_pos
         return out
 
-    def get_diffs(self, geno_offset_idx, q_starts=None, q_ends=None, keep=None, keep_offsets=None, clipped=True):
+    def get_diffs(self, geno_offset_idx, q_starts=None, q_ends=None, keep=None, keep_offsets=None, clipped=True, regions=None,
+                  max_records: int = 0):
         n_q, ploidy = geno_offset_idx.shape
         diffs = torch.empty((n_q, ploidy), dtype=torch.int32, device=self.device)
+        if self.svar2 is not None:  # hap_diffs_svar2 over the merged lists (src/svar2/mod.rs:73-146)
+            ch = self.svar2_channels(geno_offset_idx)
+            check(lib.gvl_dev_hap_diffs_svar2(self.ctx.handle, C.byref(self.tab), C.byref(ch), ptr(regions), c_i64(n_q),
+                                              c_i64(ploidy), c_i64(int(max_records)), ptr(diffs), _stream()))
+            return diffs
         check(lib.gvl_dev_get_diffs_sparse(self.ctx.handle, C.byref(self.tab), ptr(geno_offset_idx), c_i64(n_q),
                                            c_i64(ploidy), ptr(keep), ptr(keep_offsets), ptr(q_starts), ptr(q_ends),
                                            C.c_int(1 if clipped else 0), ptr(diffs), _stream()))
@@ -226,11 +278,16 @@ class Engine:
         b_cap, ploidy = geno_offset_idx.shape
         batch = b_cap if batch is None else int(batch)  # (a prefix of preallocated buffers)
         n_tracks = len(names)
+        if out is None:
+            out = torch.empty(n_tracks * total_per_track, dtype=torch.float32, device=self.device)
+        if self.svar2 is not None:
+            self.realign_tracks_plan(names, regions, shifts, geno_offset_idx, offset_idxs, track_lengths, out_offsets,
+                                     total_per_track, strategy_ids, params, base_seed, max_records, keep, keep_offsets, to_rc,
+                                     query_seed, layout, base_seed_dev, batch, sub_batch)
+            return self.realign_tracks_exec(out)
         itv = (Intervals * n_tracks)(*[self.tracks[n][4] for n in names])
         sid = (c_i32 * n_tracks)(*[int(s) for s in strategy_ids])
         par = (C.c_double * n_tracks)(*[float(p) for p in params])
-        if out is None:
-            out = torch.empty(n_tracks * total_per_track, dtype=torch.float32, device=self.device)
         fn = lib.gvl_dev_realign_tracks_btp if layout == "btp" else lib.gvl_dev_realign_tracks
         check(fn(
             self.ctx.handle, C.byref(self.tab), ptr(regions), ptr(shifts), ptr(geno_offset_idx), c_i64(batch),
@@ -251,8 +308,10 @@ class Engine:
         itv = (Intervals * n_tracks)(*[self.tracks[n][4] for n in names])
         sid = (c_i32 * n_tracks)(*[int(s) for s in strategy_ids])
         par = (C.c_double * n_tracks)(*[float(p) for p in params])
+        ch = self.svar2_channels(geno_offset_idx) if self.svar2 is not None else None
         check(lib.gvl_dev_realign_tracks_plan(
-            self.ctx.handle, C.byref(self.tab), ptr(regions), ptr(shifts), ptr(geno_offset_idx), c_i64(batch), c_i64(ploidy),
+            self.ctx.handle, C.byref(self.tab), C.byref(ch) if ch is not None else c_vp(0), ptr(regions), ptr(shifts),
+            ptr(geno_offset_idx), c_i64(batch), c_i64(ploidy),
             ptr(keep), ptr(keep_offsets), ptr(to_rc), c_i64(n_tracks), itv, ptr(offset_idxs), ptr(track_lengths),
             ptr(out_offsets), c_i64(int(total_per_track)), sid, par, c_u64(int(base_seed)), ptr(base_seed_dev),
             c_i64(int(sub_batch)), ptr(query_seed), c_i64(int(max_records)), C.c_int(1 if layout == "btp" else 0), _stream()))

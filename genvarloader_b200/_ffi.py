@@ -46,6 +46,14 @@ class Intervals(C.Structure):
                 ("n_slots", c_i64)]
 
 
+class Svar2Channels(C.Structure):
+    """gvl_svar2_channels (include/gvl_b200.h)."""
+
+    _fields_ = [("vk_pos", c_vp), ("vk_key", c_vp), ("vk_off", c_vp), ("dense_pos", c_vp), ("dense_key", c_vp),
+                ("dense_range", c_vp), ("dense_present", c_vp), ("dense_present_off", c_vp), ("vk_stop", c_vp),
+                ("row_slot", c_vp), ("query_div", c_i64)]
+
+
 class DatasetView(C.Structure):
     """gvl_dataset_view (include/gvl_b200.h)."""
 

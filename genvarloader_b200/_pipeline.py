@@ -97,8 +97,6 @@ def supports(ds) -> str | None:
         return "nothing to read"
     if len(ds.active_tracks) > 8:
         return "more than 8 tracks"
-    if getattr(ds.engine, "svar2", None) is not None:
-        return "svar2 source"
     return None
 
 
@@ -204,7 +202,7 @@ class FixedPipeline:
         eng.batch_prep(self.view, idx_dev, jit_dev, n, self.ref_slot, sp.t, sp.annot_mask, scr.args, sub_batch=sub_batch)
         if sp.want_seqs:
             eng.plan(scr.regions, scr.shifts, scr.goi[:n], sp.L, self._cap(n), to_rc=scr.to_rc if sp.rc_neg else None,
-                     out_offsets=scr.out_offsets, diffs=scr.diffs)
+                     out_offsets=scr.out_offsets, diffs=scr.diffs, use_svar2=not sp.is_ref)
         if sp.realign:
             eng.track_lengths(scr.regions, scr.diffs, n, sp.p, scr.track_lengths)
             eng.realign_tracks_plan(sp.names, scr.regions, scr.shifts, scr.goi, scr.offset_idxs, scr.track_lengths,

@@ -168,6 +168,7 @@ struct Svar2Slots {
 static int svar2_static(gvl_ctx *ctx, const Svar2Host &h, gvl_svar2_channels *ch) {
     int rc;
     const void *d;
+    memset(ch, 0, sizeof(*ch));  // (per-call flat layout: no resident-table indirection)
     if ((rc = static_dev(ctx, h.dense_pos, sizeof(int32_t) * h.n_dense, 16, &d))) return rc;
     ch->dense_pos = (const int32_t *)d;
     if ((rc = static_dev(ctx, h.dense_key, sizeof(int32_t) * h.n_dense, 17, &d))) return rc;

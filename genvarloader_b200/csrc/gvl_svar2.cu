@@ -35,17 +35,33 @@ __device__ __forceinline__ int64_t count_bits(const uint8_t *__restrict__ bits, 
 }
 
 constexpr int MERGE_WARPS = 4;
+constexpr int MERGE_WORDS = 512;  // presence words (32 dense entries each) a warp keeps in shared memory: 16,384 dense entries
+
+// 32 presence bits of a row starting at its bit j (bits beyond the row's window are garbage: callers mask)
+__device__ __forceinline__ uint32_t present_word(const uint8_t *__restrict__ bits, int64_t bit) {
+    const uint8_t *p = bits + (bit >> 3);
+    const unsigned sh = (unsigned)(bit & 7);
+    uint64_t v = 0;
+#pragma unroll
+    for (int i = 0; i < 5; i++) v |= (uint64_t)p[i] << (8 * i);  // (the presence buffer carries 8 bytes of slack)
+    return (uint32_t)(v >> sh);
+}
 
 __global__ void __launch_bounds__(MERGE_WARPS * 32) svar2_merge_kernel(MergeParams P) {
-    const int lane = lane_id();
-    const int64_t k = (int64_t)blockIdx.x * MERGE_WARPS + (threadIdx.x >> 5);
+    // per warp: the row's presence bits as 32-bit words + the number of present entries before each word
+    __shared__ uint32_t s_word[MERGE_WARPS][MERGE_WORDS];
+    __shared__ int32_t s_pre[MERGE_WARPS][MERGE_WORDS];
+    const int lane = lane_id(), wid = threadIdx.x >> 5;
+    const int64_t k = (int64_t)blockIdx.x * MERGE_WARPS + wid;
     if (k >= P.n_work) return;
     const int64_t query = k / P.ploidy;
-    const int64_t vk_lo = P.ch.vk_off[k], vk_hi = P.ch.vk_off[k + 1];
+    const int64_t ks = P.ch.row_slot ? P.ch.row_slot[k] : k;  // entry of the per-row tables
+    const int64_t vk_lo = P.ch.vk_off[ks], vk_hi = P.ch.vk_stop ? P.ch.vk_stop[ks] : P.ch.vk_off[ks + 1];
     const int64_t n_vk = imax64(vk_hi - vk_lo, 0);
-    const int64_t ds = P.ch.dense_range[query * 2], de = P.ch.dense_range[query * 2 + 1];
+    const int64_t qs = P.ch.query_div > 0 ? (P.ch.row_slot ? P.ch.row_slot[query * P.ploidy] : query * P.ploidy) / P.ch.query_div : query;
+    const int64_t ds = P.ch.dense_range[qs * 2], de = P.ch.dense_range[qs * 2 + 1];
     const int64_t nd = imax64(de - ds, 0);
-    const int64_t base_bit = P.ch.dense_present_off[k];
+    const int64_t base_bit = P.ch.dense_present_off[ks];
     const int32_t *__restrict__ vpos = P.ch.vk_pos + vk_lo;
     const int32_t *__restrict__ vkey = P.ch.vk_key + vk_lo;
     const int32_t *__restrict__ dpos = P.ch.dense_pos + ds;
@@ -63,11 +79,45 @@ __global__ void __launch_bounds__(MERGE_WARPS * 32) svar2_merge_kernel(MergePara
         }
         return;
     }
+    // presence words + exclusive prefix popcounts (a warp scan per 32 words) when the window fits shared memory
+    const int64_t n_words = (nd + 31) >> 5;
+    const bool staged = n_words <= MERGE_WORDS;
+    if (staged) {
+        int carry = 0;
+        for (int64_t w0 = 0; w0 < n_words; w0 += 32) {
+            const int64_t w = w0 + lane;
+            uint32_t word = 0;
+            if (w < n_words) {
+                word = present_word(P.ch.dense_present, base_bit + 32 * w);
+                const int64_t left = nd - 32 * w;
+                if (left < 32) word &= (1u << left) - 1u;
+            }
+            int x = __popc(word);
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
+            }
+            if (w < n_words) {
+                s_word[wid][w] = word;
+                s_pre[wid][w] = carry + x - __popc(word);
+            }
+            carry += __shfl_sync(0xffffffffu, x, 31);
+        }
+        __syncwarp();
+    }
+    // present entries strictly before dense index j
+    auto rank = [&](int64_t j) -> int64_t {
+        if (!staged) return count_bits(P.ch.dense_present, base_bit, j);
+        const int64_t w = j >> 5;
+        if (w >= n_words) return s_pre[wid][n_words - 1] + __popc(s_word[wid][n_words - 1]);
+        return s_pre[wid][w] + __popc(s_word[wid][w] & ((1u << (j & 31)) - 1u));
+    };
     // dense entries that are present: rank among present + var_key entries at or before them
     int64_t n_present = 0;
     for (int64_t base = 0; base < nd; base += 32) {
         const int64_t j = base + lane;
-        const bool pr = (j < nd) && present_bit(P.ch.dense_present, base_bit + j);
+        const bool pr = (j < nd) && (staged ? ((s_word[wid][j >> 5] >> (j & 31)) & 1u) != 0 : present_bit(P.ch.dense_present, base_bit + j) != 0);
         const unsigned mask = __ballot_sync(0xffffffffu, pr);
         if (pr) {
             const int32_t p = dpos[j];
@@ -90,7 +140,7 @@ __global__ void __launch_bounds__(MERGE_WARPS * 32) svar2_merge_kernel(MergePara
             int64_t mid = (lo + hi) >> 1;
             if (dpos[mid] < p) lo = mid + 1; else hi = mid;
         }
-        const int64_t w = off + i + count_bits(P.ch.dense_present, base_bit, lo);
+        const int64_t w = off + i + (nd > 0 ? rank(lo) : 0);
         P.m_pos[w] = p;
         P.m_key[w] = vkey[i];
     }

@@ -475,15 +475,17 @@ int gvl_dev_realign_tracks_btp(gvl_ctx *ctx, const gvl_sparse_tables *tab, const
                         params, base_seed, query_seed, max_records, out, stream, 1, base_seed_dev, sub_batch);
 }
 
-int gvl_dev_realign_tracks_plan(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_t *regions, const int32_t *shifts,
-                                const int64_t *geno_offset_idx, int64_t batch, int64_t ploidy, const uint8_t *keep,
+int gvl_dev_realign_tracks_plan(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_svar2_channels *svar2,
+                                const int32_t *regions, const int32_t *shifts, const int64_t *geno_offset_idx, int64_t batch, int64_t ploidy, const uint8_t *keep,
                                 const int64_t *keep_offsets, const uint8_t *to_rc, int64_t n_tracks, const gvl_intervals *itv,
                                 const int64_t *offset_idxs, const int32_t *track_lengths, const int64_t *out_offsets,
                                 int64_t total_per_track, const int32_t *strategy_ids, const double *params, uint64_t base_seed,
                                 const uint64_t *base_seed_dev, int64_t sub_batch, const int64_t *query_seed,
                                 int64_t max_records, int layout_btp, gvl_stream stream) {
     if (!itv || !offset_idxs) return fail(GVL_ERR_ARG, "gvl_dev_realign_tracks_plan: NULL argument");
-    return realign_impl(ctx, tab, nullptr, regions, shifts, geno_offset_idx, batch, ploidy, keep, keep_offsets, to_rc, n_tracks,
+    if (svar2 && (!svar2->vk_off || !svar2->dense_range || !svar2->dense_present_off))
+        return fail(GVL_ERR_ARG, "gvl_dev_realign_tracks_plan: NULL channel");
+    return realign_impl(ctx, tab, svar2, regions, shifts, geno_offset_idx, batch, ploidy, keep, keep_offsets, to_rc, n_tracks,
                         itv, offset_idxs, nullptr, nullptr, track_lengths, out_offsets, total_per_track, strategy_ids,
                         params, base_seed, query_seed, max_records, nullptr, stream, layout_btp ? 1 : 0, base_seed_dev, sub_batch,
                         true);

@@ -261,3 +261,95 @@ def to_svar2_channels(d: SynthData, regions, ds_idx, dense_frac: float = 0.5, se
                 dense_range=np.array(dense_range, np.int32).reshape(b, 2), dense_present=dense_present,
                 dense_present_off=np.array(bit_off, np.int64), key_ilen=key_ilen.astype(np.int32),
                 key_alt=np.ascontiguousarray(key_alt), key_alt_off=alt_off)
+
+
+def to_svar2_dataset(d: SynthData, dense_frac: float = 0.5, seed: int = 0, pure_del: bool = True, pad: int = 64) -> dict:
+    """The WHOLE dataset re-expressed as a resident svar2 two-channel source (the layout a dataset replica keeps in HBM;
+    the reference keeps the same information as range tables into the .svar2 store, docs/source/format.md:88-96):
+
+      * a random `dense_frac` of the variant table is "dense" (shared): per REGION the dense window is every dense
+        variant overlapping the (max_jitter + `pad`)-expanded region, `dense_range` (R, 2) into `dense_pos/dense_key`;
+        every (region, sample, ploid) slot owns LSB-first presence bits over its region's window, starting at bit
+        `present_off[slot]` of `dense_present`
+      * everything else a haplotype carries lives in its private var_key list `vk_pos/vk_key[vk_range[0, slot] : vk_range[1, slot]]`
+      * keys index the decoded key table (key_ilen, key_alt, key_alt_off); deletions become PURE deletions (empty ALT)
+        when `pure_del` and their stored ALT equals the reference base
+
+    Vectorised (cohort-scale slot counts); equivalent to `to_svar2_channels` batch by batch."""
+    rng = np.random.default_rng(seed)
+    V = d.v_starts.size
+    is_dense = rng.random(V) < dense_frac
+    key_ilen, alt_off, key_alt = d.ilens.copy(), d.alt_offsets.copy(), d.alt_alleles
+    if pure_del:
+        contig0 = d.reference[d.ref_offsets[0]:d.ref_offsets[1]]
+        lens = np.diff(d.alt_offsets)
+        is_del = (d.ilens < 0) & (lens == 1) & (d.alt_alleles[d.alt_offsets[:-1]] == contig0[d.v_starts])
+        alt_off = np.concatenate([[0], np.cumsum(np.where(is_del, 0, lens))]).astype(np.int64)
+        key_alt = d.alt_alleles[np.repeat(~is_del, lens)]
+    go = np.asarray(d.geno_offsets)
+    n_slots = go.shape[1]
+    lengths = go[1] - go[0]
+    assert (go[0][1:] == go[1][:-1]).all() and go[0][0] == 0, "expects a gap-free genotype CSR"
+    gv = np.asarray(d.geno_v_idxs)
+    slot_of = np.repeat(np.arange(n_slots, dtype=np.int64), lengths)
+    ent_dense = is_dense[gv]
+    # var_key channel
+    vk_key = gv[~ent_dense].astype(np.int32)
+    vk_pos = d.v_starts[vk_key].astype(np.int32)
+    vk_cnt = np.bincount(slot_of[~ent_dense], minlength=n_slots).astype(np.int64)
+    vk_stop = np.cumsum(vk_cnt)
+    vk_range = np.stack([vk_stop - vk_cnt, vk_stop]).astype(np.int64)
+    # dense channel: one window per region
+    dense_idx = np.flatnonzero(is_dense).astype(np.int32)
+    dpos_all = d.v_starts[dense_idx]
+    R = d.n_regions
+    lo = np.searchsorted(dpos_all, d.regions[:, 1] - d.max_jitter - pad, "left")
+    hi = np.searchsorted(dpos_all, d.regions[:, 2] + d.max_jitter + pad, "left")
+    win = (hi - lo).astype(np.int64)
+    w_stop = np.cumsum(win)
+    dense_range = np.stack([w_stop - win, w_stop], 1).astype(np.int32)
+    take = np.concatenate([np.arange(a, b) for a, b in zip(lo, hi)]) if R else np.empty(0, np.int64)
+    dense_key = dense_idx[take].astype(np.int32)
+    dense_pos = dpos_all[take].astype(np.int32)
+    # presence bits: slot -> window of its region
+    spr = n_slots // R  # slots per region (samples x ploidy)
+    slot_region = np.arange(n_slots) // spr
+    bits_per_slot = win[slot_region]
+    present_off = np.concatenate([[0], np.cumsum(bits_per_slot)]).astype(np.int64)
+    total_bits = int(present_off[-1])
+    bits = np.zeros(total_bits + 64, np.bool_)
+    ds = slot_of[ent_dense]
+    rank = np.searchsorted(dense_idx, gv[ent_dense])  # index of the variant among the dense ones
+    inside = (rank >= lo[slot_region[ds]]) & (rank < hi[slot_region[ds]])
+    assert inside.all(), "a carried dense variant lies outside its region's dense window"
+    bits[present_off[ds] + (rank - lo[slot_region[ds]])] = True
+    dense_present = np.packbits(bits, bitorder="little")
+    return dict(vk_pos=vk_pos, vk_key=vk_key, vk_range=vk_range, dense_pos=dense_pos, dense_key=dense_key,
+                dense_range=dense_range, dense_present=dense_present, present_off=present_off[:-1].copy(),
+                slots_per_region=int(spr), key_ilen=key_ilen.astype(np.int32), key_alt=np.ascontiguousarray(key_alt),
+                key_alt_off=alt_off, win=win)
+
+
+def svar2_batch_channels(sv: dict, ds_idx, ploidy: int, n_samples: int) -> dict:
+    """The per-call flat channel arrays (`gvl_svar2_channels` / the oracle's arguments) of a batch of a resident svar2
+    dataset (`to_svar2_dataset`): what the reference gathers per call from its range cache."""
+    ds_idx = np.asarray(ds_idx, np.int64)
+    slots = (ds_idx[:, None] * ploidy + np.arange(ploidy)[None, :]).ravel()
+    r = ds_idx // n_samples
+    vk_lo, vk_hi = sv["vk_range"][0, slots], sv["vk_range"][1, slots]
+    vk_off = np.concatenate([[0], np.cumsum(vk_hi - vk_lo)]).astype(np.int64)
+    take = np.concatenate([np.arange(a, b) for a, b in zip(vk_lo, vk_hi)]) if len(slots) else np.empty(0, np.int64)
+    dr = sv["dense_range"][r]
+    d_off = np.concatenate([[0], np.cumsum(dr[:, 1] - dr[:, 0])]).astype(np.int64)
+    d_take = np.concatenate([np.arange(a, b) for a, b in dr]) if len(r) else np.empty(0, np.int64)
+    allbits = np.unpackbits(sv["dense_present"], bitorder="little")
+    row_bits, bit_off = [], [0]
+    for k, s in enumerate(slots):
+        w = int(sv["win"][r[k // ploidy]])
+        row_bits.append(allbits[sv["present_off"][s]: sv["present_off"][s] + w])
+        bit_off.append(bit_off[-1] + w)
+    bits = np.concatenate(row_bits) if row_bits else np.zeros(0, np.uint8)
+    return dict(vk_pos=sv["vk_pos"][take], vk_key=sv["vk_key"][take], vk_off=vk_off, dense_pos=sv["dense_pos"][d_take],
+                dense_key=sv["dense_key"][d_take], dense_range=np.stack([d_off[:-1], d_off[1:]], 1).astype(np.int32),
+                dense_present=np.packbits(bits, bitorder="little"), dense_present_off=np.array(bit_off, np.int64),
+                key_ilen=sv["key_ilen"], key_alt=sv["key_alt"], key_alt_off=sv["key_alt_off"])

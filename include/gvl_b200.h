@@ -141,6 +141,12 @@ typedef struct {
     const int32_t *dense_range;       /* i32[b,2] window [ds, de) of each query                       */
     const uint8_t *dense_present;     /* presence bits over the window, LSB first                     */
     const int64_t *dense_present_off; /* i64[b*p+1] BIT offsets by flat row                           */
+    /* Optional (NULL / 0 = the per-call flat layout above).  A dataset replica keeps the two channels RESIDENT instead
+     * of gathering them per call (the range cache of docs/source/format.md:88-96, `_svar2_haps.py:1269-1313`): the
+     * per-row arrays are then tables over all (region, sample, ploid) slots and the per-query one over all regions. */
+    const int64_t *vk_stop;           /* row i holds var_key entries [vk_off[i], vk_stop[i])           */
+    const int64_t *row_slot;          /* i64[b*p]: row k reads entry row_slot[k] of vk_off / vk_stop / dense_present_off */
+    int64_t query_div;                /* > 0: query q reads dense_range[row_slot[q*p] / query_div] (slots per region) */
 } gvl_svar2_channels;
 
 /* gvl_dev_hap_plan for the svar2 source: merges each row's two channels on the device (stable by position,
@@ -229,10 +235,12 @@ int gvl_dev_realign_tracks_btp(gvl_ctx *ctx, const gvl_sparse_tables *tab, const
 
 /* gvl_dev_realign_tracks in two steps, so that a pipeline can run the latency-bound part (variant plan, tile map, per-tile
  * searches) on one stream and the bandwidth-bound execute launch on another: _plan takes the arguments of
- * gvl_dev_realign_tracks (layout_btp selects the (b, t, p, ~l) order) except `out`; _exec writes the planned call into
+ * gvl_dev_realign_tracks (layout_btp selects the (b, t, p, ~l) order) except `out`, plus `svar2`: non-NULL = the variants
+ * come from the svar2 two-channel source (merged on the device like gvl_dev_hap_plan_svar2; geno_offset_idx and the keep
+ * mask are then ignored, max_records = max_merged); _exec writes the planned call into
  * `out` (device f32[n_tracks * total_per_track], 16-byte aligned).  The caller orders the two (stream / event). */
-int gvl_dev_realign_tracks_plan(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_t *regions, const int32_t *shifts,
-                                const int64_t *geno_offset_idx, int64_t batch, int64_t ploidy, const uint8_t *keep,
+int gvl_dev_realign_tracks_plan(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_svar2_channels *svar2,
+                                const int32_t *regions, const int32_t *shifts, const int64_t *geno_offset_idx, int64_t batch, int64_t ploidy, const uint8_t *keep,
                                 const int64_t *keep_offsets, const uint8_t *to_rc, int64_t n_tracks, const gvl_intervals *itv,
                                 const int64_t *offset_idxs, const int32_t *track_lengths, const int64_t *out_offsets,
                                 int64_t total_per_track, const int32_t *strategy_ids, const double *params, uint64_t base_seed,

@@ -43,9 +43,10 @@ ALG_BYTES_PER_ROW = 56.0
 WORKLOADS = {
     "cfg1": dict(desc="configs[0]: 1 Mb contig, 8 diploid samples, ~1 variant/kb, 1,000 regions x 16,384 bp, 64 haplotypes/batch",
                  contig_len=1_000_000, n_samples=8, n_regions=1000, window=16_384, pairs=32, vkb=1.0),
-    "cfg2": dict(desc="configs[1]: 50 Mb contig, 2,504 diploid samples, ~1 variant/kb/haplotype (~0.55 M variant table), "
-                      "64 regions x 131,072 bp, 64 haplotypes/batch",
-                 contig_len=50_000_000, n_samples=2504, n_regions=64, window=131_072, pairs=32, vkb=1.0),
+    "cfg2": dict(desc="configs[1]: 50 Mb contig, 2,504 diploid samples, ~1 variant/kb/haplotype (~0.55 M variant table) in an "
+                      "svar2 two-channel store (half of the variants dense + presence bits), 64 regions x 131,072 bp, "
+                      "64 haplotypes/batch",
+                 contig_len=50_000_000, n_samples=2504, n_regions=64, window=131_072, pairs=32, vkb=1.0, source="svar2"),
     "cfg3": dict(desc="configs[2] (haplotype part): 524,288-bp indel-bearing windows (20% indels), 512 regions on a 300 Mb contig, "
                       "32 haplotypes/batch, jitter 128, 50% negative strand (reverse-complemented)",
                  contig_len=300_000_000, n_samples=4, n_regions=512, window=524_288, pairs=16, vkb=1.0, neg=0.5, jitter=128,
@@ -69,6 +70,7 @@ def build_workload(name: str, seed: int):
     d = synth.make_dataset(seed, w["contig_len"], w["n_samples"], w["n_regions"], w["window"] + 2 * j, w["vkb"],
                            max_jitter=j, neg_strand_frac=w.get("neg", 0.0), straddle_ends=False,
                            n_tracks=w.get("tracks_avail", w.get("tracks", 0)), fast_tracks=True)
+    d.svar2 = synth.to_svar2_dataset(d, dense_frac=0.5, seed=seed) if w.get("source") == "svar2" else None
     return w, d
 
 
@@ -96,7 +98,10 @@ def host_batches(d, w, n_batches: int, seed: int, rank: int = 0, world: int = 1)
         regions[:, 2] = regions[:, 1] + w["window"]  # (the fused entry pads / truncates to output_length anyway)
         shifts = np.zeros(goi.shape, np.int32)
         nvar = int((d.geno_offsets[1, goi.ravel()] - d.geno_offsets[0, goi.ravel()]).sum())
-        out.append(dict(regions=regions, goi=goi, to_rc=to_rc, shifts=shifts, nvar=nvar, ds_idx=ds_idx))
+        b = dict(regions=regions, goi=goi, to_rc=to_rc, shifts=shifts, nvar=nvar, ds_idx=ds_idx)
+        if getattr(d, "svar2", None) is not None:  # the per-call flat channels the reference slices out of its range cache
+            b["ch"] = synth.svar2_batch_channels(d.svar2, ds_idx, d.ploidy, d.n_samples)
+        out.append(b)
     return out
 
 
@@ -174,7 +179,31 @@ def track_bytes(w, n_tracks: int) -> float:
 # ----------------------------------------------------------------------------------------------
 # CPU arm: the oracle (C restatement of the reference's Rust/rayon path) on the host cores
 # ----------------------------------------------------------------------------------------------
+class Svar2Timer:
+    """One batch through the oracle's svar2 path: reconstruct_haplotypes_from_svar2 (merge + reconstruct, one task per
+    (query, hap)) into a fresh fixed-length buffer, reverse-complement, then the separate one-hot pass."""
+
+    def __init__(self, O, d, w, b):
+        self.O, self.d, self.w, self.b = O, d, w, b
+        rows = b["goi"].size
+        self.oo = (np.arange(rows + 1) * w["window"]).astype(np.int64)
+        self.bounds = np.ascontiguousarray(np.stack([self.oo[:-1], self.oo[1:]], 1))
+
+    def __call__(self, parallel=True):
+        O, d, b, ch = self.O, self.d, self.b, self.b["ch"]
+        out = np.empty(int(self.oo[-1]), np.uint8)
+        O.reconstruct_haplotypes_from_svar2(out, self.bounds, b["regions"], b["shifts"], ch["vk_pos"], ch["vk_key"], ch["vk_off"],
+                                            ch["dense_pos"], ch["dense_key"], ch["dense_range"], ch["dense_present"],
+                                            ch["dense_present_off"], ch["key_ilen"], ch["key_alt"], ch["key_alt_off"],
+                                            d.reference, d.ref_offsets, N_CHAR, parallel=parallel)
+        O.rc_flat_rows_inplace(out, self.oo, b["to_rc"])
+        O.onehot(out, parallel=parallel)
+        return out.size
+
+
 def _timers(O, d, w, batches):
+    if getattr(d, "svar2", None) is not None:
+        return [Svar2Timer(O, d, w, b) for b in batches]
     return [O.FusedTimer(b["regions"], b["shifts"], b["goi"], d.geno_offsets, d.geno_v_idxs, d.v_starts, d.ilens,
                          d.alt_alleles, d.alt_offsets, d.reference, d.ref_offsets, N_CHAR, w["window"], b["to_rc"],
                          onehot=True) for b in batches]
@@ -248,7 +277,8 @@ def workload_config(name, w, nvar, mode, n_tracks=0):
             "output": {"onehot": "uint8 one-hot (L,4)", "u8": "uint8 haplotype bytes",
                        "annotated": "uint8 bytes + int32 variant index + int32 reference coordinate"}[mode]
             + (f" + {n_tracks} float32 tracks (b, t, p, L)" if n_tracks else ""),
-            "source": "SVAR1-style sparse CSR", "jitter": w.get("jitter", 0)}
+            "source": "svar2 two-channel source (var_key ranges + dense windows + presence bits, decoded key table)"
+            if w.get("source") == "svar2" else "SVAR1-style sparse CSR", "jitter": w.get("jitter", 0)}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -278,7 +308,7 @@ def run_b200(args):
     L, rows, pairs = w["window"], w["pairs"] * 2, w["pairs"]
     bp_per_step = rows * L
     mode = args.mode
-    ds0 = Dataset.from_synth(dev, d, rng=args.seed + 7 + rank)
+    ds0 = Dataset.from_synth(dev, d, rng=args.seed + 7 + rank, svar2=d.svar2)
     ds0 = ds0.with_len(L).with_settings(jitter=w.get("jitter", 0))
     if mode == "annotated":
         ds0 = ds0.with_seqs("annotated")
@@ -304,7 +334,7 @@ def run_b200(args):
     if w.get("jitter", 0):
         jr = np.random.default_rng(args.seed + 5 + rank)
         jit_sets = torch.from_numpy(jr.integers(-w["jitter"], w["jitter"] + 1, size=(n_sets, n_q), dtype=np.int32)).to(dev)
-    nvar_per_step = float(np.mean([(d.geno_offsets[1] - d.geno_offsets[0])[
+    nvar_per_step = float(np.mean([np.asarray(d.geno_offsets[1] - d.geno_offsets[0])[
         (draw_indices(d, n_q, args.seed + 100 + i, rank, world)[:, None] * 2 + np.arange(2)[None, :]).ravel()].sum()
         for i in range(2)])) / ring
     main = torch.cuda.current_stream()
@@ -451,16 +481,28 @@ def run_b200(args):
     # ---- e2e: the reference-shaped host-buffer call (numpy in, pinned numpy out), copies included; every rank ----
     eng0 = ds.engine
     batches = host_batches(d, w, 8, args.seed + 1, rank, world)
-    _kernels.pin_static(d.geno_offsets, d.geno_v_idxs, d.v_starts, d.ilens, d.alt_alleles, d.alt_offsets,
-                        d.reference, d.ref_offsets, ctx=eng0.ctx)
     e2e_bytes_out = rows * L * 4  # the e2e leg always returns the one-hot (the headline metric)
     pinned = _kernels.PinnedBuffer(e2e_bytes_out)
+    if d.svar2 is not None:
+        sv = d.svar2
+        _kernels.pin_static(d.reference, d.ref_offsets, sv["key_ilen"], sv["key_alt"], sv["key_alt_off"], ctx=eng0.ctx)
 
-    def e2e_step(b):
-        _kernels.reconstruct_haplotypes_fused(b["regions"], b["shifts"], b["goi"], d.geno_offsets, d.geno_v_idxs,
-                                              d.v_starts, d.ilens, d.alt_alleles, d.alt_offsets, d.reference,
-                                              d.ref_offsets, N_CHAR, L, None, None, b["to_rc"], mode="onehot",
-                                              out=pinned.array, ctx=eng0.ctx)
+        def e2e_step(b):
+            ch = b["ch"]
+            _kernels.reconstruct_haplotypes_from_svar2(b["regions"], b["shifts"], ch["vk_pos"], ch["vk_key"], ch["vk_off"],
+                                                       ch["dense_pos"], ch["dense_key"], ch["dense_range"], ch["dense_present"],
+                                                       ch["dense_present_off"], sv["key_ilen"], sv["key_alt"], sv["key_alt_off"],
+                                                       d.reference, d.ref_offsets, N_CHAR, L, to_rc=b["to_rc"], mode="onehot",
+                                                       out=pinned.array, ctx=eng0.ctx)
+    else:
+        _kernels.pin_static(d.geno_offsets, d.geno_v_idxs, d.v_starts, d.ilens, d.alt_alleles, d.alt_offsets,
+                            d.reference, d.ref_offsets, ctx=eng0.ctx)
+
+        def e2e_step(b):
+            _kernels.reconstruct_haplotypes_fused(b["regions"], b["shifts"], b["goi"], d.geno_offsets, d.geno_v_idxs,
+                                                  d.v_starts, d.ilens, d.alt_alleles, d.alt_offsets, d.reference,
+                                                  d.ref_offsets, N_CHAR, L, None, None, b["to_rc"], mode="onehot",
+                                                  out=pinned.array, ctx=eng0.ctx)
 
     for i in range(3):
         e2e_step(batches[i % len(batches)])
@@ -474,10 +516,16 @@ def run_b200(args):
     if dist is not None:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     h2d = int(sum(batches[0][k].nbytes for k in ("regions", "shifts", "goi", "to_rc")))
+    if d.svar2 is not None:  # the batch's gathered channels travel too (the reference slices them from its range cache)
+        h2d = int(sum(batches[0][k].nbytes for k in ("regions", "shifts", "to_rc")) + sum(
+            batches[0]["ch"][k].nbytes for k in ("vk_pos", "vk_key", "vk_off", "dense_pos", "dense_key", "dense_range",
+                                                 "dense_present", "dense_present_off")))
     e2e = {"value": world * n_e2e * bp_per_step / float(e2e_t.item()), "unit": "bp/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": int(e2e_bytes_out + (rows + 1) * 8), "steps": n_e2e, "ranks": world,
-           "path": "genvarloader_b200._kernels.reconstruct_haplotypes_fused(mode='onehot') -> gvl_reconstruct_haplotypes_fused_begin/_finish, "
-                   "host numpy in, pinned host numpy out; every rank runs it on its own PCIe link, value = all ranks' bp / max time"}
+           "path": ("genvarloader_b200._kernels.reconstruct_haplotypes_from_svar2(mode='onehot') -> gvl_reconstruct_haplotypes_from_svar2_begin / "
+                    "gvl_reconstruct_haplotypes_fused_finish" if d.svar2 is not None else
+                    "genvarloader_b200._kernels.reconstruct_haplotypes_fused(mode='onehot') -> gvl_reconstruct_haplotypes_fused_begin/_finish")
+                   + ", host numpy in, pinned host numpy out; every rank runs it on its own PCIe link, value = all ranks' bp / max time"}
 
     # ---- single-consumer gather over NCCL / NVLink (reported apart from the roofline) ----
     gather = None

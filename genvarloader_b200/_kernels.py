@@ -391,7 +391,7 @@ def hap_diffs_svar2(regions, ploidy, vk_pos, vk_key, vk_off, dense_pos, dense_ke
 def reconstruct_haplotypes_from_svar2(regions, shifts, vk_pos, vk_key, vk_off, dense_pos, dense_key, dense_range,
                                       dense_present, dense_present_off, key_ilen, key_alt, key_alt_off, ref_,
                                       ref_offsets, pad_char, output_length, parallel=True, *, to_rc=None, mode="u8",
-                                      ctx=None):
+                                      out=None, ctx=None):
     """src/ffi/mod.rs:874-893 with the codec keys + LUT replaced by the DECODED key table
     (key_ilen, key_alt, key_alt_off; see gvl_svar2_channels in include/gvl_b200.h).  Returns (out, out_offsets)."""
     ctx = ctx or default_ctx()
@@ -414,6 +414,10 @@ def reconstruct_haplotypes_from_svar2(regions, shifts, vk_pos, vk_key, vk_off, d
         out, av, ap = np.empty(n, np.uint8), np.empty(n, np.int32), np.empty(n, np.int32)
         check(lib.gvl_reconstruct_haplotypes_fused_finish(ctx.handle, C.c_int(m), c_u8(int(pad_char)), _p(out), _p(av), _p(ap)))
         return out, av, ap, out_offsets
-    out = np.empty(n * (4 if m in (MODE_ONEHOT, MODE_ONEHOT_CF) else 1), np.uint8)
+    nbytes = n * (4 if m in (MODE_ONEHOT, MODE_ONEHOT_CF) else 1)
+    if out is None:
+        out = np.empty(nbytes, np.uint8)
+    assert out.dtype == np.uint8 and out.size >= nbytes and out.flags.c_contiguous
     check(lib.gvl_reconstruct_haplotypes_fused_finish(ctx.handle, C.c_int(m), c_u8(int(pad_char)), _p(out), c_vp(0), c_vp(0)))
+    out = out[:nbytes]
     return (out.reshape(n, 4) if m == MODE_ONEHOT else out), out_offsets

@@ -322,7 +322,8 @@ def run_b200(args):
 
     # ---- ring geometry: K steps = n_sub device calls of `ring` batches each, alternating between two halves ----
     out_bytes_step = bp_per_step * ({"onehot": 4, "u8": 1, "annotated": 9}[mode] + 4 * n_tracks_main)
-    ring_cap = max(1, min(args.ring, int(args.ring_gib * (1 << 30)) // (2 * out_bytes_step)))
+    # (at most ~2 GiB of output per device call: longer calls gain nothing and delay the first batch)
+    ring_cap = max(1, min(args.ring, int(args.ring_gib * (1 << 30)) // (2 * out_bytes_step), max(1, (2 << 30) // out_bytes_step)))
     ring = max((r for r in range(1, ring_cap + 1) if args.steps % r == 0 and args.steps // r >= min(args.min_calls, args.steps)), default=1)
     n_sub = args.steps // ring
     pipe = FixedPipeline(ds, pairs, ring=ring)
@@ -457,7 +458,7 @@ def run_b200(args):
     n_api_batches = ring * max(4, min(16, int(np.ceil(200.0 / max(ms / n_sub, 1e-3)))))
     order = draw_indices(d, n_api_batches * pairs, args.seed + 999, rank, world)
     # (indices address the dataset's (region, sample) grid: flat = r * n_samples + s, the loader's own convention)
-    loader = ds.to_dataloader(batch_size=pairs, sampler=order.tolist(), mode="double_buffered", copy=False, ring=ring)
+    loader = ds.to_dataloader(batch_size=pairs, sampler=order, mode="double_buffered", copy=False, ring=ring)
     for _ in loader:  # warm-up epoch (builds nothing new: the pipeline exists since construction)
         pass
     torch.cuda.synchronize()
@@ -532,14 +533,16 @@ def run_b200(args):
     if dist is not None:
         from genvarloader_b200._dist import gather_rows
 
-        out_t = pipe.halves[0].out.seq[: rows * L * 4].view(rows * L, 4) if mode == "onehot" else pipe.halves[0].out.seq[: rows * L]
-        offs = torch.arange(rows + 1, device=dev, dtype=torch.int64) * L
+        # a whole device call's output (ring batches) per rank: large enough to show the link rate
+        g_rows = rows * ring
+        out_t = pipe.halves[0].out.seq[: g_rows * L * 4].view(g_rows * L, 4) if mode == "onehot" else pipe.halves[0].out.seq[: g_rows * L]
+        offs = torch.arange(g_rows + 1, device=dev, dtype=torch.int64) * L
         for _ in range(2):
             gather_rows(out_t, offs, dst=0)
         torch.cuda.synchronize()
         dist.barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n_g = 10
+        n_g = 5
         g0.record()
         for _ in range(n_g):
             gather_rows(out_t, offs, dst=0)
@@ -548,7 +551,7 @@ def run_b200(args):
         g_ms = torch.tensor([g0.elapsed_time(g1) / n_g], device=dev, dtype=torch.float64)
         dist.all_reduce(g_ms, op=dist.ReduceOp.MAX)
         recv = (world - 1) * out_t.numel() * out_t.element_size()
-        gather = {"ms_per_batch": float(g_ms.item()), "consumer_ingest_GBps": recv / (float(g_ms.item()) * 1e-3) / 1e9,
+        gather = {"ms_per_device_call": float(g_ms.item()), "batches": ring, "consumer_ingest_GBps": recv / (float(g_ms.item()) * 1e-3) / 1e9,
                   "bytes_received_by_consumer": recv, "how": "genvarloader_b200._dist.gather_rows: every rank's batch output "
                   "(one-hot rows) sent to rank 0 over NCCL point-to-point; not on the hot path, not part of the roofline"}
     clk = clocks.stop() if rank == 0 else None
@@ -619,7 +622,7 @@ def main():
     ap.add_argument("--seed", type=int, default=3)
     ap.add_argument("--mode", default="onehot", choices=["onehot", "u8", "annotated"],
                     help="output of the execute kernel (the headline metric is one-hot)")
-    ap.add_argument("--ring", type=int, default=32, help="batches per device call, at most (must divide --steps)")
+    ap.add_argument("--ring", type=int, default=128, help="batches per device call, at most (the largest divisor of --steps)")
     ap.add_argument("--min-calls", type=int, default=1, help="device calls per timed block, at least")
     ap.add_argument("--ring-gib", type=float, default=12.0, help="output memory of the two ring halves, at most")
     ap.add_argument("--no-tracks", action="store_true", help="skip the cfg3t extra leg")

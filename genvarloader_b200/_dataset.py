@@ -768,7 +768,8 @@ class BatchLoader:
 
     def __iter__(self):
         if self.sampler is not None:
-            order = np.fromiter(iter(self.sampler), np.int64)
+            order = (np.ascontiguousarray(self.sampler, np.int64).ravel() if isinstance(self.sampler, np.ndarray)
+                     else np.fromiter(iter(self.sampler), np.int64))
         elif self.shuffle:
             order = self._rng.permutation(len(self.ds))
         else:

@@ -419,6 +419,8 @@ def _as_rng(generator):
 
 def epoch_order(ds, sampler, shuffle, rng) -> np.ndarray:
     if sampler is not None:
+        if isinstance(sampler, np.ndarray):  # (an index array is its own sampler: no per-element iteration)
+            return np.ascontiguousarray(sampler, np.int64).ravel()
         return np.fromiter(iter(sampler), np.int64)
     if shuffle:
         return rng.permutation(len(ds)).astype(np.int64)

@@ -38,6 +38,21 @@ struct RecArrays {
     int32_t *vpos;
 };
 
+// One record of a TRACK row (32 bytes, AoS so that a tile's records are one contiguous read): the variant writes
+// output positions [a, e) -- DEL: track[vrel] once; INS: e - a of vlen fill values -- and the source resumes at `resume`
+// (positions relative to the query start).
+struct __align__(16) TRec {
+    int32_t a;       // output (haplotype) position of the variant's values
+    int32_t e;       // a + values written (writable_length, src/tracks/mod.rs:329)
+    int32_t resume;  // source position after the variant (v_rel_end, :267)
+    int32_t vrel;    // v_rel_pos (:264)
+    int32_t vlen;    // (possibly shift-trimmed) v_len handed to the fill (:306, :338)
+    int32_t vdiff;   // ilen
+    int32_t pad0, pad1;
+};
+static_assert(sizeof(TRec) == 32, "TRec is a 32-byte record");
+constexpr int FLAG_JUMPS = 1;  // RowPlan.lead_pad of a track row: the row has jump records (unsorted variant list)
+
 // Optional per-call MERGED variant lists: the svar2 two-channel source (var_key + dense/presence,
 // src/svar2/mod.rs:45-66) after the device merge.  Row k's list is key/pos[off[k] .. off[k]+len[k]); keys
 // index the decoded-key table that is passed as gvl_sparse_tables.ilens / alt_offsets / alt_alleles.

@@ -49,6 +49,9 @@ struct HapPlanParams {
     int32_t *row_len;
     int32_t *dir;        // fixed-length plans: checkpoint directory (NULL otherwise)
     int64_t dir_stride;  // entries per row = ceil(length / DIR_Q) + 1
+    // track mode (hap_plan_par_kernel<NT, true>): 32-byte records, per-query source window lengths
+    TRec *trecs;
+    const int32_t *track_lengths;
 };
 
 constexpr int PLAN_WARPS = 4;
@@ -255,6 +258,7 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) hap_plan_serial_kernel(HapPla
     if (lane_id() == 0) plan_row_done(P.words, P.n_work);
 }
 
+#include "gvl_trk_plan.cuh"
 #include "gvl_plan_par.cuh"
 
 // ragged plans: exclusive scan of row lengths -> out_offsets, RowPlan.out_off, tile map, totals.
@@ -849,6 +853,8 @@ static int hap_plan_impl(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_s
     P.row_len = ctx->hap.row_len;
     P.dir = nullptr;
     P.dir_stride = 0;
+    P.trecs = nullptr;
+    P.track_lengths = nullptr;
     ctx->dir_stride = 0;
     if (output_length >= 0) {
         const int64_t stride = (output_length + DIR_Q - 1) / DIR_Q + 1;
@@ -868,11 +874,11 @@ static int hap_plan_impl(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_s
         const unsigned grid = (unsigned)((n_work + PLAN_WARPS - 1) / PLAN_WARPS);
         hap_plan_serial_kernel<<<grid, PLAN_WARPS * 32, 0, st>>>(P);
     } else if (force_nt == 32 || (!force_nt && max_records <= 40 * n_work)) {  // short lists: one warp per row, 4 rows per CTA
-        hap_plan_par_kernel<32><<<(unsigned)((n_work + 3) / 4), 128, 0, st>>>(P);
+        hap_plan_par_kernel<32, false><<<(unsigned)((n_work + 3) / 4), 128, 0, st>>>(P);
     } else if (force_nt == 256 || (!force_nt && max_records <= 384 * n_work)) {  // one 256-thread CTA per row
-        hap_plan_par_kernel<256><<<(unsigned)n_work, 256, 0, st>>>(P);
+        hap_plan_par_kernel<256, false><<<(unsigned)n_work, 256, 0, st>>>(P);
     } else {  // long lists: 512 variants per sequential chunk
-        hap_plan_par_kernel<512><<<(unsigned)n_work, 512, 0, st>>>(P);
+        hap_plan_par_kernel<512, false><<<(unsigned)n_work, 512, 0, st>>>(P);
     }
     GVL_LAUNCH_CHECK();
     if (output_length >= 0) {
@@ -884,6 +890,43 @@ static int hap_plan_impl(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_s
         ctx->total = -1;
     }
     ctx->plan_valid = true;
+    return GVL_OK;
+}
+
+// The track plan: the same kernel in track mode over the TRACK workspace of the context (rows sized by the caller's
+// out_offsets; merged svar2 lists when `merged` is set).  Called by gvl_tracks.cu.
+int gvl_trk_plan_launch(gvl_ctx *ctx, const gvl_sparse_tables *tab, const MergedLists *merged, const int32_t *regions,
+                        const int32_t *shifts, const int64_t *geno_offset_idx, int64_t batch, int64_t ploidy,
+                        const uint8_t *keep, const int64_t *keep_offsets, const uint8_t *to_rc, const int32_t *track_lengths,
+                        const int64_t *out_offsets, int64_t max_records, int64_t *words, cudaStream_t st) {
+    const int64_t n_work = batch * ploidy;
+    HapPlanParams P;
+    P.tab = *tab;
+    P.merged = merged ? *merged : MergedLists{nullptr, nullptr, nullptr, nullptr};
+    P.regions = regions;
+    P.shifts = shifts;
+    P.goi = geno_offset_idx;
+    P.keep = keep;
+    P.keep_off = keep_offsets;
+    P.to_rc = to_rc;
+    P.n_work = n_work;
+    P.ploidy = ploidy;
+    P.output_length = -2;  // rows sized by the caller's offsets
+    P.rec_cap = ctx->trk.trec_cap;
+    P.rows = ctx->trk.rows;
+    P.rec = RecArrays{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    P.words = words;
+    P.out_offsets = const_cast<int64_t *>(out_offsets);  // (read only in this mode)
+    P.diffs = nullptr;
+    P.row_len = ctx->trk.row_len;
+    P.dir = nullptr;
+    P.dir_stride = 0;
+    P.trecs = (TRec *)ctx->trk.trecs;
+    P.track_lengths = track_lengths;
+    if (max_records <= 40 * n_work) hap_plan_par_kernel<32, true><<<(unsigned)((n_work + 3) / 4), 128, 0, st>>>(P);
+    else if (max_records <= 384 * n_work) hap_plan_par_kernel<256, true><<<(unsigned)n_work, 256, 0, st>>>(P);
+    else hap_plan_par_kernel<512, true><<<(unsigned)n_work, 512, 0, st>>>(P);
+    GVL_LAUNCH_CHECK();
     return GVL_OK;
 }
 

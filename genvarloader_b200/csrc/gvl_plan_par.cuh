@@ -78,7 +78,12 @@ struct PlanSmem {
     int flag;
 };
 
-template <int NT>
+// TRK = false: haplotype rows (reconstruct_haplotype_core).  TRK = true: track rows (shift_and_realign_track_core,
+// src/tracks/mod.rs:224-406) -- the SAME offset scan with the track core's three differences: the "ALT length" of a
+// variant is max(ilen, 0) + 1 (:282), SNPs take part in the shift bookkeeping only and otherwise change nothing
+// (:310-314), and there is no leading-pad clause (the source window is query-relative, positions left of it just read 0).
+// Records go out as 32-byte TRec (output range, resume point, anchor, fill length, ilen) in window-relative coordinates.
+template <int NT, bool TRK>
 __global__ void __launch_bounds__(NT == 32 ? 128 : NT) hap_plan_par_kernel(HapPlanParams P) {
     constexpr int ROWS_PER_CTA = (NT == 32) ? 4 : 1;
     __shared__ PlanSmem<NT> s_all[ROWS_PER_CTA];
@@ -91,9 +96,10 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) hap_plan_par_kernel(HapPl
     const RowVars rv = row_vars(P.tab, P.merged, P.goi, k);
     const int64_t nvar = rv.nvar;
     const int64_t c_idx = P.regions[query * 3 + 0];
-    const int64_t c_s = P.tab.ref_offsets[c_idx];
-    const int64_t contig_len = P.tab.ref_offsets[c_idx + 1] - c_s;
+    const int64_t c_s = TRK ? 0 : P.tab.ref_offsets[c_idx];
     const int64_t q_start = P.regions[query * 3 + 1];
+    // (tracks: the "contig" is the source window [q_start, q_start + track_n), _reconstruct.py:191-196)
+    const int64_t contig_len = TRK ? q_start + (int64_t)P.track_lengths[query] : P.tab.ref_offsets[c_idx + 1] - c_s;
     const int64_t q_end = P.regions[query * 3 + 2];
     const int64_t shift = P.shifts[k];
     const bool has_keep = (P.keep && P.keep_off);
@@ -101,7 +107,7 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) hap_plan_par_kernel(HapPl
     const int32_t *__restrict__ gv = rv.gv;
     const bool ragged = P.output_length < 0;
     const bool sized = P.output_length == -1;
-    const bool want_diff = sized || (P.diffs != nullptr);
+    const bool want_diff = !TRK && (sized || (P.diffs != nullptr));
 
     // record workspace of the row: one atomic per row.  Its round trip overlaps with the first gathers: the value
     // stays in thread 0 until the first chunk's loads are in flight (bcast_off below).
@@ -230,6 +236,12 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) hap_plan_par_kernel(HapPl
     // ---------------------------------------------------------------- pass 2: haplotype records
     HapState hs;
     hap_init(hs, q_start, shift, length);  // leading pad, :68-83
+    if (TRK) {  // src/tracks/mod.rs:249-251: no pad clause, the cursor starts at the window start
+        hs.ref_idx = q_start;
+        hs.out_idx = 0;
+        hs.shifted = 0;
+        hs.lead_pad = 0;
+    }
     int64_t R = hs.ref_idx, O = hs.out_idx, shifted = hs.shifted;
     int64_t n_emit = 0, ref0 = 0;
     bool done = false;
@@ -243,7 +255,8 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) hap_plan_par_kernel(HapPl
             vi = gv[i];
             pos = var_pos(P.tab, rv, i, vi);
             il = P.tab.ilens[vi];
-            var_alt(P.tab, rv, vi, pos, c_s, aoff, alen);
+            if (TRK) alen = imax64(il, 0) + 1;  // v_len, src/tracks/mod.rs:282
+            else var_alt(P.tab, rv, vi, pos, c_s, aoff, alen);
             kept = has_keep ? (P.keep[keep_base + i] != 0) : true;
             if (rv.mpos) vi = (int32_t)i;  // svar2 annotates with the LOCAL index (src/reconstruct/mod.rs:734)
         }
@@ -303,6 +316,7 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) hap_plan_par_kernel(HapPl
             shifted = shift;
         }
         elig = elig && t >= start;
+        if (TRK) elig = elig && il != 0;  // a SNP "writes nothing" and does not move the cursor (src/tracks/mod.rs:310-314)
         // -- C: applied set
         const int64_t mx_incl = grp_scan_incl<NT, true>(elig ? end : INT64_MIN, S.warp);
         int64_t mx_excl = __shfl_up_sync(0xffffffffu, mx_incl, 1);
@@ -357,12 +371,19 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) hap_plan_par_kernel(HapPl
         const int64_t rank_incl = grp_scan_incl<NT, false>(valid ? 1 : 0, S.warp);
         if (valid && !overflow) {
             const int64_t w = rec_off + n_emit + rank_incl - 1;
-            P.rec.a[w] = (int32_t)a;
-            P.rec.n[w] = (int32_t)n;
-            P.rec.src[w] = aoff + my_trim;
-            P.rec.resume[w] = (int32_t)end;
-            P.rec.vidx[w] = vi;
-            P.rec.vpos[w] = (int32_t)pos;
+            if (TRK) {
+                TRec r;
+                r.a = (int32_t)a, r.e = (int32_t)(a + n), r.resume = (int32_t)(end - q_start), r.vrel = (int32_t)(pos - q_start);
+                r.vlen = (int32_t)alen_eff, r.vdiff = (int32_t)il, r.pad0 = 0, r.pad1 = 0;
+                P.trecs[w] = r;
+            } else {
+                P.rec.a[w] = (int32_t)a;
+                P.rec.n[w] = (int32_t)n;
+                P.rec.src[w] = aoff + my_trim;
+                P.rec.resume[w] = (int32_t)end;
+                P.rec.vidx[w] = vi;
+                P.rec.vpos[w] = (int32_t)pos;
+            }
         }
         // carried state: last valid record of the chunk
         const int64_t last_valid = grp_reduce<NT, true>(valid ? (int64_t)t : -1, S.warp);
@@ -387,8 +408,37 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) hap_plan_par_kernel(HapPl
     bcast_off();
     if (unsorted) {
         // exact replan in list order by one warp (rare; out of the writers' contract)
-        if (NT == 32 || threadIdx.x < 32) plan_row_serial(P, k, rec_off);
+        if (NT == 32 || threadIdx.x < 32) {
+            if (TRK) trk_plan_row_serial(P, k, rec_off);
+            else plan_row_serial(P, k, rec_off);
+        }
         if (t == 0) plan_row_done(P.words, P.n_work);
+        return;
+    }
+    if (TRK) {
+        if (nvar == 0) {
+            R = q_start;  // src/tracks/mod.rs:240-246: an EMPTY variant list copies track[:length], whatever the shift
+        } else if (shifted < shift) {
+            R = imin64(R + (shift - shifted), contig_len);  // :365-369
+        }
+        if (n_emit == 0) ref0 = R;
+        if (t == 0) {
+            RowPlan rp;
+            rp.out_off = P.out_offsets[k];
+            rp.ref_base = 0;
+            rp.rec_off = rec_off;
+            rp.length = (int32_t)length;
+            rp.contig_len = (int32_t)(contig_len - q_start);
+            rp.lead_pad = 0;  // (flags of a track row: no jump records on this path)
+            rp.ref0 = (int32_t)(ref0 - q_start);
+            rp.n_rec = overflow ? 0 : (int32_t)n_emit;
+            rp.rc = (P.to_rc && P.to_rc[k]) ? 1 : 0;
+            rp.diff = 0;
+            rp.q_start = (int32_t)q_start;
+            P.rows[k] = rp;
+            P.row_len[k] = (int32_t)length;
+            plan_row_done(P.words, P.n_work);
+        }
         return;
     }
 

@@ -21,194 +21,10 @@ namespace gvl {
 
 constexpr int TRK_TILE = 8192;  // output values per execute CTA (one tile of one (track, row))
 
-// One record of a track row (32 bytes, AoS so that a pass's records arrive with ONE bulk copy): the variant writes
-// output positions [a, e) -- DEL: track[vrel] once; INS: e - a of vlen fill values -- and the source resumes at `resume`.
-struct __align__(16) TRec {
-    int32_t a;       // output (haplotype) position of the variant's values
-    int32_t e;       // a + values written (writable_length, src/tracks/mod.rs:329)
-    int32_t resume;  // source position after the variant (v_rel_end, :267)
-    int32_t vrel;    // v_rel_pos (:264)
-    int32_t vlen;    // (possibly shift-trimmed) v_len handed to the fill (:306, :338)
-    int32_t vdiff;   // ilen
-    int32_t pad0, pad1;
-};
-static_assert(sizeof(TRec) == 32, "TRec is a 32-byte record");
-
 // =====================================================================================
-// plan: shift_and_realign_track_core state machine (src/tracks/mod.rs:224-406), one warp per row
+// plan: the scan-based plan kernel of the haplotype path in track mode (gvl_plan_par.cuh, hap_plan_par_kernel<NT, true>;
+// launched through gvl_trk_plan_launch, gvl_hap.cu) -- the same offset scan serves both paths
 // =====================================================================================
-struct TrkPlanParams {
-    gvl_sparse_tables tab;
-    MergedLists merged;
-    const int32_t *regions;
-    const int32_t *shifts;
-    const int64_t *goi;
-    const uint8_t *keep;
-    const int64_t *keep_off;
-    const uint8_t *to_rc;
-    const int32_t *track_lengths;  // [batch]
-    const int64_t *out_offsets;    // [n_work+1]
-    int64_t n_work, ploidy, rec_cap;
-    RowPlan *rows;
-    TRec *trecs;
-    int64_t *words;
-    int32_t *row_len;
-};
-
-constexpr int TPLAN_WARPS = 4;
-constexpr int FLAG_JUMPS_PLAN = 1;  // == FLAG_JUMPS of the execute kernel
-
-__device__ __forceinline__ void put_trec(TRec *t, int64_t a, int64_t n, int64_t resume, int64_t vrel, int64_t vlen, int64_t vdiff) {
-    TRec r;
-    r.a = (int32_t)a, r.e = (int32_t)(a + n), r.resume = (int32_t)resume, r.vrel = (int32_t)vrel, r.vlen = (int32_t)vlen;
-    r.vdiff = (int32_t)vdiff, r.pad0 = 0, r.pad1 = 0;
-    *t = r;
-}
-
-__global__ void __launch_bounds__(TPLAN_WARPS * 32) trk_plan_kernel(TrkPlanParams P) {
-    const int lane = lane_id();
-    const int64_t k = (int64_t)blockIdx.x * TPLAN_WARPS + (threadIdx.x >> 5);
-    if (k >= P.n_work) return;
-    const int64_t query = k / P.ploidy;
-    const RowVars rv = row_vars(P.tab, P.merged, P.goi, k);
-    const int64_t nvar = rv.nvar;
-    const int64_t q_start = P.regions[query * 3 + 1];
-    const int64_t shift = P.shifts[k];
-    const bool has_keep = (P.keep && P.keep_off);
-    const int64_t keep_base = has_keep ? P.keep_off[k] : 0;
-    const int32_t *__restrict__ gv = rv.gv;
-    const int64_t length = imax64(P.out_offsets[k + 1] - P.out_offsets[k], 0);
-    const int64_t track_n = P.track_lengths[query];
-
-    int64_t rec_off = 0;
-    if (lane == 0) rec_off = (int64_t)atomicAdd((unsigned long long *)&P.words[W_CURSOR], (unsigned long long)(nvar + 1));
-    rec_off = __shfl_sync(0xffffffffu, rec_off, 0);
-    const bool overflow = rec_off + nvar + 1 > P.rec_cap;
-    if (overflow && lane == 0) atomicMax((unsigned long long *)&P.words[W_STATUS], (unsigned long long)(rec_off + nvar + 1));
-
-    TrkState ts;
-    trk_init(ts, shift, length);
-    int64_t n_emit = 0, track0 = 0, prev_resume = 0;
-    bool done = false, jumps = false;  // jumps: an unsorted list moved the source cursor between emissions
-    // chunk loader: variant i = base + lane of the row (positions, ilens, keep flag)
-    auto load_chunk = [&](int64_t base, int32_t &pos, int32_t &il, bool &kp) {
-        pos = 0, il = 0, kp = false;
-        const int64_t i = base + lane;
-        if (i < nvar) {
-            const int32_t vi = gv[i];
-            pos = (int32_t)var_pos(P.tab, rv, i, vi);
-            il = P.tab.ilens[vi];
-            kp = has_keep ? (P.keep[keep_base + i] != 0) : true;
-        }
-    };
-    int32_t pos, il, n_pos = 0, n_il = 0;
-    bool kp, n_kp = false;
-    load_chunk(0, pos, il, kp);
-    for (int64_t base = 0; base < nvar && !done; base += 32) {
-        if (base + 32 < nvar) load_chunk(base + 32, n_pos, n_il, n_kp);  // next chunk's gathers fly during this one
-        // once the shift is consumed a SNP (ilen 0) changes nothing (src/tracks/mod.rs:277-314: skipped or
-        // "writes nothing"), so only indels take part
-        const bool part = kp && (il != 0 || ts.shifted < ts.shift);
-        unsigned mask = __ballot_sync(0xffffffffu, part);
-        const int64_t rel = (int64_t)pos - q_start;                        // v_rel_pos (:264)
-        const int64_t v_end = rel - imin64(il, 0) + 1;                     // v_rel_end (:267)
-        // ---- whole chunk at once: shift consumed, nothing left of the window, and every participating indel starts
-        //      at or after the end of the previous one (no overlap -> every one is applied, :277-279) ----
-        bool fast = mask != 0 && ts.shifted >= ts.shift && (n_emit == 0 || ts.track_idx == prev_resume) &&
-                    !__any_sync(0xffffffffu, part && rel < 0);
-        int64_t prev_end = ts.track_idx;
-        if (fast) {
-            const unsigned below = mask & ((1u << lane) - 1u);
-            const int pl = below ? 31 - __clz(below) : 0;
-            const int64_t pe = __shfl_sync(0xffffffffu, v_end, pl);
-            if (below) prev_end = pe;
-            fast = !__any_sync(0xffffffffu, part && rel < prev_end);
-        }
-        if (fast) {
-            const int64_t v_len = imax64(il, 0) + 1;                         // :282
-            const int64_t ref_len = part ? rel - prev_end : 0;               // track_len (:317)
-            int64_t inc = part ? ref_len + v_len : 0, scan = inc;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int64_t y = __shfl_up_sync(0xffffffffu, scan, o);
-                if (lane >= o) scan += y;
-            }
-            const int64_t a = ts.out_idx + (scan - inc) + ref_len;           // out_idx after the span copy
-            const bool valid = part && a < ts.length;                        // :319-321 (positions grow: a prefix)
-            const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-            const bool broke = __any_sync(0xffffffffu, part && !valid);
-            const int64_t n = valid ? imin64(v_len, ts.length - a) : 0;      // writable_length (:329)
-            if (vmask) {
-                const int last = 31 - __clz(vmask);
-                if (n_emit == 0) track0 = ts.track_idx;  // span_src of the first record
-                if (valid && !overflow) {
-                    const int64_t w = rec_off + n_emit + __popc(vmask & ((1u << lane) - 1u));
-                    put_trec(P.trecs + w, a, n, v_end, rel, v_len, il);
-                }
-                n_emit += __popc(vmask);
-                ts.out_idx = __shfl_sync(0xffffffffu, a + n, last);
-                ts.track_idx = __shfl_sync(0xffffffffu, v_end, last);
-                prev_resume = ts.track_idx;
-                if (ts.out_idx >= ts.length) done = true;  // :359-361
-            }
-            if (broke) done = true;
-            mask = 0;
-        }
-        while (mask && !done) {
-            int t = __ffs(mask) - 1;
-            mask &= mask - 1;
-            int64_t p = __shfl_sync(0xffffffffu, pos, t);
-            int64_t l = __shfl_sync(0xffffffffu, il, t);
-            TrkRec r;
-            int act = trk_step(ts, p - q_start, l, r);  // v_rel_pos = v_start - query_start (:264)
-            if (act == STEP_BREAK) {
-                done = true;
-            } else if (act == STEP_EMIT) {
-                if (n_emit == 0) track0 = r.span_src;
-                if (n_emit > 0 && r.span_src != prev_resume) {  // unsorted input: jump record
-                    if (lane == t && !overflow) put_trec(P.trecs + rec_off + n_emit, r.a - (r.v_rel_pos - r.span_src), 0, r.span_src, 0, 1, 0);
-                    n_emit++;
-                    jumps = true;
-                }
-                if (lane == t && !overflow) put_trec(P.trecs + rec_off + n_emit, r.a, r.n, r.resume, r.v_rel_pos, r.v_len, r.v_diff);
-                n_emit++;
-                prev_resume = r.resume;
-                if (ts.out_idx >= ts.length) done = true;  // :359-361
-            }
-        }
-        pos = n_pos, il = n_il, kp = n_kp;
-    }
-    if (nvar == 0) {
-        track0 = 0;  // :240-246: an EMPTY variant list copies track[:length], whatever the shift
-    } else {
-        trk_finish(ts, track_n);
-        if (n_emit == 0) {
-            track0 = ts.track_idx;
-        } else if (ts.track_idx != prev_resume) {
-            if (lane == 0 && !overflow) put_trec(P.trecs + rec_off + n_emit, imin64(ts.out_idx, length), 0, ts.track_idx, 0, 1, 0);
-            n_emit++;
-            jumps = true;
-        }
-    }
-    if (lane == 0) {
-        RowPlan rp;
-        rp.out_off = P.out_offsets[k];
-        rp.ref_base = 0;
-        rp.rec_off = rec_off;
-        rp.length = (int32_t)length;
-        rp.contig_len = (int32_t)track_n;
-        rp.lead_pad = jumps ? FLAG_JUMPS_PLAN : 0;  // (track rows carry flags here: see gvl_tracks_exec.cuh)
-        rp.ref0 = (int32_t)track0;
-        rp.n_rec = overflow ? 0 : (int32_t)n_emit;
-        rp.rc = (P.to_rc && P.to_rc[k]) ? 1 : 0;
-        rp.diff = 0;
-        rp.q_start = (int32_t)q_start;
-        P.rows[k] = rp;
-        P.row_len[k] = (int32_t)length;
-        plan_row_done(P.words, P.n_work);
-    }
-}
-
 // identity plan for intervals_to_tracks: one row per query, no records, source window = row
 __global__ void paint_plan_kernel(int64_t n, const int32_t *__restrict__ starts, const int64_t *__restrict__ out_offsets,
                                   const uint8_t *__restrict__ to_rc, RowPlan *rows, int32_t *row_len) {
@@ -372,6 +188,12 @@ static int launch_trk_exec(gvl_ctx *ctx, int64_t n_work, int64_t ploidy, int64_t
     return trk_execute(ctx, out, st);
 }
 
+// the scan-based plan kernel in track mode (gvl_hap.cu)
+int gvl_trk_plan_launch(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl::MergedLists *merged, const int32_t *regions,
+                        const int32_t *shifts, const int64_t *geno_offset_idx, int64_t batch, int64_t ploidy,
+                        const uint8_t *keep, const int64_t *keep_offsets, const uint8_t *to_rc, const int32_t *track_lengths,
+                        const int64_t *out_offsets, int64_t max_records, int64_t *words, cudaStream_t st);
+
 // svar2 two-channel merge (gvl_svar2.cu)
 int gvl_svar2_merge_launch(gvl_ctx *ctx, gvl_workspace *ws, int64_t *words, const gvl_svar2_channels *ch, int64_t batch,
                            int64_t ploidy, int64_t max_merged, cudaStream_t st);
@@ -402,31 +224,15 @@ static int realign_impl(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_sv
     if ((rc = ensure_rows(ctx, ctx->trk, n_work))) return rc;
     if ((rc = ensure_trecs(ctx, ctx->trk, max_records + n_work))) return rc;
     int64_t *words = ctx->dev_words + W_COUNT;  // (left at zero by the previous plan, see plan_row_done)
-    TrkPlanParams PP;
-    PP.tab = *tab;
-    PP.merged = MergedLists{nullptr, nullptr, nullptr, nullptr};
+    MergedLists merged{nullptr, nullptr, nullptr, nullptr};
     if (svar2) {  // merged two-channel variant lists (src/svar2/mod.rs:45-66), same merge as the haplotype path
         if ((rc = ensure_merged(ctx, ctx->trk, max_records))) return rc;
         if ((rc = gvl_svar2_merge_launch(ctx, &ctx->trk, words, svar2, batch, ploidy, max_records, st))) return rc;
-        PP.merged = MergedLists{ctx->trk.m_pos, ctx->trk.m_key, ctx->trk.m_off, ctx->trk.m_len};
+        merged = MergedLists{ctx->trk.m_pos, ctx->trk.m_key, ctx->trk.m_off, ctx->trk.m_len};
     }
-    PP.regions = regions;
-    PP.shifts = shifts;
-    PP.goi = geno_offset_idx;
-    PP.keep = keep;
-    PP.keep_off = keep_offsets;
-    PP.to_rc = to_rc;
-    PP.track_lengths = track_lengths;
-    PP.out_offsets = out_offsets;
-    PP.n_work = n_work;
-    PP.ploidy = ploidy;
-    PP.rec_cap = ctx->trk.trec_cap;
-    PP.rows = ctx->trk.rows;
-    PP.trecs = (TRec *)ctx->trk.trecs;
-    PP.words = words;
-    PP.row_len = ctx->trk.row_len;
-    trk_plan_kernel<<<(unsigned)((n_work + TPLAN_WARPS - 1) / TPLAN_WARPS), TPLAN_WARPS * 32, 0, st>>>(PP);
-    GVL_LAUNCH_CHECK();
+    if ((rc = gvl_trk_plan_launch(ctx, tab, svar2 ? &merged : nullptr, regions, shifts, geno_offset_idx, batch, ploidy, keep,
+                                  keep_offsets, to_rc, track_lengths, out_offsets, max_records, words, st)))
+        return rc;
     TrkDesc desc[MAX_TRACKS];
     if (n_tracks > MAX_TRACKS) return fail(GVL_ERR_ARG, "at most %d tracks per call", MAX_TRACKS);
     for (int64_t t = 0; t < n_tracks; t++) {

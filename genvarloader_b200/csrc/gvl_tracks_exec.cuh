@@ -34,7 +34,6 @@ constexpr int T2_THREADS = 256;
 constexpr int T3_ITV = 512;                 // stored intervals staged per sub-pass (two per thread)
 constexpr int T3_REC = 96;                  // records staged per sub-pass (carry + new ones + sentinel)
 constexpr int T3_WORDS = T3_TILE / 32;
-constexpr int FLAG_JUMPS = 1;               // RowPlan.lead_pad of a track row: the row has jump records
 constexpr int TD_RC = 1, TD_GENERIC = 2, TD_BIG = 4;  // TileDesc.flags
 
 // What trk_tile_prep_kernel leaves for one (track, tile); row < 0 = no such tile.

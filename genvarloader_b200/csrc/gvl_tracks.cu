@@ -177,7 +177,7 @@ static int launch_trk_exec(gvl_ctx *ctx, int64_t n_work, int64_t ploidy, int64_t
     int rc;
     if ((rc = ensure_tdesc(ctx, ctx->trk, grid))) return rc;
     TileDesc *tdesc = (TileDesc *)ctx->trk.tdesc;
-    trk_tile_prep_kernel<<<(unsigned)((grid + 127) / 128), 128, 0, st>>>(P, tdesc);
+    trk_tile_prep_kernel<<<(unsigned)((grid + 3) / 4), 128, 0, st>>>(P, tdesc);  // one warp per tile
     GVL_LAUNCH_CHECK();
     // the execute launch may follow later, on another stream (gvl_dev_realign_tracks_exec): keep its parameters
     if (!ctx->trk_params) ctx->trk_params = malloc(sizeof(TrkExecParams));

@@ -246,7 +246,9 @@ __device__ __forceinline__ void t2_set_bit(uint32_t *mk, uint32_t *mk2, int u) {
 // tile preparation: one thread per (track, tile)
 // =====================================================================================
 __global__ void __launch_bounds__(128) trk_tile_prep_kernel(TrkExecParams P, TileDesc *__restrict__ tdesc) {
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // one WARP per (track, tile): the searches are 32-ary (a probe per lane), the record counts one strided pass
+    const int lane = threadIdx.x & 31;
+    const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (g >= P.grid_per_track * P.n_tracks) return;
     const int64_t track = g / P.grid_per_track;
     const int64_t b = g % P.grid_per_track;
@@ -254,9 +256,14 @@ __global__ void __launch_bounds__(128) trk_tile_prep_kernel(TrkExecParams P, Til
     D.row = -1;
     if (b < P.tile_off[P.n_work]) {
         int64_t lo = 0, hi = P.n_work;  // row of the tile: last row with tile_off[row] <= b
-        while (hi - lo > 1) {
-            const int64_t mid = (lo + hi) >> 1;
-            if (P.tile_off[mid] <= b) lo = mid; else hi = mid;
+        while (hi - lo > 1) {           // (32-ary: lane l probes the l-th of 32 cut points)
+            const int64_t step = (hi - lo + 31) / 32;
+            const int64_t idx = lo + (int64_t)(lane + 1) * step;
+            const bool ok = idx < hi && P.tile_off[idx] <= b;
+            const int cnt = __popc(__ballot_sync(0xffffffffu, ok));  // probes are monotone
+            const int64_t nlo = lo + (int64_t)cnt * step;
+            hi = imin64(hi, nlo + step);
+            lo = nlo;
         }
         const int64_t row = lo, tile = b - P.tile_off[row];
         const RowPlan rp = P.rows[row];
@@ -299,55 +306,44 @@ __global__ void __launch_bounds__(128) trk_tile_prep_kernel(TrkExecParams P, Til
                 const int64_t slot = P.offset_idxs[track * P.n_queries + query];
                 D.it_lo = T.itv_offsets[slot];
                 D.it_hi = T.itv_offsets[slot + 1];
-                // carry record: last record with a <= h0
+                // carry record (last with a <= h0) and last record that starts inside the tile (a < h1): one strided
+                // pass over the row's sorted records (independent loads)
                 const TRec *__restrict__ recs = P.trecs + rp.rec_off;
-                int32_t rl = -1, rh = rp.n_rec;
-                while (rh - rl > 1) {
-                    const int32_t mid = (rl + rh) >> 1;
-                    if (recs[mid].a <= D.h0) rl = mid; else rh = mid;
+                int c0 = 0, c1 = 0;
+                for (int i = lane; i < rp.n_rec; i += 32) {
+                    const int32_t a = recs[i].a;
+                    c0 += (a <= D.h0);
+                    c1 += (a < D.h1);
                 }
+                const int32_t rl = __reduce_add_sync(0xffffffffu, c0) - 1;
+                const int32_t el = max(__reduce_add_sync(0xffffffffu, c1) - 1, rl);
                 D.r = rl;
                 int64_t src = (int64_t)rp.ref0 + D.h0;  // source position that feeds h0
                 if (rl >= 0) {
                     const TRec cr = recs[rl];
                     src = D.h0 < cr.e ? (int64_t)cr.vrel : (int64_t)cr.resume + (D.h0 - cr.e);
                 }
-                // records that start inside the tile, and the source position that feeds h1
-                int32_t el = rl, eh = rp.n_rec;  // last record with a < h1
-                while (eh - el > 1) {
-                    const int32_t mid = (el + eh) >> 1;
-                    if (recs[mid].a < D.h1) el = mid; else eh = mid;
-                }
                 D.m = 1 + (el - rl);
-                int64_t src_hi = (int64_t)rp.ref0 + D.h1;
+                int64_t src_hi = (int64_t)rp.ref0 + D.h1;  // ... and the one that feeds h1
                 if (el >= 0) {
                     const TRec cr = recs[el];
                     src_hi = D.h1 <= cr.e ? (int64_t)cr.vrel + 1 : (int64_t)cr.resume + (D.h1 - cr.e);
                 }
                 D.src_lo = (int32_t)src;
                 D.src_hi = (int32_t)src_hi;
-                // first interval whose end lies beyond src (ends are sorted: the slot's intervals do not overlap)
+                // first interval whose end lies beyond src (ends are sorted: the slot's intervals do not overlap) ...
                 const int64_t gpos = (int64_t)rp.q_start + src;
-                int64_t a = D.it_lo, bb = D.it_hi;
-                while (a < bb) {
-                    const int64_t mid = (a + bb) >> 1;
-                    if ((int64_t)T.itv_ends[mid] <= gpos) a = mid + 1; else bb = mid;
-                }
+                const int64_t a = warp_upper_le(T.itv_ends, D.it_lo, D.it_hi, (int32_t)imax64(imin64(gpos, INT32_MAX), INT32_MIN)) + 1;
                 D.it0 = a;
                 D.val0 = (src >= 0 && src < (int64_t)rp.contig_len && a < D.it_hi && (int64_t)T.itv_starts[a] <= gpos) ? T.itv_values[a] : 0.0f;
                 // ... and the first one that starts at or beyond src_hi: the tile needs the intervals in between
                 const int64_t ghi = (int64_t)rp.q_start + src_hi;
-                int64_t c = a;
-                bb = D.it_hi;
-                while (c < bb) {
-                    const int64_t mid = (c + bb) >> 1;
-                    if ((int64_t)T.itv_starts[mid] < ghi) c = mid + 1; else bb = mid;
-                }
+                const int64_t c = warp_upper_le(T.itv_starts, a, D.it_hi, (int32_t)imax64(imin64(ghi - 1, INT32_MAX), INT32_MIN)) + 1;
                 D.cnt = (int32_t)imin64(c - a, INT32_MAX);
                 if (D.m > T3_REC || c - a > T3_ITV) D.flags |= TD_BIG;
                 // the execute CTA of this tile reads these next: have them in L2 by then
                 const int64_t n_pf = imin64(c - a, T3_ITV);
-                for (int64_t o = (a * 4) & ~(int64_t)127; o < (a + n_pf) * 4; o += 128) {
+                for (int64_t o = ((a * 4) & ~(int64_t)127) + 128 * lane; o < (a + n_pf) * 4; o += 128 * 32) {
                     asm volatile("prefetch.global.L2 [%0];" ::"l"((const char *)T.itv_starts + o));
                     asm volatile("prefetch.global.L2 [%0];" ::"l"((const char *)T.itv_ends + o));
                     asm volatile("prefetch.global.L2 [%0];" ::"l"((const char *)T.itv_values + o));
@@ -355,7 +351,7 @@ __global__ void __launch_bounds__(128) trk_tile_prep_kernel(TrkExecParams P, Til
             }
         }
     }
-    tdesc[g] = D;
+    if (lane == 0) tdesc[g] = D;
 }
 
 // =====================================================================================

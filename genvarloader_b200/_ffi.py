@@ -67,6 +67,16 @@ class BatchArgs(C.Structure):
                 ("offset_idxs", c_vp), ("base_seed", c_vp), ("starts", c_vp)]
 
 
+class FixedJob(C.Structure):
+    """gvl_fixed_job (include/gvl_b200.h)."""
+
+    _fields_ = [("view", c_vp), ("tab", c_vp), ("svar2", c_vp), ("args", BatchArgs), ("out_offsets", c_vp), ("diffs", c_vp),
+                ("track_lengths", c_vp), ("paint_offsets", c_vp), ("itv", c_vp), ("strategy_ids", c_vp), ("params", c_vp),
+                ("ploidy", c_i64), ("rows_p", c_i64), ("output_length", c_i64), ("ref_slot", c_i64), ("n_tracks", c_i64),
+                ("max_slot_len", c_i64), ("annot_mask", C.c_uint32), ("mode", c_i32), ("realign", c_i32), ("rc_neg", c_i32),
+                ("pad_char", c_u8)]
+
+
 def _load() -> C.CDLL:
     if not LIB_PATH.exists():
         raise ImportError(
@@ -79,6 +89,10 @@ def _load() -> C.CDLL:
     lib.gvl_launch_count.argtypes = [C.c_int]
     lib.gvl_packed_reference_words.restype = c_i64
     lib.gvl_packed_reference_words.argtypes = [c_i64]
+    # the per-batch entries of the fixed-length path take plain ints (no per-call ctypes objects)
+    lib.gvl_dev_fixed_plan.argtypes = [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]
+    lib.gvl_dev_fixed_exec.argtypes = [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]
+    lib.gvl_dev_fixed_run.argtypes = [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]
     return lib
 
 

@@ -27,7 +27,7 @@ import torch
 
 from . import _ffi
 from ._engine import MODES, Engine, _stream
-from ._ffi import BatchArgs, DatasetView, c_i32, c_i64, c_u8, c_u64, c_vp, check, lib, ptr
+from ._ffi import BatchArgs, DatasetView, FixedJob, Intervals, c_i32, c_i64, c_u8, c_u64, c_vp, check, lib, ptr
 from ._insertion_fill import Repeat5p, lower
 from ._types import AnnotatedHaps
 
@@ -143,7 +143,10 @@ class _Out:
         sp, b = self.spec, self.b
         L, p, t = sp.L, sp.p, sp.t
         n = b - lo if n is None else n
-        f = (lambda x: x[lo: lo + n].clone()) if clone else (lambda x: x[lo: lo + n])
+        if lo == 0 and n == b and not clone:
+            f = lambda x: x
+        else:
+            f = (lambda x: x[lo: lo + n].clone()) if clone else (lambda x: x[lo: lo + n])
         res = []
         if sp.want_seqs:
             lead = (b,) if sp.is_ref else (b, p)
@@ -179,68 +182,96 @@ class FixedPipeline:
         b, dev = self.b, self.dev
         with torch.cuda.device(dev):
             # eager path (Dataset.__getitem__): one scratch set, one pinned index buffer
+            self._keep = []
+            self._paint_off = torch.arange(max(self.ring, 1) * b + 1, dtype=torch.int64, device=dev) * sp.L
             self._scr0 = _Scratch(sp, b, dev)
-            self._pin0 = PinnedArray((b + (b + 1) // 2,), np.int64)  # [ds_idx i64[b]][jitter i32[b]]: one copy per call
-            self._pin0_jit = self._pin0.array[b:].view(np.int32)
+            self._scr0.job = self._make_job(self._scr0)
+            # [ds_idx i64[b]][jitter i32[b]]: one copy per call, out of a rotating pool of pinned slots
+            self._pins = [PinnedArray((b + (b + 1) // 2,), np.int64) for _ in range(8)]
+            self._pin_evs = [None] * len(self._pins)
+            self._k = 0
             self._idx0 = torch.zeros(b + (b + 1) // 2, dtype=torch.int64, device=dev)
             self._jit0 = self._idx0[b:].view(torch.int32)
-            self._pin_ev = None
-            self._paint_off = torch.arange(max(self.ring, 1) * b + 1, dtype=torch.int64, device=dev) * sp.L
+            self._ctx_handle, self._job0_adr = self.eng.ctx.handle, C.addressof(self._scr0.job)
+            self._idx0_ptr, self._jit0_ptr = self._idx0.data_ptr(), self._jit0.data_ptr()
         self.halves = []
         if self.ring > 0:
             self._build_rings()
 
     def _cap(self, n_queries: int) -> int:
+        """Plan workspace (records) for `n_queries`: what gvl_dev_fixed_plan derives from the job."""
         return n_queries * self.spec.rows_p * max(self.eng.max_slot_len, 1) if self.ref_slot < 0 else 0
 
+    def _make_job(self, scr: _Scratch) -> FixedJob:
+        """gvl_fixed_job over one scratch set: everything `gvl_dev_fixed_plan/_exec` need that does not change per batch.
+        The host-side structs it points to are kept alive on `self._keep`."""
+        sp, eng = self.spec, self.eng
+        keep = self._keep
+        keep.append(self.view)
+        sv = None
+        if eng.svar2 is not None:
+            sv = eng.svar2_channels(None)
+            keep.append(sv)
+        itv = sid = par = None
+        if sp.t:
+            itv = (Intervals * sp.t)(*[eng.tracks[n][4] for n in sp.names])
+            sid = (c_i32 * sp.t)(*[int(x) for x in sp.fill_ids])
+            par = (C.c_double * sp.t)(*[float(x) for x in sp.fill_params])
+            keep.extend([itv, sid, par])
+        adr = lambda x: c_vp(C.addressof(x)) if x is not None else c_vp(0)
+        mode = MODES[sp.mode] if sp.want_seqs else -1
+        return FixedJob(adr(self.view), adr(eng.tab), adr(sv), scr.args, ptr(scr.out_offsets), ptr(scr.diffs), ptr(scr.track_lengths),
+                        ptr(self._paint_off) if (sp.t and not sp.realign) else c_vp(0), adr(itv), adr(sid), adr(par),
+                        sp.p, sp.rows_p, sp.L, self.ref_slot, sp.t, max(eng.max_slot_len, 1), sp.annot_mask, mode,
+                        1 if sp.realign else 0, 1 if sp.rc_neg else 0, eng.pad_char)
+
     # ------------------------------------------------------------------ one device call over n queries
-    # Stage P ("plan"): batch prep + variant plan.  Stage E ("execute"): the bandwidth-bound kernels.  The eager path
-    # runs both on the current stream; rings run P on a plan stream and E on an execute stream, so the plan of ring
-    # k+1 (latency-bound, few CTAs) overlaps the execute launch of ring k.
+    # Stage P ("plan"): batch prep + variant plan (+ track plan / tile prep).  Stage E ("execute"): the bandwidth-bound
+    # kernels.  The eager path runs both on the current stream (gvl_dev_fixed_run); rings run P on a plan stream and E
+    # on an execute stream, so the plan of ring k+1 (latency-bound, few CTAs) overlaps the execute launch of ring k.
     def _stage_plan(self, eng: Engine, scr: _Scratch, idx_dev, jit_dev, n: int, sub_batch: int = 0):
-        sp = self.spec
-        eng.batch_prep(self.view, idx_dev, jit_dev, n, self.ref_slot, sp.t, sp.annot_mask, scr.args, sub_batch=sub_batch)
-        if sp.want_seqs:
-            eng.plan(scr.regions, scr.shifts, scr.goi[:n], sp.L, self._cap(n), to_rc=scr.to_rc if sp.rc_neg else None,
-                     out_offsets=scr.out_offsets, diffs=scr.diffs, use_svar2=not sp.is_ref)
-        if sp.realign:
-            eng.track_lengths(scr.regions, scr.diffs, n, sp.p, scr.track_lengths)
-            eng.realign_tracks_plan(sp.names, scr.regions, scr.shifts, scr.goi, scr.offset_idxs, scr.track_lengths,
-                                    scr.out_offsets, n * sp.p * sp.L, sp.fill_ids, sp.fill_params, 0, self._cap(n),
-                                    to_rc=scr.to_rc if sp.rc_neg else None, layout="btp", base_seed_dev=scr.base_seed, batch=n,
-                                    sub_batch=sub_batch)
+        check(lib.gvl_dev_fixed_plan(eng.ctx.handle, C.addressof(scr.job), idx_dev.data_ptr(),
+                                     jit_dev.data_ptr() if jit_dev is not None else None, n, sub_batch, _stream()))
 
     def _stage_exec(self, eng: Engine, scr: _Scratch, out: _Out, n: int, sub_batch: int = 0):
-        sp = self.spec
-        rc = scr.to_rc if sp.rc_neg else None
-        if sp.want_seqs:
-            eng.execute(sp.mode, out=out.seq, annot_v=out.av, annot_pos=out.ap)
-        if sp.t:
-            if sp.realign:
-                eng.realign_tracks_exec(out.trk)
-            else:
-                eng.paint_tracks(sp.names, scr.offset_idxs, scr.starts, self._paint_off, n * sp.L,
-                                 scr.to_rc_q if sp.rc_neg else None, out=out.trk, n_queries=n)
+        dp = lambda x: x.data_ptr() if x is not None else None
+        check(lib.gvl_dev_fixed_exec(eng.ctx.handle, C.addressof(scr.job), n, dp(out.seq), dp(out.av), dp(out.ap), dp(out.trk),
+                                     _stream()))
 
     def run_eager(self, ds_idx: np.ndarray, jitter: np.ndarray | None):
-        """One batch (len(ds_idx) <= batch_size) on the current stream; returns freshly allocated outputs."""
+        """One batch (len(ds_idx) <= batch_size) on the current stream; returns freshly allocated outputs.  Host side:
+        one copy into a pinned slot (a small rotating pool, so the host never waits for the previous call's device work),
+        the output allocation and ONE library call (upload + prep + plan + execute)."""
         n = len(ds_idx)
         if n > self.b:
             raise ValueError("batch larger than the pipeline's batch size")
-        host = self._pin0.array
-        with torch.cuda.device(self.dev):
-            if self._pin_ev is not None:
-                self._pin_ev.synchronize()  # the previous call's copy out of the pinned buffer has finished
+        dev = self.dev
+        k = self._k = (self._k + 1) % len(self._pins)
+        pin, ev = self._pins[k], self._pin_evs[k]
+        guard = torch._C._cuda_getDevice() != dev.index
+        if guard:
+            prev = torch.cuda.current_device()
+            torch.cuda.set_device(dev)
+        try:
+            if ev is not None:
+                ev.synchronize()  # the copy out of this pinned slot, len(pool) calls ago, has finished
+            else:
+                ev = self._pin_evs[k] = torch.cuda.Event()
+            host = pin.array
             host[:n] = ds_idx
             if jitter is not None:
-                self._pin0_jit[:n] = jitter
-            check(lib.gvl_dev_upload(self.eng.ctx.handle, ptr(self._idx0), c_vp(self._pin0.ptr), c_i64(self._pin0.nbytes), _stream()))
-            if self._pin_ev is None:
-                self._pin_ev = torch.cuda.Event()
-            self._pin_ev.record()
-            out = _Out(self.spec, n, self.dev)
-            self._stage_plan(self.eng, self._scr0, self._idx0, self._jit0 if jitter is not None else None, n)
-            self._stage_exec(self.eng, self._scr0, out, n)
+                host[self.b:].view(np.int32)[:n] = jitter
+            out = _Out(self.spec, n, dev)
+            dp = lambda x: x.data_ptr() if x is not None else None
+            rc = lib.gvl_dev_fixed_run(self._ctx_handle, self._job0_adr, pin.ptr, pin.nbytes, self._idx0_ptr,
+                                       self._jit0_ptr if jitter is not None else None, n, dp(out.seq), dp(out.av), dp(out.ap),
+                                       dp(out.trk), _stream())
+            if rc:
+                check(rc)
+            ev.record()
+        finally:
+            if guard:
+                torch.cuda.set_device(prev)
         return out.result()
 
     # ------------------------------------------------------------------ rings
@@ -253,6 +284,7 @@ class FixedPipeline:
                 H = type("Half", (), {})()
                 H.eng = self.eng.fork()
                 H.scr = _Scratch(sp, n, dev, n_sub=K)
+                H.scr.job = self._make_job(H.scr)
                 H.out = _Out(sp, n, dev)
                 H.pin = PinnedArray((n + (n + 1) // 2,), np.int64)  # [ds_idx i64[n]][jitter i32[n]]
                 H.pin_jit = H.pin.array[n:].view(np.int32)

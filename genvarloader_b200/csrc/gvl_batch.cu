@@ -144,4 +144,74 @@ int gvl_dev_upload(gvl_ctx *ctx, void *dev, const void *host, int64_t bytes, gvl
     return GVL_OK;
 }
 
+// ---- one fixed-length batch, end to end (the C side of Dataset.__getitem__ / the loader's device calls) ----
+int gvl_dev_fixed_plan(gvl_ctx *ctx, const gvl_fixed_job *J, const int64_t *ds_idx, const int32_t *jitter, int64_t n,
+                       int64_t sub_batch, gvl_stream stream) {
+    if (!ctx || !J || !J->view || !J->tab) return fail(GVL_ERR_ARG, "gvl_dev_fixed_plan: NULL argument");
+    if (J->realign && (J->mode < 0 || J->ref_slot >= 0 || !J->diffs || !J->track_lengths))
+        return fail(GVL_ERR_ARG, "gvl_dev_fixed_plan: realigned tracks need haplotypes, diffs and track_lengths scratch");
+    int rc = gvl_dev_batch_prep(ctx, J->view, ds_idx, jitter, n, sub_batch, J->ref_slot, J->n_tracks, J->annot_mask, &J->args, stream);
+    if (rc) return rc;
+    const gvl_batch_args &A = J->args;
+    const uint8_t *to_rc = J->rc_neg ? A.to_rc : NULL;
+    const int64_t cap = J->ref_slot < 0 ? n * J->rows_p * (J->max_slot_len > 1 ? J->max_slot_len : 1) : 0;
+    gvl_svar2_channels ch;
+    const bool sv = J->svar2 != NULL && J->ref_slot < 0;
+    if (sv) {
+        ch = *J->svar2;
+        ch.row_slot = A.goi;
+    }
+    if (J->mode >= 0) {
+        if (sv)
+            rc = gvl_dev_hap_plan_svar2(ctx, J->tab, &ch, A.regions, A.shifts, n, J->rows_p, to_rc, J->output_length, cap,
+                                        J->out_offsets, J->diffs, stream);
+        else
+            rc = gvl_dev_hap_plan(ctx, J->tab, A.regions, A.shifts, A.goi, n, J->rows_p, NULL, NULL, to_rc, J->output_length, cap,
+                                  J->out_offsets, J->diffs, stream);
+        if (rc) return rc;
+    }
+    if (J->realign) {
+        rc = gvl_dev_track_lengths(ctx, A.regions, J->diffs, n, J->ploidy, J->track_lengths, stream);
+        if (rc) return rc;
+        rc = gvl_dev_realign_tracks_plan(ctx, J->tab, sv ? &ch : NULL, A.regions, A.shifts, A.goi, n, J->ploidy, NULL, NULL, to_rc,
+                                         J->n_tracks, J->itv, A.offset_idxs, J->track_lengths, J->out_offsets,
+                                         n * J->ploidy * J->output_length, J->strategy_ids, J->params, 0, A.base_seed, sub_batch,
+                                         NULL, cap, 1, stream);
+        if (rc) return rc;
+    }
+    return GVL_OK;
+}
+
+int gvl_dev_fixed_exec(gvl_ctx *ctx, const gvl_fixed_job *J, int64_t n, uint8_t *seq, int32_t *annot_v, int32_t *annot_pos,
+                       float *trk, gvl_stream stream) {
+    if (!ctx || !J || !J->tab) return fail(GVL_ERR_ARG, "gvl_dev_fixed_exec: NULL argument");
+    int rc;
+    if (J->mode >= 0) {
+        if (!seq) return fail(GVL_ERR_ARG, "gvl_dev_fixed_exec: sequence output missing");
+        rc = gvl_dev_hap_exec(ctx, J->tab, J->mode, J->pad_char, seq, annot_v, annot_pos, stream);
+        if (rc) return rc;
+    }
+    if (J->n_tracks > 0) {
+        if (!trk) return fail(GVL_ERR_ARG, "gvl_dev_fixed_exec: track output missing");
+        if (J->realign)
+            rc = gvl_dev_realign_tracks_exec(ctx, trk, stream);
+        else
+            rc = gvl_dev_paint_tracks(ctx, J->n_tracks, J->itv, J->args.offset_idxs, J->args.starts, n, J->paint_offsets,
+                                      n * J->output_length, J->rc_neg ? J->args.to_rc_q : NULL, trk, stream);
+        if (rc) return rc;
+    }
+    return GVL_OK;
+}
+
+int gvl_dev_fixed_run(gvl_ctx *ctx, const gvl_fixed_job *J, const void *host, int64_t host_bytes, int64_t *idx_dev,
+                      const int32_t *jitter_dev, int64_t n, uint8_t *seq, int32_t *annot_v, int32_t *annot_pos, float *trk,
+                      gvl_stream stream) {
+    int rc = gvl_dev_upload(ctx, idx_dev, host, host_bytes, stream);
+    if (rc) return rc;
+    rc = gvl_dev_fixed_plan(ctx, J, idx_dev, jitter_dev, n, 0, stream);
+    if (rc) return rc;
+    return gvl_dev_fixed_exec(ctx, J, n, seq, annot_v, annot_pos, trk, stream);
+}
+
+
 }  // extern "C"

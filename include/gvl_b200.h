@@ -354,6 +354,49 @@ int gvl_dev_track_lengths(gvl_ctx *ctx, const int32_t *regions, const int32_t *d
 /* cudaMemcpyAsync(host -> device) on the caller's stream: one copy stages the indices of a whole ring of batches. */
 int gvl_dev_upload(gvl_ctx *ctx, void *dev, const void *host, int64_t bytes, gvl_stream stream);
 
+/* ---- device layer: one fixed-length (region, sample) batch, end to end ------------------ */
+/* What `Dataset.__getitem__` (_dataset/_impl.py:2074-2121 -> _query.py:66-204 -> Haps.__call__ _haps.py:578-870 /
+ * HapsTracks.__call__ _reconstruct.py:132-307) does for a dataset state with a FIXED output length, as two calls over
+ * prepared state: everything that does not change from batch to batch lives in a `gvl_fixed_job` the caller fills once.
+ * All pointers are device pointers unless noted; `args`, `out_offsets`, `diffs`, `track_lengths` are scratch sized for
+ * the largest batch the job will see.  No host sync; graph-capturable. */
+typedef struct gvl_fixed_job {
+    const gvl_dataset_view *view;     /* HOST pointer */
+    const gvl_sparse_tables *tab;     /* HOST pointer */
+    const gvl_svar2_channels *svar2;  /* HOST pointer or NULL (sparse CSR source); its row_slot is ignored: rows read slot args.goi[k] */
+    gvl_batch_args args;
+    int64_t *out_offsets;             /* i64[cap*rows_p + 1] */
+    int32_t *diffs;                   /* i32[cap*ploidy]   realigned tracks only, else NULL */
+    int32_t *track_lengths;           /* i32[cap]          realigned tracks only, else NULL */
+    const int64_t *paint_offsets;     /* i64[cap + 1] = q * output_length: un-realigned tracks only, else NULL */
+    const gvl_intervals *itv;         /* HOST pointer, n_tracks entries (NULL when n_tracks == 0) */
+    const int32_t *strategy_ids;      /* HOST i32[n_tracks] insertion-fill strategy per track */
+    const double *params;             /* HOST f64[n_tracks] */
+    int64_t ploidy, rows_p;           /* rows_p = 1 for "reference" / track-only reads, else ploidy */
+    int64_t output_length;
+    int64_t ref_slot;                 /* >= 0: every row reads this (empty) genotype slot; < 0: haplotypes */
+    int64_t n_tracks;
+    int64_t max_slot_len;             /* upper bound of one row's variant-list length (plan workspace = rows * this) */
+    uint32_t annot_mask;
+    int32_t mode;                     /* GVL_MODE_* of the sequence output; < 0: no sequence output */
+    int32_t realign;                  /* tracks are realigned to the haplotypes (needs mode >= 0 and ref_slot < 0) */
+    int32_t rc_neg;                   /* reverse(-complement) rows of negative-strand regions */
+    uint8_t pad_char;
+} gvl_fixed_job;
+/* batch prep + variant plan (+ track plan and tile prep) of `n` queries; sub_batch as in gvl_dev_batch_prep. */
+int gvl_dev_fixed_plan(gvl_ctx *ctx, const gvl_fixed_job *job, const int64_t *ds_idx, const int32_t *jitter, int64_t n,
+                       int64_t sub_batch, gvl_stream stream);
+/* the bandwidth-bound launches of the batch planned last on `ctx`: seq u8[n*rows_p*L (*4 one-hot)], annot_* i32[n*rows_p*L]
+ * (GVL_MODE_ANNOTATED), trk f32[n*n_tracks*(ploidy|1)*L] in (b, t, p, L) / (b, t, L) order.  Unused outputs NULL. */
+int gvl_dev_fixed_exec(gvl_ctx *ctx, const gvl_fixed_job *job, int64_t n, uint8_t *seq, int32_t *annot_v, int32_t *annot_pos,
+                       float *trk, gvl_stream stream);
+/* upload (`host` = pinned [ds_idx i64[n_cap]][jitter i32[n_cap]], `host_bytes` of it, into `idx_dev`) + plan + exec on one
+ * stream: the whole of a fixed-length `Dataset.__getitem__` in one call.  jitter_dev: where the jitter part lands inside
+ * idx_dev, or NULL. */
+int gvl_dev_fixed_run(gvl_ctx *ctx, const gvl_fixed_job *job, const void *host, int64_t host_bytes, int64_t *idx_dev,
+                      const int32_t *jitter_dev, int64_t n, uint8_t *seq, int32_t *annot_v, int32_t *annot_pos, float *trk,
+                      gvl_stream stream);
+
 /* ---- host layer: reference-shaped entries (host pointers in, host pointers out) ------ */
 /* Upload (or refresh) a static array and cache it by host address; later gvl_* calls that see
  * the same (ptr, bytes) use the device copy.  The caller must not mutate or free the host array

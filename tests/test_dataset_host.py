@@ -67,7 +67,14 @@ def test_validation_like_reference():
         FlankSample(flank_width=-1)
     assert ds.with_tracks(False).active_tracks == ()
     assert ds.with_tracks("t1").active_tracks == ("t1",)
-    d2 = ds.with_insertion_fill(Interpolate(2))
+    # with_insertion_fill mirrors the reference's guards (_impl.py:856-873): tracks active, haplotypes active, realign on
+    with pytest.raises(ValueError, match="tracks are active"):
+        ds.with_tracks(False).with_insertion_fill(Interpolate(2))
+    with pytest.raises(ValueError, match="haplotypes"):
+        ds.with_tracks(["t0", "t1"]).with_seqs("reference").with_insertion_fill(Interpolate(2))
+    with pytest.raises(ValueError, match="realign_tracks=False"):
+        ds.with_tracks(["t0", "t1"]).with_settings(realign_tracks=False).with_insertion_fill(Interpolate(2))
+    d2 = ds.with_tracks(["t0", "t1"]).with_insertion_fill(Interpolate(2))
     assert set(d2.insertion_fill) == {"t0", "t1"}
     with pytest.raises(ValueError):
         ds.with_encoding("onehot_cf")  # ragged length
@@ -100,10 +107,15 @@ def test_batch_loader_host_logic():
     sh = BatchLoader(ds, 4, True, None, False, 7, True, None)
     a, b = list(sh), list(sh)
     flat = np.sort(np.concatenate([x[0] * 3 + x[1] for x in a]))  # (the stub's batch is the (r, s) tuple; indices are appended)
-    assert (flat == np.arange(12)).all() and a[0][2].min() >= 10   # epoch covers everything; indices are non-subset ones
+    assert (flat == np.arange(12)).all()                            # epoch covers everything
+    # return_indices appends the (region, sample) indices the dataset was indexed with (_torch.py:293-300)
+    assert all(len(x) == 4 and (x[2] == x[0]).all() and (x[3] == x[1]).all() for x in a)
     assert any((x[0] != y[0]).any() for x, y in zip(a, b))          # reshuffled every epoch
-    smp = BatchLoader(ds, 2, False, [3, 1, 0], False, None, False, lambda t: ("x", t))
+    # the transform receives the batch's elements as separate arguments (_torch.py:302-303)
+    smp = BatchLoader(ds, 2, False, [3, 1, 0], False, None, False, lambda r, s: ("x", r, s))
     out = list(smp)
-    assert len(smp) == 2 and out[0][0] == "x" and (out[0][1][0] == np.array([1, 0])).all()
+    assert len(smp) == 2 and out[0][0] == "x" and (out[0][1] == np.array([1, 0])).all() and (out[0][2] == np.array([0, 1])).all()
+    smp = BatchLoader(ds, 2, False, np.array([3, 1, 0]), False, None, True, lambda r, s, ri, si: (ri, si))
+    assert (list(smp)[1][0] == np.array([0])).all()
     with pytest.raises(ValueError):
         BatchLoader(ds, 0, False, None, False, None, False, None)

@@ -200,13 +200,22 @@ class Dataset:
 
     @property
     def _r_idx(self) -> np.ndarray:
-        if self.region_subset is not None:
-            return self.region_subset
-        return np.arange(len(self.full_regions)) if self.region_map is None else self.region_map
+        v = self._cache.get("r_idx")
+        if v is None:
+            if self.region_subset is not None:
+                v = self.region_subset
+            else:
+                v = np.arange(len(self.full_regions)) if self.region_map is None else self.region_map
+            v = self._cache["r_idx"] = np.ascontiguousarray(v, np.int64)
+        return v
 
     @property
     def _s_idx(self) -> np.ndarray:
-        return np.arange(len(self.sample_names)) if self.sample_subset is None else self.sample_subset
+        v = self._cache.get("s_idx")
+        if v is None:
+            v = np.arange(len(self.sample_names)) if self.sample_subset is None else self.sample_subset
+            v = self._cache["s_idx"] = np.ascontiguousarray(v, np.int64)
+        return v
 
     # ------------------------------------------------------------------ with_* (immutable evolution)
     def _check_valid_state(self) -> None:
@@ -373,6 +382,12 @@ class Dataset:
             r, s = idx
         else:
             raise IndexError("a Dataset is indexed by (regions, samples)")
+        if (type(r) is np.ndarray and type(s) is np.ndarray and r.ndim == 1 and s.shape == r.shape
+                and r.dtype.kind in "iu" and s.dtype.kind in "iu"):
+            # the loader's case, two paired 1-D integer arrays: fancy indexing does the bounds check, the negative wrap
+            # and the subset mapping in one step each
+            flat = self._r_idx[r] * len(self.sample_names) + self._s_idx[s]
+            return (flat if flat.dtype == np.int64 else flat.astype(np.int64)), False, None
         is_basic = lambda x: isinstance(x, (int, np.integer, slice))
         is_int = lambda x: isinstance(x, (int, np.integer))
         n_s = len(self.sample_names)

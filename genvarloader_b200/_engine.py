@@ -20,13 +20,14 @@ MODES = {"haplotypes": MODE_U8, "u8": MODE_U8, "onehot": MODE_ONEHOT, "onehot_cf
 
 
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)  # ~1 us; torch.cuda.current_stream() costs ~15 us
+if _raw_stream is None:  # pragma: no cover  (older torch)
+    def _raw_stream(device_index: int) -> int:
+        return torch.cuda.current_stream(device_index).cuda_stream
 
 
 def _stream() -> c_vp:
     """torch's current CUDA stream of the current device as a raw handle."""
-    if _raw_stream is not None:
-        return c_vp(_raw_stream(torch._C._cuda_getDevice()))
-    return c_vp(torch.cuda.current_stream().cuda_stream)
+    return c_vp(_raw_stream(torch._C._cuda_getDevice()))
 
 
 def _dev(a, dtype, device, pad: int = 0) -> torch.Tensor:

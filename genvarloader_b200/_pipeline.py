@@ -26,7 +26,7 @@ import numpy as np
 import torch
 
 from . import _ffi
-from ._engine import MODES, Engine, _stream
+from ._engine import MODES, Engine, _raw_stream, _stream
 from ._ffi import BatchArgs, DatasetView, FixedJob, Intervals, c_i32, c_i64, c_u8, c_u64, c_vp, check, lib, ptr
 from ._insertion_fill import Repeat5p, lower
 from ._types import AnnotatedHaps
@@ -186,10 +186,6 @@ class FixedPipeline:
             self._paint_off = torch.arange(max(self.ring, 1) * b + 1, dtype=torch.int64, device=dev) * sp.L
             self._scr0 = _Scratch(sp, b, dev)
             self._scr0.job = self._make_job(self._scr0)
-            # [ds_idx i64[b]][jitter i32[b]]: one copy per call, out of a rotating pool of pinned slots
-            self._pins = [PinnedArray((b + (b + 1) // 2,), np.int64) for _ in range(8)]
-            self._pin_evs = [None] * len(self._pins)
-            self._k = 0
             self._idx0 = torch.zeros(b + (b + 1) // 2, dtype=torch.int64, device=dev)
             self._jit0 = self._idx0[b:].view(torch.int32)
             self._ctx_handle, self._job0_adr = self.eng.ctx.handle, C.addressof(self._scr0.job)
@@ -240,35 +236,25 @@ class FixedPipeline:
 
     def run_eager(self, ds_idx: np.ndarray, jitter: np.ndarray | None):
         """One batch (len(ds_idx) <= batch_size) on the current stream; returns freshly allocated outputs.  Host side:
-        one copy into a pinned slot (a small rotating pool, so the host never waits for the previous call's device work),
-        the output allocation and ONE library call (upload + prep + plan + execute)."""
+        the output allocation and ONE library call (gvl_dev_fixed_run: staged index upload + prep + plan + execute)."""
         n = len(ds_idx)
         if n > self.b:
             raise ValueError("batch larger than the pipeline's batch size")
         dev = self.dev
-        k = self._k = (self._k + 1) % len(self._pins)
-        pin, ev = self._pins[k], self._pin_evs[k]
         guard = torch._C._cuda_getDevice() != dev.index
         if guard:
             prev = torch.cuda.current_device()
             torch.cuda.set_device(dev)
         try:
-            if ev is not None:
-                ev.synchronize()  # the copy out of this pinned slot, len(pool) calls ago, has finished
-            else:
-                ev = self._pin_evs[k] = torch.cuda.Event()
-            host = pin.array
-            host[:n] = ds_idx
-            if jitter is not None:
-                host[self.b:].view(np.int32)[:n] = jitter
             out = _Out(self.spec, n, dev)
-            dp = lambda x: x.data_ptr() if x is not None else None
-            rc = lib.gvl_dev_fixed_run(self._ctx_handle, self._job0_adr, pin.ptr, pin.nbytes, self._idx0_ptr,
-                                       self._jit0_ptr if jitter is not None else None, n, dp(out.seq), dp(out.av), dp(out.ap),
-                                       dp(out.trk), _stream())
+            seq, av, ap, trk = out.seq, out.av, out.ap, out.trk
+            rc = lib.gvl_dev_fixed_run(self._ctx_handle, self._job0_adr, ds_idx.ctypes.data,
+                                       jitter.ctypes.data if jitter is not None else None, n, self._idx0_ptr, self._jit0_ptr,
+                                       seq.data_ptr() if seq is not None else None, av.data_ptr() if av is not None else None,
+                                       ap.data_ptr() if ap is not None else None, trk.data_ptr() if trk is not None else None,
+                                       _raw_stream(dev.index))
             if rc:
                 check(rc)
-            ev.record()
         finally:
             if guard:
                 torch.cuda.set_device(prev)

@@ -6,6 +6,8 @@
 // interval slot of every (track, query) (_reconstruct.py:233-236).  Here the same O(batch) arithmetic is one
 // small kernel over the flat dataset indices, so a batch needs ONE host->device copy (its indices) and the
 // whole chain prep -> plan -> execute can be captured in a CUDA graph and replayed with new indices.
+#include <cstring>
+
 #include "gvl_internal.cuh"
 
 using namespace gvl;
@@ -29,7 +31,15 @@ struct PrepParams {
     int32_t *starts;
 };
 
-__global__ void __launch_bounds__(128) batch_prep_kernel(PrepParams P) {
+// Indices of a small batch passed BY VALUE with the launch (kernel parameter space): no staging copy, no event.
+constexpr int INLINE_MAX = 256;
+struct InlineIdx {
+    int64_t idx[INLINE_MAX];
+    int32_t jit[INLINE_MAX];
+};
+
+template <class IdxOf, class JitOf>
+__device__ __forceinline__ void batch_prep_body(const PrepParams &P, IdxOf idx_of, JitOf jit_of) {
     if (P.base_seed) {
         // deterministic fill seed of every logical batch: xor-reduce of its dataset indices as u64
         // (_reconstruct.py:215-218); one warp per logical batch, warps stride over them
@@ -39,7 +49,7 @@ __global__ void __launch_bounds__(128) batch_prep_kernel(PrepParams P) {
         for (int64_t sb = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); sb < n_sub; sb += n_warps) {
             const int64_t lo = sb * P.sub_batch, hi = imin64(lo + P.sub_batch, P.batch);
             uint64_t x = 0;
-            for (int64_t i = lo + lane; i < hi; i += 32) x ^= (uint64_t)P.ds_idx[i];
+            for (int64_t i = lo + lane; i < hi; i += 32) x ^= (uint64_t)idx_of(i);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) x ^= __shfl_xor_sync(0xffffffffu, x, o);
             if (lane == 0) P.base_seed[sb] = x;
@@ -47,11 +57,11 @@ __global__ void __launch_bounds__(128) batch_prep_kernel(PrepParams P) {
     }
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= P.batch) return;
-    const int64_t idx = P.ds_idx[q];
+    const int64_t idx = idx_of(q);
     const int64_t r = idx / P.n_samples;
     const int4 reg = *reinterpret_cast<const int4 *>(P.full_regions + 4 * r);  // contig, start, end, strand
     const int32_t len = reg.z - reg.y;
-    const int32_t start = reg.y + (P.jitter ? P.jitter[q] : 0);  // _query.py:165-171
+    const int32_t start = reg.y + jit_of(q);  // _query.py:165-171
     P.regions[3 * q + 0] = reg.x;
     P.regions[3 * q + 1] = start;
     P.regions[3 * q + 2] = start + len;
@@ -68,6 +78,14 @@ __global__ void __launch_bounds__(128) batch_prep_kernel(PrepParams P) {
         P.offset_idxs[t * P.batch + q] = ((P.annot_mask >> t) & 1u) ? r : idx;
 }
 
+__global__ void __launch_bounds__(128) batch_prep_kernel(PrepParams P) {
+    batch_prep_body(P, [&](int64_t i) { return P.ds_idx[i]; }, [&](int64_t i) { return P.jitter ? P.jitter[i] : 0; });
+}
+
+__global__ void __launch_bounds__(128) batch_prep_inline_kernel(PrepParams P, const __grid_constant__ InlineIdx I) {
+    batch_prep_body(P, [&](int64_t i) { return I.idx[i]; }, [&](int64_t i) { return P.jitter ? I.jit[i] : 0; });
+}
+
 __global__ void __launch_bounds__(128) track_lengths_kernel(const int32_t *__restrict__ regions,
                                                             const int32_t *__restrict__ diffs, int64_t batch,
                                                             int64_t ploidy, int32_t *__restrict__ out) {
@@ -82,9 +100,10 @@ __global__ void __launch_bounds__(128) track_lengths_kernel(const int32_t *__res
 
 extern "C" {
 
-int gvl_dev_batch_prep(gvl_ctx *ctx, const gvl_dataset_view *view, const int64_t *ds_idx, const int32_t *jitter,
-                       int64_t batch, int64_t sub_batch, int64_t ref_slot, int64_t n_tracks, uint32_t annot_mask,
-                       const gvl_batch_args *args, gvl_stream stream) {
+// ds_idx / jitter are device arrays, or -- inline_host -- host arrays of <= INLINE_MAX entries passed with the launch
+static int launch_batch_prep(gvl_ctx *ctx, const gvl_dataset_view *view, const int64_t *ds_idx, const int32_t *jitter,
+                             bool inline_host, int64_t batch, int64_t sub_batch, int64_t ref_slot, int64_t n_tracks,
+                             uint32_t annot_mask, const gvl_batch_args *args, gvl_stream stream) {
     if (!ctx || !view || !args) return fail(GVL_ERR_ARG, "gvl_dev_batch_prep: NULL argument");
     if (batch == 0) return GVL_OK;
     if (!ds_idx || !view->full_regions || !args->regions || !args->shifts || !args->goi || !args->to_rc)
@@ -115,9 +134,28 @@ int gvl_dev_batch_prep(gvl_ctx *ctx, const gvl_dataset_view *view, const int64_t
     P.offset_idxs = args->offset_idxs;
     P.base_seed = args->base_seed;
     P.starts = args->starts;
-    batch_prep_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, (cudaStream_t)stream>>>(P);
+    const unsigned grid = (unsigned)((batch + 127) / 128);
+    if (inline_host) {
+        if (batch > INLINE_MAX) return fail(GVL_ERR_ARG, "gvl_dev_batch_prep: inline batch too large");
+        const int64_t n_rows = view->n_regions * view->n_samples;
+        InlineIdx I;
+        for (int64_t i = 0; i < batch; i++) {
+            if (ds_idx[i] < 0 || ds_idx[i] >= n_rows) return fail(GVL_ERR_ARG, "dataset index %lld out of range", (long long)ds_idx[i]);
+            I.idx[i] = ds_idx[i];
+        }
+        if (jitter) memcpy(I.jit, jitter, (size_t)batch * 4);
+        batch_prep_inline_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(P, I);
+    } else {
+        batch_prep_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(P);
+    }
     GVL_LAUNCH_CHECK();
     return GVL_OK;
+}
+
+int gvl_dev_batch_prep(gvl_ctx *ctx, const gvl_dataset_view *view, const int64_t *ds_idx, const int32_t *jitter,
+                       int64_t batch, int64_t sub_batch, int64_t ref_slot, int64_t n_tracks, uint32_t annot_mask,
+                       const gvl_batch_args *args, gvl_stream stream) {
+    return launch_batch_prep(ctx, view, ds_idx, jitter, false, batch, sub_batch, ref_slot, n_tracks, annot_mask, args, stream);
 }
 
 // track_lengths[q] = (end - start) - min(0, min_h diffs[q, h]): the source window of a realigned track grows by the
@@ -145,13 +183,21 @@ int gvl_dev_upload(gvl_ctx *ctx, void *dev, const void *host, int64_t bytes, gvl
 }
 
 // ---- one fixed-length batch, end to end (the C side of Dataset.__getitem__ / the loader's device calls) ----
+static int fixed_plan_prepared(gvl_ctx *ctx, const gvl_fixed_job *J, int64_t n, int64_t sub_batch, gvl_stream stream);
+
 int gvl_dev_fixed_plan(gvl_ctx *ctx, const gvl_fixed_job *J, const int64_t *ds_idx, const int32_t *jitter, int64_t n,
                        int64_t sub_batch, gvl_stream stream) {
     if (!ctx || !J || !J->view || !J->tab) return fail(GVL_ERR_ARG, "gvl_dev_fixed_plan: NULL argument");
     if (J->realign && (J->mode < 0 || J->ref_slot >= 0 || !J->diffs || !J->track_lengths))
         return fail(GVL_ERR_ARG, "gvl_dev_fixed_plan: realigned tracks need haplotypes, diffs and track_lengths scratch");
-    int rc = gvl_dev_batch_prep(ctx, J->view, ds_idx, jitter, n, sub_batch, J->ref_slot, J->n_tracks, J->annot_mask, &J->args, stream);
+    int rc = launch_batch_prep(ctx, J->view, ds_idx, jitter, false, n, sub_batch, J->ref_slot, J->n_tracks, J->annot_mask, &J->args, stream);
     if (rc) return rc;
+    return fixed_plan_prepared(ctx, J, n, sub_batch, stream);
+}
+
+// everything of gvl_dev_fixed_plan after the batch prep
+static int fixed_plan_prepared(gvl_ctx *ctx, const gvl_fixed_job *J, int64_t n, int64_t sub_batch, gvl_stream stream) {
+    int rc;
     const gvl_batch_args &A = J->args;
     const uint8_t *to_rc = J->rc_neg ? A.to_rc : NULL;
     const int64_t cap = J->ref_slot < 0 ? n * J->rows_p * (J->max_slot_len > 1 ? J->max_slot_len : 1) : 0;
@@ -203,15 +249,57 @@ int gvl_dev_fixed_exec(gvl_ctx *ctx, const gvl_fixed_job *J, int64_t n, uint8_t 
     return GVL_OK;
 }
 
-int gvl_dev_fixed_run(gvl_ctx *ctx, const gvl_fixed_job *J, const void *host, int64_t host_bytes, int64_t *idx_dev,
-                      const int32_t *jitter_dev, int64_t n, uint8_t *seq, int32_t *annot_v, int32_t *annot_pos, float *trk,
+int gvl_dev_fixed_run(gvl_ctx *ctx, const gvl_fixed_job *J, const int64_t *ds_idx, const int32_t *jitter, int64_t n,
+                      int64_t *idx_dev, int32_t *jitter_dev, uint8_t *seq, int32_t *annot_v, int32_t *annot_pos, float *trk,
                       gvl_stream stream) {
-    int rc = gvl_dev_upload(ctx, idx_dev, host, host_bytes, stream);
-    if (rc) return rc;
-    rc = gvl_dev_fixed_plan(ctx, J, idx_dev, jitter_dev, n, 0, stream);
+    if (!ctx || !J || n < 0 || (n > 0 && (!ds_idx || !idx_dev)) || (jitter && !jitter_dev))
+        return fail(GVL_ERR_ARG, "gvl_dev_fixed_run: bad argument");
+    if (n == 0) return GVL_OK;
+    GVL_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n <= INLINE_MAX) {  // small batch: the indices travel with the prep launch
+        if (!J->view || !J->tab) return fail(GVL_ERR_ARG, "gvl_dev_fixed_run: NULL argument");
+        if (J->realign && (J->mode < 0 || J->ref_slot >= 0 || !J->diffs || !J->track_lengths))
+            return fail(GVL_ERR_ARG, "gvl_dev_fixed_run: realigned tracks need haplotypes, diffs and track_lengths scratch");
+        int rc = launch_batch_prep(ctx, J->view, ds_idx, jitter, true, n, 0, J->ref_slot, J->n_tracks, J->annot_mask, &J->args, stream);
+        if (rc) return rc;
+        rc = fixed_plan_prepared(ctx, J, n, 0, stream);
+        if (rc) return rc;
+        return gvl_dev_fixed_exec(ctx, J, n, seq, annot_v, annot_pos, trk, stream);
+    }
+    // stage the (pageable) indices through a rotating pinned slot: the host never waits for the previous call's copy
+    gvl_ctx::StageSlot &S = ctx->stage[ctx->stage_k];
+    ctx->stage_k = (ctx->stage_k + 1) % 8;
+    if (S.used) GVL_CUDA(cudaEventSynchronize(S.ev));
+    const int64_t need = n * 12;
+    if (S.bytes < need) {
+        if (S.host) cudaFreeHost(S.host);
+        S.host = nullptr;
+        S.bytes = 0;
+        int64_t cap = 4096;
+        while (cap < need) cap *= 2;
+        GVL_CUDA(cudaMallocHost(&S.host, (size_t)cap));
+        S.bytes = cap;
+    }
+    if (!S.ev) GVL_CUDA(cudaEventCreateWithFlags(&S.ev, cudaEventDisableTiming));
+    {
+        const int64_t n_rows = J->view ? J->view->n_regions * J->view->n_samples : 0;
+        int64_t *dst = (int64_t *)S.host;
+        for (int64_t i = 0; i < n; i++) {
+            if (ds_idx[i] < 0 || ds_idx[i] >= n_rows) return fail(GVL_ERR_ARG, "dataset index %lld out of range", (long long)ds_idx[i]);
+            dst[i] = ds_idx[i];
+        }
+    }
+    GVL_CUDA(cudaMemcpyAsync(idx_dev, S.host, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    if (jitter) {
+        memcpy((char *)S.host + n * 8, jitter, (size_t)n * 4);
+        GVL_CUDA(cudaMemcpyAsync(jitter_dev, (char *)S.host + n * 8, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    }
+    GVL_CUDA(cudaEventRecord(S.ev, st));
+    S.used = true;
+    int rc = gvl_dev_fixed_plan(ctx, J, idx_dev, jitter ? jitter_dev : NULL, n, 0, stream);
     if (rc) return rc;
     return gvl_dev_fixed_exec(ctx, J, n, seq, annot_v, annot_pos, trk, stream);
 }
-
 
 }  // extern "C"

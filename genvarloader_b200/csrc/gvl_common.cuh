@@ -125,6 +125,14 @@ struct gvl_ctx {
     int last_exec_kernel;       // 0 byte-oriented, 1 packed one-hot (gvl_debug_last_exec_kernel)
     void *trk_params;           // parameters of the pending track execute launch (gvl_tracks.cu)
     bool trk_plan_valid;
+    // gvl_dev_fixed_run: rotating pinned staging slots for the per-call index upload (gvl_batch.cu)
+    struct StageSlot {
+        void *host = nullptr;
+        int64_t bytes = 0;
+        cudaEvent_t ev = nullptr;
+        bool used = false;
+    } stage[8];
+    int stage_k = 0;
     void *zeros;                // device zeros (gvl_aux.cu: rows without genotypes)
     int64_t zeros_bytes;
     // host layer

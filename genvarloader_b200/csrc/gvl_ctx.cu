@@ -195,6 +195,10 @@ void gvl_ctx_destroy(gvl_ctx *ctx) {
     for (auto &kv : ctx->packed_refs) cudaFree(kv.second);
     for (auto &s : ctx->scratch) cudaFree(s.first);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (auto &sl : ctx->stage) {
+        if (sl.host) cudaFreeHost(sl.host);
+        if (sl.ev) cudaEventDestroy(sl.ev);
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }

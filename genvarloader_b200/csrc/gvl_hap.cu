@@ -261,6 +261,19 @@ __global__ void __launch_bounds__(PLAN_WARPS * 32) hap_plan_serial_kernel(HapPla
 #include "gvl_trk_plan.cuh"
 #include "gvl_plan_par.cuh"
 
+// Threads per (query, hap) row of the parallel plan kernel, from the mean list-length bound: one warp for short lists; one
+// 256-thread CTA up to ~4,000 variants (cfg3's ~600-variant rows: 52 us per 640 rows against 63 us with 512 threads -- a
+// half-empty second chunk costs more than a third pass; cfg2d's ~1,300-variant rows: 125 vs 144 us); 512 beyond.  GVL_PLAN_NT=32|256|512 forces a width (A/B runs).
+static int plan_width(int64_t max_records, int64_t n_work) {
+    static const int force_nt = [] {
+        const char *e = getenv("GVL_PLAN_NT");
+        return e ? atoi(e) : 0;
+    }();
+    if (force_nt == 32 || force_nt == 256 || force_nt == 512) return force_nt;
+    if (max_records <= 40 * n_work) return 32;
+    return max_records <= 4096 * n_work ? 256 : 512;
+}
+
 // ragged plans: exclusive scan of row lengths -> out_offsets, RowPlan.out_off, tile map, totals.
 __global__ void __launch_bounds__(1024) row_scan_kernel(int64_t n_work, const int32_t *__restrict__ row_len,
                                                         RowPlan *rows, int64_t *out_offsets, int64_t *tile_off,
@@ -866,16 +879,13 @@ static int hap_plan_impl(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_s
         const char *e = getenv("GVL_PLAN");
         return e && e[0] == 's';
     }();
-    static const int force_nt = [] {  // GVL_PLAN_NT=32|256|512: A/B runs of the plan kernel's width
-        const char *e = getenv("GVL_PLAN_NT");
-        return e ? atoi(e) : 0;
-    }();
+    const int nt = plan_width(max_records, n_work);
     if (force_serial) {
         const unsigned grid = (unsigned)((n_work + PLAN_WARPS - 1) / PLAN_WARPS);
         hap_plan_serial_kernel<<<grid, PLAN_WARPS * 32, 0, st>>>(P);
-    } else if (force_nt == 32 || (!force_nt && max_records <= 40 * n_work)) {  // short lists: one warp per row, 4 rows per CTA
+    } else if (nt == 32) {  // short lists: one warp per row, 4 rows per CTA
         hap_plan_par_kernel<32, false><<<(unsigned)((n_work + 3) / 4), 128, 0, st>>>(P);
-    } else if (force_nt == 256 || (!force_nt && max_records <= 384 * n_work)) {  // one 256-thread CTA per row
+    } else if (nt == 256) {  // one 256-thread CTA per row
         hap_plan_par_kernel<256, false><<<(unsigned)n_work, 256, 0, st>>>(P);
     } else {  // long lists: 512 variants per sequential chunk
         hap_plan_par_kernel<512, false><<<(unsigned)n_work, 512, 0, st>>>(P);
@@ -923,8 +933,9 @@ int gvl_trk_plan_launch(gvl_ctx *ctx, const gvl_sparse_tables *tab, const Merged
     P.dir_stride = 0;
     P.trecs = (TRec *)ctx->trk.trecs;
     P.track_lengths = track_lengths;
-    if (max_records <= 40 * n_work) hap_plan_par_kernel<32, true><<<(unsigned)((n_work + 3) / 4), 128, 0, st>>>(P);
-    else if (max_records <= 384 * n_work) hap_plan_par_kernel<256, true><<<(unsigned)n_work, 256, 0, st>>>(P);
+    const int nt = plan_width(max_records, n_work);
+    if (nt == 32) hap_plan_par_kernel<32, true><<<(unsigned)((n_work + 3) / 4), 128, 0, st>>>(P);
+    else if (nt == 256) hap_plan_par_kernel<256, true><<<(unsigned)n_work, 256, 0, st>>>(P);
     else hap_plan_par_kernel<512, true><<<(unsigned)n_work, 512, 0, st>>>(P);
     GVL_LAUNCH_CHECK();
     return GVL_OK;

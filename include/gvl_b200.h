@@ -390,11 +390,13 @@ int gvl_dev_fixed_plan(gvl_ctx *ctx, const gvl_fixed_job *job, const int64_t *ds
  * (GVL_MODE_ANNOTATED), trk f32[n*n_tracks*(ploidy|1)*L] in (b, t, p, L) / (b, t, L) order.  Unused outputs NULL. */
 int gvl_dev_fixed_exec(gvl_ctx *ctx, const gvl_fixed_job *job, int64_t n, uint8_t *seq, int32_t *annot_v, int32_t *annot_pos,
                        float *trk, gvl_stream stream);
-/* upload (`host` = pinned [ds_idx i64[n_cap]][jitter i32[n_cap]], `host_bytes` of it, into `idx_dev`) + plan + exec on one
- * stream: the whole of a fixed-length `Dataset.__getitem__` in one call.  jitter_dev: where the jitter part lands inside
- * idx_dev, or NULL. */
-int gvl_dev_fixed_run(gvl_ctx *ctx, const gvl_fixed_job *job, const void *host, int64_t host_bytes, int64_t *idx_dev,
-                      const int32_t *jitter_dev, int64_t n, uint8_t *seq, int32_t *annot_v, int32_t *annot_pos, float *trk,
+/* The whole of a fixed-length `Dataset.__getitem__` in one call: ds_idx i64[n] / jitter i32[n] (optional) are HOST arrays
+ * (pageable is fine, the caller may reuse them at once).  Up to 256 queries they travel BY VALUE with the batch-prep launch
+ * (kernel parameter space: no copy, no event); larger batches are staged through a rotating pool of pinned slots owned by the
+ * context into idx_dev / jitter_dev (device scratch, n entries), so the host never waits for earlier calls.  Indices are
+ * range-checked against the view (GVL_ERR_ARG).  Then gvl_dev_fixed_plan + gvl_dev_fixed_exec on `stream`. */
+int gvl_dev_fixed_run(gvl_ctx *ctx, const gvl_fixed_job *job, const int64_t *ds_idx, const int32_t *jitter, int64_t n,
+                      int64_t *idx_dev, int32_t *jitter_dev, uint8_t *seq, int32_t *annot_v, int32_t *annot_pos, float *trk,
                       gvl_stream stream);
 
 /* ---- host layer: reference-shaped entries (host pointers in, host pointers out) ------ */

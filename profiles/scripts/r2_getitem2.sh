@@ -1,0 +1,15 @@
+mkdir -p gpurun_out
+python -m pytest tests/test_gpu_pipeline.py tests/test_gpu_dataset.py tests/test_gpu_svar2_dataset.py tests/test_gpu_open.py -x -q -m gpu 2>&1 | tail -3
+python profiles/probe_dataset.py cfg2 > gpurun_out/probe_dataset_cfg2.log 2>&1; head -1 gpurun_out/probe_dataset_cfg2.log; sed -n 2,24p gpurun_out/probe_dataset_cfg2.log | cut -c1-150
+python profiles/probe_dataset.py cfg3 > gpurun_out/probe_dataset_cfg3.log 2>&1; head -1 gpurun_out/probe_dataset_cfg3.log
+pick() { python - "$1" <<'PY'
+import json,sys
+d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+print(sys.argv[1], 'value %.4g'%d['value'], 'blk', d['timed_block_ms']['median'], d['timed_block_ms']['min'], 'whole %.3f'%d['whole_step_frac'], 'exec %.4f plan %.4f'%(d['roofline']['launch_ms'], d['roofline']['plan_kernel_ms']), 'api %.4g'%d['api']['value'], 'trk', d.get('tracks',{}).get('ms_per_step'))
+PY
+}
+python bench.py --steps 20 --warmup 5 --cpu-seconds 0.5 > gpurun_out/ab_default.json 2>gpurun_out/ab.err; pick gpurun_out/ab_default.json
+GVL_PLAN_NT=256 python bench.py --steps 20 --warmup 5 --cpu-seconds 0.5 > gpurun_out/ab_nt256.json 2>gpurun_out/ab.err; pick gpurun_out/ab_nt256.json
+GVL_LIB_NAME=libgvl_occ1536.so python bench.py --steps 20 --warmup 5 --cpu-seconds 0.5 > gpurun_out/ab_occ.json 2>gpurun_out/ab.err; pick gpurun_out/ab_occ.json
+GVL_LIB_NAME=libgvl_occ1536.so GVL_PLAN_NT=256 python bench.py --steps 20 --warmup 5 --cpu-seconds 0.5 > gpurun_out/ab_occ_nt256.json 2>gpurun_out/ab.err; pick gpurun_out/ab_occ_nt256.json
+python bench.py --steps 20 --warmup 5 --cpu-seconds 0.5 > gpurun_out/ab_default2.json 2>gpurun_out/ab.err; pick gpurun_out/ab_default2.json

@@ -67,6 +67,55 @@ __device__ __forceinline__ int64_t grp_reduce(int64_t x, int64_t *s_warp) {
     return r;
 }
 
+// One-barrier block scan: inclusive result, the value of the thread before (`excl`, identity for thread 0) and the
+// group's aggregate (`total`), for 32- or 64-bit operands.  Consecutive scans alternate between two staging buffers
+// (`sb` toggles uniformly), so the buffer a scan writes was last read two scans -- at least one barrier -- ago.
+template <class T, bool IS_MAX> struct ScanId;
+template <> struct ScanId<int32_t, true> { static constexpr int32_t v = INT32_MIN; };
+template <> struct ScanId<int64_t, true> { static constexpr int64_t v = INT64_MIN; };
+template <> struct ScanId<int32_t, false> { static constexpr int32_t v = 0; };
+template <> struct ScanId<int64_t, false> { static constexpr int64_t v = 0; };
+
+template <int NT, bool IS_MAX, class T>
+__device__ __forceinline__ T grp_scan_x(T x, int64_t (*bufs)[NT / 32 + 1], int &sb, T &excl, T &total) {
+    const int lane = threadIdx.x & 31;
+    constexpr T ID = ScanId<T, IS_MAX>::v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const T y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x = IS_MAX ? (x > y ? x : y) : x + y;
+    }
+    T ex = __shfl_up_sync(0xffffffffu, x, 1);
+    if (lane == 0) ex = ID;
+    if (NT == 32) {
+        excl = ex;
+        total = __shfl_sync(0xffffffffu, x, 31);
+        return x;
+    }
+    T *s = reinterpret_cast<T *>(bufs[sb]);
+    sb ^= 1;
+    const int warp = threadIdx.x >> 5;
+    if (lane == 31) s[warp] = x;
+    __syncthreads();
+    T pre = ID, tot = ID;
+#pragma unroll
+    for (int w = 0; w < NT / 32; w++) {
+        const T v = s[w];
+        if (w < warp) pre = IS_MAX ? (pre > v ? pre : v) : pre + v;
+        tot = IS_MAX ? (tot > v ? tot : v) : tot + v;
+    }
+    excl = IS_MAX ? (ex > pre ? ex : pre) : ex + pre;
+    total = tot;
+    return IS_MAX ? (x > pre ? x : pre) : x + pre;
+}
+
+// number of threads of the group whose predicate holds, to all threads (one barrier)
+template <int NT>
+__device__ __forceinline__ int grp_count(bool p) {
+    if (NT == 32) return __popc(__ballot_sync(0xffffffffu, p));
+    return __syncthreads_count(p);
+}
+
 template <int NT>
 struct PlanSmem {
     int32_t pos[NT];
@@ -75,6 +124,8 @@ struct PlanSmem {
     uint8_t head[NT];
     uint8_t applied[NT];
     int64_t warp[NT / 32 + 1];
+    int64_t scan[2][NT / 32 + 1];  // grp_scan_x staging (double-buffered)
+    int64_t st[2];                  // carried state broadcast (output cursor, reference cursor)
     int flag;
 };
 
@@ -137,6 +188,7 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT, GVL_PLAN_OCC / (NT == 32 
     if (want_diff && nvar > 0) {
         int64_t d_ref = q_start;  // running max end of counted variants (src/genotypes/mod.rs:57,78)
         int64_t last_pos = INT64_MIN;
+        int sb1 = 0;
         for (int64_t base = 0; base < nvar; base += NT) {
             const int64_t i = base + t;
             int64_t pos = INT64_MAX, il = 0;
@@ -149,27 +201,26 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT, GVL_PLAN_OCC / (NT == 32 
             }
             const int64_t end = (i < nvar) ? pos - imin64(il, 0) + 1 : INT64_MIN;
             // sortedness (of the whole list, kept or not)
-            grp_sync<NT>();
+            const int nv = (int)imin64(NT, nvar - base);  // entries of this chunk
+            const int32_t end32 = (int32_t)imax64(imin64(end, INT32_MAX), INT32_MIN);
             S.pos[t] = (int32_t)imin64(pos, INT32_MAX);
+            S.end[t] = end32;
             grp_sync<NT>();
             const int64_t prev = (t > 0) ? (int64_t)S.pos[t - 1] : last_pos;
             bool bad = (i < nvar) && (pos < prev);
+            if (NT == 32) bad = __any_sync(0xffffffffu, bad); else bad = __syncthreads_or(bad);
+            if (bad) {
+                unsorted = true;
+                break;
+            }
+            last_pos = S.pos[nv - 1];
             // variants that take part at all: :69-74 (the `break` is a suffix cut for sorted input)
             const bool in = kept && (end > q_start) && (pos < q_end);
-            const int64_t mx_incl = grp_scan_incl<NT, true>(in ? end : INT64_MIN, S.warp);
-            int64_t mx_excl = __shfl_up_sync(0xffffffffu, mx_incl, 1);
-            if (NT != 32) {
-                grp_sync<NT>();
-                if ((t & 31) == 31) S.warp[t >> 5] = mx_incl;
-                grp_sync<NT>();
-                if ((t & 31) == 0) mx_excl = (t > 0) ? S.warp[(t >> 5) - 1] : INT64_MIN;
-            } else if (t == 0) {
-                mx_excl = INT64_MIN;
-            }
-            mx_excl = imax64(mx_excl, d_ref);
+            int32_t mx_excl32, tot32;
+            grp_scan_x<NT, true, int32_t>(in ? end32 : INT32_MIN, S.scan, sb1, mx_excl32, tot32);
+            const int64_t mx_excl = imax64((int64_t)mx_excl32, d_ref);
             const bool left = in && pos < q_start;          // always counted
             const bool head = in && !left && pos >= mx_excl;  // certainly counted, resets the running max
-            S.end[t] = (int32_t)imax64(imin64(end, INT32_MAX), INT32_MIN);
             S.elig[t] = in ? (left ? 2 : 1) : 0;
             S.head[t] = head;
             S.applied[t] = (left || head);
@@ -178,7 +229,6 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT, GVL_PLAN_OCC / (NT == 32 
             if (head || t == 0) {
                 int64_t cur = head ? end : d_ref;
                 int u = head ? t + 1 : 0;
-                const int nv = (int)imin64(NT, nvar - base);  // entries past the list end are idle: do not walk them
                 for (; u < nv && !S.head[u]; u++) {
                     const int e = S.elig[u];
                     if (e == 0) continue;
@@ -198,32 +248,13 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT, GVL_PLAN_OCC / (NT == 32 
                 if (il < 0) adj += imax64(q_start - pos - 1, 0);  // :79-81
                 adj += imax64(end - q_end, 0);                     // :82
             }
-            const int64_t tot = grp_scan_incl<NT, false>(adj, S.warp);
-            // totals + carried state, broadcast from the last thread
-            int64_t chunk_sum, chunk_max;
-            {
-                int64_t cm = grp_reduce<NT, true>(counted ? end : INT64_MIN, S.warp);
-                chunk_max = cm;
-                if (NT == 32) {
-                    chunk_sum = __shfl_sync(0xffffffffu, tot, 31);
-                } else {
-                    grp_sync<NT>();
-                    if (t == NT - 1) S.warp[NT / 32] = tot;
-                    grp_sync<NT>();
-                    chunk_sum = S.warp[NT / 32];
-                }
-            }
+            // chunk totals: sum of the adjustments, maximum end of the counted variants
+            int64_t adj_excl, chunk_sum;
+            grp_scan_x<NT, false, int64_t>(adj, S.scan, sb1, adj_excl, chunk_sum);
+            int32_t cm_excl, chunk_max;
+            grp_scan_x<NT, true, int32_t>(counted ? end32 : INT32_MIN, S.scan, sb1, cm_excl, chunk_max);
             diff_acc += chunk_sum;
-            d_ref = imax64(d_ref, chunk_max);
-            {
-                int64_t lp = grp_reduce<NT, true>((i < nvar) ? pos : INT64_MIN, S.warp);
-                last_pos = imax64(last_pos, lp);
-            }
-            if (NT == 32) bad = __any_sync(0xffffffffu, bad); else bad = __syncthreads_or(bad);
-            if (bad) {
-                unsorted = true;
-                break;
-            }
+            d_ref = imax64(d_ref, (int64_t)chunk_max);
         }
     }
 
@@ -247,6 +278,7 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT, GVL_PLAN_OCC / (NT == 32 
     }
     int64_t R = hs.ref_idx, O = hs.out_idx, shifted = hs.shifted;
     int64_t n_emit = 0, ref0 = 0;
+    int sb = 0;
     bool done = false;
     int64_t last_pos = INT64_MIN;
     for (int64_t base = 0; base < nvar && !done && !unsorted; base += NT) {
@@ -265,9 +297,11 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT, GVL_PLAN_OCC / (NT == 32 
         }
         bcast_off();  // (first chunk only; the gathers above are already in flight)
         const int64_t end = (i < nvar) ? pos - imin64(il, 0) + 1 : INT64_MIN;
-        grp_sync<NT>();
+        const int nv = (int)imin64(NT, nvar - base);  // entries of this chunk
+        // (every read of S.pos / S.end of the previous chunk is followed by at least one barrier of that chunk)
+        const int32_t end32 = (int32_t)imax64(imin64(end, INT32_MAX), INT32_MIN);
         S.pos[t] = (int32_t)imin64(pos, INT32_MAX);
-        S.end[t] = (int32_t)imax64(imin64(end, INT32_MAX), INT32_MIN);
+        S.end[t] = end32;
         grp_sync<NT>();
         {
             const int64_t prev = (t > 0) ? (int64_t)S.pos[t - 1] : last_pos;
@@ -277,12 +311,15 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT, GVL_PLAN_OCC / (NT == 32 
                 unsorted = true;
                 break;
             }
-            last_pos = imax64(last_pos, grp_reduce<NT, true>((i < nvar) ? pos : INT64_MIN, S.warp));
+            last_pos = S.pos[nv - 1];  // sorted: the chunk's last entry is its maximum
         }
-        // -- A: deletions spanning the window start (:99-102): the last one sets R
+        // -- A: deletions spanning the window start (:99-102): the last one sets R.  Only chunks that begin left of
+        // the window can hold one (sorted list).
         const bool span = kept && pos < q_start && il < 0 && end >= q_start;
-        const int64_t last_span = grp_reduce<NT, true>(span ? (int64_t)t : -1, S.warp);
-        if (last_span >= 0) R = S.end[last_span];
+        if ((int64_t)S.pos[0] < q_start) {
+            const int64_t last_span = grp_reduce<NT, true>(span ? (int64_t)t : -1, S.warp);
+            if (last_span >= 0) R = S.end[last_span];
+        }
         bool elig = kept && pos >= q_start;  // everything else is skipped without side effects
         // -- B: shift phase (:115-146)
         int64_t start = 0, trim_at = -1, trim = 0;
@@ -320,20 +357,12 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT, GVL_PLAN_OCC / (NT == 32 
         }
         elig = elig && t >= start;
         if (TRK) elig = elig && il != 0;  // a SNP "writes nothing" and does not move the cursor (src/tracks/mod.rs:310-314)
-        // -- C: applied set
-        const int64_t mx_incl = grp_scan_incl<NT, true>(elig ? end : INT64_MIN, S.warp);
-        int64_t mx_excl = __shfl_up_sync(0xffffffffu, mx_incl, 1);
-        if (NT != 32) {
-            grp_sync<NT>();
-            if ((t & 31) == 31) S.warp[t >> 5] = mx_incl;
-            grp_sync<NT>();
-            if ((t & 31) == 0) mx_excl = (t > 0) ? S.warp[(t >> 5) - 1] : INT64_MIN;
-        } else if (t == 0) {
-            mx_excl = INT64_MIN;
-        }
-        mx_excl = imax64(mx_excl, R);
+        // -- C: applied set.  Ends are compared as saturated 32-bit values (coordinates are int32 throughout the ABI).
+        int32_t mx_excl32, tot32;
+        grp_scan_x<NT, true, int32_t>(elig ? end32 : INT32_MIN, S.scan, sb, mx_excl32, tot32);
+        const int64_t mx_excl = imax64((int64_t)mx_excl32, R);
         const bool head = elig && pos >= mx_excl;
-        grp_sync<NT>();
+        // (S.elig / S.head / S.applied of the previous chunk were last read before that chunk's later barriers)
         S.elig[t] = elig;
         S.head[t] = head;
         S.applied[t] = head;
@@ -341,7 +370,6 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT, GVL_PLAN_OCC / (NT == 32 
         if (head || t == 0) {
             int64_t cur = head ? end : R;
             int u = head ? t + 1 : 0;
-            const int nv = (int)imin64(NT, nvar - base);  // entries past the list end are idle: do not walk them
             for (; u < nv && !S.head[u]; u++) {
                 if (S.elig[u] && (int64_t)S.pos[u] >= cur) {  // :108-110
                     S.applied[u] = 1;
@@ -352,26 +380,20 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT, GVL_PLAN_OCC / (NT == 32 
         grp_sync<NT>();
         const bool applied = S.applied[t] != 0;
         // -- D: gaps, output positions, validity
-        const int64_t pe_incl = grp_scan_incl<NT, true>(applied ? end : INT64_MIN, S.warp);
-        int64_t pe_excl = __shfl_up_sync(0xffffffffu, pe_incl, 1);
-        if (NT != 32) {
-            grp_sync<NT>();
-            if ((t & 31) == 31) S.warp[t >> 5] = pe_incl;
-            grp_sync<NT>();
-            if ((t & 31) == 0) pe_excl = (t > 0) ? S.warp[(t >> 5) - 1] : INT64_MIN;
-        } else if (t == 0) {
-            pe_excl = INT64_MIN;
-        }
-        const int64_t prev_end = imax64(pe_excl, R);
+        int32_t pe_excl32;
+        grp_scan_x<NT, true, int32_t>(applied ? end32 : INT32_MIN, S.scan, sb, pe_excl32, tot32);
+        const int64_t prev_end = imax64((int64_t)pe_excl32, R);
         const int64_t my_trim = (t == trim_at) ? trim : 0;
         const int64_t ref_len = applied ? pos - prev_end : 0;
         const int64_t alen_eff = applied ? alen - my_trim : 0;
-        const int64_t c_incl = grp_scan_incl<NT, false>(ref_len + alen_eff, S.warp);
+        // one scan for the output positions and the rank among applied variants: lengths << 10 | applied (<= 512 per chunk)
+        int64_t pk_excl, pk_tot;
+        const int64_t pk_incl = grp_scan_x<NT, false, int64_t>(((ref_len + alen_eff) << 10) | (applied ? 1 : 0), S.scan, sb, pk_excl, pk_tot);
+        const int64_t c_incl = pk_incl >> 10;
         const int64_t a = O + (c_incl - (ref_len + alen_eff)) + ref_len;  // ALT start in the output
-        const bool valid = applied && a < length;                         // :154-158
-        const bool broke = applied && !valid;
+        const bool valid = applied && a < length;                         // :154-158 (a prefix of the applied variants)
         const int64_t n = valid ? imin64(alen_eff, length - a) : 0;     // :178
-        const int64_t rank_incl = grp_scan_incl<NT, false>(valid ? 1 : 0, S.warp);
+        const int64_t rank_incl = pk_incl & 1023;                        // (= rank among VALID ones for a valid variant)
         if (valid && !overflow) {
             const int64_t w = rec_off + n_emit + rank_incl - 1;
             if (TRK) {
@@ -388,22 +410,19 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT, GVL_PLAN_OCC / (NT == 32 
                 P.rec.vpos[w] = (int32_t)pos;
             }
         }
-        // carried state: last valid record of the chunk
-        const int64_t last_valid = grp_reduce<NT, true>(valid ? (int64_t)t : -1, S.warp);
-        const bool any_broke = (NT == 32) ? __any_sync(0xffffffffu, broke) : (__syncthreads_or(broke) != 0);
-        if (last_valid >= 0) {
-            grp_sync<NT>();
-            if (t == last_valid) {
-                S.warp[0] = a + n;
-                S.warp[1] = end;
-                S.warp[2] = rank_incl;
+        // carried state: the chunk's last valid record
+        const int n_valid = grp_count<NT>(valid);
+        const bool any_broke = (int64_t)n_valid < (pk_tot & 1023);
+        if (n_valid > 0) {
+            if (valid && rank_incl == n_valid) {
+                S.st[0] = a + n;
+                S.st[1] = end;
             }
             grp_sync<NT>();
             if (n_emit == 0) ref0 = R;  // the first applied variant's gap starts at R (after the shift)
-            O = S.warp[0];
-            R = S.warp[1];
-            n_emit += S.warp[2];
-            grp_sync<NT>();
+            O = S.st[0];
+            R = S.st[1];
+            n_emit += n_valid;
         }
         if (any_broke || O >= length) done = true;  // :154-158, :195-197
     }

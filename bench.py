@@ -357,11 +357,11 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize()
         e0.record(main)
-        pl.s_plan.wait_event(e0)
-        pl.s_exec.wait_event(e0)
+        pl.wait_all(e0)
         for i in range(n_sub):
             submit_resident(pl, i % pl.n_halves)
-        main.wait_event(pl.halves[(n_sub - 1) % pl.n_halves].done)  # (the execute stream runs the calls in order)
+        for h in range(min(n_sub, pl.n_halves)):  # every half that ran (their streams are independent)
+            main.wait_event(pl.halves[h].done)
         e1.record(main)
         torch.cuda.synchronize()
         return e0.elapsed_time(e1)  # ms

@@ -21,6 +21,7 @@ double-buffered mode: valid until the ring is refilled); `copy=True` hands out c
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -179,6 +180,7 @@ class FixedPipeline:
         self.view = self.eng.dataset_view(ds.full_regions, len(ds.sample_names), ds.ploidy, ds.rc_neg)
         self.ref_slot = self.eng.empty_slot if (sp.is_ref or not sp.want_seqs) else -1
         self.ring, self.n_halves, self.use_graph = int(ring), int(halves), bool(graph)
+        self.fused = os.environ.get("GVL_PIPE_SPLIT", "0") != "1"
         b, dev = self.b, self.dev
         with torch.cuda.device(dev):
             # eager path (Dataset.__getitem__): one scratch set, one pinned index buffer
@@ -291,13 +293,30 @@ class FixedPipeline:
             torch.cuda.synchronize(dev)
             for H in self.halves:
                 H.eng.check()
+            # Fused mode (default): ONE graph per half -- prep -> plan -> execute -- replayed on the half's own stream, so a
+            # device call is one graph launch and the plan of the next call (other half, other stream) still overlaps this
+            # call's execute.  Split mode (GVL_PIPE_SPLIT=1, the first round-2 design): stage P on a plan stream and stage E
+            # on an execute stream, two graphs and one cross-stream event per call.
+            for i, H in enumerate(self.halves):
+                H.stream = (self.s_plan, self.s_exec)[i % 2] if self.fused else None
             if self.use_graph:
                 for H in self.halves:
+                    if self.fused:
+                        H.g_plan = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(H.g_plan, stream=H.stream):
+                            self._stage_plan(H.eng, H.scr, H.idx, jit(H), n, sub_batch=b)
+                            self._stage_exec(H.eng, H.scr, H.out, n, sub_batch=b)
+                        continue
                     H.g_plan, H.g_exec = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
                     with torch.cuda.graph(H.g_plan, stream=self.s_plan):
                         self._stage_plan(H.eng, H.scr, H.idx, jit(H), n, sub_batch=b)
                     with torch.cuda.graph(H.g_exec, stream=self.s_exec):
                         self._stage_exec(H.eng, H.scr, H.out, n, sub_batch=b)
+
+    def wait_all(self, event):
+        """Every stream of the pipeline waits for `event` (bench: one start event for a timed block)."""
+        self.s_plan.wait_event(event)
+        self.s_exec.wait_event(event)
 
     def submit(self, h: int, ds_idx=None, jitter=None):
         """Produce half `h`.  `ds_idx`: int64 (ring * b) indices -- a numpy array (staged through pinned memory, one H2D
@@ -306,21 +325,34 @@ class FixedPipeline:
         H = self.halves[h]
         n = self.ring * self.b
         sp = self.spec
+        s_in = H.stream if self.fused else self.s_plan  # the stream the indices arrive on and the plan runs on
         with torch.cuda.device(self.dev):
-            self.s_plan.wait_event(H.done)  # this half's previous execute has finished with the plan workspace / scratch
+            if not self.fused:
+                self.s_plan.wait_event(H.done)  # this half's previous execute has finished with the plan workspace / scratch
             if isinstance(ds_idx, np.ndarray):
                 H.uploaded.synchronize()  # the previous copy out of the pinned buffer has finished
                 H.pin.array[:n] = ds_idx
                 if jitter is not None:
                     H.pin_jit[:n] = jitter
                 check(lib.gvl_dev_upload(self.eng.ctx.handle, ptr(H.idx), c_vp(H.pin.ptr), c_i64(H.pin.nbytes),
-                                         c_vp(self.s_plan.cuda_stream)))
-                H.uploaded.record(self.s_plan)
+                                         c_vp(s_in.cuda_stream)))
+                H.uploaded.record(s_in)
             elif ds_idx is not None:
-                with torch.cuda.stream(self.s_plan):
+                with torch.cuda.stream(s_in):
                     H.idx[:n].copy_(ds_idx, non_blocking=True)
                     if jitter is not None:
                         H.jit[:n].copy_(jitter, non_blocking=True)
+            if self.fused:
+                if H.free is not None:
+                    s_in.wait_event(H.free)  # the consumer has let go of this half's output buffers
+                with torch.cuda.stream(s_in):
+                    if H.g_plan is not None:
+                        H.g_plan.replay()
+                    else:
+                        self._stage_plan(H.eng, H.scr, H.idx, H.jit if sp.jitter else None, n, sub_batch=self.b)
+                        self._stage_exec(H.eng, H.scr, H.out, n, sub_batch=self.b)
+                H.done.record(s_in)
+                return
             with torch.cuda.stream(self.s_plan):
                 if H.g_plan is not None:
                     H.g_plan.replay()

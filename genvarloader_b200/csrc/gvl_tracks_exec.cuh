@@ -361,19 +361,22 @@ __global__ void __launch_bounds__(128) trk_tile_prep_kernel(TrkExecParams P, Til
 template <bool RC>
 __device__ __forceinline__ void t3_write_chunks(const T3Smem &S, float *__restrict__ out_row, int32_t j0, int32_t n_chunks,
                                                 int32_t jo_lo, int32_t jo_hi, int32_t L, int32_t cur) {
+    // Every thread owns 16 consecutive output values (64 bytes: two 256-bit stores; lanes 64 bytes apart still run at
+    // the full store rate on B200, 128 bytes per lane do not -- profiles/microbench/fill.py), so the search for the
+    // value in effect before the chunk is paid once per 16 values and the walk carries it in a register.
     const uint32_t *mk = S.mk, *mk2 = S.mk2;
     const int tid = threadIdx.x;
-    int32_t j = j0 + 8 * tid;                          // first output position of the thread's chunk
-    int32_t u_lo = (RC ? (L - 8 - j) : j) - cur;       // its lowest tile-relative haplotype position
+    int32_t j = j0 + 16 * tid;                          // first output position of the thread's chunk
+    int32_t u_lo = (RC ? (L - 16 - j) : j) - cur;       // its lowest tile-relative haplotype position
     float *dst = out_row + j;
-    for (int32_t c = tid; c < n_chunks; c += T2_THREADS, j += 8 * T2_THREADS, u_lo += RC ? -8 * T2_THREADS : 8 * T2_THREADS,
-                 dst += 8 * T2_THREADS) {
+    for (int32_t c = tid; c < n_chunks; c += T2_THREADS, j += 16 * T2_THREADS, u_lo += RC ? -16 * T2_THREADS : 16 * T2_THREADS,
+                 dst += 16 * T2_THREADS) {
         uint32_t bits;
         if (u_lo >= 0) {
             const int w = u_lo >> 5;
-            bits = __funnelshift_r(mk[w], mk[w + 1], u_lo & 31) & 0xffu;
+            bits = __funnelshift_r(mk[w], mk[w + 1], u_lo & 31) & 0xffffu;
         } else {
-            bits = (mk[0] << (-u_lo)) & 0xffu;
+            bits = (mk[0] << (-u_lo)) & 0xffffu;
         }
         float cv = 0.0f;
         const int q = max(u_lo, 0) - 1;  // last position before the chunk (position 0 always holds a marker)
@@ -389,19 +392,24 @@ __device__ __forceinline__ void t3_write_chunks(const T3Smem &S, float *__restri
             }
             cv = S.val[32 * w + 31 - __clz(mm)];
         }
-        float x[8];  // in OUTPUT order: haplotype position u_lo + t is output RC ? 7 - t : t
+        const bool whole = j >= jo_lo && j + 16 <= jo_hi;
 #pragma unroll
-        for (int t = 0; t < 8; t++) {
-            if ((bits >> t) & 1u) cv = S.val[u_lo + t];
-            x[RC ? 7 - t : t] = cv;
-        }
-        if (j >= jo_lo && j + 8 <= jo_hi) {
-            stg_f8(dst, x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
-        } else {  // chunk cut by the tile / row ends
+        for (int h = 0; h < 2; h++) {  // two halves of 8 in HAPLOTYPE order; the reversed row stores them back to front
+            float x[8];                // in OUTPUT order: haplotype position u_lo + 8h + t is output RC ? 7 - t : t of its half
 #pragma unroll
             for (int t = 0; t < 8; t++) {
-                const int32_t jj = j + t;
-                if (jj >= jo_lo && jj < jo_hi) dst[t] = x[t];
+                if ((bits >> (8 * h + t)) & 1u) cv = S.val[u_lo + 8 * h + t];
+                x[RC ? 7 - t : t] = cv;
+            }
+            const int off = RC ? 8 * (1 - h) : 8 * h;
+            if (whole) {
+                stg_f8(dst + off, x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
+            } else {  // chunk cut by the tile / row ends
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
+                    const int32_t jj = j + off + t;
+                    if (jj >= jo_lo && jj < jo_hi) dst[off + t] = x[t];
+                }
             }
         }
     }
@@ -560,11 +568,11 @@ __device__ __forceinline__ void t3_tile(const TileCtx &X, const TileDesc &D, T3S
             __syncthreads();
         }
 
-        // ---- output: chunks of 8 values on 32-byte aligned addresses ----
+        // ---- output: chunks of 16 values on 64-byte aligned addresses ----
         const int32_t jo_lo = rc ? L - pass_end : cur;
         const int32_t jo_hi = rc ? L - cur : pass_end;
-        const int32_t j0 = (int32_t)(((base_elems + jo_lo) & ~(int64_t)7) - base_elems);  // may be < jo_lo
-        const int32_t n_chunks = (jo_hi - j0 + 7) >> 3;
+        const int32_t j0 = (int32_t)(((base_elems + jo_lo) & ~(int64_t)15) - base_elems);  // may be < jo_lo
+        const int32_t n_chunks = (jo_hi - j0 + 15) >> 4;
         // (the two directions are separate instantiations: the walk then writes its registers in output order)
         if (rc) t3_write_chunks<true>(S, out_row, j0, n_chunks, jo_lo, jo_hi, L, cur);
         else t3_write_chunks<false>(S, out_row, j0, n_chunks, jo_lo, jo_hi, L, cur);
@@ -636,10 +644,12 @@ __global__ void __launch_bounds__(T2_THREADS, GVL_T3_MINB) trk_exec3_kernel(TrkE
     TileCtx X;
     {
         const int64_t query = D.query;
-        const int64_t sub = P.sub_batch;
+        // (queries and logical batch sizes are < 2^31: 32-bit division, the 64-bit one was 8 % of the kernel's instructions)
+        const uint32_t sub = P.sub_batch > 0 ? (uint32_t)P.sub_batch : 0u;
+        const uint32_t q_blk = sub ? (uint32_t)D.query / sub : 0u;
         X.hap = (uint64_t)(D.row - D.query * (int32_t)P.ploidy);
-        X.qseed = P.query_seed ? (uint64_t)P.query_seed[query] : (uint64_t)(sub > 0 ? query % sub : query);
-        X.base_seed = P.base_seed_dev ? P.base_seed_dev[sub > 0 ? query / sub : 0] : P.base_seed;
+        X.qseed = P.query_seed ? (uint64_t)P.query_seed[query] : (uint64_t)(sub ? (uint32_t)D.query - q_blk * sub : (uint32_t)D.query);
+        X.base_seed = P.base_seed_dev ? P.base_seed_dev[q_blk] : P.base_seed;
         X.recs = P.trecs + D.rec_base;
         X.out_row = P.out + D.out_base;
         X.base_elems = (int64_t)(reinterpret_cast<uintptr_t>(P.out) >> 2) + D.out_base;

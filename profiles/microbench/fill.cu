@@ -28,7 +28,26 @@ __global__ void fill_tiled_kernel(uint8_t *out, int64_t tile_bytes, uint32_t v) 
     }
 }
 
+// lane-blocked stores: every lane owns `LB` contiguous bytes (LB / 32 256-bit stores), lanes LB bytes apart -- what a
+// kernel does whose threads walk consecutive output values with a carried state (track execute, round 2)
+template <int LB>
+__global__ void fill_blocked_kernel(uint8_t *out, int64_t tile_bytes, uint32_t v) {
+    uint8_t *base = out + (int64_t)blockIdx.x * tile_bytes;
+    for (int64_t o = (int64_t)threadIdx.x * LB; o + LB <= tile_bytes; o += (int64_t)blockDim.x * LB) {
+#pragma unroll
+        for (int k = 0; k < LB / 32; k++)
+            asm volatile("st.global.v8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"l"(base + o + 32 * k), "r"(v) : "memory");
+    }
+}
+
 extern "C" {
+int fill_blocked_launch(void *out, int64_t n_bytes, int64_t tile_bytes, int lane_bytes, int block, void *stream) {
+    const int grid = (int)(n_bytes / tile_bytes);
+    if (lane_bytes == 64) fill_blocked_kernel<64><<<grid, block, 0, (cudaStream_t)stream>>>((uint8_t *)out, tile_bytes, 0x01000000u);
+    else if (lane_bytes == 128) fill_blocked_kernel<128><<<grid, block, 0, (cudaStream_t)stream>>>((uint8_t *)out, tile_bytes, 0x01000000u);
+    else fill_blocked_kernel<256><<<grid, block, 0, (cudaStream_t)stream>>>((uint8_t *)out, tile_bytes, 0x01000000u);
+    return (int)cudaGetLastError();
+}
 int fill_launch(void *out, int64_t n_bytes, int width, int grid, int block, void *stream) {
     if (width == 16) fill_kernel<16><<<grid, block, 0, (cudaStream_t)stream>>>((uint8_t *)out, n_bytes, 0x01000000u);
     else fill_kernel<32><<<grid, block, 0, (cudaStream_t)stream>>>((uint8_t *)out, n_bytes, 0x01000000u);

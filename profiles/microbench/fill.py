@@ -46,6 +46,17 @@ for width in (16, 32):
         t = timeit(f, n=200, warm=20)
         print(f"tiled fill 33.5 MB x ring 8  st.{width * 8:3d}  tile {tile:6d} B x {block:3d} thr ({ring[0].numel() // tile} CTAs): "
               f"{t * 1e6:.2f} us/launch, {ring[0].numel() / t / 1e9:.0f} GB/s")
+# lane-blocked stores (every lane writes 64 / 128 / 256 contiguous bytes): 2.68 GB like a 20-batch track ring
+bigf = torch.empty(5 * (1 << 29), dtype=torch.uint8, device=dev)
+for lb in (64, 128, 256):
+    for tile, block in ((32768, 256), (32768, 128), (65536, 256)):
+        t = timeit(lambda: lib.fill_blocked_launch(C.c_void_p(bigf.data_ptr()), C.c_int64(bigf.numel()), C.c_int64(tile), lb, block,
+                                                   C.c_void_p(st)), n=10, warm=3)
+        print(f"lane-blocked fill 2.68 GB  {lb:3d} B per lane  tile {tile} B x {block} thr: {bigf.numel() / t / 1e9:.0f} GB/s")
+for tile, block in ((32768, 256), (32768, 128)):
+    t = timeit(lambda: lib.fill_tiled_launch(C.c_void_p(bigf.data_ptr()), C.c_int64(bigf.numel()), C.c_int64(tile), 32, block,
+                                             C.c_void_p(st)), n=10, warm=3)
+    print(f"coalesced tiled fill 2.68 GB  st.256  tile {tile} B x {block} thr: {bigf.numel() / t / 1e9:.0f} GB/s")
 i = [0]
 
 

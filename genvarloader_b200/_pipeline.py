@@ -179,7 +179,8 @@ class FixedPipeline:
         self.spec = sp = _Spec(ds)
         self.view = self.eng.dataset_view(ds.full_regions, len(ds.sample_names), ds.ploidy, ds.rc_neg)
         self.ref_slot = self.eng.empty_slot if (sp.is_ref or not sp.want_seqs) else -1
-        self.ring, self.n_halves, self.use_graph = int(ring), int(halves), bool(graph)
+        self.ring, self.n_halves = int(ring), int(halves)
+        self.use_graph = bool(graph) and os.environ.get("GVL_PIPE_GRAPH", "1") != "0"  # (0: eager launches, for tool runs)
         self.fused = os.environ.get("GVL_PIPE_SPLIT", "0") != "1"
         b, dev = self.b, self.dev
         with torch.cuda.device(dev):

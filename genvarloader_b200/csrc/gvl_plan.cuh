@@ -3,12 +3,11 @@
 // The reference walks each haplotype's variant list with a sequential state machine
 // (src/reconstruct/mod.rs:39-256 for bytes, src/tracks/mod.rs:224-406 for tracks,
 // src/genotypes/mod.rs:15-125 for the length diff).  Here the same state machines are
-// expressed as `init / step / finish` functions over plain integers so that
-//   * the device "plan" kernels can drive them (lock-step across a warp, one variant per
-//     step, operands broadcast with shuffles), emitting a compact segment table instead
-//     of copying bytes, and
-//   * a host build (tests/test_plan_host.py via gvl_plan_host.cpp) can replay them on the
-//     CPU without a GPU.
+// expressed as `init / step / finish` functions over plain integers so that the serial device
+// plan routines (rows with unsorted lists, GVL_PLAN=s) can drive them in lock-step across a warp,
+// one variant per step with operands broadcast by shuffles, emitting a compact segment table
+// instead of copying bytes.  (The scan-based kernel of gvl_plan_par.cuh restates the same rules
+// as block-wide scans.)
 // The execute kernels never see variants -- only the records emitted here.
 #pragma once
 #include <stdint.h>

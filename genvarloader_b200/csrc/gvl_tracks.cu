@@ -220,6 +220,14 @@ static int realign_impl(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_sv
     if (n_work == 0 || n_tracks == 0 || total_per_track == 0) return GVL_OK;
     if (!plan_only && (!out || ((uintptr_t)out & 15))) return fail(GVL_ERR_ARG, "gvl_dev_realign_tracks: out must be 16-byte aligned");
     if (plan_only) out = nullptr;
+    // every argument is checked before the first launch: a rejected call leaves no half-planned state behind
+    if (n_tracks < 0 || n_tracks > MAX_TRACKS) return fail(GVL_ERR_ARG, "at most %d tracks per call", MAX_TRACKS);
+    for (int64_t t = 0; t < n_tracks; t++) {
+        if (strategy_ids[t] < 0 || strategy_ids[t] > GVL_FILL_INTERPOLATE)
+            return fail(GVL_ERR_ARG, "unknown insertion-fill strategy %d", strategy_ids[t]);
+        if (strategy_ids[t] == GVL_FILL_INTERPOLATE && !(params[t] >= 1 && params[t] <= 3))
+            return fail(GVL_ERR_ARG, "Interpolate order must be 1, 2 or 3");
+    }
     int rc;
     if ((rc = ensure_rows(ctx, ctx->trk, n_work))) return rc;
     if ((rc = ensure_trecs(ctx, ctx->trk, max_records + n_work))) return rc;
@@ -234,7 +242,6 @@ static int realign_impl(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_sv
                                   keep_offsets, to_rc, track_lengths, out_offsets, max_records, words, st)))
         return rc;
     TrkDesc desc[MAX_TRACKS];
-    if (n_tracks > MAX_TRACKS) return fail(GVL_ERR_ARG, "at most %d tracks per call", MAX_TRACKS);
     for (int64_t t = 0; t < n_tracks; t++) {
         desc[t].itv_starts = itv ? itv[t].itv_starts : nullptr;
         desc[t].itv_ends = itv ? itv[t].itv_ends : nullptr;
@@ -244,10 +251,6 @@ static int realign_impl(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_sv
         desc[t].dense_offsets = dense_offsets;
         desc[t].strategy = strategy_ids[t];
         desc[t].param = params[t];
-        if (strategy_ids[t] < 0 || strategy_ids[t] > GVL_FILL_INTERPOLATE)
-            return fail(GVL_ERR_ARG, "unknown insertion-fill strategy %d", strategy_ids[t]);
-        if (strategy_ids[t] == GVL_FILL_INTERPOLATE && !(params[t] >= 1 && params[t] <= 3))
-            return fail(GVL_ERR_ARG, "Interpolate order must be 1, 2 or 3");
     }
     return launch_trk_exec(ctx, n_work, ploidy, batch, n_tracks, desc, offset_idxs, total_per_track, query_seed,
                            base_seed, out, layout_btp, st, base_seed_dev, sub_batch);

@@ -20,3 +20,21 @@ def cuda_device():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+@pytest.fixture(autouse=True)
+def _drain_device_between_tests():
+    """GVL_TEST_SYNC=1 (tool runs): drain the device and collect garbage after every test, so that an asynchronous error is
+    reported by the test that caused it and no object dies with device work in flight."""
+    yield
+    import os
+
+    if os.environ.get("GVL_TEST_SYNC") == "1":
+        import gc
+
+        import torch
+
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+            gc.collect()
+            torch.cuda.synchronize()

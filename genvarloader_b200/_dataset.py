@@ -353,6 +353,9 @@ class Dataset:
         """Reference: `Dataset.subset_to`, _impl.py:1153-1221 (integer / slice / boolean / sample-name selectors)."""
         kw = {}
         if regions is not None:
+            if self.splice_rows is not None:
+                raise ValueError("subset_to(regions=...) on a spliced dataset would mix splice rows with regions: subset first, "
+                                 "then with_settings(splice_info=...)")
             kw["region_subset"] = self._r_idx[_idx_to_array(regions, self.n_regions)]
         if samples is not None:
             if isinstance(samples, str) or (np.ndim(samples) > 0 and len(samples) and isinstance(samples[0], str)):
@@ -426,7 +429,9 @@ class Dataset:
         (indices address regions like `ds[r, s]` does)."""
         r_map = self._r_idx
         names = None
-        if isinstance(splice_info, (str, tuple)) and all(isinstance(x, str) for x in np.atleast_1d(splice_info)):
+        by_column = isinstance(splice_info, str) or (isinstance(splice_info, tuple) and len(splice_info) == 2
+                                                     and all(isinstance(x, str) for x in splice_info))
+        if by_column:
             cols = self.bed_columns or {}
             id_col, order_col = (splice_info, None) if isinstance(splice_info, str) else splice_info
             for c in (id_col, order_col):
@@ -439,7 +444,21 @@ class Dataset:
             if order_col is not None:
                 order = np.asarray(cols[order_col])
                 groups = {k: sorted(v, key=lambda i: order[i]) for k, v in groups.items()}
-            names, lists = list(groups), list(groups.values())
+            # BED columns are in INPUT order: rows map to storage through region_map (not through a subset); with a region
+            # subset active, elements outside it drop out and rows left empty disappear
+            full_map = self.region_map if self.region_map is not None else np.arange(len(self.full_regions), dtype=np.int64)
+            allowed = None if self.region_subset is None else set(np.asarray(self.region_subset).tolist())
+            names, rows = [], []
+            for k, v in groups.items():
+                st = [int(full_map[i]) for i in v]
+                if allowed is not None:
+                    st = [x for x in st if x in allowed]
+                if st:
+                    names.append(k)
+                    rows.append(np.asarray(st, np.int64))
+            if not rows:
+                raise ValueError("no splice row is left after subsetting")
+            return tuple(rows), tuple(names)
         elif isinstance(splice_info, dict):
             names, lists = list(splice_info), list(splice_info.values())
         else:
@@ -518,6 +537,8 @@ class Dataset:
             out = Ragged(eng.execute("haplotypes"), group_offsets, shape)
         else:
             raise ValueError("channels-first one-hot needs a fixed output length; spliced output is ragged")
+        if self.output_length == "variable" and self.output_format != "flat":  # pad like the unspliced path (_query.py:94-127)
+            out = self._shape_output(out, None, False)
         if is_int(r_sel) and is_int(s_sel):
             out = out.squeeze(0).squeeze(0) if hasattr(out, "squeeze") else out
         return out

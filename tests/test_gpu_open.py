@@ -84,6 +84,20 @@ def test_spliced_haplotypes_are_concatenated_elements(cuda_device, tmp_path):
     assert pair.shape == (2, d.ploidy, None)
     ann = sp.with_seqs("annotated")[0, 0]
     assert (ann.haps.data.cpu().numpy() == sp[0, 0].data.cpu().numpy()).all()
+    # edge cases: a tuple of ragged index lists is a mapping (not column names); "variable" pads like the unspliced path;
+    # region subsets do not mix with splice rows
+    sp_t = mem.with_settings(splice_info=([3, 0, 7], [5]))
+    assert sp_t.n_regions == 2 and (sp_t[0, 1].data.cpu().numpy() == sp[0, 1].data.cpu().numpy()).all()
+    var = sp.with_len("variable")[:, :]
+    rag = sp[:, :]
+    lens = (rag.offsets[1:] - rag.offsets[:-1]).cpu().numpy()
+    assert var.shape == (3, mem.n_samples, d.ploidy, int(lens.max()))
+    flat = var.reshape(-1, var.shape[-1]).cpu().numpy()
+    ro = rag.offsets.cpu().numpy()
+    for k in (0, 4, len(lens) - 1):
+        assert (flat[k, : lens[k]] == rag.data[ro[k]: ro[k + 1]].cpu().numpy()).all() and (flat[k, lens[k]:] == ord("N")).all()
+    with pytest.raises(ValueError, match="spliced"):
+        sp.subset_to(regions=[0, 1])
     # the same rows from BED columns of an opened dataset: (id column, order column)
     order = np.arange(d.n_regions)
     write_gvl_dataset(tmp_path / "ds", d, ["chr1"], ["a", "b", "c"], order)
@@ -106,6 +120,14 @@ def test_spliced_haplotypes_are_concatenated_elements(cuda_device, tmp_path):
     assert set(names) == {"tA", "tB", "tC", "x"}
     got = spd[names.index("tC"), 1]
     assert (got.data.cpu().numpy() == sp[2, 1].data.cpu().numpy()).all() and (got.offsets.cpu().numpy() == sp[2, 1].offsets.cpu().numpy()).all()
+    # BED-column splice rows of a region SUBSET: elements outside the subset drop out, rows left empty disappear
+    sub = dsk.subset_to(regions=[11, 10, 3, 0, 7]).with_settings(splice_info=("transcript", "exon"))
+    sn = list(sub.splice_names)
+    assert set(sn) == {"tA", "tC"}
+    g = sub[sn.index("tA"), 2]
+    assert (g.data.cpu().numpy() == sp[0, 2].data.cpu().numpy()).all()
+    g = sub[sn.index("tC"), 0]   # elements 11, 10 of [11, 10, 9, 8] are left, in exon order
+    assert (g.data.cpu().numpy() == mem.with_settings(splice_info=[[11, 10]])[0, 0].data.cpu().numpy()).all()
 
 
 def test_open_svar_linked_dataset(cuda_device, tmp_path):

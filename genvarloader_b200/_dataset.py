@@ -585,6 +585,8 @@ class Dataset:
             # fixed-length fast path: the O(batch) prep runs on the device (gvl_dev_batch_prep), one small H2D copy per call
             jit = self.rng.integers(-self.jitter, self.jitter + 1, size=len(ds_idx), dtype=np.int32) if self.jitter else None
             out = pipe.run_eager(ds_idx, jit)
+            if out_reshape is None and not squeeze and type(out) is torch.Tensor:
+                return out  # (paired array indices, sequences only: nothing to reshape)
             out = out if isinstance(out, tuple) else (out,)
             out = tuple(self._shape_output(o, out_reshape, squeeze) for o in out)
             return out[0] if len(out) == 1 else out

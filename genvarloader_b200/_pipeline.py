@@ -192,6 +192,10 @@ class FixedPipeline:
             self._idx0 = torch.zeros(b + (b + 1) // 2, dtype=torch.int64, device=dev)
             self._jit0 = self._idx0[b:].view(torch.int32)
             self._ctx_handle, self._job0_adr = self.eng.ctx.handle, C.addressof(self._scr0.job)
+            self._simple_shape = None
+            if sp.want_seqs and not sp.annotated and not sp.t:
+                lead = () if sp.is_ref else (sp.p,)
+                self._simple_shape = {"onehot": (*lead, sp.L, 4), "onehot_cf": (*lead, 4, sp.L)}.get(sp.mode, (*lead, sp.L))
             self._idx0_ptr, self._jit0_ptr = self._idx0.data_ptr(), self._jit0.data_ptr()
         self.halves = []
         if self.ring > 0:
@@ -249,6 +253,15 @@ class FixedPipeline:
             prev = torch.cuda.current_device()
             torch.cuda.set_device(dev)
         try:
+            shp = self._simple_shape
+            if shp is not None:  # sequences only (bytes / one-hot): allocate the result in its final shape, no wrapper objects
+                seq = torch.empty((n, *shp), dtype=torch.uint8, device=dev)
+                rc = lib.gvl_dev_fixed_run(self._ctx_handle, self._job0_adr, ds_idx.__array_interface__["data"][0],
+                                           jitter.__array_interface__["data"][0] if jitter is not None else None, n,
+                                           self._idx0_ptr, self._jit0_ptr, seq.data_ptr(), None, None, None, _raw_stream(dev.index))
+                if rc:
+                    check(rc)
+                return seq
             out = _Out(self.spec, n, dev)
             seq, av, ap, trk = out.seq, out.av, out.ap, out.trk
             rc = lib.gvl_dev_fixed_run(self._ctx_handle, self._job0_adr, ds_idx.ctypes.data,
@@ -340,9 +353,12 @@ class FixedPipeline:
                 H.uploaded.record(s_in)
             elif ds_idx is not None:
                 with torch.cuda.stream(s_in):
-                    H.idx[:n].copy_(ds_idx, non_blocking=True)
-                    if jitter is not None:
-                        H.jit[:n].copy_(jitter, non_blocking=True)
+                    if ds_idx.numel() == H.idx.numel():  # already in the staging layout [ds_idx][jitter]: one copy
+                        H.idx.copy_(ds_idx, non_blocking=True)
+                    else:
+                        H.idx[:n].copy_(ds_idx, non_blocking=True)
+                        if jitter is not None:
+                            H.jit[:n].copy_(jitter, non_blocking=True)
             if self.fused:
                 if H.free is not None:
                     s_in.wait_event(H.free)  # the consumer has let go of this half's output buffers

@@ -313,19 +313,46 @@ class FixedPipeline:
             # on an execute stream, two graphs and one cross-stream event per call.
             for i, H in enumerate(self.halves):
                 H.stream = (self.s_plan, self.s_exec)[i % 2] if self.fused else None
+                H.side = torch.cuda.Stream(dev, priority=-1) if self.fused else None  # (its small kernels go first when SM slots free up)
             if self.use_graph:
                 for H in self.halves:
                     if self.fused:
                         H.g_plan = torch.cuda.CUDAGraph()
                         with torch.cuda.graph(H.g_plan, stream=H.stream):
-                            self._stage_plan(H.eng, H.scr, H.idx, jit(H), n, sub_batch=b)
-                            self._stage_exec(H.eng, H.scr, H.out, n, sub_batch=b)
+                            self._stages_fused(H, jit(H), n, b)
                         continue
                     H.g_plan, H.g_exec = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
                     with torch.cuda.graph(H.g_plan, stream=self.s_plan):
                         self._stage_plan(H.eng, H.scr, H.idx, jit(H), n, sub_batch=b)
                     with torch.cuda.graph(H.g_exec, stream=self.s_exec):
                         self._stage_exec(H.eng, H.scr, H.out, n, sub_batch=b)
+
+    def _stages_fused(self, H, jit_dev, n: int, b: int):
+        """One device call of half H on the current stream (= H.stream).  With realigned tracks the call forks: the track
+        plan (variant walk, tile scan, per-tile searches: ~120 us of small latency-bound kernels for a 20-batch ring) runs
+        on a side stream next to the bandwidth-bound haplotype execute, and joins before the track execute.  Inside a
+        capture the fork / join become graph edges."""
+        sp = self.spec
+        if not (sp.realign and sp.want_seqs):
+            self._stage_plan(H.eng, H.scr, H.idx, jit_dev, n, sub_batch=b)
+            self._stage_exec(H.eng, H.scr, H.out, n, sub_batch=b)
+            return
+        h, job = H.eng.ctx.handle, C.addressof(H.scr.job)
+        idx, jit = H.idx.data_ptr(), (jit_dev.data_ptr() if jit_dev is not None else None)
+        o = H.out
+        dp = lambda x: x.data_ptr() if x is not None else None
+        args = (idx, jit, n, b, dp(o.seq), dp(o.av), dp(o.ap), dp(o.trk))
+        main = torch.cuda.current_stream(self.dev)
+        check(lib.gvl_dev_fixed_stage(h, job, 1, *args, _stream()))  # batch prep + haplotype plan
+        fork, join = torch.cuda.Event(), torch.cuda.Event()
+        fork.record(main)
+        H.side.wait_event(fork)
+        with torch.cuda.stream(H.side):
+            check(lib.gvl_dev_fixed_stage(h, job, 2, *args, _stream()))  # track plan
+            join.record(H.side)
+        check(lib.gvl_dev_fixed_stage(h, job, 3, *args, _stream()))  # haplotype execute
+        main.wait_event(join)
+        check(lib.gvl_dev_fixed_stage(h, job, 4, *args, _stream()))  # track execute
 
     def wait_all(self, event):
         """Every stream of the pipeline waits for `event` (bench: one start event for a timed block)."""
@@ -366,8 +393,7 @@ class FixedPipeline:
                     if H.g_plan is not None:
                         H.g_plan.replay()
                     else:
-                        self._stage_plan(H.eng, H.scr, H.idx, H.jit if sp.jitter else None, n, sub_batch=self.b)
-                        self._stage_exec(H.eng, H.scr, H.out, n, sub_batch=self.b)
+                        self._stages_fused(H, H.jit if sp.jitter else None, n, self.b)
                 H.done.record(s_in)
                 return
             with torch.cuda.stream(self.s_plan):
@@ -418,6 +444,7 @@ class PipelinedLoader:
             ring = max(1, min((256 << 20) // max(per_batch, 1), 64))
         ring = max(1, min(int(ring), -(-n_batches // 2)))
         self.pipe = FixedPipeline(ds, self.batch_size, ring=ring)
+        self._views = {}
 
     def __len__(self) -> int:
         n = len(self.sampler) if self.sampler is not None else len(self.ds)
@@ -456,6 +483,18 @@ class PipelinedLoader:
             h = ring_i % pipe.n_halves
             out = pipe.acquire(h)
             chunk = chunks.pop(ring_i)
+            if plain and not self.copy and len(chunk) == K * b:
+                # zero-copy views of a full ring are the same tensors every time the half comes around: built once
+                views = self._views.get(h)
+                if views is None:
+                    views = self._views[h] = [out.result(lo, b) for lo in range(0, K * b, b)]
+                yield from views
+                pipe.release(h)
+                nxt = ring_i + pipe.n_halves
+                if nxt < n_rings:
+                    flat, j, chunks[nxt] = fill(nxt)
+                    pipe.submit(h, flat, j)
+                continue
             for lo in range(0, len(chunk), b):
                 m = min(b, len(chunk) - lo)
                 batch = out.result(lo, m, clone=self.copy)

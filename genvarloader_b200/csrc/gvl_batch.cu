@@ -183,7 +183,7 @@ int gvl_dev_upload(gvl_ctx *ctx, void *dev, const void *host, int64_t bytes, gvl
 }
 
 // ---- one fixed-length batch, end to end (the C side of Dataset.__getitem__ / the loader's device calls) ----
-static int fixed_plan_prepared(gvl_ctx *ctx, const gvl_fixed_job *J, int64_t n, int64_t sub_batch, gvl_stream stream);
+static int fixed_plan_prepared(gvl_ctx *ctx, const gvl_fixed_job *J, int64_t n, int64_t sub_batch, gvl_stream stream, int what);
 
 int gvl_dev_fixed_plan(gvl_ctx *ctx, const gvl_fixed_job *J, const int64_t *ds_idx, const int32_t *jitter, int64_t n,
                        int64_t sub_batch, gvl_stream stream) {
@@ -192,11 +192,11 @@ int gvl_dev_fixed_plan(gvl_ctx *ctx, const gvl_fixed_job *J, const int64_t *ds_i
         return fail(GVL_ERR_ARG, "gvl_dev_fixed_plan: realigned tracks need haplotypes, diffs and track_lengths scratch");
     int rc = launch_batch_prep(ctx, J->view, ds_idx, jitter, false, n, sub_batch, J->ref_slot, J->n_tracks, J->annot_mask, &J->args, stream);
     if (rc) return rc;
-    return fixed_plan_prepared(ctx, J, n, sub_batch, stream);
+    return fixed_plan_prepared(ctx, J, n, sub_batch, stream, 3);
 }
 
-// everything of gvl_dev_fixed_plan after the batch prep
-static int fixed_plan_prepared(gvl_ctx *ctx, const gvl_fixed_job *J, int64_t n, int64_t sub_batch, gvl_stream stream) {
+// everything of gvl_dev_fixed_plan after the batch prep: the haplotype plan (what = 1), the track plan (what = 2) or both
+static int fixed_plan_prepared(gvl_ctx *ctx, const gvl_fixed_job *J, int64_t n, int64_t sub_batch, gvl_stream stream, int what) {
     int rc;
     const gvl_batch_args &A = J->args;
     const uint8_t *to_rc = J->rc_neg ? A.to_rc : NULL;
@@ -207,7 +207,7 @@ static int fixed_plan_prepared(gvl_ctx *ctx, const gvl_fixed_job *J, int64_t n, 
         ch = *J->svar2;
         ch.row_slot = A.goi;
     }
-    if (J->mode >= 0) {
+    if ((what & 1) && J->mode >= 0) {
         if (sv)
             rc = gvl_dev_hap_plan_svar2(ctx, J->tab, &ch, A.regions, A.shifts, n, J->rows_p, to_rc, J->output_length, cap,
                                         J->out_offsets, J->diffs, stream);
@@ -216,7 +216,7 @@ static int fixed_plan_prepared(gvl_ctx *ctx, const gvl_fixed_job *J, int64_t n, 
                                   J->out_offsets, J->diffs, stream);
         if (rc) return rc;
     }
-    if (J->realign) {
+    if ((what & 2) && J->realign) {
         rc = gvl_dev_track_lengths(ctx, A.regions, J->diffs, n, J->ploidy, J->track_lengths, stream);
         if (rc) return rc;
         rc = gvl_dev_realign_tracks_plan(ctx, J->tab, sv ? &ch : NULL, A.regions, A.shifts, A.goi, n, J->ploidy, NULL, NULL, to_rc,
@@ -226,6 +226,34 @@ static int fixed_plan_prepared(gvl_ctx *ctx, const gvl_fixed_job *J, int64_t n, 
         if (rc) return rc;
     }
     return GVL_OK;
+}
+
+// One stage of a fixed-length batch, for callers that spread a device call over two streams (the track plan -- a chain of
+// small latency-bound kernels -- next to the bandwidth-bound haplotype execute): GVL_STAGE_HAP_PLAN = batch prep +
+// haplotype plan, GVL_STAGE_TRK_PLAN (needs the diffs of HAP_PLAN), GVL_STAGE_HAP_EXEC, GVL_STAGE_TRK_EXEC (needs TRK_PLAN).
+int gvl_dev_fixed_stage(gvl_ctx *ctx, const gvl_fixed_job *J, int stage, const int64_t *ds_idx, const int32_t *jitter, int64_t n,
+                        int64_t sub_batch, uint8_t *seq, int32_t *annot_v, int32_t *annot_pos, float *trk, gvl_stream stream) {
+    if (!ctx || !J || !J->view || !J->tab) return fail(GVL_ERR_ARG, "gvl_dev_fixed_stage: NULL argument");
+    int rc;
+    switch (stage) {
+        case GVL_STAGE_HAP_PLAN:
+            rc = launch_batch_prep(ctx, J->view, ds_idx, jitter, false, n, sub_batch, J->ref_slot, J->n_tracks, J->annot_mask, &J->args, stream);
+            if (rc) return rc;
+            return fixed_plan_prepared(ctx, J, n, sub_batch, stream, 1);
+        case GVL_STAGE_TRK_PLAN:
+            return fixed_plan_prepared(ctx, J, n, sub_batch, stream, 2);
+        case GVL_STAGE_HAP_EXEC:
+            if (J->mode < 0) return GVL_OK;
+            if (!seq) return fail(GVL_ERR_ARG, "gvl_dev_fixed_stage: sequence output missing");
+            return gvl_dev_hap_exec(ctx, J->tab, J->mode, J->pad_char, seq, annot_v, annot_pos, stream);
+        case GVL_STAGE_TRK_EXEC:
+            if (J->n_tracks <= 0) return GVL_OK;
+            if (!trk) return fail(GVL_ERR_ARG, "gvl_dev_fixed_stage: track output missing");
+            if (J->realign) return gvl_dev_realign_tracks_exec(ctx, trk, stream);
+            return gvl_dev_paint_tracks(ctx, J->n_tracks, J->itv, J->args.offset_idxs, J->args.starts, n, J->paint_offsets,
+                                        n * J->output_length, J->rc_neg ? J->args.to_rc_q : NULL, trk, stream);
+        default: return fail(GVL_ERR_ARG, "gvl_dev_fixed_stage: unknown stage %d", stage);
+    }
 }
 
 int gvl_dev_fixed_exec(gvl_ctx *ctx, const gvl_fixed_job *J, int64_t n, uint8_t *seq, int32_t *annot_v, int32_t *annot_pos,
@@ -263,7 +291,7 @@ int gvl_dev_fixed_run(gvl_ctx *ctx, const gvl_fixed_job *J, const int64_t *ds_id
             return fail(GVL_ERR_ARG, "gvl_dev_fixed_run: realigned tracks need haplotypes, diffs and track_lengths scratch");
         int rc = launch_batch_prep(ctx, J->view, ds_idx, jitter, true, n, 0, J->ref_slot, J->n_tracks, J->annot_mask, &J->args, stream);
         if (rc) return rc;
-        rc = fixed_plan_prepared(ctx, J, n, 0, stream);
+        rc = fixed_plan_prepared(ctx, J, n, 0, stream, 3);
         if (rc) return rc;
         return gvl_dev_fixed_exec(ctx, J, n, seq, annot_v, annot_pos, trk, stream);
     }

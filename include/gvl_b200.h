@@ -390,6 +390,15 @@ int gvl_dev_fixed_plan(gvl_ctx *ctx, const gvl_fixed_job *job, const int64_t *ds
  * (GVL_MODE_ANNOTATED), trk f32[n*n_tracks*(ploidy|1)*L] in (b, t, p, L) / (b, t, L) order.  Unused outputs NULL. */
 int gvl_dev_fixed_exec(gvl_ctx *ctx, const gvl_fixed_job *job, int64_t n, uint8_t *seq, int32_t *annot_v, int32_t *annot_pos,
                        float *trk, gvl_stream stream);
+/* One stage of gvl_dev_fixed_plan / _exec, for callers that spread a device call over two streams: the track plan (a chain of
+ * small latency-bound kernels) can run next to the bandwidth-bound haplotype execute.  Order: HAP_PLAN (batch prep +
+ * haplotype plan) -> { HAP_EXEC, TRK_PLAN (reads the diffs of HAP_PLAN) } -> TRK_EXEC (after TRK_PLAN). */
+#define GVL_STAGE_HAP_PLAN 1
+#define GVL_STAGE_TRK_PLAN 2
+#define GVL_STAGE_HAP_EXEC 3
+#define GVL_STAGE_TRK_EXEC 4
+int gvl_dev_fixed_stage(gvl_ctx *ctx, const gvl_fixed_job *job, int stage, const int64_t *ds_idx, const int32_t *jitter, int64_t n,
+                        int64_t sub_batch, uint8_t *seq, int32_t *annot_v, int32_t *annot_pos, float *trk, gvl_stream stream);
 /* The whole of a fixed-length `Dataset.__getitem__` in one call: ds_idx i64[n] / jitter i32[n] (optional) are HOST arrays
  * (pageable is fine, the caller may reuse them at once).  Up to 256 queries they travel BY VALUE with the batch-prep launch
  * (kernel parameter space: no copy, no event); larger batches are staged through a rotating pool of pinned slots owned by the

@@ -130,6 +130,20 @@ def _utf8_to_bytes_offsets(col) -> tuple:
     return np.ascontiguousarray(data[lo:hi]), offs - lo
 
 
+def _compact_ranges(go: np.ndarray, store_idxs: np.ndarray, keep_below: float = 0.5):
+    """A dataset linked to a cohort-scale `.svar` store references only the slices of the store's `variant_idxs.npy` that
+    fall into its regions.  When those are less than `keep_below` of the store, gather them into a compact array (in slot
+    order) and rebase the `(2, n)` starts / stops, so that only referenced genotypes are uploaded to HBM; otherwise the
+    store's array is used as it is (zero-copy memmap).  Ranges may be empty (stop <= start)."""
+    starts, lens = go[0], np.maximum(go[1] - go[0], 0)
+    total = int(lens.sum())
+    if total >= keep_below * store_idxs.size:
+        return go, store_idxs
+    new_starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64) if lens.size else np.zeros(0, np.int64)
+    src = np.repeat(starts - new_starts, lens) + np.arange(total, dtype=np.int64)  # store index of every kept entry
+    return np.stack([new_starts, new_starts + lens]), np.ascontiguousarray(store_idxs[src])
+
+
 def _resolve_svar(gvl_path: Path, link, override) -> Path:
     """The `.svar` directory a dataset points at (reference `_resolve_svar`, _svar_link.py:24-61): override, stored
     relative path, stored absolute path, a unique sibling `*.svar`; legacy datasets carry a `genotypes/link.svar` symlink."""
@@ -254,8 +268,10 @@ def read_dataset_arrays(path, reference=None, svar=None) -> dict:
             if len(shape) != 4 or shape[0] != 2 or int(np.prod(shape[1:])) != n_slots:
                 raise ValueError(f"genotypes/svar_meta.json: shape {shape} does not match (2, {n_regions}, {len(samples)}, {ploidy})")
             go = np.memmap(gdir / "offsets.npy", shape=shape, dtype=np.dtype(sm["dtype"]), mode="r").reshape(2, -1)
+            store_idxs = np.memmap(svar_path / "variant_idxs.npy", dtype=np.int32, mode="r")
+            go, store_idxs = _compact_ranges(np.asarray(go, np.int64), store_idxs)
             out.update(v_starts=pos.astype(np.int32), ilens=ilen, alt_alleles=alt, alt_offsets=alt_off, geno_offsets=go,
-                       geno_v_idxs=np.memmap(svar_path / "variant_idxs.npy", dtype=np.int32, mode="r"), svar_path=svar_path)
+                       geno_v_idxs=store_idxs, svar_path=svar_path)
         else:
             out.update(v_starts=pos.astype(np.int32), ilens=ilen, alt_alleles=alt, alt_offsets=alt_off,
                        geno_v_idxs=np.memmap(gdir / "variant_idxs.npy", dtype=np.int32, mode="r"),

@@ -101,3 +101,25 @@ def test_svar_linked_dataset(disk, tmp_path):
     (moved / "ds" / "metadata.json").write_text(json.dumps(meta))
     with pytest.raises(ValueError, match="fingerprint mismatch"):
         read_dataset_arrays(moved / "ds", svar=moved / "renamed.svar")
+
+
+def test_linked_store_ranges_are_compacted():
+    """A dataset linked to a large `.svar` store uploads only the genotype slices it references (`_compact_ranges`): same
+    slice contents, rebased (2, n) starts / stops, empty and inverted ranges kept empty; a mostly-referenced store is left as
+    it is."""
+    from genvarloader_b200._open import _compact_ranges
+
+    rng = np.random.default_rng(0)
+    store = rng.integers(0, 1000, size=10_000).astype(np.int32)
+    st = np.sort(rng.integers(0, 9_000, size=50))
+    ln = rng.integers(0, 20, size=50)
+    ln[3] = 0
+    go = np.stack([st, st + ln]).astype(np.int64)
+    go[1, 7] = go[0, 7] - 5  # stop < start: an empty slot
+    g2, s2 = _compact_ranges(go, store)
+    assert s2.size < store.size and s2.size == int(np.maximum(go[1] - go[0], 0).sum())
+    for k in range(50):
+        assert (store[go[0, k]: max(go[1, k], go[0, k])] == s2[g2[0, k]: g2[1, k]]).all(), k
+    whole = np.stack([np.arange(0, 10_000, 100), np.arange(100, 10_100, 100)]).astype(np.int64)
+    g3, s3 = _compact_ranges(whole, store)
+    assert s3 is store and g3 is whole

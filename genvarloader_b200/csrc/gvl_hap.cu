@@ -833,6 +833,7 @@ static int hap_plan_impl(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_s
     // (no memset of the status words: every plan leaves its cursors at zero, see plan_row_done)
     ctx->n_work = n_work;
     ctx->fixed_len = output_length >= 0 ? output_length : -1;
+    ctx->rec_bound_per_row = n_work > 0 ? max_records / n_work : 0;
     ctx->plan_out_offsets = out_offsets;
     if (n_work == 0) {
         GVL_CUDA(cudaMemsetAsync(out_offsets, 0, sizeof(int64_t), st));
@@ -1029,6 +1030,11 @@ int gvl_dev_hap_exec(gvl_ctx *ctx, const gvl_sparse_tables *tab, int mode, uint8
         }();
         const int64_t target_ctas = 3 * (int64_t)sms;
         int64_t tl = ctx->fixed_len * ctx->n_work / target_ctas;
+        // tiles beyond 16,384 positions only where the plan's record bound promises one staging pass per tile (REC_CAP = 128:
+        // about 100 records per tile); denser -- or loosely bounded, like the svar2 source whose bound counts the whole
+        // cohort's dense window -- lists keep the 16,384 of round 1 (cfg2d: 8,192 -> 336 us, 16,384 -> 352, 32,768 -> 373)
+        if (tl > 16384 && !(ctx->rec_bound_per_row > 0 && ctx->rec_bound_per_row * (int64_t)OH_MAX_TILE <= 100 * ctx->fixed_len))
+            tl = 16384;
         if (tile_env > 0) tl = tile_env;
         tl = imax64(q, imin64(tl / q * q, OH_MAX_TILE));
         P.tile_len = (int32_t)tl;

@@ -21,7 +21,13 @@
 namespace gvl {
 
 constexpr int OH_GROUP = 256;                                  // positions per warp step (8 per lane)
-constexpr int OH_MAX_TILE_WANTED = 16384;                      // haplotype positions per CTA, at most
+// (round 1 capped tiles at 16,384: its launches were single batches.  A ring launch has thousands of CTAs, and a CTA's fixed
+//  cost -- ~3.3 us of dependent round trips and barriers before its first store -- is worth amortising over twice the positions:
+//  cfg3 execute 272 -> 259 us per 20 batches.  The launch code shortens tiles again when variants are dense.)
+#ifndef GVL_OH_MAX_TILE
+#define GVL_OH_MAX_TILE 32768
+#endif
+constexpr int OH_MAX_TILE_WANTED = GVL_OH_MAX_TILE;            // haplotype positions per CTA, at most
 
 #ifndef GVL_OH_THREADS
 #define GVL_OH_THREADS 128

@@ -417,14 +417,12 @@ def run_b200(args):
             H.idx[:n_q].copy_(idx_sets[k])
             if jit_sets is not None:
                 H.jit[:n_q].copy_(jit_sets[k])
-            H.eng.batch_prep(pipe.view, H.idx, H.jit if sp.jitter else None, n_q, pipe.ref_slot, sp.t, sp.annot_mask, H.scr.args,
-                             sub_batch=pairs)
+            # the same library calls the pipeline's graph holds (gvl_dev_fixed_plan / gvl_dev_fixed_exec over the half's job)
             a0, a1, a2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             a0.record(pipe.s_exec)
-            H.eng.plan(H.scr.regions, H.scr.shifts, H.scr.goi[:n_q], L, pipe._cap(n_q), to_rc=H.scr.to_rc if sp.rc_neg else None,
-                       out_offsets=H.scr.out_offsets, diffs=H.scr.diffs)
+            pipe._stage_plan(H.eng, H.scr, H.idx, H.jit if sp.jitter else None, n_q, sub_batch=pairs)  # batch prep + plan (+ svar2 merge)
             a1.record(pipe.s_exec)
-            H.eng.execute(sp.mode, out=H.out.seq, annot_v=H.out.av, annot_pos=H.out.ap)
+            pipe._stage_exec(H.eng, H.scr, H.out, n_q, sub_batch=pairs)
             a2.record(pipe.s_exec)
             pipe.s_exec.synchronize()
             if i >= 2:
@@ -606,6 +604,8 @@ def run_b200(args):
                      "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
                      "alg_bytes_per_launch": ab_launch, "launch_ms": exec_ms, "plan_kernel_ms": plan_ms,
                      "batches_per_launch": ring,
+                     "plan_note": "plan_kernel_ms = batch prep + plan (+ svar2 merge) of the same device call between two events on an "
+                                  "otherwise idle stream (includes the launch latencies of its 2-3 kernels)",
                      "how": f"one execute launch covers the {ring} batches of a device call; its duration is the time between two CUDA "
                             "events around that single launch on the stream it runs on (median of 10, nothing else on the GPU)",
                      "frac_of_nominal_8TBps": achieved / 8000.0,

@@ -67,6 +67,7 @@ class Engine:
         self.geno_offsets_host = np.ascontiguousarray(go, np.int64)  # O(batch) capacity sums stay on the host
         # longest variant list of any (region, sample, ploid) slot: workspace capacity of graph-replayed batches
         self.max_slot_len = int(np.maximum(go[1] - go[0], 0).max()) if go.shape[1] else 0
+        self.typ_slot_len = 0  # (the CSR bound is tight enough; svar2 sources set a hint, set_svar2)
         self._views: dict = {}
         with torch.cuda.device(self.device):
             self.ref = _dev(reference, np.uint8, self.device, pad=32)
@@ -126,6 +127,9 @@ class Engine:
         self.svar2 = dict(t=t, spr=spr, vk_len=vk_len, win=win)
         # longest merged list of any slot (var_key entries + the whole dense window): workspace capacity per row
         self.max_slot_len = int((vk_len.max() if vk_len.size else 0) + (win.max() if win.size else 0))
+        # typical merged length (hint for the execute kernel's tile length; the bound above counts the whole cohort's window)
+        n_present = int(np.bitwise_count(np.asarray(sv["dense_present"], np.uint8)).sum(dtype=np.int64))
+        self.typ_slot_len = int(2 * (vk_len.sum() + n_present) / max(vk_len.size, 1)) + 1
 
     def svar2_channels(self, geno_offset_idx) -> Svar2Channels:
         """gvl_svar2_channels over the resident tables; row k reads slot geno_offset_idx[k] (device i64 (b, p))."""

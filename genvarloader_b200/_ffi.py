@@ -73,7 +73,7 @@ class FixedJob(C.Structure):
     _fields_ = [("view", c_vp), ("tab", c_vp), ("svar2", c_vp), ("args", BatchArgs), ("out_offsets", c_vp), ("diffs", c_vp),
                 ("track_lengths", c_vp), ("paint_offsets", c_vp), ("itv", c_vp), ("strategy_ids", c_vp), ("params", c_vp),
                 ("ploidy", c_i64), ("rows_p", c_i64), ("output_length", c_i64), ("ref_slot", c_i64), ("n_tracks", c_i64),
-                ("max_slot_len", c_i64), ("annot_mask", C.c_uint32), ("mode", c_i32), ("realign", c_i32), ("rc_neg", c_i32),
+                ("max_slot_len", c_i64), ("typ_slot_len", c_i64), ("annot_mask", C.c_uint32), ("mode", c_i32), ("realign", c_i32), ("rc_neg", c_i32),
                 ("pad_char", c_u8)]
 
 

@@ -225,7 +225,7 @@ class FixedPipeline:
         mode = MODES[sp.mode] if sp.want_seqs else -1
         return FixedJob(adr(self.view), adr(eng.tab), adr(sv), scr.args, ptr(scr.out_offsets), ptr(scr.diffs), ptr(scr.track_lengths),
                         ptr(self._paint_off) if (sp.t and not sp.realign) else c_vp(0), adr(itv), adr(sid), adr(par),
-                        sp.p, sp.rows_p, sp.L, self.ref_slot, sp.t, max(eng.max_slot_len, 1), sp.annot_mask, mode,
+                        sp.p, sp.rows_p, sp.L, self.ref_slot, sp.t, max(eng.max_slot_len, 1), int(getattr(eng, "typ_slot_len", 0)), sp.annot_mask, mode,
                         1 if sp.realign else 0, 1 if sp.rc_neg else 0, eng.pad_char)
 
     # ------------------------------------------------------------------ one device call over n queries

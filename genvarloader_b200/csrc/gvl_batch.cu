@@ -215,6 +215,7 @@ static int fixed_plan_prepared(gvl_ctx *ctx, const gvl_fixed_job *J, int64_t n, 
             rc = gvl_dev_hap_plan(ctx, J->tab, A.regions, A.shifts, A.goi, n, J->rows_p, NULL, NULL, to_rc, J->output_length, cap,
                                   J->out_offsets, J->diffs, stream);
         if (rc) return rc;
+        if (J->typ_slot_len > 0) ctx->rec_bound_per_row = imin64(ctx->rec_bound_per_row, J->typ_slot_len);  // (tile-length hint)
     }
     if ((what & 2) && J->realign) {
         rc = gvl_dev_track_lengths(ctx, A.regions, J->diffs, n, J->ploidy, J->track_lengths, stream);

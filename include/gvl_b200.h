@@ -377,6 +377,9 @@ typedef struct gvl_fixed_job {
     int64_t ref_slot;                 /* >= 0: every row reads this (empty) genotype slot; < 0: haplotypes */
     int64_t n_tracks;
     int64_t max_slot_len;             /* upper bound of one row's variant-list length (plan workspace = rows * this) */
+    int64_t typ_slot_len;             /* typical (about twice the mean) variant-list length of a row: a HINT for the one-hot execute
+                                       * kernel's tile length where the bound is loose (svar2: the bound counts the cohort's whole dense
+                                       * window); 0 = use the bound */
     uint32_t annot_mask;
     int32_t mode;                     /* GVL_MODE_* of the sequence output; < 0: no sequence output */
     int32_t realign;                  /* tracks are realigned to the haplotypes (needs mode >= 0 and ref_slot < 0) */

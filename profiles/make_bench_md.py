@@ -1,0 +1,46 @@
+"""profiles/r2_bench.md from the JSON lines in profiles/r2_bench/ (copied from the final-shaped GPU runs)."""
+import json
+from pathlib import Path
+
+D = Path(__file__).resolve().parent / "r2_bench"
+
+
+def get(k):
+    return json.loads((D / f"{k}.json").read_text().strip().splitlines()[-1])
+
+
+order = ['cfg3_s20', 'cfg3_s640', 'cfg2_s20', 'cfg2_s640', 'cfg1_s20', 'cfg1_s640', 'cfg4_s20', 'cfg4_s640', 'cfg4ann_s640', 'cfg2d_s20', 'cfg2d_s640']
+out = ["# Round 2: bench lines of the final library (one B200 unless noted; `profiles/scripts/r2_final2.sh`, `r2_multi8.sh`)", "",
+       "Full JSON lines: `profiles/r2_bench/*.json` (this table: `python profiles/make_bench_md.py`).  `python bench.py --steps K --warmup W "
+       "[--workload ...]`; clocks 1,965 MHz, no throttle reasons in any run.", "",
+       "| run | bp/s (`value`) | µs/step | `whole_step_frac` | `roofline.frac` (one execute launch) | execute launch | prep + plan (+ merge) | `api` bp/s | `e2e` bp/s | CPU port, 16 threads | tracks leg: µs/step, frac |",
+       "|---|---|---|---|---|---|---|---|---|---|---|"]
+for k in order:
+    d = get(k); r = d['roofline']; t = d.get('tracks') or {}
+    out.append(f"| {k.replace('_s', ' @ ')} steps | {d['value']:.3e} | {d['ms_per_step'] * 1e3:.2f} | {d['whole_step_frac']:.3f} | {r['frac']:.3f} | "
+               f"{r['launch_ms'] * 1e3:.0f} µs / {r['batches_per_launch']} batches | {r['plan_kernel_ms'] * 1e3:.0f} µs | {d['api']['value']:.3e} | "
+               f"{d['e2e']['value']:.3e} | {d['cpu_baseline']['value']:.2e} | "
+               + (f"{t['ms_per_step'] * 1e3:.1f}, {t['whole_step_frac']:.3f}" if t else "") + " |")
+out.append("")
+out.append("`roofline.frac` and `whole_step_frac` use SURVEY.md's 5 algorithmic bytes per bp against the measured read+write copy peak "
+           "(6,530 GB/s); the kernel reads a PACKED reference (0.5 B/bp) and is nearly write-only, so values a little above 1.0 are "
+           "possible (measured steady-state DRAM traffic: 4.26 B/bp, `ncu_exec_traffic.json`).")
+out.append("")
+for k in ['ref_cfg3_s20', 'ref_cfg2_s20']:
+    d = get(k)
+    out.append(f"* `--impl reference` {k[4:].replace('_s', ' @ ')} steps: {d['value']:.3e} bp/s ({d['cpu_baseline']['cores']} threads; "
+               f"{d['cpu_baseline']['sample'][:110]}...)")
+out += ["", "## 8 GPUs (one box, torchrun, NCCL barrier; `value` = all ranks' bp / max time)", "",
+        "| run | bp/s | × one GPU | per-rank block ms | `e2e` bp/s (every rank on its own PCIe link, max time) | gather of a ring's outputs to rank 0 |",
+        "|---|---|---|---|---|---|"]
+one = {'s20': get('cfg3_s20')['value'], 's640': get('cfg3_s640')['value']}
+for k, s_ in (('cfg3_s20_n8', 's20'), ('cfg3_s640_n8', 's640')):
+    d = get(k); g = d['gather']
+    out.append(f"| {k} | {d['value']:.3e} | {d['value'] / one[s_]:.2f} | {min(d['per_rank_ms']):.3f}–{max(d['per_rank_ms']):.3f} | "
+               f"{d['e2e']['value']:.3e} | {g['ms_per_device_call']:.1f} ms per {g['batches']} batches, {g['consumer_ingest_GBps']:.0f} GB/s into rank 0 |")
+out += ["", "`e2e` does not scale with the GPU count (2.4 × 10¹⁰ bp/s on 8 ranks against 1.3 × 10¹⁰ on one): eight ranks copying one-hot",
+        "bytes into pinned host memory at once share the host's memory system — the reason the product is the GPU-resident loader.", "",
+        "Other measurements of the same run: `Dataset.__getitem__` host time 27 µs per call on the cfg2 and cfg3 shapes "
+        "(`profiles/probe_dataset.py`); one realign call on the cfg3 shape 76.4 µs (`profiles/probe_tracks.py`)."]
+(D.parent / "r2_bench.md").write_text("\n".join(out) + "\n")
+print("\n".join(out[4:18]))

@@ -1035,6 +1035,8 @@ int gvl_dev_hap_exec(gvl_ctx *ctx, const gvl_sparse_tables *tab, int mode, uint8
         // cohort's dense window -- lists keep the 16,384 of round 1 (cfg2d: 8,192 -> 336 us, 16,384 -> 352, 32,768 -> 373)
         if (tl > 16384 && !(ctx->rec_bound_per_row > 0 && ctx->rec_bound_per_row * (int64_t)OH_MAX_TILE <= 100 * ctx->fixed_len))
             tl = 16384;
+        // lists so dense that a 16,384-position tile needs a second staging pass (REC_CAP = 128): 8,192 (cfg2d: 304 -> 285 us)
+        if (tl > 8192 && ctx->fixed_len > 0 && ctx->rec_bound_per_row * (int64_t)16384 > (int64_t)REC_CAP * ctx->fixed_len) tl = 8192;
         if (tile_env > 0) tl = tile_env;
         tl = imax64(q, imin64(tl / q * q, OH_MAX_TILE));
         P.tile_len = (int32_t)tl;
@@ -1072,7 +1074,15 @@ int gvl_dev_hap_exec(gvl_ctx *ctx, const gvl_sparse_tables *tab, int mode, uint8
     switch (mode) {
         case GVL_MODE_U8: hap_exec_kernel<GVL_MODE_U8><<<grid3, EXEC_THREADS, 0, st>>>(P); break;
         case GVL_MODE_ONEHOT:
-            if (packed) hap_exec_oh_kernel<<<grid3, OH_THREADS, 0, st>>>(P);
+            if (packed) {
+                // loads of 4 groups in flight per warp for long, sparse rows; 2 where the record bound says "dense" (the tile
+                // length above stayed at 16,384 for that reason) or a warp has fewer than 8 groups to walk
+                const bool sparse = ctx->fixed_len > 0 && ctx->rec_bound_per_row > 0 &&
+                                    ctx->rec_bound_per_row * (int64_t)OH_MAX_TILE <= 100 * ctx->fixed_len;
+                const int64_t groups_per_warp = (imin64(P.tile_len, ctx->fixed_len) / OH_GROUP) / (OH_THREADS / 32);
+                if (sparse && groups_per_warp >= 8) hap_exec_oh_kernel<OH_UNROLL_LONG><<<grid3, OH_THREADS, 0, st>>>(P);
+                else hap_exec_oh_kernel<2><<<grid3, OH_THREADS, 0, st>>>(P);
+            }
             else hap_exec_kernel<GVL_MODE_ONEHOT><<<grid3, EXEC_THREADS, 0, st>>>(P);
             break;
         case GVL_MODE_ONEHOT_CF: hap_exec_kernel<GVL_MODE_ONEHOT_CF><<<grid3, EXEC_THREADS, 0, st>>>(P); break;

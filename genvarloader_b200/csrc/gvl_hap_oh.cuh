@@ -45,7 +45,7 @@ constexpr int OH_EDGE_ROUNDS = (2 * REC_CAP + 2 + GVL_OH_THREADS - 1) / GVL_OH_T
 #ifndef GVL_OH_UNROLL
 #define GVL_OH_UNROLL 4
 #endif
-constexpr int OH_UNROLL = GVL_OH_UNROLL;                                   // groups per warp whose loads are issued together
+constexpr int OH_UNROLL_LONG = GVL_OH_UNROLL;                              // groups per warp whose loads are issued together (long sparse rows)
 
 struct OhRecs {
     int32_t a[REC_CAP + 2];   // ALT start (haplotype coordinate); a[m], a[m+1] sentinels
@@ -207,16 +207,33 @@ __device__ __forceinline__ unsigned long long gtime() {
 }
 #define GVL_TR(slot)                                                                                       \
     do {                                                                                                   \
-        if (g_trace && threadIdx.x == 0) g_trace[tr_cta * 6 + (slot)] = gtime();                            \
+        if (GVL_TRACE == 1 && g_trace && threadIdx.x == 0) g_trace[tr_cta * 6 + (slot)] = gtime();          \
     } while (0)
 #else
 #define GVL_TR(slot) do { } while (0)
 #endif
+// GVL_TRACE == 2: cycles thread 0 of every CTA spends in each phase, summed over the passes of its tile (profiles/trace_dense.py):
+// g_trace[cta * 8 + i], i = 0 prologue, 1 record staging, 2 group table, 3 edge slots part 1, 4 group loop, 5 edge slots part 2,
+// 6 = passes, 7 = smid
+#if GVL_TRACE == 2
+#define GVL_TC(i)                       \
+    do {                                \
+        const long long now_ = clock64(); \
+        tc_acc[i] += now_ - tc_last;    \
+        tc_last = now_;                 \
+    } while (0)
+#else
+#define GVL_TC(i) do { } while (0)
+#endif
 
+// OH_UNROLL = groups per warp whose loads are issued together: 4 for long sparse rows (cfg3: 259 us per 20 batches against 270
+// with 2), 2 where most groups take the mixed path or a warp has only a handful of groups (cfg2d: 358 -> 304 us, cfg4: 613 ->
+// 551 us) -- the launch code picks (profiles/r2_plan.md).
+template <int OH_UNROLL>
 __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(HapExecParams P) {
 #if GVL_TRACE
     const unsigned long long tr_cta = blockIdx.x + (unsigned long long)gridDim.x * (blockIdx.y + (unsigned long long)gridDim.y * blockIdx.z);
-    if (g_trace && threadIdx.x == 0) {
+    if (GVL_TRACE == 1 && g_trace && threadIdx.x == 0) {
         unsigned smid;
         asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
         g_trace[tr_cta * 6 + 0] = smid;
@@ -231,6 +248,10 @@ __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(Ha
     __shared__ uint32_t s_edge[OH_EDGE_ROUNDS][8][OH_THREADS];
     __shared__ int64_t s_lo, s_hi;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#if GVL_TRACE == 2
+    long long tc_acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    long long tc_last = clock64();
+#endif
 
     // ---- tile -> (row, tile-in-row) ----
     int64_t row, tile;
@@ -317,6 +338,7 @@ __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(Ha
     }
     __syncthreads();
     GVL_TR(2);
+    GVL_TC(0);
     const int64_t r_hi = s_hi;
     int64_t r = s_lo;
     int32_t cur = h0;
@@ -371,6 +393,7 @@ __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(Ha
         }
         if (tid == 0) S.a[m] = S.a[m + 1] = INT32_MAX;
         __syncthreads();
+        GVL_TC(1);
 
         // ---- output range of the pass in units of 8 positions aligned on the GLOBAL flat index (32-byte
         //      aligned stores); a group is 32 units (one per lane), warp w owns groups w, w+4, ... ----
@@ -403,6 +426,7 @@ __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(Ha
             s_grp[tid] = make_uint2((uint32_t)dl, (uint32_t)idx | ((uint32_t)cnt << 8) | (plain ? 0x80000000u : 0u));
         }
         __syncthreads();
+        GVL_TC(2);
 
         GVL_TR(3);
         uint8_t *const out_lane = out_row + 4 * ((int64_t)j0 + 8 * lane);
@@ -481,6 +505,7 @@ __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(Ha
         };
         for (int s_ = tid, rd = 0; s_ < n_slots; s_ += OH_THREADS, rd++) edge_begin(s_, rd);  // (one round unless variants are dense)
         cp_async_commit();
+        GVL_TC(3);
 
         // ---- the group loop: every lane streams the units that are a single run ----
         for (int gb = warp; gb < n_groups; gb += OH_UNROLL * (OH_THREADS / 32)) {
@@ -552,6 +577,7 @@ __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(Ha
             }
         }
 
+        GVL_TC(4);
         // ---- edge slots, part 2: blend (the copies were started before the group loop) + store ----
         cp_async_wait<0>();
 #pragma unroll 1
@@ -600,10 +626,22 @@ __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(Ha
                 }
             }
         }
+        GVL_TC(5);
+#if GVL_TRACE == 2
+        tc_acc[6] += 1;
+#endif
         cur = seg_end;
         r += m_new;
     }
-#if GVL_TRACE
+#if GVL_TRACE == 2
+    if (g_trace && threadIdx.x == 0) {
+        for (int i = 0; i < 7; i++) g_trace[tr_cta * 8 + i] = (unsigned long long)tc_acc[i];
+        unsigned smid2;
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid2));
+        g_trace[tr_cta * 8 + 7] = smid2;
+    }
+#endif
+#if GVL_TRACE == 1
     __syncthreads();
     GVL_TR(4);
 #endif

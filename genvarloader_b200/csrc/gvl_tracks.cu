@@ -321,13 +321,6 @@ int gvl_dev_shift_and_realign_tracks(gvl_ctx *ctx, const gvl_sparse_tables *tab,
                         base_seed, query_seed, max_records, out, stream);
 }
 
-#if GVL_TRACE
-__attribute__((visibility("default"))) int gvl_debug_set_trk_trace(void *dev_buf) {
-    unsigned long long *p = (unsigned long long *)dev_buf;
-    GVL_CUDA(cudaMemcpyToSymbol(g_trk_trace, &p, sizeof(p)));
-    return GVL_OK;
-}
-#endif
 
 int gvl_dev_shift_and_realign_tracks_svar2(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_svar2_channels *ch,
                                            const int32_t *regions, const int32_t *shifts, int64_t batch, int64_t ploidy,

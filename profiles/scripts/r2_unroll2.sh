@@ -1,0 +1,14 @@
+mkdir -p gpurun_out
+python -m pytest tests -x -q -m gpu 2>&1 | tail -2
+pick() { python - "$1" <<'PY'
+import json,sys
+d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+print(sys.argv[1], 'value %.4g'%d['value'], 'whole %.3f'%d['whole_step_frac'], 'exec %.4f'%d['roofline']['launch_ms'], 'roof %.3f'%d['roofline']['frac'])
+PY
+}
+for wl in cfg3 cfg2 cfg2d cfg4 cfg1; do
+python bench.py --steps 20 --warmup 5 --cpu-seconds 0.2 --workload $wl > gpurun_out/u2_${wl}.json 2>gpurun_out/ab.err; pick gpurun_out/u2_${wl}.json
+done
+GVL_OH_TILE=8192 python bench.py --steps 20 --warmup 5 --cpu-seconds 0.2 --workload cfg2d > gpurun_out/u2_cfg2d_t8k.json 2>gpurun_out/ab.err; pick gpurun_out/u2_cfg2d_t8k.json
+python bench.py --steps 640 --warmup 5 --cpu-seconds 0.2 --workload cfg2d > gpurun_out/u2_cfg2d_640.json 2>gpurun_out/ab.err; pick gpurun_out/u2_cfg2d_640.json
+python bench.py --steps 640 --warmup 5 --cpu-seconds 0.2 --workload cfg4 > gpurun_out/u2_cfg4_640.json 2>gpurun_out/ab.err; pick gpurun_out/u2_cfg4_640.json

@@ -1080,8 +1080,11 @@ int gvl_dev_hap_exec(gvl_ctx *ctx, const gvl_sparse_tables *tab, int mode, uint8
                 const bool sparse = ctx->fixed_len > 0 && ctx->rec_bound_per_row > 0 &&
                                     ctx->rec_bound_per_row * (int64_t)OH_MAX_TILE <= 100 * ctx->fixed_len;
                 const int64_t groups_per_warp = (imin64(P.tile_len, ctx->fixed_len) / OH_GROUP) / (OH_THREADS / 32);
-                if (sparse && groups_per_warp >= 8) hap_exec_oh_kernel<OH_UNROLL_LONG><<<grid3, OH_THREADS, 0, st>>>(P);
-                else hap_exec_oh_kernel<2><<<grid3, OH_THREADS, 0, st>>>(P);
+                if (imin64(P.tile_len, ctx->fixed_len) <= 8192 && P.tiles_per_row == 1)  // short rows: one tile per row, 2-warp CTAs
+                    hap_exec_oh_kernel<2, 64><<<grid3, 64, 0, st>>>(P);
+                else if (ctx->fixed_len < 0 || (sparse && groups_per_warp >= 8))  // (ragged plans: as in round 1)
+                    hap_exec_oh_kernel<OH_UNROLL_LONG, OH_THREADS><<<grid3, OH_THREADS, 0, st>>>(P);
+                else hap_exec_oh_kernel<2, OH_THREADS><<<grid3, OH_THREADS, 0, st>>>(P);
             }
             else hap_exec_kernel<GVL_MODE_ONEHOT><<<grid3, EXEC_THREADS, 0, st>>>(P);
             break;

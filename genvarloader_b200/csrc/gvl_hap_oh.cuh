@@ -229,8 +229,11 @@ __device__ __forceinline__ unsigned long long gtime() {
 // OH_UNROLL = groups per warp whose loads are issued together: 4 for long sparse rows (cfg3: 259 us per 20 batches against 270
 // with 2), 2 where most groups take the mixed path or a warp has only a handful of groups (cfg2d: 358 -> 304 us, cfg4: 613 ->
 // 551 us) -- the launch code picks (profiles/r2_plan.md).
-template <int OH_UNROLL>
-__global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(HapExecParams P) {
+// NT = threads per CTA: 128, or 64 for rows of at most 8,192 positions (one tile per row: twelve 2-warp CTAs per SM keep more
+// rows in flight against the ~3.3 us of fixed latency per CTA than eight 4-warp ones -- cfg4: 551 -> 479 us per 20 batches).
+template <int OH_UNROLL, int NT>
+__global__ void __launch_bounds__(NT, NT == 64 ? 12 : OH_MIN_CTAS) hap_exec_oh_kernel(HapExecParams P) {
+    constexpr int EDGE_ROUNDS = (2 * REC_CAP + 2 + NT - 1) / NT;  // edge slots per thread and pass
 #if GVL_TRACE
     const unsigned long long tr_cta = blockIdx.x + (unsigned long long)gridDim.x * (blockIdx.y + (unsigned long long)gridDim.y * blockIdx.z);
     if (GVL_TRACE == 1 && g_trace && threadIdx.x == 0) {
@@ -244,8 +247,8 @@ __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(Ha
     __shared__ OhRecs S;
     __shared__ __align__(16) uint2 s_lut[256];         // byte (2 codes) -> 8 one-hot bytes
     __shared__ __align__(8) uint2 s_grp[OH_MAX_GROUPS];  // per group: {reference delta, idx | cnt << 8 | plain << 31}
-    // per thread and round (2 * REC_CAP + 2 slots over OH_THREADS threads): 6 staged code words of an edge unit, descriptor, position
-    __shared__ uint32_t s_edge[OH_EDGE_ROUNDS][8][OH_THREADS];
+    // per thread and round (2 * REC_CAP + 2 slots over NT threads): 6 staged code words of an edge unit, descriptor, position
+    __shared__ uint32_t s_edge[EDGE_ROUNDS][8][NT];
     __shared__ int64_t s_lo, s_hi;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #if GVL_TRACE == 2
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(Ha
     }
 
     // spread(n): byte c = bit c of the 4-bit code n   (n * 0x204081 puts bit c at bit 8c, no carries)
-    for (int i = tid; i < 256; i += OH_THREADS)
+    for (int i = tid; i < 256; i += NT)
         s_lut[i] = make_uint2(((i & 15) * 0x204081u) & 0x01010101u, ((i >> 4) * 0x204081u) & 0x01010101u);
 
     const int32_t *__restrict__ ra = P.rec.a + rp.rec_off;
@@ -375,7 +378,7 @@ __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(Ha
         const int m = m_new + 1;
         const int32_t seg_end = (r + 1 + m_new < r_hi) ? ra[r + 1 + m_new] : h1;
         __syncthreads();  // previous pass finished reading S
-        for (int i = tid; i < m; i += OH_THREADS) {
+        for (int i = tid; i < m; i += NT) {
             const int64_t idx = r + i;
             if (idx < 0) {  // virtual record: leading pad, then reference from ref0
                 S.a[0] = 0;
@@ -477,7 +480,7 @@ __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(Ha
                     if (vA > 0 && (U.x1 > 0 || U.x2 < 8)) {
                         const uint32_t *w = P.ref_packed + (nA >> 3);
                         cp_async4(slot, w);
-                        cp_async4(slot + 4 * OH_THREADS, w + 1);
+                        cp_async4(slot + 4 * NT, w + 1);
                     }
                     if (U.x1 > 0 && U.x2 < 8) {  // a record starts inside the unit: reference resumes with its own delta
                         const int64_t nB = rp.ref_base + e_p + U.dlB;
@@ -485,8 +488,8 @@ __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(Ha
                         e_desc |= (uint32_t)vB << 14 | ((uint32_t)nB & 7u) << 21;
                         if (vB > 0) {
                             const uint32_t *w = P.ref_packed + (nB >> 3);
-                            cp_async4(slot + 8 * OH_THREADS, w);
-                            cp_async4(slot + 12 * OH_THREADS, w + 1);
+                            cp_async4(slot + 8 * NT, w);
+                            cp_async4(slot + 12 * NT, w + 1);
                         }
                     }
                     if (U.alt == ALT_PAD) {
@@ -495,20 +498,20 @@ __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(Ha
                         const int64_t nC = U.alt >= 0 ? U.alt : ~U.alt;
                         const uint32_t *w = (U.alt >= 0 ? P.alt_packed : P.ref_packed) + (nC >> 3);
                         e_desc |= ((uint32_t)nC & 7u) << 24;
-                        cp_async4(slot + 16 * OH_THREADS, w);
-                        cp_async4(slot + 20 * OH_THREADS, w + 1);
+                        cp_async4(slot + 16 * NT, w);
+                        cp_async4(slot + 20 * NT, w + 1);
                     }
                 }
             }
             s_edge[rd][6][tid] = e_desc | (uint32_t)e_kind;
             s_edge[rd][7][tid] = (uint32_t)e_p;
         };
-        for (int s_ = tid, rd = 0; s_ < n_slots; s_ += OH_THREADS, rd++) edge_begin(s_, rd);  // (one round unless variants are dense)
+        for (int s_ = tid, rd = 0; s_ < n_slots; s_ += NT, rd++) edge_begin(s_, rd);  // (one round unless variants are dense)
         cp_async_commit();
         GVL_TC(3);
 
         // ---- the group loop: every lane streams the units that are a single run ----
-        for (int gb = warp; gb < n_groups; gb += OH_UNROLL * (OH_THREADS / 32)) {
+        for (int gb = warp; gb < n_groups; gb += OH_UNROLL * (NT / 32)) {
             uint8_t *const out_it = out_lane + (int64_t)gb * (4 * OH_GROUP);  // the lane's unit in group gb
             // phase 1: all loads of the warp's next OH_UNROLL groups (2 per lane and group in flight)
             uint32_t w0[OH_UNROLL], w1[OH_UNROLL], sh[OH_UNROLL];
@@ -516,7 +519,7 @@ __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(Ha
             unsigned mixmask = 0;  // per warp
 #pragma unroll
             for (int u = 0; u < OH_UNROLL; u++) {
-                const int g = gb + u * (OH_THREADS / 32);
+                const int g = gb + u * (NT / 32);
                 w0[u] = w1[u] = sh[u] = 0;
                 unsigned nv = 15;
                 if (g < n_groups) {
@@ -572,7 +575,7 @@ __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(Ha
                         const uint32_t mk = nib_mask((int)nv);
                         v = (v & mk) | (padnib & ~mk);
                     }
-                    emit8(out_it + u * (OH_THREADS / 32) * (4 * OH_GROUP), rc8(v));  // rc: nibble t = output position j + t, complemented
+                    emit8(out_it + u * (NT / 32) * (4 * OH_GROUP), rc8(v));  // rc: nibble t = output position j + t, complemented
                 }
             }
         }
@@ -581,11 +584,11 @@ __global__ void __launch_bounds__(OH_THREADS, OH_MIN_CTAS) hap_exec_oh_kernel(Ha
         // ---- edge slots, part 2: blend (the copies were started before the group loop) + store ----
         cp_async_wait<0>();
 #pragma unroll 1
-        for (int s_ = tid, rd = 0; s_ < n_slots; s_ += OH_THREADS, rd++) {
+        for (int s_ = tid, rd = 0; s_ < n_slots; s_ += NT, rd++) {
             int e_kind, e_il = 0;
             int32_t e_p;
             uint32_t e_desc = 0;
-            const uint32_t(*sl)[OH_THREADS] = s_edge[rd];
+            const uint32_t(*sl)[NT] = s_edge[rd];
             e_desc = sl[6][tid];
             e_kind = e_desc & 3u;
             e_p = (int32_t)sl[7][tid];

@@ -207,6 +207,12 @@ static int fixed_plan_prepared(gvl_ctx *ctx, const gvl_fixed_job *J, int64_t n, 
         ch = *J->svar2;
         ch.row_slot = A.goi;
     }
+    // every row's list is bounded by max_slot_len: static record slices (no allocation atomics in the plan kernels)
+    ctx->row_stride_hint = J->ref_slot < 0 ? (J->max_slot_len > 1 ? J->max_slot_len : 1) + 1 : 1;
+    struct Unhint {
+        gvl_ctx *c;
+        ~Unhint() { c->row_stride_hint = 0; }
+    } unhint{ctx};
     if ((what & 1) && J->mode >= 0) {
         if (sv)
             rc = gvl_dev_hap_plan_svar2(ctx, J->tab, &ch, A.regions, A.shifts, n, J->rows_p, to_rc, J->output_length, cap,

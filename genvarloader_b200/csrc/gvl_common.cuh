@@ -119,6 +119,7 @@ struct gvl_ctx {
     bool plan_valid;
     int64_t n_work;
     int64_t fixed_len;  // >=0 fixed, -1 ragged
+    int64_t row_stride_hint = 0;    // set around a plan by callers that bound the variant-list length per row (gvl_batch.cu)
     int64_t rec_bound_per_row = 0;  // the plan's record bound / rows (tile length of the one-hot kernel)
     int64_t dir_stride; // directory entries per row of the current plan (0 = no directory)
     int64_t total;      // -1 = unknown (ragged before sync)

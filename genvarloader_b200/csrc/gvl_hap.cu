@@ -49,6 +49,9 @@ struct HapPlanParams {
     int32_t *row_len;
     int32_t *dir;        // fixed-length plans: checkpoint directory (NULL otherwise)
     int64_t dir_stride;  // entries per row = ceil(length / DIR_Q) + 1
+    // > 0: every row owns record slots [k * row_stride, (k + 1) * row_stride) (callers that bound the list length PER ROW: no
+    // cursor atomic, and -- without merged lists -- no completion count either); 0: rows take space from words[W_CURSOR]
+    int64_t row_stride;
     // track mode (hap_plan_par_kernel<NT, true>): 32-byte records, per-query source window lengths
     TRec *trecs;
     const int32_t *track_lengths;
@@ -859,6 +862,7 @@ static int hap_plan_impl(gvl_ctx *ctx, const gvl_sparse_tables *tab, const gvl_s
     P.ploidy = ploidy;
     P.output_length = output_length >= 0 ? output_length : (output_length == -2 ? -2 : -1);
     P.rec_cap = ctx->hap.rec_cap;
+    P.row_stride = (ctx->row_stride_hint > 0 && ctx->row_stride_hint * n_work <= ctx->hap.rec_cap) ? ctx->row_stride_hint : 0;
     P.rows = ctx->hap.rows;
     P.rec = ctx->hap.rec;
     P.words = ctx->dev_words;
@@ -924,6 +928,7 @@ int gvl_trk_plan_launch(gvl_ctx *ctx, const gvl_sparse_tables *tab, const Merged
     P.ploidy = ploidy;
     P.output_length = -2;  // rows sized by the caller's offsets
     P.rec_cap = ctx->trk.trec_cap;
+    P.row_stride = (ctx->row_stride_hint > 0 && ctx->row_stride_hint * n_work <= ctx->trk.trec_cap) ? ctx->row_stride_hint : 0;
     P.rows = ctx->trk.rows;
     P.rec = RecArrays{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     P.words = words;

@@ -166,10 +166,20 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT, GVL_PLAN_OCC / (NT == 32 
     // record workspace of the row: one atomic per row.  Its round trip overlaps with the first gathers: the value
     // stays in thread 0 until the first chunk's loads are in flight (bcast_off below).
     int64_t rec_off = 0;
-    if (t == 0) rec_off = (int64_t)atomicAdd((unsigned long long *)&P.words[W_CURSOR], (unsigned long long)(nvar + 1));
+    const bool static_rows = P.row_stride > 0;  // the row owns a fixed slice: no atomic (81,920 same-address atomics cost cfg4 ~90 us)
+    if (static_rows) rec_off = k * P.row_stride;
+    else if (t == 0) rec_off = (int64_t)atomicAdd((unsigned long long *)&P.words[W_CURSOR], (unsigned long long)(nvar + 1));
+    // (rows of a statically sliced plan that reads no merged lists leave the cursors untouched: nothing to put back)
+    const bool count_done = !static_rows || P.merged.off != nullptr;
     bool have_off = false, overflow = false;
     auto bcast_off = [&]() {
         if (have_off) return;
+        if (static_rows) {
+            overflow = nvar + 1 > P.row_stride;
+            if (overflow && t == 0) atomicMax((unsigned long long *)&P.words[W_STATUS], (unsigned long long)(P.rec_cap + nvar + 1));
+            have_off = true;
+            return;
+        }
         if (NT == 32) {
             rec_off = __shfl_sync(0xffffffffu, rec_off, 0);
         } else {
@@ -434,7 +444,7 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT, GVL_PLAN_OCC / (NT == 32 
             if (TRK) trk_plan_row_serial(P, k, rec_off);
             else plan_row_serial(P, k, rec_off);
         }
-        if (t == 0) plan_row_done(P.words, P.n_work);
+        if (t == 0 && count_done) plan_row_done(P.words, P.n_work);
         return;
     }
     if (TRK) {
@@ -459,7 +469,7 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT, GVL_PLAN_OCC / (NT == 32 
             rp.q_start = (int32_t)q_start;
             P.rows[k] = rp;
             P.row_len[k] = (int32_t)length;
-            plan_row_done(P.words, P.n_work);
+            if (count_done) plan_row_done(P.words, P.n_work);
         }
         return;
     }
@@ -491,6 +501,6 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT, GVL_PLAN_OCC / (NT == 32 
         }
     }
     write_dir<NT>(P, k, rec_off, overflow ? 0 : n_emit, t);
-    if (t == 0) plan_row_done(P.words, P.n_work);
+    if (t == 0 && count_done) plan_row_done(P.words, P.n_work);
 }
 

@@ -7,8 +7,8 @@
 One "step" = one pass of the hot path over ONE batch of synthetic (region, sample) pairs: device-side batch prep,
 plan (variant state machine -> segment table) and execute (fused copy / ALT scatter / pad / RC / one-hot), with every
 input already resident in HBM.  The product path is the read-ahead loader (`genvarloader_b200._pipeline`): `ring`
-consecutive batches are reconstructed by one device call, two ring halves alternate on two streams -- the timed region
-replays exactly that machinery for K batches.  Default workload = BASELINE.json configs[2] / the north-star target:
+consecutive batches are reconstructed by one device call (one CUDA graph: prep -> plan -> execute), two ring halves alternate
+on two streams -- the timed region replays exactly that machinery for K batches.  Default workload = BASELINE.json configs[2] / the north-star target:
 524,288-bp indel-bearing windows, 32 haplotypes per batch, 512 regions on a 300 Mb contig (packed reference 150 MB >
 126 MB L2).  `--workload cfg2` = configs[1].
 

@@ -9,10 +9,11 @@ then plan -> execute (-> tracks) run as in `Dataset.__getitem__`.  Two users:
                                   H2D copy, no per-call pinned allocation).
   * `FixedPipeline` rings      -- the loader reads AHEAD: `ring` consecutive batches are reconstructed as ONE device
                                   call (rows of all batches in one plan launch and one execute launch, so every launch
-                                  fills the GPU for hundreds of microseconds instead of ~10), into two buffer halves
-                                  that are produced alternately on two streams: while the consumer reads the batches
-                                  of one half, the other is being produced.  Rows are independent
-                                  (src/reconstruct/mod.rs:374-422), so batch i of a ring is simply rows
+                                  fills the GPU for hundreds of microseconds instead of ~10), into two buffer halves.
+                                  Each half owns one CUDA graph (prep -> plan -> execute [-> tracks]) replayed on the
+                                  half's own stream: while the consumer reads the batches of one half, the other is being
+                                  produced, and the plan of one call overlaps the execute of the other half's call.  Rows
+                                  are independent (src/reconstruct/mod.rs:374-422), so batch i of a ring is simply rows
                                   [i*b*p, (i+1)*b*p) of the ring's output.  `PipelinedLoader` drives it.
 
 Batches of a ring are views into the ring's output buffers (zero-copy, like `copy=False` of the reference's

@@ -148,3 +148,30 @@ def test_pipelined_loader_subset_jitter_and_fallback(env):
     from genvarloader_b200._dataset import BatchLoader
 
     assert isinstance(ds.with_tracks(False).to_dataloader(batch_size=3, mode="double_buffered"), BatchLoader)
+
+
+def test_getitem_large_batch_and_index_checks(env):
+    """Batches beyond 256 queries take the staged upload of gvl_dev_fixed_run (indices through the context's pinned slots)
+    instead of travelling with the prep launch; both agree with the general path, with and without jitter and tracks.
+    Out-of-range indices are rejected (numpy's fancy indexing for `ds[r, s]`, the library's own check for raw flat indices)."""
+    from genvarloader_b200 import _ffi
+
+    d, ds, O = env
+    rng = np.random.default_rng(5)
+    r, s = rng.integers(0, ds.n_regions, 300), rng.integers(0, ds.n_samples, 300)
+    a = ds.with_tracks(False).with_len(640).with_encoding("onehot")
+    assert _eq(a[r, s], _slow(a)[r, s])
+    assert _eq(a[r[:256], s[:256]], _slow(a)[r[:256], s[:256]])  # the largest inline batch
+    j1 = ds.with_tracks(False).with_len(700).with_settings(jitter=5, rng=3)
+    j2 = _slow(ds.with_tracks(False).with_len(700).with_settings(jitter=5, rng=3))
+    assert _eq(j1[r, s], j2[r, s])
+    t = ds.with_len(512)
+    assert _eq(t[r[:280], s[:280]], _slow(t)[r[:280], s[:280]])
+    with pytest.raises(IndexError):
+        a[np.array([ds.n_regions]), np.array([0])]
+    pipe = a._eager_pipeline(4)
+    with pytest.raises(_ffi.GvlError, match="out of range"):
+        pipe.run_eager(np.array([0, len(ds.full_regions) * len(ds.sample_names)], np.int64), None)
+    big = np.full(300, -1, np.int64)
+    with pytest.raises(_ffi.GvlError, match="out of range"):
+        a._eager_pipeline(300).run_eager(big, None)

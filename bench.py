@@ -540,6 +540,30 @@ def run_b200(args):
                     "genvarloader_b200._kernels.reconstruct_haplotypes_fused(mode='onehot') -> gvl_reconstruct_haplotypes_fused_begin/_finish")
                    + ", host numpy in, pinned host numpy out; every rank runs it on its own PCIe link, value = all ranks' bp / max time"}
 
+    # ---- e2e_loader: the loader delivering into pinned HOST memory (the reference's DataLoader hands out host batches too):
+    #      every ring is copied device-to-host on a copy stream while the next one is produced ----
+    ring_h = max(1, min(ring, int((256 << 20) // max(rows * L * 4, 1))))
+    n_h = ring_h * max(4, min(64, int(np.ceil(1.5e9 / max(ring_h * rows * L * 4, 1)))))
+    order_h = draw_indices(d, n_h * pairs, args.seed + 555, rank, world)
+    loader_h = ds.to_dataloader(batch_size=pairs, sampler=order_h, mode="double_buffered", copy=False, ring=ring_h, to_host=True)
+    for _ in loader_h:  # warm-up epoch: allocates the pinned twins
+        pass
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    nbh = 0
+    for hb in loader_h:
+        nbh += 1
+    eh_t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(eh_t, op=dist.ReduceOp.MAX)
+    e2e_loader = {"value": world * nbh * bp_per_step / float(eh_t.item()), "unit": "bp/s", "batches": nbh, "ring": ring_h,
+                  "h2d_bytes_per_step": pairs * (8 + (4 if w.get("jitter", 0) else 0)), "d2h_bytes_per_step": int(rows * L * 4),
+                  "path": "for batch in Dataset.to_dataloader(batch_size, sampler=..., mode='double_buffered', copy=False, to_host=True): "
+                          "numpy batches in pinned host memory; the device-to-host copy of ring n overlaps the production of ring n+1"}
+    del loader_h
+
     # ---- single-consumer gather over NCCL / NVLink (reported apart from the roofline) ----
     gather = None
     if dist is not None:
@@ -617,7 +641,7 @@ def run_b200(args):
                          "sample": f"{cpu_n} batches ({cpu_s:.1f} s) of the same workload; C restatement of the reference's "
                                    "reconstruct_haplotypes_fused + separate one-hot pass (oracle/gvl_oracle.c), persistent thread pool",
                          "single_thread_value": cpu1_v, "thread_gate": gate},
-        "api": api, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+        "api": api, "e2e": e2e, "e2e_loader": e2e_loader, "gpu_launches": int(launches), "clocks": clk,
     }
     if tracks_line:
         line["tracks"] = tracks_line

@@ -546,7 +546,7 @@ class Dataset:
     # ------------------------------------------------------------------ iteration (reference: to_dataloader, _impl.py:1963-2072)
     def to_dataloader(self, batch_size: int = 1, shuffle: bool = False, sampler=None, num_workers: int = 0, collate_fn=None,
                       pin_memory: bool = False, drop_last: bool = False, generator=None, *, return_indices: bool = False,
-                      transform=None, mode=None, copy: bool = True, ring: int = 0, **ignored):
+                      transform=None, mode=None, copy: bool = True, ring: int = 0, to_host: bool = False, **ignored):
         """Batches over the flat `(region, sample)` index like the reference's DataLoader (which wraps its sampler in a
         `BatchSampler` so that the dataset is indexed with lists of indices, _torch.py:160-228).  The batches are born on
         the GPU, so there are no workers, no pinning and no collation: `num_workers`, `pin_memory`, `collate_fn`,
@@ -558,6 +558,9 @@ class Dataset:
         for ~256 MiB of output), two ring halves produced alternately while the other is consumed (`_pipeline.py`).  `copy=False` hands out zero-copy
         views into the ring that stay valid until `ring` more batches have been drawn (the reference's `copy=False`
         contract: "only valid until the next batch is yielded"); `copy=True` (default) clones every batch.
+        `to_host=True` (pipelined modes): batches are delivered as NUMPY arrays in pinned host memory -- every ring is copied
+        device-to-host on a copy stream while the next one is produced, so a CPU consumer sees the PCIe copy rate instead of
+        copy + compute + launch latency per batch (`copy=False`: views valid until the half comes around again).
         Datasets the pipeline cannot serve (ragged / variable lengths, random shifts, splicing, var_filter) fall back to
         `mode=None`."""
         if sampler is not None and shuffle:
@@ -569,7 +572,7 @@ class Dataset:
 
             if _pipeline.supports(self) is None:
                 return _pipeline.PipelinedLoader(self, int(batch_size), bool(shuffle), sampler, bool(drop_last), generator,
-                                                 bool(return_indices), transform, bool(copy), ring)
+                                                 bool(return_indices), transform, bool(copy), ring, to_host=bool(to_host))
         return BatchLoader(self, int(batch_size), bool(shuffle), sampler, bool(drop_last), generator, bool(return_indices), transform)
 
     # ------------------------------------------------------------------ the hot path

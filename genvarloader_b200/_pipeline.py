@@ -435,7 +435,7 @@ class FixedPipeline:
 class PipelinedLoader:
     """Re-iterable loader over a `Dataset` backed by a `FixedPipeline` (see `Dataset.to_dataloader(mode=...)`)."""
 
-    def __init__(self, ds, batch_size, shuffle, sampler, drop_last, generator, return_indices, transform, copy, ring):
+    def __init__(self, ds, batch_size, shuffle, sampler, drop_last, generator, return_indices, transform, copy, ring, to_host=False):
         self.ds, self.batch_size, self.shuffle, self.sampler = ds, int(batch_size), shuffle, sampler
         self.drop_last, self.return_indices, self.transform, self.copy = drop_last, return_indices, transform, copy
         self._rng = _as_rng(generator)
@@ -446,6 +446,11 @@ class PipelinedLoader:
         ring = max(1, min(int(ring), -(-n_batches // 2)))
         self.pipe = FixedPipeline(ds, self.batch_size, ring=ring)
         self._views = {}
+        # host delivery (`to_host=True`): every ring is copied into a pinned host twin of its half on a copy stream while the other
+        # half is produced; batches are numpy views of that buffer (valid until the half comes around again)
+        self.to_host = bool(to_host)
+        self._host = {}
+        self._copy_stream = torch.cuda.Stream(self.pipe.dev) if self.to_host else None
 
     def __len__(self) -> int:
         n = len(self.sampler) if self.sampler is not None else len(self.ds)
@@ -480,6 +485,9 @@ class PipelinedLoader:
             flat, j, chunks[ring_i] = fill(ring_i)
             pipe.submit(ring_i % pipe.n_halves, flat, j)
         plain = not self.return_indices and self.transform is None
+        if self.to_host:
+            yield from self._iter_host(pipe, chunks, fill, n_rings, K, b, n_s)
+            return
         for ring_i in range(n_rings):
             h = ring_i % pipe.n_halves
             out = pipe.acquire(h)
@@ -514,6 +522,59 @@ class PipelinedLoader:
             if nxt < n_rings:
                 flat, j, chunks[nxt] = fill(nxt)
                 pipe.submit(h, flat, j)
+
+
+    # ------------------------------------------------------------------ host delivery
+    def _host_half(self, h: int):
+        """Pinned host twin of half h's output buffers (+ the event of its last copy)."""
+        ent = self._host.get(h)
+        if ent is None:
+            out = self.pipe.halves[h].out
+            bufs = {k: torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for k in ("seq", "av", "ap", "trk")
+                    if (t := getattr(out, k)) is not None}
+            twin = _Out.__new__(_Out)
+            twin.spec, twin.b = out.spec, out.b
+            twin.seq, twin.av, twin.ap, twin.trk = (bufs.get(k) for k in ("seq", "av", "ap", "trk"))
+            ent = self._host[h] = (twin, torch.cuda.Event(), bufs)
+        return ent
+
+    def _iter_host(self, pipe, chunks, fill, n_rings, K, b, n_s):
+        cs = self._copy_stream
+
+        def start_copy(h):  # device half -> pinned twin, on the copy stream, as soon as the half is produced
+            H = pipe.halves[h]
+            twin, ev, bufs = self._host_half(h)
+            cs.wait_event(H.done)
+            with torch.cuda.stream(cs):
+                for k, dst in bufs.items():
+                    dst.copy_(getattr(H.out, k), non_blocking=True)
+            ev.record(cs)
+            H.free = ev  # the device half may be refilled once its copy has left
+
+        for ring_i in range(min(pipe.n_halves, n_rings)):
+            start_copy(ring_i % pipe.n_halves)
+        for ring_i in range(n_rings):
+            h = ring_i % pipe.n_halves
+            twin, ev, _ = self._host_half(h)
+            ev.synchronize()  # the ring is in host memory
+            chunk = chunks.pop(ring_i)
+            for lo in range(0, len(chunk), b):
+                m = min(b, len(chunk) - lo)
+                batch = twin.result(lo, m, clone=self.copy)
+                batch = tuple(x.numpy() if isinstance(x, torch.Tensor) else x for x in (batch if isinstance(batch, tuple) else (batch,)))
+                if self.return_indices:
+                    c = chunk[lo: lo + m]
+                    batch = (*batch, c // n_s, c % n_s)
+                if self.transform is not None:
+                    batch = self.transform(*batch)
+                elif len(batch) == 1:
+                    batch = batch[0]
+                yield batch
+            nxt = ring_i + pipe.n_halves
+            if nxt < n_rings:  # (the consumer is past every batch of this half: its pinned twin may be overwritten)
+                flat, j, chunks[nxt] = fill(nxt)
+                pipe.submit(h, flat, j)
+                start_copy(h)
 
 
 def _as_rng(generator):

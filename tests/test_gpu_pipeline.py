@@ -175,3 +175,23 @@ def test_getitem_large_batch_and_index_checks(env):
     big = np.full(300, -1, np.int64)
     with pytest.raises(_ffi.GvlError, match="out of range"):
         a._eager_pipeline(300).run_eager(big, None)
+
+
+def test_loader_delivers_host_batches(env):
+    """`to_dataloader(..., to_host=True)`: numpy batches out of pinned host memory, equal to indexing the dataset, for
+    sequences and for sequences + realigned tracks, full and partial last rings / batches."""
+    d, ds, O = env
+    a = ds.with_tracks(False).with_len(768).with_encoding("onehot")
+    n = len(a)
+    got = [x.copy() for x in a.to_dataloader(batch_size=5, mode="double_buffered", copy=False, ring=3, to_host=True)]
+    assert all(isinstance(x, np.ndarray) for x in got)
+    idx = np.arange(n)
+    exp = a[idx // a.n_samples, idx % a.n_samples].cpu().numpy()
+    assert (np.concatenate(got) == exp).all()
+    t = ds.with_len(640)
+    k = 0
+    for x, tr, r, s in t.to_dataloader(batch_size=4, mode="buffered", ring=2, to_host=True, return_indices=True):
+        ex, et = t[r, s]
+        assert (x == ex.cpu().numpy()).all() and (tr.view(np.uint32) == et.cpu().numpy().view(np.uint32)).all()
+        k += len(r)
+    assert k == len(t)

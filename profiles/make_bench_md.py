@@ -13,13 +13,13 @@ order = ['cfg3_s20', 'cfg3_s640', 'cfg2_s20', 'cfg2_s640', 'cfg1_s20', 'cfg1_s64
 out = ["# Round 2: bench lines of the final library (one B200 unless noted; `profiles/scripts/r2_final2.sh`, `r2_multi8.sh`)", "",
        "Full JSON lines: `profiles/r2_bench/*.json` (this table: `python profiles/make_bench_md.py`).  `python bench.py --steps K --warmup W "
        "[--workload ...]`; clocks 1,965 MHz, no throttle reasons in any run.", "",
-       "| run | bp/s (`value`) | µs/step | `whole_step_frac` | `roofline.frac` (one execute launch) | execute launch | prep + plan (+ merge) | `api` bp/s | `e2e` bp/s | CPU port, 16 threads | tracks leg: µs/step, frac |",
+       "| run | bp/s (`value`) | µs/step | `whole_step_frac` | `roofline.frac` (one execute launch) | execute launch | prep + plan (+ merge) | `api` bp/s | `e2e` bp/s (per call / host-delivering loader) | CPU port, 16 threads | tracks leg: µs/step, frac |",
        "|---|---|---|---|---|---|---|---|---|---|---|"]
 for k in order:
     d = get(k); r = d['roofline']; t = d.get('tracks') or {}
     out.append(f"| {k.replace('_s', ' @ ')} steps | {d['value']:.3e} | {d['ms_per_step'] * 1e3:.2f} | {d['whole_step_frac']:.3f} | {r['frac']:.3f} | "
                f"{r['launch_ms'] * 1e3:.0f} µs / {r['batches_per_launch']} batches | {r['plan_kernel_ms'] * 1e3:.0f} µs | {d['api']['value']:.3e} | "
-               f"{d['e2e']['value']:.3e} | {d['cpu_baseline']['value']:.2e} | "
+               f"{d['e2e']['value']:.3e} / {(d.get('e2e_loader') or {}).get('value', float('nan')):.3e} | {d['cpu_baseline']['value']:.2e} | "
                + (f"{t['ms_per_step'] * 1e3:.1f}, {t['whole_step_frac']:.3f}" if t else "") + " |")
 out.append("")
 out.append("`roofline.frac` and `whole_step_frac` use SURVEY.md's 5 algorithmic bytes per bp against the measured read+write copy peak "

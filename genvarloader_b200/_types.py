@@ -55,7 +55,7 @@ class Ragged:
 
     def to_padded(self, pad_value: Any) -> torch.Tensor:
         """Right-pad every row to the longest one (reference `to_padded`, _ragged.py:281-314 ->
-        src/ragged/mod.rs:7-23): pre-fill with the pad value, then gvl_dev_ragged_to_padded copies the rows."""
+        src/ragged/mod.rs:7-23): gvl_dev_ragged_to_padded_fill copies the rows and writes the pad item behind them in one pass."""
         import ctypes as C
 
         from ._engine import _stream
@@ -67,14 +67,23 @@ class Ragged:
         n_rows = lens.numel()
         max_len = int(lens.max().item()) if n_rows else 0
         dev = self.data.device
-        out = torch.full((n_rows, max_len, *self.data.shape[1:]), pad_value, dtype=self.data.dtype, device=dev)
+        # one pass: the kernel copies the rows AND writes the pad item behind them (no torch.full pre-fill of the whole output)
+        out = torch.empty((n_rows, max_len, *self.data.shape[1:]), dtype=self.data.dtype, device=dev)
         if n_rows and max_len:
             data, offsets = self.data.contiguous(), self.offsets.contiguous()
             itemsize = data.element_size() * int(np.prod(data.shape[1:], dtype=np.int64))  # one-hot rows: 4 bytes per position
+            np_dt = {torch.uint8: np.uint8, torch.int32: np.int32, torch.float32: np.float32, torch.int64: np.int64}[data.dtype]
+            pad_item = np.full(tuple(data.shape[1:]) or (1,), pad_value, np_dt).tobytes()
             with torch.cuda.device(dev):
-                check(lib.gvl_dev_ragged_to_padded(default_ctx(dev.index or 0).handle, ptr(data), ptr(offsets),
-                                                   C.c_int64(n_rows), ptr(out), C.c_int64(itemsize), C.c_int64(max_len),
-                                                   _stream()))
+                if len(pad_item) <= 8:
+                    check(lib.gvl_dev_ragged_to_padded_fill(default_ctx(dev.index or 0).handle, ptr(data), ptr(offsets),
+                                                            C.c_int64(n_rows), ptr(out), C.c_int64(itemsize), C.c_int64(max_len),
+                                                            C.c_char_p(pad_item), _stream()))
+                else:  # (items wider than 8 bytes: pre-fill, then copy)
+                    out.fill_(pad_value)
+                    check(lib.gvl_dev_ragged_to_padded(default_ctx(dev.index or 0).handle, ptr(data), ptr(offsets),
+                                                       C.c_int64(n_rows), ptr(out), C.c_int64(itemsize), C.c_int64(max_len),
+                                                       _stream()))
         return out.reshape(*outer, max_len, *self.data.shape[1:])
 
     def to_numpy(self):

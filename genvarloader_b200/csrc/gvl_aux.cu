@@ -4,6 +4,8 @@
 //   ragged_to_padded        (src/ragged/mod.rs:7-23, seqpro-core Ragged::to_padded_into)  "variable" output shaping
 // All three are bandwidth-trivial next to reconstruction; they exist so that the whole per-batch path stays on the
 // device and in this library (no host round trip, no framework ops between plan and execute).
+#include <cstring>
+
 #include "gvl_internal.cuh"
 
 using namespace gvl;
@@ -89,7 +91,10 @@ __global__ void __launch_bounds__(256) exonic_keep_kernel(gvl_sparse_tables tab,
 __global__ void __launch_bounds__(256) ragged_to_padded_kernel(const uint8_t *__restrict__ data,
                                                                const int64_t *__restrict__ offsets, int64_t n_rows,
                                                                uint8_t *__restrict__ out, int64_t itemsize,
-                                                               int64_t out_len, int64_t words_per_row) {
+                                                               int64_t out_len, int64_t words_per_row, int fill,
+                                                               uint64_t pad_bits) {
+    // fill != 0: the kernel also writes the pad item (itemsize <= 8 bytes, little endian in pad_bits) behind every row, so the
+    // caller needs no pre-fill pass over the whole output
     const int64_t n_units = n_rows * words_per_row;
     const int64_t row_bytes = out_len * itemsize;
     for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += (int64_t)gridDim.x * blockDim.x) {
@@ -97,6 +102,11 @@ __global__ void __launch_bounds__(256) ragged_to_padded_kernel(const uint8_t *__
         const int64_t o_s = offsets[r];
         const int64_t n_bytes = imin64(offsets[r + 1] - o_s, out_len) * itemsize;  // bytes of this row that are copied
         const int64_t b0 = w * 4;
+        if (fill) {  // pad bytes of this unit: [max(b0, n_bytes), min(b0 + 4, row_bytes))
+            uint8_t *row = out + r * row_bytes;
+            for (int64_t b = imax64(b0, n_bytes); b < imin64(b0 + 4, row_bytes); b++)
+                row[b] = (uint8_t)(pad_bits >> (8 * (b % itemsize)));
+        }
         if (b0 >= n_bytes) continue;
         const uint8_t *src = data + o_s * itemsize + b0;
         uint8_t *dst = out + r * row_bytes + b0;
@@ -161,8 +171,24 @@ int gvl_dev_choose_exonic_variants(gvl_ctx *ctx, const gvl_sparse_tables *tab, c
     return GVL_OK;
 }
 
+static int ragged_to_padded_impl(gvl_ctx *ctx, const void *data, const int64_t *offsets, int64_t n_rows, void *out, int64_t itemsize,
+                                 int64_t out_len, int fill, uint64_t pad_bits, gvl_stream stream);
+
 int gvl_dev_ragged_to_padded(gvl_ctx *ctx, const void *data, const int64_t *offsets, int64_t n_rows, void *out,
                              int64_t itemsize, int64_t out_len, gvl_stream stream) {
+    return ragged_to_padded_impl(ctx, data, offsets, n_rows, out, itemsize, out_len, 0, 0, stream);
+}
+
+int gvl_dev_ragged_to_padded_fill(gvl_ctx *ctx, const void *data, const int64_t *offsets, int64_t n_rows, void *out,
+                                  int64_t itemsize, int64_t out_len, const void *pad_item, gvl_stream stream) {
+    if (!pad_item || itemsize < 1 || itemsize > 8) return fail(GVL_ERR_ARG, "gvl_dev_ragged_to_padded_fill: pad item of 1..8 bytes");
+    uint64_t bits = 0;
+    memcpy(&bits, pad_item, (size_t)itemsize);
+    return ragged_to_padded_impl(ctx, data, offsets, n_rows, out, itemsize, out_len, 1, bits, stream);
+}
+
+static int ragged_to_padded_impl(gvl_ctx *ctx, const void *data, const int64_t *offsets, int64_t n_rows, void *out, int64_t itemsize,
+                                 int64_t out_len, int fill, uint64_t pad_bits, gvl_stream stream) {
     if (!ctx) return fail(GVL_ERR_ARG, "gvl_dev_ragged_to_padded: ctx is NULL");
     if (n_rows < 0 || itemsize < 1 || out_len < 0) return fail(GVL_ERR_ARG, "gvl_dev_ragged_to_padded: bad sizes");
     if (n_rows == 0 || out_len == 0) return GVL_OK;
@@ -172,7 +198,7 @@ int gvl_dev_ragged_to_padded(gvl_ctx *ctx, const void *data, const int64_t *offs
     const int64_t n_units = n_rows * words_per_row;
     const int64_t blocks = imin64((n_units + 255) / 256, 148 * 32);
     ragged_to_padded_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-        (const uint8_t *)data, offsets, n_rows, (uint8_t *)out, itemsize, out_len, words_per_row);
+        (const uint8_t *)data, offsets, n_rows, (uint8_t *)out, itemsize, out_len, words_per_row, fill, pad_bits);
     GVL_LAUNCH_CHECK();
     return GVL_OK;
 }

@@ -312,6 +312,10 @@ int gvl_dev_get_reference(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int3
  * caller, exactly like the reference.  Device pointers, any alignment. */
 int gvl_dev_ragged_to_padded(gvl_ctx *ctx, const void *data, const int64_t *offsets, int64_t n_rows, void *out,
                              int64_t itemsize, int64_t out_len, gvl_stream stream);
+/* The same with the padding written by the kernel: `out` may be uninitialised, `pad_item` is a HOST pointer to one item
+ * (itemsize <= 8 bytes).  One pass over the output instead of pre-fill + copy. */
+int gvl_dev_ragged_to_padded_fill(gvl_ctx *ctx, const void *data, const int64_t *offsets, int64_t n_rows, void *out,
+                                  int64_t itemsize, int64_t out_len, const void *pad_item, gvl_stream stream);
 
 /* ---- device layer: batch preparation (the host prep of the reference, on the device) --- */
 /* Per-replica region table for gvl_dev_batch_prep: the reference's `_full_regions` (int32 (R,4): contig index, start,

@@ -62,6 +62,11 @@ WORKLOADS = {
 }
 
 
+# (profiles/sweep_cfg5_r2.py: one extra workload described by the environment, e.g. a cell of the configs[4] sweep)
+if os.environ.get("GVL_BENCH_CUSTOM"):
+    WORKLOADS["custom"] = json.loads(os.environ["GVL_BENCH_CUSTOM"])
+
+
 def build_workload(name: str, seed: int):
     from genvarloader_b200 import synth
 

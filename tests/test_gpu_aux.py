@@ -119,6 +119,38 @@ def test_ragged_to_padded_vs_oracle(K, O, dtype, out_len):
         K.ragged_to_padded(data, oo, got[:, ::2], dtype.itemsize, out_len)
 
 
+@pytest.mark.parametrize("dtype", ["u1", "<u2", "<i4", "<f4", "<i8"])
+def test_ragged_to_padded_fill_writes_the_padding_itself(O, dtype):
+    """gvl_dev_ragged_to_padded_fill: rows AND padding in one pass over an UNINITIALISED output (what `Ragged.to_padded`
+    calls), against the oracle's pre-fill + copy, for every item size up to 8 bytes and unaligned row starts."""
+    import ctypes as C
+
+    import torch
+
+    from genvarloader_b200._engine import _stream
+    from genvarloader_b200._ffi import check, lib, ptr
+    from genvarloader_b200._kernels import default_ctx
+
+    dtype = np.dtype(dtype)
+    rng = np.random.default_rng(dtype.itemsize)
+    for out_len in (1, 7, 33, 130):
+        n_rows = 41
+        lens = rng.integers(0, 2 * out_len, n_rows)
+        lens[[0, 3, 8]] = [0, out_len, out_len + 1]
+        oo = (5 + np.concatenate([[0], np.cumsum(lens)])).astype(np.int64)
+        data = rng.integers(0, 256, int(oo[-1] + 3) * dtype.itemsize, dtype=np.uint8).view(dtype)
+        pad = rng.integers(0, 256, dtype.itemsize, dtype=np.uint8)
+        exp = np.tile(pad, n_rows * out_len).view(dtype).reshape(n_rows, out_len).copy()
+        O.ragged_to_padded(data, oo, exp, dtype.itemsize, out_len)
+        dev = torch.device("cuda", 0)
+        d_data = torch.from_numpy(data.view(np.uint8).copy()).to(dev)
+        d_oo = torch.from_numpy(oo).to(dev)
+        d_out = torch.full((n_rows * out_len * dtype.itemsize,), 0xAB, dtype=torch.uint8, device=dev)  # (garbage, not the pad)
+        check(lib.gvl_dev_ragged_to_padded_fill(default_ctx(0).handle, ptr(d_data), ptr(d_oo), C.c_int64(n_rows), ptr(d_out),
+                                                C.c_int64(dtype.itemsize), C.c_int64(out_len), C.c_char_p(pad.tobytes()), _stream()))
+        assert d_out.cpu().numpy().tobytes() == exp.tobytes(), (dtype, out_len)
+
+
 @pytest.mark.parametrize("vkb,use_keep", [(2.0, False), (15.0, True)])
 def test_spliced_fused_vs_oracle(K, O, vkb, use_keep):
     """The splice entries: permuted exon elements (ploidy-1 rows) with caller-sized rows, per-element RC;

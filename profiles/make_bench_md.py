@@ -30,11 +30,11 @@ for k in ['ref_cfg3_s20', 'ref_cfg2_s20']:
     d = get(k)
     out.append(f"* `--impl reference` {k[4:].replace('_s', ' @ ')} steps: {d['value']:.3e} bp/s ({d['cpu_baseline']['cores']} threads; "
                f"{d['cpu_baseline']['sample'][:110]}...)")
-out += ["", "## 8 GPUs (one box, torchrun, NCCL barrier; `value` = all ranks' bp / max time)", "",
+out += ["", "## 2 and 8 GPUs (one box, torchrun, NCCL barrier; `value` = all ranks' bp / max time)", "",
         "| run | bp/s | × one GPU | per-rank block ms | `e2e` bp/s (every rank on its own PCIe link, max time) | gather of a ring's outputs to rank 0 |",
         "|---|---|---|---|---|---|"]
 one = {'s20': get('cfg3_s20')['value'], 's640': get('cfg3_s640')['value']}
-for k, s_ in (('cfg3_s20_n8', 's20'), ('cfg3_s640_n8', 's640')):
+for k, s_ in (('cfg3_s20_n2', 's20'), ('cfg3_s20_n8', 's20'), ('cfg3_s640_n8', 's640')):
     d = get(k); g = d['gather']
     out.append(f"| {k} | {d['value']:.3e} | {d['value'] / one[s_]:.2f} | {min(d['per_rank_ms']):.3f}–{max(d['per_rank_ms']):.3f} | "
                f"{d['e2e']['value']:.3e} | {g['ms_per_device_call']:.1f} ms per {g['batches']} batches, {g['consumer_ingest_GBps']:.0f} GB/s into rank 0 |")

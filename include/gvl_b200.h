@@ -380,7 +380,8 @@ typedef struct gvl_fixed_job {
     int64_t output_length;
     int64_t ref_slot;                 /* >= 0: every row reads this (empty) genotype slot; < 0: haplotypes */
     int64_t n_tracks;
-    int64_t max_slot_len;             /* upper bound of one row's variant-list length (plan workspace = rows * this) */
+    int64_t max_slot_len;             /* upper bound of one row's variant-list length: the plan workspace is rows * (this + 1) and every
+                                       * row owns a static slice of it (no allocation atomics in the plan kernels) */
     int64_t typ_slot_len;             /* typical (about twice the mean) variant-list length of a row: a HINT for the one-hot execute
                                        * kernel's tile length where the bound is loose (svar2: the bound counts the cohort's whole dense
                                        * window); 0 = use the bound */

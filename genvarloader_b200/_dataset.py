@@ -191,6 +191,88 @@ class Dataset:
     def is_subset(self) -> bool:
         return self.region_subset is not None or self.sample_subset is not None
 
+    # ---- what the dataset holds (reference: _impl.py:954-1110, 1234-1340, 1848-1895) ----
+    @property
+    def has_reference(self) -> bool:
+        return True  # (an Engine always holds a reference; datasets without one are not opened here)
+
+    @property
+    def has_genotypes(self) -> bool:
+        return self.engine.svar2 is not None or int(self.engine.alt_offsets.numel()) > 1  # (a variant table with entries)
+
+    @property
+    def has_intervals(self) -> bool:
+        return bool(self.track_kinds)
+
+    def __repr__(self) -> str:
+        return (f"GVL dataset (B200-resident) with shape {self.shape}: sequences={self.sequence_type!r}, tracks={list(self.active_tracks)}, "
+                f"output_length={self.output_length!r}, jitter={self.jitter} (max {self.max_jitter}), deterministic={self.deterministic}, "
+                f"rc_neg={self.rc_neg}, is_subset={self.is_subset}, is_spliced={self.is_spliced}")
+
+    def _shape_counts(self, x: np.ndarray, squeeze: bool, out_reshape):
+        if squeeze:
+            x = x.squeeze(0)
+        if out_reshape is not None:
+            x = x.reshape(*out_reshape, x.shape[-1])
+        return x
+
+    def n_variants(self, regions=None, samples=None) -> np.ndarray:
+        """`Dataset.n_variants`, _impl.py:1293-1340: variants per (region, sample, ploid) -> int32 (..., ploidy)."""
+        ds_idx, squeeze, out_reshape = self._parse_idx((slice(None) if regions is None else regions,
+                                                        slice(None) if samples is None else samples))
+        p = self.ploidy
+        goi = ds_idx[:, None] * p + np.arange(p, dtype=np.int64)[None, :]
+        if self.engine.svar2 is not None:
+            raise NotImplementedError("n_variants of an svar2-backed dataset needs the presence-bit popcounts (not kept on the host)")
+        go = self.engine.geno_offsets_host
+        n = np.maximum(go[1, goi] - go[0, goi], 0).astype(np.int32)
+        return self._shape_counts(n, squeeze, out_reshape)
+
+    def n_intervals(self, regions=None, samples=None) -> np.ndarray:
+        """`Dataset.n_intervals`, _impl.py:1848-1895: stored intervals per (region, sample) and ACTIVE track -> int32 (..., tracks)."""
+        ds_idx, squeeze, out_reshape = self._parse_idx((slice(None) if regions is None else regions,
+                                                        slice(None) if samples is None else samples))
+        if not self.active_tracks:
+            return self._shape_counts(np.zeros((len(ds_idx), 0), np.int32), squeeze, out_reshape)
+        r_idx = ds_idx // len(self.sample_names)
+        cols = []
+        for name in self.active_tracks:
+            off = self._cache.get(("itv_off", name))
+            if off is None:
+                off = self._cache[("itv_off", name)] = self.engine.tracks[name][3].cpu().numpy()
+            slot = r_idx if self.track_kinds[name] == "annot" else ds_idx
+            cols.append((off[slot + 1] - off[slot]).astype(np.int32))
+        return self._shape_counts(np.stack(cols, -1), squeeze, out_reshape)
+
+    def haplotype_lengths(self, regions=None, samples=None):
+        """`Dataset.haplotype_lengths`, _impl.py:1234-1291: lengths of the JITTER-EXTENDED haplotypes -> int32 (..., ploidy);
+        None when the lengths are not a fixed property of the dataset (no genotypes, random shifts)."""
+        if self.splice_rows is not None:
+            raise NotImplementedError("Haplotype lengths are not yet implemented for spliced datasets.")
+        if not self.has_genotypes or not self.deterministic:
+            return None
+        ds_idx, squeeze, out_reshape = self._parse_idx((slice(None) if regions is None else regions,
+                                                        slice(None) if samples is None else samples))
+        eng, dev, p = self.engine, self.engine.device, self.ploidy
+        reg = self.full_regions[ds_idx // len(self.sample_names)].copy()
+        reg[:, 1] -= self.jitter
+        reg[:, 2] += self.jitter
+        goi = ds_idx[:, None] * p + np.arange(p, dtype=np.int64)[None, :]
+        t_reg = torch.from_numpy(np.ascontiguousarray(reg[:, :3])).to(dev)
+        t_goi = torch.from_numpy(goi).to(dev)
+        keep = keep_off = None
+        if self.var_filter == "exonic":
+            keep, keep_off = self._exonic_keep(t_goi, t_reg, goi)
+        d = eng.get_diffs(t_goi, t_reg[:, 1].contiguous(), t_reg[:, 2].contiguous(), keep, keep_off, regions=t_reg,
+                          max_records=eng.max_records(goi)).cpu().numpy()
+        lens = ((reg[:, 2] - reg[:, 1])[:, None] + d).astype(np.int32)
+        return self._shape_counts(lens, squeeze, out_reshape)
+
+    def to_torch_dataset(self, return_indices: bool = False, transform=None):
+        """`Dataset.to_torch_dataset`, _impl.py:1940-1961 -> `TorchDataset`, _torch.py:272-307: a map-style dataset over the flat
+        (region, sample) index; an int or a list of ints selects a batch (the batches are CUDA tensors)."""
+        return _MapDataset(self, bool(return_indices), transform)
+
     @property
     def regions(self) -> np.ndarray:
         return self.full_regions[self._r_idx]
@@ -831,3 +913,25 @@ class BatchLoader:
             elif len(batch) == 1:
                 batch = batch[0]
             yield batch
+
+
+class _MapDataset:
+    """Map-style view of a Dataset (reference `TorchDataset`, _torch.py:272-307); usable with torch.utils.data.DataLoader
+    (batch_size=None + a BatchSampler, as the reference's own loader does)."""
+
+    def __init__(self, dataset: Dataset, include_indices: bool, transform):
+        self.dataset, self.include_indices, self.transform = dataset, include_indices, transform
+
+    def __len__(self) -> int:
+        return len(self.dataset)
+
+    def __getitem__(self, idx):
+        r_idx, s_idx = np.unravel_index(idx, self.dataset.shape)
+        batch = self.dataset[r_idx, s_idx]
+        if not isinstance(batch, tuple):
+            batch = (batch,)
+        if self.include_indices:
+            batch = (*batch, r_idx, s_idx)
+        if self.transform is not None:
+            return self.transform(*batch)
+        return batch[0] if len(batch) == 1 else batch

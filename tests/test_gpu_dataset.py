@@ -216,3 +216,30 @@ def test_to_dataloader_batches_match_direct_indexing(env):
     assert n == len(dsl) and len(dl) == -(-len(dsl) // 7)
     sh = dsl.to_dataloader(batch_size=16, shuffle=True, drop_last=True, generator=3)
     assert sum(b.shape[0] for b in sh) == (len(dsl) // 16) * 16
+
+
+def test_read_side_helpers_like_the_reference(env):
+    """n_variants / n_intervals / haplotype_lengths / to_torch_dataset / has_* (reference _impl.py:954-1110, 1234-1340,
+    1848-1895, _torch.py:272-307) against the synthetic tables and the dataset's own ragged output."""
+    d, ds, O, _ = env
+    assert ds.has_reference and ds.has_genotypes and ds.has_intervals and "shape" in repr(ds)
+    r, s = np.array([0, 3, 5, 3]), np.array([1, 0, 2, 0])
+    goi = (r[:, None] * d.n_samples + s[:, None]) * d.ploidy + np.arange(d.ploidy)[None, :]
+    go = np.asarray(d.geno_offsets).reshape(2, -1) if np.asarray(d.geno_offsets).ndim == 2 else np.stack([d.geno_offsets[:-1], d.geno_offsets[1:]])
+    assert (ds.n_variants(r, s) == (go[1, goi] - go[0, goi])).all()
+    assert ds.n_variants().shape == (ds.n_regions, ds.n_samples, d.ploidy) and ds.n_variants(2, 1).shape == (d.ploidy,)
+    ni = ds.n_intervals(r, s)
+    assert ni.shape == (4, len(ds.active_tracks))
+    for t, name in enumerate(ds.active_tracks):
+        off = np.asarray(d.tracks[name][3])
+        slot = r * d.n_samples + s
+        assert (ni[:, t] == off[slot + 1] - off[slot]).all()
+    # haplotype lengths = row lengths of the ragged output (jitter 0), and grow by 2 * jitter with it
+    rag = ds.with_tracks(False).with_len("ragged")[r, s]
+    lens = (rag.offsets[1:] - rag.offsets[:-1]).cpu().numpy().reshape(4, d.ploidy)
+    assert (ds.haplotype_lengths(r, s) == lens).all()
+    assert ds.with_settings(deterministic=False).haplotype_lengths(r, s) is None
+    tds = ds.with_tracks(False).with_len(512).to_torch_dataset(return_indices=True)
+    x, ri, si = tds[[0, 7, 9]]
+    assert len(tds) == len(ds) and x.shape[0] == 3 and (ri == np.array([0, 7, 9]) // ds.n_samples).all()
+    assert (x == ds.with_tracks(False).with_len(512)[ri, si]).all()

@@ -30,17 +30,17 @@ for k in ['ref_cfg3_s20', 'ref_cfg2_s20']:
     d = get(k)
     out.append(f"* `--impl reference` {k[4:].replace('_s', ' @ ')} steps: {d['value']:.3e} bp/s ({d['cpu_baseline']['cores']} threads; "
                f"{d['cpu_baseline']['sample'][:110]}...)")
-out += ["", "## 2 and 8 GPUs (one box, torchrun, NCCL barrier; `value` = all ranks' bp / max time)", "",
+out += ["", "## 2, 4 and 8 GPUs (one box, torchrun, NCCL barrier; `value` = all ranks' bp / max time)", "",
         "| run | bp/s | × one GPU | per-rank block ms | `e2e` bp/s (every rank on its own PCIe link, max time) | gather of a ring's outputs to rank 0 |",
         "|---|---|---|---|---|---|"]
 one = {'s20': get('cfg3_s20')['value'], 's640': get('cfg3_s640')['value']}
-for k, s_ in (('cfg3_s20_n2', 's20'), ('cfg3_s20_n8', 's20'), ('cfg3_s640_n8', 's640')):
+for k, s_ in (('cfg3_s20_n2', 's20'), ('cfg3_s20_n4', 's20'), ('cfg3_s20_n8', 's20'), ('cfg3_s640_n8', 's640')):
     d = get(k); g = d['gather']
     out.append(f"| {k} | {d['value']:.3e} | {d['value'] / one[s_]:.2f} | {min(d['per_rank_ms']):.3f}–{max(d['per_rank_ms']):.3f} | "
                f"{d['e2e']['value']:.3e} | {g['ms_per_device_call']:.1f} ms per {g['batches']} batches, {g['consumer_ingest_GBps']:.0f} GB/s into rank 0 |")
 out += ["", "(The 20-step 8-GPU line is the max over ranks of ONE 0.33 ms block per rank: in this run one rank's block took 0.365 ms against",
         "0.324–0.328 for the other seven; the run before it, on another box and a library a few commits older, read 8.18 × 10¹² = 7.8 × one GPU.)"]
-out += ["", "`e2e` does not scale with the GPU count (2.4 × 10¹⁰ bp/s on 8 ranks against 1.3 × 10¹⁰ on one): eight ranks copying one-hot",
+out += ["", "`e2e` stops scaling beyond two GPUs (2.6 × 10¹⁰ bp/s on 2 ranks, 1.9 × 10¹⁰ on 4, 2.4 × 10¹⁰ on 8, against 1.3 × 10¹⁰ on one): eight ranks copying one-hot",
         "bytes into pinned host memory at once share the host's memory system — the reason the product is the GPU-resident loader.", "",
         "Other measurements of the same run: `Dataset.__getitem__` host time 27 µs per call on the cfg2 and cfg3 shapes "
         "(`profiles/probe_dataset.py`); one realign call on the cfg3 shape 76.4 µs (`profiles/probe_tracks.py`)."]

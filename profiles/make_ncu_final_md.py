@@ -46,6 +46,6 @@ L += ["", f"Execute kernel, steady state (launches after the first): {rd:.0f} MB
       "The write count sits a little under the 1,342 MB the launch stores because the last ~60 MB are still dirty in L2 when the kernel ends.",
       "Shared memory: the conflicts are all on loads (28.95 M of 43.3 M load wavefronts) -- the 256-entry byte -> 8 one-hot bytes table of `emit8`, read at data-dependent addresses by 4 `LDS.64` per lane."
       "  With the kernel at the store-bandwidth bound (issue active 59 %, barrier stall 0.78 per issue -- round 1: one launch per batch, 0.38-0.45) they are not the limiter;"
-      " the table-free spread is kept as the `GVL_EXP & 4` timing switch and did not move the launch time."]
+      " `GVL_EXP & 4` is the build switch that times the kernel without the lookups."]
 open("profiles/r2_ncu_final.md", "w").write("\n".join(L) + "\n")
 print("\n".join(L))

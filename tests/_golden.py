@@ -25,6 +25,10 @@ def load_golden(name: str) -> list:
     for ci in range(n_cases):
         none = set(z[f"c{ci}_none"].tolist())
         inputs = tuple(None if j in none else _unbox(z[f"c{ci}_a{j}"]) for j in range(n_args))
+        if n_gold < 0:  # dict-valued golden (assemble_variant_buffers): {field: (data, seq_offsets)} in the reference's order
+            names = [str(x) for x in z[f"c{ci}_gnames"]]
+            cases.append((inputs, {nm: (z[f"c{ci}_g{2 * j}"], z[f"c{ci}_g{2 * j + 1}"]) for j, nm in enumerate(names)}))
+            continue
         gold = tuple(_unbox(z[f"c{ci}_g{j}"]) for j in range(n_gold))
         cases.append((inputs, gold if n_gold > 1 else gold[0]))
     return cases

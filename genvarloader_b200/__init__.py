@@ -3,7 +3,8 @@
 from ._insertion_fill import Constant, FlankSample, InsertionFill, Interpolate, Repeat5p, Repeat5pNormalized
 
 __all__ = ["Dataset", "Engine", "AnnotatedHaps", "Ragged", "RaggedAnnotatedHaps", "InsertionFill", "Repeat5p",
-           "Repeat5pNormalized", "Constant", "FlankSample", "Interpolate", "Reference"]
+           "Repeat5pNormalized", "Constant", "FlankSample", "Interpolate", "Reference", "DummyVariant", "RaggedAlleles",
+           "RaggedVariants"]
 
 
 def __getattr__(name):  # torch + the CUDA library are loaded on first use
@@ -19,7 +20,7 @@ def __getattr__(name):  # torch + the CUDA library are loaded on first use
         from ._engine import Engine
 
         return Engine
-    if name in ("AnnotatedHaps", "Ragged", "RaggedAnnotatedHaps"):
+    if name in ("AnnotatedHaps", "Ragged", "RaggedAnnotatedHaps", "DummyVariant", "RaggedAlleles", "RaggedVariants"):
         from . import _types
 
         return getattr(_types, name)

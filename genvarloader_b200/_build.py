@@ -16,7 +16,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "_lib" / os.environ.get("GVL_LIB_NAME", "libgvl_b200.so")
-SOURCES = ["gvl_ctx.cu", "gvl_hap.cu", "gvl_svar2.cu", "gvl_tracks.cu", "gvl_aux.cu", "gvl_batch.cu", "gvl_host.cu"]
+SOURCES = ["gvl_ctx.cu", "gvl_hap.cu", "gvl_svar2.cu", "gvl_tracks.cu", "gvl_aux.cu", "gvl_batch.cu", "gvl_variants.cu", "gvl_host.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

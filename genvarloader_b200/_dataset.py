@@ -22,7 +22,7 @@ import torch
 
 from ._engine import Engine
 from ._insertion_fill import InsertionFill, Repeat5p, lower
-from ._types import AnnotatedHaps, Ragged, RaggedAnnotatedHaps
+from ._types import AnnotatedHaps, DummyVariant, Ragged, RaggedAlleles, RaggedAnnotatedHaps, RaggedVariants
 
 SeqKind = Literal["reference", "haplotypes", "annotated"]
 N_CHAR = ord("N")
@@ -65,6 +65,11 @@ class Dataset:
     realign_tracks: bool = True
     output_format: str = "ragged"                     # "ragged" | "flat"  (with_output_format)
     encoding: str = "bytes"                           # "bytes" | "onehot" | "onehot_cf"  (this build's fused one-hot)
+    var_fields: tuple = ("alt", "ilen", "start")      # fields of the "variants" output (_haps.py:268)
+    dummy_variant: object = None                      # DummyVariant for empty (region, sample, ploid) groups, or None
+    unphased_union: bool = False                      # fold the ploidy rows of a (region, sample) into one (_flat_variants.py:925-938)
+    min_af: object = None                             # AF filter of the "variants" output (_flat_variants.py:899-923)
+    max_af: object = None
     rng: np.random.Generator = field(default_factory=np.random.default_rng)
     region_subset: object = None
     sample_subset: object = None
@@ -78,11 +83,15 @@ class Dataset:
     @classmethod
     def from_arrays(cls, device, reference, ref_offsets, v_starts, ilens, alt_alleles, alt_offsets, geno_v_idxs,
                     geno_offsets, regions, n_samples: int, ploidy: int, max_jitter: int = 0, tracks: dict | None = None,
-                    track_kinds: dict | None = None, sample_names=None, rng=None) -> "Dataset":
+                    track_kinds: dict | None = None, sample_names=None, rng=None, ref_alleles=None,
+                    variant_info: dict | None = None) -> "Dataset":
         """In-memory dataset (the GPU counterpart of `get_dummy_dataset`, python/genvarloader/_dummy.py).
         `tracks`: name -> (itv_starts, itv_ends, itv_values, itv_offsets); SAMPLE tracks have one interval slot
-        per (region, sample), ANNOT tracks one per region (_reconstruct.py:233-236)."""
+        per (region, sample), ANNOT tracks one per region (_reconstruct.py:233-236).  `ref_alleles` = (bytes, offsets) of
+        the REF strings and `variant_info` = {name: 4-byte column} feed the "variants" output (`var_fields`, AF filter)."""
         eng = Engine(device, reference, ref_offsets, v_starts, ilens, alt_alleles, alt_offsets, geno_v_idxs, geno_offsets)
+        if ref_alleles is not None or variant_info:
+            eng.set_variant_fields(ref_alleles, variant_info)
         kinds = {}
         for name, t in (tracks or {}).items():
             eng.add_track(name, *t)
@@ -182,6 +191,12 @@ class Dataset:
     @property
     def full_shape(self) -> tuple:
         return (len(self.full_regions), len(self.sample_names))
+
+    @property
+    def available_var_fields(self) -> list:
+        """Reference: `Haps.available_var_fields`, _haps.py:313-319."""
+        eng = self.engine
+        return ["alt", "ilen", "start"] + (["ref"] if eng.ref_alleles is not None else []) + sorted(eng.var_info)
 
     @property
     def available_tracks(self) -> list:
@@ -319,6 +334,8 @@ class Dataset:
                     f" The maximum output length is the minimum region length ({min_r_len}) + 2 * (max_jitter={self.max_jitter}).")
         elif self.output_length not in ("ragged", "variable"):
             raise ValueError(f"Output length must be 'ragged', 'variable' or a positive integer, got {self.output_length!r}")
+        if (self.min_af is not None or self.max_af is not None) and self.sequence_type != "variants":
+            raise NotImplementedError("Filtering by AF is not supported for haplotype output yet.")  # _haps.py:695-698
         if self.encoding != "bytes" and self.sequence_type not in ("haplotypes", "reference"):
             raise ValueError("one-hot encoding applies to 'haplotypes' / 'reference' sequences only")
         if self.encoding == "onehot_cf":
@@ -335,9 +352,27 @@ class Dataset:
     def with_settings(self, jitter=None, rng=None, deterministic=None, rc_neg=None, var_filter=None, realign_tracks=None,
                       min_af=None, max_af=None, splice_info=None, **unsupported) -> "Dataset":
         """Reference: `Dataset.with_settings`, _impl.py:228-499 (hot-path settings only)."""
-        if min_af not in (None, False) or max_af not in (None, False):
-            raise NotImplementedError("Filtering by AF is not supported for haplotype output yet.")  # _haps.py:695-698
         kw = {}
+        if min_af is not None:
+            kw["min_af"] = None if min_af is False else float(min_af)
+        if max_af is not None:
+            kw["max_af"] = None if max_af is False else float(max_af)
+        for name in ("var_fields", "dummy_variant", "unphased_union"):
+            if name in unsupported:
+                v = unsupported.pop(name)
+                if v is None:
+                    continue
+                if name == "var_fields":
+                    avail = self.available_var_fields
+                    missing = sorted(set(v) - set(avail))
+                    if missing:
+                        raise ValueError(f"Missing variant fields: {missing}")  # _impl.py:343-346
+                    v = tuple(v)
+                elif name == "dummy_variant":
+                    v = None if v is False else v
+                else:
+                    v = bool(v)
+                kw[name] = v
         if splice_info is False:
             kw["splice_rows"], kw["splice_names"] = None, None
         elif splice_info is not None:
@@ -372,9 +407,13 @@ class Dataset:
 
     def with_seqs(self, kind) -> "Dataset":
         """Reference: `Dataset.with_seqs`, _impl.py:649-783."""
-        if kind in ("variants", "variant-windows"):
-            raise NotImplementedError(f"with_seqs({kind!r}) is outside the scope of the B200 hot path.")
-        if kind not in (None, "reference", "haplotypes", "annotated"):
+        if kind == "variant-windows":
+            raise NotImplementedError("with_seqs('variant-windows'): the token-window kernels are exposed as "
+                                      "genvarloader_b200._variants.assemble_variant_buffers; the Dataset mode is not wired")
+        if kind == "variants" and getattr(self.engine, "svar2", None) is not None:
+            raise NotImplementedError("with_seqs('variants') needs the SVAR1 genotype CSR (the svar2 source decodes variants "
+                                      "through its store)")
+        if kind not in (None, "reference", "haplotypes", "annotated", "variants"):
             raise ValueError(f"Unknown sequence type {kind!r}")
         enc = self.encoding if kind in ("haplotypes", "reference") else "bytes"
         return self._evolve(sequence_type=kind, encoding=enc)
@@ -663,6 +702,8 @@ class Dataset:
         if self.sequence_type is None and not self.active_tracks:
             raise ValueError("Dataset has neither sequences nor tracks active.")
         if self.splice_rows is not None:
+            if self.sequence_type == "variants":
+                raise NotImplementedError("spliced 'variants' output is not built")
             return self._getitem_spliced(idx)
         ds_idx, squeeze, out_reshape = self._parse_idx(idx)
         pipe = self._eager_pipeline(len(ds_idx))
@@ -714,7 +755,7 @@ class Dataset:
         want_seqs = self.sequence_type is not None
         want_tracks = len(self.active_tracks) > 0
         is_ref = self.sequence_type == "reference"
-        realign = want_tracks and want_seqs and not is_ref and self.realign_tracks
+        realign = want_tracks and want_seqs and not is_ref and self.realign_tracks and self.sequence_type != "variants"
         to_rc_q = (self.full_regions[r_idx, 3] == -1) if self.rc_neg else None
         lengths = (regions[:, 2] - regions[:, 1]).astype(np.int64)
 
@@ -749,6 +790,10 @@ class Dataset:
 
         results = []
         oo = total = diffs = None
+        if self.sequence_type == "variants":
+            # Haps._get_variants -> get_variants_flat (_haps.py:602-609, _flat_variants.py:869-1112), on the device
+            results.append(self._get_variants(t_goi, t_rc, b))
+            want_seqs = False
         if want_seqs:
             out_len = int(self.output_length) if fixed else -1
             if fixed and not self.deterministic and not is_ref:
@@ -810,6 +855,18 @@ class Dataset:
                 results.append(Ragged(out, offsets, (b, t, None)))
         return tuple(results)
 
+    def _get_variants(self, t_goi, t_rc, b: int) -> RaggedVariants:
+        p = self.ploidy
+        fold = p if self.unphased_union else 1
+        g = self.engine.gather_variants(t_goi, t_rc, self.var_fields, self.dummy_variant, self.min_af, self.max_af, fold)
+        shape = (b, 1 if self.unphased_union else p, None)
+        off = g["row_offsets"]
+        fields = {}
+        for name in self.var_fields:
+            v = g[name]
+            fields[name] = RaggedAlleles(v[0], v[1], off, shape) if isinstance(v, tuple) else Ragged(v, off, shape)
+        return RaggedVariants(fields, off, shape)
+
     def _exonic_keep(self, t_goi, t_reg, goi):
         """choose_exonic_variants (src/genotypes/mod.rs:132-176): variants fully inside the query, on the device."""
         eng = self.engine
@@ -817,7 +874,7 @@ class Dataset:
 
     # ---- output shaping, _query.py:94-127 ----
     def _shape_output(self, o, out_reshape, squeeze):
-        if isinstance(o, (torch.Tensor, AnnotatedHaps)) or self.output_format == "flat" or self.output_length == "ragged":
+        if isinstance(o, (torch.Tensor, AnnotatedHaps, RaggedVariants)) or self.output_format == "flat" or self.output_length == "ragged":
             res = o  # already dense (fixed-length pipeline, channels-first one-hot); "flat"/"ragged" hand the flat triple back
         elif self.output_length == "variable":
             if isinstance(o, RaggedAnnotatedHaps):

@@ -99,6 +99,8 @@ class Engine:
             ptr(self.alt_packed))
         self.tracks: dict[str, tuple] = {}
         self.svar2 = None  # resident svar2 two-channel source (set_svar2)
+        self.ref_alleles = None  # (bytes, offsets) of the REF allele strings (set_variant_fields)
+        self.var_info: dict[str, torch.Tensor] = {}
         self._n_work = 0
         self._fixed = -1
 
@@ -178,6 +180,139 @@ class Engine:
                                                  ptr(geno_offset_idx), c_i64(n_q), c_i64(ploidy), ptr(keep),
                                                  c_i64(int(keep_cap)), ptr(keep_offsets), _stream()))
         return keep, keep_offsets
+
+    # ------------------------------------------------------------------ `variants` output (csrc/gvl_variants.cu)
+    def set_variant_fields(self, ref_alleles=None, info: dict | None = None) -> None:
+        """Optional per-variant columns of the `variants` output: REF allele strings `(bytes, offsets)` and 4-byte info
+        columns (e.g. "AF" float32 for `min_af` / `max_af`) -- `_Variants.ref` / `.info`, _haps.py:139-157."""
+        with torch.cuda.device(self.device):
+            if ref_alleles is not None:
+                self.ref_alleles = (_dev(ref_alleles[0], np.uint8, self.device, pad=16), _dev(ref_alleles[1], np.int64, self.device))
+            for k, v in (info or {}).items():
+                v = np.ascontiguousarray(v)
+                if v.dtype.itemsize != 4:
+                    raise TypeError(f"info column {k!r}: 4-byte values expected (int32 / float32), got {v.dtype}")
+                self.var_info[k] = _dev(v, v.dtype, self.device)
+
+    def _scan_total(self, offsets: torch.Tensor) -> int:
+        return int(offsets[-1].item())  # the one synchronisation of a ragged output
+
+    def gather_variants(self, geno_offset_idx: torch.Tensor, to_rc_row, fields, dummy=None, min_af=None, max_af=None,
+                        fold: int = 1) -> dict:
+        """The tail of `get_variants_flat` (python/genvarloader/_dataset/_flat_variants.py:869-1112) on the device: per
+        (b*p) row the variant indices of its genotype slice (gather_rows, src/variants/mod.rs:6-49), optional AF
+        compaction (:112-153), positions / indel lengths / info columns (`table[v_idxs]`), ALT / REF allele strings
+        (:52-78), reverse complement of the alleles of negative-strand rows (:90-108) and one dummy variant per empty row
+        (:157-329).  `geno_offset_idx`: device i64, flat (b*p); `to_rc_row`: device u8 (b*p) or None; `fold` = ploidy
+        folds the rows of one (region, sample) into one (`unphased_union`, _flat_variants.py:925-938).
+        Returns {"row_offsets": i64, "v_idxs": i32, name: tensor | (bytes, seq_offsets)}."""
+        if self.svar2 is not None:
+            raise NotImplementedError("`variants` output is built for the SVAR1 genotype CSR; the svar2 source decodes variants "
+                                      "through its store (decode_variants_from_svar2_readbound, src/ffi/mod.rs:1692)")
+        h, dev, st = self.ctx.handle, self.device, _stream
+        goi = geno_offset_idx.reshape(-1).contiguous()
+        n_rows = goi.numel()
+        i64 = lambda n: torch.empty(n, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            row_off = i64(n_rows + 1)
+            check(lib.gvl_dev_gather_rows_offsets(h, ptr(goi), c_i64(n_rows), ptr(self.geno_starts), ptr(self.geno_stops), ptr(row_off), st()))
+            n = self._scan_total(row_off)
+            v_idxs = torch.empty(n, dtype=torch.int32, device=dev)
+            check(lib.gvl_dev_gather_rows(h, ptr(goi), c_i64(n_rows), ptr(self.geno_starts), ptr(self.geno_v_idxs), ptr(row_off), c_i64(n),
+                                          ptr(v_idxs), st()))
+
+            def take(table: torch.Tensor) -> torch.Tensor:
+                out = torch.empty(n, dtype=table.dtype, device=dev)
+                check(lib.gvl_dev_take_u32(h, ptr(table), ptr(v_idxs), c_i64(n), ptr(out), st()))
+                return out
+
+            if min_af is not None or max_af is not None:  # _flat_variants.py:899-923
+                if "AF" not in self.var_info:
+                    raise ValueError("min_af / max_af need the variants' AF column (Engine.set_variant_fields(info={'AF': ...}))")
+                af = take(self.var_info["AF"])
+                keep = torch.ones(n, dtype=torch.bool, device=dev)
+                if min_af is not None:
+                    keep &= af >= min_af
+                if max_af is not None:
+                    keep &= af <= max_af
+                keep = keep.view(torch.uint8)
+                pos, new_off = i64(n + 1), i64(n_rows + 1)
+                check(lib.gvl_dev_compact_keep_offsets(h, ptr(keep), c_i64(n), ptr(row_off), c_i64(n_rows), ptr(pos), ptr(new_off), st()))
+                n_keep = self._scan_total(pos)
+                kept = torch.empty(n_keep, dtype=torch.int32, device=dev)
+                check(lib.gvl_dev_compact_keep(h, ptr(v_idxs), ptr(keep), c_i64(n), ptr(pos), ptr(kept), st()))
+                v_idxs, row_off, n = kept, new_off, n_keep
+            if fold > 1:
+                row_off = row_off[::fold].contiguous()
+                if to_rc_row is not None:
+                    to_rc_row = to_rc_row[::fold].contiguous()
+                n_rows //= fold
+
+            out = {"v_idxs": v_idxs}
+            alleles = {}
+            for name in fields:
+                if name in ("alt", "ref"):
+                    if name == "ref" and self.ref_alleles is None:
+                        raise ValueError("Missing variant fields: ['ref']")
+                    ab, ao = (self.alt_alleles, self.alt_offsets) if name == "alt" else self.ref_alleles
+                    seq_off = i64(n + 1)
+                    check(lib.gvl_dev_gather_alleles_offsets(h, ptr(v_idxs), c_i64(n), ptr(ao), ptr(seq_off), st()))
+                    nb = self._scan_total(seq_off)
+                    data = torch.empty(nb, dtype=torch.uint8, device=dev)
+                    check(lib.gvl_dev_gather_alleles(h, ptr(v_idxs), c_i64(n), ptr(ab), ptr(ao), ptr(seq_off), c_i64(nb), c_vp(0),
+                                                     C.c_int(1), ptr(data), st()))
+                    alleles[name] = (data, seq_off)
+                elif name == "start":
+                    out[name] = take(self.v_starts)
+                elif name == "ilen":
+                    out[name] = take(self.ilens)
+                elif name in self.var_info:
+                    out[name] = take(self.var_info[name])
+                else:
+                    raise ValueError(f"Missing variant fields: [{name!r}]")
+            def rc(alleles_: dict, n_var: int, var_off: torch.Tensor) -> None:
+                # negative-strand rows: reverse-complement their alleles in place (applied after the dummy fill, like
+                # `_query.py:485-529` after `get_variants_flat`)
+                if to_rc_row is None:
+                    return
+                for data, seq_off in alleles_.values():
+                    check(lib.gvl_dev_rc_alleles(h, ptr(data), ptr(seq_off), c_i64(n_var), ptr(var_off), c_i64(n_rows), ptr(to_rc_row),
+                                                 c_i64(data.numel()), st()))
+
+            if dummy is None:
+                rc(alleles, n, row_off)
+                out["row_offsets"] = row_off
+                out.update(alleles)
+                return out
+            # ---- one dummy variant per empty row (fill_empty_groups, _flat_variants.py:501-535) ----
+            new_off = i64(n_rows + 1)
+            check(lib.gvl_dev_fill_empty_offsets(h, ptr(row_off), c_i64(n_rows), ptr(new_off), st()))
+            n_new = self._scan_total(new_off)
+            for name in list(out):
+                t = out[name]
+                np_dt = np.float32 if t.dtype == torch.float32 else np.int32
+                fill = -1 if name == "v_idxs" else dummy.scalar_for(name, np_dt)
+                bits = int(np.array(fill, np_dt).view(np.uint32))
+                filled = torch.empty(n_new, dtype=t.dtype, device=dev)
+                check(lib.gvl_dev_fill_empty_fixed(h, ptr(t), ptr(row_off), c_i64(n_rows), ptr(new_off), c_i64(n_new), c_i64(1),
+                                                   C.c_uint32(bits), ptr(filled), st()))
+                out[name] = filled
+            src_var = i64(max(n_new, 1))
+            for name, (data, seq_off) in alleles.items():
+                db = np.frombuffer(dummy.alt if name == "alt" else dummy.ref, np.uint8)
+                d_dummy = torch.from_numpy(db.copy()).to(dev)
+                new_seq = i64(n_new + 1)
+                check(lib.gvl_dev_fill_empty_seq_offsets(h, ptr(row_off), c_i64(n_rows), ptr(seq_off), c_i64(db.size), ptr(new_off),
+                                                         c_i64(n_new), ptr(src_var), ptr(new_seq), st()))
+                nb = self._scan_total(new_seq)
+                filled = torch.empty(nb, dtype=torch.uint8, device=dev)
+                check(lib.gvl_dev_fill_empty_seq(h, ptr(data), C.c_int(1), ptr(seq_off), ptr(d_dummy), ptr(src_var), ptr(new_seq),
+                                                 c_i64(n_new), c_i64(nb), ptr(filled), st()))
+                alleles[name] = (filled, new_seq)
+            rc(alleles, n_new, new_off)
+            out.update(alleles)
+            out["row_offsets"] = new_off
+            return out
 
     # ------------------------------------------------------------------ tracks
     def add_track(self, name: str, itv_starts, itv_ends, itv_values, itv_offsets) -> None:

@@ -91,6 +91,8 @@ def supports(ds) -> str | None:
         return "output_length is not fixed"
     if ds.splice_rows is not None:
         return "spliced output"
+    if ds.sequence_type == "variants":
+        return "the variants output is ragged by nature"
     if ds.var_filter is not None:
         return "var_filter needs per-batch keep masks"
     if not ds.deterministic and ds.sequence_type in ("haplotypes", "annotated"):

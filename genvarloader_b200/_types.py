@@ -132,3 +132,88 @@ class RaggedAnnotatedHaps:
     def to_padded(self) -> AnnotatedHaps:
         # pad values: python/genvarloader/_flat.py:207-214
         return AnnotatedHaps(self.haps.to_padded(ord("N")), self.var_idxs.to_padded(-1), self.ref_coords.to_padded(INT32_MAX))
+
+
+@dataclass(frozen=True)
+class DummyVariant:
+    """Per-field values of the dummy variant inserted into empty (region, sample, ploid) groups (reference
+    `DummyVariant`, python/genvarloader/_dataset/_flat_variants.py:39-68): unspecified info fields default to 0 for
+    integer columns and NaN for float columns."""
+
+    start: int = -1
+    ilen: int = 0
+    dosage: float = 0.0
+    ref: bytes = b"N"
+    alt: bytes = b"N"
+    info: Any = None
+
+    def scalar_for(self, name: str, dtype):
+        dt = np.dtype(dtype)
+        if name == "start":
+            return dt.type(self.start)
+        if name == "ilen":
+            return dt.type(self.ilen)
+        if name == "dosage":
+            return dt.type(self.dosage)
+        if self.info and name in self.info:
+            return dt.type(self.info[name])
+        return dt.type(np.nan) if np.issubdtype(dt, np.floating) else dt.type(0)
+
+
+@dataclass(frozen=True)
+class RaggedAlleles:
+    """Two-level ragged allele strings on the device (reference `_FlatAlleles`, _flat_variants.py:70-188): allele a of
+    the batch is `data[seq_offsets[a]:seq_offsets[a+1]]`, row r owns alleles `var_offsets[r]:var_offsets[r+1]`."""
+
+    data: torch.Tensor         # uint8 bytes
+    seq_offsets: torch.Tensor  # int64 (n_alleles + 1,)
+    var_offsets: torch.Tensor  # int64 (n_rows + 1,)
+    shape: tuple
+
+    def reshape(self, shape) -> "RaggedAlleles":
+        shape = (shape,) if isinstance(shape, int) else tuple(shape)
+        return RaggedAlleles(self.data, self.seq_offsets, self.var_offsets, shape + (None,))
+
+    def to_list(self) -> list:
+        """Host copy as nested lists of `bytes` (tests, debugging)."""
+        d, so, vo = self.data.cpu().numpy().tobytes(), self.seq_offsets.cpu().numpy(), self.var_offsets.cpu().numpy()
+        return [[d[so[a]:so[a + 1]] for a in range(vo[r], vo[r + 1])] for r in range(len(vo) - 1)]
+
+
+@dataclass(frozen=True)
+class RaggedVariants:
+    """The `variants` output (reference `RaggedVariants` / `_FlatVariants`, _rag_variants.py, _flat_variants.py:405-535):
+    one ragged field per requested name, all sharing `offsets` (variants per (b, p) row).  Scalar fields are `Ragged`
+    (int32 `start`, `ilen`; 4-byte info columns), `alt` / `ref` are `RaggedAlleles`."""
+
+    fields: dict
+    offsets: torch.Tensor
+    shape: tuple
+
+    def __getitem__(self, name: str):
+        return self.fields[name]
+
+    def __getattr__(self, name: str):
+        f = object.__getattribute__(self, "fields")
+        if name in f:
+            return f[name]
+        raise AttributeError(name)
+
+    @property
+    def lengths(self) -> torch.Tensor:
+        outer = tuple(d for d in self.shape if d is not None)
+        return (self.offsets[1:] - self.offsets[:-1]).reshape(outer)
+
+    def reshape(self, shape) -> "RaggedVariants":
+        shape = (shape,) if isinstance(shape, int) else tuple(shape)
+        return RaggedVariants({k: v.reshape(shape) for k, v in self.fields.items()}, self.offsets, shape + (None,))
+
+    def squeeze(self, axis=None) -> "RaggedVariants":
+        outer = [d for d in self.shape if d is not None]
+        if axis is None:
+            outer = [d for d in outer if d != 1]
+        else:
+            if outer[axis] != 1:
+                raise ValueError(f"cannot squeeze axis {axis} with size {outer[axis]}")
+            del outer[axis]
+        return self.reshape(tuple(outer))

@@ -140,6 +140,9 @@ struct gvl_ctx {
     int stage_k = 0;
     void *zeros;                // device zeros (gvl_aux.cu: rows without genotypes)
     int64_t zeros_bytes;
+    void *var_scratch = nullptr;    // block sums of the offset scans (gvl_variants.cu)
+    int64_t var_scratch_bytes = 0;
+    std::vector<std::pair<void *, int64_t>> var_results;  // device results of the last host-layer variants entry (gvl_variants_fetch)
     // host layer
     std::map<const void *, gvl_static_entry> statics;
     std::map<const void *, void *> packed_refs;  // device ASCII reference (pinned static) -> its packed copy

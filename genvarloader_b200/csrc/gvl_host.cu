@@ -960,3 +960,5 @@ int gvl_intervals_to_tracks(gvl_ctx *ctx, const int64_t *offset_idxs, const int3
 }
 
 }  // extern "C"
+
+#include "gvl_host_variants.cuh"

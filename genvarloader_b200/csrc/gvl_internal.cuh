@@ -13,6 +13,7 @@ int ensure_dir(gvl_ctx *ctx, gvl_workspace &ws, int64_t n);
 int ensure_trecs(gvl_ctx *ctx, gvl_workspace &ws, int64_t n);
 int ensure_tdesc(gvl_ctx *ctx, gvl_workspace &ws, int64_t n);
 int ensure_zeros(gvl_ctx *ctx, int64_t bytes, cudaStream_t st);
+int ensure_var_scratch(gvl_ctx *ctx, int64_t bytes);
 
 #define GVL_CUDA(expr)                                                                                  \
     do {                                                                                                \

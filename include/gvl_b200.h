@@ -561,6 +561,115 @@ int gvl_debug_xorshift64(gvl_ctx *ctx, uint64_t x, uint64_t *out);
  * (tests assert that the intended kernel ran). */
 int gvl_debug_last_exec_kernel(gvl_ctx *ctx);
 
+/* ====================================================================================
+ * `variants` / `variant-windows` outputs: the variants of every (region, sample, ploid) row
+ * themselves -- indices, positions, indel lengths, allele byte strings, flank / window tokens -- instead of the
+ * reconstructed haplotype.  Reference: src/variants/mod.rs, src/variants/windows.rs; callers
+ * python/genvarloader/_dataset/_flat_variants.py:869-1112 (get_variants_flat), _rag_variants.py:300-325.
+ * Every entry is "lengths -> exclusive scan -> ragged copy": an `_offsets` call writes the (n + 1) offsets on the device,
+ * the caller reads offsets[n] (its one synchronisation, as for every ragged output), allocates, and calls the fill.
+ * 4-byte items (i32 variant indices / positions, f32 dosages) move as raw 32-bit words: bit-exact for floats.
+ * ==================================================================================== */
+#define GVL_WINDOW_REF 0    /* tokens of the reference window [start - L, end + L), end = start - min(ilen, 0) + 1 */
+#define GVL_WINDOW_ALT 1    /* tokens of flank5 . ALT . flank3                                                     */
+#define GVL_WINDOW_FLANKS 2 /* tokens of [flank5 | flank3], 2 L per variant (the `flank_tokens` field)             */
+
+/* gather_rows_{i32,f32}, src/ffi/mod.rs:255-288 -> src/variants/mod.rs:6-49: row i = data[o_starts[g] .. o_stops[g]) with
+ * g = geno_offset_idx[i].  out_offsets i64[n_rows + 1]. */
+int gvl_dev_gather_rows_offsets(gvl_ctx *ctx, const int64_t *geno_offset_idx, int64_t n_rows, const int64_t *o_starts,
+                                const int64_t *o_stops, int64_t *out_offsets, gvl_stream stream);
+int gvl_dev_gather_rows(gvl_ctx *ctx, const int64_t *geno_offset_idx, int64_t n_rows, const int64_t *o_starts, const void *data,
+                        const int64_t *out_offsets, int64_t total, void *out, gvl_stream stream);
+/* table[v_idxs[i]] for a 4-byte table: start / ilen / info fields of the gathered variants (_flat_variants.py:948-953). */
+int gvl_dev_take_u32(gvl_ctx *ctx, const void *table, const int32_t *v_idxs, int64_t n, void *out, gvl_stream stream);
+
+/* gather_alleles, src/ffi/mod.rs:291-304 -> src/variants/mod.rs:52-78.  seq_offsets i64[n + 1].  With lut != NULL the
+ * bytes are tokenised on the way out (windows.rs:9-22): out[e] = lut[byte], lut = 256 tokens of tok_bytes (1 or 4). */
+int gvl_dev_gather_alleles_offsets(gvl_ctx *ctx, const int32_t *v_idxs, int64_t n, const int64_t *allele_offsets,
+                                   int64_t *seq_offsets, gvl_stream stream);
+int gvl_dev_gather_alleles(gvl_ctx *ctx, const int32_t *v_idxs, int64_t n, const uint8_t *allele_bytes,
+                           const int64_t *allele_offsets, const int64_t *seq_offsets, int64_t total, const void *lut,
+                           int tok_bytes, void *out, gvl_stream stream);
+
+/* rc_alleles, src/ffi/mod.rs:2808 -> src/variants/mod.rs:90-108: reverse-complement, in place, every allele of the
+ * (b*p) rows with to_rc_row != 0 (src/reverse.rs:45-53).  seq_offsets i64[n_alleles + 1] (seq_offsets[0] = 0),
+ * var_offsets i64[n_rows + 1], total_bytes = seq_offsets[n_alleles]. */
+int gvl_dev_rc_alleles(gvl_ctx *ctx, uint8_t *byte_data, const int64_t *seq_offsets, int64_t n_alleles,
+                       const int64_t *var_offsets, int64_t n_rows, const uint8_t *to_rc_row, int64_t total_bytes,
+                       gvl_stream stream);
+
+/* compact_keep_{i32,f32}, src/ffi/mod.rs:308-333 -> src/variants/mod.rs:112-153.  pos i64[n + 1] is caller scratch that
+ * receives the exclusive scan of keep (pos[n] = values kept); new_offsets i64[n_rows + 1]. */
+int gvl_dev_compact_keep_offsets(gvl_ctx *ctx, const uint8_t *keep, int64_t n, const int64_t *row_offsets, int64_t n_rows,
+                                 int64_t *pos, int64_t *new_offsets, gvl_stream stream);
+int gvl_dev_compact_keep(gvl_ctx *ctx, const void *values, const uint8_t *keep, int64_t n, const int64_t *pos, void *out,
+                         gvl_stream stream);
+
+/* fill_empty_{scalar,fixed}_{i32,f32}, src/ffi/mod.rs:336-388 -> src/variants/mod.rs:157-256: every empty row receives one
+ * dummy variant of `inner` items equal to fill_bits (scalar: inner = 1).  new_offsets i64[n_rows + 1] count variants;
+ * new_total = new_offsets[n_rows]; out holds new_total * inner items. */
+int gvl_dev_fill_empty_offsets(gvl_ctx *ctx, const int64_t *offsets, int64_t n_rows, int64_t *new_offsets, gvl_stream stream);
+int gvl_dev_fill_empty_fixed(gvl_ctx *ctx, const void *data, const int64_t *offsets, int64_t n_rows, const int64_t *new_offsets,
+                             int64_t new_total, int64_t inner, uint32_t fill_bits, void *out, gvl_stream stream);
+
+/* fill_empty_seq_{u8,i32}, src/ffi/mod.rs:391-445 -> src/variants/mod.rs:259-329: two-level ragged (rows -> variants ->
+ * items); every empty row receives one dummy sequence.  new_var_offsets comes from gvl_dev_fill_empty_offsets
+ * (n_new_vars = new_var_offsets[n_rows]); src_var i64[n_new_vars] is caller scratch (source variant of every new variant,
+ * -1 = dummy); new_seq_offsets i64[n_new_vars + 1]; total = new_seq_offsets[n_new_vars]. */
+int gvl_dev_fill_empty_seq_offsets(gvl_ctx *ctx, const int64_t *var_offsets, int64_t n_rows, const int64_t *seq_offsets,
+                                   int64_t dummy_len, const int64_t *new_var_offsets, int64_t n_new_vars, int64_t *src_var,
+                                   int64_t *new_seq_offsets, gvl_stream stream);
+int gvl_dev_fill_empty_seq(gvl_ctx *ctx, const void *data, int itemsize, const int64_t *seq_offsets, const void *dummy,
+                           const int64_t *src_var, const int64_t *new_seq_offsets, int64_t n_new_vars, int64_t total, void *out,
+                           gvl_stream stream);
+
+/* Flank / window tokens, src/variants/windows.rs:27-134, 196-214, 262-291 (fetch_windows + slice_flanks +
+ * assemble_alt_window + tokenize in one pass; the intermediate window bytes are never materialised).  Reads
+ * tab->{v_starts, ilens, alt_alleles, alt_offsets, ref, ref_offsets}; v_contigs i32[n] = contig of every selected variant
+ * (NULL: contig 0); positions outside the contig read as pad_char; lut = 256 tokens of tok_bytes (1 or 4).
+ * GVL_WINDOW_FLANKS needs no offsets (2 * flank_len tokens per variant). */
+int gvl_dev_variant_windows_offsets(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_t *v_idxs, int64_t n,
+                                    int64_t flank_len, int kind, int64_t *win_offsets, gvl_stream stream);
+int gvl_dev_variant_windows(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int32_t *v_idxs, const int32_t *v_contigs,
+                            int64_t n, int64_t flank_len, int kind, uint8_t pad_char, const void *lut, int tok_bytes,
+                            const int64_t *win_offsets, int64_t total, void *out, gvl_stream stream);
+
+/* ---- host layer of the same entries: the reference's #[pyfunction] argument lists, host pointers in.  The reference
+ * returns arrays it allocates; here a call leaves its results on the device, reports their sizes, and the caller copies
+ * each one out with gvl_variants_fetch(which) into a buffer of exactly that size (results stay valid until the next
+ * host-layer variants call on the context).  Offsets that size other results are also written straight to host. */
+int gvl_variants_fetch(gvl_ctx *ctx, int which, void *host_out, int64_t bytes);
+/* result 0: data (4 * total bytes).  geno_offsets is the (2, n_geno) starts / stops array. */
+int gvl_gather_rows(gvl_ctx *ctx, const int64_t *geno_offset_idx, int64_t n_rows, const int64_t *geno_offsets, int64_t n_geno,
+                    const void *data, int64_t n_data, int64_t *out_offsets, int64_t *total);
+/* result 0: bytes (total). */
+int gvl_gather_alleles(gvl_ctx *ctx, const int32_t *v_idxs, int64_t n, const uint8_t *allele_bytes, int64_t n_bytes,
+                       const int64_t *allele_offsets, int64_t n_table, int64_t *seq_offsets, int64_t *total);
+/* in place on the caller's host buffer. */
+int gvl_rc_alleles(gvl_ctx *ctx, uint8_t *byte_data, int64_t n_bytes, const int64_t *seq_offsets, int64_t n_alleles,
+                   const int64_t *var_offsets, int64_t n_rows, const uint8_t *to_rc_row);
+/* result 0: kept values (4 * total bytes). */
+int gvl_compact_keep(gvl_ctx *ctx, const void *values, int64_t n, const int64_t *row_offsets, int64_t n_rows,
+                     const uint8_t *keep, int64_t *new_offsets, int64_t *total);
+/* result 0: data (4 * new_total * inner bytes); fill_empty_scalar = inner 1. */
+int gvl_fill_empty_fixed(gvl_ctx *ctx, const void *data, int64_t n_data, const int64_t *offsets, int64_t n_rows, int64_t inner,
+                         uint32_t fill_bits, int64_t *new_offsets, int64_t *new_total);
+/* result 0: data (itemsize * total bytes), result 1: new_seq_offsets (8 * (n_new_vars + 1) bytes). */
+int gvl_fill_empty_seq(gvl_ctx *ctx, const void *data, int itemsize, int64_t n_data, const int64_t *var_offsets, int64_t n_rows,
+                       const int64_t *seq_offsets, int64_t n_vars, const void *dummy, int64_t dummy_len,
+                       int64_t *new_var_offsets, int64_t *n_new_vars, int64_t *total);
+/* assemble_variant_buffers_{u8,i32}, src/ffi/mod.rs:460-630.  Up to three fields come back in the reference's order:
+ * field_kind[j] in {0 alt, 1 ref, 2 flank_tokens, 3 ref_window, 4 alt_window}, field_items[j] = items of its data,
+ * field_tok[j] = bytes per item; data = result 2 j, seq offsets = result 2 j + 1 (i64[n + 1]; flank_tokens has none: its
+ * offsets are the caller's row_offsets).  lut may be NULL when no tokens are requested. */
+int gvl_assemble_variant_buffers(gvl_ctx *ctx, int64_t mode, const int32_t *v_idxs, int64_t n, const uint8_t *alt_global,
+                                 const int64_t *alt_off_global, const uint8_t *ref_global, const int64_t *ref_off_global,
+                                 int64_t n_variants, int want_ref_bytes, int want_flank, int64_t ref_mode, int64_t alt_mode,
+                                 int64_t flank_len, const void *lut, int tok_bytes, const int32_t *v_contigs,
+                                 const int32_t *v_starts, const int32_t *ilens, const uint8_t *reference,
+                                 const int64_t *ref_offsets, int64_t n_contigs, uint8_t pad_char, int32_t *n_fields,
+                                 int32_t *field_kind, int64_t *field_items, int32_t *field_tok);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -162,8 +162,8 @@ def assemble_variant_buffers(mode, v_idxs, row_offsets, alt_global, alt_off_glob
             lut = np.asarray(lut)
             rw, rw_off = fetch_windows(v_contigs, sv, iv, L, reference, ref_offsets, pad_char)
             cols = np.arange(L, dtype=np.int64)
-            f5 = rw[(rw_off[:-1, None] + cols).reshape(-1)].reshape(-1, L)  # windows.rs:27-52
-            f3 = rw[(rw_off[1:, None] - L + cols).reshape(-1)].reshape(-1, L)
+            f5 = rw[(rw_off[:-1, None] + cols).reshape(-1)].reshape(len(v), L)  # windows.rs:27-52
+            f3 = rw[(rw_off[1:, None] - L + cols).reshape(-1)].reshape(len(v), L)
             out["flank_tokens"] = (lut[np.concatenate([f5, f3], axis=1).reshape(-1)], np.asarray(row_offsets, np.int64).copy())
         return out
     lut = np.asarray(lut)

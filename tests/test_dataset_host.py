@@ -58,7 +58,10 @@ def test_validation_like_reference():
     with pytest.raises(ValueError, match="not found"):
         ds.with_tracks(["missing"])
     with pytest.raises(NotImplementedError):
-        ds.with_seqs("variants")
+        ds.with_seqs("variant-windows")
+    assert ds.with_seqs("variants").sequence_type == "variants"
+    with pytest.raises(NotImplementedError, match="AF"):
+        ds.with_settings(min_af=0.1)  # haplotype output (_haps.py:695-698); allowed with with_seqs("variants")
     with pytest.raises(NotImplementedError):
         ds.with_settings(min_af=0.1)
     with pytest.raises(ValueError):

@@ -22,7 +22,8 @@ import torch
 
 from ._engine import Engine
 from ._insertion_fill import InsertionFill, Repeat5p, lower
-from ._types import AnnotatedHaps, DummyVariant, Ragged, RaggedAlleles, RaggedAnnotatedHaps, RaggedVariants
+from ._types import (AnnotatedHaps, DummyVariant, Ragged, RaggedAlleles, RaggedAnnotatedHaps, RaggedVariants, VarWindowOpt,
+                     build_token_lut)
 
 SeqKind = Literal["reference", "haplotypes", "annotated"]
 N_CHAR = ord("N")
@@ -70,6 +71,10 @@ class Dataset:
     unphased_union: bool = False                      # fold the ploidy rows of a (region, sample) into one (_flat_variants.py:925-938)
     min_af: object = None                             # AF filter of the "variants" output (_flat_variants.py:899-923)
     max_af: object = None
+    window_opt: object = None                         # VarWindowOpt of with_seqs("variant-windows", ...)
+    flank_length: int = 0                             # "variants": flank tokens around every variant (with a token alphabet)
+    token_alphabet: object = None                     # bytes; with unknown_token defines the byte -> token table
+    unknown_token: object = None
     rng: np.random.Generator = field(default_factory=np.random.default_rng)
     region_subset: object = None
     sample_subset: object = None
@@ -334,7 +339,7 @@ class Dataset:
                     f" The maximum output length is the minimum region length ({min_r_len}) + 2 * (max_jitter={self.max_jitter}).")
         elif self.output_length not in ("ragged", "variable"):
             raise ValueError(f"Output length must be 'ragged', 'variable' or a positive integer, got {self.output_length!r}")
-        if (self.min_af is not None or self.max_af is not None) and self.sequence_type != "variants":
+        if (self.min_af is not None or self.max_af is not None) and self.sequence_type not in ("variants", "variant-windows"):
             raise NotImplementedError("Filtering by AF is not supported for haplotype output yet.")  # _haps.py:695-698
         if self.encoding != "bytes" and self.sequence_type not in ("haplotypes", "reference"):
             raise ValueError("one-hot encoding applies to 'haplotypes' / 'reference' sequences only")
@@ -357,6 +362,18 @@ class Dataset:
             kw["min_af"] = None if min_af is False else float(min_af)
         if max_af is not None:
             kw["max_af"] = None if max_af is False else float(max_af)
+        ta, ut = unsupported.pop("token_alphabet", None), unsupported.pop("unknown_token", None)
+        if ta is not None or ut is not None:  # _impl.py:432-441
+            if ta is None or ut is None:
+                raise ValueError("token_alphabet and unknown_token must be set together.")
+            kw["token_alphabet"] = ta.encode("ascii") if isinstance(ta, str) else bytes(ta)
+            kw["unknown_token"] = int(ut)
+        fl = unsupported.pop("flank_length", None)
+        if fl is not None:
+            if fl is not False and kw.get("token_alphabet", self.token_alphabet) is None:
+                raise ValueError("flank_length requires a token LUT; pass token_alphabet and unknown_token to with_settings(...)"
+                                 " (in this or a prior call).")  # _impl.py:442-446
+            kw["flank_length"] = 0 if fl is False else int(fl)
         for name in ("var_fields", "dummy_variant", "unphased_union"):
             if name in unsupported:
                 v = unsupported.pop(name)
@@ -405,18 +422,24 @@ class Dataset:
             output_length = int(output_length)
         return self._evolve(output_length=output_length)
 
-    def with_seqs(self, kind) -> "Dataset":
+    def with_seqs(self, kind, window_opt=None) -> "Dataset":
         """Reference: `Dataset.with_seqs`, _impl.py:649-783."""
-        if kind == "variant-windows":
-            raise NotImplementedError("with_seqs('variant-windows'): the token-window kernels are exposed as "
-                                      "genvarloader_b200._variants.assemble_variant_buffers; the Dataset mode is not wired")
-        if kind == "variants" and getattr(self.engine, "svar2", None) is not None:
-            raise NotImplementedError("with_seqs('variants') needs the SVAR1 genotype CSR (the svar2 source decodes variants "
+        if kind in ("variants", "variant-windows") and getattr(self.engine, "svar2", None) is not None:
+            raise NotImplementedError(f"with_seqs({kind!r}) needs the SVAR1 genotype CSR (the svar2 source decodes variants "
                                       "through its store)")
-        if kind not in (None, "reference", "haplotypes", "annotated", "variants"):
+        if kind not in (None, "reference", "haplotypes", "annotated", "variants", "variant-windows"):
             raise ValueError(f"Unknown sequence type {kind!r}")
+        kw = {}
+        if kind == "variant-windows":
+            if not isinstance(window_opt, VarWindowOpt):
+                raise ValueError("with_seqs('variant-windows') requires window_opt=VarWindowOpt(...)")  # _impl.py:741-747
+            kw["window_opt"] = window_opt
+        elif window_opt is not None:
+            raise ValueError("window_opt only applies to with_seqs('variant-windows')")
+        if kind in ("haplotypes", "annotated") and self.unphased_union:
+            raise ValueError("unphased_union is incompatible with 'haplotypes'/'annotated' output")  # _impl.py:769-779
         enc = self.encoding if kind in ("haplotypes", "reference") else "bytes"
-        return self._evolve(sequence_type=kind, encoding=enc)
+        return self._evolve(sequence_type=kind, encoding=enc, **kw)
 
     def with_encoding(self, encoding: str) -> "Dataset":
         """Fused one-hot output (this build's extension; the reference leaves one-hot to `seqpro.DNA.ohe`,
@@ -702,7 +725,7 @@ class Dataset:
         if self.sequence_type is None and not self.active_tracks:
             raise ValueError("Dataset has neither sequences nor tracks active.")
         if self.splice_rows is not None:
-            if self.sequence_type == "variants":
+            if self.sequence_type in ("variants", "variant-windows"):
                 raise NotImplementedError("spliced 'variants' output is not built")
             return self._getitem_spliced(idx)
         ds_idx, squeeze, out_reshape = self._parse_idx(idx)
@@ -755,7 +778,8 @@ class Dataset:
         want_seqs = self.sequence_type is not None
         want_tracks = len(self.active_tracks) > 0
         is_ref = self.sequence_type == "reference"
-        realign = want_tracks and want_seqs and not is_ref and self.realign_tracks and self.sequence_type != "variants"
+        realign = (want_tracks and want_seqs and not is_ref and self.realign_tracks
+                   and self.sequence_type not in ("variants", "variant-windows"))
         to_rc_q = (self.full_regions[r_idx, 3] == -1) if self.rc_neg else None
         lengths = (regions[:, 2] - regions[:, 1]).astype(np.int64)
 
@@ -790,9 +814,9 @@ class Dataset:
 
         results = []
         oo = total = diffs = None
-        if self.sequence_type == "variants":
+        if self.sequence_type in ("variants", "variant-windows"):
             # Haps._get_variants -> get_variants_flat (_haps.py:602-609, _flat_variants.py:869-1112), on the device
-            results.append(self._get_variants(t_goi, t_rc, b))
+            results.append(self._get_variants(t_goi, t_rc, b, regions))
             want_seqs = False
         if want_seqs:
             out_len = int(self.output_length) if fixed else -1
@@ -855,16 +879,32 @@ class Dataset:
                 results.append(Ragged(out, offsets, (b, t, None)))
         return tuple(results)
 
-    def _get_variants(self, t_goi, t_rc, b: int) -> RaggedVariants:
-        p = self.ploidy
+    def _get_variants(self, t_goi, t_rc, b: int, regions) -> RaggedVariants:
+        p, eng = self.ploidy, self.engine
         fold = p if self.unphased_union else 1
-        g = self.engine.gather_variants(t_goi, t_rc, self.var_fields, self.dummy_variant, self.min_af, self.max_af, fold)
+        windows = self.sequence_type == "variant-windows"
+        tokens = row_contigs = None
+        if windows:
+            o = self.window_opt
+            lut, _ = build_token_lut(o.token_alphabet, o.unknown_token)
+            tokens = dict(lut=lut, unk=o.unknown_token, L=o.flank_length, ref=1 if o.ref == "window" else 2,
+                          alt=1 if o.alt == "window" else 2)
+        elif self.flank_length and self.token_alphabet is not None:
+            lut, _ = build_token_lut(self.token_alphabet, self.unknown_token)
+            tokens = dict(lut=lut, unk=self.unknown_token, L=self.flank_length, flank=True)
+        if tokens is not None:  # contig of every (b*p) row (_flat_variants.py:985-989)
+            row_contigs = torch.from_numpy(np.repeat(regions[:, 0].astype(np.int32), p)).to(eng.device)
+        g = eng.gather_variants(t_goi, t_rc, self.var_fields, self.dummy_variant, self.min_af, self.max_af, fold, tokens, row_contigs)
         shape = (b, 1 if self.unphased_union else p, None)
         off = g["row_offsets"]
         fields = {}
-        for name in self.var_fields:
+        names = [n for n in self.var_fields if not (windows and n in ("alt", "ref"))]
+        names += [n for n in ("ref_window", "alt_window", "ref", "alt") if windows and n in g]  # token buffers of the windows tail
+        for name in names:
             v = g[name]
             fields[name] = RaggedAlleles(v[0], v[1], off, shape) if isinstance(v, tuple) else Ragged(v, off, shape)
+        if "flank_tokens" in g:  # (b, p, ~v, 2 L): the trailing token axis stays on `data`
+            fields["flank_tokens"] = Ragged(g["flank_tokens"].view(-1, 2 * self.flank_length), off, shape)
         return RaggedVariants(fields, off, shape)
 
     def _exonic_keep(self, t_goi, t_reg, goi):

@@ -198,14 +198,19 @@ class Engine:
         return int(offsets[-1].item())  # the one synchronisation of a ragged output
 
     def gather_variants(self, geno_offset_idx: torch.Tensor, to_rc_row, fields, dummy=None, min_af=None, max_af=None,
-                        fold: int = 1) -> dict:
+                        fold: int = 1, tokens: dict | None = None, row_contigs=None) -> dict:
         """The tail of `get_variants_flat` (python/genvarloader/_dataset/_flat_variants.py:869-1112) on the device: per
         (b*p) row the variant indices of its genotype slice (gather_rows, src/variants/mod.rs:6-49), optional AF
         compaction (:112-153), positions / indel lengths / info columns (`table[v_idxs]`), ALT / REF allele strings
         (:52-78), reverse complement of the alleles of negative-strand rows (:90-108) and one dummy variant per empty row
         (:157-329).  `geno_offset_idx`: device i64, flat (b*p); `to_rc_row`: device u8 (b*p) or None; `fold` = ploidy
         folds the rows of one (region, sample) into one (`unphased_union`, _flat_variants.py:925-938).
-        Returns {"row_offsets": i64, "v_idxs": i32, name: tensor | (bytes, seq_offsets)}."""
+        `tokens` = {"lut": 256-entry uint8 / int32 array, "unk": int, "L": flank length, "ref": 0 | 1 window | 2 allele,
+        "alt": likewise, "flank": bool} adds the token buffers of `assemble_variant_buffers` (src/variants/windows.rs:162-296):
+        `flank_tokens` for the variants tail, `ref_window` / `alt_window` / tokenised `ref` / `alt` for the windows tail
+        (then `alt` / `ref` in `fields` are skipped and nothing is reverse-complemented: windows are reference-oriented);
+        `row_contigs`: device i32, contig of every (b*p) row.
+        Returns {"row_offsets": i64, "v_idxs": i32, name: tensor | (data, seq_offsets)}."""
         if self.svar2 is not None:
             raise NotImplementedError("`variants` output is built for the SVAR1 genotype CSR; the svar2 source decodes variants "
                                       "through its store (decode_variants_from_svar2_readbound, src/ffi/mod.rs:1692)")
@@ -250,7 +255,67 @@ class Engine:
 
             out = {"v_idxs": v_idxs}
             alleles = {}
+            windows_mode = tokens is not None and (tokens.get("ref") or tokens.get("alt"))
+            tok_fixed = {}   # flank_tokens: tokens per variant (fixed inner axis: returned without seq offsets)
+            tok_dummy = {}   # window field -> dummy window length
+            if tokens is not None:
+                lut_np = np.ascontiguousarray(tokens["lut"])
+                tdt = torch.uint8 if lut_np.dtype == np.uint8 else torch.int32
+                tb = lut_np.dtype.itemsize
+                d_lut = torch.from_numpy(lut_np).to(dev)
+                L = int(tokens["L"])
+                if fold > 1 and row_contigs is not None:
+                    row_contigs = row_contigs[::fold].contiguous()
+                v_contigs = None
+                if row_contigs is not None:  # _flat_variants.py:985-989
+                    v_contigs = torch.empty(n, dtype=torch.int32, device=dev)
+                    check(lib.gvl_dev_expand_rows_u32(h, ptr(row_contigs), ptr(row_off), c_i64(n_rows), c_i64(n), ptr(v_contigs), st()))
+
+                def window(kind: int):
+                    if kind == 2:  # GVL_WINDOW_FLANKS: 2 L tokens per variant, no offsets
+                        data = torch.empty(n * 2 * L, dtype=tdt, device=dev)
+                        check(lib.gvl_dev_variant_windows(h, C.byref(self.tab), ptr(v_idxs), ptr(v_contigs), c_i64(n), c_i64(L), C.c_int(2),
+                                                          c_u8(self.pad_char), ptr(d_lut), C.c_int(tb), c_vp(0), c_i64(n * 2 * L), ptr(data), st()))
+                        return data
+                    w_off = i64(n + 1)
+                    check(lib.gvl_dev_variant_windows_offsets(h, C.byref(self.tab), ptr(v_idxs), c_i64(n), c_i64(L), C.c_int(kind), ptr(w_off), st()))
+                    nt = self._scan_total(w_off)
+                    data = torch.empty(nt, dtype=tdt, device=dev)
+                    check(lib.gvl_dev_variant_windows(h, C.byref(self.tab), ptr(v_idxs), ptr(v_contigs), c_i64(n), c_i64(L), C.c_int(kind),
+                                                      c_u8(self.pad_char), ptr(d_lut), C.c_int(tb), ptr(w_off), c_i64(nt), ptr(data), st()))
+                    return data, w_off
+
+                def tok_alleles(ab, ao):
+                    seq_off = i64(n + 1)
+                    check(lib.gvl_dev_gather_alleles_offsets(h, ptr(v_idxs), c_i64(n), ptr(ao), ptr(seq_off), st()))
+                    nb = self._scan_total(seq_off)
+                    data = torch.empty(nb, dtype=tdt, device=dev)
+                    check(lib.gvl_dev_gather_alleles(h, ptr(v_idxs), c_i64(n), ptr(ab), ptr(ao), ptr(seq_off), c_i64(nb), ptr(d_lut),
+                                                     C.c_int(tb), ptr(data), st()))
+                    return data, seq_off
+
+                if windows_mode:  # windows.rs:227-296 (ref side first, like the reference's field order)
+                    d_alt = len(dummy.alt) if dummy is not None else 0
+                    d_ref = len(dummy.ref) if dummy is not None else 0
+                    if tokens.get("ref") == 1:
+                        alleles["ref_window"], tok_dummy["ref_window"] = window(0), 2 * L + d_ref
+                    elif tokens.get("ref") == 2:
+                        if self.ref_alleles is None:
+                            raise ValueError("VarWindowOpt(ref='allele') needs the REF allele strings (ref_alleles=)")
+                        alleles["ref"], tok_dummy["ref"] = tok_alleles(*self.ref_alleles), d_ref
+                    if tokens.get("alt") == 1:
+                        alleles["alt_window"], tok_dummy["alt_window"] = window(1), 2 * L + d_alt
+                    elif tokens.get("alt") == 2:
+                        alleles["alt"], tok_dummy["alt"] = tok_alleles(self.alt_alleles, self.alt_offsets), d_alt
+                    to_rc_row = None
+                elif tokens.get("flank") and L > 0:
+                    # 2 L tokens per variant; carried as a two-level ragged with constant strides so that the dummy fill
+                    # below is the same fill_empty_seq pass for 1- and 4-byte tokens
+                    alleles["flank_tokens"] = (window(2), torch.arange(0, (n + 1) * 2 * L, 2 * L, dtype=torch.int64, device=dev))
+                    tok_dummy["flank_tokens"] = tok_fixed["flank_tokens"] = 2 * L
             for name in fields:
+                if name in ("alt", "ref") and windows_mode:
+                    continue
                 if name in ("alt", "ref"):
                     if name == "ref" and self.ref_alleles is None:
                         raise ValueError("Missing variant fields: ['ref']")
@@ -280,9 +345,9 @@ class Engine:
                                                  c_i64(data.numel()), st()))
 
             if dummy is None:
-                rc(alleles, n, row_off)
+                rc({k: v for k, v in alleles.items() if k not in tok_dummy}, n, row_off)
                 out["row_offsets"] = row_off
-                out.update(alleles)
+                out.update({k: (v[0] if k in tok_fixed else v) for k, v in alleles.items()})
                 return out
             # ---- one dummy variant per empty row (fill_empty_groups, _flat_variants.py:501-535) ----
             new_off = i64(n_rows + 1)
@@ -299,18 +364,21 @@ class Engine:
                 out[name] = filled
             src_var = i64(max(n_new, 1))
             for name, (data, seq_off) in alleles.items():
-                db = np.frombuffer(dummy.alt if name == "alt" else dummy.ref, np.uint8)
+                if name in tok_dummy:  # token windows / flank tokens: all-unknown tokens (:385-393, :527-534)
+                    db = np.full(tok_dummy[name], tokens["unk"], np.uint8 if data.dtype == torch.uint8 else np.int32)
+                else:
+                    db = np.frombuffer(dummy.alt if name == "alt" else dummy.ref, np.uint8)
                 d_dummy = torch.from_numpy(db.copy()).to(dev)
                 new_seq = i64(n_new + 1)
                 check(lib.gvl_dev_fill_empty_seq_offsets(h, ptr(row_off), c_i64(n_rows), ptr(seq_off), c_i64(db.size), ptr(new_off),
                                                          c_i64(n_new), ptr(src_var), ptr(new_seq), st()))
                 nb = self._scan_total(new_seq)
-                filled = torch.empty(nb, dtype=torch.uint8, device=dev)
-                check(lib.gvl_dev_fill_empty_seq(h, ptr(data), C.c_int(1), ptr(seq_off), ptr(d_dummy), ptr(src_var), ptr(new_seq),
-                                                 c_i64(n_new), c_i64(nb), ptr(filled), st()))
+                filled = torch.empty(nb, dtype=data.dtype, device=dev)
+                check(lib.gvl_dev_fill_empty_seq(h, ptr(data), C.c_int(data.element_size()), ptr(seq_off), ptr(d_dummy), ptr(src_var),
+                                                 ptr(new_seq), c_i64(n_new), c_i64(nb), ptr(filled), st()))
                 alleles[name] = (filled, new_seq)
-            rc(alleles, n_new, new_off)
-            out.update(alleles)
+            rc({k: v for k, v in alleles.items() if k not in tok_dummy}, n_new, new_off)
+            out.update({k: (v[0] if k in tok_fixed else v) for k, v in alleles.items()})
             out["row_offsets"] = new_off
             return out
 

@@ -91,7 +91,7 @@ def supports(ds) -> str | None:
         return "output_length is not fixed"
     if ds.splice_rows is not None:
         return "spliced output"
-    if ds.sequence_type == "variants":
+    if ds.sequence_type in ("variants", "variant-windows"):
         return "the variants output is ragged by nature"
     if ds.var_filter is not None:
         return "var_filter needs per-batch keep masks"

@@ -217,3 +217,34 @@ class RaggedVariants:
                 raise ValueError(f"cannot squeeze axis {axis} with size {outer[axis]}")
             del outer[axis]
         return self.reshape(tuple(outer))
+
+
+def build_token_lut(alphabet, unknown_token: int):
+    """256-entry byte -> token table (reference `build_token_lut`, _flat_flanks.py:23-40): byte i of the alphabet maps to
+    token i, every other byte (N, padding outside the contig) to `unknown_token`; uint8 when every token fits, else int32."""
+    alphabet = alphabet.encode("ascii") if isinstance(alphabet, str) else bytes(alphabet)
+    max_token = max(len(alphabet) - 1, int(unknown_token))
+    dtype = np.uint8 if max_token <= 255 else np.int32
+    lut = np.full(256, unknown_token, dtype=dtype)
+    for i, b in enumerate(alphabet):
+        lut[b] = i
+    return lut, np.dtype(dtype)
+
+
+@dataclass(frozen=True)
+class VarWindowOpt:
+    """Options of `with_seqs("variant-windows")` (reference `VarWindowOpt`, _flat_variants.py:291-321): "window" emits the
+    flanked, tokenised window (ref: the reference read [start - L, end + L); alt: flank5 . alt . flank3), "allele" the bare
+    tokenised allele."""
+
+    flank_length: int
+    token_alphabet: Any
+    unknown_token: int
+    ref: str = "window"
+    alt: str = "window"
+
+    def __post_init__(self):
+        a = self.token_alphabet
+        object.__setattr__(self, "token_alphabet", a.encode("ascii") if isinstance(a, str) else bytes(a))
+        if self.ref not in ("window", "allele") or self.alt not in ("window", "allele"):
+            raise ValueError("VarWindowOpt.ref / .alt must be 'window' or 'allele'")

@@ -389,6 +389,11 @@ struct CompactScatter {  // mod.rs:128-133
         if (keep[j]) dst[pos[j]] = src[j];
     }
 };
+struct EmitExpand {  // np.repeat(values, np.diff(offsets)): the row's value for every variant of the row
+    const uint32_t *values;
+    uint32_t *out;
+    __device__ void operator()(int64_t row, int64_t, int64_t, int64_t e) const { out[e] = values[row]; }
+};
 struct TakeU32 {
     const uint32_t *t;
     const int32_t *v;
@@ -563,6 +568,17 @@ int gvl_dev_variant_windows(gvl_ctx *ctx, const gvl_sparse_tables *tab, const in
     if (kind == GVL_WINDOW_ALT)
         return seg_emit(EmitAltWindow<int32_t>{W, tab->alt_alleles, tab->alt_offsets, l, o}, win_offsets, n, total, 1, st);
     return for_each(EmitFlanks<int32_t>{W, l, o}, total, st);
+}
+
+// np.repeat(values, np.diff(offsets)) for 4-byte values: the contig of every gathered variant from the contig of its row
+// (_flat_variants.py:985-989)
+int gvl_dev_expand_rows_u32(gvl_ctx *ctx, const void *values, const int64_t *offsets, int64_t n_rows, int64_t total, void *out,
+                            gvl_stream stream) {
+    VARG(ctx && n_rows >= 0 && total >= 0, "gvl_dev_expand_rows_u32");
+    if (n_rows == 0 || total == 0) return GVL_OK;
+    VARG(values && offsets && out, "gvl_dev_expand_rows_u32");
+    GVL_CUDA(cudaSetDevice(ctx->device));
+    return seg_emit(EmitExpand{(const uint32_t *)values, (uint32_t *)out}, offsets, n_rows, total, 1, S(stream));
 }
 
 // table[v_idxs[i]] for a 4-byte table (start / ilen / info fields of the selected variants: `np.asarray(x)[v_idxs]`,

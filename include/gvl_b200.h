@@ -583,6 +583,11 @@ int gvl_dev_gather_rows(gvl_ctx *ctx, const int64_t *geno_offset_idx, int64_t n_
 /* table[v_idxs[i]] for a 4-byte table: start / ilen / info fields of the gathered variants (_flat_variants.py:948-953). */
 int gvl_dev_take_u32(gvl_ctx *ctx, const void *table, const int32_t *v_idxs, int64_t n, void *out, gvl_stream stream);
 
+/* np.repeat(values, np.diff(offsets)) for 4-byte values: e.g. the contig of every gathered variant from the contig of its
+ * row (_flat_variants.py:985-989), which gvl_dev_variant_windows takes as v_contigs. */
+int gvl_dev_expand_rows_u32(gvl_ctx *ctx, const void *values, const int64_t *offsets, int64_t n_rows, int64_t total, void *out,
+                            gvl_stream stream);
+
 /* gather_alleles, src/ffi/mod.rs:291-304 -> src/variants/mod.rs:52-78.  seq_offsets i64[n + 1].  With lut != NULL the
  * bytes are tokenised on the way out (windows.rs:9-22): out[e] = lut[byte], lut = 256 tokens of tok_bytes (1 or 4). */
 int gvl_dev_gather_alleles_offsets(gvl_ctx *ctx, const int32_t *v_idxs, int64_t n, const int64_t *allele_offsets,

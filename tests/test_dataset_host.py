@@ -57,8 +57,12 @@ def test_validation_like_reference():
         ds.with_len(104).with_settings(jitter=4)
     with pytest.raises(ValueError, match="not found"):
         ds.with_tracks(["missing"])
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError, match="window_opt"):
         ds.with_seqs("variant-windows")
+    with pytest.raises(ValueError, match="set together"):
+        ds.with_settings(token_alphabet="ACGT")
+    with pytest.raises(ValueError, match="token LUT"):
+        ds.with_settings(flank_length=4)
     assert ds.with_seqs("variants").sequence_type == "variants"
     with pytest.raises(NotImplementedError, match="AF"):
         ds.with_settings(min_af=0.1)  # haplotype output (_haps.py:695-698); allowed with with_seqs("variants")

@@ -304,3 +304,79 @@ def test_dataset_variants_vs_oracle(cuda_device, O):
     _check_variants(got, exp, off, (12, S, 1, None))
     with pytest.raises(ValueError, match="Missing variant fields"):
         dsv.with_settings(var_fields=["alt", "dosage"])
+
+
+@pytest.mark.parametrize("alphabet,unk", [("ACGT", 4), ("ACGT", 300)])
+def test_dataset_variant_windows_and_flank_tokens_vs_oracle(cuda_device, O, alphabet, unk):
+    """with_seqs("variant-windows", VarWindowOpt(...)) and with_settings(flank_length=...) against the oracle's
+    assemble_variant_buffers + fill_empty_* (get_variants_flat, _flat_variants.py:1006-1110); unk = 300 makes the tokens int32
+    (build_token_lut, _flat_flanks.py:23-40).  Two contigs, so the per-variant contig expansion matters."""
+    from genvarloader_b200 import DummyVariant, VarWindowOpt
+    from genvarloader_b200._dataset import Dataset
+    from genvarloader_b200._types import build_token_lut
+
+    rng = np.random.default_rng(unk)
+    contig_lens = [4000, 2500]
+    ref_off = np.concatenate([[0], np.cumsum(contig_lens)]).astype(np.int64)
+    reference = rng.choice(np.frombuffer(b"ACGTN", np.uint8), ref_off[-1])
+    n_var = 300
+    v_starts = np.sort(rng.integers(0, 2500, n_var)).astype(np.int32)
+    v_starts[:2], v_starts[-2:] = [0, 1], [2498, 2499]
+    ilens = rng.integers(-12, 13, n_var).astype(np.int32)
+    alt_off = np.concatenate([[0], np.cumsum(np.where(ilens > 0, ilens + 1, 1))]).astype(np.int64)
+    rfo = np.concatenate([[0], np.cumsum(np.where(ilens < 0, 1 - ilens, 1))]).astype(np.int64)
+    alt = rng.choice(np.frombuffer(b"ACGT", np.uint8), alt_off[-1])
+    rfa = rng.choice(np.frombuffer(b"ACGT", np.uint8), rfo[-1])
+    R, S, P = 6, 3, 2
+    regions = np.stack([rng.integers(0, 2, R), rng.integers(0, 2000, R), np.zeros(R, np.int64), np.where(rng.random(R) < 0.5, -1, 1)], 1)
+    regions[:, 2] = regions[:, 1] + 400
+    regions = regions.astype(np.int32)
+    glen = rng.integers(0, 9, R * S * P)
+    glen[rng.random(R * S * P) < 0.3] = 0
+    geno_off = np.concatenate([[0], np.cumsum(glen)]).astype(np.int64)
+    geno_v = np.concatenate([np.sort(rng.choice(n_var, k, replace=False)) for k in glen] + [np.zeros(0, np.int64)]).astype(np.int32)
+    ds = Dataset.from_arrays(cuda_device, reference, ref_off, v_starts, ilens, alt, alt_off, geno_v, geno_off, regions, S, P,
+                             ref_alleles=(rfa, rfo))
+    lut, tok_dt = build_token_lut(alphabet, unk)
+    assert tok_dt == (np.uint8 if unk < 256 else np.int32)
+    r, s = np.arange(R).repeat(S), np.tile(np.arange(S), R)
+    goi = ((r * S + s)[:, None] * P + np.arange(P)[None, :]).reshape(-1)
+    go = np.stack([geno_off[:-1], geno_off[1:]])
+    v, off = O.gather_rows(goi, go, geno_v)
+    v_contigs = np.repeat(np.repeat(regions[r, 0], P), np.diff(off)).astype(np.int32)
+    L = 5
+    dummy = DummyVariant(alt=b"NN", ref=b"N")
+    for ref_kind, alt_kind in (("window", "window"), ("allele", "window"), ("window", "allele"), ("allele", "allele")):
+        opt = VarWindowOpt(L, alphabet, unk, ref=ref_kind, alt=alt_kind)
+        for dv in (None, dummy):
+            got = ds.with_seqs("variant-windows", opt).with_settings(dummy_variant=dv if dv is not None else False)[:, :]
+            exp = O.assemble_variant_buffers(1, v, off, alt, alt_off, rfa, rfo, False, False, 1 if ref_kind == "window" else 2,
+                                             1 if alt_kind == "window" else 2, L, lut, v_contigs, v_starts, ilens, reference, ref_off,
+                                             ord("N"))
+            exp_off = off
+            assert sorted(got.fields) == sorted(["ilen", "start"] + list(exp))
+            for name, (data, so) in exp.items():
+                if dv is not None:
+                    base = len(dv.alt if name in ("alt", "alt_window") else dv.ref)
+                    wl = 2 * L + base if name.endswith("_window") else base
+                    data, exp_off, so = O.fill_empty_seq(data, off, so, np.full(wl, unk, tok_dt))
+                f = got[name]
+                eq(f"windows.{name}.data", 0, f.data.cpu().numpy(), data)
+                eq(f"windows.{name}.seq_offsets", 0, f.seq_offsets.cpu().numpy(), so)
+                eq(f"windows.{name}.var_offsets", 0, f.var_offsets.cpu().numpy(), exp_off)
+            st = v_starts[v]
+            if dv is not None:
+                st, _ = O.fill_empty_scalar(st, off, np.int32(dv.start))
+            eq("windows.start", 0, got["start"].data.cpu().numpy(), st)
+            assert got.shape == (R, S, P, None)
+    # variants + flank tokens ride-along (negative-strand alleles reverse-complemented, tokens reference-oriented)
+    fl = ds.with_seqs("variants").with_settings(token_alphabet=alphabet, unknown_token=unk, flank_length=L, dummy_variant=dummy)
+    got = fl[:, :]
+    exp = O.assemble_variant_buffers(0, v, off, alt, alt_off, None, None, False, True, 0, 0, L, lut, v_contigs, v_starts, ilens,
+                                     reference, ref_off, ord("N"))
+    tok, new_off = O.fill_empty_fixed(exp["flank_tokens"][0], off, 2 * L, tok_dt.type(unk))
+    eq("flank_tokens", 0, got["flank_tokens"].data.cpu().numpy(), tok.reshape(-1, 2 * L))
+    eq("flank_tokens.offsets", 0, got.offsets.cpu().numpy(), new_off)
+    a_data, a_vo, a_so = O.fill_empty_seq(exp["alt"][0], off, exp["alt"][1], np.frombuffer(b"NN", np.uint8))
+    to_rc = np.repeat(regions[r, 3] == -1, P)
+    eq("alt", 0, got["alt"].data.cpu().numpy(), O.rc_alleles(a_data, a_so, a_vo, to_rc))

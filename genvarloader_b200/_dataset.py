@@ -339,6 +339,10 @@ class Dataset:
                     f" The maximum output length is the minimum region length ({min_r_len}) + 2 * (max_jitter={self.max_jitter}).")
         elif self.output_length not in ("ragged", "variable"):
             raise ValueError(f"Output length must be 'ragged', 'variable' or a positive integer, got {self.output_length!r}")
+        if self.unphased_union and self.sequence_type in ("haplotypes", "annotated"):
+            raise ValueError("unphased_union is incompatible with 'haplotypes'/'annotated' output (a union of phased sequences is "
+                             "ill-defined). Use 'variant-windows' or 'variants', or clear the flag with "
+                             "with_settings(unphased_union=False).")  # _impl.py:769-779
         if (self.min_af is not None or self.max_af is not None) and self.sequence_type not in ("variants", "variant-windows"):
             raise NotImplementedError("Filtering by AF is not supported for haplotype output yet.")  # _haps.py:695-698
         if self.encoding != "bytes" and self.sequence_type not in ("haplotypes", "reference"):
@@ -436,8 +440,6 @@ class Dataset:
             kw["window_opt"] = window_opt
         elif window_opt is not None:
             raise ValueError("window_opt only applies to with_seqs('variant-windows')")
-        if kind in ("haplotypes", "annotated") and self.unphased_union:
-            raise ValueError("unphased_union is incompatible with 'haplotypes'/'annotated' output")  # _impl.py:769-779
         enc = self.encoding if kind in ("haplotypes", "reference") else "bytes"
         return self._evolve(sequence_type=kind, encoding=enc, **kw)
 

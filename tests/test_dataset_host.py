@@ -64,6 +64,9 @@ def test_validation_like_reference():
     with pytest.raises(ValueError, match="token LUT"):
         ds.with_settings(flank_length=4)
     assert ds.with_seqs("variants").sequence_type == "variants"
+    with pytest.raises(ValueError, match="unphased_union"):
+        ds.with_settings(unphased_union=True)  # haplotype output
+    assert ds.with_seqs("variants").with_settings(unphased_union=True).unphased_union
     with pytest.raises(NotImplementedError, match="AF"):
         ds.with_settings(min_af=0.1)  # haplotype output (_haps.py:695-698); allowed with with_seqs("variants")
     with pytest.raises(NotImplementedError):

@@ -89,14 +89,15 @@ class Dataset:
     def from_arrays(cls, device, reference, ref_offsets, v_starts, ilens, alt_alleles, alt_offsets, geno_v_idxs,
                     geno_offsets, regions, n_samples: int, ploidy: int, max_jitter: int = 0, tracks: dict | None = None,
                     track_kinds: dict | None = None, sample_names=None, rng=None, ref_alleles=None,
-                    variant_info: dict | None = None) -> "Dataset":
+                    variant_info: dict | None = None, dosages=None) -> "Dataset":
         """In-memory dataset (the GPU counterpart of `get_dummy_dataset`, python/genvarloader/_dummy.py).
         `tracks`: name -> (itv_starts, itv_ends, itv_values, itv_offsets); SAMPLE tracks have one interval slot
         per (region, sample), ANNOT tracks one per region (_reconstruct.py:233-236).  `ref_alleles` = (bytes, offsets) of
-        the REF strings and `variant_info` = {name: 4-byte column} feed the "variants" output (`var_fields`, AF filter)."""
+        the REF strings, `variant_info` = {name: numeric column, one value per variant} and `dosages` (float32, parallel to
+        `geno_v_idxs`) feed the "variants" output (`var_fields`, AF filter)."""
         eng = Engine(device, reference, ref_offsets, v_starts, ilens, alt_alleles, alt_offsets, geno_v_idxs, geno_offsets)
-        if ref_alleles is not None or variant_info:
-            eng.set_variant_fields(ref_alleles, variant_info)
+        if ref_alleles is not None or variant_info or dosages is not None:
+            eng.set_variant_fields(ref_alleles, variant_info, dosages)
         kinds = {}
         for name, t in (tracks or {}).items():
             eng.add_track(name, *t)
@@ -167,6 +168,8 @@ class Dataset:
             eng = Engine(device, ref.reference, ref.offsets, np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.uint8),
                          np.zeros(1, np.int64), np.zeros(0, np.int32), np.zeros(n_regions * len(samples) * ploidy + 1, np.int64),
                          pad_char=ref.pad_char)
+        if has_geno and (a.get("ref_alleles") is not None or a.get("variant_info")):
+            eng.set_variant_fields(a.get("ref_alleles"), a.get("variant_info"))  # "variants" output: REF strings, INFO columns
         for name, t in a["tracks"].items():
             eng.add_track(name, *t)
         ds = cls(engine=eng, full_regions=a["full_regions"], sample_names=tuple(samples), ploidy=ploidy,
@@ -201,7 +204,8 @@ class Dataset:
     def available_var_fields(self) -> list:
         """Reference: `Haps.available_var_fields`, _haps.py:313-319."""
         eng = self.engine
-        return ["alt", "ilen", "start"] + (["ref"] if eng.ref_alleles is not None else []) + sorted(eng.var_info)
+        return (["alt", "ilen", "start"] + (["ref"] if eng.ref_alleles is not None else [])
+                + (["dosage"] if eng.dosages is not None else []) + sorted(eng.var_info))
 
     @property
     def available_tracks(self) -> list:

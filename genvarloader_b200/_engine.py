@@ -100,7 +100,10 @@ class Engine:
         self.tracks: dict[str, tuple] = {}
         self.svar2 = None  # resident svar2 two-channel source (set_svar2)
         self.ref_alleles = None  # (bytes, offsets) of the REF allele strings (set_variant_fields)
-        self.var_info: dict[str, torch.Tensor] = {}
+        self.var_info: dict[str, torch.Tensor] = {}   # 4-byte info columns on the device (output fields)
+        self.var_info_host: dict[str, np.ndarray] = {}  # every info column (the AF filter is evaluated per variant on the host)
+        self._af_tables: dict = {}
+        self.dosages = None
         self._n_work = 0
         self._fixed = -1
 
@@ -182,17 +185,43 @@ class Engine:
         return keep, keep_offsets
 
     # ------------------------------------------------------------------ `variants` output (csrc/gvl_variants.cu)
-    def set_variant_fields(self, ref_alleles=None, info: dict | None = None) -> None:
-        """Optional per-variant columns of the `variants` output: REF allele strings `(bytes, offsets)` and 4-byte info
-        columns (e.g. "AF" float32 for `min_af` / `max_af`) -- `_Variants.ref` / `.info`, _haps.py:139-157."""
+    def set_variant_fields(self, ref_alleles=None, info: dict | None = None, dosages=None) -> None:
+        """Optional columns of the `variants` output: REF allele strings `(bytes, offsets)`, per-variant info columns
+        (`_Variants.ref` / `.info`, _haps.py:139-157: any numeric dtype can drive `min_af` / `max_af`; 4-byte columns can
+        also be requested as output fields) and per-call dosages (float32, parallel to `geno_v_idxs`; `Haps.dosages`)."""
         with torch.cuda.device(self.device):
             if ref_alleles is not None:
                 self.ref_alleles = (_dev(ref_alleles[0], np.uint8, self.device, pad=16), _dev(ref_alleles[1], np.int64, self.device))
             for k, v in (info or {}).items():
                 v = np.ascontiguousarray(v)
-                if v.dtype.itemsize != 4:
-                    raise TypeError(f"info column {k!r}: 4-byte values expected (int32 / float32), got {v.dtype}")
-                self.var_info[k] = _dev(v, v.dtype, self.device)
+                if v.shape != (int(self.v_starts.numel()),):
+                    raise ValueError(f"info column {k!r}: one value per variant expected, got shape {v.shape}")
+                self.var_info_host[k] = v
+                if v.dtype.itemsize == 4 and v.dtype.kind in "if":
+                    self.var_info[k] = _dev(v, v.dtype, self.device)
+                self._af_tables.clear()
+            if dosages is not None:
+                dz = np.ascontiguousarray(dosages, np.float32)
+                if dz.size != int(self.geno_v_idxs.numel()) - 4:  # (geno_v_idxs carries 4 spare elements)
+                    raise ValueError("dosages: one float32 per sparse genotype entry expected")
+                self.dosages = _dev(dz, np.float32, self.device, pad=4)
+
+    def _af_keep_table(self, min_af, max_af) -> torch.Tensor:
+        """Per-VARIANT keep flags of the AF filter (int32 0 / 1), evaluated once per (min_af, max_af) on the host in the
+        column's own dtype: `(af >= min_af)[v_idxs]` is what `af[v_idxs] >= min_af` computes (_flat_variants.py:899-909)."""
+        key = (min_af, max_af)
+        if key not in self._af_tables:
+            if "AF" not in self.var_info_host:
+                raise ValueError("min_af / max_af need the variants' AF column (variant_info={'AF': ...})")
+            af = self.var_info_host["AF"]
+            keep = np.ones(af.shape, np.bool_)
+            if min_af is not None:
+                keep &= af >= min_af
+            if max_af is not None:
+                keep &= af <= max_af
+            with torch.cuda.device(self.device):
+                self._af_tables[key] = _dev(keep.astype(np.int32), np.int32, self.device)
+        return self._af_tables[key]
 
     def _scan_total(self, offsets: torch.Tensor) -> int:
         return int(offsets[-1].item())  # the one synchronisation of a ragged output
@@ -231,21 +260,24 @@ class Engine:
                 check(lib.gvl_dev_take_u32(h, ptr(table), ptr(v_idxs), c_i64(n), ptr(out), st()))
                 return out
 
+            dosage = None
+            if "dosage" in fields:  # parallel to the genotypes: same offset ranges (_flat_variants.py:911-921)
+                if self.dosages is None:
+                    raise ValueError("Missing variant fields: ['dosage']")
+                dosage = torch.empty(n, dtype=torch.float32, device=dev)
+                check(lib.gvl_dev_gather_rows(h, ptr(goi), c_i64(n_rows), ptr(self.geno_starts), ptr(self.dosages), ptr(row_off), c_i64(n),
+                                              ptr(dosage), st()))
             if min_af is not None or max_af is not None:  # _flat_variants.py:899-923
-                if "AF" not in self.var_info:
-                    raise ValueError("min_af / max_af need the variants' AF column (Engine.set_variant_fields(info={'AF': ...}))")
-                af = take(self.var_info["AF"])
-                keep = torch.ones(n, dtype=torch.bool, device=dev)
-                if min_af is not None:
-                    keep &= af >= min_af
-                if max_af is not None:
-                    keep &= af <= max_af
-                keep = keep.view(torch.uint8)
+                keep = (take(self._af_keep_table(min_af, max_af)) != 0).view(torch.uint8)
                 pos, new_off = i64(n + 1), i64(n_rows + 1)
                 check(lib.gvl_dev_compact_keep_offsets(h, ptr(keep), c_i64(n), ptr(row_off), c_i64(n_rows), ptr(pos), ptr(new_off), st()))
                 n_keep = self._scan_total(pos)
                 kept = torch.empty(n_keep, dtype=torch.int32, device=dev)
                 check(lib.gvl_dev_compact_keep(h, ptr(v_idxs), ptr(keep), c_i64(n), ptr(pos), ptr(kept), st()))
+                if dosage is not None:  # compacted with the SAME mask (:923-926)
+                    kd = torch.empty(n_keep, dtype=torch.float32, device=dev)
+                    check(lib.gvl_dev_compact_keep(h, ptr(dosage), ptr(keep), c_i64(n), ptr(pos), ptr(kd), st()))
+                    dosage = kd
                 v_idxs, row_off, n = kept, new_off, n_keep
             if fold > 1:
                 row_off = row_off[::fold].contiguous()
@@ -327,6 +359,8 @@ class Engine:
                     check(lib.gvl_dev_gather_alleles(h, ptr(v_idxs), c_i64(n), ptr(ab), ptr(ao), ptr(seq_off), c_i64(nb), c_vp(0),
                                                      C.c_int(1), ptr(data), st()))
                     alleles[name] = (data, seq_off)
+                elif name == "dosage":
+                    out[name] = dosage
                 elif name == "start":
                     out[name] = take(self.v_starts)
                 elif name == "ilen":

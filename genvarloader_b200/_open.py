@@ -260,6 +260,15 @@ def read_dataset_arrays(path, reference=None, svar=None) -> dict:
         else:  # ALT length - REF length (_haps.py:127-134)
             _, ref_off = _utf8_to_bytes_offsets(vt.column("REF"))
             ilen = (np.diff(alt_off) - np.diff(ref_off)).astype(np.int32)
+        # columns of the "variants" output (`_Variants.from_table`, _haps.py:139-157): REF strings, numeric INFO columns
+        import pyarrow.types as pat
+
+        if "REF" in vt.column_names:
+            out["ref_alleles"] = _utf8_to_bytes_offsets(vt.column("REF"))
+        out["variant_info"] = {
+            n: vt.column(n).to_numpy(zero_copy_only=False) for n in vt.column_names
+            if n not in ("POS", "ILEN") and (pat.is_integer(vt.schema.field(n).type) or pat.is_floating(vt.schema.field(n).type))
+            and vt.column(n).null_count == 0}
         n_slots = n_regions * len(samples) * int(ploidy)
         if linked:
             _verify_svar_fingerprint(svar_path, meta.get("svar_link"), len(pos))

@@ -36,6 +36,19 @@ def test_open_matches_in_memory_dataset(cuda_device, tmp_path):
     re_ = mem.with_seqs("haplotypes")[order[[0, 7, 3]], [2, 0, 1]]
     assert (rg[0].data == re_[0].data).all() and (rg[0].offsets == re_[0].offsets).all()
     assert (rg[1].data.view(dtype=rg[1].data.dtype) == re_[1].data).all()
+    # the "variants" output of the opened dataset; its AF column (float64 on disk) drives the AF filter
+    af = np.linspace(0, 1, d.v_starts.size)  # what tests/_gvl_disk.py writes
+    memv = Dataset.from_arrays(cuda_device, d.reference, d.ref_offsets, d.v_starts, d.ilens, d.alt_alleles, d.alt_offsets,
+                               d.geno_v_idxs, d.geno_offsets, d.regions, d.n_samples, d.ploidy, variant_info={"AF": af})
+    assert "AF" not in memv.available_var_fields and "AF" not in dsk.available_var_fields  # (8-byte column: filter only)
+    for kw in (dict(), dict(min_af=0.3, max_af=0.8)):
+        gv = dsk.with_tracks(False).with_seqs("variants").with_settings(**kw)[:5, :]
+        ev = memv.with_seqs("variants").with_settings(**kw)[order[:5], :]
+        assert gv.shape == ev.shape == (5, 3, d.ploidy, None)
+        assert (gv.offsets == ev.offsets).all() and (gv["start"].data == ev["start"].data).all()
+        assert (gv["alt"].data == ev["alt"].data).all() and (gv["alt"].seq_offsets == ev["alt"].seq_offsets).all()
+        assert (gv["ilen"].data == ev["ilen"].data).all()
+    assert int(gv.offsets[-1]) < int(dsk.with_tracks(False).with_seqs("variants")[:5, :].offsets[-1])  # the filter removed variants
     # subset by input-order region indices
     sub = dsk.subset_to(regions=[2, 5], samples=["c"]).with_len(L).with_tracks(False)
     assert (sub[:, :] == mem.with_len(L).with_tracks(False)[order[[2, 5]], [2]].reshape(sub[:, :].shape)).all()

@@ -205,18 +205,22 @@ def test_assemble_variant_buffers_vs_oracle(V, O, tok, flank):
 
 
 # ---------------------------------------------------------------- Dataset.with_seqs("variants")
-def _expected_variants(O, d, ds_idx, to_rc_q, fields, dummy, ref_alleles=None, af=None, min_af=None, max_af=None, fold=False):
+def _expected_variants(O, d, ds_idx, to_rc_q, fields, dummy, ref_alleles=None, af=None, min_af=None, max_af=None, fold=False,
+                       dosages=None):
     """get_variants_flat (_flat_variants.py:869-1112) + the strand pass of _query.py:485-529, from oracle primitives."""
     p = d.ploidy
     goi = (ds_idx[:, None] * p + np.arange(p)[None, :]).reshape(-1)
     go = np.stack([d.geno_offsets[:-1], d.geno_offsets[1:]]) if np.asarray(d.geno_offsets).ndim == 1 else d.geno_offsets
     v, off = O.gather_rows(goi, go, d.geno_v_idxs)
+    dos = O.gather_rows(goi, go, dosages)[0] if dosages is not None else None
     if min_af is not None or max_af is not None:
         keep = np.ones(len(v), bool)
         if min_af is not None:
             keep &= af[v] >= np.float32(min_af)
         if max_af is not None:
             keep &= af[v] <= np.float32(max_af)
+        if dos is not None:
+            dos, _ = O.compact_keep(dos, off, keep)
         v, off = O.compact_keep(v, off, keep)
     to_rc = np.repeat(to_rc_q, p)
     if fold:
@@ -233,7 +237,7 @@ def _expected_variants(O, d, ds_idx, to_rc_q, fields, dummy, ref_alleles=None, a
                 new_off = vo
             out[name] = (O.rc_alleles(data, so, vo, to_rc), so)
         else:
-            col = {"start": d.v_starts, "ilen": d.ilens, "AF": af}[name][v]
+            col = dos if name == "dosage" else {"start": d.v_starts, "ilen": d.ilens, "AF": af}[name][v]
             if dummy is not None:
                 col, new_off = O.fill_empty_scalar(col, off, dummy.scalar_for(name, col.dtype))
             out[name] = col
@@ -267,8 +271,8 @@ def test_dataset_variants_vs_oracle(cuda_device, O):
     af = rng.random(n_var).astype(np.float32)
     ds = Dataset.from_arrays(cuda_device, d.reference, d.ref_offsets, d.v_starts, d.ilens, d.alt_alleles, d.alt_offsets,
                              d.geno_v_idxs, d.geno_offsets, d.regions, d.n_samples, d.ploidy, ref_alleles=(rfa, rfo),
-                             variant_info={"AF": af})
-    assert ds.available_var_fields == ["alt", "ilen", "start", "ref", "AF"]
+                             variant_info={"AF": af}, dosages=(dz := rng.random(len(d.geno_v_idxs)).astype(np.float32)))
+    assert ds.available_var_fields == ["alt", "ilen", "start", "ref", "dosage", "AF"]
     S = d.n_samples
     dsv = ds.with_seqs("variants")
     r, s = np.arange(12).repeat(S), np.tile(np.arange(S), 12)
@@ -284,26 +288,27 @@ def test_dataset_variants_vs_oracle(cuda_device, O):
     assert got.alt.to_list()[0] == [bytes(exp["alt"][0][exp["alt"][1][a]:exp["alt"][1][a + 1]]) for a in range(off[0], off[1])]
 
     # every field + dummy variant + rc_neg off
-    dummy = DummyVariant(start=-5, ilen=9, alt=b"AC", ref=b"G", info={"AF": 0.25})
-    full = dsv.with_settings(var_fields=["alt", "start", "ref", "ilen", "AF"], dummy_variant=dummy)
+    dummy = DummyVariant(start=-5, ilen=9, alt=b"AC", ref=b"G", dosage=0.5, info={"AF": 0.25})
+    every = ("alt", "start", "ref", "ilen", "dosage", "AF")
+    full = dsv.with_settings(var_fields=list(every), dummy_variant=dummy)
     sel_r, sel_s = np.array([0, 3, 3, 11, 7]), np.array([5, 0, 1, 2, 2])
     got = full[sel_r, sel_s]
-    exp, off = _expected_variants(O, d, sel_r * S + sel_s, d.regions[sel_r, 3] == -1, ("alt", "start", "ref", "ilen", "AF"), dummy,
-                                  (rfa, rfo), af)
+    exp, off = _expected_variants(O, d, sel_r * S + sel_s, d.regions[sel_r, 3] == -1, every, dummy, (rfa, rfo), af, dosages=dz)
     assert (np.diff(off) >= 1).all()
     _check_variants(got, exp, off, (5, d.ploidy, None))
     got = full.with_settings(rc_neg=False)[sel_r, sel_s]
-    exp, off = _expected_variants(O, d, sel_r * S + sel_s, np.zeros(5, bool), ("alt", "start", "ref", "ilen", "AF"), dummy,
-                                  (rfa, rfo), af)
+    exp, off = _expected_variants(O, d, sel_r * S + sel_s, np.zeros(5, bool), every, dummy, (rfa, rfo), af, dosages=dz)
     _check_variants(got, exp, off, (5, d.ploidy, None))
 
     # AF filter + unphased union
-    flt = dsv.with_settings(min_af=0.2, max_af=0.9, unphased_union=True, dummy_variant=DummyVariant())
+    flt = dsv.with_settings(min_af=0.2, max_af=0.9, unphased_union=True, dummy_variant=DummyVariant(),
+                            var_fields=["alt", "ilen", "start", "dosage"])
     got = flt[:, :]
-    exp, off = _expected_variants(O, d, ds_idx, to_rc_q, ("alt", "ilen", "start"), DummyVariant(), None, af, 0.2, 0.9, fold=True)
+    exp, off = _expected_variants(O, d, ds_idx, to_rc_q, ("alt", "ilen", "start", "dosage"), DummyVariant(), None, af, 0.2, 0.9,
+                                  fold=True, dosages=dz)
     _check_variants(got, exp, off, (12, S, 1, None))
     with pytest.raises(ValueError, match="Missing variant fields"):
-        dsv.with_settings(var_fields=["alt", "dosage"])
+        dsv.with_settings(var_fields=["alt", "QUAL"])
 
 
 @pytest.mark.parametrize("alphabet,unk", [("ACGT", 4), ("ACGT", 300)])

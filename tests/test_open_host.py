@@ -28,6 +28,8 @@ def test_read_dataset_arrays_roundtrip(disk):
     assert (a["region_map"] == order).all()
     assert (a["v_starts"] == d.v_starts).all() and (a["ilens"] == d.ilens).all()  # 1-based POS from version 0.18.0
     assert (a["alt_alleles"] == d.alt_alleles).all() and (a["alt_offsets"] == d.alt_offsets).all()
+    assert list(a["variant_info"]) == ["AF"] and (a["variant_info"]["AF"] == np.linspace(0, 1, d.v_starts.size)).all()
+    assert "ref_alleles" not in a  # (this table has no REF column; the .svar store's index.arrow has one)
     go = np.asarray(d.geno_offsets)
     assert a["geno_offsets"].size == go.shape[1] + 1
     for k in (0, 5, go.shape[1] - 1):
@@ -78,6 +80,9 @@ def test_svar_linked_dataset(disk, tmp_path):
     a = read_dataset_arrays(tmp_path / "ds")
     assert (a["v_starts"] == d.v_starts).all() and (a["ilens"] == d.ilens).all()
     assert (a["alt_alleles"] == d.alt_alleles).all() and (a["alt_offsets"] == d.alt_offsets).all()
+    assert a["variant_info"] == {}  # the store's index.arrow: POS, REF, ALT[, ILEN]
+    rb, ro = a["ref_alleles"]
+    assert (np.diff(ro) == np.diff(d.alt_offsets) - d.ilens).all() and (rb == ord("N")).all()  # len(ALT) - len(REF) = ILEN
     go = np.asarray(d.geno_offsets)
     assert a["geno_offsets"].shape == go.shape and (np.asarray(a["geno_offsets"]) == go).all()
     assert (np.asarray(a["geno_v_idxs"]) == d.geno_v_idxs).all() and a["svar_path"] == (tmp_path / "cohort.svar").resolve()

@@ -822,7 +822,7 @@ class Dataset:
         oo = total = diffs = None
         if self.sequence_type in ("variants", "variant-windows"):
             # Haps._get_variants -> get_variants_flat (_haps.py:602-609, _flat_variants.py:869-1112), on the device
-            results.append(self._get_variants(t_goi, t_rc, b, regions))
+            results.append(self._get_variants(t_goi, t_rc, b, regions, max_rec))
             want_seqs = False
         if want_seqs:
             out_len = int(self.output_length) if fixed else -1
@@ -885,7 +885,7 @@ class Dataset:
                 results.append(Ragged(out, offsets, (b, t, None)))
         return tuple(results)
 
-    def _get_variants(self, t_goi, t_rc, b: int, regions) -> RaggedVariants:
+    def _get_variants(self, t_goi, t_rc, b: int, regions, n_variants: int) -> RaggedVariants:
         p, eng = self.ploidy, self.engine
         fold = p if self.unphased_union else 1
         windows = self.sequence_type == "variant-windows"
@@ -900,7 +900,9 @@ class Dataset:
             tokens = dict(lut=lut, unk=self.unknown_token, L=self.flank_length, flank=True)
         if tokens is not None:  # contig of every (b*p) row (_flat_variants.py:985-989)
             row_contigs = torch.from_numpy(np.repeat(regions[:, 0].astype(np.int32), p)).to(eng.device)
-        g = eng.gather_variants(t_goi, t_rc, self.var_fields, self.dummy_variant, self.min_af, self.max_af, fold, tokens, row_contigs)
+        # (n_variants = sum of the rows' genotype slice lengths, known from the host copy of the offsets: no sync for it)
+        g = eng.gather_variants(t_goi, t_rc, self.var_fields, self.dummy_variant, self.min_af, self.max_af, fold, tokens, row_contigs,
+                                n_hint=n_variants)
         shape = (b, 1 if self.unphased_union else p, None)
         off = g["row_offsets"]
         fields = {}

@@ -227,7 +227,7 @@ class Engine:
         return int(offsets[-1].item())  # the one synchronisation of a ragged output
 
     def gather_variants(self, geno_offset_idx: torch.Tensor, to_rc_row, fields, dummy=None, min_af=None, max_af=None,
-                        fold: int = 1, tokens: dict | None = None, row_contigs=None) -> dict:
+                        fold: int = 1, tokens: dict | None = None, row_contigs=None, n_hint: int | None = None) -> dict:
         """The tail of `get_variants_flat` (python/genvarloader/_dataset/_flat_variants.py:869-1112) on the device: per
         (b*p) row the variant indices of its genotype slice (gather_rows, src/variants/mod.rs:6-49), optional AF
         compaction (:112-153), positions / indel lengths / info columns (`table[v_idxs]`), ALT / REF allele strings
@@ -238,7 +238,8 @@ class Engine:
         "alt": likewise, "flank": bool} adds the token buffers of `assemble_variant_buffers` (src/variants/windows.rs:162-296):
         `flank_tokens` for the variants tail, `ref_window` / `alt_window` / tokenised `ref` / `alt` for the windows tail
         (then `alt` / `ref` in `fields` are skipped and nothing is reverse-complemented: windows are reference-oriented);
-        `row_contigs`: device i32, contig of every (b*p) row.
+        `row_contigs`: device i32, contig of every (b*p) row.  `n_hint`: the number of gathered variants when the caller
+        already knows it (the host holds the genotype offsets: `max_records`), which saves the first synchronisation.
         Returns {"row_offsets": i64, "v_idxs": i32, name: tensor | (data, seq_offsets)}."""
         if self.svar2 is not None:
             raise NotImplementedError("`variants` output is built for the SVAR1 genotype CSR; the svar2 source decodes variants "
@@ -250,10 +251,13 @@ class Engine:
         with torch.cuda.device(dev):
             row_off = i64(n_rows + 1)
             check(lib.gvl_dev_gather_rows_offsets(h, ptr(goi), c_i64(n_rows), ptr(self.geno_starts), ptr(self.geno_stops), ptr(row_off), st()))
-            n = self._scan_total(row_off)
+            n = int(n_hint) if n_hint is not None else self._scan_total(row_off)
+            filtered = min_af is not None or max_af is not None
             v_idxs = torch.empty(n, dtype=torch.int32, device=dev)
-            check(lib.gvl_dev_gather_rows(h, ptr(goi), c_i64(n_rows), ptr(self.geno_starts), ptr(self.geno_v_idxs), ptr(row_off), c_i64(n),
-                                          ptr(v_idxs), st()))
+            # positions and indel lengths ride along with the row gather (they are re-taken after an AF compaction)
+            pre = {k: torch.empty(n, dtype=torch.int32, device=dev) for k in ("start", "ilen") if k in fields and not filtered}
+            check(lib.gvl_dev_gather_variant_rows(h, C.byref(self.tab), ptr(goi), c_i64(n_rows), ptr(row_off), c_i64(n), ptr(v_idxs),
+                                                  ptr(pre.get("start")), ptr(pre.get("ilen")), st()))
 
             def take(table: torch.Tensor) -> torch.Tensor:
                 out = torch.empty(n, dtype=table.dtype, device=dev)
@@ -362,9 +366,9 @@ class Engine:
                 elif name == "dosage":
                     out[name] = dosage
                 elif name == "start":
-                    out[name] = take(self.v_starts)
+                    out[name] = pre[name] if name in pre else take(self.v_starts)
                 elif name == "ilen":
-                    out[name] = take(self.ilens)
+                    out[name] = pre[name] if name in pre else take(self.ilens)
                 elif name in self.var_info:
                     out[name] = take(self.var_info[name])
                 else:

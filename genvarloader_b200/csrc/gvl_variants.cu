@@ -269,6 +269,17 @@ struct EmitRows {  // :19-27
     uint32_t *out;
     __device__ void operator()(int64_t s, int64_t k, int64_t, int64_t e) const { out[e] = __ldg(data + o_starts[goi[s]] + k); }
 };
+struct EmitVariantRows {  // EmitRows + the `table[v_idxs]` takes of start / ilen in the same pass (_flat_variants.py:948-953)
+    const int64_t *goi, *o_starts;
+    const int32_t *geno_v_idxs, *v_starts, *ilens;
+    int32_t *v_out, *start_out, *ilen_out;
+    __device__ void operator()(int64_t s, int64_t k, int64_t, int64_t e) const {
+        const int32_t v = __ldg(geno_v_idxs + o_starts[goi[s]] + k);
+        v_out[e] = v;
+        if (start_out) start_out[e] = __ldg(v_starts + v);
+        if (ilen_out) ilen_out[e] = __ldg(ilens + v);
+    }
+};
 template <typename Tok, bool LUT>
 struct EmitAlleles {  // :64-76 (+ windows.rs:9-22 tokenize)
     const int32_t *v;
@@ -426,6 +437,20 @@ int gvl_dev_gather_rows(gvl_ctx *ctx, const int64_t *geno_offset_idx, int64_t n_
     GVL_CUDA(cudaSetDevice(ctx->device));
     return seg_emit(EmitRows{geno_offset_idx, o_starts, (const uint32_t *)data, (uint32_t *)out}, out_offsets, n_rows, total, 1,
                     S(stream));
+}
+
+int gvl_dev_gather_variant_rows(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int64_t *geno_offset_idx, int64_t n_rows,
+                                const int64_t *out_offsets, int64_t total, int32_t *v_idxs, int32_t *starts, int32_t *ilens,
+                                gvl_stream stream) {
+    VARG(ctx && tab && n_rows >= 0 && total >= 0, "gvl_dev_gather_variant_rows");
+    if (n_rows == 0 || total == 0) return GVL_OK;
+    VARG(geno_offset_idx && out_offsets && v_idxs && tab->geno_starts && tab->geno_v_idxs && (!starts || tab->v_starts) &&
+             (!ilens || tab->ilens),
+         "gvl_dev_gather_variant_rows");
+    GVL_CUDA(cudaSetDevice(ctx->device));
+    return seg_emit(EmitVariantRows{geno_offset_idx, tab->geno_starts, tab->geno_v_idxs, tab->v_starts, tab->ilens, v_idxs, starts,
+                                    ilens},
+                    out_offsets, n_rows, total, 1, S(stream));
 }
 
 int gvl_dev_gather_alleles_offsets(gvl_ctx *ctx, const int32_t *v_idxs, int64_t n, const int64_t *allele_offsets,

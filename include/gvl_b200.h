@@ -580,6 +580,12 @@ int gvl_dev_gather_rows_offsets(gvl_ctx *ctx, const int64_t *geno_offset_idx, in
                                 const int64_t *o_stops, int64_t *out_offsets, gvl_stream stream);
 int gvl_dev_gather_rows(gvl_ctx *ctx, const int64_t *geno_offset_idx, int64_t n_rows, const int64_t *o_starts, const void *data,
                         const int64_t *out_offsets, int64_t total, void *out, gvl_stream stream);
+/* gvl_dev_gather_rows over the genotype CSR of `tab` with the positions and indel lengths of the gathered variants taken in
+ * the same pass: v_idxs[e] = geno_v_idxs[...], starts[e] = v_starts[v_idxs[e]], ilens[e] = ilens[v_idxs[e]] (starts / ilens
+ * may be NULL).  One launch for the three fields every `variants` read asks for. */
+int gvl_dev_gather_variant_rows(gvl_ctx *ctx, const gvl_sparse_tables *tab, const int64_t *geno_offset_idx, int64_t n_rows,
+                                const int64_t *out_offsets, int64_t total, int32_t *v_idxs, int32_t *starts, int32_t *ilens,
+                                gvl_stream stream);
 /* table[v_idxs[i]] for a 4-byte table: start / ilen / info fields of the gathered variants (_flat_variants.py:948-953). */
 int gvl_dev_take_u32(gvl_ctx *ctx, const void *table, const int32_t *v_idxs, int64_t n, void *out, gvl_stream stream);
 

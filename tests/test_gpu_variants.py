@@ -90,6 +90,22 @@ def test_assemble_variant_buffers_golden(V):
         _eq_bufs(f"assemble#{ci}", V.assemble_variant_buffers(*inputs), gold)
 
 
+def test_pyref_twins(V):
+    """Vectors produced by executing the reference's own numpy twins of these cores (tests/golden/make_pyref_variants_golden.py:
+    bigger, more ragged cases than the frozen goldens), through the C ABI."""
+    from tests.test_oracle_variants import alt_window_args
+
+    def windows(rw, rw_off, a_data, a_off, L):
+        out = V.assemble_variant_buffers(*alt_window_args(rw, rw_off, a_data, a_off, L))
+        eq("ref_window", 0, out["ref_window"][0], rw)
+        eq("ref_window", 1, out["ref_window"][1], rw_off)
+        return out["alt_window"]
+
+    for name, fn in (("gather_rows", V.gather_rows), ("compact_keep", V.compact_keep), ("fill_empty_scalar", V.fill_empty_scalar),
+                     ("fill_empty_fixed", V.fill_empty_fixed), ("fill_empty_seq", V.fill_empty_seq), ("alt_windows", windows)):
+        _replay(f"pyref_{name}", fn, 40)
+
+
 # ---------------------------------------------------------------- seeded cases vs the oracle
 def _ragged_offsets(rng, n, max_len, empty_frac=0.3):
     ln = rng.integers(1, max_len + 1, n)
